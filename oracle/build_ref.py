@@ -1,0 +1,129 @@
+#!/usr/bin/env python3
+"""Build recipe for oracle/_ref/: the reference's OWN serial CPU implementation of the hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Nothing here is copied from the reference:
+the reference's generator (/root/reference/src/pairs) is *executed* on the reference's own
+example scripts (/root/reference/examples/md.py, dem.py -- optionally with a few scalar
+parameters substituted in a scratch copy, e.g. lattice size or number of timesteps) and the
+C++ it prints is compiled, where it lies in oracle/_ref/gen/, against the reference runtime
+sources where they lie in /root/reference/runtime, plus the single-rank MPI stand-in
+oracle/mpi_stub/mpi.h (the image has no MPI).  Outputs go only into oracle/_ref/ (git-ignored,
+NOT gpurun-ignored, so the built .so / binaries travel to the GPU box).
+
+Variants (name -> substitutions applied to examples/md.py in a scratch copy):
+  md        stock examples/md.py (config C1: 32^3 cells = 131072 atoms, 200 steps)
+  md_t1     nx=ny=nz=8 (2048 atoms), 100 steps, thermo every step   -> per-step parity dumps
+  md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
+  md_bench  nx=ny=nz=63 (1000188 atoms), 18 steps (= 19 loop iterations, ONE reneighbour, the
+            steady-state 1-in-20 ratio) -> bounded CPU-baseline sample for bench.py
+
+Usage: python oracle/build_ref.py [variant ...]    (default: all; no-op if /root/reference is absent)
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("PAIRS_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+GEN = os.path.join(OUT, "gen")
+
+RUNTIME_SRCS = ["runtime/pairs.cpp", "runtime/domain/regular_6d_stencil.cpp", "runtime/devices/dummy.cpp"]
+# -ffp-contract=off: no FMA contraction, so per-operation IEEE results are comparable with a
+# CUDA build compiled with --fmad=false.  No -ffast-math (Makefile:18 uses it for the GPU target only).
+CXXFLAGS = ["-O3", "-ffp-contract=off", "-w"]
+
+
+def _sub(text, pattern, repl, count=1):
+    new, n = re.subn(pattern, repl, text, count=count, flags=re.M)
+    if n == 0:
+        raise RuntimeError(f"pattern not found in reference example: {pattern}")
+    return new
+
+
+def md_variant(nx, steps, thermo, reneigh, pcap=None):
+    def patch(text):
+        text = _sub(text, r"^nx = \d+", f"nx = {nx}")
+        text = _sub(text, r"^ny = \d+", f"ny = {nx}")
+        text = _sub(text, r"^nz = \d+", f"nz = {nx}")
+        extra = f", particle_capacity={pcap}" if pcap else ""
+        text = _sub(text, r"timesteps=\d+", f"timesteps={steps}{extra}")
+        text = _sub(text, r"compute_thermo\(\d+\)", f"compute_thermo({thermo})")
+        text = _sub(text, r"reneighbor_every\(\d+\)", f"reneighbor_every({reneigh})")
+        return text
+    return patch
+
+
+VARIANTS = {
+    # name: (example script, patch function or None, harness defines, also build executable)
+    "md": ("examples/md.py", None, ["-DREF_IS_MD"], True),
+    "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
+    "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
+    "md_bench": ("examples/md.py", md_variant(63, 18, 100, 20, pcap=1400000), ["-DREF_IS_MD"], True),
+}
+
+
+def run(cmd, **kw):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, **kw)
+    if r.returncode != 0:
+        raise RuntimeError(f"command failed: {' '.join(cmd)}\n{r.stdout[-4000:]}")
+    return r.stdout
+
+
+def newer(target, deps):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+
+
+def build_variant(name):
+    script, patch, defines, want_exe = VARIANTS[name]
+    gdir = os.path.join(GEN, name)
+    os.makedirs(gdir, exist_ok=True)
+    src_script = os.path.join(REF, script)
+    base = os.path.splitext(os.path.basename(script))[0]          # md / dem -> generated file name
+    gen_cpp = os.path.join(gdir, f"{base}.cpp")
+    lib = os.path.join(OUT, f"libref_{name}.so")
+    exe = os.path.join(OUT, f"{name}_cpu")
+    deps = [src_script, os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "mpi_stub", "mpi.h"), __file__]
+    if newer(lib, deps) and (not want_exe or newer(exe, deps)):
+        return "up to date"
+
+    # 1. run the reference generator on (a scratch copy of) the reference's example script
+    text = open(src_script).read()
+    if patch is not None:
+        text = patch(text)
+    scratch_script = os.path.join(gdir, f"{base}_{name}_input.py")
+    with open(scratch_script, "w") as f:
+        f.write(text)
+    env = dict(os.environ, PYTHONPATH=os.path.join(REF, "src"))
+    run([sys.executable, scratch_script, "cpu"], cwd=gdir, env=env)
+    if not os.path.exists(gen_cpp):
+        raise RuntimeError(f"generator did not write {gen_cpp}")
+
+    inc = ["-I" + os.path.join(HERE, "mpi_stub"), "-I" + REF, "-I" + os.path.join(REF, "runtime")]
+    rt = [os.path.join(REF, s) for s in RUNTIME_SRCS]
+    # 2. shared library with hooks + per-module wrappers
+    run(["g++", *CXXFLAGS, "-shared", "-fPIC", *defines, f'-DREF_GENERATED="{gen_cpp}"', *inc,
+         os.path.join(HERE, "ref_harness.cpp"), *rt, "-o", lib])
+    # 3. stock executable (for wall-clock baselines; prints the reference's own timers)
+    if want_exe:
+        run(["g++", *CXXFLAGS, *inc, gen_cpp, *rt, "-o", exe])
+    return "built"
+
+
+def main(argv):
+    if not os.path.isdir(REF):
+        print(f"[oracle/_ref] {REF} not present: keeping prebuilt artefacts")
+        return 0
+    names = argv or list(VARIANTS)
+    os.makedirs(GEN, exist_ok=True)
+    for n in names:
+        print(f"[oracle/_ref] {n}: {build_variant(n)}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))
