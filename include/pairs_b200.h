@@ -1,0 +1,140 @@
+/* pairs_b200.h -- C-ABI of libpairs_b200.so: a B200 (sm_100a) execution backend for the per-timestep
+ * particle pipeline of P4IRS/"pairs" (cell binning -> neighbour lists -> pair force -> integrate ->
+ * halo/migration).
+ *
+ * This is the LOWER boundary of the drop-in: in the reference every building
+ * block is a generated module `void <name>(PairsSimulation *pairs, scalars..., arrays...)`
+ * (code_gen/cgen.py:144-200) calling into the C++ runtime (runtime/pairs.hpp:27-297).  Here each
+ * module is one entry point on an opaque context that owns all device memory.  Python
+ * (pairs_b200/, the unchanged `pairs` DSL surface) binds these with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every entry returns int: 0 = ok, < 0 = error (text via pb_last_error), > 0 only where documented.
+ *   - host arrays use the reference's layouts: vectors are AoS [n][3] doubles, ints are int32.
+ *   - `grid`  = {xmin, xmax, ymin, ymax, zmin, zmax} (argument order of PairsSimulation::initDomain,
+ *     runtime/pairs.cpp:14-16); `subdom` likewise per rank.
+ *   - the library never exits the process and has NO CPU fallback: without a CUDA device pb_create fails.
+ *   - one context per GPU / per process rank; entry points are not re-entrant per context.
+ */
+#ifndef PAIRS_B200_H
+#define PAIRS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb_ctx pb_ctx;
+
+/* particle flags (runtime/pairs.hpp:20-23, src/pairs/sim/flags.py) and shapes (src/pairs/sim/shapes.py) */
+#define PB_FLAG_INFINITE 1
+#define PB_FLAG_GHOST 2
+#define PB_FLAG_FIXED 4
+#define PB_FLAG_GLOBAL 8
+#define PB_SHAPE_SPHERE 0
+#define PB_SHAPE_HALFSPACE 1
+#define PB_SHAPE_POINTMASS 2
+
+/* domain partitioners (runtime/pairs.cpp:18-26: Regular = {1,1,1}, RegularXY = {1,1,0}) */
+#define PB_PARTITION_REGULAR 0
+#define PB_PARTITION_REGULAR_XY 1
+
+/* ---- lifecycle: replaces `new PairsSimulation(...)` / `delete pairs` (code_gen/cgen.py:128) ---- */
+int pb_create(pb_ctx **out, int device);
+void pb_destroy(pb_ctx *ctx);
+const char *pb_last_error(const pb_ctx *ctx); /* ctx may be NULL: error of the last failed pb_create */
+const char *pb_version(void);
+
+/* ---- domain: PairsSimulation::initDomain + Regular6DStencil::{setConfig,setBoundingBox,fillArrays}
+ *      (runtime/pairs.cpp:14-29, runtime/domain/regular_6d_stencil.cpp:10-111), without MPI:
+ *      `rank`/`world_size` come from the launcher (torchrun env). ---- */
+int pb_init_domain(pb_ctx *ctx, const double grid[6], const int pbc[3], int partitioner, int world_size, int rank);
+int pb_get_decomposition(const pb_ctx *ctx, int nranks[3], int neighbor_ranks[6], int pbc[6], double subdom[6]);
+/* pure helper = Regular6DStencil::setConfig */
+int pb_rank_grid(int world_size, const double grid[6], int partitioner, int nranks[3]);
+
+/* ---- capacities: particle_capacity / neighbor_capacity of pairs.simulation() (src/pairs/__init__.py:9-17).
+ *      Both grow automatically (the reference's resize protocol, transformations/modules.py:159-203). ---- */
+int pb_reserve(pb_ctx *ctx, int particle_capacity, int neighbor_capacity);
+
+/* ---- set-up (host side, bit-identical to the reference's runtime) ----
+ * pb_copper_fcc_lattice = pairs::copper_fcc_lattice (runtime/copper_fcc_lattice.hpp:64-145); returns nlocal
+ * of this rank in *nlocal.  pb_adjust_thermo = pairs::adjust_thermo (runtime/thermo.hpp:53-97). */
+int pb_copper_fcc_lattice(pb_ctx *ctx, int nx, int ny, int nz, double rho, int ntypes, int *nlocal);
+int pb_adjust_thermo(pb_ctx *ctx, double temp);
+/* Bulk upload of local particles (replaces property initialisation + copy*ToDevice, runtime/pairs.cpp:161-327).
+ * Any pointer except position may be NULL (defaults: velocity 0, mass 1, type 0, flags 0, uid 0, shape point mass). */
+int pb_upload_particles(pb_ctx *ctx, int n, const double *position, const double *velocity, const double *mass,
+                        const int *type, const int *flags, const int *uid, const int *shape);
+
+/* ---- state download (tests, output): device order; `tag` = index the particle had at upload / lattice time
+ *      (+ first tag of the rank), ghosts carry the tag of their source.  n = nlocal (+ nghost if with_ghosts). ---- */
+int pb_counts(const pb_ctx *ctx, int *nlocal, int *nghost);
+int pb_download_real(pb_ctx *ctx, const char *name, double *out, int with_ghosts); /* position|linear_velocity|force [n][3], mass [n] */
+int pb_download_int(pb_ctx *ctx, const char *name, int *out, int with_ghosts);     /* type|flags|uid|shape|tag|particle_cell|numneighs */
+/* neighbour lists as the reference stores them on the CPU: out[i*capacity + k] (sim/neighbor_lists.py:14), device indices */
+int pb_download_neighbors(pb_ctx *ctx, int *out, int capacity);
+int pb_neighbor_capacity(const pb_ctx *ctx);
+int pb_max_neighbors(const pb_ctx *ctx);
+/* ghost bookkeeping (send_map / send_mult of sim/comm.py:223-259, one entry per ghost this rank OWNS as receiver):
+ * src[g] = device index of the source particle on the sending rank, mult[g][3] = PBC multipliers */
+int pb_download_ghost_map(pb_ctx *ctx, int *src, int *mult);
+
+/* ---- cell lists ----
+ * pb_setup_cells  = BuildCellListsStencil (sim/cell_lists.py:46-87): dim_cells, ncells, 27-cell stencil.
+ * pb_build_cell_lists = BuildCellLists + PartitionCellLists (sim/cell_lists.py:90-171) over nlocal+nghost particles:
+ *   particle_cell[] is bit-identical to the reference's; storage is a CSR cell list (counting sort). */
+int pb_setup_cells(pb_ctx *ctx, double spacing);
+int pb_get_cells(const pb_ctx *ctx, int dim_cells[3], int *ncells, int stencil[27]);
+int pb_build_cell_lists(pb_ctx *ctx);
+/* CSR cell list download: cell_start[ncells+1], cell_list[nlocal+nghost] */
+int pb_download_cell_lists(pb_ctx *ctx, int *cell_start, int *cell_list);
+
+/* ---- neighbour lists: BuildNeighborLists (sim/neighbor_lists.py:21-48), full lists, ghosts included as j,
+ *      padded column-major (ELLPACK) storage on the device. ---- */
+int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff);
+
+/* ---- kernels of examples/md.py ---- */
+/* feature properties epsilon/sigma6 [ntypes*ntypes] (add_feature_property, sim/simulation.py:179) */
+int pb_set_lj_params(pb_ctx *ctx, int ntypes, const double *epsilon, const double *sigma6);
+int pb_reset_volatile(pb_ctx *ctx);                       /* ResetVolatileProperties, sim/properties.py:61-70 */
+int pb_lennard_jones(pb_ctx *ctx, double cutoff);         /* examples/md.py:5-8 via ParticleInteraction */
+int pb_initial_integrate(pb_ctx *ctx, double dt);         /* examples/md.py:11-13 */
+int pb_final_integrate(pb_ctx *ctx, double dt);           /* examples/md.py:16-17 */
+/* pairs::compute_thermo (runtime/thermo.hpp:11-51): T and P over ALL ranks' locals (rank-local sums are returned
+ * in *sum_mv2 / *natoms when world_size > 1 and no communicator is attached) */
+int pb_compute_thermo(pb_ctx *ctx, double *temperature, double *pressure);
+int pb_thermo_partial(pb_ctx *ctx, double *sum_mv2, int *natoms);
+
+/* ---- communication (sim/comm.py): exchange = migration + PBC wrap (+ cell-order reordering of the locals),
+ *      borders = ghost creation, synchronize = per-step ghost refresh ---- */
+int pb_exchange(pb_ctx *ctx);
+int pb_borders(pb_ctx *ctx);
+int pb_synchronize(pb_ctx *ctx);
+
+/* multi-GPU: NCCL communicator over the ranks of pb_init_domain.  id = 128-byte ncclUniqueId made by rank 0
+ * (pb_nccl_unique_id) and distributed by the launcher. */
+int pb_nccl_unique_id(void *id128);
+int pb_nccl_init(pb_ctx *ctx, const void *id128);
+
+/* ---- whole timestep loop (sim/timestep.py:9-72 + sim/simulation.py:387-417), iterations ts in [ts_begin, ts_end):
+ *      guards ((ts+1)%every==0)||ts==0 and ts>0 exactly as generated.  thermo_out (may be NULL) receives
+ *      {ts, T, P} triples for every thermo step, up to thermo_cap triples; *n_thermo = number written. ---- */
+typedef struct pb_md_params {
+    double dt, cutoff_force, cutoff_lists, cell_spacing;
+    int reneighbor_every, thermo_every;
+} pb_md_params;
+int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo);
+
+/* ---- streams / timing ---- */
+int pb_synchronize_device(pb_ctx *ctx);
+/* per-stage device time in ms accumulated with CUDA events when enabled (names follow the reference's timers) */
+int pb_timers_enable(pb_ctx *ctx, int on);
+int pb_timers_get(pb_ctx *ctx, const char *name, double *ms, long *calls);
+int pb_timers_reset(pb_ctx *ctx);
+/* number of kernels launched by this context so far */
+long pb_kernel_launches(const pb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

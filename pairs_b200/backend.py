@@ -1,0 +1,335 @@
+"""ctypes binding of libpairs_b200.so (include/pairs_b200.h): the thin C-ABI shim between the Python host
+code and the hand-written sm_100a kernels.  No PyTorch, no Triton, no CPU fallback: if the library or a CUDA
+device is missing, construction fails loudly.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "lib", "libpairs_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu"]
+
+# --fmad=false: fp64 multiplies and adds are never contracted, so per-operation results equal the reference CPU
+# build compiled with -ffp-contract=off (the parity contract).
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "ctx.cuh"), os.path.join(INCLUDE, "pairs_b200.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
+        return LIB_PATH
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-I" + INCLUDE, "-o", LIB_PATH, *srcs, "-ldl"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise BackendError("nvcc failed building libpairs_b200.so")
+    return LIB_PATH
+
+
+class MdParams(ctypes.Structure):
+    _fields_ = [("dt", ctypes.c_double), ("cutoff_force", ctypes.c_double), ("cutoff_lists", ctypes.c_double),
+                ("cell_spacing", ctypes.c_double), ("reneighbor_every", ctypes.c_int), ("thermo_every", ctypes.c_int)]
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_D = ctypes.c_double
+_IP = ctypes.POINTER(ctypes.c_int)
+_DP = ctypes.POINTER(ctypes.c_double)
+_S = ctypes.c_char_p
+
+# every symbol include/pairs_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "pb_create": (_I, [ctypes.POINTER(_P), _I]),
+    "pb_destroy": (None, [_P]),
+    "pb_last_error": (_S, [_P]),
+    "pb_version": (_S, []),
+    "pb_init_domain": (_I, [_P, _DP, _IP, _I, _I, _I]),
+    "pb_get_decomposition": (_I, [_P, _IP, _IP, _IP, _DP]),
+    "pb_rank_grid": (_I, [_I, _DP, _I, _IP]),
+    "pb_reserve": (_I, [_P, _I, _I]),
+    "pb_copper_fcc_lattice": (_I, [_P, _I, _I, _I, _D, _I, _IP]),
+    "pb_adjust_thermo": (_I, [_P, _D]),
+    "pb_upload_particles": (_I, [_P, _I, _DP, _DP, _DP, _IP, _IP, _IP, _IP]),
+    "pb_counts": (_I, [_P, _IP, _IP]),
+    "pb_download_real": (_I, [_P, _S, _DP, _I]),
+    "pb_download_int": (_I, [_P, _S, _IP, _I]),
+    "pb_download_neighbors": (_I, [_P, _IP, _I]),
+    "pb_neighbor_capacity": (_I, [_P]),
+    "pb_max_neighbors": (_I, [_P]),
+    "pb_download_ghost_map": (_I, [_P, _IP, _IP]),
+    "pb_setup_cells": (_I, [_P, _D]),
+    "pb_get_cells": (_I, [_P, _IP, _IP, _IP]),
+    "pb_build_cell_lists": (_I, [_P]),
+    "pb_download_cell_lists": (_I, [_P, _IP, _IP]),
+    "pb_build_neighbor_lists": (_I, [_P, _D]),
+    "pb_set_lj_params": (_I, [_P, _I, _DP, _DP]),
+    "pb_reset_volatile": (_I, [_P]),
+    "pb_lennard_jones": (_I, [_P, _D]),
+    "pb_initial_integrate": (_I, [_P, _D]),
+    "pb_final_integrate": (_I, [_P, _D]),
+    "pb_compute_thermo": (_I, [_P, _DP, _DP]),
+    "pb_thermo_partial": (_I, [_P, _DP, _IP]),
+    "pb_exchange": (_I, [_P]),
+    "pb_borders": (_I, [_P]),
+    "pb_synchronize": (_I, [_P]),
+    "pb_nccl_unique_id": (_I, [_P]),
+    "pb_nccl_init": (_I, [_P, _P]),
+    "pb_md_run": (_I, [_P, ctypes.POINTER(MdParams), _I, _I, _DP, _I, _IP]),
+    "pb_synchronize_device": (_I, [_P]),
+    "pb_timers_enable": (_I, [_P, _I]),
+    "pb_timers_get": (_I, [_P, _S, _DP, ctypes.POINTER(ctypes.c_long)]),
+    "pb_timers_reset": (_I, [_P]),
+    "pb_kernel_launches": (ctypes.c_long, [_P]),
+}
+
+_LIB = None
+
+
+def load():
+    """dlopen the shim and type every entry point.  Raises BackendError if the library is not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise BackendError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_DP)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(_IP)
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else a.reshape(shape)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def rank_grid(world_size, grid, partitioner=0):
+    out = np.zeros(3, np.int32)
+    g = _f64(grid)
+    load().pb_rank_grid(world_size, _dp(g), partitioner, _ip(out))
+    return tuple(int(x) for x in out)
+
+
+class Context:
+    """One GPU's particle store + the per-stage entry points (one per reference module)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = _P()
+        rc = self.lib.pb_create(ctypes.byref(h), device)
+        if rc != 0:
+            raise BackendError(self.lib.pb_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise BackendError(self.lib.pb_last_error(self.h).decode())
+        return rc
+
+    # ---- domain ----
+    def init_domain(self, grid, pbc=(1, 1, 1), partitioner=0, world_size=1, rank=0):
+        g = _f64(grid)
+        p = _i32([1 if b else 0 for b in pbc])
+        self._ck(self.lib.pb_init_domain(self.h, _dp(g), _ip(p), partitioner, world_size, rank))
+
+    def decomposition(self):
+        nr = np.zeros(3, np.int32)
+        nb = np.zeros(6, np.int32)
+        pbc = np.zeros(6, np.int32)
+        sub = np.zeros(6, np.float64)
+        self._ck(self.lib.pb_get_decomposition(self.h, _ip(nr), _ip(nb), _ip(pbc), _dp(sub)))
+        return {"nranks": nr, "neighbor_ranks": nb, "pbc": pbc, "subdom": sub}
+
+    def reserve(self, particle_capacity=0, neighbor_capacity=0):
+        self._ck(self.lib.pb_reserve(self.h, particle_capacity, neighbor_capacity))
+
+    # ---- set-up ----
+    def copper_fcc_lattice(self, nx, ny, nz, rho, ntypes):
+        n = _I(0)
+        self._ck(self.lib.pb_copper_fcc_lattice(self.h, nx, ny, nz, rho, ntypes, ctypes.byref(n)))
+        return n.value
+
+    def adjust_thermo(self, temp):
+        self._ck(self.lib.pb_adjust_thermo(self.h, temp))
+
+    def upload(self, position, velocity=None, mass=None, type_=None, flags=None, uid=None, shape=None):
+        pos = _f64(position)
+        n = pos.size // 3
+        vel, m = _f64(velocity), _f64(mass)
+        t, f, u, s = _i32(type_), _i32(flags), _i32(uid), _i32(shape)
+        self._ck(self.lib.pb_upload_particles(self.h, n, _dp(pos), _dp(vel), _dp(m), _ip(t), _ip(f), _ip(u), _ip(s)))
+
+    # ---- download ----
+    def counts(self):
+        a, b = _I(0), _I(0)
+        self.lib.pb_counts(self.h, ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    def real(self, name, with_ghosts=False):
+        nl, ng = self.counts()
+        n = nl + (ng if with_ghosts else 0)
+        w = 1 if name == "mass" else 3
+        out = np.zeros(n * w, np.float64)
+        self._ck(self.lib.pb_download_real(self.h, name.encode(), _dp(out), 1 if with_ghosts else 0))
+        return out.reshape(n, 3) if w == 3 else out
+
+    def ints(self, name, with_ghosts=False):
+        nl, ng = self.counts()
+        n = nl + (ng if with_ghosts else 0)
+        if name == "numneighs":
+            n = nl
+        out = np.zeros(n, np.int32)
+        self._ck(self.lib.pb_download_int(self.h, name.encode(), _ip(out), 1 if with_ghosts else 0))
+        return out
+
+    def neighbors(self):
+        nl, _ = self.counts()
+        cap = max(self.lib.pb_max_neighbors(self.h), 1)
+        out = np.zeros(nl * cap, np.int32)
+        self._ck(self.lib.pb_download_neighbors(self.h, _ip(out), cap))
+        return out.reshape(nl, cap)
+
+    def ghost_map(self):
+        _, ng = self.counts()
+        src = np.zeros(ng, np.int32)
+        mult = np.zeros(ng * 3, np.int32)
+        self._ck(self.lib.pb_download_ghost_map(self.h, _ip(src), _ip(mult)))
+        return src, mult.reshape(ng, 3)
+
+    # ---- stages ----
+    def setup_cells(self, spacing):
+        self._ck(self.lib.pb_setup_cells(self.h, spacing))
+
+    def cells(self):
+        dc = np.zeros(3, np.int32)
+        nc = _I(0)
+        st = np.zeros(27, np.int32)
+        self._ck(self.lib.pb_get_cells(self.h, _ip(dc), ctypes.byref(nc), _ip(st)))
+        return dc, nc.value, st
+
+    def build_cell_lists(self):
+        self._ck(self.lib.pb_build_cell_lists(self.h))
+
+    def cell_lists(self):
+        _, nc, _ = self.cells()
+        nl, ng = self.counts()
+        cs = np.zeros(nc + 1, np.int32)
+        cl = np.zeros(nl + ng, np.int32)
+        self._ck(self.lib.pb_download_cell_lists(self.h, _ip(cs), _ip(cl)))
+        return cs, cl
+
+    def build_neighbor_lists(self, cutoff):
+        self._ck(self.lib.pb_build_neighbor_lists(self.h, cutoff))
+
+    def set_lj_params(self, ntypes, epsilon, sigma6):
+        e, s = _f64(epsilon), _f64(sigma6)
+        self._ck(self.lib.pb_set_lj_params(self.h, ntypes, _dp(e), _dp(s)))
+
+    def reset_volatile(self):
+        self._ck(self.lib.pb_reset_volatile(self.h))
+
+    def lennard_jones(self, cutoff):
+        self._ck(self.lib.pb_lennard_jones(self.h, cutoff))
+
+    def initial_integrate(self, dt):
+        self._ck(self.lib.pb_initial_integrate(self.h, dt))
+
+    def final_integrate(self, dt):
+        self._ck(self.lib.pb_final_integrate(self.h, dt))
+
+    def compute_thermo(self):
+        t, p = _D(0.0), _D(0.0)
+        self._ck(self.lib.pb_compute_thermo(self.h, ctypes.byref(t), ctypes.byref(p)))
+        return t.value, p.value
+
+    def exchange(self):
+        self._ck(self.lib.pb_exchange(self.h))
+
+    def borders(self):
+        self._ck(self.lib.pb_borders(self.h))
+
+    def synchronize(self):
+        self._ck(self.lib.pb_synchronize(self.h))
+
+    def nccl_init(self, id128: bytes):
+        buf = ctypes.create_string_buffer(id128, 128)
+        self._ck(self.lib.pb_nccl_init(self.h, ctypes.cast(buf, _P)))
+
+    def md_run(self, ts_begin, ts_end, dt, cutoff_force, cutoff_lists, cell_spacing, reneighbor_every, thermo_every):
+        p = MdParams(dt, cutoff_force, cutoff_lists, cell_spacing, reneighbor_every, thermo_every)
+        cap = max(8, (ts_end - ts_begin) // max(thermo_every, 1) + 4) if thermo_every > 0 else 1
+        out = np.zeros(cap * 3, np.float64)
+        n = _I(0)
+        self._ck(self.lib.pb_md_run(self.h, ctypes.byref(p), ts_begin, ts_end, _dp(out), cap, ctypes.byref(n)))
+        return out[: min(n.value, cap) * 3].reshape(-1, 3)
+
+    def sync(self):
+        self._ck(self.lib.pb_synchronize_device(self.h))
+
+    def timers_enable(self, on=True):
+        self.lib.pb_timers_enable(self.h, 1 if on else 0)
+
+    def timers_reset(self):
+        self.lib.pb_timers_reset(self.h)
+
+    def timer(self, name):
+        ms = _D(0.0)
+        calls = ctypes.c_long(0)
+        self.lib.pb_timers_get(self.h, name.encode(), ctypes.byref(ms), ctypes.byref(calls))
+        return ms.value, calls.value
+
+    def kernel_launches(self):
+        return int(self.lib.pb_kernel_launches(self.h))
+
+
+def nccl_unique_id():
+    buf = ctypes.create_string_buffer(128)
+    if load().pb_nccl_unique_id(ctypes.cast(buf, _P)) != 0:
+        raise BackendError("ncclGetUniqueId failed")
+    return buf.raw

@@ -1,0 +1,335 @@
+// Cell binning as a deterministic counting sort + cell-order reordering of the local particles.
+// Replaces BuildCellListsStencil / BuildCellLists / PartitionCellLists (sim/cell_lists.py:46-171) and the dense
+// cell_particles[ncells][cell_capacity] array (25.6 MB, 64-slot rows, atomic slot claims) by
+//   particle_cell[i]  -- bit-identical to the reference's value (same fp64 subtract / divide / truncate / clamp)
+//   cell_start[c], cell_list[k]  -- CSR cell list; inside a cell particles are in ascending index order
+// so there is no cell_capacity to overflow and the result is run-to-run reproducible.
+//
+// Kernels (all HBM-bound; algorithmic bytes per binned particle: pos 32 + flags 4 + particle_cell 4 w + slot 4 w,
+// then slot 4 r + cell 4 r + list 4 w; the per-cell arrays are ncells*4 B and stay in L2):
+//   pb_k_cell_count   cell index + warp-aggregated histogram (one atomic per distinct cell per warp)
+//   pb_k_scan_*       exclusive scan of the histogram
+//   pb_k_cell_fill    scatter indices to cell_start[c] + slot
+//   pb_k_cell_sort    per-cell insertion sort of the (<= ~30) indices -> deterministic order
+//   pb_k_reorder_*    gather of every per-particle array through the permutation (cell order)
+#include <algorithm>
+#include <cmath>
+
+#include "ctx.cuh"
+
+// ---- BuildCellListsStencil (sim/cell_lists.py:46-87): host, same fp64 expression order ---------------------
+extern "C" int pb_setup_cells(pb_ctx *ctx, double spacing) {
+    if(!ctx->domain_set) { ctx->set_error("pb_setup_cells: domain not initialised"); return -1; }
+    PB_CHECK(cudaSetDevice(ctx->device));
+    ctx->spacing = spacing;
+    for(int d = 0; d < 3; d++) {
+        const double hi = ctx->subdom[d * 2 + 1] + spacing;
+        const double lo = ctx->subdom[d * 2 + 0] - spacing;
+        const double len = hi - lo;
+        const double q = len / spacing;
+        ctx->dim_cells[d] = ((int) ceil(q)) + 1;
+    }
+    const long nc = (long) ctx->dim_cells[0] * ctx->dim_cells[1] * ctx->dim_cells[2] + 1;
+    if(nc > 0x7fffff00L) { ctx->set_error("pb_setup_cells: too many cells"); return -1; }
+    ctx->ncells = (int) nc;
+    int k = 0;
+    for(int i = -1; i < 2; i++) {
+        for(int j = -1; j < 2; j++) {
+            for(int l = -1; l < 2; l++) { ctx->stencil[k++] = (i * ctx->dim_cells[1] + j) * ctx->dim_cells[2] + l; }
+        }
+    }
+    if(ctx->ncells + 1 > ctx->ccap) {
+        if(ctx->cell_count != nullptr) { PB_CHECK(cudaFree(ctx->cell_count)); }
+        if(ctx->cell_start != nullptr) { PB_CHECK(cudaFree(ctx->cell_start)); }
+        ctx->ccap = ctx->ncells + 1;
+        PB_CHECK(cudaMalloc(&ctx->cell_count, sizeof(int) * ((size_t) ctx->ccap + 1)));
+        PB_CHECK(cudaMalloc(&ctx->cell_start, sizeof(int) * ((size_t) ctx->ccap + 1)));
+    }
+    ctx->cells_set = true;
+    ctx->cells_n = 0;
+    return 0;
+}
+
+extern "C" int pb_get_cells(const pb_ctx *ctx, int dim_cells[3], int *ncells, int stencil[27]) {
+    for(int d = 0; d < 3; d++) { dim_cells[d] = ctx->dim_cells[d]; }
+    *ncells = ctx->ncells;
+    for(int k = 0; k < 27; k++) { stencil[k] = ctx->stencil[k]; }
+    return 0;
+}
+
+// ---- exclusive scan (3 kernels, 2048 items per block) -----------------------------------------------------
+static const int SCAN_T = 512;
+static const int SCAN_ITEMS = 4;
+static const int SCAN_BLOCK = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ int pb_block_exclusive_scan(int v, int *total, int *warp_sums) {
+    // inclusive warp scan
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for(int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if(lane >= o) { x += y; }
+    }
+    if(lane == 31) { warp_sums[wid] = x; }
+    __syncthreads();
+    if(wid == 0) {
+        int w = (lane < (int) (blockDim.x >> 5)) ? warp_sums[lane] : 0;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if(lane >= o) { w += y; }
+        }
+        warp_sums[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_off = (wid == 0) ? 0 : warp_sums[wid - 1];
+    *total = warp_sums[(blockDim.x >> 5) - 1];
+    return warp_off + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) pb_k_scan_reduce(const int *__restrict__ in, int n, int *__restrict__ block_sums) {
+    __shared__ int warp_sums[32];
+    const int base = blockIdx.x * SCAN_BLOCK;
+    int s = 0;
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; k++) {
+        const int i = base + k * SCAN_T + threadIdx.x;
+        s += (i < n) ? in[i] : 0;
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); }
+    if((threadIdx.x & 31) == 0) { warp_sums[threadIdx.x >> 5] = s; }
+    __syncthreads();
+    if(threadIdx.x < 32) {
+        int w = (threadIdx.x < (SCAN_T >> 5)) ? warp_sums[threadIdx.x] : 0;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { w += __shfl_down_sync(0xffffffffu, w, o); }
+        if(threadIdx.x == 0) { block_sums[blockIdx.x] = w; }
+    }
+}
+
+// single block: exclusive scan of the block sums in place (serial over chunks of SCAN_T)
+__global__ void __launch_bounds__(SCAN_T) pb_k_scan_sums(int *__restrict__ block_sums, int nblocks, int *__restrict__ total_out) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if(threadIdx.x == 0) { carry_s = 0; }
+    __syncthreads();
+    for(int base = 0; base < nblocks; base += SCAN_T) {
+        const int i = base + threadIdx.x;
+        const int v = (i < nblocks) ? block_sums[i] : 0;
+        int total;
+        const int ex = pb_block_exclusive_scan(v, &total, warp_sums);
+        const int carry = carry_s;
+        if(i < nblocks) { block_sums[i] = carry + ex; }
+        __syncthreads();
+        if(threadIdx.x == 0) { carry_s = carry + total; }
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) { *total_out = carry_s; }
+}
+
+__global__ void __launch_bounds__(SCAN_T) pb_k_scan_apply(const int *__restrict__ in, int n, const int *__restrict__ block_sums,
+                                                           int *__restrict__ out) {
+    __shared__ int warp_sums[32];
+    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;   // blocked arrangement: thread owns 4 consecutive items
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = pb_block_exclusive_scan(s, &total, warp_sums) + block_sums[blockIdx.x];
+#pragma unroll
+    for(int k = 0; k < SCAN_ITEMS; k++) {
+        if(base + k < n) { out[base + k] = ex; }
+        ex += v[k];
+    }
+}
+
+// out[0..n-1] = exclusive prefix sums, out[n] = total
+int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n) {
+    if(n <= 0) {
+        PB_CHECK(cudaMemsetAsync(out, 0, sizeof(int), ctx->stream));
+        return 0;
+    }
+    const int nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    if(nblocks > ctx->scan_tmp_cap) {
+        if(ctx->scan_tmp != nullptr) { PB_CHECK(cudaFree(ctx->scan_tmp)); }
+        ctx->scan_tmp_cap = nblocks + 1024;
+        PB_CHECK(cudaMalloc(&ctx->scan_tmp, sizeof(int) * (size_t) ctx->scan_tmp_cap));
+    }
+    PB_LAUNCH(pb_k_scan_reduce, nblocks, SCAN_T, in, n, ctx->scan_tmp);
+    PB_LAUNCH(pb_k_scan_sums, 1, SCAN_T, ctx->scan_tmp, nblocks, out + n);
+    PB_LAUNCH(pb_k_scan_apply, nblocks, SCAN_T, in, n, ctx->scan_tmp, out);
+    return 0;
+}
+
+// ---- binning ----------------------------------------------------------------------------------------------
+struct PbCellGeom {
+    double lo[3];       // subdom_min - spacing
+    double spacing;
+    int dim[3];
+    int ncells;
+};
+
+// BuildCellLists index arithmetic (sim/cell_lists.py:111-127; generated md.cpp build_cell_lists):
+//   c_d = clamp((int)((x_d - (min_d - s)) / s), 0, dim_d - 1);  flat = (c0*dim1 + c1)*dim2 + c2 + 1;  INFINITE -> 0
+__device__ __forceinline__ int pb_cell_index(const PbCellGeom &g, double x, double y, double z, int flags) {
+    if(flags & PB_FLAG_INFINITE) { return 0; }
+    const double q0 = __ddiv_rn(__dsub_rn(x, g.lo[0]), g.spacing);
+    const double q1 = __ddiv_rn(__dsub_rn(y, g.lo[1]), g.spacing);
+    const double q2 = __ddiv_rn(__dsub_rn(z, g.lo[2]), g.spacing);
+    int c0 = (int) q0, c1 = (int) q1, c2 = (int) q2;      // truncation toward zero, as the C cast
+    c0 = (c0 >= 0) ? c0 : 0; c0 = (c0 < g.dim[0]) ? c0 : g.dim[0] - 1;
+    c1 = (c1 >= 0) ? c1 : 0; c1 = (c1 < g.dim[1]) ? c1 : g.dim[1] - 1;
+    c2 = (c2 >= 0) ? c2 : 0; c2 = (c2 < g.dim[2]) ? c2 : g.dim[2] - 1;
+    return (c0 * g.dim[1] + c1) * g.dim[2] + c2 + 1;
+}
+
+// Warp-aggregated histogram: lanes of a warp that hit the same cell elect a leader which issues ONE atomicAdd
+// for the whole group; every lane derives its slot from the leader's base + its rank inside the group.
+__global__ void __launch_bounds__(256) pb_k_cell_count(PbCellGeom g, int first, int n, const double4 *__restrict__ pos,
+                                                       const int *__restrict__ flags, int *__restrict__ particle_cell,
+                                                       int *__restrict__ cell_count, int *__restrict__ cell_slot) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = k < n;
+    int cell = -1;
+    if(active) {
+        const double4 p = pos[first + k];
+        cell = pb_cell_index(g, p.x, p.y, p.z, flags[first + k]);
+        particle_cell[first + k] = cell;
+    }
+    const unsigned live = __ballot_sync(0xffffffffu, active);
+    if(!active) { return; }
+    const unsigned peers = __match_any_sync(live, cell);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    const int rank_in_group = __popc(peers & ((1u << lane) - 1u));
+    int base = 0;
+    if(lane == leader) { base = atomicAdd(&cell_count[cell], __popc(peers)); }
+    base = __shfl_sync(peers, base, leader);
+    cell_slot[first + k] = base + rank_in_group;
+}
+
+__global__ void __launch_bounds__(256) pb_k_cell_fill(int first, int n, const int *__restrict__ particle_cell,
+                                                      const int *__restrict__ cell_slot, const int *__restrict__ cell_start,
+                                                      int *__restrict__ cell_list) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k < n) {
+        const int i = first + k;
+        cell_list[cell_start[particle_cell[i]] + cell_slot[i]] = i;
+    }
+}
+
+// One thread per cell: insertion sort of the cell's index run (ascending).  Runs are short (mean ~18 at liquid
+// density with cells of one cutoff) and the arrival order is already nearly sorted.
+__global__ void __launch_bounds__(128) pb_k_cell_sort(int ncells, const int *__restrict__ cell_start, int *__restrict__ cell_list) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c >= ncells) { return; }
+    const int b = cell_start[c], e = cell_start[c + 1];
+    for(int i = b + 1; i < e; i++) {
+        const int v = cell_list[i];
+        int j = i - 1;
+        while(j >= b && cell_list[j] > v) {
+            cell_list[j + 1] = cell_list[j];
+            j--;
+        }
+        cell_list[j + 1] = v;
+    }
+}
+
+static PbCellGeom pb_geom(const pb_ctx *ctx) {
+    PbCellGeom g;
+    for(int d = 0; d < 3; d++) {
+        g.lo[d] = ctx->subdom[d * 2] - ctx->spacing;
+        g.dim[d] = ctx->dim_cells[d];
+    }
+    g.spacing = ctx->spacing;
+    g.ncells = ctx->ncells;
+    return g;
+}
+
+// Bins particles [first, first+n): particle_cell, cell_start[0..ncells], cell_list[0..n) (absolute indices).
+int pb_bin_particles(pb_ctx *ctx, int first, int n, bool /*write_particle_cell*/) {
+    if(!ctx->cells_set) { ctx->set_error("cell lists not set up (pb_setup_cells)"); return -1; }
+    PB_CHECK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(int) * ((size_t) ctx->ncells + 1), ctx->stream));
+    if(n > 0) {
+        PB_LAUNCH(pb_k_cell_count, pb_blocks(n, 256), 256, pb_geom(ctx), first, n, ctx->pos, ctx->flags, ctx->particle_cell,
+                  ctx->cell_count, ctx->cell_slot);
+    }
+    PB_TRY(pb_exclusive_scan(ctx, ctx->cell_count, ctx->cell_start, ctx->ncells));
+    if(n > 0) {
+        PB_LAUNCH(pb_k_cell_fill, pb_blocks(n, 256), 256, first, n, ctx->particle_cell, ctx->cell_slot, ctx->cell_start, ctx->cell_list);
+        PB_LAUNCH(pb_k_cell_sort, pb_blocks(ctx->ncells, 128), 128, ctx->ncells, ctx->cell_start, ctx->cell_list);
+    }
+    return 0;
+}
+
+// ---- public: BuildCellLists + PartitionCellLists over locals + ghosts -------------------------------------
+extern "C" int pb_build_cell_lists(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "build_cell_lists");
+    const int n = ctx->nlocal + ctx->nghost;
+    PB_TRY(pb_bin_particles(ctx, 0, n, true));
+    ctx->cells_n = n;
+    return 0;
+}
+
+extern "C" int pb_download_cell_lists(pb_ctx *ctx, int *cell_start, int *cell_list) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PB_CHECK(cudaMemcpyAsync(cell_start, ctx->cell_start, sizeof(int) * ((size_t) ctx->ncells + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if(ctx->cells_n > 0) {
+        PB_CHECK(cudaMemcpyAsync(cell_list, ctx->cell_list, sizeof(int) * (size_t) ctx->cells_n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- cell-order reordering of the locals ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pb_k_reorder(int n, int cap, const int *__restrict__ perm,
+                                                    const double4 *__restrict__ pos, double4 *__restrict__ pos_o,
+                                                    const double *__restrict__ vel, double *__restrict__ vel_o,
+                                                    const double *__restrict__ mass, double *__restrict__ mass_o,
+                                                    const int *__restrict__ type, int *__restrict__ type_o,
+                                                    const int *__restrict__ flags, int *__restrict__ flags_o,
+                                                    const int *__restrict__ uid, int *__restrict__ uid_o,
+                                                    const int *__restrict__ shape, int *__restrict__ shape_o,
+                                                    const int *__restrict__ tag, int *__restrict__ tag_o) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= n) { return; }
+    const int s = perm[k];
+    pos_o[k] = pos[s];
+    vel_o[k] = vel[s];
+    vel_o[cap + k] = vel[cap + s];
+    vel_o[2 * cap + k] = vel[2 * cap + s];
+    mass_o[k] = mass[s];
+    type_o[k] = type[s];
+    flags_o[k] = flags[s];
+    uid_o[k] = uid[s];
+    shape_o[k] = shape[s];
+    tag_o[k] = tag[s];
+}
+
+// Sort the locals into cell order (stable: ties keep ascending previous index).  Called from pb_exchange, before
+// ghosts exist; volatile `force` is not carried (it is reset before the next force evaluation, exactly as the
+// reference never transfers volatile properties, sim/comm.py:103).
+int pb_sort_locals(pb_ctx *ctx) {
+    const int n = ctx->nlocal;
+    if(n == 0) { return 0; }
+    PB_TRY(pb_bin_particles(ctx, 0, n, true));
+    PB_LAUNCH(pb_k_reorder, pb_blocks(n, 256), 256, n, ctx->pcap, ctx->cell_list, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
+              ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt,
+              ctx->shape, ctx->shape_alt, ctx->tag, ctx->tag_alt);
+    std::swap(ctx->pos, ctx->pos_alt);
+    std::swap(ctx->vel, ctx->vel_alt);
+    std::swap(ctx->mass, ctx->mass_alt);
+    std::swap(ctx->type, ctx->type_alt);
+    std::swap(ctx->flags, ctx->flags_alt);
+    std::swap(ctx->uid, ctx->uid_alt);
+    std::swap(ctx->shape, ctx->shape_alt);
+    std::swap(ctx->tag, ctx->tag_alt);
+    return 0;
+}

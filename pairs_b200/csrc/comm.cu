@@ -1,0 +1,280 @@
+// Communication stages of sim/comm.py as device-side select / pack / unpack kernels:
+//   pb_exchange     Comm.exchange   (comm.py:100-151)  migration + periodic wrap, then cell-order sort of the locals
+//   pb_borders      Comm.borders    (comm.py:56-98)    ghost creation, 3 ordered phases x -> y -> z
+//   pb_synchronize  Comm.synchronize(comm.py:45-54)    per-step ghost refresh
+// The reference selects with atomics (send order = whatever the atomics give, serial order on the CPU target);
+// here selection is a flag + exclusive scan + scatter, i.e. an ORDERED stream compaction, so send lists -- and
+// with them ghost numbering -- are deterministic: (dim, side, ascending source index).
+//
+// Transport between ranks is abstracted by pb_transport_* (comm_nccl.cu): a neighbour that is the rank itself
+// (single rank in that dimension, Regular6DStencil::communicateData's copy_in_device branch,
+// runtime/domain/regular_6d_stencil.cpp:156-157,175-176) is served from the send buffer directly.
+//
+// Wire records are rows of doubles as in the reference (ints cast to double, comm.py:328-329), one extra element
+// carries the particle tag:   exchange: uid shape flags x y z mass vx vy vz type tag          (12 doubles)
+//                             borders : uid type mass x y z vx vy vz shape tag              (11 doubles)
+//                             sync    : x y z vx vy vz                                      ( 6 doubles)
+// Positions are shifted by send_mult * L on ALL three axes exactly as comm.py:320-321 does (two of the
+// multipliers are zero), so ghost coordinates are bit-identical to the reference's.
+#include <algorithm>
+
+#include "ctx.cuh"
+
+int pb_sort_locals(pb_ctx *ctx);
+int pb_transport_sizes(pb_ctx *ctx, int dim);
+int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const double **recv_src);
+
+static const int EXCH_ELEMS = 12, BORDER_ELEMS = 11, SYNC_ELEMS = 6;
+
+struct PbBox {
+    double len[3];
+};
+
+// ---- selection ---------------------------------------------------------------------------------------------
+// sim/domain_partitioning.py:31-65: side 0 -> pos < min + offset, side 1 -> pos > max - offset; INFINITE/GLOBAL skipped
+__global__ void __launch_bounds__(256) pb_k_select(int n, int dim, int side, double bound, const double4 *__restrict__ pos,
+                                                   const int *__restrict__ flags, int *__restrict__ sel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    int hit = 0;
+    if((flags[i] & (PB_FLAG_INFINITE | PB_FLAG_GLOBAL)) == 0) {
+        const double4 p = pos[i];
+        const double x = (dim == 0) ? p.x : ((dim == 1) ? p.y : p.z);
+        hit = (side == 0) ? (x < bound) : (x > bound);
+    }
+    sel[i] = hit;
+}
+
+__global__ void __launch_bounds__(256) pb_k_scatter_sel(int n, int dim, int mult, int base, const int *__restrict__ sel,
+                                                        const int *__restrict__ scan, int *__restrict__ send_map,
+                                                        int *__restrict__ send_mult) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || sel[i] == 0) { return; }
+    const int k = base + scan[i];
+    send_map[k] = i;
+    send_mult[k * 3 + 0] = (dim == 0) ? mult : 0;
+    send_mult[k * 3 + 1] = (dim == 1) ? mult : 0;
+    send_mult[k * 3 + 2] = (dim == 2) ? mult : 0;
+}
+
+// Appends the particles of [0, n) selected for (dim, side) to the send lists; returns their number in *count.
+static int pb_select_side(pb_ctx *ctx, int n, int dim, int side, double offset, int *count) {
+    *count = 0;
+    const int j = dim * 2 + side;
+    if(n == 0 || (!ctx->pbc_flag[dim] && ctx->pbc[j] != 0)) { return 0; }
+    const double bound = (side == 0) ? (ctx->subdom[j] + offset) : (ctx->subdom[j] - offset);
+    PB_LAUNCH(pb_k_select, pb_blocks(n, 256), 256, n, dim, side, bound, ctx->pos, ctx->flags, ctx->sel_flag);
+    PB_TRY(pb_exclusive_scan(ctx, ctx->sel_flag, ctx->sel_scan, n));
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->sel_scan + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    const int c = ctx->h_scalars[0];
+    if(c > 0) {
+        PB_TRY(pb_ensure_send_capacity(ctx, ctx->nsend_all + c));
+        PB_LAUNCH(pb_k_scatter_sel, pb_blocks(n, 256), 256, n, dim, ctx->pbc[j], ctx->nsend_all, ctx->sel_flag, ctx->sel_scan,
+                  ctx->send_map, ctx->send_mult);
+    }
+    *count = c;
+    return 0;
+}
+
+// SetCommunicationOffsets (comm.py:262-288)
+static void pb_set_offsets(pb_ctx *ctx, int step) {
+    int isend = 0, irecv = 0;
+    for(int i = 0; i < step; i++) {
+        for(int j = i * 2; j < i * 2 + 2; j++) { isend += ctx->nsend[j]; irecv += ctx->nrecv[j]; }
+    }
+    for(int j = step * 2; j < step * 2 + 2; j++) {
+        ctx->send_offsets[j] = isend; ctx->recv_offsets[j] = irecv;
+        isend += ctx->nsend[j]; irecv += ctx->nrecv[j];
+    }
+}
+
+// ---- borders -----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, int cap, PbBox box, const int *__restrict__ send_map,
+                                                        const int *__restrict__ send_mult, const double4 *__restrict__ pos,
+                                                        const double *__restrict__ vel, const double *__restrict__ mass,
+                                                        const int *__restrict__ uid, const int *__restrict__ shape,
+                                                        const int *__restrict__ tag, double *__restrict__ buf) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    const int e = first + k;
+    const int p = send_map[e];
+    const double4 x = pos[p];
+    double *b = buf + (size_t) e * BORDER_ELEMS;
+    b[0] = (double) uid[p];
+    b[1] = (double) pb_w_type(x.w);
+    b[2] = mass[p];
+    b[3] = __dadd_rn(x.x, __dmul_rn((double) send_mult[e * 3 + 0], box.len[0]));
+    b[4] = __dadd_rn(x.y, __dmul_rn((double) send_mult[e * 3 + 1], box.len[1]));
+    b[5] = __dadd_rn(x.z, __dmul_rn((double) send_mult[e * 3 + 2], box.len[2]));
+    b[6] = vel[p];
+    b[7] = vel[cap + p];
+    b[8] = vel[2 * cap + p];
+    b[9] = (double) shape[p];
+    b[10] = (double) tag[p];
+}
+
+__global__ void __launch_bounds__(256) pb_k_unpack_border(int first_rec, int count, int dst0, int cap, const double *__restrict__ buf,
+                                                          double4 *__restrict__ pos, double *__restrict__ vel, double *__restrict__ mass,
+                                                          int *__restrict__ type, int *__restrict__ flags, int *__restrict__ uid,
+                                                          int *__restrict__ shape, int *__restrict__ tag) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    const double *b = buf + (size_t) (first_rec + k) * BORDER_ELEMS;
+    const int p = dst0 + k;
+    const int t = (int) b[1];
+    uid[p] = (int) b[0];
+    type[p] = t;
+    mass[p] = b[2];
+    pos[p] = make_double4(b[3], b[4], b[5], pb_type_w(t));
+    vel[p] = b[6];
+    vel[cap + p] = b[7];
+    vel[2 * cap + p] = b[8];
+    shape[p] = (int) b[9];
+    tag[p] = (int) b[10];
+    // The reference never transmits ghost flags (the slot keeps a stale value); here they are
+    // defined: GHOST only -- so ghosts are binned (not INFINITE), forwarded (not GLOBAL) and never integrated.
+    flags[p] = PB_FLAG_GHOST;
+}
+
+static PbBox pb_box(const pb_ctx *ctx) {
+    PbBox b;
+    for(int d = 0; d < 3; d++) { b.len[d] = ctx->grid[d * 2 + 1] - ctx->grid[d * 2]; }
+    return b;
+}
+
+extern "C" int pb_borders(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "borders");
+    if(!ctx->cells_set) { ctx->set_error("pb_borders: cell spacing unknown (pb_setup_cells)"); return -1; }
+    ctx->nsend_all = 0;
+    ctx->nghost = 0;
+    ctx->cells_n = 0;
+    for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
+    for(int step = 0; step < 3; step++) {
+        const int n = ctx->nlocal + ctx->nghost;     // locals AND ghosts received so far: edges/corners are forwarded
+        for(int side = 0; side < 2; side++) {
+            int c = 0;
+            PB_TRY(pb_select_side(ctx, n, step, side, ctx->spacing, &c));
+            ctx->nsend[step * 2 + side] = c;
+            ctx->nsend_all += c;
+        }
+        PB_TRY(pb_transport_sizes(ctx, step));
+        pb_set_offsets(ctx, step);
+        const int ns = ctx->nsend[step * 2] + ctx->nsend[step * 2 + 1];
+        const int nr = ctx->nrecv[step * 2] + ctx->nrecv[step * 2 + 1];
+        PB_TRY(pb_ensure_particle_capacity(ctx, ctx->nlocal + ctx->nghost + nr));
+        if(ns > 0) {
+            PB_LAUNCH(pb_k_pack_border, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, pb_box(ctx), ctx->send_map,
+                      ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf);
+        }
+        const double *src = nullptr;
+        PB_TRY(pb_transport_data(ctx, step, step + 1, BORDER_ELEMS, &src));
+        if(nr > 0) {
+            PB_LAUNCH(pb_k_unpack_border, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
+                      ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                      ctx->uid, ctx->shape, ctx->tag);
+        }
+        ctx->nghost += nr;
+    }
+    return 0;
+}
+
+// ---- synchronize -------------------------------------------------------------------------------------------
+// Comm.synchronize packs EVERY send entry from the current arrays in one pass, then transfers, then unpacks
+// (comm.py:45-54; generated pack_all_ghost_particles / unpack_all_ghost_particles).  A forwarded ghost (edge or
+// corner image, whose source is itself a ghost) therefore carries the coordinates its source ghost had BEFORE this
+// refresh -- one step stale per forwarding level.  That behaviour is part of the reference's results and is
+// reproduced here by construction: one pack kernel over all entries, then one unpack kernel.
+__global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, PbBox box, const int *__restrict__ send_map,
+                                                      const int *__restrict__ send_mult, const double4 *__restrict__ pos,
+                                                      const double *__restrict__ vel, double *__restrict__ buf) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if(e >= count) { return; }
+    const int p = send_map[e];
+    const double4 x = pos[p];
+    double *b = buf + (size_t) e * SYNC_ELEMS;
+    b[0] = __dadd_rn(x.x, __dmul_rn((double) send_mult[e * 3 + 0], box.len[0]));
+    b[1] = __dadd_rn(x.y, __dmul_rn((double) send_mult[e * 3 + 1], box.len[1]));
+    b[2] = __dadd_rn(x.z, __dmul_rn((double) send_mult[e * 3 + 2], box.len[2]));
+    b[3] = vel[p];
+    b[4] = vel[cap + p];
+    b[5] = vel[2 * cap + p];
+}
+
+__global__ void __launch_bounds__(256) pb_k_unpack_sync(int count, int dst0, int cap, const double *__restrict__ buf,
+                                                        double4 *__restrict__ pos, double *__restrict__ vel) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    const double *b = buf + (size_t) k * SYNC_ELEMS;
+    const int p = dst0 + k;
+    const double w = pos[p].w;
+    pos[p] = make_double4(b[0], b[1], b[2], w);
+    vel[p] = b[3];
+    vel[cap + p] = b[4];
+    vel[2 * cap + p] = b[5];
+}
+
+extern "C" int pb_synchronize(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "synchronize");
+    if(ctx->nsend_all > 0) {
+        PB_LAUNCH(pb_k_pack_sync, pb_blocks(ctx->nsend_all, 256), 256, ctx->nsend_all, ctx->pcap, pb_box(ctx), ctx->send_map,
+                  ctx->send_mult, ctx->pos, ctx->vel, ctx->send_buf);
+    }
+    const double *src = nullptr;
+    PB_TRY(pb_transport_data(ctx, 0, 3, SYNC_ELEMS, &src));
+    if(ctx->nghost > 0) {
+        PB_LAUNCH(pb_k_unpack_sync, pb_blocks(ctx->nghost, 256), 256, ctx->nghost, ctx->nlocal, ctx->pcap, src, ctx->pos, ctx->vel);
+    }
+    return 0;
+}
+
+// ---- exchange ----------------------------------------------------------------------------------------------
+// Single rank in a dimension: "leaving" through a face means re-entering through the opposite one, i.e.
+// position += pbc * L applied in place (what pack (comm.py:320-321) + self-copy + unpack produce).  Side 0 and
+// side 1 are decided from the position BEFORE the shift, as the reference determines both sides before packing.
+__global__ void __launch_bounds__(256) pb_k_wrap(int nlocal, int dim, double lo, double hi, int do_lo, int do_hi, double shift_lo,
+                                                 double shift_hi, const int *__restrict__ flags, double4 *__restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal || (flags[i] & (PB_FLAG_INFINITE | PB_FLAG_GLOBAL)) != 0) { return; }
+    double4 p = pos[i];
+    const double x = (dim == 0) ? p.x : ((dim == 1) ? p.y : p.z);
+    double nx = x;
+    if(do_lo && x < lo) { nx = __dadd_rn(x, shift_lo); }
+    else if(do_hi && x > hi) { nx = __dadd_rn(x, shift_hi); }
+    else { return; }
+    // the other two axes get "+ 0 * L" in the reference: x + 0.0 == x bit-for-bit except for -0.0, which cannot be
+    // told apart numerically; they are left untouched
+    if(dim == 0) { p.x = nx; } else if(dim == 1) { p.y = nx; } else { p.z = nx; }
+    pos[i] = p;
+}
+
+int pb_exchange_multi(pb_ctx *ctx, int dim);
+
+extern "C" int pb_exchange(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "exchange");
+    if(!ctx->domain_set || !ctx->cells_set) { ctx->set_error("pb_exchange: domain / cells not initialised"); return -1; }
+    // ghosts are discarded by the reference at this point as well (nghost = 0, comm.py:108)
+    ctx->nghost = 0;
+    ctx->nsend_all = 0;
+    ctx->cells_n = 0;
+    ctx->neigh_n = -1;
+    for(int dim = 0; dim < 3; dim++) {
+        if(ctx->nranks[dim] == 1) {
+            if(ctx->nlocal == 0) { continue; }
+            const double L = ctx->grid[dim * 2 + 1] - ctx->grid[dim * 2];
+            const int do_lo = ctx->pbc_flag[dim] || ctx->pbc[dim * 2] == 0;
+            const int do_hi = ctx->pbc_flag[dim] || ctx->pbc[dim * 2 + 1] == 0;
+            PB_LAUNCH(pb_k_wrap, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, dim, ctx->subdom[dim * 2], ctx->subdom[dim * 2 + 1],
+                      do_lo, do_hi, (double) ctx->pbc[dim * 2] * L, (double) ctx->pbc[dim * 2 + 1] * L, ctx->flags, ctx->pos);
+        } else {
+            PB_TRY(pb_exchange_multi(ctx, dim));
+        }
+    }
+    // cell-order reordering of the locals (north-star item a): the reference permutes locals here too (hole filling,
+    // comm.py:445-506); ours is a stable counting sort on the flat cell index
+    PB_TRY(pb_sort_locals(ctx));
+    return 0;
+}

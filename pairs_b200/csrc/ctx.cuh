@@ -1,0 +1,159 @@
+// Internal context of libpairs_b200.so (see include/pairs_b200.h for the public C-ABI).
+//
+// Device data layout (all owned by the context; the reference's AoS host layout exists only at the
+// upload/download boundary):
+//   pos    double4[pcap]      x, y, z, w = particle type in the low 32 bits (so a neighbour gather is ONE
+//                             32-byte sector: position and the index into the epsilon/sigma6 tables)
+//   vel    double[3][pcap]    SoA, coalesced streaming in the integrators
+//   force  double[3][pcap]    SoA
+//   mass   double[pcap];  type/flags/uid/shape/tag  int[pcap]
+//   [0, nlocal) are this rank's particles in CELL ORDER (sorted by the reference's flat cell index,
+//   ties by previous index: a stable, deterministic counting sort); [nlocal, nlocal+nghost) are ghosts.
+//   neigh  int[ncap][pitch]   padded column-major (ELLPACK) neighbour lists, pitch = nlocal rounded to 32
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pairs_b200.h"
+
+#define PB_CHECK(call)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if(e_ != cudaSuccess) {                                                                                \
+            ctx->set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" +        \
+                           std::to_string(__LINE__) + ")");                                                    \
+            return -1;                                                                                         \
+        }                                                                                                      \
+    } while(0)
+
+#define PB_TRY(expr)                   \
+    do {                               \
+        int rc_ = (expr);              \
+        if(rc_ < 0) { return rc_; }    \
+    } while(0)
+
+struct PbTimer {
+    double ms = 0.0;
+    long calls = 0;
+};
+
+struct pb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long launches = 0;
+
+    // ---- domain (runtime/domain/regular_6d_stencil.cpp) ----
+    bool domain_set = false;
+    double grid[6] = {0, 0, 0, 0, 0, 0};
+    int pbc_flag[3] = {1, 1, 1};
+    int partitioner = 0, world = 1, rank = 0;
+    int nranks[3] = {1, 1, 1}, coords[3] = {0, 0, 0};
+    int neighbor_ranks[6] = {0, 0, 0, 0, 0, 0}, pbc[6] = {1, -1, 1, -1, 1, -1};
+    double subdom[6] = {0, 0, 0, 0, 0, 0};
+
+    // ---- particles ----
+    int pcap = 0, nlocal = 0, nghost = 0;
+    int tag_base = 0;
+    double4 *pos = nullptr, *pos_alt = nullptr;
+    double *vel = nullptr, *vel_alt = nullptr, *force = nullptr;
+    double *mass = nullptr, *mass_alt = nullptr;
+    int *type = nullptr, *type_alt = nullptr, *flags = nullptr, *flags_alt = nullptr;
+    int *uid = nullptr, *uid_alt = nullptr, *shape = nullptr, *shape_alt = nullptr, *tag = nullptr, *tag_alt = nullptr;
+    bool force_is_zero = false;   // reset_volatile requested and not yet materialised (fused into the force kernel)
+
+    // ---- cells (sim/cell_lists.py) ----
+    bool cells_set = false;
+    double spacing = 0.0;
+    int dim_cells[3] = {0, 0, 0}, ncells = 0, stencil[27];
+    int ccap = 0;                 // capacity of per-cell arrays
+    int *particle_cell = nullptr; // [pcap]
+    int *cell_count = nullptr;    // [ccap+1]
+    int *cell_start = nullptr;    // [ccap+1]
+    int *cell_slot = nullptr;     // [pcap] slot of the particle inside its cell (arrival order, sorted later)
+    int *cell_list = nullptr;     // [pcap]
+    int *scan_tmp = nullptr;      // block sums for the scan
+    int scan_tmp_cap = 0;
+    int cells_n = 0;              // number of particles binned by the last pb_build_cell_lists
+
+    // ---- neighbour lists (sim/neighbor_lists.py) ----
+    int ncap = 0, pitch = 0, max_neigh = 0;
+    size_t neigh_bytes = 0;
+    int *neigh = nullptr, *numneigh = nullptr;
+    int neigh_n = 0;              // nlocal at build time
+
+    // ---- LJ feature properties ----
+    int ntypes = 0;
+    bool lj_uniform = false;
+    double *d_eps = nullptr, *d_sig6 = nullptr;
+    double h_eps[64], h_sig6[64];
+
+    // ---- comm (sim/comm.py) ----
+    int send_cap = 0;             // entries
+    int nsend_all = 0, nsend[6] = {0, 0, 0, 0, 0, 0}, nrecv[6] = {0, 0, 0, 0, 0, 0};
+    int send_offsets[6] = {0, 0, 0, 0, 0, 0}, recv_offsets[6] = {0, 0, 0, 0, 0, 0};
+    int *send_map = nullptr;      // [send_cap] source index of every send entry (locals or ghosts)
+    int *send_mult = nullptr;     // [send_cap][3]
+    double *send_buf = nullptr, *recv_buf = nullptr; // [send_cap][PB_MAX_ELEMS]
+    int recv_cap = 0;
+    int *sel_flag = nullptr, *sel_scan = nullptr; // [pcap+1] compaction scratch
+    void *nccl = nullptr;         // NcclState* (comm_nccl.cu), null on a single rank
+
+    // ---- reductions / host mirrors ----
+    double *d_partial = nullptr;  // thermo partial sums
+    int d_partial_cap = 0;
+    int *d_scalars = nullptr;     // small device scratch: [0] max neighbours, [1..] counters
+    int *h_scalars = nullptr;     // pinned mirror
+
+    // ---- timers ----
+    bool timers_on = false;
+    std::map<std::string, PbTimer> timers;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    void set_error(const std::string &e) { err = e; }
+};
+
+static const int PB_MAX_ELEMS = 12;   // doubles per packed particle record (exchange: 12, borders: 11, sync: 6)
+static const int PB_NSCALARS = 16;
+
+// ---- helpers shared by the .cu files ----
+int pb_ensure_particle_capacity(pb_ctx *ctx, int needed);
+int pb_ensure_send_capacity(pb_ctx *ctx, int needed);
+int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n);   // out[0..n], out[n] = total
+int pb_bin_particles(pb_ctx *ctx, int first, int n, bool write_particle_cell);
+
+struct PbStage {
+    pb_ctx *ctx;
+    const char *name;
+    PbStage(pb_ctx *c, const char *n) : ctx(c), name(n) {
+        if(ctx->timers_on) { cudaEventRecord(ctx->ev0, ctx->stream); }
+    }
+    ~PbStage() {
+        if(ctx->timers_on) {
+            cudaEventRecord(ctx->ev1, ctx->stream);
+            cudaEventSynchronize(ctx->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+            PbTimer &t = ctx->timers[name];
+            t.ms += ms;
+            t.calls += 1;
+        }
+    }
+};
+
+static inline int pb_blocks(long n, int threads) { return (int) ((n + threads - 1) / threads); }
+
+#define PB_LAUNCH(kernel, grid, block, ...)                                    \
+    do {                                                                       \
+        kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);              \
+        ctx->launches++;                                                       \
+        PB_CHECK(cudaGetLastError());                                          \
+    } while(0)
+
+// particle type rides in the low 32 bits of pos.w
+__device__ __forceinline__ int pb_w_type(double w) { return (int) (__double_as_longlong(w) & 0xffffffffLL); }
+__device__ __forceinline__ double pb_type_w(int t) { return __longlong_as_double((long long) (unsigned int) t); }

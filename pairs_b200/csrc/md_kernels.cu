@@ -1,0 +1,287 @@
+// Kernels of examples/md.py: Lennard-Jones pair force, velocity-Verlet halves, volatile reset, thermo.
+//
+// Arithmetic contract: every fp64 operation below is written with explicit round-to-nearest intrinsics
+// (__dmul_rn / __dadd_rn / __dsub_rn / __ddiv_rn are never contracted into FMAs) in exactly the order the
+// reference's generator emits them (generated md.cpp lennard_jones / initial_integrate / final_integrate), so each
+// pair term and each integrator update is bit-identical to the reference CPU build compiled with
+// -ffp-contract=off.  The only difference is the ORDER in which a particle's pair terms are summed (our lists are
+// cell-sorted, the reference's follow its own particle numbering): |df| <= ~K * eps * max|f_ij|, tested to 1e-12.
+//
+// Rooflines (B200): the force kernel moves 4*K + ~100 B per particle (K = mean list length) against ~23 fp64
+// instructions per accepted and 9 per rejected pair -- it is co-limited by the fp64 pipe (64 lanes/clk/SM) and
+// the L1 gather path, not by tensor cores (nothing here is a dense contraction).  The integrators are pure
+// streaming kernels (132 B resp. 84 B per particle in the reference's accounting).
+#include <algorithm>
+
+#include "ctx.cuh"
+
+// ---- Lennard-Jones (examples/md.py:5-8, sim/interaction.py:201-292) -------------------------------------------
+// One thread per local particle; neighbour ids are read column-major (coalesced), neighbour positions are
+// gathered as one 32-byte double4 (x, y, z, type) each.  UNROLL independent gathers are in flight per thread.
+template<bool UNIFORM, bool ACCUMULATE, int UNROLL>
+__global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int pitch, int cap, double cutsq, int ntypes,
+                                                          double eps_u, double sig6_u,
+                                                          const double *__restrict__ eps_t, const double *__restrict__ sig6_t,
+                                                          const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                          const int *__restrict__ numneigh, const int *__restrict__ neigh,
+                                                          double *__restrict__ force) {
+    __shared__ double s_eps[64], s_sig6[64];
+    if(!UNIFORM) {
+        for(int k = threadIdx.x; k < ntypes * ntypes; k += blockDim.x) { s_eps[k] = eps_t[k]; s_sig6[k] = sig6_t[k]; }
+        __syncthreads();
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal) { return; }
+    const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    if(!fixed) {
+        const double4 pi = pos[i];
+        const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * ntypes;
+        const int nn = numneigh[i];
+        const int *nb = neigh + i;
+        int k = 0;
+        for(; k + UNROLL <= nn; k += UNROLL) {
+            int j[UNROLL];
+            double4 pj[UNROLL];
+#pragma unroll
+            for(int u = 0; u < UNROLL; u++) { j[u] = __ldg(nb + (size_t) (k + u) * pitch); }
+#pragma unroll
+            for(int u = 0; u < UNROLL; u++) { pj[u] = pos[j[u]]; }
+#pragma unroll
+            for(int u = 0; u < UNROLL; u++) {
+                const double dx = __dsub_rn(pi.x, pj[u].x);
+                const double dy = __dsub_rn(pi.y, pj[u].y);
+                const double dz = __dsub_rn(pi.z, pj[u].z);
+                const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if(rsq < cutsq) {
+                    const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type(pj[u].w)];
+                    const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type(pj[u].w)];
+                    const double sr2 = __ddiv_rn(1.0, rsq);
+                    const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);
+                    const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);
+                    fx = __dadd_rn(fx, __dmul_rn(dx, f));
+                    fy = __dadd_rn(fy, __dmul_rn(dy, f));
+                    fz = __dadd_rn(fz, __dmul_rn(dz, f));
+                }
+            }
+        }
+        for(; k < nn; k++) {
+            const int j = __ldg(nb + (size_t) k * pitch);
+            const double4 pj = pos[j];
+            const double dx = __dsub_rn(pi.x, pj.x);
+            const double dy = __dsub_rn(pi.y, pj.y);
+            const double dz = __dsub_rn(pi.z, pj.z);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if(rsq < cutsq) {
+                const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type(pj.w)];
+                const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type(pj.w)];
+                const double sr2 = __ddiv_rn(1.0, rsq);
+                const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);
+                const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);
+                fx = __dadd_rn(fx, __dmul_rn(dx, f));
+                fy = __dadd_rn(fy, __dmul_rn(dy, f));
+                fz = __dadd_rn(fz, __dmul_rn(dz, f));
+            }
+        }
+    }
+    // force[i] = force[i] + acc (sim/interaction.py:280-292).  When the preceding reset_volatile_properties is fused in
+    // (ACCUMULATE == false) the old value is the freshly written 0.0, also for FIXED particles.
+    if(ACCUMULATE) {
+        if(!fixed) {
+            force[i] = __dadd_rn(force[i], fx);
+            force[cap + i] = __dadd_rn(force[cap + i], fy);
+            force[2 * cap + i] = __dadd_rn(force[2 * cap + i], fz);
+        }
+    } else {
+        force[i] = __dadd_rn(0.0, fx);
+        force[cap + i] = __dadd_rn(0.0, fy);
+        force[2 * cap + i] = __dadd_rn(0.0, fz);
+    }
+}
+
+extern "C" int pb_set_lj_params(pb_ctx *ctx, int ntypes, const double *epsilon, const double *sigma6) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(ntypes < 1 || ntypes > 8) { ctx->set_error("pb_set_lj_params: 1 <= ntypes <= 8 supported"); return -1; }
+    ctx->ntypes = ntypes;
+    const int n2 = ntypes * ntypes;
+    bool uniform = true;
+    for(int k = 0; k < n2; k++) {
+        ctx->h_eps[k] = epsilon[k];
+        ctx->h_sig6[k] = sigma6[k];
+        uniform = uniform && epsilon[k] == epsilon[0] && sigma6[k] == sigma6[0];
+    }
+    ctx->lj_uniform = uniform;   // same table entry for every type pair: skip the lookups (result is bit-identical)
+    if(ctx->d_eps == nullptr) {
+        PB_CHECK(cudaMalloc(&ctx->d_eps, sizeof(double) * 64));
+        PB_CHECK(cudaMalloc(&ctx->d_sig6, sizeof(double) * 64));
+    }
+    PB_CHECK(cudaMemcpyAsync(ctx->d_eps, ctx->h_eps, sizeof(double) * n2, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(ctx->d_sig6, ctx->h_sig6, sizeof(double) * n2, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ResetVolatileProperties (sim/properties.py:61-70) is deferred and fused into the next force kernel.
+extern "C" int pb_reset_volatile(pb_ctx *ctx) {
+    ctx->force_is_zero = true;
+    return 0;
+}
+
+int pb_materialise_force_reset(pb_ctx *ctx) {
+    if(ctx->force_is_zero) {
+        for(int d = 0; d < 3; d++) {
+            PB_CHECK(cudaMemsetAsync(ctx->force + (size_t) d * ctx->pcap, 0, sizeof(double) * (size_t) ctx->nlocal, ctx->stream));
+        }
+        ctx->force_is_zero = false;
+    }
+    return 0;
+}
+
+extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "lennard_jones");
+    if(ctx->ntypes == 0) { ctx->set_error("pb_lennard_jones: pb_set_lj_params not called"); return -1; }
+    if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_lennard_jones: neighbour lists are stale"); return -1; }
+    const int n = ctx->nlocal;
+    if(n == 0) { return 0; }
+    const double cutsq = cutoff * cutoff;
+    const int T = 128, B = pb_blocks(n, T);
+    const bool acc = !ctx->force_is_zero;
+#define PB_LJ(UNI, ACC)                                                                                                   \
+    PB_LAUNCH((pb_k_lennard_jones<UNI, ACC, 4>), B, T, n, ctx->pitch, ctx->pcap, cutsq, ctx->ntypes, ctx->h_eps[0],       \
+              ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh, ctx->force)
+    if(ctx->lj_uniform) {
+        if(acc) { PB_LJ(true, true); } else { PB_LJ(true, false); }
+    } else {
+        if(acc) { PB_LJ(false, true); } else { PB_LJ(false, false); }
+    }
+#undef PB_LJ
+    ctx->force_is_zero = false;
+    return 0;
+}
+
+// ---- velocity Verlet (examples/md.py:11-17) -------------------------------------------------------------------
+// v += ((dt*0.5) * f) / m   (multiplication first, division last, per component);   x += dt * v
+template<bool WITH_POSITION>
+__global__ void __launch_bounds__(256) pb_k_integrate(int nlocal, int cap, double dt, double half_dt, const int *__restrict__ flags,
+                                                      const double *__restrict__ force, const double *__restrict__ mass,
+                                                      double *__restrict__ vel, double4 *__restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal || (flags[i] & PB_FLAG_FIXED) != 0) { return; }
+    const double m = mass[i];
+    const double vx = __dadd_rn(vel[i], __ddiv_rn(__dmul_rn(half_dt, force[i]), m));
+    const double vy = __dadd_rn(vel[cap + i], __ddiv_rn(__dmul_rn(half_dt, force[cap + i]), m));
+    const double vz = __dadd_rn(vel[2 * cap + i], __ddiv_rn(__dmul_rn(half_dt, force[2 * cap + i]), m));
+    vel[i] = vx;
+    vel[cap + i] = vy;
+    vel[2 * cap + i] = vz;
+    if(WITH_POSITION) {
+        double4 p = pos[i];
+        p.x = __dadd_rn(p.x, __dmul_rn(dt, vx));
+        p.y = __dadd_rn(p.y, __dmul_rn(dt, vy));
+        p.z = __dadd_rn(p.z, __dmul_rn(dt, vz));
+        pos[i] = p;
+    }
+}
+
+extern "C" int pb_initial_integrate(pb_ctx *ctx, double dt) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "initial_integrate");
+    PB_TRY(pb_materialise_force_reset(ctx));
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_integrate<true>, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, dt, dt * 0.5, ctx->flags, ctx->force,
+              ctx->mass, ctx->vel, ctx->pos);
+    return 0;
+}
+
+extern "C" int pb_final_integrate(pb_ctx *ctx, double dt) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "final_integrate");
+    PB_TRY(pb_materialise_force_reset(ctx));
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_integrate<false>, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, dt, dt * 0.5, ctx->flags, ctx->force,
+              ctx->mass, ctx->vel, ctx->pos);
+    return 0;
+}
+
+// ---- thermo (runtime/thermo.hpp:11-51) ------------------------------------------------------------------------
+// t = sum_i m_i * (vx*vx + vy*vy + vz*vz): per-thread terms exactly as the reference, summed by a fixed-shape tree
+// (warp shuffles -> per-block partials -> one final block), so the result is run-to-run reproducible; it differs from
+// the reference's serial left-to-right sum by reduction order only (tested to 1e-9 relative, typically ~1e-15).
+static const int THERMO_T = 256;
+
+__global__ void __launch_bounds__(THERMO_T) pb_k_thermo_partial(int nlocal, int cap, const double *__restrict__ mass,
+                                                                const double *__restrict__ vel, double *__restrict__ partial) {
+    __shared__ double s[THERMO_T / 32];
+    double t = 0.0;
+    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+        const double vx = vel[i], vy = vel[cap + i], vz = vel[2 * cap + i];
+        const double e = __dmul_rn(mass[i], __dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
+        t = __dadd_rn(t, e);
+    }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, o)); }
+    if((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5] = t; }
+    __syncthreads();
+    if(threadIdx.x < 32) {
+        double w = (threadIdx.x < THERMO_T / 32) ? s[threadIdx.x] : 0.0;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { w = __dadd_rn(w, __shfl_down_sync(0xffffffffu, w, o)); }
+        if(threadIdx.x == 0) { partial[blockIdx.x] = w; }
+    }
+}
+
+__global__ void __launch_bounds__(THERMO_T) pb_k_thermo_final(int nparts, const double *__restrict__ partial, double *__restrict__ out) {
+    __shared__ double s[THERMO_T / 32];
+    double t = 0.0;
+    for(int i = threadIdx.x; i < nparts; i += blockDim.x) { t = __dadd_rn(t, partial[i]); }
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { t = __dadd_rn(t, __shfl_down_sync(0xffffffffu, t, o)); }
+    if((threadIdx.x & 31) == 0) { s[threadIdx.x >> 5] = t; }
+    __syncthreads();
+    if(threadIdx.x < 32) {
+        double w = (threadIdx.x < THERMO_T / 32) ? s[threadIdx.x] : 0.0;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { w = __dadd_rn(w, __shfl_down_sync(0xffffffffu, w, o)); }
+        if(threadIdx.x == 0) { out[0] = w; }
+    }
+}
+
+extern "C" int pb_thermo_partial(pb_ctx *ctx, double *sum_mv2, int *natoms) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "compute_thermo");
+    const int nparts = 592;   // 4 blocks per SM on 148 SMs
+    if(ctx->d_partial == nullptr) {
+        PB_CHECK(cudaMalloc(&ctx->d_partial, sizeof(double) * (nparts + 8)));
+        ctx->d_partial_cap = nparts + 8;
+    }
+    double h = 0.0;
+    if(ctx->nlocal > 0) {
+        PB_LAUNCH(pb_k_thermo_partial, nparts, THERMO_T, ctx->nlocal, ctx->pcap, ctx->mass, ctx->vel, ctx->d_partial);
+        PB_LAUNCH(pb_k_thermo_final, 1, THERMO_T, nparts, ctx->d_partial, ctx->d_partial + nparts);
+        PB_CHECK(cudaMemcpyAsync(&h, ctx->d_partial + nparts, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    *sum_mv2 = h;
+    *natoms = ctx->nlocal;
+    return 0;
+}
+
+int pb_allreduce_thermo(pb_ctx *ctx, double *sum_mv2, long *natoms);
+
+extern "C" int pb_compute_thermo(pb_ctx *ctx, double *temperature, double *pressure) {
+    double t = 0.0;
+    int nl = 0;
+    PB_TRY(pb_thermo_partial(ctx, &t, &nl));
+    long natoms = nl;
+    if(ctx->world > 1) { PB_TRY(pb_allreduce_thermo(ctx, &t, &natoms)); }
+    const double xprd = ctx->grid[1] - ctx->grid[0], yprd = ctx->grid[3] - ctx->grid[2], zprd = ctx->grid[5] - ctx->grid[4];
+    const double mvv2e = 1.0;
+    const double dof_boltz = (double) (natoms * 3 - 3);
+    const double t_scale = mvv2e / dof_boltz;
+    const double p_scale = 1.0 / 3 / xprd / yprd / zprd;
+    t = t * t_scale;
+    if(temperature != nullptr) { *temperature = t; }
+    if(pressure != nullptr) { *pressure = (t * dof_boltz) * p_scale; }
+    return 0;
+}

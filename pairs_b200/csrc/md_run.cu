@@ -1,0 +1,40 @@
+// The generated timestep loop of examples/md.py, run natively: sim/timestep.py:9-72 (loop of nsteps+1 iterations,
+// guards `every` -> ((ts+1) % n == 0) || ts == 0 and `skip_first` -> ts > 0) around the per-step procedure list of
+// sim/simulation.py:387-417:  pre_step kernels (initial_integrate) -> exchange + borders | synchronize ->
+// build_cell_lists -> partition_cell_lists -> build_neighbor_lists -> reset_volatile_properties -> lennard_jones ->
+// final_integrate -> compute_thermo.  Everything stays on the device; only thermo scalars (every `thermo_every`
+// steps) and capacity counters (every reneighbouring) are read back.
+#include "ctx.cuh"
+
+extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->cells_set || ctx->spacing != p->cell_spacing) { PB_TRY(pb_setup_cells(ctx, p->cell_spacing)); }
+    int nt = 0;
+    for(int ts = ts_begin; ts < ts_end; ts++) {
+        const bool reneigh = (((ts + 1) % p->reneighbor_every) == 0) || (ts == 0);
+        if(ts > 0) { PB_TRY(pb_initial_integrate(ctx, p->dt)); }
+        if(reneigh) {
+            PB_TRY(pb_exchange(ctx));
+            PB_TRY(pb_borders(ctx));
+            PB_TRY(pb_build_cell_lists(ctx));
+            PB_TRY(pb_build_neighbor_lists(ctx, p->cutoff_lists));
+        } else {
+            PB_TRY(pb_synchronize(ctx));
+        }
+        PB_TRY(pb_reset_volatile(ctx));
+        PB_TRY(pb_lennard_jones(ctx, p->cutoff_force));
+        if(ts > 0) { PB_TRY(pb_final_integrate(ctx, p->dt)); }
+        if(p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0)) {
+            double t = 0.0, pr = 0.0;
+            PB_TRY(pb_compute_thermo(ctx, &t, &pr));
+            if(thermo_out != nullptr && nt < thermo_cap) {
+                thermo_out[nt * 3 + 0] = (double) ts;
+                thermo_out[nt * 3 + 1] = t;
+                thermo_out[nt * 3 + 2] = pr;
+            }
+            nt++;
+        }
+    }
+    if(n_thermo != nullptr) { *n_thermo = nt; }
+    return 0;
+}

@@ -1,0 +1,178 @@
+// Particle migration between ranks: the multi-rank branch of Comm.exchange (sim/comm.py:100-151) for one
+// dimension.  Reference: determine_exchange_particles (atomics) -> pack -> remove_exchanged_particles pt1 (HOST loop)
+// + pt2 (hole filling from the tail) -> MPI -> unpack (append).  Here: ordered select of the leavers, pack, an
+// ordered stream compaction of the stayers (device only, no host loop), NCCL, append.  The resulting SET of local
+// particles per rank is the reference's; their order is ours (and is replaced by cell order right afterwards).
+#include <algorithm>
+
+#include "ctx.cuh"
+
+int pb_transport_sizes(pb_ctx *ctx, int dim);
+int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const double **recv_src);
+
+static const int EXCH_ELEMS = 12;
+
+struct PbBox3 {
+    double len[3];
+};
+
+__global__ void __launch_bounds__(256) pb_k_sel_leave(int n, int dim, double lo, double hi, int do_lo, int do_hi,
+                                                      const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                      int *__restrict__ sel_lo, int *__restrict__ sel_hi, int *__restrict__ stay) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    int a = 0, b = 0;
+    if((flags[i] & (PB_FLAG_INFINITE | PB_FLAG_GLOBAL)) == 0) {
+        const double4 p = pos[i];
+        const double x = (dim == 0) ? p.x : ((dim == 1) ? p.y : p.z);
+        a = do_lo && (x < lo);
+        b = do_hi && (x > hi);
+    }
+    sel_lo[i] = a;
+    sel_hi[i] = b;
+    stay[i] = !(a || b);
+}
+
+__global__ void __launch_bounds__(256) pb_k_pack_exchange(int n, int cap, int dim, int mult_lo, int mult_hi, int base_hi, double len,
+                                                          const int *__restrict__ sel_lo, const int *__restrict__ scan_lo,
+                                                          const int *__restrict__ sel_hi, const int *__restrict__ scan_hi,
+                                                          const double4 *__restrict__ pos, const double *__restrict__ vel,
+                                                          const double *__restrict__ mass, const int *__restrict__ flags,
+                                                          const int *__restrict__ uid, const int *__restrict__ shape,
+                                                          const int *__restrict__ tag, double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    int e, mult;
+    if(sel_lo[i]) { e = scan_lo[i]; mult = mult_lo; }
+    else if(sel_hi[i]) { e = base_hi + scan_hi[i]; mult = mult_hi; }
+    else { return; }
+    const double4 x = pos[i];
+    const double sh = __dmul_rn((double) mult, len);
+    double *b = buf + (size_t) e * EXCH_ELEMS;
+    b[0] = (double) uid[i];
+    b[1] = (double) shape[i];
+    b[2] = (double) flags[i];
+    b[3] = (dim == 0) ? __dadd_rn(x.x, sh) : x.x;
+    b[4] = (dim == 1) ? __dadd_rn(x.y, sh) : x.y;
+    b[5] = (dim == 2) ? __dadd_rn(x.z, sh) : x.z;
+    b[6] = mass[i];
+    b[7] = vel[i];
+    b[8] = vel[cap + i];
+    b[9] = vel[2 * cap + i];
+    b[10] = (double) pb_w_type(x.w);
+    b[11] = (double) tag[i];
+}
+
+__global__ void __launch_bounds__(256) pb_k_compact(int n, int cap, const int *__restrict__ stay, const int *__restrict__ scan,
+                                                    const double4 *__restrict__ pos, double4 *__restrict__ pos_o,
+                                                    const double *__restrict__ vel, double *__restrict__ vel_o,
+                                                    const double *__restrict__ mass, double *__restrict__ mass_o,
+                                                    const int *__restrict__ type, int *__restrict__ type_o,
+                                                    const int *__restrict__ flags, int *__restrict__ flags_o,
+                                                    const int *__restrict__ uid, int *__restrict__ uid_o,
+                                                    const int *__restrict__ shape, int *__restrict__ shape_o,
+                                                    const int *__restrict__ tag, int *__restrict__ tag_o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || !stay[i]) { return; }
+    const int k = scan[i];
+    pos_o[k] = pos[i];
+    vel_o[k] = vel[i];
+    vel_o[cap + k] = vel[cap + i];
+    vel_o[2 * cap + k] = vel[2 * cap + i];
+    mass_o[k] = mass[i];
+    type_o[k] = type[i];
+    flags_o[k] = flags[i];
+    uid_o[k] = uid[i];
+    shape_o[k] = shape[i];
+    tag_o[k] = tag[i];
+}
+
+__global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0, int cap, const double *__restrict__ buf,
+                                                            double4 *__restrict__ pos, double *__restrict__ vel,
+                                                            double *__restrict__ mass, int *__restrict__ type, int *__restrict__ flags,
+                                                            int *__restrict__ uid, int *__restrict__ shape, int *__restrict__ tag) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    const double *b = buf + (size_t) k * EXCH_ELEMS;
+    const int p = dst0 + k;
+    const int t = (int) b[10];
+    uid[p] = (int) b[0];
+    shape[p] = (int) b[1];
+    flags[p] = (int) b[2];
+    pos[p] = make_double4(b[3], b[4], b[5], pb_type_w(t));
+    mass[p] = b[6];
+    vel[p] = b[7];
+    vel[cap + p] = b[8];
+    vel[2 * cap + p] = b[9];
+    type[p] = t;
+    tag[p] = (int) b[11];
+}
+
+int pb_exchange_multi(pb_ctx *ctx, int dim) {
+    const int n = ctx->nlocal;
+    const int j0 = dim * 2, j1 = dim * 2 + 1;
+    const int do_lo = ctx->pbc_flag[dim] || ctx->pbc[j0] == 0;
+    const int do_hi = ctx->pbc_flag[dim] || ctx->pbc[j1] == 0;
+    // scratch: sel_lo = sel_flag, sel_hi / stay / scans live in cell_slot, cell_list, particle_cell, sel_scan (all [pcap])
+    int *sel_lo = ctx->sel_flag, *sel_hi = ctx->cell_slot, *stay = ctx->cell_list;
+    int *scan_lo = ctx->sel_scan, *scan_hi = ctx->particle_cell;
+    int *scan_stay = nullptr;
+    PB_CHECK(cudaMalloc(&scan_stay, sizeof(int) * ((size_t) n + 1)));
+    int *scan_hi_full = nullptr;
+    PB_CHECK(cudaMalloc(&scan_hi_full, sizeof(int) * ((size_t) n + 1)));
+    scan_hi = scan_hi_full;
+    for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
+    int c_lo = 0, c_hi = 0, c_stay = 0;
+    if(n > 0) {
+        PB_LAUNCH(pb_k_sel_leave, pb_blocks(n, 256), 256, n, dim, ctx->subdom[j0], ctx->subdom[j1], do_lo, do_hi, ctx->pos, ctx->flags,
+                  sel_lo, sel_hi, stay);
+        PB_TRY(pb_exclusive_scan(ctx, sel_lo, scan_lo, n));
+        PB_TRY(pb_exclusive_scan(ctx, sel_hi, scan_hi, n));
+        PB_TRY(pb_exclusive_scan(ctx, stay, scan_stay, n));
+        PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 0, scan_lo + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 1, scan_hi + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 2, scan_stay + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        c_lo = ctx->h_scalars[0]; c_hi = ctx->h_scalars[1]; c_stay = ctx->h_scalars[2];
+    }
+    ctx->nsend[j0] = c_lo;
+    ctx->nsend[j1] = c_hi;
+    ctx->send_offsets[j0] = 0;
+    ctx->send_offsets[j1] = c_lo;
+    PB_TRY(pb_ensure_send_capacity(ctx, c_lo + c_hi));
+    if(c_lo + c_hi > 0) {
+        const double len = ctx->grid[dim * 2 + 1] - ctx->grid[dim * 2];
+        PB_LAUNCH(pb_k_pack_exchange, pb_blocks(n, 256), 256, n, ctx->pcap, dim, ctx->pbc[j0], ctx->pbc[j1], c_lo, len, sel_lo, scan_lo,
+                  sel_hi, scan_hi, ctx->pos, ctx->vel, ctx->mass, ctx->flags, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf);
+    }
+    PB_TRY(pb_transport_sizes(ctx, dim));
+    ctx->recv_offsets[j0] = 0;
+    ctx->recv_offsets[j1] = ctx->nrecv[j0];
+    const int nr = ctx->nrecv[j0] + ctx->nrecv[j1];
+    PB_TRY(pb_ensure_particle_capacity(ctx, c_stay + nr));
+    if(n > 0 && c_stay < n) {
+        PB_LAUNCH(pb_k_compact, pb_blocks(n, 256), 256, n, ctx->pcap, stay, scan_stay, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
+                  ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape,
+                  ctx->shape_alt, ctx->tag, ctx->tag_alt);
+        std::swap(ctx->pos, ctx->pos_alt);
+        std::swap(ctx->vel, ctx->vel_alt);
+        std::swap(ctx->mass, ctx->mass_alt);
+        std::swap(ctx->type, ctx->type_alt);
+        std::swap(ctx->flags, ctx->flags_alt);
+        std::swap(ctx->uid, ctx->uid_alt);
+        std::swap(ctx->shape, ctx->shape_alt);
+        std::swap(ctx->tag, ctx->tag_alt);
+    }
+    const double *src = nullptr;
+    PB_TRY(pb_transport_data(ctx, dim, dim + 1, EXCH_ELEMS, &src));
+    if(nr > 0) {
+        PB_LAUNCH(pb_k_unpack_exchange, pb_blocks(nr, 256), 256, nr, c_stay, ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type,
+                  ctx->flags, ctx->uid, ctx->shape, ctx->tag);
+    }
+    ctx->nlocal = c_stay + nr;
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    PB_CHECK(cudaFree(scan_stay));
+    PB_CHECK(cudaFree(scan_hi_full));
+    for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
+    return 0;
+}

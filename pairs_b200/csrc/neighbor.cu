@@ -1,0 +1,132 @@
+// Neighbour-list build: full Verlet lists in padded column-major (ELLPACK) storage.
+// Replaces BuildNeighborLists (sim/neighbor_lists.py:21-48, loop nest sim/interaction.py:91-120).
+//
+// Reference semantics kept exactly: for every local, non-FIXED particle i visit cell 0 (INFINITE particles) and the
+// 27 stencil cells `particle_cell[i] + stencil[k]` that satisfy 0 < cell < ncells (flat-index test only, no per-axis
+// wrap test), and append every j != i with  (dx*dx + dy*dy) + dz*dz < cutoff^2  (separate fp64 multiplies and adds,
+// no FMA contraction) -- so the neighbour SETS are bit-identical to the reference's.  Storage differs:
+//   neigh[k * pitch + i]  (k-th neighbour of i; a warp reads 32 consecutive ints per k) instead of AoS [i][k];
+//   inside a list, neighbours are in ascending cell order, and ascending index inside a cell (deterministic).
+// The three z-adjacent stencil cells of one (dx,dy) row are consecutive flat indices, so each row is ONE
+// contiguous run of the CSR cell list: 9 runs + cell 0 per particle.
+//
+// HBM bytes per local particle: pos 32 + cell 4 + list write 4*K + count 4; candidates (~27 cells * occupancy)
+// are served from L1/L2 because the 32 lanes of a warp sit in the same 1-3 cells.
+#include <algorithm>
+
+#include "ctx.cuh"
+
+template<bool STORE>
+__global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncells, int dim1, int dim2, int ncap, int pitch,
+                                                            double cutsq, const double4 *__restrict__ pos,
+                                                            const int *__restrict__ flags, const int *__restrict__ particle_cell,
+                                                            const int *__restrict__ cell_start, const int *__restrict__ cell_list,
+                                                            int *__restrict__ neigh, int *__restrict__ numneigh,
+                                                            int *__restrict__ max_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int count = 0;
+    if(i < nlocal && (flags[i] & PB_FLAG_FIXED) == 0) {
+        const double4 pi = pos[i];
+        const int pc = particle_cell[i];
+        // run 0: cell 0; runs 1..9: rows (dx,dy) in stencil order, each covering dz = -1,0,+1
+        for(int run = 0; run < 10; run++) {
+            int c_lo, c_hi;   // inclusive cell range of this run
+            if(run == 0) {
+                c_lo = 0; c_hi = 0;
+            } else {
+                const int r = run - 1;
+                const int mid = pc + ((r / 3 - 1) * dim1 + (r % 3 - 1)) * dim2;
+                c_lo = max(mid - 1, 1);
+                c_hi = min(mid + 1, ncells - 1);
+                if(c_lo > c_hi) { continue; }
+            }
+            const int b = cell_start[c_lo], e = cell_start[c_hi + 1];
+            for(int k = b; k < e; k++) {
+                const int j = cell_list[k];
+                if(j == i) { continue; }
+                const double4 pj = pos[j];
+                const double dx = __dsub_rn(pi.x, pj.x);
+                const double dy = __dsub_rn(pi.y, pj.y);
+                const double dz = __dsub_rn(pi.z, pj.z);
+                const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if(rsq < cutsq) {
+                    if(STORE && count < ncap) { neigh[(size_t) count * pitch + i] = j; }
+                    count++;
+                }
+            }
+        }
+    }
+    if(i < nlocal) { numneigh[i] = count; }
+    // block-wide max -> one atomic per warp
+    int m = count;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+    if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(max_count, m); }
+}
+
+static int pb_alloc_neigh(pb_ctx *ctx, int ncap, int pitch) {
+    const size_t bytes = sizeof(int) * (size_t) ncap * (size_t) pitch;
+    if(bytes > ctx->neigh_bytes) {
+        if(ctx->neigh != nullptr) { PB_CHECK(cudaFree(ctx->neigh)); ctx->neigh = nullptr; }
+        const size_t want = bytes + bytes / 8;
+        PB_CHECK(cudaMalloc(&ctx->neigh, want));
+        ctx->neigh_bytes = want;
+    }
+    return 0;
+}
+
+extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "build_neighbor_lists");
+    if(ctx->cells_n != ctx->nlocal + ctx->nghost) {
+        ctx->set_error("pb_build_neighbor_lists: cell lists are stale (call pb_build_cell_lists first)");
+        return -1;
+    }
+    const int n = ctx->nlocal;
+    ctx->neigh_n = n;
+    if(n == 0) { ctx->max_neigh = 0; return 0; }
+    const double cutsq = cutoff * cutoff;
+    const int pitch = (n + 31) / 32 * 32;
+    if(ctx->ncap <= 0) { ctx->ncap = 100; }   // neighbor_capacity default of pairs.simulation() (src/pairs/__init__.py:16)
+    for(int attempt = 0; attempt < 8; attempt++) {
+        PB_TRY(pb_alloc_neigh(ctx, ctx->ncap, pitch));
+        ctx->pitch = pitch;
+        PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
+        PB_LAUNCH(pb_k_build_neighbors<true>, pb_blocks(n, 128), 128, n, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], ctx->ncap,
+                  pitch, cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->neigh, ctx->numneigh,
+                  ctx->d_scalars);
+        PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->max_neigh = ctx->h_scalars[0];
+        if(ctx->max_neigh <= ctx->ncap) { return 0; }
+        // capacity-overflow protocol (transformations/modules.py:159-203): grow to twice the need and re-run the module
+        ctx->ncap = ctx->max_neigh * 2;
+    }
+    ctx->set_error("pb_build_neighbor_lists: capacity did not converge");
+    return -1;
+}
+
+extern "C" int pb_neighbor_capacity(const pb_ctx *ctx) { return ctx->ncap; }
+extern "C" int pb_max_neighbors(const pb_ctx *ctx) { return ctx->max_neigh; }
+
+__global__ void pb_k_neigh_to_aos(int n, int cap_out, int ncap, int pitch, const int *__restrict__ neigh,
+                                  const int *__restrict__ numneigh, int *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    const int c = min(numneigh[i], min(cap_out, ncap));
+    for(int k = 0; k < c; k++) { out[(size_t) i * cap_out + k] = neigh[(size_t) k * pitch + i]; }
+    for(int k = c; k < cap_out; k++) { out[(size_t) i * cap_out + k] = -1; }
+}
+
+extern "C" int pb_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    const int n = ctx->neigh_n;
+    if(n == 0) { return 0; }
+    int *stage = nullptr;
+    PB_CHECK(cudaMalloc(&stage, sizeof(int) * (size_t) n * (size_t) capacity));
+    PB_LAUNCH(pb_k_neigh_to_aos, pb_blocks(n, 128), 128, n, capacity, ctx->ncap, ctx->pitch, ctx->neigh, ctx->numneigh, stage);
+    PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(int) * (size_t) n * (size_t) capacity, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    PB_CHECK(cudaFree(stage));
+    return 0;
+}

@@ -1,0 +1,235 @@
+"""GPU parity tests of the MD (Lennard-Jones) path: CUDA kernels through the C-ABI vs the oracle.
+
+Comparator: oracle/pairs_oracle.c (restatement, bit-identical to the reference's generated C++, see
+test_oracle_pin.py) and, where present, oracle/_ref (the reference's own generated code)."""
+import numpy as np
+import pytest
+
+from tests.util import by_id, f2i, neighbor_rows, rel_err_force, rows_sorted
+
+pytestmark = pytest.mark.gpu
+
+RHO, TEMP, NTYPES = 0.8442, 1.44, 4
+CUT, SKIN, DT = 2.5, 0.3, 0.005
+
+
+def box(nx):
+    L = nx * pow((4.0 / RHO), (1.0 / 3.0))
+    return [0.0, L, 0.0, L, 0.0, L]
+
+
+def make_gpu(nx, ntypes=NTYPES, eps=None, sig6=None):
+    from pairs_b200.backend import Context
+    ctx = Context(0)
+    ctx.init_domain(box(nx))
+    n = ctx.copper_fcc_lattice(nx, nx, nx, RHO, ntypes)
+    ctx.adjust_thermo(TEMP)
+    ctx.setup_cells(CUT + SKIN)
+    n2 = ntypes * ntypes
+    ctx.set_lj_params(ntypes, eps if eps is not None else [1.0] * n2, sig6 if sig6 is not None else [1.0] * n2)
+    return ctx, n
+
+
+def make_oracle(nx, reneigh=20, ntypes=NTYPES, eps=None, sig6=None, world=1):
+    from oracle import port
+    sim = port.md_example(nx, world_size=world, reneigh_every=reneigh, ntypes=ntypes, particle_capacity=max(60000, 8 * 4 * nx ** 3),
+                          send_capacity=max(60000, 4 * 4 * nx ** 3))
+    if eps is not None:
+        sim.set_params(CUT + SKIN, CUT + SKIN, CUT, DT, ntypes, eps, sig6, reneigh)
+    off = 0
+    for r in sim.ranks:   # identity: uid = lattice index (the reference leaves uid at 0 for md.py)
+        r.ints("uid", r.nlocal, view=True)[:] = np.arange(off, off + r.nlocal)
+        off += r.nlocal
+    return sim
+
+
+@pytest.mark.parametrize("nx", [4, 8, 11])
+def test_lattice_and_adjust_thermo_bit_exact(nx):
+    ctx, n = make_gpu(nx)
+    sim = make_oracle(nx)
+    r = sim.ranks[0]
+    assert n == r.nlocal == 4 * nx ** 3
+    tag = ctx.ints("tag")
+    assert np.array_equal(by_id(tag, ctx.real("position")), r.real("position"))
+    assert np.array_equal(by_id(tag, ctx.real("linear_velocity")), r.real("linear_velocity"))
+    assert np.array_equal(by_id(tag, ctx.ints("type")), r.ints("type"))
+    assert np.array_equal(by_id(tag, ctx.real("mass")), r.real("mass"))
+    t_gpu, p_gpu = ctx.compute_thermo()
+    t_ref, p_ref = sim.thermo()
+    assert abs(t_gpu - t_ref) <= 1e-12 * abs(t_ref)
+    assert abs(p_gpu - p_ref) <= 1e-12 * abs(p_ref)
+
+
+def _reneighbor_gpu(ctx):
+    ctx.exchange()
+    ctx.borders()
+    ctx.build_cell_lists()
+    ctx.build_neighbor_lists(CUT + SKIN)
+
+
+@pytest.mark.parametrize("nx", [4, 8, 12])
+def test_cells_ghosts_neighbors_bit_exact_at_step0(nx):
+    ctx, n = make_gpu(nx)
+    sim = make_oracle(nx)
+    sim.step(0)
+    r = sim.ranks[0]
+    _reneighbor_gpu(ctx)
+    nl, ng = ctx.counts()
+    assert (nl, ng) == (r.nlocal, r.nghost)
+    dc, ncells, stencil = ctx.cells()
+    assert ncells == r.ncells and np.array_equal(dc, r.decomposition()["dim_cells"])
+    assert np.array_equal(stencil, r.ints("stencil", 27))
+    # particle identity + exact coordinates + cell of every particle (locals and ghosts)
+    tot = nl + ng
+    g_rows = rows_sorted(ctx.ints("tag", True).astype(np.int64), *f2i(ctx.real("position", True)).T,
+                         ctx.ints("particle_cell", True).astype(np.int64))
+    o_rows = rows_sorted(r.ints("uid", tot).astype(np.int64), *f2i(r.real("position", tot)).T,
+                         r.ints("particle_cell", tot).astype(np.int64))
+    assert np.array_equal(g_rows, o_rows)
+    # CSR cell list is a partition consistent with particle_cell, ascending inside each cell
+    cs, cl = ctx.cell_lists()
+    pc = ctx.ints("particle_cell", True)
+    assert cs[0] == 0 and cs[-1] == tot and np.array_equal(np.sort(cl), np.arange(tot))
+    assert np.array_equal(np.repeat(np.arange(ncells), np.diff(cs)), pc[cl])
+    inner = np.ones(tot, bool)
+    inner[cs[:-1][np.diff(cs) > 0]] = False
+    assert np.all(np.diff(cl)[inner[1:]] > 0)
+    # neighbour sets
+    nn_o, nl_o = r.neighbor_sets()
+    o = neighbor_rows(r.ints("uid", tot), r.real("position", tot), nn_o, nl_o, nl)
+    g = neighbor_rows(ctx.ints("tag", True), ctx.real("position", True), ctx.ints("numneighs"), ctx.neighbors(), nl)
+    assert g.shape == o.shape and np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_force_at_step0_and_integrators(uniform):
+    nx, nt = 8, 4
+    rng = np.random.default_rng(5)
+    eps = [1.0] * 16 if uniform else list(0.8 + 0.4 * rng.random(16))
+    sig6 = [1.0] * 16 if uniform else list(0.9 + 0.2 * rng.random(16))
+    ctx, n = make_gpu(nx, nt, eps, sig6)
+    sim = make_oracle(nx, 20, nt, eps, sig6)
+    # perturb both identically so that forces do not cancel by lattice symmetry
+    d = 0.05 * (rng.random((n, 3)) - 0.5)
+    r = sim.ranks[0]
+    r.real("position", n, view=True)[:] += d
+    ctx.upload(r.real("position"), r.real("linear_velocity"), r.real("mass"), r.ints("type"))
+    sim.step(0)
+    _reneighbor_gpu(ctx)
+    ctx.reset_volatile()
+    ctx.lennard_jones(CUT)
+    f_o = by_id(r.ints("uid"), r.real("force"))
+    f_g = by_id(ctx.ints("tag"), ctx.real("force"))
+    assert rel_err_force(f_g, f_o) <= 1e-12
+    big = np.abs(f_o).max(axis=1) > 1e-3 * np.abs(f_o).max()
+    assert np.max(np.abs(f_g - f_o)[big] / np.abs(f_o).max(axis=1)[big, None]) <= 1e-11
+    # a second accumulate-mode call doubles the force (force[i] = force[i] + acc)
+    ctx.lennard_jones(CUT)
+    assert rel_err_force(by_id(ctx.ints("tag"), ctx.real("force")), 2.0 * f_o) <= 1e-12
+    # integrators are per-particle: bit-exact given identical inputs
+    ctx.upload(by_id(r.ints("uid"), r.real("position")), by_id(r.ints("uid"), r.real("linear_velocity")),
+               by_id(r.ints("uid"), r.real("mass")), by_id(r.ints("uid"), r.ints("type")))
+    _reneighbor_gpu(ctx)
+    ctx.reset_volatile()
+    ctx.lennard_jones(CUT)
+    f_g = by_id(ctx.ints("tag"), ctx.real("force"))
+    uid = r.ints("uid")
+    r.real("force", n, view=True)[:] = f_g[uid]          # feed the oracle the GPU force: isolates the integrator
+    sim.initial_integrate()
+    ctx.initial_integrate(DT)
+    tag = ctx.ints("tag")
+    assert np.array_equal(by_id(tag, ctx.real("position")), by_id(uid, r.real("position")))
+    assert np.array_equal(by_id(tag, ctx.real("linear_velocity")), by_id(uid, r.real("linear_velocity")))
+    sim.final_integrate()
+    ctx.final_integrate(DT)
+    assert np.array_equal(by_id(ctx.ints("tag"), ctx.real("linear_velocity")), by_id(uid, r.real("linear_velocity")))
+
+
+@pytest.mark.parametrize("nx,reneigh,steps", [(8, 20, 100), (12, 5, 60)])
+def test_md_run_matches_oracle_over_100_steps(nx, reneigh, steps):
+    """Free-running trajectories: thermo within 1e-9 relative at every step, neighbour sets identical at every
+    reneighbouring, forces within 1e-12 (max-norm relative) when evaluated from identical positions."""
+    ctx, n = make_gpu(nx)
+    sim = make_oracle(nx, reneigh)
+    r = sim.ranks[0]
+    worst_t = 0.0
+    for ts in range(steps + 1):
+        sim.step(ts)
+        th = ctx.md_run(ts, ts + 1, DT, CUT, CUT + SKIN, CUT + SKIN, reneigh, 1)
+        t_o, p_o = sim.thermo()
+        assert th.shape == (1, 3) and th[0, 0] == ts
+        worst_t = max(worst_t, abs(th[0, 1] - t_o) / t_o, abs(th[0, 2] - p_o) / p_o)
+        assert ctx.counts() == (r.nlocal, r.nghost), ts
+    assert worst_t <= 1e-9, worst_t
+    # state after the run
+    uid, tag = r.ints("uid"), ctx.ints("tag")
+    assert np.abs(by_id(tag, ctx.real("position")) - by_id(uid, r.real("position"))).max() <= 1e-9
+    assert np.abs(by_id(tag, ctx.real("linear_velocity")) - by_id(uid, r.real("linear_velocity"))).max() <= 1e-9
+    assert rel_err_force(by_id(tag, ctx.real("force")), by_id(uid, r.real("force"))) <= 1e-9
+
+
+def test_forces_from_oracle_state_at_reneighbor_steps():
+    """Per-step force parity on IDENTICAL inputs: at a reneighbouring step ghosts are rebuilt from the locals, so
+    uploading the oracle's local positions reproduces its whole force evaluation."""
+    nx, reneigh = 8, 20
+    sim = make_oracle(nx, reneigh)
+    r = sim.ranks[0]
+    from pairs_b200.backend import Context
+    ctx = Context(0)
+    ctx.init_domain(box(nx))
+    ctx.setup_cells(CUT + SKIN)
+    ctx.set_lj_params(NTYPES, [1.0] * 16, [1.0] * 16)
+    checked = 0
+    for ts in range(60):
+        sim.step(ts)
+        if (ts + 1) % reneigh == 0:
+            uid = r.ints("uid")
+            ctx.upload(by_id(uid, r.real("position")), by_id(uid, r.real("linear_velocity")), by_id(uid, r.real("mass")),
+                       by_id(uid, r.ints("type")))
+            _reneighbor_gpu(ctx)
+            ctx.reset_volatile()
+            ctx.lennard_jones(CUT)
+            tot = r.nlocal + r.nghost
+            nn_o, nl_o = r.neighbor_sets()
+            o = neighbor_rows(r.ints("uid", tot), r.real("position", tot), nn_o, nl_o, r.nlocal)
+            g = neighbor_rows(ctx.ints("tag", True), ctx.real("position", True), ctx.ints("numneighs"), ctx.neighbors(), r.nlocal)
+            assert np.array_equal(g, o)
+            assert rel_err_force(by_id(ctx.ints("tag"), ctx.real("force")), by_id(uid, r.real("force"))) <= 1e-12
+            checked += 1
+    assert checked == 3
+
+
+def test_reference_generated_code_agrees():
+    """Same run against the reference's OWN generated C++ (oracle/_ref), when it was built in the source container."""
+    import ctypes
+    from oracle import ref
+    if not ref.available("md_t1"):
+        pytest.skip("oracle/_ref not built")
+    ctypes.CDLL(None).srand(1)
+    snaps = ref.RefProgram("md_t1").run_collect_thermo()
+    ctx, n = make_gpu(8)
+    th = ctx.md_run(0, 101, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
+    assert len(th) == len(snaps) == 101
+    for k, s in enumerate(snaps):
+        m, v = s["mass"], s["linear_velocity"]
+        t = 0.0
+        for i in range(s["nlocal"]):     # serial left-to-right, as runtime/thermo.hpp:32-36
+            t += m[i] * (v[i, 0] * v[i, 0] + v[i, 1] * v[i, 1] + v[i, 2] * v[i, 2])
+        t *= 1.0 / (3 * s["nlocal"] - 3)
+        assert abs(th[k, 1] - t) <= 1e-9 * t, k
+
+
+def test_capacity_protocol_neighbor_overflow():
+    ctx, n = make_gpu(6)
+    ctx.reserve(0, 8)                     # far too small: the build must grow and re-run (modules.py:159-203)
+    _reneighbor_gpu(ctx)
+    assert ctx.ints("numneighs").max() == 78 and ctx.lib.pb_neighbor_capacity(ctx.h) >= 78
+
+
+def test_errors_are_reported_not_fatal():
+    from pairs_b200.backend import BackendError, Context
+    ctx = Context(0)
+    with pytest.raises(BackendError):
+        ctx.setup_cells(2.8)              # domain not initialised
+    with pytest.raises(BackendError):
+        Context(9999)
