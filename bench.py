@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""Benchmark of the pairs MD hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W                 our CUDA path (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   the reference's own CPU implementation (rank 0 only)
+
+Metric (BASELINE.json): LJ atom-steps/s.  A "step" is one iteration of the generated timestep loop of examples/md.py
+(initial_integrate -> exchange+borders+cell/neighbour build every 20th step | ghost refresh -> lennard_jones ->
+final_integrate, thermo every 100).  Workload at N = 1: BASELINE.json configs[1] -- synthetic FCC lattice, 100^3 cells =
+4,000,000 atoms, cutoff 2.5 sigma, skin 0.3, reneighbour every 20 steps, fp64.  N > 1: weak scaling, 4M atoms per GPU
+(configs[3]), regular domain partitioner, NCCL halo exchange.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RHO, TEMP, NTYPES = 0.8442, 1.44, 4
+CUT, SKIN, DT, RENEIGH, THERMO = 2.5, 0.3, 0.005, 20, 100
+METRIC, UNIT = "lj_atom_steps_per_s", "atom-steps/s"
+# rank grids Regular6DStencil::setConfig picks when the global box is built from per-GPU cubes
+WEAK_GRIDS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
+REF_SAMPLE_NX = 63   # oracle/_ref variant md_bench: 4 * 63^3 = 1,000,188 atoms
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def workload_config(n_gpus, nx):
+    return {"workload": f"lj_onetype-style synthetic FCC lattice, {4 * nx ** 3} atoms per GPU ({nx}^3 cells), rho 0.8442, "
+                        f"cutoff 2.5 sigma + skin 0.3, reneighbour every {RENEIGH}, thermo every {THERMO}, fp64"
+                        + (f"; weak scaling over {n_gpus} GPUs, regular partitioner, NCCL halo exchange" if n_gpus > 1 else ""),
+            "atoms_per_gpu": 4 * nx ** 3, "n_gpus": n_gpus,
+            "l2_policy": "inputs larger than L2 (neighbour lists ~1.3 GB + 0.5 GB particle state per step vs 126 MB L2)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the force kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "lj_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(warmup, steps, replicas):
+    """Times the reference's own generated serial C++ (oracle/_ref, kind 'reference') or, if that was not built, the
+    restatement oracle/pairs_oracle.c (kind 'port') on a bounded 1,000,188-atom sample of the same workload."""
+    from oracle import ref
+    n_atoms = 4 * REF_SAMPLE_NX ** 3
+    if ref.available("md_bench"):
+        from oracle import ref_worker
+        res = ref_worker.bench_many("md_bench", warmup, steps, replicas)
+        value = sum(r["n"] * r["steps"] / r["seconds"] for r in res)
+        secs = max(r["seconds"] for r in res)
+        kind = "reference"
+    else:
+        from oracle import port
+        sim = port.md_example(REF_SAMPLE_NX, reneigh_every=RENEIGH, particle_capacity=1400000, send_capacity=400000)
+        for ts in range(warmup + 1):
+            sim.step(ts)
+        t0 = time.perf_counter()
+        for ts in range(warmup + 1, warmup + 1 + steps):
+            sim.step(ts)
+        secs = time.perf_counter() - t0
+        value = n_atoms * steps / secs
+        kind, replicas = "port", 1
+    sample = (f"{n_atoms} atoms (same lattice generator, nx={REF_SAMPLE_NX}), loop iterations {warmup + 1}..{warmup + steps} "
+              f"timed after iteration 0 (set-up + first list build) and {warmup} warm-up iterations; reneighbour every {RENEIGH}; "
+              f"serial target, g++ -O3 -ffp-contract=off; {replicas} independent replica process(es), aggregate throughput")
+    return {"value": value, "unit": UNIT, "cores": replicas, "kind": kind, "sample": sample, "seconds": secs}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    replicas = args.ref_replicas or max(1, min(os.cpu_count() or 1, 64))
+    try:
+        avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+        replicas = max(1, min(replicas, int(avail_gb // 2.0)))     # ~1.5 GB per 1M-atom replica
+    except (ValueError, OSError):
+        pass
+    t0 = time.perf_counter()
+    cb = cpu_reference_sample(args.warmup, args.steps, replicas)
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * cb["seconds"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, args.nx),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from pairs_b200 import backend
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist   # plumbing only: rendezvous, barrier, max-over-ranks
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    nx = args.nx
+    gx = WEAK_GRIDS.get(world)
+    if gx is None:
+        raise SystemExit(f"unsupported --gpus {world}")
+    lattice = pow((4.0 / RHO), (1.0 / 3.0))
+    cells = [nx * g for g in gx]
+    grid = [0.0, cells[0] * lattice, 0.0, cells[1] * lattice, 0.0, cells[2] * lattice]
+    assert backend.rank_grid(world, grid) == gx, (backend.rank_grid(world, grid), gx)
+
+    ctx = backend.Context(local)
+    ctx.init_domain(grid, world_size=world, rank=rank)
+    if world > 1:
+        ids = [backend.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.nccl_init(ids[0])
+    t_setup = time.perf_counter()
+    nlocal0 = ctx.copper_fcc_lattice(cells[0], cells[1], cells[2], RHO, NTYPES)
+    ctx.adjust_thermo(TEMP)
+    ctx.set_lj_params(NTYPES, [1.0] * (NTYPES * NTYPES), [1.0] * (NTYPES * NTYPES))
+    n_global = 4 * cells[0] * cells[1] * cells[2]
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    W, K = args.warmup, args.steps
+    run = lambda a, b: ctx.md_run(a, b, DT, CUT, CUT + SKIN, CUT + SKIN, RENEIGH, THERMO)  # noqa: E731
+    run(0, W)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.timers_reset()
+    ctx.timers_enable(True)
+    launches0 = ctx.kernel_launches()
+    barrier()
+    t_wall = time.perf_counter()
+    ctx.stream_timer_start()
+    thermo = run(W, W + K)
+    ms = ctx.stream_timer_stop()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ctx.timers_enable(False)
+    launches = ctx.kernel_launches() - launches0
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    value = n_global * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (lennard_jones), measured live over the timed region ----
+    lj_ms, lj_calls = ctx.timer("lennard_jones")
+    nl, ng = ctx.counts()
+    nn = ctx.ints("numneighs")
+    kbar = float(nn.mean()) if len(nn) else 0.0
+    bytes_per_atom = 4.0 * kbar + 60.0 + 24.0 * ng / max(nl, 1)     # ids + numneighs + x_i + type + flags + force write + ghost x
+    peak, peak_src = measured_peak()
+    achieved = (bytes_per_atom * nl / 1e9) / (lj_ms / max(lj_calls, 1) * 1e-3) if lj_ms > 0 else None
+    stages = {}
+    for name in ("lennard_jones", "initial_integrate", "final_integrate", "synchronize", "exchange", "borders", "build_cell_lists",
+                 "build_neighbor_lists", "compute_thermo"):
+        s_ms, s_calls = ctx.timer(name)
+        stages[name] = {"ms": round(s_ms, 4), "calls": s_calls}
+    roofline = {"bound": "hbm", "kernel": "pb_k_lennard_jones", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "algorithmic_bytes_per_atom": bytes_per_atom, "mean_neighbors": kbar, "atoms_per_launch": nl,
+                "avg_launch_ms": lj_ms / max(lj_calls, 1), "force_kernel_atoms_per_s": nl / (lj_ms / max(lj_calls, 1) * 1e-3) if lj_ms > 0 else None,
+                "share_of_step": lj_ms / ms if ms > 0 else None}
+
+    # ---- end to end through the C-ABI with HOST buffers: upload (pinned) -> K loop iterations from ts = 0 (first list build
+    #      included) with thermo read-backs -> download of positions and velocities ----
+    pos = ctx.real("position")
+    vel = ctx.real("linear_velocity")
+    mass = ctx.real("mass")
+    typ = ctx.ints("type")
+    out_pos, out_vel = np.empty_like(pos), np.empty_like(vel)
+    for a in (pos, vel, mass, typ, out_pos, out_vel):
+        ctx.host_register(a)
+    barrier()
+    t0 = time.perf_counter()
+    ctx.upload(pos, vel, mass, typ)
+    th2 = run(0, K)
+    ctx.real_into("position", out_pos)
+    ctx.real_into("linear_velocity", out_vel)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    h2d = (pos.nbytes + vel.nbytes + mass.nbytes + typ.nbytes) * world
+    d2h = (out_pos.nbytes + out_vel.nbytes + th2.nbytes) * world
+    e2e = {"value": n_global * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+           "what": "pb_upload_particles (pinned host arrays) + pb_md_run over K iterations from ts=0 incl. first neighbour build "
+                   "+ thermo read-backs + pb_download_real(position, linear_velocity)"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_sample(1, 20, 1)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline["host_cores_available"] = os.cpu_count()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world, nx), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms": stages, "atoms_global": n_global,
+                "nlocal_rank0": nl, "nghost_rank0": ng, "wall_s_timed_region": t_wall, "setup_s": t_setup,
+                "thermo_last": [float(x) for x in thermo[-1]] if len(thermo) else None}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=100, help="FCC cells per GPU and dimension (100 -> 4M atoms: BASELINE configs[1])")
+    ap.add_argument("--ref-replicas", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -19,6 +19,8 @@
 #ifndef PAIRS_B200_H
 #define PAIRS_B200_H
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -131,6 +133,12 @@ int pb_synchronize_device(pb_ctx *ctx);
 int pb_timers_enable(pb_ctx *ctx, int on);
 int pb_timers_get(pb_ctx *ctx, const char *name, double *ms, long *calls);
 int pb_timers_reset(pb_ctx *ctx);
+/* CUDA-event bracket on the context's stream around an arbitrary region (bench.py's timed region) */
+int pb_stream_timer_start(pb_ctx *ctx);
+int pb_stream_timer_stop(pb_ctx *ctx, double *ms);
+/* page-lock a caller-owned host buffer (cudaHostRegister) so uploads/downloads are DMA transfers */
+int pb_host_register(pb_ctx *ctx, void *ptr, size_t bytes);
+int pb_host_unregister(pb_ctx *ctx, void *ptr);
 /* number of kernels launched by this context so far */
 long pb_kernel_launches(const pb_ctx *ctx);
 

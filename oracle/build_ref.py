@@ -14,8 +14,9 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md        stock examples/md.py (config C1: 32^3 cells = 131072 atoms, 200 steps)
   md_t1     nx=ny=nz=8 (2048 atoms), 100 steps, thermo every step   -> per-step parity dumps
   md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
-  md_bench  nx=ny=nz=63 (1000188 atoms), 18 steps (= 19 loop iterations, ONE reneighbour, the
-            steady-state 1-in-20 ratio) -> bounded CPU-baseline sample for bench.py
+  md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
+            bench.py time a bounded number of loop iterations and then leave the loop)
+            -> CPU-baseline sample for bench.py
 
 Usage: python oracle/build_ref.py [variant ...]    (default: all; no-op if /root/reference is absent)
 """
@@ -60,7 +61,7 @@ VARIANTS = {
     "md": ("examples/md.py", None, ["-DREF_IS_MD"], True),
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
-    "md_bench": ("examples/md.py", md_variant(63, 18, 100, 20, pcap=1400000), ["-DREF_IS_MD"], True),
+    "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
 }
 
 

@@ -13,7 +13,9 @@
 //
 // Build: g++ -O3 -ffp-contract=off -shared -fPIC -DREF_GENERATED='"gen/md.cpp"' [-DREF_IS_MD]
 //        -Ioracle/mpi_stub -I/root/reference  (see oracle/build_ref.py)
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,7 +36,10 @@ ref_hook_fn g_hook = nullptr;
 void *g_hook_user = nullptr;
 std::vector<std::string> g_timer_names;
 int g_thermo_calls = 0;
+int g_thermo_limit = -1;               // stop the generated loop after this many compute_thermo calls (< 0: never)
 bool g_quiet = false;
+std::vector<double> g_thermo_times;    // wall-clock seconds (steady clock) at every compute_thermo call
+struct RefStop {};
 }
 
 namespace pairs {
@@ -59,7 +64,9 @@ double ref_hook_compute_thermo(PairsSimulation *ps, int nlocal, double xprd, dou
     g_ps = ps;
     double t = compute_thermo(ps, nlocal, xprd, yprd, zprd, g_quiet ? 0 : print);
     g_thermo_calls++;
+    g_thermo_times.push_back(std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count());
     if(g_hook != nullptr) { g_hook("thermo", nlocal, g_hook_user); }
+    if(g_thermo_limit >= 0 && g_thermo_calls >= g_thermo_limit) { throw RefStop(); }
     return t;
 }
 
@@ -83,14 +90,36 @@ int ref_run(ref_hook_fn hook, void *user, int quiet) {
     g_hook_user = user;
     g_quiet = quiet != 0;
     g_thermo_calls = 0;
+    g_thermo_times.clear();
     g_timer_names.clear();
+    // the reference draws particle types from rand() in its process-initial state (runtime/copper_fcc_lattice.hpp:128)
+    srand(1);
     char arg0[] = "ref";
     char *argv_[] = {arg0, nullptr};
     char **argv = argv_;
-    int rc = ref_generated_main(1, argv);
+    int rc = 0;
+    try {
+        rc = ref_generated_main(1, argv);
+    } catch(const RefStop &) {
+        rc = 0;   // bounded run: the generated loop was left after g_thermo_limit thermo calls (its state is leaked)
+    }
     g_hook = nullptr;
     g_ps = nullptr;
+    g_thermo_limit = -1;
     return rc;
+}
+
+// Bounded run for timing: programs generated with compute_thermo(1) call the hook once per loop iteration; the
+// loop is left after `max_thermo_calls` iterations.  Timestamps of every iteration end are kept.
+int ref_run_limited(int max_thermo_calls, int quiet) {
+    g_thermo_limit = max_thermo_calls;
+    return ref_run(nullptr, nullptr, quiet);
+}
+
+int ref_thermo_times(double *out, int cap) {
+    const int n = (int) g_thermo_times.size();
+    for(int k = 0; k < n && k < cap; k++) { out[k] = g_thermo_times[k]; }
+    return n;
 }
 
 // Valid only inside a hook callback (the PairsSimulation is deleted when main returns).

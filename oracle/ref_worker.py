@@ -1,0 +1,91 @@
+"""Runs a reference program (oracle/_ref) in a FRESH process.  TEST INFRASTRUCTURE ONLY.
+
+Why a fresh process: the reference allocates its property arrays with posix_memalign and never initialises the
+ghost part (runtime/allocate.hpp:14-45; ghost `flags` are read but never transmitted), so
+its results depend on the heap being zero pages -- true for its own executable, not inside a long-lived pytest
+process.  MALLOC_MMAP_THRESHOLD_ forces those allocations to come from fresh zero-filled mmaps.
+
+  python -m oracle.ref_worker dump  <variant> <out.npz> [nsteps]   per-thermo-step snapshots (locals only)
+  python -m oracle.ref_worker bench <variant> <warmup> <steps>     prints JSON {"n": atoms, "seconds": t, "steps": k}
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ENV = {"MALLOC_MMAP_THRESHOLD_": "65536", "MALLOC_PERTURB_": "0"}
+
+
+def spawn(args, **kw):
+    env = dict(os.environ, **ENV)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    return subprocess.Popen([sys.executable, "-m", "oracle.ref_worker", *[str(a) for a in args]], cwd=root, env=env,
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, **kw)
+
+
+def dump(variant, out_path, nsteps=None):
+    """Snapshots of every thermo step of `variant`, produced in a fresh process; returns list of dicts."""
+    p = spawn(["dump", variant, out_path] + ([nsteps] if nsteps is not None else []))
+    out, err = p.communicate()
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_worker dump failed:\n{out}\n{err}")
+    z = np.load(out_path)
+    n = int(z["count"])
+    return [{k: z[f"{k}_{i}"] for k in ("position", "linear_velocity", "force", "mass", "type")} | {"nlocal": int(z["nlocal"][i]), "nghost": int(z["nghost"][i])}
+            for i in range(n)]
+
+
+def bench_many(variant, warmup, steps, replicas):
+    """`replicas` concurrent fresh processes, each timing `steps` loop iterations after `warmup`; list of results."""
+    procs = [spawn(["bench", variant, warmup, steps]) for _ in range(replicas)]
+    res = []
+    for p in procs:
+        out, err = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"ref_worker bench failed:\n{out[-2000:]}\n{err[-2000:]}")
+        res.append(json.loads(out.strip().splitlines()[-1]))
+    return res
+
+
+def _main(argv):
+    from oracle.ref import RefProgram
+    mode, variant = argv[0], argv[1]
+    prog = RefProgram(variant)
+    if mode == "dump":
+        out_path = argv[2]
+        nsteps = int(argv[3]) if len(argv) > 3 else None
+        snaps = prog.run_collect_thermo(steps=nsteps)
+        d = {"count": len(snaps), "nlocal": np.array([s["nlocal"] for s in snaps]), "nghost": np.array([s["nghost"] for s in snaps])}
+        for i, s in enumerate(snaps):
+            for k in ("position", "linear_velocity", "force", "mass", "type"):
+                d[f"{k}_{i}"] = s[k]
+        np.savez(out_path, **d)
+        return 0
+    if mode == "bench":
+        warmup, steps = int(argv[2]), int(argv[3])
+        # redirect the program's own stdout chatter away from our JSON line
+        sys.stdout.flush()
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        saved = os.dup(1)
+        os.dup2(devnull, 1)
+        prog.lib.ref_run_limited.argtypes = [ctypes.c_int, ctypes.c_int]
+        prog.lib.ref_run_limited(warmup + steps + 1, 1)      # iteration 0 (set-up + first build) is never timed
+        os.dup2(saved, 1)
+        buf = (ctypes.c_double * (warmup + steps + 8))()
+        prog.lib.ref_thermo_times.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.c_int]
+        n = prog.lib.ref_thermo_times(buf, len(buf))
+        t = list(buf)[:n]
+        assert n >= warmup + steps + 1, (n, warmup, steps)
+        seconds = t[warmup + steps] - t[warmup]
+        atoms = {"md_bench": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3}[variant]
+        print(json.dumps({"n": atoms, "seconds": seconds, "steps": steps, "warmup": warmup}))
+        return 0
+    raise SystemExit(f"unknown mode {mode}")
+
+
+if __name__ == "__main__":
+    sys.exit(_main(sys.argv[1:]))

@@ -95,6 +95,10 @@ SIGNATURES = {
     "pb_timers_enable": (_I, [_P, _I]),
     "pb_timers_get": (_I, [_P, _S, _DP, ctypes.POINTER(ctypes.c_long)]),
     "pb_timers_reset": (_I, [_P]),
+    "pb_stream_timer_start": (_I, [_P]),
+    "pb_stream_timer_stop": (_I, [_P, _DP]),
+    "pb_host_register": (_I, [_P, _P, ctypes.c_size_t]),
+    "pb_host_unregister": (_I, [_P, _P]),
     "pb_kernel_launches": (ctypes.c_long, [_P]),
 }
 
@@ -323,6 +327,24 @@ class Context:
         calls = ctypes.c_long(0)
         self.lib.pb_timers_get(self.h, name.encode(), ctypes.byref(ms), ctypes.byref(calls))
         return ms.value, calls.value
+
+    def stream_timer_start(self):
+        self._ck(self.lib.pb_stream_timer_start(self.h))
+
+    def stream_timer_stop(self):
+        ms = _D(0.0)
+        self._ck(self.lib.pb_stream_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def host_register(self, arr):
+        self._ck(self.lib.pb_host_register(self.h, arr.ctypes.data_as(_P), arr.nbytes))
+
+    def host_unregister(self, arr):
+        self._ck(self.lib.pb_host_unregister(self.h, arr.ctypes.data_as(_P)))
+
+    def real_into(self, name, out, with_ghosts=False):
+        self._ck(self.lib.pb_download_real(self.h, name.encode(), _dp(out), 1 if with_ghosts else 0))
+        return out
 
     def kernel_launches(self):
         return int(self.lib.pb_kernel_launches(self.h))

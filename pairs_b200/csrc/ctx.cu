@@ -58,6 +58,8 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->d_partial, ctx->d_scalars};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
+    for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
+    for(cudaEvent_t e : ctx->event_pool) { cudaEventDestroy(e); }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -388,14 +390,62 @@ extern "C" int pb_synchronize_device(pb_ctx *ctx) {
 
 extern "C" int pb_timers_enable(pb_ctx *ctx, int on) { ctx->timers_on = on != 0; return 0; }
 
-extern "C" int pb_timers_reset(pb_ctx *ctx) { ctx->timers.clear(); return 0; }
+static void pb_timer_collect(pb_ctx *ctx, PbTimer &t) {
+    for(auto &pr : t.pending) {
+        cudaEventSynchronize(pr.second);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pr.first, pr.second);
+        t.ms += ms;
+        t.calls += 1;
+        ctx->event_pool.push_back(pr.first);
+        ctx->event_pool.push_back(pr.second);
+    }
+    t.pending.clear();
+}
+
+extern "C" int pb_timers_reset(pb_ctx *ctx) {
+    for(auto &kv : ctx->timers) { pb_timer_collect(ctx, kv.second); }
+    ctx->timers.clear();
+    return 0;
+}
 
 extern "C" int pb_timers_get(pb_ctx *ctx, const char *name, double *ms, long *calls) {
     auto it = ctx->timers.find(name);
     if(it == ctx->timers.end()) { *ms = 0.0; *calls = 0; return 0; }
+    pb_timer_collect(ctx, it->second);
     *ms = it->second.ms;
     *calls = it->second.calls;
     return 0;
 }
 
+// whole-region device timing on the launching stream
+extern "C" int pb_stream_timer_start(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PB_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+
+extern "C" int pb_stream_timer_stop(pb_ctx *ctx, double *ms) {
+    PB_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    PB_CHECK(cudaEventSynchronize(ctx->ev1));
+    float f = 0.f;
+    PB_CHECK(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+    *ms = (double) f;
+    return 0;
+}
+
 extern "C" long pb_kernel_launches(const pb_ctx *ctx) { return ctx->launches; }
+
+// Page-lock / unlock a caller-owned host buffer so that uploads and downloads through the C-ABI are true DMA
+// transfers (bench.py's end-to-end leg).
+extern "C" int pb_host_register(pb_ctx *ctx, void *ptr, size_t bytes) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PB_CHECK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+
+extern "C" int pb_host_unregister(pb_ctx *ctx, void *ptr) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PB_CHECK(cudaHostUnregister(ptr));
+    return 0;
+}

@@ -39,6 +39,7 @@
 struct PbTimer {
     double ms = 0.0;
     long calls = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;   // recorded, not yet read back (no sync on the hot path)
 };
 
 struct pb_ctx {
@@ -109,10 +110,18 @@ struct pb_ctx {
     int *d_scalars = nullptr;     // small device scratch: [0] max neighbours, [1..] counters
     int *h_scalars = nullptr;     // pinned mirror
 
-    // ---- timers ----
+    // ---- timers: CUDA events on the launching stream, collected lazily (pb_timers_get) ----
     bool timers_on = false;
     std::map<std::string, PbTimer> timers;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // pb_stream_timer_start / stop
+
+    cudaEvent_t get_event() {
+        if(!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
 
     void set_error(const std::string &e) { err = e; }
 };
@@ -126,21 +135,19 @@ int pb_ensure_send_capacity(pb_ctx *ctx, int needed);
 int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n);   // out[0..n], out[n] = total
 int pb_bin_particles(pb_ctx *ctx, int first, int n, bool write_particle_cell);
 
+// Brackets one stage with two events from the pool; nothing is synchronised here.
 struct PbStage {
     pb_ctx *ctx;
     const char *name;
+    cudaEvent_t a = nullptr;
     PbStage(pb_ctx *c, const char *n) : ctx(c), name(n) {
-        if(ctx->timers_on) { cudaEventRecord(ctx->ev0, ctx->stream); }
+        if(ctx->timers_on) { a = ctx->get_event(); cudaEventRecord(a, ctx->stream); }
     }
     ~PbStage() {
-        if(ctx->timers_on) {
-            cudaEventRecord(ctx->ev1, ctx->stream);
-            cudaEventSynchronize(ctx->ev1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-            PbTimer &t = ctx->timers[name];
-            t.ms += ms;
-            t.calls += 1;
+        if(a != nullptr) {
+            cudaEvent_t b = ctx->get_event();
+            cudaEventRecord(b, ctx->stream);
+            ctx->timers[name].pending.emplace_back(a, b);
         }
     }
 };
