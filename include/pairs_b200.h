@@ -127,6 +127,9 @@ typedef struct pb_md_params {
 } pb_md_params;
 int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo);
 
+/* tuning knobs: "lanes_per_particle" (1,2,4,8,16; applies from the next neighbour-list build), "lj_unroll" (1,2,4,8) */
+int pb_set_option(pb_ctx *ctx, const char *name, int value);
+
 /* ---- streams / timing ---- */
 int pb_synchronize_device(pb_ctx *ctx);
 /* per-stage device time in ms accumulated with CUDA events when enabled (names follow the reference's timers) */

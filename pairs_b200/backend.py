@@ -91,6 +91,7 @@ SIGNATURES = {
     "pb_nccl_unique_id": (_I, [_P]),
     "pb_nccl_init": (_I, [_P, _P]),
     "pb_md_run": (_I, [_P, ctypes.POINTER(MdParams), _I, _I, _DP, _I, _IP]),
+    "pb_set_option": (_I, [_P, _S, _I]),
     "pb_synchronize_device": (_I, [_P]),
     "pb_timers_enable": (_I, [_P, _I]),
     "pb_timers_get": (_I, [_P, _S, _DP, ctypes.POINTER(ctypes.c_long)]),
@@ -312,6 +313,9 @@ class Context:
         n = _I(0)
         self._ck(self.lib.pb_md_run(self.h, ctypes.byref(p), ts_begin, ts_end, _dp(out), cap, ctypes.byref(n)))
         return out[: min(n.value, cap) * 3].reshape(-1, 3)
+
+    def set_option(self, name, value):
+        self._ck(self.lib.pb_set_option(self.h, name.encode(), int(value)))
 
     def sync(self):
         self._ck(self.lib.pb_synchronize_device(self.h))

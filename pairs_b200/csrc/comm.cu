@@ -24,7 +24,7 @@ int pb_sort_locals(pb_ctx *ctx);
 int pb_transport_sizes(pb_ctx *ctx, int dim);
 int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const double **recv_src);
 
-static const int EXCH_ELEMS = 12, BORDER_ELEMS = 11, SYNC_ELEMS = 6;
+static const int BORDER_ELEMS = 11, SYNC_ELEMS = 6;
 
 struct PbBox {
     double len[3];

@@ -83,6 +83,9 @@ struct pb_ctx {
 
     // ---- neighbour lists (sim/neighbor_lists.py) ----
     int ncap = 0, pitch = 0, max_neigh = 0;
+    int lanes = 4;                // lanes of a warp that share one particle's list in the force kernel (1,2,4,8,16)
+    int lj_unroll = 4;            // independent gathers in flight per lane
+    int nslots = 0;               // list slots per group row: ceil(ncap / lanes)
     size_t neigh_bytes = 0;
     int *neigh = nullptr, *numneigh = nullptr;
     int neigh_n = 0;              // nlocal at build time
@@ -160,6 +163,27 @@ static inline int pb_blocks(long n, int threads) { return (int) ((n + threads - 
         ctx->launches++;                                                       \
         PB_CHECK(cudaGetLastError());                                          \
     } while(0)
+
+// One 256-bit read-only load (sm_100: LDG.E.256): a particle's double4 is exactly one 32-byte sector, fetched with a
+// single instruction / single L1 tag lookup instead of two 128-bit halves.
+__device__ __forceinline__ double4 pb_ld_pos(const double4 *p) {
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
+// Neighbour-list layout: "interleaved sliced ELLPACK".  A warp serves A = 32/G particles, G lanes each.  The k-th
+// neighbour of particle i lives at
+//     ((i / A) * T + k / G) * 32 + (i % A) * G + k % G          T = ceil(capacity / G)
+// so that in iteration t the 32 lanes of the warp read 32 CONSECUTIVE ints (one 128-byte line), and the G lanes of
+// one particle fetch G consecutive neighbours of its (cell-sorted, hence memory-adjacent) list -> their 32-byte
+// position gathers fall into the same one or two 128-byte lines.  G = 1 is the classic slice-32 ELLPACK.
+struct PbNeighLayout {
+    int G, A, T;
+    __host__ __device__ __forceinline__ size_t idx(int i, int k) const {
+        return ((size_t) (i / A) * T + (size_t) (k / G)) * 32 + (size_t) ((i % A) * G + (k % G));
+    }
+};
 
 // particle type rides in the low 32 bits of pos.w
 __device__ __forceinline__ int pb_w_type(double w) { return (int) (__double_as_longlong(w) & 0xffffffffLL); }

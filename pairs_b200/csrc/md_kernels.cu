@@ -12,78 +12,91 @@
 // the L1 gather path, not by tensor cores (nothing here is a dense contraction).  The integrators are pure
 // streaming kernels (132 B resp. 84 B per particle in the reference's accounting).
 #include <algorithm>
+#include <string>
 
 #include "ctx.cuh"
 
 // ---- Lennard-Jones (examples/md.py:5-8, sim/interaction.py:201-292) -------------------------------------------
-// One thread per local particle; neighbour ids are read column-major (coalesced), neighbour positions are
-// gathered as one 32-byte double4 (x, y, z, type) each.  UNROLL independent gathers are in flight per thread.
-template<bool UNIFORM, bool ACCUMULATE, int UNROLL>
-__global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int pitch, int cap, double cutsq, int ntypes,
+// G lanes of a warp share one local particle (A = 32/G particles per warp).  Per iteration the warp reads 32
+// consecutive neighbour ids (one 128-byte line of the interleaved sliced-ELLPACK list, PbNeighLayout) and every lane
+// gathers ONE neighbour as a single 256-bit load (x, y, z, type = one 32-byte sector).  The G lanes of a particle
+// fetch G consecutive entries of its cell-sorted list, i.e. memory-adjacent particles, which is what keeps the L1
+// tag/sector traffic of the gather low (ncu: the thread-per-particle version ran at 94 % L1TEX throughput).
+// UNROLL iterations are issued back to back so UNROLL gathers are in flight per lane.  Per-lane partial forces are
+// combined with warp shuffles in a fixed tree (deterministic); lane 0 of the group writes.
+template<int G, bool UNIFORM, bool ACCUMULATE, int UNROLL>
+__global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int cap, double cutsq, int ntypes,
                                                           double eps_u, double sig6_u,
                                                           const double *__restrict__ eps_t, const double *__restrict__ sig6_t,
                                                           const double4 *__restrict__ pos, const int *__restrict__ flags,
                                                           const int *__restrict__ numneigh, const int *__restrict__ neigh,
                                                           double *__restrict__ force) {
+    constexpr int A = 32 / G;
     __shared__ double s_eps[64], s_sig6[64];
     if(!UNIFORM) {
         for(int k = threadIdx.x; k < ntypes * ntypes; k += blockDim.x) { s_eps[k] = eps_t[k]; s_sig6[k] = sig6_t[k]; }
         __syncthreads();
     }
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= nlocal) { return; }
-    const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = lane % G;
+    const int i = warp * A + lane / G;
+    const bool live = i < nlocal;
+    const bool fixed = live && (flags[i] & PB_FLAG_FIXED) != 0;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    if(!fixed) {
-        const double4 pi = pos[i];
+    if(live && !fixed) {
+        const double4 pi = pb_ld_pos(pos + i);
         const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * ntypes;
         const int nn = numneigh[i];
-        const int *nb = neigh + i;
-        int k = 0;
-        for(; k + UNROLL <= nn; k += UNROLL) {
+        const int iters = (nn + G - 1) / G;
+        const int *nb = neigh + (size_t) warp * T * 32 + lane;
+        int t = 0;
+#define PB_LJ_PAIR(PJ, VALID)                                                                                                  \
+        {                                                                                                                      \
+            const double dx = __dsub_rn(pi.x, (PJ).x);                                                                         \
+            const double dy = __dsub_rn(pi.y, (PJ).y);                                                                         \
+            const double dz = __dsub_rn(pi.z, (PJ).z);                                                                         \
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));                  \
+            if((VALID) && rsq < cutsq) {                                                                                       \
+                const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type((PJ).w)];                                         \
+                const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type((PJ).w)];                                            \
+                const double sr2 = __ddiv_rn(1.0, rsq);                                                                        \
+                const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);                                       \
+                const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);         \
+                fx = __dadd_rn(fx, __dmul_rn(dx, f));                                                                          \
+                fy = __dadd_rn(fy, __dmul_rn(dy, f));                                                                          \
+                fz = __dadd_rn(fz, __dmul_rn(dz, f));                                                                          \
+            }                                                                                                                  \
+        }
+        for(; t + UNROLL <= iters; t += UNROLL) {
             int j[UNROLL];
             double4 pj[UNROLL];
 #pragma unroll
-            for(int u = 0; u < UNROLL; u++) { j[u] = __ldg(nb + (size_t) (k + u) * pitch); }
-#pragma unroll
-            for(int u = 0; u < UNROLL; u++) { pj[u] = pos[j[u]]; }
-#pragma unroll
             for(int u = 0; u < UNROLL; u++) {
-                const double dx = __dsub_rn(pi.x, pj[u].x);
-                const double dy = __dsub_rn(pi.y, pj[u].y);
-                const double dz = __dsub_rn(pi.z, pj[u].z);
-                const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if(rsq < cutsq) {
-                    const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type(pj[u].w)];
-                    const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type(pj[u].w)];
-                    const double sr2 = __ddiv_rn(1.0, rsq);
-                    const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);
-                    const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);
-                    fx = __dadd_rn(fx, __dmul_rn(dx, f));
-                    fy = __dadd_rn(fy, __dmul_rn(dy, f));
-                    fz = __dadd_rn(fz, __dmul_rn(dz, f));
-                }
+                const bool valid = (t + u) * G + g < nn;
+                j[u] = valid ? __ldg(nb + (size_t) (t + u) * 32) : i;
             }
+#pragma unroll
+            for(int u = 0; u < UNROLL; u++) { pj[u] = pb_ld_pos(pos + j[u]); }
+#pragma unroll
+            for(int u = 0; u < UNROLL; u++) { PB_LJ_PAIR(pj[u], j[u] != i) }
         }
-        for(; k < nn; k++) {
-            const int j = __ldg(nb + (size_t) k * pitch);
-            const double4 pj = pos[j];
-            const double dx = __dsub_rn(pi.x, pj.x);
-            const double dy = __dsub_rn(pi.y, pj.y);
-            const double dz = __dsub_rn(pi.z, pj.z);
-            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if(rsq < cutsq) {
-                const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type(pj.w)];
-                const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type(pj.w)];
-                const double sr2 = __ddiv_rn(1.0, rsq);
-                const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);
-                const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);
-                fx = __dadd_rn(fx, __dmul_rn(dx, f));
-                fy = __dadd_rn(fy, __dmul_rn(dy, f));
-                fz = __dadd_rn(fz, __dmul_rn(dz, f));
-            }
+        for(; t < iters; t++) {
+            const bool valid = t * G + g < nn;
+            const int j = valid ? __ldg(nb + (size_t) t * 32) : i;
+            const double4 pj = pb_ld_pos(pos + j);
+            PB_LJ_PAIR(pj, j != i)
         }
+#undef PB_LJ_PAIR
     }
+    // fixed-shape tree over the G lanes of the particle
+#pragma unroll
+    for(int o = G / 2; o > 0; o >>= 1) {
+        fx = __dadd_rn(fx, __shfl_xor_sync(0xffffffffu, fx, o));
+        fy = __dadd_rn(fy, __shfl_xor_sync(0xffffffffu, fy, o));
+        fz = __dadd_rn(fz, __shfl_xor_sync(0xffffffffu, fz, o));
+    }
+    if(!live || g != 0) { return; }
     // force[i] = force[i] + acc (sim/interaction.py:280-292).  When the preceding reset_volatile_properties is fused in
     // (ACCUMULATE == false) the old value is the freshly written 0.0, also for FIXED particles.
     if(ACCUMULATE) {
@@ -137,18 +150,15 @@ int pb_materialise_force_reset(pb_ctx *ctx) {
     return 0;
 }
 
-extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) {
-    PB_CHECK(cudaSetDevice(ctx->device));
-    PbStage st(ctx, "lennard_jones");
-    if(ctx->ntypes == 0) { ctx->set_error("pb_lennard_jones: pb_set_lj_params not called"); return -1; }
-    if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_lennard_jones: neighbour lists are stale"); return -1; }
+template<int G, int UNROLL>
+static int pb_launch_lj(pb_ctx *ctx, double cutsq) {
     const int n = ctx->nlocal;
-    if(n == 0) { return 0; }
-    const double cutsq = cutoff * cutoff;
-    const int T = 128, B = pb_blocks(n, T);
+    const int A = 32 / G;
+    const long warps = ((long) n + A - 1) / A;
+    const int T = 128, B = (int) ((warps * 32 + T - 1) / T);
     const bool acc = !ctx->force_is_zero;
-#define PB_LJ(UNI, ACC)                                                                                                   \
-    PB_LAUNCH((pb_k_lennard_jones<UNI, ACC, 4>), B, T, n, ctx->pitch, ctx->pcap, cutsq, ctx->ntypes, ctx->h_eps[0],       \
+#define PB_LJ(UNI, ACC)                                                                                                        \
+    PB_LAUNCH((pb_k_lennard_jones<G, UNI, ACC, UNROLL>), B, T, n, ctx->nslots, ctx->pcap, cutsq, ctx->ntypes, ctx->h_eps[0],   \
               ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh, ctx->force)
     if(ctx->lj_uniform) {
         if(acc) { PB_LJ(true, true); } else { PB_LJ(true, false); }
@@ -156,8 +166,56 @@ extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) {
         if(acc) { PB_LJ(false, true); } else { PB_LJ(false, false); }
     }
 #undef PB_LJ
+    return 0;
+}
+
+template<int G>
+static int pb_launch_lj_u(pb_ctx *ctx, double cutsq) {
+    switch(ctx->lj_unroll) {
+        case 1: return pb_launch_lj<G, 1>(ctx, cutsq);
+        case 2: return pb_launch_lj<G, 2>(ctx, cutsq);
+        case 8: return pb_launch_lj<G, 8>(ctx, cutsq);
+        default: return pb_launch_lj<G, 4>(ctx, cutsq);
+    }
+}
+
+extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "lennard_jones");
+    if(ctx->ntypes == 0) { ctx->set_error("pb_lennard_jones: pb_set_lj_params not called"); return -1; }
+    if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_lennard_jones: neighbour lists are stale"); return -1; }
+    if(ctx->nlocal == 0) { return 0; }
+    const double cutsq = cutoff * cutoff;
+    int rc;
+    switch(ctx->lanes) {
+        case 1: rc = pb_launch_lj_u<1>(ctx, cutsq); break;
+        case 2: rc = pb_launch_lj_u<2>(ctx, cutsq); break;
+        case 4: rc = pb_launch_lj_u<4>(ctx, cutsq); break;
+        case 8: rc = pb_launch_lj_u<8>(ctx, cutsq); break;
+        case 16: rc = pb_launch_lj_u<16>(ctx, cutsq); break;
+        default: ctx->set_error("lanes_per_particle must be 1, 2, 4, 8 or 16"); return -1;
+    }
+    PB_TRY(rc);
     ctx->force_is_zero = false;
     return 0;
+}
+
+// Tuning knobs (bench/ncu sweeps): "lanes_per_particle" (takes effect at the next neighbour-list build), "lj_unroll".
+extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
+    const std::string nm(name);
+    if(nm == "lanes_per_particle") {
+        if(value != 1 && value != 2 && value != 4 && value != 8 && value != 16) { ctx->set_error("lanes_per_particle must be 1, 2, 4, 8 or 16"); return -1; }
+        ctx->lanes = value;
+        ctx->neigh_n = -1;      // lists must be rebuilt in the new layout
+        return 0;
+    }
+    if(nm == "lj_unroll") {
+        if(value != 1 && value != 2 && value != 4 && value != 8) { ctx->set_error("lj_unroll must be 1, 2, 4 or 8"); return -1; }
+        ctx->lj_unroll = value;
+        return 0;
+    }
+    ctx->set_error("pb_set_option: unknown option " + nm);
+    return -1;
 }
 
 // ---- velocity Verlet (examples/md.py:11-17) -------------------------------------------------------------------

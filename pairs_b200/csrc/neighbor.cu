@@ -5,8 +5,8 @@
 // 27 stencil cells `particle_cell[i] + stencil[k]` that satisfy 0 < cell < ncells (flat-index test only, no per-axis
 // wrap test), and append every j != i with  (dx*dx + dy*dy) + dz*dz < cutoff^2  (separate fp64 multiplies and adds,
 // no FMA contraction) -- so the neighbour SETS are bit-identical to the reference's.  Storage differs:
-//   neigh[k * pitch + i]  (k-th neighbour of i; a warp reads 32 consecutive ints per k) instead of AoS [i][k];
-//   inside a list, neighbours are in ascending cell order, and ascending index inside a cell (deterministic).
+//   interleaved sliced ELLPACK (PbNeighLayout in ctx.cuh: a warp reads 32 consecutive ints per iteration) instead of
+//   AoS [i][k]; inside a list, neighbours are in ascending cell order, ascending index inside a cell (deterministic).
 // The three z-adjacent stencil cells of one (dx,dy) row are consecutive flat indices, so each row is ONE
 // contiguous run of the CSR cell list: 9 runs + cell 0 per particle.
 //
@@ -17,7 +17,7 @@
 #include "ctx.cuh"
 
 template<bool STORE>
-__global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncells, int dim1, int dim2, int ncap, int pitch,
+__global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncells, int dim1, int dim2, int ncap, PbNeighLayout lay,
                                                             double cutsq, const double4 *__restrict__ pos,
                                                             const int *__restrict__ flags, const int *__restrict__ particle_cell,
                                                             const int *__restrict__ cell_start, const int *__restrict__ cell_list,
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int count = 0;
     if(i < nlocal && (flags[i] & PB_FLAG_FIXED) == 0) {
-        const double4 pi = pos[i];
+        const double4 pi = pb_ld_pos(pos + i);
         const int pc = particle_cell[i];
         // run 0: cell 0; runs 1..9: rows (dx,dy) in stencil order, each covering dz = -1,0,+1
         for(int run = 0; run < 10; run++) {
@@ -44,13 +44,13 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
             for(int k = b; k < e; k++) {
                 const int j = cell_list[k];
                 if(j == i) { continue; }
-                const double4 pj = pos[j];
+                const double4 pj = pb_ld_pos(pos + j);
                 const double dx = __dsub_rn(pi.x, pj.x);
                 const double dy = __dsub_rn(pi.y, pj.y);
                 const double dz = __dsub_rn(pi.z, pj.z);
                 const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                 if(rsq < cutsq) {
-                    if(STORE && count < ncap) { neigh[(size_t) count * pitch + i] = j; }
+                    if(STORE && count < ncap) { neigh[lay.idx(i, count)] = j; }
                     count++;
                 }
             }
@@ -64,8 +64,18 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
     if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(max_count, m); }
 }
 
-static int pb_alloc_neigh(pb_ctx *ctx, int ncap, int pitch) {
-    const size_t bytes = sizeof(int) * (size_t) ncap * (size_t) pitch;
+static PbNeighLayout pb_layout(const pb_ctx *ctx) {
+    PbNeighLayout lay;
+    lay.G = ctx->lanes;
+    lay.A = 32 / ctx->lanes;
+    lay.T = (ctx->ncap + ctx->lanes - 1) / ctx->lanes;
+    return lay;
+}
+
+static int pb_alloc_neigh(pb_ctx *ctx, int n) {
+    const PbNeighLayout lay = pb_layout(ctx);
+    const size_t groups = ((size_t) n + lay.A - 1) / lay.A;
+    const size_t bytes = sizeof(int) * groups * (size_t) lay.T * 32;
     if(bytes > ctx->neigh_bytes) {
         if(ctx->neigh != nullptr) { PB_CHECK(cudaFree(ctx->neigh)); ctx->neigh = nullptr; }
         const size_t want = bytes + bytes / 8;
@@ -86,14 +96,13 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
     ctx->neigh_n = n;
     if(n == 0) { ctx->max_neigh = 0; return 0; }
     const double cutsq = cutoff * cutoff;
-    const int pitch = (n + 31) / 32 * 32;
     if(ctx->ncap <= 0) { ctx->ncap = 100; }   // neighbor_capacity default of pairs.simulation() (src/pairs/__init__.py:16)
     for(int attempt = 0; attempt < 8; attempt++) {
-        PB_TRY(pb_alloc_neigh(ctx, ctx->ncap, pitch));
-        ctx->pitch = pitch;
+        PB_TRY(pb_alloc_neigh(ctx, n));
+        ctx->nslots = pb_layout(ctx).T;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
         PB_LAUNCH(pb_k_build_neighbors<true>, pb_blocks(n, 128), 128, n, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], ctx->ncap,
-                  pitch, cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->neigh, ctx->numneigh,
+                  pb_layout(ctx), cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->neigh, ctx->numneigh,
                   ctx->d_scalars);
         PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -109,12 +118,12 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
 extern "C" int pb_neighbor_capacity(const pb_ctx *ctx) { return ctx->ncap; }
 extern "C" int pb_max_neighbors(const pb_ctx *ctx) { return ctx->max_neigh; }
 
-__global__ void pb_k_neigh_to_aos(int n, int cap_out, int ncap, int pitch, const int *__restrict__ neigh,
+__global__ void pb_k_neigh_to_aos(int n, int cap_out, int ncap, PbNeighLayout lay, const int *__restrict__ neigh,
                                   const int *__restrict__ numneigh, int *__restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) { return; }
     const int c = min(numneigh[i], min(cap_out, ncap));
-    for(int k = 0; k < c; k++) { out[(size_t) i * cap_out + k] = neigh[(size_t) k * pitch + i]; }
+    for(int k = 0; k < c; k++) { out[(size_t) i * cap_out + k] = neigh[lay.idx(i, k)]; }
     for(int k = c; k < cap_out; k++) { out[(size_t) i * cap_out + k] = -1; }
 }
 
@@ -124,7 +133,7 @@ extern "C" int pb_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
     if(n == 0) { return 0; }
     int *stage = nullptr;
     PB_CHECK(cudaMalloc(&stage, sizeof(int) * (size_t) n * (size_t) capacity));
-    PB_LAUNCH(pb_k_neigh_to_aos, pb_blocks(n, 128), 128, n, capacity, ctx->ncap, ctx->pitch, ctx->neigh, ctx->numneigh, stage);
+    PB_LAUNCH(pb_k_neigh_to_aos, pb_blocks(n, 128), 128, n, capacity, ctx->ncap, pb_layout(ctx), ctx->neigh, ctx->numneigh, stage);
     PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(int) * (size_t) n * (size_t) capacity, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     PB_CHECK(cudaFree(stage));
