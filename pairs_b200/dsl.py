@@ -1,0 +1,515 @@
+"""The `pairs` DSL surface (src/pairs/__init__.py:9-67, Simulation methods src/pairs/sim/simulation.py:37-452) on top of
+the B200 backend: examples/md.py runs unchanged, but generate() plans the per-timestep procedure list
+(sim/simulation.py:387-417) and RUNS it on the GPU through the C-ABI shim instead of printing C++/CUDA source.
+
+User kernels are ordinary Python functions (examples/md.py:5-17).  The reference lowers them through an IR
+(mapping/funcs.py:285-334); this backend RECOGNISES them: the function's AST is unified with the templates of the
+hand-written kernel families below (names of properties / symbols are free, structure and literals must match) and
+bound to the corresponding CUDA kernel.  Anything else fails loudly -- there is no CPU fallback and no generic codegen
+(SURVEY.md section 8f row 3 is "next").
+"""
+import ast
+import inspect
+import math
+import os
+import sys
+import textwrap
+import time
+
+import numpy as np
+
+_builtin_float = float     # the façade defines pairs.float() below
+
+
+# ---- enums of the façade (src/pairs/ir/types.py, sim/shapes.py, sim/domain_partitioners.py, code_gen/target.py) --------
+class Types:
+    Int32, Float, Double, Real, Vector, Matrix, Quaternion = range(7)
+
+
+class Shapes:
+    Sphere, Halfspace, PointMass = 0, 1, 2
+
+
+class DomainPartitioners:
+    Regular, RegularXY = 0, 1
+
+
+class Target:
+    def __init__(self, gpu, parallel=False):
+        self.gpu = gpu
+        self.parallel = parallel
+
+    def is_gpu(self):
+        return self.gpu
+
+
+class DslError(RuntimeError):
+    pass
+
+
+# ---- kernel recognition -------------------------------------------------------------------------------------------------
+# Templates: role names starting with `R_` unify with any user name (bound consistently); `P_i` / `P_j` are the particle
+# parameters; DSL keywords (squared_distance, delta, apply) and literals must match exactly.
+TEMPLATES = {
+    # examples/md.py:5-8
+    "lennard_jones": """
+def K(P_i, P_j):
+    L_sr2 = 1.0 / squared_distance(P_i, P_j)
+    L_sr6 = L_sr2 * L_sr2 * L_sr2 * R_sigma6[P_i, P_j]
+    apply(R_force, delta(P_i, P_j) * (48.0 * L_sr6 * (L_sr6 - 0.5) * L_sr2 * R_epsilon[P_i, P_j]))
+""",
+    # examples/md.py:11-13
+    "initial_integrate": """
+def K(P_i):
+    R_velocity[P_i] += (R_dt * 0.5) * R_force[P_i] / R_mass[P_i]
+    R_position[P_i] += R_dt * R_velocity[P_i]
+""",
+    # examples/md.py:16-17
+    "final_integrate": """
+def K(P_i):
+    R_velocity[P_i] += (R_dt * 0.5) * R_force[P_i] / R_mass[P_i]
+""",
+}
+
+
+def _unify(t, u, binding):
+    """Structural unification of template AST `t` with user AST `u`."""
+    if isinstance(t, ast.Name):
+        if not isinstance(u, ast.Name):
+            return False
+        if t.id[:2] in ("R_", "P_", "L_"):
+            if t.id in binding:
+                return binding[t.id] == u.id
+            if t.id[:2] != "R_" and u.id in binding.values():
+                return False
+            binding[t.id] = u.id
+            return True
+        return t.id == u.id
+    if type(t) is not type(u):
+        return False
+    if isinstance(t, ast.Constant):
+        return type(t.value) is type(u.value) and t.value == u.value
+    if isinstance(t, ast.arg):
+        binding.setdefault(t.arg, u.arg)
+        return binding[t.arg] == u.arg
+    for field in t._fields:
+        if field in ("ctx", "lineno", "col_offset", "end_lineno", "end_col_offset", "type_comment", "kind", "decorator_list",
+                     "returns", "name", "type_params"):
+            continue
+        a, b = getattr(t, field, None), getattr(u, field, None)
+        if isinstance(a, list):
+            if not isinstance(b, list) or len(a) != len(b):
+                return False
+            if not all(_unify(x, y, binding) for x, y in zip(a, b)):
+                return False
+        elif isinstance(a, ast.AST):
+            if not isinstance(b, ast.AST) or not _unify(a, b, binding):
+                return False
+        elif a != b:
+            return False
+    return True
+
+
+def recognise(func):
+    """-> (family, {role: user name}) or raises DslError."""
+    src = textwrap.dedent(inspect.getsource(func))
+    tree = ast.parse(src).body[0]
+    if not isinstance(tree, ast.FunctionDef):
+        raise DslError(f"{func.__name__}: not a plain function")
+    for family, tsrc in TEMPLATES.items():
+        ttree = ast.parse(textwrap.dedent(tsrc)).body[0]
+        binding = {}
+        if _unify(ttree.args, tree.args, binding) and _unify_body(ttree.body, tree.body, binding):
+            return family, {k[2:]: v for k, v in binding.items() if k.startswith("R_")}
+    raise DslError(
+        f"kernel '{func.__name__}' is not one of the kernel families this backend implements in CUDA "
+        f"({', '.join(TEMPLATES)}); there is no generic code generator and no CPU fallback")
+
+
+def _unify_body(tb, ub, binding):
+    ub = [s for s in ub if not (isinstance(s, ast.Expr) and isinstance(s.value, ast.Constant))]   # docstrings
+    return len(tb) == len(ub) and all(_unify(a, b, binding) for a, b in zip(tb, ub))
+
+
+# ---- the Simulation object ----------------------------------------------------------------------------------------------
+class _Prop:
+    def __init__(self, name, ptype, value, volatile):
+        self.name, self.type, self.value, self.volatile = name, ptype, value, volatile
+
+
+def _fmt(x):
+    """std::ostream default formatting of a double (precision 6, %g-like) as used by runtime/thermo.hpp:47."""
+    return f"{x:.6g}"
+
+
+class Simulation:
+    def __init__(self, ref, shapes=None, dims=3, timesteps=100, double_prec=False, use_contact_history=False,
+                 particle_capacity=800000, neighbor_capacity=100, debug=False):
+        if dims != 3:
+            raise DslError("only 3-D simulations are supported")
+        self.ref = ref
+        self.shapes = list(shapes) if shapes is not None else [Shapes.PointMass]     # legacy API: shapes optional
+        self.ntimesteps = timesteps
+        self.double_prec = double_prec
+        self.use_contact_history = use_contact_history
+        self.particle_capacity = particle_capacity
+        self.neighbor_capacity = neighbor_capacity
+        self.debug = debug
+        self.props = {}
+        self.position_name = None
+        self.features = {}
+        self.feature_props = {}
+        self.contact_props = {}
+        self._target = None
+        self._partitioner = DomainPartitioners.Regular
+        self._pbc = [True, True, True]
+        self.grid = None
+        self.reneighbor_frequency = 1            # sim/simulation.py:89
+        self._compute_thermo = 0
+        self.cell_spacing = None
+        self.neighbor_cutoff = None
+        self.setups = []
+        self.pre_step = []
+        self.functions = []
+        self.vtk_file = None
+        self.ctx = None
+        self.thermo_log = []
+        for n in ("uid", "shape", "flags"):     # implicit properties, sim/simulation.py:63-65
+            self.props[n] = _Prop(n, Types.Int32, 0, False)
+
+    # -- configuration (names, defaults and call-order tolerance of the reference) --
+    def target(self, t):
+        self._target = t
+
+    def set_domain_partitioner(self, p):
+        if p not in (DomainPartitioners.Regular, DomainPartitioners.RegularXY):
+            raise Exception("Invalid domain partitioner.")
+        self._partitioner = p
+
+    def partitioner(self):
+        return self._partitioner
+
+    def pbc(self, cfg):
+        assert len(cfg) == 3, "PBC must be specified for each dimension."
+        self._pbc = list(cfg)
+
+    def compute_half(self):
+        raise DslError("compute_half() (Newton-3 half lists) is not implemented by this backend yet (SURVEY.md 8f rank 1)")
+
+    def add_property(self, name, ptype, value=0.0, volatile=False):
+        assert name not in self.props, f"Property already defined: {name}"
+        self.props[name] = _Prop(name, ptype, value, volatile)
+        return self.props[name]
+
+    def add_position(self, name, value=(0.0, 0.0, 0.0), volatile=False, layout=None):
+        assert name not in self.props, f"Property already defined: {name}"
+        self.position_name = name
+        self.props[name] = _Prop(name, Types.Vector, value, volatile)
+        return self.props[name]
+
+    def add_feature(self, name, nkinds):
+        assert name not in self.features, f"Feature already defined: {name}"
+        self.features[name] = nkinds
+
+    def add_feature_property(self, feature, name, ptype, data):
+        assert feature in self.features, f"Feature not found: {feature}"
+        nk = self.features[feature]
+        assert len(data) == nk * nk
+        self.feature_props[name] = (feature, [_builtin_float(x) for x in data])
+
+    def add_contact_property(self, name, ptype, default, layout=None):
+        self.contact_props[name] = (ptype, default)
+
+    # legacy API used by examples/lj_onetype.py (absent from the reference)
+    def add_real_property(self, name, value=0.0, vol=False):
+        return self.add_property(name, Types.Real, value, vol)
+
+    def add_vector_property(self, name, value=(0.0, 0.0, 0.0), vol=False):
+        return self.add_property(name, Types.Vector, value, vol)
+
+    def set_domain(self, grid):
+        self.grid = [_builtin_float(g) for g in grid]       # xmin, ymin, zmin, xmax, ymax, zmax (sim/simulation.py:228)
+
+    def reneighbor_every(self, n):
+        self.reneighbor_frequency = n
+
+    def compute_thermo(self, every=0):
+        self._compute_thermo = every
+
+    def vtk_output(self, filename, frequency=0):
+        self.vtk_file = filename                   # VTK output is out of scope (debug output); ignored
+
+    def copper_fcc_lattice(self, nx, ny, nz, rho, temperature, ntypes):
+        lattice = pow((4.0 / rho), (1.0 / 3.0))    # sim/copper_fcc_lattice.py:19-23
+        self.set_domain([0.0, 0.0, 0.0, nx * lattice, ny * lattice, nz * lattice])
+        self.setups.append(("copper_fcc_lattice", (nx, ny, nz, rho, temperature, ntypes)))
+
+    def read_particle_data(self, filename, prop_names, shape_id):
+        self.setups.append(("read_particle_data", (filename, list(prop_names), shape_id)))
+
+    def from_file(self, filename, prop_names):      # legacy
+        self.read_particle_data(filename, prop_names, Shapes.PointMass)
+
+    def dem_sc_grid(self, *args):
+        raise DslError("dem_sc_grid: the DEM path is not implemented by this backend yet (SURVEY.md 8a rows a10-a13)")
+
+    def setup(self, func, symbols={}):
+        raise DslError("setup(): only the MD (Lennard-Jones) path is implemented by this backend so far")
+
+    def build_cell_lists(self, spacing, store_neighbors_per_cell=False):
+        if store_neighbors_per_cell:
+            raise DslError("store_neighbors_per_cell is not implemented (SURVEY.md 8f rank 2)")
+        self.cell_spacing = spacing
+
+    def build_neighbor_lists(self, spacing):
+        self.cell_spacing = spacing                 # sim/simulation.py:255-261: cells and lists share the spacing
+        self.neighbor_cutoff = spacing
+
+    def compute(self, func, cutoff_radius=None, symbols={}, pre_step=False, skip_first=False):
+        family, roles = recognise(func)
+        entry = {"name": func.__name__, "family": family, "roles": roles, "cutoff": cutoff_radius, "symbols": dict(symbols),
+                 "skip_first": skip_first, "globals": func.__globals__}
+        (self.pre_step if pre_step else self.functions).append(entry)
+
+    # -- helpers --
+    def _symbol(self, entry, role):
+        name = entry["roles"][role]
+        if name in entry["symbols"]:
+            return _builtin_float(entry["symbols"][name])
+        if name in entry["globals"] and isinstance(entry["globals"][name], (int, float)):
+            return _builtin_float(entry["globals"][name])
+        raise DslError(f"{entry['name']}: symbol '{name}' has no value (pass it in symbols={{...}})")
+
+    def _check_prop(self, entry, role, expected):
+        name = entry["roles"][role]
+        if name not in self.props and name not in self.feature_props:
+            raise DslError(f"{entry['name']}: '{name}' is not a registered property")
+        return name
+
+    # -- generate(): plan + run on the GPU(s) --
+    def generate(self):
+        assert self._target is not None, "Target not specified!"
+        if not self._target.is_gpu():
+            raise DslError("this backend executes on B200 GPUs only: use pairs.target_gpu() (there is no CPU path; the "
+                           "reference's own CPU build is available as the parity oracle under oracle/)")
+        # real_t is double throughout the reference runtime (runtime/pairs_common.hpp:7, MPI_DOUBLE hard-coded): all
+        # arithmetic here is fp64 whatever double_prec says
+        from . import backend
+        rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        if self.grid is None:
+            raise DslError("no domain: call set_domain() or copper_fcc_lattice()")
+        g = self.grid
+        grid = [g[0], g[3], g[1], g[4], g[2], g[5]]
+        ctx = backend.Context(local)
+        self.ctx = ctx
+        ctx.init_domain(grid, self._pbc, self._partitioner, world, rank)
+        if world > 1:
+            ctx.nccl_init(_broadcast_nccl_id(backend, rank, world))
+        ctx.reserve(0, self.neighbor_capacity)
+        if self.cell_spacing is None:
+            raise DslError("build_cell_lists() / build_neighbor_lists() was not called")
+
+        # ---- set-up ----
+        nlocal = 0
+        for kind, args in self.setups:
+            if kind == "copper_fcc_lattice":
+                nx, ny, nz, rho, temp, ntypes = args
+                nlocal = ctx.copper_fcc_lattice(nx, ny, nz, rho, ntypes)
+                ctx.adjust_thermo(temp)
+            elif kind == "read_particle_data":
+                nlocal = self._read_particle_data(ctx, *args)
+        ctx.setup_cells(self.cell_spacing)
+
+        # ---- bind kernels ----
+        plan_pre, plan_fn = [self._bind(ctx, e) for e in self.pre_step], [self._bind(ctx, e) for e in self.functions]
+        native = self._native_md_params(plan_pre, plan_fn)
+
+        # ---- timestep loop (sim/timestep.py:9-72) ----
+        ctx.timers_enable(True)
+        ctx.sync()
+        t0 = time.perf_counter()
+        nsteps = self.ntimesteps + 1
+        if native is not None:
+            th = ctx.md_run(0, nsteps, *native)
+            for row in th:
+                self._thermo_line(rank, int(row[0]), row[1], row[2])
+        else:
+            self._python_loop(ctx, plan_pre, plan_fn, nsteps, rank)
+        ctx.sync()
+        all_ms = (time.perf_counter() - t0) * 1e3
+        self._print_summary(ctx, all_ms, rank)
+        return ctx
+
+    def _bind(self, ctx, e):
+        fam = e["family"]
+        if fam == "lennard_jones":
+            if self.neighbor_cutoff is None:
+                raise DslError("lennard_jones needs build_neighbor_lists()")
+            eps_name, sig_name = e["roles"]["epsilon"], e["roles"]["sigma6"]
+            for n in (eps_name, sig_name):
+                if n not in self.feature_props:
+                    raise DslError(f"{e['name']}: '{n}' must be a feature property (add_feature_property)")
+            feat = self.feature_props[eps_name][0]
+            nk = self.features[feat]
+            ctx.set_lj_params(nk, self.feature_props[eps_name][1], self.feature_props[sig_name][1])
+            self._check_prop(e, "force", Types.Vector)
+            cutoff = _builtin_float(e["cutoff"])
+            return dict(e, call=lambda: ctx.lennard_jones(cutoff), cutoff_value=cutoff)
+        if fam in ("initial_integrate", "final_integrate"):
+            dt = self._symbol(e, "dt")
+            for role in ("velocity", "force", "mass"):
+                self._check_prop(e, role, None)
+            if fam == "initial_integrate":
+                if e["roles"]["position"] != self.position_name:
+                    raise DslError(f"{e['name']}: '{e['roles']['position']}' is not the position property")
+                return dict(e, call=lambda: ctx.initial_integrate(dt), dt=dt)
+            return dict(e, call=lambda: ctx.final_integrate(dt), dt=dt)
+        raise DslError(f"unbound kernel family {fam}")
+
+    def _native_md_params(self, pre, fn):
+        """The standard md.py procedure list runs in the native loop (pb_md_run); anything else in the Python loop."""
+        if [p["family"] for p in pre] == ["initial_integrate"] and [f["family"] for f in fn] == ["lennard_jones", "final_integrate"] \
+                and pre[0]["skip_first"] and fn[1]["skip_first"] and not fn[0]["skip_first"] and pre[0]["dt"] == fn[1]["dt"]:
+            return (pre[0]["dt"], fn[0]["cutoff_value"], self.neighbor_cutoff, self.cell_spacing, self.reneighbor_frequency,
+                    self._compute_thermo)
+        return None
+
+    def _python_loop(self, ctx, pre, fn, nsteps, rank):
+        for ts in range(nsteps):
+            for p in pre:
+                if ts > 0 or not p["skip_first"]:
+                    p["call"]()
+            if ((ts + 1) % self.reneighbor_frequency) == 0 or ts == 0:
+                ctx.exchange()
+                ctx.borders()
+                ctx.build_cell_lists()
+                if self.neighbor_cutoff is not None:
+                    ctx.build_neighbor_lists(self.neighbor_cutoff)
+            else:
+                ctx.synchronize()
+            ctx.reset_volatile()
+            for f in fn:
+                if ts > 0 or not f["skip_first"]:
+                    f["call"]()
+            if self._compute_thermo > 0 and (((ts + 1) % self._compute_thermo) == 0 or ts == 0):
+                t, p = ctx.compute_thermo()
+                self._thermo_line(rank, ts, t, p)
+
+    def _thermo_line(self, rank, ts, t, p):
+        self.thermo_log.append((ts, t, p))
+        if rank == 0:
+            print(f"{_fmt(t)}\t{_fmt(p)}")       # runtime/thermo.hpp:45-48
+
+    def _print_summary(self, ctx, all_ms, rank):
+        """stdout contract of the reference: all + timer categories + particle counts."""
+        cats = {"communication": ("exchange", "borders", "synchronize"), "neighbors": ("build_cell_lists", "build_neighbor_lists")}
+        lines = [("all", all_ms)]
+        for e in self.pre_step + self.functions:
+            lines.append((e["name"], ctx.timer(e["family"])[0]))
+        for cat, names in cats.items():
+            lines.append((cat, sum(ctx.timer(n)[0] for n in names)))
+        nl, ng = ctx.counts()
+        if rank == 0:
+            for name, ms in lines:
+                print(f"{name}: {_fmt(ms)}")
+            print(f"Number of local particles: {nl} / {nl}")
+            print(f"Number of ghost particles: {ng} / {ng}")
+
+    def _read_particle_data(self, ctx, filename, prop_names, shape_id):
+        """runtime/read_from_file.hpp:33-115: CSV rows, columns in the order of prop_names (vectors = 3 columns)."""
+        path = filename
+        if not os.path.exists(path):
+            alt = os.path.join(os.path.dirname(os.path.abspath(sys.argv[0])), "..", filename)
+            if os.path.exists(alt):
+                path = alt
+            else:
+                raise DslError(f"read_particle_data: {filename} not found")
+        cols = []
+        for n in prop_names:
+            w = 3 if self.props[n].type == Types.Vector else 1
+            cols.append((n, w))
+        data = np.loadtxt(path, delimiter=",", ndmin=2)
+        k = 0
+        arrays = {}
+        for n, w in cols:
+            arrays[n] = data[:, k:k + w] if w > 1 else data[:, k]
+            k += w
+        pos = arrays[self.position_name]
+        vel_name = next((n for n in arrays if "velocity" in n and self.props[n].type == Types.Vector), None)
+        ctx.upload(pos, arrays.get(vel_name), arrays.get("mass"), arrays.get("type"), arrays.get("flags"), arrays.get("uid"),
+                   np.full(len(pos), shape_id, np.int32))
+        return len(pos)
+
+
+def _broadcast_nccl_id(backend, rank, world):
+    """ncclUniqueId from rank 0 to all ranks through the launcher's TCP store (torchrun env: MASTER_ADDR / MASTER_PORT)."""
+    from torch.distributed import TCPStore
+    from datetime import timedelta
+    store = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", 29500)) + 17, world,
+                     is_master=(rank == 0), timeout=timedelta(seconds=120))
+    if rank == 0:
+        store.set("pairs_b200_nccl_id", backend.nccl_unique_id())
+    return bytes(store.get("pairs_b200_nccl_id"))
+
+
+# ---- module-level factory functions (src/pairs/__init__.py:9-67) -------------------------------------------------------
+def simulation(ref, shapes=None, dims=3, timesteps=100, double_prec=False, use_contact_history=False, particle_capacity=800000,
+               neighbor_capacity=100, debug=False):
+    return Simulation(ref, shapes, dims, timesteps, double_prec, use_contact_history, particle_capacity, neighbor_capacity, debug)
+
+
+def target_cpu(parallel=False):
+    return Target(False, parallel)
+
+
+def target_gpu():
+    return Target(True)
+
+
+def int32():
+    return Types.Int32
+
+
+def float():
+    return Types.Float
+
+
+def double():
+    return Types.Double
+
+
+def real():
+    return Types.Real
+
+
+def vector():
+    return Types.Vector
+
+
+def matrix():
+    return Types.Matrix
+
+
+def quaternion():
+    return Types.Quaternion
+
+
+def point_mass():
+    return Shapes.PointMass
+
+
+def sphere():
+    return Shapes.Sphere
+
+
+def halfspace():
+    return Shapes.Halfspace
+
+
+def regular_domain_partitioner():
+    return DomainPartitioners.Regular
+
+
+def regular_domain_partitioner_xy():
+    return DomainPartitioners.RegularXY

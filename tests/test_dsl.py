@@ -1,0 +1,94 @@
+"""The `pairs` DSL surface (CPU part): API names/defaults of the reference façade, kernel recognition, error behaviour."""
+import ast
+import importlib.util
+import os
+import sys
+
+import pytest
+
+import pairs
+from pairs_b200 import dsl
+from tests.conftest import HAS_GPU
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "scripts"))
+
+
+def test_facade_names_of_the_reference_api():
+    # src/pairs/__init__.py:9-67
+    for name in ("simulation", "target_cpu", "target_gpu", "int32", "float", "double", "real", "vector", "matrix", "quaternion",
+                 "point_mass", "sphere", "halfspace", "regular_domain_partitioner", "regular_domain_partitioner_xy"):
+        assert callable(getattr(pairs, name)), name
+    sim = pairs.simulation("md", [pairs.point_mass()], timesteps=200, double_prec=True)
+    # Simulation methods, src/pairs/sim/simulation.py
+    for m in ("target", "add_position", "add_property", "add_feature", "add_feature_property", "add_contact_property", "set_domain",
+              "set_domain_partitioner", "pbc", "copper_fcc_lattice", "dem_sc_grid", "read_particle_data", "setup", "build_cell_lists",
+              "build_neighbor_lists", "reneighbor_every", "compute_half", "compute_thermo", "vtk_output", "compute", "generate",
+              "add_real_property", "add_vector_property", "from_file"):
+        assert callable(getattr(sim, m)), m
+    assert sim.reneighbor_frequency == 1 and sim.particle_capacity == 800000 and sim.neighbor_capacity == 100
+    assert set(sim.props) == {"uid", "shape", "flags"}
+    assert (pairs.sphere(), pairs.halfspace(), pairs.point_mass()) == (0, 1, 2)          # sim/shapes.py
+
+
+def test_recognises_the_md_kernels_with_renamed_properties():
+    import lj_script
+    assert dsl.recognise(lj_script.lennard_jones)[0] == "lennard_jones"
+    fam, roles = dsl.recognise(lj_script.initial_integrate)
+    assert fam == "initial_integrate" and roles["velocity"] == "linear_velocity" and roles["dt"] == "dt"
+    assert dsl.recognise(lj_script.final_integrate)[0] == "final_integrate"
+
+    def lj2(a, b):
+        s2 = 1.0 / squared_distance(a, b)                                   # noqa: F821
+        s6 = s2 * s2 * s2 * sg[a, b]                                        # noqa: F821
+        apply(f, delta(a, b) * (48.0 * s6 * (s6 - 0.5) * s2 * ep[a, b]))    # noqa: F821
+    fam, roles = dsl.recognise(lj2)
+    assert fam == "lennard_jones" and roles == {"sigma6": "sg", "force": "f", "epsilon": "ep"}
+
+
+def test_unknown_kernels_fail_loudly():
+    def morse(i, j):
+        apply(force, delta(i, j) * 2.0)      # noqa: F821
+
+    def lj_wrong_constant(i, j):
+        sr2 = 1.0 / squared_distance(i, j)                                               # noqa: F821
+        sr6 = sr2 * sr2 * sr2 * sigma6[i, j]                                             # noqa: F821
+        apply(force, delta(i, j) * (24.0 * sr6 * (sr6 - 0.5) * sr2 * epsilon[i, j]))     # noqa: F821
+    for k in (morse, lj_wrong_constant):
+        with pytest.raises(dsl.DslError, match="not one of the kernel families"):
+            dsl.recognise(k)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference checkout not present")
+def test_recognises_the_reference_example_functions_verbatim(tmp_path):
+    src = open("/root/reference/examples/md.py").read()
+    got = {}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef):
+            p = tmp_path / f"k_{node.name}.py"
+            p.write_text(ast.get_source_segment(src, node) + "\n")
+            spec = importlib.util.spec_from_file_location(node.name, p)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            got[node.name] = dsl.recognise(getattr(mod, node.name))[0]
+    assert got == {"lennard_jones": "lennard_jones", "initial_integrate": "initial_integrate", "final_integrate": "final_integrate"}
+
+
+def test_plan_and_error_behaviour():
+    import lj_script
+    psim = lj_script.build("gpu", 8, 100, 20, 10)
+    assert [e["family"] for e in psim.pre_step] == ["initial_integrate"]
+    assert [e["family"] for e in psim.functions] == ["lennard_jones", "final_integrate"]
+    assert psim.cell_spacing == 2.5 + 0.3 and psim.neighbor_cutoff == 2.5 + 0.3
+    L = 8 * pow(4.0 / 0.8442, 1.0 / 3.0)
+    assert psim.grid == [0.0, 0.0, 0.0, L, L, L]
+    cpu = lj_script.build("cpu", 8, 10, 20, 10)
+    with pytest.raises(dsl.DslError, match="B200 GPUs only"):
+        cpu.generate()
+    with pytest.raises(dsl.DslError):
+        psim.compute_half()
+    assert dsl._fmt(1.44) == "1.44" and dsl._fmt(1.215643219) == "1.21564" and dsl._fmt(0.6928049) == "0.692805"
+    if not HAS_GPU:
+        from pairs_b200.backend import BackendError
+        with pytest.raises(BackendError):
+            psim.generate()
