@@ -186,13 +186,14 @@ extern "C" int pb_borders(pb_ctx *ctx) {
 // corner image, whose source is itself a ghost) therefore carries the coordinates its source ghost had BEFORE this
 // refresh -- one step stale per forwarding level.  That behaviour is part of the reference's results and is
 // reproduced here by construction: one pack kernel over all entries, then one unpack kernel.
-__global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, PbBox box, const int *__restrict__ send_map,
+__global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, int nlocal, PbBox box, const int *__restrict__ send_map,
                                                       const int *__restrict__ send_mult, const double4 *__restrict__ pos,
-                                                      const double *__restrict__ vel, double *__restrict__ buf) {
+                                                      const double4 *__restrict__ pos_ghost, const double *__restrict__ vel,
+                                                      double *__restrict__ buf) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= count) { return; }
     const int p = send_map[e];
-    const double4 x = pos[p];
+    const double4 x = (p < nlocal) ? pos[p] : pos_ghost[p];     // ghosts: the values of the previous refresh
     double *b = buf + (size_t) e * SYNC_ELEMS;
     b[0] = __dadd_rn(x.x, __dmul_rn((double) send_mult[e * 3 + 0], box.len[0]));
     b[1] = __dadd_rn(x.y, __dmul_rn((double) send_mult[e * 3 + 1], box.len[1]));
@@ -203,12 +204,13 @@ __global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, PbBox 
 }
 
 __global__ void __launch_bounds__(256) pb_k_unpack_sync(int count, int dst0, int cap, const double *__restrict__ buf,
-                                                        double4 *__restrict__ pos, double *__restrict__ vel) {
+                                                        const double4 *__restrict__ pos_ghost, double4 *__restrict__ pos,
+                                                        double *__restrict__ vel) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= count) { return; }
     const double *b = buf + (size_t) k * SYNC_ELEMS;
     const int p = dst0 + k;
-    const double w = pos[p].w;
+    const double w = pos_ghost[p].w;
     pos[p] = make_double4(b[0], b[1], b[2], w);
     vel[p] = b[3];
     vel[cap + p] = b[4];
@@ -218,15 +220,17 @@ __global__ void __launch_bounds__(256) pb_k_unpack_sync(int count, int dst0, int
 extern "C" int pb_synchronize(pb_ctx *ctx) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "synchronize");
+    const double4 *pos_ghost = ctx->ghosts_in_alt ? ctx->pos_alt : ctx->pos;
     if(ctx->nsend_all > 0) {
-        PB_LAUNCH(pb_k_pack_sync, pb_blocks(ctx->nsend_all, 256), 256, ctx->nsend_all, ctx->pcap, pb_box(ctx), ctx->send_map,
-                  ctx->send_mult, ctx->pos, ctx->vel, ctx->send_buf);
+        PB_LAUNCH(pb_k_pack_sync, pb_blocks(ctx->nsend_all, 256), 256, ctx->nsend_all, ctx->pcap, ctx->nlocal, pb_box(ctx), ctx->send_map,
+                  ctx->send_mult, ctx->pos, pos_ghost, ctx->vel, ctx->send_buf);
     }
     const double *src = nullptr;
     PB_TRY(pb_transport_data(ctx, 0, 3, SYNC_ELEMS, &src));
     if(ctx->nghost > 0) {
-        PB_LAUNCH(pb_k_unpack_sync, pb_blocks(ctx->nghost, 256), 256, ctx->nghost, ctx->nlocal, ctx->pcap, src, ctx->pos, ctx->vel);
+        PB_LAUNCH(pb_k_unpack_sync, pb_blocks(ctx->nghost, 256), 256, ctx->nghost, ctx->nlocal, ctx->pcap, src, pos_ghost, ctx->pos, ctx->vel);
     }
+    ctx->ghosts_in_alt = false;
     return 0;
 }
 
@@ -261,6 +265,7 @@ extern "C" int pb_exchange(pb_ctx *ctx) {
     ctx->nsend_all = 0;
     ctx->cells_n = 0;
     ctx->neigh_n = -1;
+    ctx->ghosts_in_alt = false;
     for(int dim = 0; dim < 3; dim++) {
         if(ctx->nranks[dim] == 1) {
             if(ctx->nlocal == 0) { continue; }

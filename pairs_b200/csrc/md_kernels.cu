@@ -24,13 +24,24 @@
 // tag/sector traffic of the gather low (ncu: the thread-per-particle version ran at 94 % L1TEX throughput).
 // UNROLL iterations are issued back to back so UNROLL gathers are in flight per lane.  Per-lane partial forces are
 // combined with warp shuffles in a fixed tree (deterministic); lane 0 of the group writes.
-template<int G, bool UNIFORM, bool ACCUMULATE, int UNROLL>
+//
+// FUSE (bit mask) folds the per-particle streaming kernels that surround the force evaluation in the generated loop
+// into this kernel's epilogue -- the thread that owns particle i already holds f_i, so v_i, m_i and x_i are touched
+// once instead of three times per step (444 B instead of 586 B per particle and step, two launches fewer):
+//   bit 0: final_integrate of THIS step   v += ((dt*0.5)*f)/m                       (examples/md.py:16-17)
+//   bit 1: initial_integrate of the NEXT step   v += ((dt*0.5)*f)/m ; x += dt*v    (examples/md.py:11-13)
+// The new positions go to a second buffer (pos_next), because other threads still gather the old ones; the buffers
+// are swapped by the host.  Per particle the operations and their order are exactly those of the separate kernels,
+// so the fused loop is bit-identical to the unfused one (tests/test_gpu_md.py::test_fused_loop_is_bit_identical).
+template<int G, bool UNIFORM, bool ACCUMULATE, int UNROLL, int FUSE>
 __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int cap, double cutsq, int ntypes,
                                                           double eps_u, double sig6_u,
                                                           const double *__restrict__ eps_t, const double *__restrict__ sig6_t,
                                                           const double4 *__restrict__ pos, const int *__restrict__ flags,
                                                           const int *__restrict__ numneigh, const int *__restrict__ neigh,
-                                                          double *__restrict__ force) {
+                                                          double *__restrict__ force, double dt, double half_dt,
+                                                          const double *__restrict__ mass, double *__restrict__ vel,
+                                                          double4 *__restrict__ pos_next) {
     constexpr int A = 32 / G;
     __shared__ double s_eps[64], s_sig6[64];
     if(!UNIFORM) {
@@ -44,8 +55,9 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int
     const bool live = i < nlocal;
     const bool fixed = live && (flags[i] & PB_FLAG_FIXED) != 0;
     double fx = 0.0, fy = 0.0, fz = 0.0;
+    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
+    if(live) { pi = pb_ld_pos(pos + i); }
     if(live && !fixed) {
-        const double4 pi = pb_ld_pos(pos + i);
         const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * ntypes;
         const int nn = numneigh[i];
         const int iters = (nn + G - 1) / G;
@@ -101,14 +113,43 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int
     // (ACCUMULATE == false) the old value is the freshly written 0.0, also for FIXED particles.
     if(ACCUMULATE) {
         if(!fixed) {
-            force[i] = __dadd_rn(force[i], fx);
-            force[cap + i] = __dadd_rn(force[cap + i], fy);
-            force[2 * cap + i] = __dadd_rn(force[2 * cap + i], fz);
+            fx = __dadd_rn(force[i], fx);
+            fy = __dadd_rn(force[cap + i], fy);
+            fz = __dadd_rn(force[2 * cap + i], fz);
+            force[i] = fx;
+            force[cap + i] = fy;
+            force[2 * cap + i] = fz;
         }
     } else {
-        force[i] = __dadd_rn(0.0, fx);
-        force[cap + i] = __dadd_rn(0.0, fy);
-        force[2 * cap + i] = __dadd_rn(0.0, fz);
+        fx = __dadd_rn(0.0, fx);
+        fy = __dadd_rn(0.0, fy);
+        fz = __dadd_rn(0.0, fz);
+        force[i] = fx;
+        force[cap + i] = fy;
+        force[2 * cap + i] = fz;
+    }
+    if(FUSE != 0) {
+        if(!fixed) {
+            const double m = mass[i];
+            double vx = vel[i], vy = vel[cap + i], vz = vel[2 * cap + i];
+            if(FUSE & 1) {
+                vx = __dadd_rn(vx, __ddiv_rn(__dmul_rn(half_dt, fx), m));
+                vy = __dadd_rn(vy, __ddiv_rn(__dmul_rn(half_dt, fy), m));
+                vz = __dadd_rn(vz, __ddiv_rn(__dmul_rn(half_dt, fz), m));
+            }
+            if(FUSE & 2) {
+                vx = __dadd_rn(vx, __ddiv_rn(__dmul_rn(half_dt, fx), m));
+                vy = __dadd_rn(vy, __ddiv_rn(__dmul_rn(half_dt, fy), m));
+                vz = __dadd_rn(vz, __ddiv_rn(__dmul_rn(half_dt, fz), m));
+                pi.x = __dadd_rn(pi.x, __dmul_rn(dt, vx));
+                pi.y = __dadd_rn(pi.y, __dmul_rn(dt, vy));
+                pi.z = __dadd_rn(pi.z, __dmul_rn(dt, vz));
+            }
+            vel[i] = vx;
+            vel[cap + i] = vy;
+            vel[2 * cap + i] = vz;
+        }
+        if(FUSE & 2) { pos_next[i] = pi; }
     }
 }
 
@@ -150,16 +191,17 @@ int pb_materialise_force_reset(pb_ctx *ctx) {
     return 0;
 }
 
-template<int G, int UNROLL>
-static int pb_launch_lj(pb_ctx *ctx, double cutsq) {
+template<int G, int UNROLL, int FUSE>
+static int pb_launch_lj(pb_ctx *ctx, double cutsq, double dt) {
     const int n = ctx->nlocal;
     const int A = 32 / G;
     const long warps = ((long) n + A - 1) / A;
     const int T = 128, B = (int) ((warps * 32 + T - 1) / T);
     const bool acc = !ctx->force_is_zero;
 #define PB_LJ(UNI, ACC)                                                                                                        \
-    PB_LAUNCH((pb_k_lennard_jones<G, UNI, ACC, UNROLL>), B, T, n, ctx->nslots, ctx->pcap, cutsq, ctx->ntypes, ctx->h_eps[0],   \
-              ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh, ctx->force)
+    PB_LAUNCH((pb_k_lennard_jones<G, UNI, ACC, UNROLL, FUSE>), B, T, n, ctx->nslots, ctx->pcap, cutsq, ctx->ntypes,            \
+              ctx->h_eps[0], ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh,          \
+              ctx->force, dt, dt * 0.5, ctx->mass, ctx->vel, ctx->pos_alt)
     if(ctx->lj_uniform) {
         if(acc) { PB_LJ(true, true); } else { PB_LJ(true, false); }
     } else {
@@ -169,17 +211,27 @@ static int pb_launch_lj(pb_ctx *ctx, double cutsq) {
     return 0;
 }
 
-template<int G>
-static int pb_launch_lj_u(pb_ctx *ctx, double cutsq) {
+template<int G, int FUSE>
+static int pb_launch_lj_u(pb_ctx *ctx, double cutsq, double dt) {
     switch(ctx->lj_unroll) {
-        case 1: return pb_launch_lj<G, 1>(ctx, cutsq);
-        case 2: return pb_launch_lj<G, 2>(ctx, cutsq);
-        case 8: return pb_launch_lj<G, 8>(ctx, cutsq);
-        default: return pb_launch_lj<G, 4>(ctx, cutsq);
+        case 2: return pb_launch_lj<G, 2, FUSE>(ctx, cutsq, dt);
+        case 8: return pb_launch_lj<G, 8, FUSE>(ctx, cutsq, dt);
+        default: return pb_launch_lj<G, 4, FUSE>(ctx, cutsq, dt);
     }
 }
 
-extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) {
+template<int G>
+static int pb_launch_lj_f(pb_ctx *ctx, double cutsq, double dt, int fuse) {
+    switch(fuse) {
+        case 1: return pb_launch_lj_u<G, 1>(ctx, cutsq, dt);
+        case 2: return pb_launch_lj_u<G, 2>(ctx, cutsq, dt);
+        case 3: return pb_launch_lj_u<G, 3>(ctx, cutsq, dt);
+        default: return pb_launch_lj_u<G, 0>(ctx, cutsq, dt);
+    }
+}
+
+// fuse: bit 0 = final_integrate of this step, bit 1 = initial_integrate of the next step (positions double-buffered)
+int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "lennard_jones");
     if(ctx->ntypes == 0) { ctx->set_error("pb_lennard_jones: pb_set_lj_params not called"); return -1; }
@@ -188,32 +240,40 @@ extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) {
     const double cutsq = cutoff * cutoff;
     int rc;
     switch(ctx->lanes) {
-        case 1: rc = pb_launch_lj_u<1>(ctx, cutsq); break;
-        case 2: rc = pb_launch_lj_u<2>(ctx, cutsq); break;
-        case 4: rc = pb_launch_lj_u<4>(ctx, cutsq); break;
-        case 8: rc = pb_launch_lj_u<8>(ctx, cutsq); break;
-        case 16: rc = pb_launch_lj_u<16>(ctx, cutsq); break;
-        default: ctx->set_error("lanes_per_particle must be 1, 2, 4, 8 or 16"); return -1;
+        case 1: rc = pb_launch_lj_f<1>(ctx, cutsq, dt, fuse); break;
+        case 2: rc = pb_launch_lj_f<2>(ctx, cutsq, dt, fuse); break;
+        case 4: rc = pb_launch_lj_f<4>(ctx, cutsq, dt, fuse); break;
+        case 8: rc = pb_launch_lj_f<8>(ctx, cutsq, dt, fuse); break;
+        default: ctx->set_error("lanes_per_particle must be 1, 2, 4 or 8"); return -1;
     }
     PB_TRY(rc);
     ctx->force_is_zero = false;
+    if(fuse & 2) {
+        // new local positions are in pos_alt; the ghosts of the current step stay behind in the old buffer until the next
+        // synchronize / borders has refreshed them
+        std::swap(ctx->pos, ctx->pos_alt);
+        ctx->ghosts_in_alt = true;
+    }
     return 0;
 }
+
+extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) { return pb_lennard_jones_fused(ctx, cutoff, 0.0, 0); }
 
 // Tuning knobs (bench/ncu sweeps): "lanes_per_particle" (takes effect at the next neighbour-list build), "lj_unroll".
 extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
     const std::string nm(name);
     if(nm == "lanes_per_particle") {
-        if(value != 1 && value != 2 && value != 4 && value != 8 && value != 16) { ctx->set_error("lanes_per_particle must be 1, 2, 4, 8 or 16"); return -1; }
+        if(value != 1 && value != 2 && value != 4 && value != 8) { ctx->set_error("lanes_per_particle must be 1, 2, 4 or 8"); return -1; }
         ctx->lanes = value;
         ctx->neigh_n = -1;      // lists must be rebuilt in the new layout
         return 0;
     }
     if(nm == "lj_unroll") {
-        if(value != 1 && value != 2 && value != 4 && value != 8) { ctx->set_error("lj_unroll must be 1, 2, 4 or 8"); return -1; }
+        if(value != 2 && value != 4 && value != 8) { ctx->set_error("lj_unroll must be 2, 4 or 8"); return -1; }
         ctx->lj_unroll = value;
         return 0;
     }
+    if(nm == "fuse_integrate") { ctx->fuse_integrate = value != 0; return 0; }
     ctx->set_error("pb_set_option: unknown option " + nm);
     return -1;
 }

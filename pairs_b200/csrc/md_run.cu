@@ -6,13 +6,17 @@
 // steps) and capacity counters (every reneighbouring) are read back.
 #include "ctx.cuh"
 
+int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse);
+
 extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(!ctx->cells_set || ctx->spacing != p->cell_spacing) { PB_TRY(pb_setup_cells(ctx, p->cell_spacing)); }
     int nt = 0;
+    bool initial_done = false;     // initial_integrate of this iteration was already applied by the previous force kernel
     for(int ts = ts_begin; ts < ts_end; ts++) {
         const bool reneigh = (((ts + 1) % p->reneighbor_every) == 0) || (ts == 0);
-        if(ts > 0) { PB_TRY(pb_initial_integrate(ctx, p->dt)); }
+        if(ts > 0 && !initial_done) { PB_TRY(pb_initial_integrate(ctx, p->dt)); }
+        initial_done = false;
         if(reneigh) {
             PB_TRY(pb_exchange(ctx));
             PB_TRY(pb_borders(ctx));
@@ -22,9 +26,18 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
             PB_TRY(pb_synchronize(ctx));
         }
         PB_TRY(pb_reset_volatile(ctx));
-        PB_TRY(pb_lennard_jones(ctx, p->cutoff_force));
-        if(ts > 0) { PB_TRY(pb_final_integrate(ctx, p->dt)); }
-        if(p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0)) {
+        const bool thermo_now = p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0);
+        if(ctx->fuse_integrate) {
+            // fold final_integrate(ts) and -- unless thermo must see the velocities in between, or the call ends here --
+            // initial_integrate(ts + 1) into the force kernel
+            int fuse = (ts > 0) ? 1 : 0;
+            if(!thermo_now && ts + 1 < ts_end) { fuse |= 2; initial_done = true; }
+            PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse));
+        } else {
+            PB_TRY(pb_lennard_jones(ctx, p->cutoff_force));
+            if(ts > 0) { PB_TRY(pb_final_integrate(ctx, p->dt)); }
+        }
+        if(thermo_now) {
             double t = 0.0, pr = 0.0;
             PB_TRY(pb_compute_thermo(ctx, &t, &pr));
             if(thermo_out != nullptr && nt < thermo_cap) {
