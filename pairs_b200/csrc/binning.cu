@@ -2,7 +2,7 @@
 // Replaces BuildCellListsStencil / BuildCellLists / PartitionCellLists (sim/cell_lists.py:46-171) and the dense
 // cell_particles[ncells][cell_capacity] array (25.6 MB, 64-slot rows, atomic slot claims) by
 //   particle_cell[i]  -- bit-identical to the reference's value (same fp64 subtract / divide / truncate / clamp)
-//   cell_start[c], cell_list[k]  -- CSR cell list; inside a cell particles are in ascending index order
+//   cell_start[c], cell_list[k]  -- CSR cell list; inside a cell particles are ordered by (sub-cell Morton key, index)
 // so there is no cell_capacity to overflow and the result is run-to-run reproducible.
 //
 // Kernels (all HBM-bound; algorithmic bytes per binned particle: pos 32 + flags 4 + particle_cell 4 w + slot 4 w,
@@ -189,11 +189,26 @@ __device__ __forceinline__ int pb_cell_index(const PbCellGeom &g, double x, doub
     return (c0 * g.dim[1] + c1) * g.dim[2] + c2 + 1;
 }
 
+// Ordering key INSIDE a cell (not a reference quantity, purely a memory-layout choice): 9-bit Morton code of the
+// particle's position in an 8x8x8 sub-grid of its cell.  Particles of a cell are stored in this order, so that
+// consecutive particles -- the 32 lanes of a warp in the force kernel, and the 4 particles of a 128-byte line -- are
+// spatial neighbours at a scale well below the cutoff: the sorted neighbour lists of adjacent lanes then run through
+// nearly the same particles at the same iteration and their 32-byte gathers fall into few distinct L1 lines.
+__device__ __forceinline__ int pb_spread3(int v) { return (v & 1) | ((v & 2) << 2) | ((v & 4) << 4); }
+
+__device__ __forceinline__ int pb_subcell_key(const PbCellGeom &g, double x, double y, double z) {
+    const double q0 = (x - g.lo[0]) / g.spacing, q1 = (y - g.lo[1]) / g.spacing, q2 = (z - g.lo[2]) / g.spacing;
+    int s0 = (int) ((q0 - floor(q0)) * 8.0), s1 = (int) ((q1 - floor(q1)) * 8.0), s2 = (int) ((q2 - floor(q2)) * 8.0);
+    s0 = min(max(s0, 0), 7); s1 = min(max(s1, 0), 7); s2 = min(max(s2, 0), 7);
+    return (pb_spread3(s0) << 2) | (pb_spread3(s1) << 1) | pb_spread3(s2);
+}
+
 // Warp-aggregated histogram: lanes of a warp that hit the same cell elect a leader which issues ONE atomicAdd
 // for the whole group; every lane derives its slot from the leader's base + its rank inside the group.
 __global__ void __launch_bounds__(256) pb_k_cell_count(PbCellGeom g, int first, int n, const double4 *__restrict__ pos,
                                                        const int *__restrict__ flags, int *__restrict__ particle_cell,
-                                                       int *__restrict__ cell_count, int *__restrict__ cell_slot) {
+                                                       int *__restrict__ cell_count, int *__restrict__ cell_slot,
+                                                       int *__restrict__ cell_key) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = k < n;
     int cell = -1;
@@ -201,6 +216,7 @@ __global__ void __launch_bounds__(256) pb_k_cell_count(PbCellGeom g, int first, 
         const double4 p = pos[first + k];
         cell = pb_cell_index(g, p.x, p.y, p.z, flags[first + k]);
         particle_cell[first + k] = cell;
+        cell_key[first + k] = pb_subcell_key(g, p.x, p.y, p.z);
     }
     const unsigned live = __ballot_sync(0xffffffffu, active);
     if(!active) { return; }
@@ -224,17 +240,23 @@ __global__ void __launch_bounds__(256) pb_k_cell_fill(int first, int n, const in
     }
 }
 
-// One thread per cell: insertion sort of the cell's index run (ascending).  Runs are short (mean ~18 at liquid
-// density with cells of one cutoff) and the arrival order is already nearly sorted.
-__global__ void __launch_bounds__(128) pb_k_cell_sort(int ncells, const int *__restrict__ cell_start, int *__restrict__ cell_list) {
+// One thread per cell: insertion sort of the cell's run by (sub-cell Morton key, index) -- a total order, hence
+// deterministic whatever order the atomics delivered.  Runs are short (mean ~18 at liquid density with cells of one
+// cutoff); the 64-bit sort keys live in registers / local memory of the thread.
+__global__ void __launch_bounds__(128) pb_k_cell_sort(int ncells, const int *__restrict__ cell_start, const int *__restrict__ cell_key,
+                                                      int *__restrict__ cell_list) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if(c >= ncells) { return; }
     const int b = cell_start[c], e = cell_start[c + 1];
     for(int i = b + 1; i < e; i++) {
         const int v = cell_list[i];
+        const long long kv = ((long long) cell_key[v] << 32) | (unsigned int) v;
         int j = i - 1;
-        while(j >= b && cell_list[j] > v) {
-            cell_list[j + 1] = cell_list[j];
+        while(j >= b) {
+            const int w = cell_list[j];
+            const long long kw = ((long long) cell_key[w] << 32) | (unsigned int) w;
+            if(kw <= kv) { break; }
+            cell_list[j + 1] = w;
             j--;
         }
         cell_list[j + 1] = v;
@@ -258,12 +280,12 @@ int pb_bin_particles(pb_ctx *ctx, int first, int n, bool /*write_particle_cell*/
     PB_CHECK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(int) * ((size_t) ctx->ncells + 1), ctx->stream));
     if(n > 0) {
         PB_LAUNCH(pb_k_cell_count, pb_blocks(n, 256), 256, pb_geom(ctx), first, n, ctx->pos, ctx->flags, ctx->particle_cell,
-                  ctx->cell_count, ctx->cell_slot);
+                  ctx->cell_count, ctx->cell_slot, ctx->cell_key);
     }
     PB_TRY(pb_exclusive_scan(ctx, ctx->cell_count, ctx->cell_start, ctx->ncells));
     if(n > 0) {
         PB_LAUNCH(pb_k_cell_fill, pb_blocks(n, 256), 256, first, n, ctx->particle_cell, ctx->cell_slot, ctx->cell_start, ctx->cell_list);
-        PB_LAUNCH(pb_k_cell_sort, pb_blocks(ctx->ncells, 128), 128, ctx->ncells, ctx->cell_start, ctx->cell_list);
+        PB_LAUNCH(pb_k_cell_sort, pb_blocks(ctx->ncells, 128), 128, ctx->ncells, ctx->cell_start, ctx->cell_key, ctx->cell_list);
     }
     return 0;
 }

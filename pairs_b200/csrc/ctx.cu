@@ -54,7 +54,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     void *bufs[] = {ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt, ctx->force, ctx->mass, ctx->mass_alt, ctx->type,
                     ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape, ctx->shape_alt, ctx->tag,
                     ctx->tag_alt, ctx->particle_cell, ctx->cell_count, ctx->cell_start, ctx->cell_slot, ctx->cell_list,
-                    ctx->scan_tmp, ctx->neigh, ctx->numneigh, ctx->d_eps, ctx->d_sig6, ctx->send_map, ctx->send_mult,
+                    ctx->cell_key, ctx->scan_tmp, ctx->neigh, ctx->numneigh, ctx->d_eps, ctx->d_sig6, ctx->send_map, ctx->send_mult,
                     ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->d_partial, ctx->d_scalars};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
@@ -119,6 +119,7 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
     PB_TRY(pb_regrow(ctx, &ctx->particle_cell, used, newcap, true));
     PB_TRY(pb_regrow(ctx, &ctx->cell_slot, 0, newcap, false));
     PB_TRY(pb_regrow(ctx, &ctx->cell_list, 0, newcap, false));
+    PB_TRY(pb_regrow(ctx, &ctx->cell_key, 0, newcap, false));
     PB_TRY(pb_regrow(ctx, &ctx->sel_flag, 0, newcap + 1, false));
     PB_TRY(pb_regrow(ctx, &ctx->sel_scan, 0, newcap + 1, false));
     PB_TRY(pb_regrow(ctx, &ctx->numneigh, 0, newcap, false));

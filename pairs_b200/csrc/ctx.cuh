@@ -79,6 +79,7 @@ struct pb_ctx {
     int *cell_start = nullptr;    // [ccap+1]
     int *cell_slot = nullptr;     // [pcap] slot of the particle inside its cell (arrival order, sorted later)
     int *cell_list = nullptr;     // [pcap]
+    int *cell_key = nullptr;      // [pcap] sub-cell Morton key (ordering inside a cell)
     int *scan_tmp = nullptr;      // block sums for the scan
     int scan_tmp_cap = 0;
     int cells_n = 0;              // number of particles binned by the last pb_build_cell_lists
