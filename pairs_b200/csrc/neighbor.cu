@@ -28,6 +28,9 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
     if(i < nlocal && (flags[i] & PB_FLAG_FIXED) == 0) {
         const double4 pi = pb_ld_pos(pos + i);
         const int pc = particle_cell[i];
+        // list slot of neighbour k: base + (k / G) * 32 + k % G  (PbNeighLayout::idx with the per-particle part hoisted)
+        int *const out = neigh + ((size_t) (i / lay.A) * lay.T * 32 + (size_t) ((i % lay.A) * lay.G));
+        const int G = lay.G;
         // run 0: cell 0; runs 1..9: rows (dx,dy) in stencil order, each covering dz = -1,0,+1
         for(int run = 0; run < 10; run++) {
             int c_lo, c_hi;   // inclusive cell range of this run
@@ -42,15 +45,17 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
             }
             const int b = cell_start[c_lo], e = cell_start[c_hi + 1];
             for(int k = b; k < e; k++) {
-                const int j = cell_list[k];
-                if(j == i) { continue; }
+                const int j = __ldg(cell_list + k);
                 const double4 pj = pb_ld_pos(pos + j);
                 const double dx = __dsub_rn(pi.x, pj.x);
                 const double dy = __dsub_rn(pi.y, pj.y);
                 const double dz = __dsub_rn(pi.z, pj.z);
                 const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if(rsq < cutsq) {
-                    if(STORE && count < ncap) { neigh[lay.idx(i, count)] = j; }
+                if(rsq < cutsq && j != i) {
+                    if(STORE && count < ncap) {
+                        if(G == 1) { out[(size_t) count * 32] = j; }
+                        else { out[(size_t) (count / G) * 32 + (count % G)] = j; }
+                    }
                     count++;
                 }
             }
