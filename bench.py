@@ -242,13 +242,16 @@ def run_ours(args):
     vel = ctx.real("linear_velocity")
     mass = ctx.real("mass")
     typ = ctx.ints("type")
-    out_pos, out_vel = np.empty_like(pos), np.empty_like(vel)
+    cap_out = int(len(pos) * 1.25) + 4096          # nlocal changes under migration when N > 1
+    out_pos, out_vel = np.empty((cap_out, 3)), np.empty((cap_out, 3))
     for a in (pos, vel, mass, typ, out_pos, out_vel):
         ctx.host_register(a)
     barrier()
     t0 = time.perf_counter()
     ctx.upload(pos, vel, mass, typ)
     th2 = run(0, K)
+    n_after = ctx.counts()[0]
+    assert n_after <= cap_out, (n_after, cap_out)
     ctx.real_into("position", out_pos)
     ctx.real_into("linear_velocity", out_vel)
     barrier()
@@ -259,7 +262,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
     h2d = (pos.nbytes + vel.nbytes + mass.nbytes + typ.nbytes) * world
-    d2h = (out_pos.nbytes + out_vel.nbytes + th2.nbytes) * world
+    d2h = (2 * n_after * 24 + th2.nbytes) * world
     e2e = {"value": n_global * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
            "what": "pb_upload_particles (pinned host arrays) + pb_md_run over K iterations from ts=0 incl. first neighbour build "
                    "+ thermo read-backs + pb_download_real(position, linear_velocity)"}
@@ -298,7 +301,14 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    try:
+        return run_ours(args)
+    except BaseException:
+        # a failing rank must not leave its peers blocked in a collective: report and hard-exit so the launcher tears down
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":
