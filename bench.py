@@ -29,6 +29,7 @@ CUT, SKIN, DT, RENEIGH, THERMO = 2.5, 0.3, 0.005, 20, 100
 METRIC, UNIT = "lj_atom_steps_per_s", "atom-steps/s"
 # rank grids Regular6DStencil::setConfig picks when the global box is built from per-GPU cubes
 WEAK_GRIDS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}
+_JSON_OUT = sys.stdout
 REF_SAMPLE_NX = 63   # oracle/_ref variant md_bench: 4 * 63^3 = 1,000,188 atoms
 
 
@@ -146,7 +147,8 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
-    print(json.dumps(line))
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
     return 0
 
 
@@ -280,7 +282,8 @@ def run_ours(args):
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms": stages, "atoms_global": n_global,
                 "nlocal_rank0": nl, "nghost_rank0": ng, "wall_s_timed_region": t_wall, "setup_s": t_setup,
                 "thermo_last": [float(x) for x in thermo[-1]] if len(thermo) else None}
-        print(json.dumps(line))
+        _JSON_OUT.write(json.dumps(line) + "\n")
+        _JSON_OUT.flush()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -288,6 +291,10 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version banner) goes to stderr
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)

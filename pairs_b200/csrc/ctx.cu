@@ -55,7 +55,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape, ctx->shape_alt, ctx->tag,
                     ctx->tag_alt, ctx->particle_cell, ctx->cell_count, ctx->cell_start, ctx->cell_slot, ctx->cell_list,
                     ctx->cell_key, ctx->scan_tmp, ctx->neigh, ctx->numneigh, ctx->d_eps, ctx->d_sig6, ctx->send_map, ctx->send_mult,
-                    ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->d_partial, ctx->d_scalars};
+                    ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->mig_scan_a, ctx->mig_scan_b, ctx->d_partial, ctx->d_scalars};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
@@ -122,6 +122,10 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
     PB_TRY(pb_regrow(ctx, &ctx->cell_key, 0, newcap, false));
     PB_TRY(pb_regrow(ctx, &ctx->sel_flag, 0, newcap + 1, false));
     PB_TRY(pb_regrow(ctx, &ctx->sel_scan, 0, newcap + 1, false));
+    if(ctx->world > 1) {
+        PB_TRY(pb_regrow(ctx, &ctx->mig_scan_a, 0, newcap + 1, false));
+        PB_TRY(pb_regrow(ctx, &ctx->mig_scan_b, 0, newcap + 1, false));
+    }
     PB_TRY(pb_regrow(ctx, &ctx->numneigh, 0, newcap, false));
     ctx->pcap = (int) newcap;
     return 0;

@@ -111,16 +111,16 @@ __global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0,
 int pb_exchange_multi(pb_ctx *ctx, int dim) {
     const int n = ctx->nlocal;
     const int j0 = dim * 2, j1 = dim * 2 + 1;
+    if(ctx->mig_scan_a == nullptr) {     // capacity was reserved before the domain became multi-rank
+        PB_CHECK(cudaMalloc(&ctx->mig_scan_a, sizeof(int) * ((size_t) ctx->pcap + 1)));
+        PB_CHECK(cudaMalloc(&ctx->mig_scan_b, sizeof(int) * ((size_t) ctx->pcap + 1)));
+    }
     const int do_lo = ctx->pbc_flag[dim] || ctx->pbc[j0] == 0;
     const int do_hi = ctx->pbc_flag[dim] || ctx->pbc[j1] == 0;
     // scratch: sel_lo = sel_flag, sel_hi / stay / scans live in cell_slot, cell_list, particle_cell, sel_scan (all [pcap])
+    // (all of them are free at this point of the reneighbouring sequence; mig_scan* are [pcap+1] and persistent)
     int *sel_lo = ctx->sel_flag, *sel_hi = ctx->cell_slot, *stay = ctx->cell_list;
-    int *scan_lo = ctx->sel_scan, *scan_hi = ctx->particle_cell;
-    int *scan_stay = nullptr;
-    PB_CHECK(cudaMalloc(&scan_stay, sizeof(int) * ((size_t) n + 1)));
-    int *scan_hi_full = nullptr;
-    PB_CHECK(cudaMalloc(&scan_hi_full, sizeof(int) * ((size_t) n + 1)));
-    scan_hi = scan_hi_full;
+    int *scan_lo = ctx->sel_scan, *scan_hi = ctx->mig_scan_a, *scan_stay = ctx->mig_scan_b;
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
     int c_lo = 0, c_hi = 0, c_stay = 0;
     if(n > 0) {
@@ -170,9 +170,6 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
                   ctx->flags, ctx->uid, ctx->shape, ctx->tag);
     }
     ctx->nlocal = c_stay + nr;
-    PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(scan_stay));
-    PB_CHECK(cudaFree(scan_hi_full));
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
     return 0;
 }
