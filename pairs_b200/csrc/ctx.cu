@@ -37,6 +37,9 @@ extern "C" int pb_create(pb_ctx **out, int device) {
     if(e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return -1; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
     cudaMalloc(&ctx->d_scalars, sizeof(int) * PB_NSCALARS);
     cudaMemset(ctx->d_scalars, 0, sizeof(int) * PB_NSCALARS);
     cudaMallocHost(&ctx->h_scalars, sizeof(int) * PB_NSCALARS);
@@ -55,13 +58,17 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape, ctx->shape_alt, ctx->tag,
                     ctx->tag_alt, ctx->particle_cell, ctx->cell_count, ctx->cell_start, ctx->cell_slot, ctx->cell_list,
                     ctx->cell_key, ctx->scan_tmp, ctx->neigh, ctx->numneigh, ctx->d_eps, ctx->d_sig6, ctx->send_map, ctx->send_mult,
-                    ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->mig_scan_a, ctx->mig_scan_b, ctx->d_partial, ctx->d_scalars};
+                    ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->mig_scan_a, ctx->mig_scan_b, ctx->d_partial, ctx->d_scalars,
+                    ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
     for(cudaEvent_t e : ctx->event_pool) { cudaEventDestroy(e); }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_prev);
+    cudaEventDestroy(ctx->ev_sync);
+    cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

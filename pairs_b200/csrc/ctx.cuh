@@ -92,6 +92,15 @@ struct pb_ctx {
     size_t neigh_bytes = 0;
     int *neigh = nullptr, *numneigh = nullptr;
     int neigh_n = 0;              // nlocal at build time
+    // interior / boundary split of the warp groups (32 particles each) for comm / compute overlap
+    int *group_flag = nullptr, *group_scan = nullptr, *groups_interior = nullptr, *groups_boundary = nullptr;
+    int group_cap = 0, n_interior = 0, n_boundary = 0;
+    bool groups_valid = false;
+    const int *lj_groups = nullptr;   // group list of the force launch being issued (null = all groups)
+    int lj_ngroups = 0;
+    bool overlap_comm = true;     // multi-rank: refresh ghosts on comm_stream while the interior groups compute
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_prev = nullptr, ev_sync = nullptr;
 
     // ---- LJ feature properties ----
     int ntypes = 0;

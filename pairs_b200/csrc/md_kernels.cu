@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int
                                                           const int *__restrict__ numneigh, const int *__restrict__ neigh,
                                                           double *__restrict__ force, double dt, double half_dt,
                                                           const double *__restrict__ mass, double *__restrict__ vel,
-                                                          double4 *__restrict__ pos_next) {
+                                                          double4 *__restrict__ pos_next, const int *__restrict__ groups,
+                                                          int ngroups) {
     constexpr int A = 32 / G;
     __shared__ double s_eps[64], s_sig6[64];
     if(!UNIFORM) {
@@ -49,7 +50,12 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // a launch serves either all warp groups or the subset listed in `groups` (interior / boundary split for overlap)
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if(groups != nullptr) {
+        if(warp >= ngroups) { return; }
+        warp = __ldg(groups + warp);
+    }
     const int g = lane % G;
     const int i = warp * A + lane / G;
     const bool live = i < nlocal;
@@ -195,13 +201,14 @@ template<int G, int UNROLL, int FUSE>
 static int pb_launch_lj(pb_ctx *ctx, double cutsq, double dt) {
     const int n = ctx->nlocal;
     const int A = 32 / G;
-    const long warps = ((long) n + A - 1) / A;
+    const long warps = (ctx->lj_groups != nullptr) ? ctx->lj_ngroups : ((long) n + A - 1) / A;
+    if(warps == 0) { return 0; }
     const int T = 128, B = (int) ((warps * 32 + T - 1) / T);
     const bool acc = !ctx->force_is_zero;
 #define PB_LJ(UNI, ACC)                                                                                                        \
     PB_LAUNCH((pb_k_lennard_jones<G, UNI, ACC, UNROLL, FUSE>), B, T, n, ctx->nslots, ctx->pcap, cutsq, ctx->ntypes,            \
               ctx->h_eps[0], ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh,          \
-              ctx->force, dt, dt * 0.5, ctx->mass, ctx->vel, ctx->pos_alt)
+              ctx->force, dt, dt * 0.5, ctx->mass, ctx->vel, ctx->pos_alt, ctx->lj_groups, ctx->lj_ngroups)
     if(ctx->lj_uniform) {
         if(acc) { PB_LJ(true, true); } else { PB_LJ(true, false); }
     } else {
@@ -231,13 +238,22 @@ static int pb_launch_lj_f(pb_ctx *ctx, double cutsq, double dt, int fuse) {
 }
 
 // fuse: bit 0 = final_integrate of this step, bit 1 = initial_integrate of the next step (positions double-buffered)
-int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse) {
+// part: 0 = all particles, 1 = interior warp groups only, 2 = boundary warp groups only (the buffer swap of a fused
+// initial_integrate happens after part 0 or part 2)
+int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int part) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "lennard_jones");
     if(ctx->ntypes == 0) { ctx->set_error("pb_lennard_jones: pb_set_lj_params not called"); return -1; }
     if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_lennard_jones: neighbour lists are stale"); return -1; }
     if(ctx->nlocal == 0) { return 0; }
     const double cutsq = cutoff * cutoff;
+    ctx->lj_groups = nullptr;
+    ctx->lj_ngroups = 0;
+    if(part != 0) {
+        if(!ctx->groups_valid || ctx->lanes != 1) { ctx->set_error("interior/boundary split not available"); return -1; }
+        ctx->lj_groups = (part == 1) ? ctx->groups_interior : ctx->groups_boundary;
+        ctx->lj_ngroups = (part == 1) ? ctx->n_interior : ctx->n_boundary;
+    }
     int rc;
     switch(ctx->lanes) {
         case 1: rc = pb_launch_lj_f<1>(ctx, cutsq, dt, fuse); break;
@@ -247,6 +263,8 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse) {
         default: ctx->set_error("lanes_per_particle must be 1, 2, 4 or 8"); return -1;
     }
     PB_TRY(rc);
+    ctx->lj_groups = nullptr;
+    if(part == 1) { return 0; }
     ctx->force_is_zero = false;
     if(fuse & 2) {
         // new local positions are in pos_alt; the ghosts of the current step stay behind in the old buffer until the next
@@ -257,7 +275,7 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse) {
     return 0;
 }
 
-extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) { return pb_lennard_jones_fused(ctx, cutoff, 0.0, 0); }
+extern "C" int pb_lennard_jones(pb_ctx *ctx, double cutoff) { return pb_lennard_jones_fused(ctx, cutoff, 0.0, 0, 0); }
 
 // Tuning knobs (bench/ncu sweeps): "lanes_per_particle" (takes effect at the next neighbour-list build), "lj_unroll".
 extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
@@ -274,6 +292,7 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
         return 0;
     }
     if(nm == "fuse_integrate") { ctx->fuse_integrate = value != 0; return 0; }
+    if(nm == "overlap_comm") { ctx->overlap_comm = value != 0; ctx->groups_valid = false; return 0; }
     ctx->set_error("pb_set_option: unknown option " + nm);
     return -1;
 }

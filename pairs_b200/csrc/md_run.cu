@@ -4,9 +4,11 @@
 // build_cell_lists -> partition_cell_lists -> build_neighbor_lists -> reset_volatile_properties -> lennard_jones ->
 // final_integrate -> compute_thermo.  Everything stays on the device; only thermo scalars (every `thermo_every`
 // steps) and capacity counters (every reneighbouring) are read back.
+#include <algorithm>
+
 #include "ctx.cuh"
 
-int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse);
+int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int part);
 
 extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo) {
     PB_CHECK(cudaSetDevice(ctx->device));
@@ -22,8 +24,24 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
             PB_TRY(pb_borders(ctx));
             PB_TRY(pb_build_cell_lists(ctx));
             PB_TRY(pb_build_neighbor_lists(ctx, p->cutoff_lists));
-        } else {
-            PB_TRY(pb_synchronize(ctx));
+        }
+        // Multi-rank steps without reneighbouring: the ghost refresh (pack -> NCCL -> unpack) runs on comm_stream while the
+        // interior warp groups -- no ghost neighbour, no halo source -- already compute on the main stream; the boundary
+        // groups follow once the refresh has landed.  (The reference's communication is blocking)
+        const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && ctx->fuse_integrate && ctx->groups_valid &&
+                             ctx->neigh_n == ctx->nlocal;
+        if(!reneigh) {
+            if(overlap) {
+                PB_CHECK(cudaEventRecord(ctx->ev_prev, ctx->stream));
+                PB_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prev, 0));
+                std::swap(ctx->stream, ctx->comm_stream);
+                const int rc = pb_synchronize(ctx);
+                if(rc >= 0) { cudaEventRecord(ctx->ev_sync, ctx->stream); }
+                std::swap(ctx->stream, ctx->comm_stream);
+                PB_TRY(rc);
+            } else {
+                PB_TRY(pb_synchronize(ctx));
+            }
         }
         PB_TRY(pb_reset_volatile(ctx));
         const bool thermo_now = p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0);
@@ -32,7 +50,13 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
             // initial_integrate(ts + 1) into the force kernel
             int fuse = (ts > 0) ? 1 : 0;
             if(!thermo_now && ts + 1 < ts_end) { fuse |= 2; initial_done = true; }
-            PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse));
+            if(overlap) {
+                PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 1));
+                PB_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
+                PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 2));
+            } else {
+                PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 0));
+            }
         } else {
             PB_TRY(pb_lennard_jones(ctx, p->cutoff_force));
             if(ts > 0) { PB_TRY(pb_final_integrate(ctx, p->dt)); }

@@ -16,17 +16,24 @@
 
 #include "ctx.cuh"
 
+struct PbFaces {
+    double lo[3], hi[3];   // subdom_min + margin, subdom_max - margin
+};
+
 template<bool STORE>
 __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncells, int dim1, int dim2, int ncap, PbNeighLayout lay,
                                                             double cutsq, const double4 *__restrict__ pos,
                                                             const int *__restrict__ flags, const int *__restrict__ particle_cell,
                                                             const int *__restrict__ cell_start, const int *__restrict__ cell_list,
                                                             int *__restrict__ neigh, int *__restrict__ numneigh,
-                                                            int *__restrict__ max_count) {
+                                                            int *__restrict__ max_count, PbFaces faces, int *__restrict__ group_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int count = 0;
+    int boundary = 0;     // has a ghost neighbour, or is itself a halo source (within `margin` of a sub-box face)
     if(i < nlocal && (flags[i] & PB_FLAG_FIXED) == 0) {
         const double4 pi = pb_ld_pos(pos + i);
+        boundary = (pi.x < faces.lo[0]) | (pi.x > faces.hi[0]) | (pi.y < faces.lo[1]) | (pi.y > faces.hi[1]) |
+                   (pi.z < faces.lo[2]) | (pi.z > faces.hi[2]);
         const int pc = particle_cell[i];
         // list slot of neighbour k: base + (k / G) * 32 + k % G  (PbNeighLayout::idx with the per-particle part hoisted)
         int *const out = neigh + ((size_t) (i / lay.A) * lay.T * 32 + (size_t) ((i % lay.A) * lay.G));
@@ -57,11 +64,15 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
                         else { out[(size_t) (count / G) * 32 + (count % G)] = j; }
                     }
                     count++;
+                    boundary |= (j >= nlocal);
                 }
             }
         }
     }
     if(i < nlocal) { numneigh[i] = count; }
+    // one flag per warp group (= 32 consecutive particles = one warp of the force kernel when G = 1)
+    const unsigned any_b = __ballot_sync(0xffffffffu, boundary != 0);
+    if((threadIdx.x & 31) == 0 && i < nlocal) { group_flag[i >> 5] = any_b != 0u; }
     // block-wide max -> one atomic per warp
     int m = count;
 #pragma unroll
@@ -90,6 +101,27 @@ static int pb_alloc_neigh(pb_ctx *ctx, int n) {
     return 0;
 }
 
+// Ordered compaction of the warp-group ids into an interior list (no ghost neighbour, no halo source: can be computed
+// while the ghost refresh is in flight) and a boundary list.
+__global__ void __launch_bounds__(256) pb_k_split_groups(int ngroups, const int *__restrict__ flag, const int *__restrict__ scan,
+                                                         int *__restrict__ interior, int *__restrict__ boundary) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if(g >= ngroups) { return; }
+    if(flag[g]) { boundary[scan[g]] = g; } else { interior[g - scan[g]] = g; }
+}
+
+static int pb_split_groups(pb_ctx *ctx, int ngroups) {
+    PB_TRY(pb_exclusive_scan(ctx, ctx->group_flag, ctx->group_scan, ngroups));
+    PB_LAUNCH(pb_k_split_groups, pb_blocks(ngroups, 256), 256, ngroups, ctx->group_flag, ctx->group_scan, ctx->groups_interior,
+              ctx->groups_boundary);
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->group_scan + ngroups, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_boundary = ctx->h_scalars[0];
+    ctx->n_interior = ngroups - ctx->n_boundary;
+    ctx->groups_valid = true;
+    return 0;
+}
+
 extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "build_neighbor_lists");
@@ -101,18 +133,35 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
     ctx->neigh_n = n;
     if(n == 0) { ctx->max_neigh = 0; return 0; }
     const double cutsq = cutoff * cutoff;
-    if(ctx->ncap <= 0) { ctx->ncap = 100; }   // neighbor_capacity default of pairs.simulation() (src/pairs/__init__.py:16)
+    if(ctx->ncap <= 0) { ctx->ncap = 100; }
+    const int ngroups = (n + 31) / 32;
+    if(ngroups + 1 > ctx->group_cap) {
+        for(int **q : {&ctx->group_flag, &ctx->group_scan, &ctx->groups_interior, &ctx->groups_boundary}) {
+            if(*q != nullptr) { PB_CHECK(cudaFree(*q)); }
+            PB_CHECK(cudaMalloc(q, sizeof(int) * ((size_t) ngroups + 1024)));
+        }
+        ctx->group_cap = ngroups + 1023;
+    }
+    PbFaces faces;
+    for(int d = 0; d < 3; d++) {
+        faces.lo[d] = ctx->subdom[d * 2] + ctx->spacing;
+        faces.hi[d] = ctx->subdom[d * 2 + 1] - ctx->spacing;
+    }
+    ctx->groups_valid = false;   // neighbor_capacity default of pairs.simulation() (src/pairs/__init__.py:16)
     for(int attempt = 0; attempt < 8; attempt++) {
         PB_TRY(pb_alloc_neigh(ctx, n));
         ctx->nslots = pb_layout(ctx).T;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
         PB_LAUNCH(pb_k_build_neighbors<true>, pb_blocks(n, 128), 128, n, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], ctx->ncap,
                   pb_layout(ctx), cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->neigh, ctx->numneigh,
-                  ctx->d_scalars);
+                  ctx->d_scalars, faces, ctx->group_flag);
         PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->max_neigh = ctx->h_scalars[0];
-        if(ctx->max_neigh <= ctx->ncap) { return 0; }
+        if(ctx->max_neigh <= ctx->ncap) {
+            if(ctx->world > 1 && ctx->overlap_comm && ctx->lanes == 1) { PB_TRY(pb_split_groups(ctx, ngroups)); }
+            return 0;
+        }
         // capacity-overflow protocol (transformations/modules.py:159-203): grow to twice the need and re-run the module
         ctx->ncap = ctx->max_neigh * 2;
     }

@@ -25,14 +25,25 @@ def main():
     ids = [backend.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     ctx.nccl_init(ids[0])
-    n = ctx.copper_fcc_lattice(nx, nx, nx, 0.8442, 4)
-    ctx.adjust_thermo(1.44)
-    ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
-    log = []
-    for ts in range(steps):
-        th = ctx.md_run(ts, ts + 1, 0.005, 2.5, 2.8, 2.8, 20, 1)
-        log.append((float(th[0, 1]), ) + ctx.counts())
-    state = {"log": log, "tag": ctx.ints("tag"), "pos": ctx.real("position"), "n0": n, "decomp": ctx.decomposition()}
+    def run_case(overlap):
+        ctx.set_option("overlap_comm", overlap)
+        n = ctx.copper_fcc_lattice(nx, nx, nx, 0.8442, 4)
+        ctx.adjust_thermo(1.44)
+        ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
+        log = {}
+        chunk = 7      # multi-step calls: fused integrators + (N > 1) ghost refresh overlapped with the interior force
+        for c in range(0, steps, chunk):
+            th = ctx.md_run(c, min(c + chunk, steps), 0.005, 2.5, 2.8, 2.8, 20, chunk)
+            for row in th:
+                log[int(row[0])] = float(row[1])
+            log[("counts", min(c + chunk, steps) - 1)] = ctx.counts()
+        return n, log, ctx.ints("tag"), ctx.real("position"), ctx.real("linear_velocity")
+
+    n, log, tag, pos, vel = run_case(1)
+    n2, log2, tag2, pos2, vel2 = run_case(0)
+    # overlap only reorders independent work: results must be bit-identical
+    assert log == log2 and np.array_equal(tag, tag2) and np.array_equal(pos, pos2) and np.array_equal(vel, vel2)
+    state = {"log": log, "tag": tag, "pos": pos, "n0": n, "decomp": ctx.decomposition()}
     gathered = [None] * world
     dist.all_gather_object(gathered, state)
     ok = True
@@ -46,13 +57,18 @@ def main():
             assert np.array_equal(d["pbc"], gathered[k]["decomp"]["pbc"]) and np.array_equal(d["subdom"], gathered[k]["decomp"]["subdom"])
             assert r.nlocal == gathered[k]["n0"]
         worst = 0.0
+        checked = 0
         for ts in range(steps):
             sim.step(ts)
             t = sim.thermo()[0]
             for k, r in enumerate(sim.ranks):
-                tg, nl, ng = gathered[k]["log"][ts]
-                assert (nl, ng) == (r.nlocal, r.nghost), (ts, k, nl, ng, r.nlocal, r.nghost)
-                worst = max(worst, abs(tg - t) / t)
+                lg = gathered[k]["log"]
+                if ("counts", ts) in lg:
+                    assert lg[("counts", ts)] == (r.nlocal, r.nghost), (ts, k, lg[("counts", ts)], r.nlocal, r.nghost)
+                if ts in lg:
+                    worst = max(worst, abs(lg[ts] - t) / t)
+                    checked += 1
+        assert checked >= world * (steps // 7)
         assert worst <= 1e-9, worst
         # per-particle end state: match through exact lattice identity = sorted coordinates per rank
         for k, r in enumerate(sim.ranks):
