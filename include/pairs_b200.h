@@ -113,6 +113,38 @@ int pb_exchange(pb_ctx *ctx);
 int pb_borders(pb_ctx *ctx);
 int pb_synchronize(pb_ctx *ctx);
 
+/* ---- DEM path of examples/dem.py (spheres + half-spaces, contact history, cell-list traversal).  Single GPU in round 1. ----
+ * pb_dem_enable            use_contact_history=True + the DEM property set (contact_capacity = neighbor_capacity of pairs.simulation())
+ * pb_dem_set_params        symbols of the kernels (examples/dem.py:189-201) + feature properties friction_static/dynamic
+ * pb_dem_sc_grid           pairs::dem_sc_grid (runtime/dem_sc_grid.hpp:62-172), host arrays out (NULL pointers: count only)
+ * pb_dem_upload_real/download_real   radius | angular_velocity | torque | normal | inv_inertia | rotation_matrix | rotation_quat |
+ *                                    force | mass | linear_velocity, n particles from index `first` (AoS host layout)
+ * pb_dem_upload/download_contacts    contact history in the reference's layout: num[n], uid/used/sticking [n][C], tsd [n][C][3], ivm [n][C]
+ * pb_dem_update_mass_and_inertia     setup() function of examples/dem.py:6-15
+ * pb_dem_reset_contact_usage / pb_dem_clear_unused_contacts   sim/contact_history.py:75-127
+ * pb_dem_gravity / pb_dem_linear_spring_dashpot / pb_dem_euler  compute() kernels of examples/dem.py:18-91
+ * pb_dem_run               the generated DEM loop (exchange, borders, cell lists, ..., euler, clear) for ts in [ts_begin, ts_end) */
+int pb_dem_enable(pb_ctx *ctx, int contact_capacity);
+int pb_dem_set_params(pb_ctx *ctx, double dt, double pi, double kappa, double ln_dry_res_coeff, double collision_time,
+                      double density_particle, double density_fluid, double gravity, int ntypes, const double *friction_static,
+                      const double *friction_dynamic);
+int pb_dem_sc_grid(pb_ctx *ctx, double xmax, double ymax, double zmax, double spacing, double diameter, double min_diameter,
+                   double max_diameter, double initial_velocity, double particle_density, int ntypes, int capacity, int *uid, int *type,
+                   double *mass, double *radius, double *position, double *velocity, int *count);
+int pb_dem_upload_real(pb_ctx *ctx, const char *name, int first, int n, const double *data);
+int pb_dem_download_real(pb_ctx *ctx, const char *name, int first, int n, double *out);
+int pb_set_counts(pb_ctx *ctx, int nlocal, int nghost);
+int pb_dem_upload_contacts(pb_ctx *ctx, int n, const int *num, const int *uid, const int *sticking, const double *tsd, const double *ivm);
+int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, int *used, int *sticking, double *tsd, double *ivm);
+int pb_dem_update_mass_and_inertia(pb_ctx *ctx);
+int pb_dem_reset_contact_usage(pb_ctx *ctx);
+int pb_dem_clear_unused_contacts(pb_ctx *ctx);
+int pb_dem_gravity(pb_ctx *ctx);
+int pb_dem_linear_spring_dashpot(pb_ctx *ctx);
+int pb_dem_euler(pb_ctx *ctx);
+int pb_dem_contact_overflow(pb_ctx *ctx);
+int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts_end);
+
 /* multi-GPU: NCCL communicator over the ranks of pb_init_domain.  id = 128-byte ncclUniqueId made by rank 0
  * (pb_nccl_unique_id) and distributed by the launcher. */
 int pb_nccl_unique_id(void *id128);

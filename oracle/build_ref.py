@@ -14,6 +14,8 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md        stock examples/md.py (config C1: 32^3 cells = 131072 atoms, 200 steps)
   md_t1     nx=ny=nz=8 (2048 atoms), 100 steps, thermo every step   -> per-step parity dumps
   md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
+  dem_t1    examples/dem.py on a 0.1 x 0.015 x 0.04 box (420 spheres + 2 planes), 700 steps, thermo hook every step
+  dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
             -> CPU-baseline sample for bench.py
@@ -56,12 +58,26 @@ def md_variant(nx, steps, thermo, reneigh, pcap=None):
     return patch
 
 
+def dem_variant(domain, steps):
+    def patch(text):
+        text = _sub(text, r"^domainSize_SI = \[[^\]]*\]", f"domainSize_SI = [{domain[0]}, {domain[1]}, {domain[2]}]")
+        text = _sub(text, r"^timeSteps = \d+", f"timeSteps = {steps}")
+        text = _sub(text, r"^psim\.vtk_output\(", "#psim.vtk_output(")          # debug output, out of scope
+        # one compute_thermo call per iteration = the harness hook that exposes nlocal and the per-step state
+        text = _sub(text, r"^psim\.generate\(\)", "psim.compute_thermo(1)\npsim.generate()")
+        return text
+    return patch
+
+
 VARIANTS = {
     # name: (example script, patch function or None, harness defines, also build executable)
     "md": ("examples/md.py", None, ["-DREF_IS_MD"], True),
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
+    # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
+    "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
+    "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000), [], False),
 }
 
 
@@ -115,12 +131,23 @@ def build_variant(name):
     return "built"
 
 
+def stage_data():
+    """The generated DEM program reads data/planes.input relative to its working directory (runtime/read_from_file.hpp);
+    the reference's 2-row input file is staged under oracle/_ref/data/ so the oracle also runs where /root/reference is absent."""
+    import shutil
+    ddir = os.path.join(OUT, "data")
+    os.makedirs(ddir, exist_ok=True)
+    os.makedirs(os.path.join(OUT, "output"), exist_ok=True)
+    shutil.copyfile(os.path.join(REF, "data", "planes.input"), os.path.join(ddir, "planes.input"))
+
+
 def main(argv):
     if not os.path.isdir(REF):
         print(f"[oracle/_ref] {REF} not present: keeping prebuilt artefacts")
         return 0
     names = argv or list(VARIANTS)
     os.makedirs(GEN, exist_ok=True)
+    stage_data()
     for n in names:
         print(f"[oracle/_ref] {n}: {build_variant(n)}")
     return 0

@@ -42,6 +42,8 @@ class RefProgram:
         self.lib.ref_array_ptr.restype = ctypes.c_void_p
         self.lib.ref_array_size.argtypes = [ctypes.c_char_p]
         self.lib.ref_array_size.restype = ctypes.c_long
+        self.lib.ref_contact_property_ptr.argtypes = [ctypes.c_char_p]
+        self.lib.ref_contact_property_ptr.restype = ctypes.c_void_p
 
     # ---- access to live state (valid only inside a hook) ----
     def prop(self, name, n, width=1, dtype=np.float64):
@@ -52,6 +54,33 @@ class RefProgram:
         buf = (ct * (n * width)).from_address(p)
         a = np.frombuffer(buf, dtype=dtype).copy()
         return a.reshape(n, width) if width > 1 else a
+
+    def contact_prop(self, name, n, width=1, dtype=np.float64):
+        p = self.lib.ref_contact_property_ptr(name.encode())
+        if not p:
+            raise KeyError(name)
+        ct = ctypes.c_double if dtype == np.float64 else ctypes.c_int
+        buf = (ct * (n * width)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype).copy()
+
+    DEM_REAL = (("position", 3), ("linear_velocity", 3), ("angular_velocity", 3), ("force", 3), ("torque", 3), ("mass", 1), ("radius", 1),
+                ("normal", 3), ("inv_inertia", 9), ("rotation_matrix", 9), ("rotation_quat", 4))
+    DEM_INT = ("uid", "type", "flags", "shape")
+
+    def dem_state(self, n, ncap=20):
+        """Full DEM particle + contact-history state of the first n particles (valid inside a hook)."""
+        s = {}
+        for name, w in self.DEM_REAL:
+            s[name] = self.prop(name, n, w)
+        for name in self.DEM_INT:
+            s[name] = self.prop(name, n, 1, np.int32)
+        s["num_contacts"] = self.array("num_contacts", np.int32, n)
+        s["contact_lists"] = self.array("contact_lists", np.int32, n * ncap).reshape(n, ncap)
+        s["contact_used"] = self.array("contact_used", np.int32, n * ncap).reshape(n, ncap)
+        s["is_sticking"] = self.contact_prop("is_sticking", n * ncap, 1, np.int32).reshape(n, ncap)
+        s["tangential_spring_displacement"] = self.contact_prop("tangential_spring_displacement", n * ncap, 3).reshape(n, ncap, 3)
+        s["impact_velocity_magnitude"] = self.contact_prop("impact_velocity_magnitude", n * ncap, 1).reshape(n, ncap)
+        return s
 
     def array(self, name, dtype=np.int32, count=None):
         p = self.lib.ref_array_ptr(name.encode())

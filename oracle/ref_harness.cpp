@@ -116,6 +116,8 @@ int ref_run_limited(int max_thermo_calls, int quiet) {
     return ref_run(nullptr, nullptr, quiet);
 }
 
+void ref_set_limit(int max_thermo_calls) { g_thermo_limit = max_thermo_calls; }
+
 int ref_thermo_times(double *out, int cap) {
     const int n = (int) g_thermo_times.size();
     for(int k = 0; k < n && k < cap; k++) { out[k] = g_thermo_times[k]; }
@@ -131,6 +133,11 @@ void *ref_property_ptr(const char *name) {
 void *ref_array_ptr(const char *name) {
     if(g_ps == nullptr) { return nullptr; }
     return g_ps->getArrayByName(name).getHostPointer();
+}
+
+void *ref_contact_property_ptr(const char *name) {
+    if(g_ps == nullptr) { return nullptr; }
+    return g_ps->getContactPropertyByName(name).getHostPointer();
 }
 
 long ref_array_size(const char *name) {

@@ -39,6 +39,15 @@ def dump(variant, out_path, nsteps=None):
             for i in range(n)]
 
 
+def dump_dem(variant, out_path, max_steps, keep):
+    """DEM snapshots (fresh process); returns the loaded npz."""
+    p = spawn(["dump_dem", variant, out_path, max_steps, ",".join(str(k) for k in keep)])
+    out, err = p.communicate()
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_worker dump_dem failed:\n{out[-3000:]}\n{err[-3000:]}")
+    return np.load(out_path)
+
+
 def bench_many(variant, warmup, steps, replicas):
     """`replicas` concurrent fresh processes, each timing `steps` loop iterations after `warmup`; list of results."""
     procs = [spawn(["bench", variant, warmup, steps]) for _ in range(replicas)]
@@ -64,6 +73,44 @@ def _main(argv):
             for k in ("position", "linear_velocity", "force", "mass", "type"):
                 d[f"{k}_{i}"] = s[k]
         np.savez(out_path, **d)
+        return 0
+    if mode == "dump_dem":
+        # argv: dump_dem <variant> <out.npz> <max_steps> <step,step,...>  -- state at the END of the listed iterations, plus the
+        # state at module boundaries inside them (after gravity = before the contact kernel, after the contact kernel, after euler)
+        out_path, max_steps = argv[2], int(argv[3])
+        keep = set(int(x) for x in argv[4].split(",")) if len(argv) > 4 and argv[4] else set()
+        os.chdir(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref"))    # data/planes.input is opened relative to cwd
+        st = {"ts": 0, "nlocal": None}
+        d = {}
+
+        def on_event(ev, a):
+            ts = st["ts"]
+            if ev == "thermo":
+                st["nlocal"] = a
+                if ts in keep:
+                    for k, v in prog.dem_state(a).items():
+                        d[f"end_{ts}_{k}"] = v
+                d.setdefault("nlocal", []).append(a)
+                nrecv = prog.array("nrecv", np.int32, 6)
+                d.setdefault("nghost", []).append(int(nrecv.sum()))
+                st["ts"] = ts + 1
+            elif st["nlocal"] is not None and ts in keep and ev in ("module:gravity", "module:linear_spring_dashpot", "module:euler"):
+                n = st["nlocal"] + int(prog.array("nrecv", np.int32, 6).sum())      # locals + ghosts
+                tag = {"module:gravity": "pre", "module:linear_spring_dashpot": "post", "module:euler": "eul"}[ev]
+                for k, v in prog.dem_state(n).items():
+                    d[f"{tag}_{ts}_{k}"] = v
+                d[f"{tag}_{ts}_particle_cell"] = prog.array("particle_cell", np.int32, n)
+
+        prog.lib.ref_run_limited.argtypes = [ctypes.c_int, ctypes.c_int]
+        import oracle.ref as _r
+        cb = _r.HOOK(lambda ev, a, _u: on_event(ev.decode(), a))
+        # bounded run with hooks: set the limit, then call ref_run (limit is consumed by ref_run)
+        prog.lib.ref_set_limit.argtypes = [ctypes.c_int]
+        prog.lib.ref_set_limit(max_steps)
+        prog.lib.ref_run(cb, None, 1)
+        d["nlocal"] = np.array(d["nlocal"])
+        d["nghost"] = np.array(d["nghost"])
+        np.savez_compressed(out_path, **d)
         return 0
     if mode == "bench":
         warmup, steps = int(argv[2]), int(argv[3])

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libpairs_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu"]
+SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu"]
 
 # --fmad=false: fp64 multiplies and adds are never contracted, so per-operation results equal the reference CPU
 # build compiled with -ffp-contract=off (the parity contract).
@@ -27,7 +27,7 @@ class BackendError(RuntimeError):
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "ctx.cuh"), os.path.join(INCLUDE, "pairs_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(INCLUDE, "pairs_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
@@ -88,6 +88,22 @@ SIGNATURES = {
     "pb_exchange": (_I, [_P]),
     "pb_borders": (_I, [_P]),
     "pb_synchronize": (_I, [_P]),
+    "pb_dem_enable": (_I, [_P, _I]),
+    "pb_dem_set_params": (_I, [_P, _D, _D, _D, _D, _D, _D, _D, _D, _I, _DP, _DP]),
+    "pb_dem_sc_grid": (_I, [_P, _D, _D, _D, _D, _D, _D, _D, _D, _D, _I, _I, _IP, _IP, _DP, _DP, _DP, _DP, _IP]),
+    "pb_dem_upload_real": (_I, [_P, _S, _I, _I, _DP]),
+    "pb_dem_download_real": (_I, [_P, _S, _I, _I, _DP]),
+    "pb_set_counts": (_I, [_P, _I, _I]),
+    "pb_dem_upload_contacts": (_I, [_P, _I, _IP, _IP, _IP, _DP, _DP]),
+    "pb_dem_download_contacts": (_I, [_P, _I, _IP, _IP, _IP, _IP, _DP, _DP]),
+    "pb_dem_update_mass_and_inertia": (_I, [_P]),
+    "pb_dem_reset_contact_usage": (_I, [_P]),
+    "pb_dem_clear_unused_contacts": (_I, [_P]),
+    "pb_dem_gravity": (_I, [_P]),
+    "pb_dem_linear_spring_dashpot": (_I, [_P]),
+    "pb_dem_euler": (_I, [_P]),
+    "pb_dem_contact_overflow": (_I, [_P]),
+    "pb_dem_run": (_I, [_P, _D, _I, _I]),
     "pb_nccl_unique_id": (_I, [_P]),
     "pb_nccl_init": (_I, [_P, _P]),
     "pb_md_run": (_I, [_P, ctypes.POINTER(MdParams), _I, _I, _DP, _I, _IP]),
@@ -301,6 +317,69 @@ class Context:
 
     def synchronize(self):
         self._ck(self.lib.pb_synchronize(self.h))
+
+    # ---- DEM ----
+    DEM_WIDTH = {"radius": 1, "angular_velocity": 3, "torque": 3, "normal": 3, "inv_inertia": 9, "rotation_matrix": 9, "rotation_quat": 4,
+                 "force": 3, "mass": 1, "linear_velocity": 3}
+
+    def dem_enable(self, contact_capacity=20):
+        self._ck(self.lib.pb_dem_enable(self.h, contact_capacity))
+        self.contact_capacity = contact_capacity
+
+    def dem_set_params(self, dt, pi, kappa, ln_dry_res_coeff, collision_time, density_particle, density_fluid, gravity, ntypes,
+                       friction_static, friction_dynamic):
+        fs, fd = _f64(friction_static), _f64(friction_dynamic)
+        self._ck(self.lib.pb_dem_set_params(self.h, dt, pi, kappa, ln_dry_res_coeff, collision_time, density_particle, density_fluid,
+                                            gravity, ntypes, _dp(fs), _dp(fd)))
+
+    def dem_sc_grid(self, xmax, ymax, zmax, spacing, diameter, min_diameter, max_diameter, initial_velocity, particle_density, ntypes):
+        n = _I(0)
+        args = (xmax, ymax, zmax, spacing, diameter, min_diameter, max_diameter, initial_velocity, particle_density, ntypes)
+        self._ck(self.lib.pb_dem_sc_grid(self.h, *args, 0, None, None, None, None, None, None, ctypes.byref(n)))
+        c = n.value
+        out = {"uid": np.zeros(c, np.int32), "type": np.zeros(c, np.int32), "mass": np.zeros(c), "radius": np.zeros(c),
+               "position": np.zeros((c, 3)), "linear_velocity": np.zeros((c, 3))}
+        self._ck(self.lib.pb_dem_sc_grid(self.h, *args, c, _ip(out["uid"]), _ip(out["type"]), _dp(out["mass"]), _dp(out["radius"]),
+                                         _dp(out["position"]), _dp(out["linear_velocity"]), ctypes.byref(n)))
+        return out
+
+    def dem_upload(self, name, data, first=0):
+        a = _f64(data)
+        n = a.size // self.DEM_WIDTH[name]
+        self._ck(self.lib.pb_dem_upload_real(self.h, name.encode(), first, n, _dp(a)))
+
+    def dem_download(self, name, n=None, first=0):
+        nl, ng = self.counts()
+        n = nl if n is None else n
+        w = self.DEM_WIDTH[name]
+        out = np.zeros(n * w)
+        self._ck(self.lib.pb_dem_download_real(self.h, name.encode(), first, n, _dp(out)))
+        return out.reshape(n, w) if w > 1 else out
+
+    def set_counts(self, nlocal, nghost):
+        self._ck(self.lib.pb_set_counts(self.h, nlocal, nghost))
+
+    def dem_upload_contacts(self, num, uid, sticking, tsd, ivm):
+        num, uid, st = _i32(num), _i32(uid), _i32(sticking)
+        t, v = _f64(tsd), _f64(ivm)
+        self._ck(self.lib.pb_dem_upload_contacts(self.h, len(num), _ip(num), _ip(uid), _ip(st), _dp(t), _dp(v)))
+
+    def dem_download_contacts(self, n=None):
+        nl, _ = self.counts()
+        n = nl if n is None else n
+        C = self.contact_capacity
+        num = np.zeros(n, np.int32)
+        uid, used, st = (np.zeros((n, C), np.int32) for _ in range(3))
+        tsd, ivm = np.zeros((n, C, 3)), np.zeros((n, C))
+        self._ck(self.lib.pb_dem_download_contacts(self.h, n, _ip(num), _ip(uid), _ip(used), _ip(st), _dp(tsd), _dp(ivm)))
+        return {"num_contacts": num, "contact_lists": uid, "contact_used": used, "is_sticking": st,
+                "tangential_spring_displacement": tsd, "impact_velocity_magnitude": ivm}
+
+    def dem_stage(self, name):
+        self._ck(getattr(self.lib, "pb_dem_" + name)(self.h))
+
+    def dem_run(self, cell_spacing, ts_begin, ts_end):
+        self._ck(self.lib.pb_dem_run(self.h, cell_spacing, ts_begin, ts_end))
 
     def nccl_init(self, id128: bytes):
         buf = ctypes.create_string_buffer(id128, 128)

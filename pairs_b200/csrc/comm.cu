@@ -13,6 +13,7 @@
 // Wire records are rows of doubles as in the reference (ints cast to double, comm.py:328-329), one extra element
 // carries the particle tag:   exchange: uid shape flags x y z mass vx vy vz type tag          (12 doubles)
 //                             borders : uid type mass x y z vx vy vz shape tag              (11 doubles)
+//                             borders (DEM): ... + radius wx wy wz                           (15 doubles)
 //                             sync    : x y z vx vy vz                                      ( 6 doubles)
 // Positions are shifted by send_mult * L on ALL three axes exactly as comm.py:320-321 does (two of the
 // multipliers are zero), so ghost coordinates are bit-identical to the reference's.
@@ -24,7 +25,7 @@ int pb_sort_locals(pb_ctx *ctx);
 int pb_transport_sizes(pb_ctx *ctx, int dim);
 int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const double **recv_src);
 
-static const int BORDER_ELEMS = 11, SYNC_ELEMS = 6;
+static const int BORDER_ELEMS = 11, BORDER_ELEMS_DEM = 15, SYNC_ELEMS = 6;
 
 struct PbBox {
     double len[3];
@@ -90,17 +91,25 @@ static void pb_set_offsets(pb_ctx *ctx, int step) {
 }
 
 // ---- borders -----------------------------------------------------------------------------------------------
+template<bool DEM>
 __global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, int cap, PbBox box, const int *__restrict__ send_map,
                                                         const int *__restrict__ send_mult, const double4 *__restrict__ pos,
                                                         const double *__restrict__ vel, const double *__restrict__ mass,
                                                         const int *__restrict__ uid, const int *__restrict__ shape,
-                                                        const int *__restrict__ tag, double *__restrict__ buf) {
+                                                        const int *__restrict__ tag, double *__restrict__ buf,
+                                                        const double *__restrict__ radius, const double *__restrict__ angvel) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= count) { return; }
     const int e = first + k;
     const int p = send_map[e];
     const double4 x = pos[p];
-    double *b = buf + (size_t) e * BORDER_ELEMS;
+    double *b = buf + (size_t) e * (DEM ? BORDER_ELEMS_DEM : BORDER_ELEMS);
+    if(DEM) {
+        b[11] = radius[p];
+        b[12] = angvel[p];
+        b[13] = angvel[cap + p];
+        b[14] = angvel[2 * cap + p];
+    }
     b[0] = (double) uid[p];
     b[1] = (double) pb_w_type(x.w);
     b[2] = mass[p];
@@ -114,14 +123,22 @@ __global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, in
     b[10] = (double) tag[p];
 }
 
+template<bool DEM>
 __global__ void __launch_bounds__(256) pb_k_unpack_border(int first_rec, int count, int dst0, int cap, const double *__restrict__ buf,
                                                           double4 *__restrict__ pos, double *__restrict__ vel, double *__restrict__ mass,
                                                           int *__restrict__ type, int *__restrict__ flags, int *__restrict__ uid,
-                                                          int *__restrict__ shape, int *__restrict__ tag) {
+                                                          int *__restrict__ shape, int *__restrict__ tag, double *__restrict__ radius,
+                                                          double *__restrict__ angvel) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= count) { return; }
-    const double *b = buf + (size_t) (first_rec + k) * BORDER_ELEMS;
+    const double *b = buf + (size_t) (first_rec + k) * (DEM ? BORDER_ELEMS_DEM : BORDER_ELEMS);
     const int p = dst0 + k;
+    if(DEM) {
+        radius[p] = b[11];
+        angvel[p] = b[12];
+        angvel[cap + p] = b[13];
+        angvel[2 * cap + p] = b[14];
+    }
     const int t = (int) b[1];
     uid[p] = (int) b[0];
     type[p] = t;
@@ -165,15 +182,28 @@ extern "C" int pb_borders(pb_ctx *ctx) {
         const int nr = ctx->nrecv[step * 2] + ctx->nrecv[step * 2 + 1];
         PB_TRY(pb_ensure_particle_capacity(ctx, ctx->nlocal + ctx->nghost + nr));
         if(ns > 0) {
-            PB_LAUNCH(pb_k_pack_border, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, pb_box(ctx), ctx->send_map,
-                      ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf);
+            if(ctx->dem) {
+                PB_LAUNCH(pb_k_pack_border<true>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, pb_box(ctx),
+                          ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
+                          ctx->radius, ctx->angvel);
+            } else {
+                PB_LAUNCH(pb_k_pack_border<false>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, pb_box(ctx),
+                          ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
+                          nullptr, nullptr);
+            }
         }
         const double *src = nullptr;
-        PB_TRY(pb_transport_data(ctx, step, step + 1, BORDER_ELEMS, &src));
+        PB_TRY(pb_transport_data(ctx, step, step + 1, ctx->dem ? BORDER_ELEMS_DEM : BORDER_ELEMS, &src));
         if(nr > 0) {
-            PB_LAUNCH(pb_k_unpack_border, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
-                      ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
-                      ctx->uid, ctx->shape, ctx->tag);
+            if(ctx->dem) {
+                PB_LAUNCH(pb_k_unpack_border<true>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
+                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                          ctx->uid, ctx->shape, ctx->tag, ctx->radius, ctx->angvel);
+            } else {
+                PB_LAUNCH(pb_k_unpack_border<false>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
+                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                          ctx->uid, ctx->shape, ctx->tag, nullptr, nullptr);
+            }
         }
         ctx->nghost += nr;
     }
@@ -280,6 +310,7 @@ extern "C" int pb_exchange(pb_ctx *ctx) {
     }
     // cell-order reordering of the locals (north-star item a): the reference permutes locals here too (hole filling,
     // comm.py:445-506); ours is a stable counting sort on the flat cell index
-    PB_TRY(pb_sort_locals(ctx));
+    // (DEM: particles keep their index so that the per-particle contact tables need not move; see dem_kernels.cu)
+    if(!ctx->dem) { PB_TRY(pb_sort_locals(ctx)); }
     return 0;
 }

@@ -59,7 +59,10 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->tag_alt, ctx->particle_cell, ctx->cell_count, ctx->cell_start, ctx->cell_slot, ctx->cell_list,
                     ctx->cell_key, ctx->scan_tmp, ctx->neigh, ctx->numneigh, ctx->d_eps, ctx->d_sig6, ctx->send_map, ctx->send_mult,
                     ctx->send_buf, ctx->recv_buf, ctx->sel_flag, ctx->sel_scan, ctx->mig_scan_a, ctx->mig_scan_b, ctx->d_partial, ctx->d_scalars,
-                    ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary};
+                    ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
+                    ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
+                    ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->d_fric_static,
+                    ctx->d_fric_dynamic, ctx->d_dem_flag};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
@@ -75,7 +78,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
 
 // ---- growable device arrays -------------------------------------------------------------------------------
 template<typename T>
-static int pb_regrow(pb_ctx *ctx, T **p, size_t old_count, size_t new_count, bool keep) {
+int pb_regrow(pb_ctx *ctx, T **p, size_t old_count, size_t new_count, bool keep) {
     T *q = nullptr;
     PB_CHECK(cudaMalloc(&q, sizeof(T) * new_count));
     if(keep && *p != nullptr && old_count > 0) {
@@ -87,13 +90,16 @@ static int pb_regrow(pb_ctx *ctx, T **p, size_t old_count, size_t new_count, boo
     return 0;
 }
 
-// SoA [3][cap] arrays need a strided move when the capacity changes
-static int pb_regrow_soa3(pb_ctx *ctx, double **p, size_t old_cap, size_t new_cap, size_t used, bool keep) {
+template int pb_regrow<int>(pb_ctx *, int **, size_t, size_t, bool);
+template int pb_regrow<double>(pb_ctx *, double **, size_t, size_t, bool);
+
+// SoA [comps][cap] arrays need a strided move when the capacity changes
+int pb_regrow_soa(pb_ctx *ctx, double **p, int comps, size_t old_cap, size_t new_cap, size_t used, bool keep) {
     double *q = nullptr;
-    PB_CHECK(cudaMalloc(&q, sizeof(double) * 3 * new_cap));
-    PB_CHECK(cudaMemsetAsync(q, 0, sizeof(double) * 3 * new_cap, ctx->stream));
+    PB_CHECK(cudaMalloc(&q, sizeof(double) * comps * new_cap));
+    PB_CHECK(cudaMemsetAsync(q, 0, sizeof(double) * comps * new_cap, ctx->stream));
     if(keep && *p != nullptr && used > 0) {
-        for(int d = 0; d < 3; d++) {
+        for(int d = 0; d < comps; d++) {
             PB_CHECK(cudaMemcpyAsync(q + d * new_cap, *p + d * old_cap, sizeof(double) * used, cudaMemcpyDeviceToDevice, ctx->stream));
         }
     }
@@ -101,6 +107,10 @@ static int pb_regrow_soa3(pb_ctx *ctx, double **p, size_t old_cap, size_t new_ca
     if(*p != nullptr) { PB_CHECK(cudaFree(*p)); }
     *p = q;
     return 0;
+}
+
+static int pb_regrow_soa3(pb_ctx *ctx, double **p, size_t old_cap, size_t new_cap, size_t used, bool keep) {
+    return pb_regrow_soa(ctx, p, 3, old_cap, new_cap, used, keep);
 }
 
 int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
@@ -134,6 +144,7 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
         PB_TRY(pb_regrow(ctx, &ctx->mig_scan_b, 0, newcap + 1, false));
     }
     PB_TRY(pb_regrow(ctx, &ctx->numneigh, 0, newcap, false));
+    if(ctx->dem) { PB_TRY(pb_dem_grow(ctx, oldcap, newcap, used)); }
     ctx->pcap = (int) newcap;
     return 0;
 }
@@ -321,6 +332,12 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
         PB_LAUNCH(pb_k_fill_real, B, T, n, ctx->mass, 1.0);
     }
     PB_CHECK(cudaMemsetAsync(ctx->force, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
+    if(ctx->dem) {   // DEM extras start zeroed (defaults of add_property); contact tables are emptied
+        PB_CHECK(cudaMemsetAsync(ctx->torque, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
+        PB_CHECK(cudaMemsetAsync(ctx->angvel, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
+        PB_CHECK(cudaMemsetAsync(ctx->normal, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
+        PB_CHECK(cudaMemsetAsync(ctx->num_contacts, 0, sizeof(int) * (size_t) ctx->pcap, ctx->stream));
+    }
     ctx->force_is_zero = false;
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     PB_CHECK(cudaFree(stage));

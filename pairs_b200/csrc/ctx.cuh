@@ -102,6 +102,22 @@ struct pb_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_sync = nullptr;
 
+    // ---- DEM (examples/dem.py): extra particle properties + per-particle contact history ----
+    bool dem = false;
+    int ccontacts = 0;            // contact capacity per particle (neighbor_capacity of pairs.simulation(), 20 in dem.py)
+    double *radius = nullptr;     // [pcap]
+    double *angvel = nullptr, *torque = nullptr, *normal = nullptr;   // SoA [3][pcap]
+    double *inv_inertia = nullptr, *rotmat = nullptr;                 // SoA [9][pcap]
+    double *quat = nullptr;                                           // SoA [4][pcap]
+    int *num_contacts = nullptr;  // [pcap]
+    int *contact_uid = nullptr, *contact_used = nullptr, *contact_stick = nullptr;   // [ccontacts][pcap]
+    double *contact_tsd = nullptr;   // [3][ccontacts][pcap]
+    double *contact_ivm = nullptr;   // [ccontacts][pcap]
+    int dem_ntypes = 1;
+    double *d_fric_static = nullptr, *d_fric_dynamic = nullptr;
+    double dem_params[16];        // PbDemParams, see dem_math.h
+    int *d_dem_flag = nullptr;    // [0]: contact capacity overflow
+
     // ---- LJ feature properties ----
     int ntypes = 0;
     bool lj_uniform = false;
@@ -142,7 +158,7 @@ struct pb_ctx {
     void set_error(const std::string &e) { err = e; }
 };
 
-static const int PB_MAX_ELEMS = 12;   // doubles per packed particle record (exchange: 12, borders: 11, sync: 6)
+static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record (exchange: 12, borders: 11, sync: 6)
 static const int PB_NSCALARS = 16;
 
 // ---- helpers shared by the .cu files ----
@@ -150,6 +166,9 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed);
 int pb_ensure_send_capacity(pb_ctx *ctx, int needed);
 int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n);   // out[0..n], out[n] = total
 int pb_bin_particles(pb_ctx *ctx, int first, int n, bool write_particle_cell);
+int pb_dem_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used);
+template<typename T> int pb_regrow(pb_ctx *ctx, T **p, size_t old_count, size_t new_count, bool keep);
+int pb_regrow_soa(pb_ctx *ctx, double **p, int comps, size_t old_cap, size_t new_cap, size_t used, bool keep);
 
 // Brackets one stage with two events from the pool; nothing is synchronised here.
 struct PbStage {

@@ -1,0 +1,609 @@
+// DEM path of examples/dem.py on the GPU: spheres + half-spaces, linear spring-dashpot contacts with tangential history.
+//
+// Replaces the generated modules update_mass_and_inertia / gravity / linear_spring_dashpot / euler /
+// reset_contact_history_usage_status / clear_unused_contact_history (examples/dem.py:6-91, sim/contact_history.py:75-127,
+// mapping/funcs.py:230-263) and the set-up function pairs::dem_sc_grid (runtime/dem_sc_grid.hpp:62-172).
+// The per-pair and per-particle arithmetic lives in dem_math.h (bit-identical to the reference's generated code).
+//
+// Traversal = the reference's cell-list traversal (no Verlet lists in dem.py): for every local, non-FIXED particle i the
+// sphere sweep over cell 0 + the 27 stencil cells, then the half-space sweep (sim/interaction.py:91-92: shape loop
+// outermost).  Contacts are keyed by the partner's uid in a per-particle table of `ccontacts` slots, stored slot-major
+// ([slot][particle]) so the 32 lanes of a warp touch consecutive addresses.  Slot order and the order in which a particle's
+// pair forces are summed follow OUR cell-list order, not the reference's: contact history is compared as per-uid sets,
+// forces to 1e-12.
+//
+// Round 1 scope: single GPU (periodic images through pb_exchange / pb_borders), particles are NOT physically re-sorted
+// (contact rows stay with their particle index); multi-GPU migration of contact history is not implemented yet.
+#include <algorithm>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "ctx.cuh"
+#include "dem_math.h"
+
+int pb_materialise_force_reset(pb_ctx *ctx);
+
+static PbDemParams pb_dem_params(const pb_ctx *ctx) {
+    PbDemParams P;
+    memcpy(&P, ctx->dem_params, sizeof(PbDemParams));
+    return P;
+}
+
+// ---- allocation -------------------------------------------------------------------------------------------------
+int pb_dem_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used) {
+    const int C = ctx->ccontacts;
+    PB_TRY(pb_regrow(ctx, &ctx->radius, used, newcap, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->angvel, 3, oldcap, newcap, used, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->torque, 3, oldcap, newcap, used, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->normal, 3, oldcap, newcap, used, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->inv_inertia, 9, oldcap, newcap, used, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->rotmat, 9, oldcap, newcap, used, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->quat, 4, oldcap, newcap, used, true));
+    // contact tables: [slot][particle] -> strided move
+    auto grow_int = [&](int **p, int comps) -> int {
+        int *q = nullptr;
+        PB_CHECK(cudaMalloc(&q, sizeof(int) * comps * newcap));
+        PB_CHECK(cudaMemsetAsync(q, 0, sizeof(int) * comps * newcap, ctx->stream));
+        if(*p != nullptr && used > 0) {
+            for(int c = 0; c < comps; c++) {
+                PB_CHECK(cudaMemcpyAsync(q + c * newcap, *p + c * oldcap, sizeof(int) * used, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        if(*p != nullptr) { PB_CHECK(cudaFree(*p)); }
+        *p = q;
+        return 0;
+    };
+    PB_TRY(grow_int(&ctx->num_contacts, 1));
+    PB_TRY(grow_int(&ctx->contact_uid, C));
+    PB_TRY(grow_int(&ctx->contact_used, C));
+    PB_TRY(grow_int(&ctx->contact_stick, C));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->contact_tsd, 3 * C, oldcap, newcap, used, true));
+    PB_TRY(pb_regrow_soa(ctx, &ctx->contact_ivm, C, oldcap, newcap, used, true));
+    return 0;
+}
+
+// use_contact_history=True path of pairs.simulation(): allocates the DEM property set.  contact_capacity = neighbor_capacity.
+extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(ctx->dem) { return 0; }
+    if(contact_capacity < 1 || contact_capacity > 64) { ctx->set_error("pb_dem_enable: 1 <= contact_capacity <= 64"); return -1; }
+    ctx->ccontacts = contact_capacity;
+    ctx->dem = true;
+    PB_CHECK(cudaMalloc(&ctx->d_dem_flag, sizeof(int) * 4));
+    PB_CHECK(cudaMemset(ctx->d_dem_flag, 0, sizeof(int) * 4));
+    if(ctx->pcap > 0) { PB_TRY(pb_dem_grow(ctx, (size_t) ctx->pcap, (size_t) ctx->pcap, (size_t) ctx->nlocal + ctx->nghost)); }
+    return 0;
+}
+
+// symbols of the dem.py kernels + feature properties friction_static / friction_dynamic [ntypes*ntypes]
+extern "C" int pb_dem_set_params(pb_ctx *ctx, double dt, double pi, double kappa, double ln_dry_res_coeff, double collision_time,
+                                 double density_particle, double density_fluid, double gravity, int ntypes,
+                                 const double *friction_static, const double *friction_dynamic) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem) { ctx->set_error("pb_dem_set_params: call pb_dem_enable first"); return -1; }
+    if(ntypes < 1 || ntypes > 8) { ctx->set_error("pb_dem_set_params: 1 <= ntypes <= 8"); return -1; }
+    PbDemParams P;
+    P.dt = dt;
+    P.c_sum = pi * pi + ln_dry_res_coeff * ln_dry_res_coeff;
+    P.ct2 = collision_time * collision_time;
+    P.ct = collision_time;
+    P.ln_coeff = ln_dry_res_coeff;
+    P.kappa = kappa;
+    P.sqrt_kappa = sqrt(kappa);
+    P.grav_coeff = density_particle - density_fluid;
+    P.gravity = gravity;
+    P.pi = pi;
+    static_assert(sizeof(PbDemParams) <= sizeof(double) * 16, "PbDemParams too large");
+    memcpy(ctx->dem_params, &P, sizeof(PbDemParams));
+    ctx->dem_ntypes = ntypes;
+    if(ctx->d_fric_static == nullptr) {
+        PB_CHECK(cudaMalloc(&ctx->d_fric_static, sizeof(double) * 64));
+        PB_CHECK(cudaMalloc(&ctx->d_fric_dynamic, sizeof(double) * 64));
+    }
+    PB_CHECK(cudaMemcpy(ctx->d_fric_static, friction_static, sizeof(double) * ntypes * ntypes, cudaMemcpyHostToDevice));
+    PB_CHECK(cudaMemcpy(ctx->d_fric_dynamic, friction_dynamic, sizeof(double) * ntypes * ntypes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ---- set-up: pairs::dem_sc_grid (runtime/dem_sc_grid.hpp:62-172), host side -------------------------------------------
+// Same libstdc++ generator (std::mt19937, default seed) and distribution as the reference, hence the same stream.  Particle
+// types use the private rand() stream of setup.cu's convention (seed 1).  Two-call pattern: out pointers may be NULL to
+// count.  Arrays are the reference's AoS host layout.
+extern "C" int pb_dem_sc_grid(pb_ctx *ctx, double xmax, double ymax, double zmax, double spacing, double diameter, double min_diameter,
+                              double max_diameter, double initial_velocity, double particle_density, int ntypes, int capacity,
+                              int *uid, int *type, double *mass, double *radius, double *position, double *velocity, int *count) {
+    if(!ctx->domain_set) { ctx->set_error("pb_dem_sc_grid: domain not initialised"); return -1; }
+    std::mt19937 generator;
+    struct random_data rd;
+    char statebuf[128];
+    memset(&rd, 0, sizeof(rd));
+    memset(statebuf, 0, sizeof(statebuf));
+    initstate_r(1, statebuf, sizeof(statebuf), &rd);
+    auto real_random = [&](double lo, double hi) {
+        std::uniform_real_distribution<double> distribution(lo, hi);
+        return distribution(generator);
+    };
+    auto within = [&](const double *p, const double *aabb) {
+        return p[0] >= aabb[0] && p[0] < aabb[3] && p[1] >= aabb[1] && p[1] < aabb[4] && p[2] >= aabb[2] && p[2] < aabb[5];
+    };
+    auto in_subdomain = [&](double x, double y, double z) {
+        return x >= ctx->subdom[0] && x < ctx->subdom[1] - 0.00001 && y >= ctx->subdom[2] && y < ctx->subdom[3] - 0.00001 &&
+               z >= ctx->subdom[4] && z < ctx->subdom[5] - 0.00001;
+    };
+    int last_uid = 1, n = 0;
+    const double xmin = 0.0, ymin = 0.0, zmin = diameter;
+    double gen_domain[] = {xmin, ymin, zmin, xmax, ymax, zmax};
+    double ref_point[] = {spacing * 0.5, spacing * 0.5, spacing * 0.5};
+    const int iret = (int) (ceil((xmin - ref_point[0]) / spacing));
+    const int jret = (int) (ceil((ymin - ref_point[1]) / spacing));
+    const int kret = (int) (ceil((zmin - ref_point[2]) / spacing));
+    int i = iret, j = jret, k = kret;
+    double point[3] = {ref_point[0] + i * spacing, ref_point[1] + j * spacing, ref_point[2] + k * spacing};
+    while(within(point, gen_domain)) {
+        const double diam = real_random(min_diameter, max_diameter);
+        if(in_subdomain(point[0], point[1], point[2])) {
+            const double rad = diam * 0.5;
+            const double vx = 0.1 * real_random(-initial_velocity, initial_velocity);
+            const double vy = 0.1 * real_random(-initial_velocity, initial_velocity);
+            int32_t r = 0;
+            random_r(&rd, &r);
+            if(uid != nullptr) {
+                if(n >= capacity) { ctx->set_error("pb_dem_sc_grid: capacity too small"); return -1; }
+                uid[n] = last_uid;
+                radius[n] = rad;
+                mass[n] = ((4.0 / 3.0) * M_PI) * rad * rad * rad * particle_density;
+                position[n * 3] = point[0]; position[n * 3 + 1] = point[1]; position[n * 3 + 2] = point[2];
+                velocity[n * 3] = vx; velocity[n * 3 + 1] = vy; velocity[n * 3 + 2] = -initial_velocity;
+                type[n] = (int) (r % ntypes);
+            }
+            n++;
+        }
+        ++i;
+        point[0] = ref_point[0] + i * spacing; point[1] = ref_point[1] + j * spacing; point[2] = ref_point[2] + k * spacing;
+        if(!within(point, gen_domain)) {
+            i = iret; j++;
+            point[0] = ref_point[0] + i * spacing; point[1] = ref_point[1] + j * spacing; point[2] = ref_point[2] + k * spacing;
+            if(!within(point, gen_domain)) {
+                j = jret; k++;
+                point[0] = ref_point[0] + i * spacing; point[1] = ref_point[1] + j * spacing; point[2] = ref_point[2] + k * spacing;
+                if(!within(point, gen_domain)) { break; }
+            }
+        }
+        last_uid++;
+    }
+    *count = n;
+    return 0;
+}
+
+// ---- generic upload / download of the DEM properties (reference AoS host layout) ------------------------------------
+struct PbDemProp {
+    double *ptr;
+    int comps;
+};
+
+static bool pb_dem_prop(pb_ctx *ctx, const std::string &nm, PbDemProp *out) {
+    if(nm == "radius") { *out = {ctx->radius, 1}; return true; }
+    if(nm == "angular_velocity") { *out = {ctx->angvel, 3}; return true; }
+    if(nm == "torque") { *out = {ctx->torque, 3}; return true; }
+    if(nm == "normal") { *out = {ctx->normal, 3}; return true; }
+    if(nm == "inv_inertia") { *out = {ctx->inv_inertia, 9}; return true; }
+    if(nm == "rotation_matrix") { *out = {ctx->rotmat, 9}; return true; }
+    if(nm == "rotation_quat") { *out = {ctx->quat, 4}; return true; }
+    if(nm == "force") { *out = {ctx->force, 3}; return true; }
+    if(nm == "mass") { *out = {ctx->mass, 1}; return true; }
+    if(nm == "linear_velocity") { *out = {ctx->vel, 3}; return true; }
+    return false;
+}
+
+__global__ void pb_k_aos_to_soa(int n, int cap, int comps, const double *__restrict__ aos, double *__restrict__ soa) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) { for(int c = 0; c < comps; c++) { soa[(size_t) c * cap + i] = aos[(size_t) i * comps + c]; } }
+}
+
+__global__ void pb_k_soa_to_aos(int n, int cap, int comps, const double *__restrict__ soa, double *__restrict__ aos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) { for(int c = 0; c < comps; c++) { aos[(size_t) i * comps + c] = soa[(size_t) c * cap + i]; } }
+}
+
+// n particles starting at index `first` (so ghosts can be placed explicitly by module-level tests)
+extern "C" int pb_dem_upload_real(pb_ctx *ctx, const char *name, int first, int n, const double *data) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbDemProp pr;
+    if(!ctx->dem || !pb_dem_prop(ctx, name, &pr)) { ctx->set_error(std::string("pb_dem_upload_real: unknown property ") + name); return -1; }
+    if(first + n > ctx->pcap) { ctx->set_error("pb_dem_upload_real: beyond capacity"); return -1; }
+    if(n == 0) { return 0; }
+    double *stage = nullptr;
+    PB_CHECK(cudaMalloc(&stage, sizeof(double) * (size_t) n * pr.comps));
+    PB_CHECK(cudaMemcpyAsync(stage, data, sizeof(double) * (size_t) n * pr.comps, cudaMemcpyHostToDevice, ctx->stream));
+    PB_LAUNCH(pb_k_aos_to_soa, pb_blocks(n, 256), 256, n, ctx->pcap, pr.comps, stage, pr.ptr + first);
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    PB_CHECK(cudaFree(stage));
+    if(std::string(name) == "force") { ctx->force_is_zero = false; }
+    return 0;
+}
+
+extern "C" int pb_dem_download_real(pb_ctx *ctx, const char *name, int first, int n, double *out) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbDemProp pr;
+    if(!ctx->dem || !pb_dem_prop(ctx, name, &pr)) { ctx->set_error(std::string("pb_dem_download_real: unknown property ") + name); return -1; }
+    if(n == 0) { return 0; }
+    if(std::string(name) == "force" || std::string(name) == "torque") { PB_TRY(pb_materialise_force_reset(ctx)); }
+    double *stage = nullptr;
+    PB_CHECK(cudaMalloc(&stage, sizeof(double) * (size_t) n * pr.comps));
+    PB_LAUNCH(pb_k_soa_to_aos, pb_blocks(n, 256), 256, n, ctx->pcap, pr.comps, pr.ptr + first, stage);
+    PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(double) * (size_t) n * pr.comps, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    PB_CHECK(cudaFree(stage));
+    return 0;
+}
+
+// explicit particle counts (module-level tests upload locals AND ghosts of a reference snapshot)
+extern "C" int pb_set_counts(pb_ctx *ctx, int nlocal, int nghost) {
+    if(nlocal + nghost > ctx->pcap) { ctx->set_error("pb_set_counts: beyond capacity"); return -1; }
+    ctx->nlocal = nlocal;
+    ctx->nghost = nghost;
+    ctx->cells_n = 0;
+    return 0;
+}
+
+// contact history in the reference's host layout: num[n], uid/sticking [n][C], tsd [n][C][3], ivm [n][C]
+__global__ void pb_k_contacts_in(int n, int cap, int C, const int *__restrict__ num, const int *__restrict__ uid,
+                                 const int *__restrict__ stick, const double *__restrict__ tsd, const double *__restrict__ ivm,
+                                 int *num_o, int *uid_o, int *used_o, int *stick_o, double *tsd_o, double *ivm_o) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    num_o[i] = num[i];
+    for(int c = 0; c < C; c++) {
+        uid_o[(size_t) c * cap + i] = uid[(size_t) i * C + c];
+        used_o[(size_t) c * cap + i] = 0;
+        stick_o[(size_t) c * cap + i] = stick[(size_t) i * C + c];
+        ivm_o[(size_t) c * cap + i] = ivm[(size_t) i * C + c];
+        for(int d = 0; d < 3; d++) { tsd_o[((size_t) d * C + c) * cap + i] = tsd[((size_t) i * C + c) * 3 + d]; }
+    }
+}
+
+__global__ void pb_k_contacts_out(int n, int cap, int C, const int *num_i, const int *uid_i, const int *used_i, const int *stick_i,
+                                  const double *tsd_i, const double *ivm_i, int *__restrict__ num, int *__restrict__ uid,
+                                  int *__restrict__ used, int *__restrict__ stick, double *__restrict__ tsd, double *__restrict__ ivm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    num[i] = num_i[i];
+    for(int c = 0; c < C; c++) {
+        uid[(size_t) i * C + c] = uid_i[(size_t) c * cap + i];
+        used[(size_t) i * C + c] = used_i[(size_t) c * cap + i];
+        stick[(size_t) i * C + c] = stick_i[(size_t) c * cap + i];
+        ivm[(size_t) i * C + c] = ivm_i[(size_t) c * cap + i];
+        for(int d = 0; d < 3; d++) { tsd[((size_t) i * C + c) * 3 + d] = tsd_i[((size_t) d * C + c) * cap + i]; }
+    }
+}
+
+extern "C" int pb_dem_upload_contacts(pb_ctx *ctx, int n, const int *num, const int *uid, const int *sticking, const double *tsd,
+                                      const double *ivm) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem || n > ctx->pcap) { ctx->set_error("pb_dem_upload_contacts: DEM not enabled / beyond capacity"); return -1; }
+    if(n == 0) { return 0; }
+    const int C = ctx->ccontacts;
+    int *d_num, *d_uid, *d_st;
+    double *d_tsd, *d_ivm;
+    PB_CHECK(cudaMalloc(&d_num, sizeof(int) * n));
+    PB_CHECK(cudaMalloc(&d_uid, sizeof(int) * (size_t) n * C));
+    PB_CHECK(cudaMalloc(&d_st, sizeof(int) * (size_t) n * C));
+    PB_CHECK(cudaMalloc(&d_tsd, sizeof(double) * (size_t) n * C * 3));
+    PB_CHECK(cudaMalloc(&d_ivm, sizeof(double) * (size_t) n * C));
+    PB_CHECK(cudaMemcpy(d_num, num, sizeof(int) * n, cudaMemcpyHostToDevice));
+    PB_CHECK(cudaMemcpy(d_uid, uid, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice));
+    PB_CHECK(cudaMemcpy(d_st, sticking, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice));
+    PB_CHECK(cudaMemcpy(d_tsd, tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyHostToDevice));
+    PB_CHECK(cudaMemcpy(d_ivm, ivm, sizeof(double) * (size_t) n * C, cudaMemcpyHostToDevice));
+    PB_LAUNCH(pb_k_contacts_in, pb_blocks(n, 128), 128, n, ctx->pcap, C, d_num, d_uid, d_st, d_tsd, d_ivm, ctx->num_contacts,
+              ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm);
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_num); cudaFree(d_uid); cudaFree(d_st); cudaFree(d_tsd); cudaFree(d_ivm);
+    return 0;
+}
+
+extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, int *used, int *sticking, double *tsd, double *ivm) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem || n > ctx->pcap) { ctx->set_error("pb_dem_download_contacts: DEM not enabled / beyond capacity"); return -1; }
+    if(n == 0) { return 0; }
+    const int C = ctx->ccontacts;
+    int *d_num, *d_uid, *d_us, *d_st;
+    double *d_tsd, *d_ivm;
+    PB_CHECK(cudaMalloc(&d_num, sizeof(int) * n));
+    PB_CHECK(cudaMalloc(&d_uid, sizeof(int) * (size_t) n * C));
+    PB_CHECK(cudaMalloc(&d_us, sizeof(int) * (size_t) n * C));
+    PB_CHECK(cudaMalloc(&d_st, sizeof(int) * (size_t) n * C));
+    PB_CHECK(cudaMalloc(&d_tsd, sizeof(double) * (size_t) n * C * 3));
+    PB_CHECK(cudaMalloc(&d_ivm, sizeof(double) * (size_t) n * C));
+    PB_LAUNCH(pb_k_contacts_out, pb_blocks(n, 128), 128, n, ctx->pcap, C, ctx->num_contacts, ctx->contact_uid, ctx->contact_used,
+              ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, d_num, d_uid, d_us, d_st, d_tsd, d_ivm);
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    PB_CHECK(cudaMemcpy(num, d_num, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    PB_CHECK(cudaMemcpy(uid, d_uid, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
+    PB_CHECK(cudaMemcpy(used, d_us, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
+    PB_CHECK(cudaMemcpy(sticking, d_st, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
+    PB_CHECK(cudaMemcpy(tsd, d_tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyDeviceToHost));
+    PB_CHECK(cudaMemcpy(ivm, d_ivm, sizeof(double) * (size_t) n * C, cudaMemcpyDeviceToHost));
+    cudaFree(d_num); cudaFree(d_uid); cudaFree(d_us); cudaFree(d_st); cudaFree(d_tsd); cudaFree(d_ivm);
+    return 0;
+}
+
+// ---- kernels ----------------------------------------------------------------------------------------------------
+// update_mass_and_inertia (examples/dem.py:6-15): runs once over all locals (a setup() function: no FIXED filter)
+__global__ void __launch_bounds__(256) pb_k_dem_update_mass_inertia(int n, int cap, const int *__restrict__ shape, double *__restrict__ mass,
+                                                                   const double *__restrict__ radius, double *__restrict__ Iinv,
+                                                                   double *__restrict__ R, double *__restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    const double eye[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0};
+    for(int c = 0; c < 9; c++) { R[(size_t) c * cap + i] = eye[c]; }
+    q[i] = 1.0; q[(size_t) cap + i] = 0.0; q[(size_t) 2 * cap + i] = 0.0; q[(size_t) 3 * cap + i] = 0.0;
+    double I[9];
+    if(shape[i] == PB_SHAPE_SPHERE) {
+        pb_dem_sphere_inv_inertia(mass[i], radius[i], I);
+    } else {
+        mass[i] = INFINITY;
+        for(int c = 0; c < 9; c++) { I[c] = 0.0; }
+    }
+    for(int c = 0; c < 9; c++) { Iinv[(size_t) c * cap + i] = I[c]; }
+}
+
+extern "C" int pb_dem_update_mass_and_inertia(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem) { ctx->set_error("DEM not enabled"); return -1; }
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_dem_update_mass_inertia, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, ctx->shape, ctx->mass, ctx->radius,
+              ctx->inv_inertia, ctx->rotmat, ctx->quat);
+    return 0;
+}
+
+// gravity (examples/dem.py:88-90), compute() kernel: FIXED particles are skipped (mapping/funcs.py:305-310)
+__global__ void __launch_bounds__(256) pb_k_dem_gravity(int n, int cap, PbDemParams P, const int *__restrict__ flags,
+                                                       const double *__restrict__ radius, double *__restrict__ force) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || (flags[i] & PB_FLAG_FIXED) != 0) { return; }
+    force[(size_t) 2 * cap + i] = pb_dem_gravity(P, radius[i], force[(size_t) 2 * cap + i]);
+}
+
+extern "C" int pb_dem_gravity(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "gravity");
+    PB_TRY(pb_materialise_force_reset(ctx));
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_dem_gravity, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, pb_dem_params(ctx), ctx->flags, ctx->radius,
+              ctx->force);
+    return 0;
+}
+
+// reset_contact_history_usage_status (sim/contact_history.py:75-87)
+__global__ void __launch_bounds__(256) pb_k_dem_reset_usage(int n, int cap, const int *__restrict__ num, int *__restrict__ used) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    const int c_n = num[i];
+    for(int c = 0; c < c_n; c++) { used[(size_t) c * cap + i] = 0; }
+}
+
+extern "C" int pb_dem_reset_contact_usage(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "reset_contact_history_usage_status");
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_dem_reset_usage, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, ctx->num_contacts, ctx->contact_used);
+    return 0;
+}
+
+// clear_unused_contact_history (sim/contact_history.py:90-127, cell-list branch): unused slots are overwritten by the last slot
+__global__ void __launch_bounds__(256) pb_k_dem_clear_unused(int n, int cap, int C, int *__restrict__ num, int *__restrict__ uid,
+                                                            int *__restrict__ used, int *__restrict__ stick, double *__restrict__ tsd,
+                                                            double *__restrict__ ivm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    int c = 0, cnt = num[i];
+    while(c < cnt) {
+        if(used[(size_t) c * cap + i] == 0) {
+            const int last = cnt - 1;
+            if(last > 0) {
+                stick[(size_t) c * cap + i] = stick[(size_t) last * cap + i];
+                for(int d = 0; d < 3; d++) { tsd[((size_t) d * C + c) * cap + i] = tsd[((size_t) d * C + last) * cap + i]; }
+                ivm[(size_t) c * cap + i] = ivm[(size_t) last * cap + i];
+                uid[(size_t) c * cap + i] = uid[(size_t) last * cap + i];
+                used[(size_t) c * cap + i] = used[(size_t) last * cap + i];
+            }
+            cnt--;
+        } else {
+            c++;
+        }
+    }
+    num[i] = cnt;
+}
+
+extern "C" int pb_dem_clear_unused_contacts(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "clear_unused_contact_history");
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_dem_clear_unused, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, ctx->ccontacts, ctx->num_contacts,
+              ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm);
+    return 0;
+}
+
+// linear_spring_dashpot (examples/dem.py:18-74) over the cell lists; one thread per local particle
+__global__ void __launch_bounds__(128) pb_k_dem_contacts(int nlocal, int cap, int ncells, int dim1, int dim2, int C, int ntypes, PbDemParams P,
+                                                         const double4 *__restrict__ pos, const double *__restrict__ vel,
+                                                         const double *__restrict__ angvel, const double *__restrict__ mass,
+                                                         const double *__restrict__ radius, const double *__restrict__ normal,
+                                                         const int *__restrict__ flags, const int *__restrict__ shape,
+                                                         const int *__restrict__ uid, const int *__restrict__ particle_cell,
+                                                         const int *__restrict__ cell_start, const int *__restrict__ cell_list,
+                                                         const double *__restrict__ fric_s, const double *__restrict__ fric_d,
+                                                         int *__restrict__ num_contacts, int *__restrict__ c_uid, int *__restrict__ c_used,
+                                                         int *__restrict__ c_stick, double *__restrict__ c_tsd, double *__restrict__ c_ivm,
+                                                         double *__restrict__ force, double *__restrict__ torque, int accumulate,
+                                                         int *__restrict__ overflow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal) { return; }
+    const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
+    double Fs[3] = {0.0, 0.0, 0.0}, Ts[3] = {0.0, 0.0, 0.0}, Fh[3] = {0.0, 0.0, 0.0}, Th[3] = {0.0, 0.0, 0.0};
+    if(!fixed) {
+        const double4 pi4 = pb_ld_pos(pos + i);
+        const double xi[3] = {pi4.x, pi4.y, pi4.z};
+        const int ti = pb_w_type(pi4.w) * ntypes;
+        const double vi[3] = {vel[i], vel[(size_t) cap + i], vel[(size_t) 2 * cap + i]};
+        const double wi[3] = {angvel[i], angvel[(size_t) cap + i], angvel[(size_t) 2 * cap + i]};
+        const double ri = radius[i];
+        const double inv_mi = 1.0 / mass[i];
+        const int pc = particle_cell[i];
+        int ncont = num_contacts[i];
+        for(int sh = 0; sh < 2; sh++) {       // shape loop outermost: spheres, then half-spaces (sim/interaction.py:91-92)
+            double *F = (sh == 0) ? Fs : Fh, *T = (sh == 0) ? Ts : Th;
+            for(int run = 0; run < 10; run++) {
+                int c_lo, c_hi;
+                if(run == 0) {
+                    c_lo = 0; c_hi = 0;
+                } else {
+                    const int r = run - 1;
+                    const int mid = pc + ((r / 3 - 1) * dim1 + (r % 3 - 1)) * dim2;
+                    c_lo = max(mid - 1, 1);
+                    c_hi = min(mid + 1, ncells - 1);
+                    if(c_lo > c_hi) { continue; }
+                }
+                const int b = cell_start[c_lo], e = cell_start[c_hi + 1];
+                for(int k = b; k < e; k++) {
+                    const int j = __ldg(cell_list + k);
+                    if(j == i || shape[j] != sh) { continue; }
+                    const double4 pj4 = pb_ld_pos(pos + j);
+                    const double xj[3] = {pj4.x, pj4.y, pj4.z};
+                    double n[3], cp[3], delta;
+                    int hit;
+                    if(sh == PB_SHAPE_SPHERE) {
+                        hit = pb_dem_geom_sphere(xi, ri, xj, radius[j], n, cp, &delta);
+                    } else {
+                        const double nj[3] = {normal[j], normal[(size_t) cap + j], normal[(size_t) 2 * cap + j]};
+                        hit = pb_dem_geom_halfspace(xi, ri, xj, nj, n, cp, &delta);
+                    }
+                    if(!hit) { continue; }
+                    // contact-history slot keyed by uid[j] (mapping/funcs.py:240-263): last match wins, miss -> append defaults
+                    const int uj = uid[j];
+                    int slot = -1;
+                    for(int c = 0; c < ncont; c++) { if(c_uid[(size_t) c * cap + i] == uj) { slot = c; } }
+                    if(slot == -1) {
+                        if(ncont >= C) { atomicMax(overflow, ncont + 1); continue; }
+                        slot = ncont++;
+                        c_uid[(size_t) slot * cap + i] = uj;
+                        c_stick[(size_t) slot * cap + i] = 0;
+                        for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = 0.0; }
+                        c_ivm[(size_t) slot * cap + i] = 0.0;
+                    }
+                    c_used[(size_t) slot * cap + i] = 1;
+                    double tsd[3] = {c_tsd[((size_t) 0 * C + slot) * cap + i], c_tsd[((size_t) 1 * C + slot) * cap + i],
+                                     c_tsd[((size_t) 2 * C + slot) * cap + i]};
+                    double ivm = c_ivm[(size_t) slot * cap + i];
+                    int stick = c_stick[(size_t) slot * cap + i];
+                    const double vj[3] = {vel[j], vel[(size_t) cap + j], vel[(size_t) 2 * cap + j]};
+                    const double wj[3] = {angvel[j], angvel[(size_t) cap + j], angvel[(size_t) 2 * cap + j]};
+                    const int tj = pb_w_type(pj4.w);
+                    double Fp[3], Tp[3];
+                    pb_dem_pair_force(P, xi, vi, wi, inv_mi, xj, vj, wj, mass[j], n, cp, delta, fric_s[ti + tj], fric_d[ti + tj], tsd, &ivm,
+                                      &stick, Fp, Tp);
+                    for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = tsd[d]; }
+                    c_ivm[(size_t) slot * cap + i] = ivm;
+                    c_stick[(size_t) slot * cap + i] = stick;
+                    for(int d = 0; d < 3; d++) { F[d] = F[d] + Fp[d]; T[d] = T[d] + Tp[d]; }
+                }
+            }
+        }
+        num_contacts[i] = ncont;
+    }
+    // prop[i] = prop[i] + (acc_sphere + acc_halfspace)  (sim/interaction.py:280-292)
+    for(int d = 0; d < 3; d++) {
+        const double f_old = accumulate ? force[(size_t) d * cap + i] : 0.0;
+        const double t_old = accumulate ? torque[(size_t) d * cap + i] : 0.0;
+        if(!fixed) {
+            force[(size_t) d * cap + i] = f_old + (Fs[d] + Fh[d]);
+            torque[(size_t) d * cap + i] = t_old + (Ts[d] + Th[d]);
+        } else if(!accumulate) {
+            force[(size_t) d * cap + i] = 0.0;
+            torque[(size_t) d * cap + i] = 0.0;
+        }
+    }
+}
+
+extern "C" int pb_dem_linear_spring_dashpot(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "linear_spring_dashpot");
+    if(!ctx->dem) { ctx->set_error("DEM not enabled"); return -1; }
+    if(ctx->cells_n != ctx->nlocal + ctx->nghost) { ctx->set_error("pb_dem_linear_spring_dashpot: cell lists are stale"); return -1; }
+    PB_TRY(pb_materialise_force_reset(ctx));     // gravity precedes this kernel and already needs the zeroed force
+    if(ctx->nlocal == 0) { return 0; }
+    PB_CHECK(cudaMemsetAsync(ctx->d_dem_flag, 0, sizeof(int), ctx->stream));
+    PB_LAUNCH(pb_k_dem_contacts, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2],
+              ctx->ccontacts, ctx->dem_ntypes, pb_dem_params(ctx), ctx->pos, ctx->vel, ctx->angvel, ctx->mass, ctx->radius, ctx->normal,
+              ctx->flags, ctx->shape, ctx->uid, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->d_fric_static, ctx->d_fric_dynamic,
+              ctx->num_contacts, ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->force,
+              ctx->torque, 1, ctx->d_dem_flag);
+    return 0;
+}
+
+// returns > 0 (needed capacity) if a particle ran out of contact slots since the last check
+extern "C" int pb_dem_contact_overflow(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_dem_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    return ctx->h_scalars[0];
+}
+
+// euler (examples/dem.py:77-85)
+__global__ void __launch_bounds__(128) pb_k_dem_euler(int n, int cap, double dt, const int *__restrict__ flags, const double *__restrict__ mass,
+                                                      const double *__restrict__ force, const double *__restrict__ torque,
+                                                      const double *__restrict__ Iinv, double4 *__restrict__ pos, double *__restrict__ vel,
+                                                      double *__restrict__ angvel, double *__restrict__ quat, double *__restrict__ rotmat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n || (flags[i] & PB_FLAG_FIXED) != 0) { return; }
+    double4 p = pos[i];
+    double x[3] = {p.x, p.y, p.z}, v[3], w[3], f[3], tau[3], q[4], R[9], I[9];
+    for(int d = 0; d < 3; d++) {
+        v[d] = vel[(size_t) d * cap + i]; w[d] = angvel[(size_t) d * cap + i];
+        f[d] = force[(size_t) d * cap + i]; tau[d] = torque[(size_t) d * cap + i];
+    }
+    for(int c = 0; c < 4; c++) { q[c] = quat[(size_t) c * cap + i]; }
+    for(int c = 0; c < 9; c++) { R[c] = rotmat[(size_t) c * cap + i]; I[c] = Iinv[(size_t) c * cap + i]; }
+    pb_dem_euler(dt, mass[i], f, tau, I, x, v, w, q, R);
+    p.x = x[0]; p.y = x[1]; p.z = x[2];
+    pos[i] = p;
+    for(int d = 0; d < 3; d++) { vel[(size_t) d * cap + i] = v[d]; angvel[(size_t) d * cap + i] = w[d]; }
+    for(int c = 0; c < 4; c++) { quat[(size_t) c * cap + i] = q[c]; }
+    for(int c = 0; c < 9; c++) { rotmat[(size_t) c * cap + i] = R[c]; }
+}
+
+extern "C" int pb_dem_euler(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "euler");
+    PB_TRY(pb_materialise_force_reset(ctx));
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_dem_euler, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, pb_dem_params(ctx).dt, ctx->flags, ctx->mass, ctx->force,
+              ctx->torque, ctx->inv_inertia, ctx->pos, ctx->vel, ctx->angvel, ctx->quat, ctx->rotmat);
+    return 0;
+}
+
+// ---- the generated DEM timestep loop (sim/simulation.py:387-417 with use_contact_history, reneighbour every step) ----
+extern "C" int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts_end) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem) { ctx->set_error("DEM not enabled"); return -1; }
+    if(ctx->world > 1) { ctx->set_error("pb_dem_run: multi-GPU DEM (contact-history migration) is not implemented yet"); return -1; }
+    if(!ctx->cells_set || ctx->spacing != cell_spacing) { PB_TRY(pb_setup_cells(ctx, cell_spacing)); }
+    for(int ts = ts_begin; ts < ts_end; ts++) {
+        PB_TRY(pb_exchange(ctx));
+        PB_TRY(pb_borders(ctx));
+        PB_TRY(pb_build_cell_lists(ctx));
+        PB_TRY(pb_dem_reset_contact_usage(ctx));
+        PB_TRY(pb_reset_volatile(ctx));
+        PB_TRY(pb_dem_gravity(ctx));
+        PB_TRY(pb_dem_linear_spring_dashpot(ctx));
+        PB_TRY(pb_dem_euler(ctx));
+        PB_TRY(pb_dem_clear_unused_contacts(ctx));
+    }
+    const int need = pb_dem_contact_overflow(ctx);
+    if(need > 0) { ctx->set_error("contact capacity exceeded: a particle needs " + std::to_string(need) + " contact slots"); return -1; }
+    return 0;
+}

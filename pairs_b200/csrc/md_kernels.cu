@@ -191,6 +191,9 @@ int pb_materialise_force_reset(pb_ctx *ctx) {
     if(ctx->force_is_zero) {
         for(int d = 0; d < 3; d++) {
             PB_CHECK(cudaMemsetAsync(ctx->force + (size_t) d * ctx->pcap, 0, sizeof(double) * (size_t) ctx->nlocal, ctx->stream));
+            if(ctx->dem) {   // torque is the second volatile property of dem.py
+                PB_CHECK(cudaMemsetAsync(ctx->torque + (size_t) d * ctx->pcap, 0, sizeof(double) * (size_t) ctx->nlocal, ctx->stream));
+            }
         }
         ctx->force_is_zero = false;
     }

@@ -1,0 +1,40 @@
+"""Generates tests/golden/dem_t1.npz from the REFERENCE ITSELF: the reference generator's serial C++ for examples/dem.py on a
+0.1 x 0.015 x 0.04 box (variant dem_t1 of oracle/build_ref.py: 420 spheres + 2 half-spaces, 700 steps), run in a fresh process.
+Kept: state at module boundaries of three iterations (before / after linear_spring_dashpot, after euler; locals + ghosts) and the
+end-of-iteration state of a few iterations.  Needs /root/reference (this container only).
+
+    python tests/golden/make_golden_dem.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_worker  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MODULE_STEPS = [150, 300, 400]
+END_STEPS = [0, 100, 200, 300, 399]
+INPUT = ["position", "linear_velocity", "angular_velocity", "force", "torque", "mass", "radius", "normal", "inv_inertia", "rotation_matrix",
+         "rotation_quat", "uid", "type", "flags", "shape", "num_contacts", "contact_lists", "is_sticking", "tangential_spring_displacement",
+         "impact_velocity_magnitude", "particle_cell"]
+POST = ["force", "torque", "num_contacts", "contact_lists", "contact_used", "is_sticking", "tangential_spring_displacement",
+        "impact_velocity_magnitude"]
+EUL = ["position", "linear_velocity", "angular_velocity", "rotation_quat", "rotation_matrix"]
+END = ["position", "linear_velocity", "angular_velocity", "rotation_quat", "uid", "num_contacts", "contact_lists", "is_sticking",
+       "tangential_spring_displacement", "impact_velocity_magnitude", "mass", "radius", "inv_inertia", "flags", "shape", "type", "normal"]
+
+z = ref_worker.dump_dem("dem_t1", "/tmp/dem_t1_golden_raw.npz", 401, sorted(set(MODULE_STEPS + END_STEPS)))
+out = {"nlocal": z["nlocal"], "nghost": z["nghost"], "module_steps": np.array(MODULE_STEPS), "end_steps": np.array(END_STEPS)}
+for ts in MODULE_STEPS:
+    for tag, names in (("pre", INPUT), ("post", POST), ("eul", EUL)):
+        for k in names:
+            out[f"{tag}_{ts}_{k}"] = z[f"{tag}_{ts}_{k}"]
+for ts in END_STEPS:
+    for k in END:
+        out[f"end_{ts}_{k}"] = z[f"end_{ts}_{k}"]
+path = os.path.join(HERE, "dem_t1.npz")
+np.savez_compressed(path, **out)
+print("dem_t1:", os.path.getsize(path) // 1024, "KiB,", int(z["nlocal"][0]), "locals,", int(z["nghost"][0]), "ghosts")

@@ -1,0 +1,136 @@
+"""GPU parity tests of the DEM path (examples/dem.py) through the C-ABI against golden states of the reference's generated C++:
+module level on identical inputs (contact kernel, euler, gravity, history bookkeeping) and the whole loop from the reference's
+own set-up (dem_sc_grid + planes + update_mass_and_inertia) over the first 400 iterations."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import dem_common as dc
+
+pytestmark = pytest.mark.gpu
+
+REAL = ["radius", "angular_velocity", "torque", "normal", "inv_inertia", "rotation_matrix", "rotation_quat", "force"]
+
+
+def make_ctx():
+    from pairs_b200.backend import Context
+    ctx = Context(0)
+    ctx.init_domain([0.0, dc.DOMAIN[0], 0.0, dc.DOMAIN[1], 0.0, dc.DOMAIN[2]], pbc=(1, 1, 0), partitioner=1)
+    ctx.dem_enable(dc.C)
+    ctx.dem_set_params(dc.DT, math.pi, dc.KAPPA, dc.LN_DRY, dc.COLLISION_TIME, dc.RHO_P, dc.RHO_F, dc.G, dc.NTYPES, dc.FS, dc.FD)
+    ctx.setup_cells(dc.CELL)
+    return ctx
+
+
+def upload_snapshot(ctx, s, nlocal):
+    """Locals AND ghosts of a reference snapshot, placed explicitly (no comm): module-level inputs are then identical."""
+    n = len(s["mass"])
+    ctx.upload(s["position"], s["linear_velocity"], s["mass"], s["type"], s["flags"], s["uid"], s["shape"])
+    for name in REAL:
+        ctx.dem_upload(name, s[name])
+    ctx.dem_upload_contacts(s["num_contacts"], s["contact_lists"], s["is_sticking"], s["tangential_spring_displacement"],
+                            s["impact_velocity_magnitude"])
+    ctx.set_counts(nlocal, n - nlocal)
+
+
+@pytest.mark.parametrize("ts", [150, 300, 400])
+def test_modules_on_reference_inputs(ts):
+    z = dc.gold()
+    nl = int(z["nlocal"][ts])
+    names = [k[len(f"pre_{ts}_"):] for k in z.files if k.startswith(f"pre_{ts}_")]
+    pre = dc.state(z, "pre", ts, names)
+    ctx = make_ctx()
+    upload_snapshot(ctx, pre, nl)
+    ctx.build_cell_lists()
+    assert np.array_equal(ctx.ints("particle_cell", True), pre["particle_cell"])          # cell assignment: bit-exact
+    ctx.dem_stage("linear_spring_dashpot")
+    assert ctx.lib.pb_dem_contact_overflow(ctx.h) == 0
+    f, t = ctx.dem_download("force", nl), ctx.dem_download("torque", nl)
+    rf, rt = z[f"post_{ts}_force"][:nl], z[f"post_{ts}_torque"][:nl]
+    assert np.abs(f - rf).max() <= 1e-12 * np.abs(rf).max()
+    assert np.abs(t - rt).max() <= 1e-12 * max(np.abs(rt).max(), 1e-300)
+    c = ctx.dem_download_contacts(nl)
+    ours = dc.contact_sets(c["num_contacts"], c["contact_lists"], c["is_sticking"], c["tangential_spring_displacement"],
+                           c["impact_velocity_magnitude"], nl)
+    ref = dc.contact_sets(z[f"post_{ts}_num_contacts"], z[f"post_{ts}_contact_lists"], z[f"post_{ts}_is_sticking"],
+                          z[f"post_{ts}_tangential_spring_displacement"], z[f"post_{ts}_impact_velocity_magnitude"], nl)
+    assert ours == ref                                              # contact-history bookkeeping: bit-exact (per partner uid)
+    used_ref = z[f"post_{ts}_contact_used"][:nl]
+    assert int(c["contact_used"].sum()) == int(sum(used_ref[i, :z[f"post_{ts}_num_contacts"][i]].sum() for i in range(nl)))
+    # euler on the reference's forces (isolates the integrator): linear part bit-exact, rotation to 1e-12 (device sin/cos)
+    ctx.dem_upload("force", z[f"post_{ts}_force"])
+    ctx.dem_upload("torque", z[f"post_{ts}_torque"])
+    ctx.dem_stage("euler")
+    assert np.array_equal(ctx.real("position")[:nl], z[f"eul_{ts}_position"][:nl])
+    assert np.array_equal(ctx.real("linear_velocity")[:nl], z[f"eul_{ts}_linear_velocity"][:nl])
+    assert np.array_equal(ctx.dem_download("angular_velocity", nl), z[f"eul_{ts}_angular_velocity"][:nl])
+    assert np.abs(ctx.dem_download("rotation_quat", nl) - z[f"eul_{ts}_rotation_quat"][:nl]).max() <= 1e-12
+    assert np.abs(ctx.dem_download("rotation_matrix", nl) - z[f"eul_{ts}_rotation_matrix"][:nl]).max() <= 1e-12
+    # clear_unused_contact_history: every surviving slot was used this step
+    ctx.dem_stage("clear_unused_contacts")
+    c2 = ctx.dem_download_contacts(nl)
+    assert all(c2["contact_used"][i, :c2["num_contacts"][i]].all() for i in range(nl))
+    assert c2["num_contacts"].sum() == c["contact_used"].sum()
+
+
+def setup_like_reference(ctx):
+    g = ctx.dem_sc_grid(dc.DOMAIN[0], dc.DOMAIN[1], dc.DOMAIN[2], dc.SPACING, dc.DIAMETER, dc.MIN_D, dc.MAX_D, dc.V0, dc.RHO_P, dc.NTYPES)
+    ns = len(g["uid"])
+    npl = len(dc.PLANES)
+    n = ns + npl
+    pos, vel = np.zeros((n, 3)), np.zeros((n, 3))
+    mass, radius, normal = np.ones(n), np.ones(n), np.zeros((n, 3))      # add_property defaults: mass 1.0, radius 1.0
+    uid, typ, flags, shape = (np.zeros(n, np.int32) for _ in range(4))
+    pos[:ns], vel[:ns], mass[:ns], radius[:ns], uid[:ns], typ[:ns] = g["position"], g["linear_velocity"], g["mass"], g["radius"], g["uid"], g["type"]
+    for k, (u, t, m, p, nrm, fl) in enumerate(dc.PLANES):
+        i = ns + k
+        uid[i], typ[i], mass[i], pos[i], normal[i], flags[i], shape[i] = u, t, m, p, nrm, fl, 1
+    ctx.upload(pos, vel, mass, typ, flags, uid, shape)
+    ctx.dem_upload("radius", radius)
+    ctx.dem_upload("normal", normal)
+    ctx.dem_stage("update_mass_and_inertia")
+    return n
+
+
+def test_setup_matches_reference_bit_for_bit():
+    z = dc.gold()
+    ctx = make_ctx()
+    n = setup_like_reference(ctx)
+    assert n == int(z["nlocal"][0]) == 422
+    ctx.dem_run(dc.CELL, 0, 1)
+    tag = ctx.ints("tag")
+    assert np.array_equal(tag, np.arange(n))                          # DEM keeps particle order
+    for name in ("mass", "radius", "inv_inertia"):
+        ours = ctx.dem_download(name, n)
+        assert np.array_equal(ours, z[f"end_0_{name}"]), name
+    assert np.array_equal(ctx.ints("uid"), z["end_0_uid"]) and np.array_equal(ctx.ints("flags"), z["end_0_flags"])
+    assert np.array_equal(ctx.real("position"), z["end_0_position"])
+    assert np.array_equal(ctx.real("linear_velocity"), z["end_0_linear_velocity"])
+    assert ctx.counts() == (int(z["nlocal"][0]), int(z["nghost"][0]))
+
+
+def test_dem_loop_matches_reference_over_400_steps():
+    """Whole generated loop (exchange, borders, cell lists, usage reset, gravity, contacts, euler, history clean-up) from the
+    reference's set-up.  Window: iterations 0..399, before the first particle with live contacts wraps around the periodic
+    box (from there on the stock reference corrupts transferred contact history)."""
+    z = dc.gold()
+    ctx = make_ctx()
+    n = setup_like_reference(ctx)
+    done = 0
+    for ts in [int(t) for t in z["end_steps"]]:
+        ctx.dem_run(dc.CELL, done, ts + 1)
+        done = ts + 1
+        assert ctx.counts() == (int(z["nlocal"][ts]), int(z["nghost"][ts])), ts
+        scale = np.abs(z[f"end_{ts}_position"][:n - 2]).max()
+        assert np.abs(ctx.real("position") - z[f"end_{ts}_position"]).max() <= 1e-12 * scale, ts
+        vref = z[f"end_{ts}_linear_velocity"]
+        assert np.abs(ctx.real("linear_velocity") - vref).max() <= 1e-10 * np.abs(vref).max(), ts
+        wref = z[f"end_{ts}_angular_velocity"]
+        assert np.abs(ctx.dem_download("angular_velocity", n) - wref).max() <= 1e-9 * max(np.abs(wref).max(), 1e-300), ts
+        c = ctx.dem_download_contacts(n)
+        assert np.array_equal(c["num_contacts"], z[f"end_{ts}_num_contacts"]), ts
+        ours = [set(c["contact_lists"][i, :c["num_contacts"][i]]) for i in range(n)]
+        ref = [set(z[f"end_{ts}_contact_lists"][i, :z[f"end_{ts}_num_contacts"][i]]) for i in range(n)]
+        assert ours == ref, ts                                        # who touches whom: identical
+    assert z[f"end_399_num_contacts"].sum() > 100
