@@ -80,7 +80,8 @@ def setup_like_reference(ctx):
     npl = len(dc.PLANES)
     n = ns + npl
     pos, vel = np.zeros((n, 3)), np.zeros((n, 3))
-    mass, radius, normal = np.ones(n), np.ones(n), np.zeros((n, 3))      # add_property defaults: mass 1.0, radius 1.0
+    # the reference never applies add_property() default values at run time: untouched slots are zero pages (planes: radius 0)
+    mass, radius, normal = np.ones(n), np.zeros(n), np.zeros((n, 3))
     uid, typ, flags, shape = (np.zeros(n, np.int32) for _ in range(4))
     pos[:ns], vel[:ns], mass[:ns], radius[:ns], uid[:ns], typ[:ns] = g["position"], g["linear_velocity"], g["mass"], g["radius"], g["uid"], g["type"]
     for k, (u, t, m, p, nrm, fl) in enumerate(dc.PLANES):
