@@ -69,6 +69,90 @@ def K(P_i):
 def K(P_i):
     R_velocity[P_i] += (R_dt * 0.5) * R_force[P_i] / R_mass[P_i]
 """,
+    # examples/dem.py:6-15 (a setup() function)
+    "update_mass_and_inertia": """
+def K(P_i):
+    R_rotation_matrix[P_i] = diagonal_matrix(1.0)
+    R_rotation_quat[P_i] = default_quaternion()
+
+    if is_sphere(P_i):
+        R_inv_inertia[P_i] = inversed(diagonal_matrix(0.4 * R_mass[P_i] * R_radius[P_i] * R_radius[P_i]))
+
+    else:
+        R_mass[P_i] = R_infinity
+        R_inv_inertia[P_i] = 0.0
+""",
+    # examples/dem.py:88-90
+    "gravity": """
+def K(P_i):
+    L_volume = (4.0 / 3.0) * R_pi * R_radius[P_i] * R_radius[P_i] * R_radius[P_i]
+    R_force[P_i][2] = R_force[P_i][2] - (R_density_particle - R_density_fluid) * L_volume * R_gravity
+""",
+    # examples/dem.py:77-85
+    "euler": """
+def K(P_i):
+    L_inv_mass = 1.0 / R_mass[P_i]
+    R_position[P_i] += 0.5 * L_inv_mass * R_force[P_i] * R_dt * R_dt + R_velocity[P_i] * R_dt
+    R_velocity[P_i] += L_inv_mass * R_force[P_i] * R_dt
+    L_wdot = R_rotation_matrix[P_i] * (R_inv_inertia[P_i] * R_torque[P_i]) * transposed(R_rotation_matrix[P_i])
+    L_phi = R_angular_velocity[P_i] * R_dt + 0.5 * L_wdot * R_dt * R_dt
+    R_rotation_quat[P_i] = quaternion(L_phi, length(L_phi)) * R_rotation_quat[P_i]
+    R_rotation_matrix[P_i] = quaternion_to_rotation_matrix(R_rotation_quat[P_i])
+    R_angular_velocity[P_i] += L_wdot * R_dt
+""",
+    # examples/dem.py:18-74: linear spring-dashpot with tangential history and Coulomb friction
+    "linear_spring_dashpot": """
+def K(P_i, P_j):
+    L_delta = -penetration_depth(P_i, P_j)
+    skip_when(L_delta < 0.0)
+
+    L_meff = 1.0 / ((1.0 / R_mass[P_i]) + (1.0 / R_mass[P_j]))
+    L_kn = L_meff * (R_pi * R_pi + R_ln_coeff * R_ln_coeff) / (R_collision_time * R_collision_time)
+    L_kt = R_kappa * L_kn
+    L_dn = -2.0 * L_meff * R_ln_coeff / R_collision_time
+    L_dtan = sqrt(R_kappa) * L_dn
+
+    L_vwi = R_velocity[P_i] + cross(R_angular_velocity[P_i], contact_point(P_i, P_j) - R_position[P_i])
+    L_vwj = R_velocity[P_j] + cross(R_angular_velocity[P_j], contact_point(P_i, P_j) - R_position[P_j])
+
+    L_rel = -(L_vwi - L_vwj)
+    L_reln = dot(L_rel, contact_normal(P_i, P_j)) * contact_normal(P_i, P_j)
+    L_relt = L_rel - L_reln
+    L_fN = L_kn * L_delta * contact_normal(P_i, P_j) + L_dn * L_reln
+
+    L_tsd = R_tsd[P_i, P_j]
+    L_ivm = R_ivm[P_i, P_j]
+    L_imp = select(L_ivm > 0.0, L_ivm, length(L_rel))
+    L_stick = R_sticking[P_i, P_j]
+
+    L_rot = L_tsd - contact_normal(P_i, P_j) * dot(L_tsd, contact_normal(P_i, P_j))
+    L_rot2 = squared_length(L_rot)
+    L_ntsd = R_dt * L_relt + select(L_rot2 <= 0.0, zero_vector(), L_rot * sqrt(squared_length(L_tsd) / L_rot2))
+
+    L_fTLS = L_kt * L_ntsd + L_dtan * L_relt
+    L_fTLS_len = length(L_fTLS)
+    L_t = normalized(L_fTLS)
+
+    L_fs = R_friction_static[P_i, P_j] * length(L_fN)
+    L_fd = R_friction_dynamic[P_i, P_j] * length(L_fN)
+    L_thr = 1e-8
+
+    L_c1 = L_stick == 1 and length(L_relt) < L_thr and L_fTLS_len < L_fs
+    L_c2 = L_stick == 1 and L_fTLS_len < L_fd
+    L_fabs = select(L_c1, L_fs, L_fd)
+    L_nstick = select(L_c1 or L_c2 or L_fTLS_len < L_fd, 1, 0)
+    R_tsd[P_i, P_j] = select(not L_c1 and not L_c2 and L_kt > 0.0, (L_fabs * L_t - L_dtan * L_relt) / L_kt, L_ntsd)
+
+    R_ivm[P_i, P_j] = L_imp
+    R_sticking[P_i, P_j] = L_nstick
+
+    L_fTabs = min(L_fTLS_len, L_fabs)
+    L_fT = L_fTabs * L_t
+    L_pf = L_fN + L_fT
+
+    apply(R_force, L_pf)
+    apply(R_torque, cross(contact_point(P_i, P_j) - R_position, L_pf))
+""",
 }
 
 
@@ -169,6 +253,7 @@ class Simulation:
         self.cell_spacing = None
         self.neighbor_cutoff = None
         self.setups = []
+        self.setup_functions = []
         self.pre_step = []
         self.functions = []
         self.vtk_file = None
@@ -210,6 +295,7 @@ class Simulation:
     def add_feature(self, name, nkinds):
         assert name not in self.features, f"Feature already defined: {name}"
         self.features[name] = nkinds
+        self.props.setdefault(name, _Prop(name, Types.Int32, 0, False))     # e.g. 'type': one int per particle
 
     def add_feature_property(self, feature, name, ptype, data):
         assert feature in self.features, f"Feature not found: {feature}"
@@ -250,11 +336,15 @@ class Simulation:
     def from_file(self, filename, prop_names):      # legacy
         self.read_particle_data(filename, prop_names, Shapes.PointMass)
 
-    def dem_sc_grid(self, *args):
-        raise DslError("dem_sc_grid: the DEM path is not implemented by this backend yet (SURVEY.md 8a rows a10-a13)")
+    def dem_sc_grid(self, xmax, ymax, zmax, spacing, diameter, min_diameter, max_diameter, initial_velocity, particle_density, ntypes):
+        self.setups.append(("dem_sc_grid", (xmax, ymax, zmax, spacing, diameter, min_diameter, max_diameter, initial_velocity,
+                                            particle_density, ntypes)))
 
     def setup(self, func, symbols={}):
-        raise DslError("setup(): only the MD (Lennard-Jones) path is implemented by this backend so far")
+        family, roles = recognise(func)
+        if family != "update_mass_and_inertia":
+            raise DslError(f"setup(): '{func.__name__}' is not a set-up function this backend implements")
+        self.setup_functions.append({"name": func.__name__, "family": family, "roles": roles, "symbols": dict(symbols)})
 
     def build_cell_lists(self, spacing, store_neighbors_per_cell=False):
         if store_neighbors_per_cell:
@@ -306,9 +396,12 @@ class Simulation:
         ctx.init_domain(grid, self._pbc, self._partitioner, world, rank)
         if world > 1:
             ctx.nccl_init(_broadcast_nccl_id(backend, rank, world))
-        ctx.reserve(0, self.neighbor_capacity)
         if self.cell_spacing is None:
             raise DslError("build_cell_lists() / build_neighbor_lists() was not called")
+        families = [e["family"] for e in self.pre_step + self.functions]
+        if "linear_spring_dashpot" in families:
+            return self._generate_dem(ctx, rank, world)
+        ctx.reserve(0, self.neighbor_capacity)
 
         # ---- set-up ----
         nlocal = 0
@@ -340,6 +433,101 @@ class Simulation:
         all_ms = (time.perf_counter() - t0) * 1e3
         self._print_summary(ctx, all_ms, rank)
         return ctx
+
+    # -- DEM (examples/dem.py): spheres + half-spaces, contact history, cell-list traversal, reneighbouring every step --
+    def _generate_dem(self, ctx, rank, world):
+        fams = [e["family"] for e in self.functions]
+        if self.pre_step or fams != ["gravity", "linear_spring_dashpot", "euler"] or not self.use_contact_history \
+                or self.neighbor_cutoff is not None or self.reneighbor_frequency != 1:
+            raise DslError("DEM: only the procedure list of examples/dem.py (gravity, linear_spring_dashpot, euler over cell lists, "
+                           "contact history, reneighbouring every step) is implemented")
+        if world > 1:
+            raise DslError("DEM on several GPUs (contact-history migration) is not implemented yet")
+        grav, lsd, eul = self.functions
+        nk = 1
+        fs_name, fd_name = lsd["roles"]["friction_static"], lsd["roles"]["friction_dynamic"]
+        for nme in (fs_name, fd_name):
+            if nme not in self.feature_props:
+                raise DslError(f"{lsd['name']}: '{nme}' must be a feature property")
+        nk = self.features[self.feature_props[fs_name][0]]
+        ctx.dem_enable(self.neighbor_capacity)
+        dt = self._symbol(lsd, "dt")
+        if dt != self._symbol(eul, "dt"):
+            raise DslError("DEM: contact kernel and integrator use different dt")
+        ctx.dem_set_params(dt, self._symbol(lsd, "pi"), self._symbol(lsd, "kappa"), self._symbol(lsd, "ln_coeff"),
+                           self._symbol(lsd, "collision_time"), self._symbol(grav, "density_particle"), self._symbol(grav, "density_fluid"),
+                           self._symbol(grav, "gravity"), nk, self.feature_props[fs_name][1], self.feature_props[fd_name][1])
+        # ---- set-up: particles are appended in the order of the setup statements (sim/simulation.py:238-247) ----
+        parts = []
+        for kind, args in self.setups:
+            if kind == "dem_sc_grid":
+                g = ctx.dem_sc_grid(*args)
+                g["shape"] = np.zeros(len(g["uid"]), np.int32)
+                g["flags"] = np.zeros(len(g["uid"]), np.int32)
+                parts.append(g)
+                if rank == 0:
+                    self._dem_banner(args, len(g["uid"]))
+            elif kind == "read_particle_data":
+                parts.append(self._read_csv(*args))
+            else:
+                raise DslError(f"DEM: unsupported set-up statement {kind}")
+        n = sum(len(p["position"]) for p in parts)
+
+        def cat(name, width, dtype, default=0):
+            out = np.full((n, width) if width > 1 else n, default, dtype)
+            k = 0
+            for p in parts:
+                m = len(p["position"])
+                if name in p:
+                    out[k:k + m] = p[name]
+                k += m
+            return out
+        # untouched slots are zero in the reference (add_property defaults are not applied at run time)
+        ctx.upload(cat("position", 3, np.float64), cat("linear_velocity", 3, np.float64), cat("mass", 1, np.float64),
+                   cat("type", 1, np.int32), cat("flags", 1, np.int32), cat("uid", 1, np.int32), cat("shape", 1, np.int32))
+        ctx.dem_upload("radius", cat("radius", 1, np.float64))
+        ctx.dem_upload("normal", cat("normal", 3, np.float64))
+        for f in self.setup_functions:
+            ctx.dem_stage("update_mass_and_inertia")
+        ctx.timers_enable(True)
+        ctx.sync()
+        t0 = time.perf_counter()
+        ctx.dem_run(self.cell_spacing, 0, self.ntimesteps + 1)
+        ctx.sync()
+        all_ms = (time.perf_counter() - t0) * 1e3
+        self._print_summary(ctx, all_ms, rank)
+        return ctx
+
+    def _dem_banner(self, a, count):
+        # runtime/dem_sc_grid.hpp:159-169
+        print("DEM Simple-Cubic Grid")
+        print(f"Domain size: <{_fmt(a[0])}, {_fmt(a[1])}, {_fmt(a[2])}>")
+        print(f"Spacing: {_fmt(a[3])}")
+        print(f"Diameter: {_fmt(a[4])} (min = {_fmt(a[5])}, max = {_fmt(a[6])})")
+        print(f"Initial velocity: {_fmt(a[7])}")
+        print(f"Particle density: {_fmt(a[8])}")
+        print(f"Number of types: {a[9]}")
+        print(f"Number of particles: {count}")
+
+    def _read_csv(self, filename, prop_names, shape_id):
+        """runtime/read_from_file.hpp:33-115 -> dict of host arrays (vectors = 3 columns, in the order of prop_names)."""
+        path = filename
+        if not os.path.exists(path):
+            alt = os.path.join(os.path.dirname(os.path.abspath(sys.argv[0])), "..", filename)
+            if not os.path.exists(alt):
+                raise DslError(f"read_particle_data: {filename} not found")
+            path = alt
+        data = np.loadtxt(path, delimiter=",", ndmin=2)
+        out, k = {}, 0
+        for nme in prop_names:
+            w = 3 if self.props[nme].type == Types.Vector else 1
+            col = data[:, k:k + w] if w > 1 else data[:, k]
+            out[nme] = col.astype(np.int32) if self.props[nme].type == Types.Int32 else col
+            k += w
+        out["shape"] = np.full(len(data), shape_id, np.int32)
+        if "position" not in out:
+            out["position"] = out[self.position_name]
+        return out
 
     def _bind(self, ctx, e):
         fam = e["family"]
@@ -407,6 +595,8 @@ class Simulation:
         lines = [("all", all_ms)]
         for e in self.pre_step + self.functions:
             lines.append((e["name"], ctx.timer(e["family"])[0]))
+        if self.use_contact_history:
+            cats["contact_history"] = ("reset_contact_history_usage_status", "clear_unused_contact_history")
         for cat, names in cats.items():
             lines.append((cat, sum(ctx.timer(n)[0] for n in names)))
         nl, ng = ctx.counts()

@@ -92,3 +92,30 @@ def test_plan_and_error_behaviour():
         from pairs_b200.backend import BackendError
         with pytest.raises(BackendError):
             psim.generate()
+
+
+def test_recognises_the_dem_kernels():
+    import dem_script
+    assert dsl.recognise(dem_script.update_mass_and_inertia)[0] == "update_mass_and_inertia"
+    assert dsl.recognise(dem_script.gravity)[0] == "gravity"
+    assert dsl.recognise(dem_script.euler)[0] == "euler"
+    fam, roles = dsl.recognise(dem_script.linear_spring_dashpot)
+    assert fam == "linear_spring_dashpot" and roles["tsd"] == "tangential_spring_displacement" and roles["ln_coeff"] == "lnDryResCoeff"
+    psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10)
+    assert [e["family"] for e in psim.functions] == ["gravity", "linear_spring_dashpot", "euler"]
+    assert psim.setup_functions[0]["family"] == "update_mass_and_inertia" and psim.use_contact_history and psim._pbc == [True, True, False]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="reference checkout not present")
+def test_recognises_the_reference_dem_example_verbatim(tmp_path):
+    src = open("/root/reference/examples/dem.py").read()
+    got = {}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef):
+            p = tmp_path / f"k_{node.name}.py"
+            p.write_text(ast.get_source_segment(src, node) + "\n")
+            spec = importlib.util.spec_from_file_location(node.name, p)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            got[node.name] = dsl.recognise(getattr(mod, node.name))[0]
+    assert got == {k: k for k in ("update_mass_and_inertia", "linear_spring_dashpot", "euler", "gravity")}
