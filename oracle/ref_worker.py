@@ -114,6 +114,7 @@ def _main(argv):
         return 0
     if mode == "bench":
         warmup, steps = int(argv[2]), int(argv[3])
+        os.chdir(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref"))    # DEM programs open data/planes.input
         # redirect the program's own stdout chatter away from our JSON line
         sys.stdout.flush()
         devnull = os.open(os.devnull, os.O_WRONLY)
@@ -128,7 +129,8 @@ def _main(argv):
         t = list(buf)[:n]
         assert n >= warmup + steps + 1, (n, warmup, steps)
         seconds = t[warmup + steps] - t[warmup]
-        atoms = {"md_bench": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3}[variant]
+        atoms = {"md_bench": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3, "dem_t1": 422,
+                 "dem_bench": 160 * 160 * 39 + 2}[variant]
         print(json.dumps({"n": atoms, "seconds": seconds, "steps": steps, "warmup": warmup}))
         return 0
     raise SystemExit(f"unknown mode {mode}")
