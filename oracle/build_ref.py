@@ -58,8 +58,10 @@ def md_variant(nx, steps, thermo, reneigh, pcap=None):
     return patch
 
 
-def dem_variant(domain, steps):
+def dem_variant(domain, steps, pcap=None):
     def patch(text):
+        if pcap:
+            text = _sub(text, r"particle_capacity=\d+", f"particle_capacity={pcap}")
         text = _sub(text, r"^domainSize_SI = \[[^\]]*\]", f"domainSize_SI = [{domain[0]}, {domain[1]}, {domain[2]}]")
         text = _sub(text, r"^timeSteps = \d+", f"timeSteps = {steps}")
         text = _sub(text, r"^psim\.vtk_output\(", "#psim.vtk_output(")          # debug output, out of scope
@@ -77,7 +79,7 @@ VARIANTS = {
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
     "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
-    "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000), [], False),
+    "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),
 }
 
 
