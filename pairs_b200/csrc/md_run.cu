@@ -30,19 +30,7 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
         // groups follow once the refresh has landed.  (The reference's communication is blocking)
         const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && ctx->fuse_integrate && ctx->groups_valid &&
                              ctx->neigh_n == ctx->nlocal;
-        if(!reneigh) {
-            if(overlap) {
-                PB_CHECK(cudaEventRecord(ctx->ev_prev, ctx->stream));
-                PB_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prev, 0));
-                std::swap(ctx->stream, ctx->comm_stream);
-                const int rc = pb_synchronize(ctx);
-                if(rc >= 0) { cudaEventRecord(ctx->ev_sync, ctx->stream); }
-                std::swap(ctx->stream, ctx->comm_stream);
-                PB_TRY(rc);
-            } else {
-                PB_TRY(pb_synchronize(ctx));
-            }
-        }
+        if(!reneigh && !overlap) { PB_TRY(pb_synchronize(ctx)); }
         PB_TRY(pb_reset_volatile(ctx));
         const bool thermo_now = p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0);
         if(ctx->fuse_integrate) {
@@ -51,9 +39,18 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
             int fuse = (ts > 0) ? 1 : 0;
             if(!thermo_now && ts + 1 < ts_end) { fuse |= 2; initial_done = true; }
             if(overlap) {
+                // main stream: interior groups.  comm stream: pack -> NCCL -> unpack -> boundary groups.  The two force
+                // launches touch disjoint particles and run concurrently; the streams join before the next iteration.
+                PB_CHECK(cudaEventRecord(ctx->ev_prev, ctx->stream));
                 PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 1));
+                PB_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prev, 0));
+                std::swap(ctx->stream, ctx->comm_stream);
+                int rc = pb_synchronize(ctx);
+                if(rc >= 0) { rc = pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 2); }
+                if(rc >= 0) { cudaEventRecord(ctx->ev_sync, ctx->stream); }
+                std::swap(ctx->stream, ctx->comm_stream);
+                PB_TRY(rc);
                 PB_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
-                PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 2));
             } else {
                 PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 0));
             }
