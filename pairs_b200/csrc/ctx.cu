@@ -37,7 +37,11 @@ extern "C" int pb_create(pb_ctx **out, int device) {
     if(e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return -1; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
-    cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking);
+    {
+        int prio_lo = 0, prio_hi = 0;      // comm stream gets the highest priority: its blocks are scheduled ahead of the force kernel's
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi);
+    }
     cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
     cudaMalloc(&ctx->d_scalars, sizeof(int) * PB_NSCALARS);

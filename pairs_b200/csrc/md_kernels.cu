@@ -267,11 +267,21 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int 
     }
     PB_TRY(rc);
     ctx->lj_groups = nullptr;
-    if(part == 1) { return 0; }
+    if(part != 0) { return 0; }      // split launches: the caller finishes with pb_lj_finish_split once both are issued
     ctx->force_is_zero = false;
     if(fuse & 2) {
         // new local positions are in pos_alt; the ghosts of the current step stay behind in the old buffer until the next
         // synchronize / borders has refreshed them
+        std::swap(ctx->pos, ctx->pos_alt);
+        ctx->ghosts_in_alt = true;
+    }
+    return 0;
+}
+
+// after the interior (part 1) and boundary (part 2) launches of one force evaluation have both been issued
+int pb_lj_finish_split(pb_ctx *ctx, int fuse) {
+    ctx->force_is_zero = false;
+    if(fuse & 2) {
         std::swap(ctx->pos, ctx->pos_alt);
         ctx->ghosts_in_alt = true;
     }

@@ -9,6 +9,7 @@
 #include "ctx.cuh"
 
 int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int part);
+int pb_lj_finish_split(pb_ctx *ctx, int fuse);
 
 extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo) {
     PB_CHECK(cudaSetDevice(ctx->device));
@@ -39,10 +40,10 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
             int fuse = (ts > 0) ? 1 : 0;
             if(!thermo_now && ts + 1 < ts_end) { fuse |= 2; initial_done = true; }
             if(overlap) {
-                // main stream: interior groups.  comm stream: pack -> NCCL -> unpack -> boundary groups.  The two force
-                // launches touch disjoint particles and run concurrently; the streams join before the next iteration.
+                // comm stream (high priority, issued first so its small kernels are scheduled ahead of the big one):
+                // pack -> NCCL -> unpack -> boundary groups.  main stream: interior groups.  The two force launches touch
+                // disjoint particles; the streams join before the next iteration.
                 PB_CHECK(cudaEventRecord(ctx->ev_prev, ctx->stream));
-                PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 1));
                 PB_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_prev, 0));
                 std::swap(ctx->stream, ctx->comm_stream);
                 int rc = pb_synchronize(ctx);
@@ -50,6 +51,8 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
                 if(rc >= 0) { cudaEventRecord(ctx->ev_sync, ctx->stream); }
                 std::swap(ctx->stream, ctx->comm_stream);
                 PB_TRY(rc);
+                PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 1));
+                PB_TRY(pb_lj_finish_split(ctx, fuse));
                 PB_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sync, 0));
             } else {
                 PB_TRY(pb_lennard_jones_fused(ctx, p->cutoff_force, p->dt, fuse, 0));
