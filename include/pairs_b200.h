@@ -102,6 +102,9 @@ int pb_reset_volatile(pb_ctx *ctx);                       /* ResetVolatileProper
 int pb_lennard_jones(pb_ctx *ctx, double cutoff);         /* examples/md.py:5-8 via ParticleInteraction */
 int pb_initial_integrate(pb_ctx *ctx, double dt);         /* examples/md.py:11-13 */
 int pb_final_integrate(pb_ctx *ctx, double dt);           /* examples/md.py:16-17 */
+/* kernels of examples/lj_onetype.py (older P4IRS API): scalar epsilon/sigma6, explicit Euler */
+int pb_lj_legacy(pb_ctx *ctx, double cutoff, double epsilon, double sigma6);
+int pb_euler_legacy(pb_ctx *ctx, double dt);
 /* pairs::compute_thermo (runtime/thermo.hpp:11-51): T and P over ALL ranks' locals (rank-local sums are returned
  * in *sum_mv2 / *natoms when world_size > 1 and no communicator is attached) */
 int pb_compute_thermo(pb_ctx *ctx, double *temperature, double *pressure);

@@ -83,6 +83,8 @@ SIGNATURES = {
     "pb_lennard_jones": (_I, [_P, _D]),
     "pb_initial_integrate": (_I, [_P, _D]),
     "pb_final_integrate": (_I, [_P, _D]),
+    "pb_lj_legacy": (_I, [_P, _D, _D, _D]),
+    "pb_euler_legacy": (_I, [_P, _D]),
     "pb_compute_thermo": (_I, [_P, _DP, _DP]),
     "pb_thermo_partial": (_I, [_P, _DP, _IP]),
     "pb_exchange": (_I, [_P]),
@@ -303,6 +305,12 @@ class Context:
 
     def final_integrate(self, dt):
         self._ck(self.lib.pb_final_integrate(self.h, dt))
+
+    def lj_legacy(self, cutoff, epsilon, sigma6):
+        self._ck(self.lib.pb_lj_legacy(self.h, cutoff, epsilon, sigma6))
+
+    def euler_legacy(self, dt):
+        self._ck(self.lib.pb_euler_legacy(self.h, dt))
 
     def compute_thermo(self):
         t, p = _D(0.0), _D(0.0)

@@ -455,9 +455,13 @@ __global__ void __launch_bounds__(128) pb_k_dem_contacts(int nlocal, int cap, in
         const double inv_mi = 1.0 / mass[i];
         const int pc = particle_cell[i];
         int ncont = num_contacts[i];
+        bool other_in_stencil = false;        // a non-sphere particle was seen in one of the 27 stencil cells
         for(int sh = 0; sh < 2; sh++) {       // shape loop outermost: spheres, then half-spaces (sim/interaction.py:91-92)
             double *F = (sh == 0) ? Fs : Fh, *T = (sh == 0) ? Ts : Th;
-            for(int run = 0; run < 10; run++) {
+            // the half-space sweep visits the same cells as the sphere sweep: if that one saw no non-sphere particle in the
+            // stencil cells, only cell 0 (where INFINITE half-spaces are binned) can contribute -- skipping is exact
+            const int nruns = (sh == 0 || other_in_stencil) ? 10 : 1;
+            for(int run = 0; run < nruns; run++) {
                 int c_lo, c_hi;
                 if(run == 0) {
                     c_lo = 0; c_hi = 0;
@@ -471,7 +475,9 @@ __global__ void __launch_bounds__(128) pb_k_dem_contacts(int nlocal, int cap, in
                 const int b = cell_start[c_lo], e = cell_start[c_hi + 1];
                 for(int k = b; k < e; k++) {
                     const int j = __ldg(cell_list + k);
-                    if(j == i || shape[j] != sh) { continue; }
+                    const int sj = shape[j];
+                    if(sh == 0 && run > 0 && sj != PB_SHAPE_SPHERE) { other_in_stencil = true; }
+                    if(j == i || sj != sh) { continue; }
                     const double4 pj4 = pb_ld_pos(pos + j);
                     const double xj[3] = {pj4.x, pj4.y, pj4.z};
                     double n[3], cp[3], delta;

@@ -310,6 +310,79 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
     return -1;
 }
 
+// ---- legacy kernels of examples/lj_onetype.py (an older P4IRS API that the current reference no longer accepts; semantics
+//      follow Python's evaluation order of the script's expressions) ------------------------------
+//   lj:     sr2 = 1.0 / rsq;  sr6 = sr2*sr2*sr2*sigma6;  force[i] += delta * 48.0 * sr6 * (sr6 - 0.5) * sr2 * epsilon
+//           i.e. per component ((((d * 48.0) * sr6) * (sr6 - 0.5)) * sr2) * epsilon, scalar sigma6 / epsilon
+//   euler:  velocity[i] += dt * force[i] / mass[i];  position[i] += dt * velocity[i]
+__global__ void __launch_bounds__(128) pb_k_lj_legacy(int nlocal, int T, int cap, double cutsq, double eps, double sig6,
+                                                      const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                      const int *__restrict__ numneigh, const int *__restrict__ neigh,
+                                                      double *__restrict__ force, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal) { return; }
+    const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
+    double fx = accumulate ? force[i] : 0.0, fy = accumulate ? force[cap + i] : 0.0, fz = accumulate ? force[2 * cap + i] : 0.0;
+    if(!fixed) {
+        const double4 pi = pb_ld_pos(pos + i);
+        const int nn = numneigh[i];
+        const int *nb = neigh + (size_t) (i >> 5) * T * 32 + (i & 31);
+        for(int k = 0; k < nn; k++) {
+            const double4 pj = pb_ld_pos(pos + __ldg(nb + (size_t) k * 32));
+            const double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if(rsq < cutsq) {
+                const double sr2 = __ddiv_rn(1.0, rsq);
+                const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);
+                const double m05 = __dsub_rn(sr6, 0.5);
+                // `force[i] += expr` accumulates pair by pair into the property (no reduction temporary in the legacy form)
+                fx = __dadd_rn(fx, __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(dx, 48.0), sr6), m05), sr2), eps));
+                fy = __dadd_rn(fy, __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(dy, 48.0), sr6), m05), sr2), eps));
+                fz = __dadd_rn(fz, __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(dz, 48.0), sr6), m05), sr2), eps));
+            }
+        }
+    }
+    force[i] = fx; force[cap + i] = fy; force[2 * cap + i] = fz;
+}
+
+extern "C" int pb_lj_legacy(pb_ctx *ctx, double cutoff, double epsilon, double sigma6) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "lj");
+    if(ctx->neigh_n != ctx->nlocal || ctx->lanes != 1) { ctx->set_error("pb_lj_legacy: neighbour lists are stale (or lanes_per_particle != 1)"); return -1; }
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_lj_legacy, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->nslots, ctx->pcap, cutoff * cutoff, epsilon, sigma6, ctx->pos,
+              ctx->flags, ctx->numneigh, ctx->neigh, ctx->force, ctx->force_is_zero ? 0 : 1);
+    ctx->force_is_zero = false;
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) pb_k_euler_legacy(int nlocal, int cap, double dt, const int *__restrict__ flags,
+                                                         const double *__restrict__ force, const double *__restrict__ mass,
+                                                         double *__restrict__ vel, double4 *__restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal || (flags[i] & PB_FLAG_FIXED) != 0) { return; }
+    const double m = mass[i];
+    const double vx = __dadd_rn(vel[i], __ddiv_rn(__dmul_rn(dt, force[i]), m));
+    const double vy = __dadd_rn(vel[cap + i], __ddiv_rn(__dmul_rn(dt, force[cap + i]), m));
+    const double vz = __dadd_rn(vel[2 * cap + i], __ddiv_rn(__dmul_rn(dt, force[2 * cap + i]), m));
+    vel[i] = vx; vel[cap + i] = vy; vel[2 * cap + i] = vz;
+    double4 p = pos[i];
+    p.x = __dadd_rn(p.x, __dmul_rn(dt, vx));
+    p.y = __dadd_rn(p.y, __dmul_rn(dt, vy));
+    p.z = __dadd_rn(p.z, __dmul_rn(dt, vz));
+    pos[i] = p;
+}
+
+extern "C" int pb_euler_legacy(pb_ctx *ctx, double dt) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "euler");
+    PB_TRY(pb_materialise_force_reset(ctx));
+    if(ctx->nlocal == 0) { return 0; }
+    PB_LAUNCH(pb_k_euler_legacy, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, dt, ctx->flags, ctx->force, ctx->mass, ctx->vel,
+              ctx->pos);
+    return 0;
+}
+
 // ---- velocity Verlet (examples/md.py:11-17) -------------------------------------------------------------------
 // v += ((dt*0.5) * f) / m   (multiplication first, division last, per component);   x += dt * v
 template<bool WITH_POSITION>

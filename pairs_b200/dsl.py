@@ -69,6 +69,19 @@ def K(P_i):
 def K(P_i):
     R_velocity[P_i] += (R_dt * 0.5) * R_force[P_i] / R_mass[P_i]
 """,
+    # examples/lj_onetype.py:5-8 (older API: bare rsq / delta symbols, scalar sigma6 / epsilon, force[i] += ...)
+    "lj_legacy": """
+def K(P_i, P_j):
+    L_sr2 = 1.0 / rsq
+    L_sr6 = L_sr2 * L_sr2 * L_sr2 * R_sigma6
+    R_force[P_i] += delta * 48.0 * L_sr6 * (L_sr6 - 0.5) * L_sr2 * R_epsilon
+""",
+    # examples/lj_onetype.py:11-13
+    "euler_legacy": """
+def K(P_i):
+    R_velocity[P_i] += R_dt * R_force[P_i] / R_mass[P_i]
+    R_position[P_i] += R_dt * R_velocity[P_i]
+""",
     # examples/dem.py:6-15 (a setup() function)
     "update_mass_and_inertia": """
 def K(P_i):
@@ -333,8 +346,22 @@ class Simulation:
     def read_particle_data(self, filename, prop_names, shape_id):
         self.setups.append(("read_particle_data", (filename, list(prop_names), shape_id)))
 
-    def from_file(self, filename, prop_names):      # legacy
-        self.read_particle_data(filename, prop_names, Shapes.PointMass)
+    def from_file(self, filename, prop_names):      # legacy API of examples/lj_onetype.py
+        """miniMD set-up files `minimd_setup_<nx>x<ny>x<nz>*.input` (rows: mass, position, velocity).  The box is not stored in
+        the file: it is nx * a with the FCC lattice constant a = (4 / 0.8442)^(1/3) of the generator that wrote those files.  If
+        the file is absent (the 32x32x32 one is not shipped, .MISSING_LARGE_BLOBS) the same system is generated synthetically."""
+        import re
+        m = re.search(r"(\d+)x(\d+)x(\d+)", os.path.basename(filename))
+        if m is None:
+            raise DslError("from_file: cannot derive the box (expected a name like minimd_setup_32x32x32.input)")
+        nx, ny, nz = (int(g) for g in m.groups())
+        lattice = pow((4.0 / 0.8442), (1.0 / 3.0))
+        self.set_domain([0.0, 0.0, 0.0, nx * lattice, ny * lattice, nz * lattice])
+        if os.path.exists(filename):
+            self.read_particle_data(filename, prop_names, Shapes.PointMass)
+        else:
+            print(f"from_file: {filename} not found -- generating the same FCC system synthetically ({4 * nx * ny * nz} atoms)")
+            self.setups.append(("copper_fcc_lattice", (nx, ny, nz, 0.8442, 1.44, 1)))
 
     def dem_sc_grid(self, xmax, ymax, zmax, spacing, diameter, min_diameter, max_diameter, initial_velocity, particle_density, ntypes):
         self.setups.append(("dem_sc_grid", (xmax, ymax, zmax, spacing, diameter, min_diameter, max_diameter, initial_velocity,
@@ -544,6 +571,15 @@ class Simulation:
             self._check_prop(e, "force", Types.Vector)
             cutoff = _builtin_float(e["cutoff"])
             return dict(e, call=lambda: ctx.lennard_jones(cutoff), cutoff_value=cutoff)
+        if fam == "lj_legacy":
+            if self.neighbor_cutoff is None:
+                raise DslError("lj needs build_neighbor_lists()")
+            eps, sig6 = self._symbol(e, "epsilon"), self._symbol(e, "sigma6")
+            cutoff = _builtin_float(e["cutoff"])
+            return dict(e, call=lambda: ctx.lj_legacy(cutoff, eps, sig6))
+        if fam == "euler_legacy":
+            dt = self._symbol(e, "dt")
+            return dict(e, call=lambda: ctx.euler_legacy(dt))
         if fam in ("initial_integrate", "final_integrate"):
             dt = self._symbol(e, "dt")
             for role in ("velocity", "force", "mass"):

@@ -119,3 +119,13 @@ def test_recognises_the_reference_dem_example_verbatim(tmp_path):
             spec.loader.exec_module(mod)
             got[node.name] = dsl.recognise(getattr(mod, node.name))[0]
     assert got == {k: k for k in ("update_mass_and_inertia", "linear_spring_dashpot", "euler", "gravity")}
+
+
+def test_legacy_api_of_lj_onetype():
+    import lj_legacy_script
+    assert dsl.recognise(lj_legacy_script.lj)[0] == "lj_legacy" and dsl.recognise(lj_legacy_script.euler)[0] == "euler_legacy"
+    psim = lj_legacy_script.build("gpu", 6, 5)
+    assert psim.shapes == [pairs.point_mass()] and psim.reneighbor_frequency == 1 and psim._target.is_gpu()
+    a = pow(4.0 / 0.8442, 1.0 / 3.0)
+    assert psim.grid == [0.0, 0.0, 0.0, 6 * a, 6 * a, 6 * a] and psim.setups[0][0] == "copper_fcc_lattice"
+    assert psim.functions[0]["symbols"] == {"sigma6": 1.0, "epsilon": 1.0}

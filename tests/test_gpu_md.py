@@ -332,3 +332,30 @@ def test_lanes_per_particle_layouts_agree(lanes):
         ctx.set_option("lj_unroll", unroll)
         ctx.reset_volatile(); ctx.lennard_jones(CUT)
         assert rel_err_force(ctx.real("force"), f1) <= 1e-12 or np.abs(ctx.real("force") - f1).max() <= 1e-12
+
+
+def test_legacy_lj_onetype_kernels(capsys):
+    """examples/lj_onetype.py (older API, no oracle: the reference itself rejects the script).  Its kernels differ from md.py's
+    only in evaluation order, so: legacy force == md-form force to rounding, explicit Euler == the same IEEE operations in numpy,
+    and the script runs through generate()."""
+    import os
+    import sys
+    ctx, n = make_gpu(6, 1, [1.0], [1.0])
+    _reneighbor_gpu(ctx)
+    ctx.reset_volatile(); ctx.lennard_jones(CUT)
+    f_md = ctx.real("force")
+    ctx.reset_volatile(); ctx.lj_legacy(CUT, 1.0, 1.0)
+    f_legacy = ctx.real("force")
+    assert np.abs(f_legacy - f_md).max() <= 1e-13 * max(np.abs(f_md).max(), 1.0)
+    x, v, m = ctx.real("position"), ctx.real("linear_velocity"), ctx.real("mass")
+    ctx.euler_legacy(DT)
+    v2 = v + (DT * f_legacy) / m[:, None]
+    assert np.array_equal(ctx.real("linear_velocity"), v2) and np.array_equal(ctx.real("position"), x + DT * v2)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import lj_legacy_script
+    psim = lj_legacy_script.build("gpu", 6, 20)
+    c = psim.generate()
+    out = capsys.readouterr().out
+    assert "generating the same FCC system synthetically (864 atoms)" in out and "Number of local particles: 864 / 864" in out
+    t, _ = c.compute_thermo()
+    assert 0.5 < t < 1.5          # explicit Euler, 21 steps from T = 1.44
