@@ -105,6 +105,8 @@ int pb_final_integrate(pb_ctx *ctx, double dt);           /* examples/md.py:16-1
 /* kernels of examples/lj_onetype.py (older P4IRS API): scalar epsilon/sigma6, explicit Euler */
 int pb_lj_legacy(pb_ctx *ctx, double cutoff, double epsilon, double sigma6);
 int pb_euler_legacy(pb_ctx *ctx, double dt);
+/* potential energy and virial of the LJ system (rank-local sums over the current lists; an addition, the reference computes neither) */
+int pb_lj_energy_virial(pb_ctx *ctx, double cutoff, double *epot, double *virial);
 /* pairs::compute_thermo (runtime/thermo.hpp:11-51): T and P over ALL ranks' locals (rank-local sums are returned
  * in *sum_mv2 / *natoms when world_size > 1 and no communicator is attached) */
 int pb_compute_thermo(pb_ctx *ctx, double *temperature, double *pressure);

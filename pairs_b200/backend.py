@@ -85,6 +85,7 @@ SIGNATURES = {
     "pb_final_integrate": (_I, [_P, _D]),
     "pb_lj_legacy": (_I, [_P, _D, _D, _D]),
     "pb_euler_legacy": (_I, [_P, _D]),
+    "pb_lj_energy_virial": (_I, [_P, _D, _DP, _DP]),
     "pb_compute_thermo": (_I, [_P, _DP, _DP]),
     "pb_thermo_partial": (_I, [_P, _DP, _IP]),
     "pb_exchange": (_I, [_P]),
@@ -311,6 +312,11 @@ class Context:
 
     def euler_legacy(self, dt):
         self._ck(self.lib.pb_euler_legacy(self.h, dt))
+
+    def lj_energy_virial(self, cutoff):
+        e, w = _D(0.0), _D(0.0)
+        self._ck(self.lib.pb_lj_energy_virial(self.h, cutoff, ctypes.byref(e), ctypes.byref(w)))
+        return e.value, w.value
 
     def compute_thermo(self):
         t, p = _D(0.0), _D(0.0)

@@ -2,8 +2,11 @@
 // Replaces BuildCellListsStencil / BuildCellLists / PartitionCellLists (sim/cell_lists.py:46-171) and the dense
 // cell_particles[ncells][cell_capacity] array (25.6 MB, 64-slot rows, atomic slot claims) by
 //   particle_cell[i]  -- bit-identical to the reference's value (same fp64 subtract / divide / truncate / clamp)
-//   cell_start[c], cell_list[k]  -- CSR cell list; inside a cell particles are ordered by (sub-cell Morton key, index)
+//   cell_start[c], cell_list[k]  -- CSR cell list; inside a cell particles are ordered by (z sub-bin, index)
 // so there is no cell_capacity to overflow and the result is run-to-run reproducible.
+// Every cell is split into `zsub` slabs along z (a memory-layout choice, not a reference quantity) and the counting sort runs on
+// the combined key cell*zsub + slab: sub_start[] lets the neighbour-list build open each (dx,dy) row of the stencil exactly at
+// the z-window that can contain neighbours instead of scanning three whole cells (neighbor.cu).
 //
 // Kernels (all HBM-bound; algorithmic bytes per binned particle: pos 32 + flags 4 + particle_cell 4 w + slot 4 w,
 // then slot 4 r + cell 4 r + list 4 w; the per-cell arrays are ncells*4 B and stay in L2):
@@ -38,12 +41,16 @@ extern "C" int pb_setup_cells(pb_ctx *ctx, double spacing) {
             for(int l = -1; l < 2; l++) { ctx->stencil[k++] = (i * ctx->dim_cells[1] + j) * ctx->dim_cells[2] + l; }
         }
     }
-    if(ctx->ncells + 1 > ctx->ccap) {
-        if(ctx->cell_count != nullptr) { PB_CHECK(cudaFree(ctx->cell_count)); }
-        if(ctx->cell_start != nullptr) { PB_CHECK(cudaFree(ctx->cell_start)); }
-        ctx->ccap = ctx->ncells + 1;
-        PB_CHECK(cudaMalloc(&ctx->cell_count, sizeof(int) * ((size_t) ctx->ccap + 1)));
-        PB_CHECK(cudaMalloc(&ctx->cell_start, sizeof(int) * ((size_t) ctx->ccap + 1)));
+    // z slabs per cell: only the Verlet-list build profits from them; DEM rebins every step over many tiny cells -> 1
+    ctx->zsub_active = ctx->dem ? 1 : ctx->zsub;
+    if((long) ctx->ncells * ctx->zsub_active > 0x7ffffff0L) { ctx->set_error("pb_setup_cells: too many cell slabs"); return -1; }
+    const long need = (long) ctx->ncells * ctx->zsub_active + 2;
+    if(need > ctx->ccap) {
+        for(int **q : {&ctx->cell_count, &ctx->cell_start, &ctx->sub_start}) {
+            if(*q != nullptr) { PB_CHECK(cudaFree(*q)); }
+            PB_CHECK(cudaMalloc(q, sizeof(int) * (size_t) (need + 2)));
+        }
+        ctx->ccap = (int) need;
     }
     ctx->cells_set = true;
     ctx->cells_n = 0;
@@ -189,18 +196,13 @@ __device__ __forceinline__ int pb_cell_index(const PbCellGeom &g, double x, doub
     return (c0 * g.dim[1] + c1) * g.dim[2] + c2 + 1;
 }
 
-// Ordering key INSIDE a cell (not a reference quantity, purely a memory-layout choice): 9-bit Morton code of the
-// particle's position in an 8x8x8 sub-grid of its cell.  Particles of a cell are stored in this order, so that
-// consecutive particles -- the 32 lanes of a warp in the force kernel, and the 4 particles of a 128-byte line -- are
-// spatial neighbours at a scale well below the cutoff: the sorted neighbour lists of adjacent lanes then run through
-// nearly the same particles at the same iteration and their 32-byte gathers fall into few distinct L1 lines.
-__device__ __forceinline__ int pb_spread3(int v) { return (v & 1) | ((v & 2) << 2) | ((v & 4) << 4); }
-
-__device__ __forceinline__ int pb_subcell_key(const PbCellGeom &g, double x, double y, double z) {
-    const double q0 = (x - g.lo[0]) / g.spacing, q1 = (y - g.lo[1]) / g.spacing, q2 = (z - g.lo[2]) / g.spacing;
-    int s0 = (int) ((q0 - floor(q0)) * 8.0), s1 = (int) ((q1 - floor(q1)) * 8.0), s2 = (int) ((q2 - floor(q2)) * 8.0);
-    s0 = min(max(s0, 0), 7); s1 = min(max(s1, 0), 7); s2 = min(max(s2, 0), 7);
-    return (pb_spread3(s0) << 2) | (pb_spread3(s1) << 1) | pb_spread3(s2);
+// z slab of a particle inside its cell (consistent with the reference cell index c2 computed above)
+__device__ __forceinline__ int pb_zslab(const PbCellGeom &g, double z, int zsub) {
+    const double q2 = (z - g.lo[2]) / g.spacing;
+    int c2 = (int) q2;
+    c2 = (c2 >= 0) ? c2 : 0; c2 = (c2 < g.dim[2]) ? c2 : g.dim[2] - 1;
+    int zs = (int) ((q2 - (double) c2) * (double) zsub);
+    return min(max(zs, 0), zsub - 1);
 }
 
 // Warp-aggregated histogram: lanes of a warp that hit the same cell elect a leader which issues ONE atomicAdd
@@ -208,15 +210,16 @@ __device__ __forceinline__ int pb_subcell_key(const PbCellGeom &g, double x, dou
 __global__ void __launch_bounds__(256) pb_k_cell_count(PbCellGeom g, int first, int n, const double4 *__restrict__ pos,
                                                        const int *__restrict__ flags, int *__restrict__ particle_cell,
                                                        int *__restrict__ cell_count, int *__restrict__ cell_slot,
-                                                       int *__restrict__ cell_key) {
+                                                       int *__restrict__ cell_key, int zsub) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = k < n;
     int cell = -1;
     if(active) {
         const double4 p = pos[first + k];
-        cell = pb_cell_index(g, p.x, p.y, p.z, flags[first + k]);
-        particle_cell[first + k] = cell;
-        cell_key[first + k] = pb_subcell_key(g, p.x, p.y, p.z);
+        const int c = pb_cell_index(g, p.x, p.y, p.z, flags[first + k]);
+        particle_cell[first + k] = c;
+        cell = c * zsub + ((c == 0) ? 0 : pb_zslab(g, p.z, zsub));      // counting-sort key: (cell, z slab)
+        cell_key[first + k] = cell;
     }
     const unsigned live = __ballot_sync(0xffffffffu, active);
     if(!active) { return; }
@@ -230,33 +233,33 @@ __global__ void __launch_bounds__(256) pb_k_cell_count(PbCellGeom g, int first, 
     cell_slot[first + k] = base + rank_in_group;
 }
 
-__global__ void __launch_bounds__(256) pb_k_cell_fill(int first, int n, const int *__restrict__ particle_cell,
-                                                      const int *__restrict__ cell_slot, const int *__restrict__ cell_start,
+__global__ void __launch_bounds__(256) pb_k_cell_fill(int first, int n, const int *__restrict__ cell_key,
+                                                      const int *__restrict__ cell_slot, const int *__restrict__ sub_start,
                                                       int *__restrict__ cell_list) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k < n) {
         const int i = first + k;
-        cell_list[cell_start[particle_cell[i]] + cell_slot[i]] = i;
+        cell_list[sub_start[cell_key[i]] + cell_slot[i]] = i;
     }
 }
 
-// One thread per cell: insertion sort of the cell's run by (sub-cell Morton key, index) -- a total order, hence
-// deterministic whatever order the atomics delivered.  Runs are short (mean ~18 at liquid density with cells of one
-// cutoff); the 64-bit sort keys live in registers / local memory of the thread.
-__global__ void __launch_bounds__(128) pb_k_cell_sort(int ncells, const int *__restrict__ cell_start, const int *__restrict__ cell_key,
-                                                      int *__restrict__ cell_list) {
+// coarse CSR (one entry per reference cell) out of the slab CSR
+__global__ void __launch_bounds__(256) pb_k_cell_coarse(int ncells, int zsub, const int *__restrict__ sub_start, int *__restrict__ cell_start) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if(c >= ncells) { return; }
-    const int b = cell_start[c], e = cell_start[c + 1];
+    if(c <= ncells) { cell_start[c] = sub_start[(size_t) c * zsub]; }
+}
+
+// One thread per slab: insertion sort of the slab's (tiny) run by index -- a total order, hence deterministic whatever order
+// the atomics delivered.
+__global__ void __launch_bounds__(128) pb_k_cell_sort(int nbins, const int *__restrict__ sub_start, int *__restrict__ cell_list) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if(c >= nbins) { return; }
+    const int b = sub_start[c], e = sub_start[c + 1];
     for(int i = b + 1; i < e; i++) {
         const int v = cell_list[i];
-        const long long kv = ((long long) cell_key[v] << 32) | (unsigned int) v;
         int j = i - 1;
-        while(j >= b) {
-            const int w = cell_list[j];
-            const long long kw = ((long long) cell_key[w] << 32) | (unsigned int) w;
-            if(kw <= kv) { break; }
-            cell_list[j + 1] = w;
+        while(j >= b && cell_list[j] > v) {
+            cell_list[j + 1] = cell_list[j];
             j--;
         }
         cell_list[j + 1] = v;
@@ -277,16 +280,19 @@ static PbCellGeom pb_geom(const pb_ctx *ctx) {
 // Bins particles [first, first+n): particle_cell, cell_start[0..ncells], cell_list[0..n) (absolute indices).
 int pb_bin_particles(pb_ctx *ctx, int first, int n, bool /*write_particle_cell*/) {
     if(!ctx->cells_set) { ctx->set_error("cell lists not set up (pb_setup_cells)"); return -1; }
-    PB_CHECK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(int) * ((size_t) ctx->ncells + 1), ctx->stream));
+    const int S = ctx->zsub_active;
+    const long nbins = (long) ctx->ncells * S;
+    PB_CHECK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(int) * ((size_t) nbins + 1), ctx->stream));
     if(n > 0) {
         PB_LAUNCH(pb_k_cell_count, pb_blocks(n, 256), 256, pb_geom(ctx), first, n, ctx->pos, ctx->flags, ctx->particle_cell,
-                  ctx->cell_count, ctx->cell_slot, ctx->cell_key);
+                  ctx->cell_count, ctx->cell_slot, ctx->cell_key, S);
     }
-    PB_TRY(pb_exclusive_scan(ctx, ctx->cell_count, ctx->cell_start, ctx->ncells));
+    PB_TRY(pb_exclusive_scan(ctx, ctx->cell_count, ctx->sub_start, (int) nbins));
     if(n > 0) {
-        PB_LAUNCH(pb_k_cell_fill, pb_blocks(n, 256), 256, first, n, ctx->particle_cell, ctx->cell_slot, ctx->cell_start, ctx->cell_list);
-        PB_LAUNCH(pb_k_cell_sort, pb_blocks(ctx->ncells, 128), 128, ctx->ncells, ctx->cell_start, ctx->cell_key, ctx->cell_list);
+        PB_LAUNCH(pb_k_cell_fill, pb_blocks(n, 256), 256, first, n, ctx->cell_key, ctx->cell_slot, ctx->sub_start, ctx->cell_list);
+        PB_LAUNCH(pb_k_cell_sort, pb_blocks(nbins, 128), 128, (int) nbins, ctx->sub_start, ctx->cell_list);
     }
+    PB_LAUNCH(pb_k_cell_coarse, pb_blocks(ctx->ncells + 1, 256), 256, ctx->ncells, S, ctx->sub_start, ctx->cell_start);
     return 0;
 }
 

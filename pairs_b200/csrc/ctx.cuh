@@ -76,10 +76,12 @@ struct pb_ctx {
     int ccap = 0;                 // capacity of per-cell arrays
     int *particle_cell = nullptr; // [pcap]
     int *cell_count = nullptr;    // [ccap+1]
-    int *cell_start = nullptr;    // [ccap+1]
+    int *cell_start = nullptr;    // [ncells+1] coarse CSR (one entry per reference cell)
+    int *sub_start = nullptr;     // [ncells*zsub+1] CSR over (cell, z slab)
+    int zsub = 8, zsub_active = 1;   // z slabs per cell (option "cell_zsub"); 1 in DEM mode
     int *cell_slot = nullptr;     // [pcap] slot of the particle inside its cell (arrival order, sorted later)
     int *cell_list = nullptr;     // [pcap]
-    int *cell_key = nullptr;      // [pcap] sub-cell Morton key (ordering inside a cell)
+    int *cell_key = nullptr;      // [pcap] counting-sort key cell*zsub + slab
     int *scan_tmp = nullptr;      // block sums for the scan
     int scan_tmp_cap = 0;
     int cells_n = 0;              // number of particles binned by the last pb_build_cell_lists

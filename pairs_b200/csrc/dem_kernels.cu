@@ -72,6 +72,7 @@ extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) {
     if(contact_capacity < 1 || contact_capacity > 64) { ctx->set_error("pb_dem_enable: 1 <= contact_capacity <= 64"); return -1; }
     ctx->ccontacts = contact_capacity;
     ctx->dem = true;
+    ctx->cells_set = false;       // DEM bins without z slabs: cell arrays are re-sized by the next pb_setup_cells
     PB_CHECK(cudaMalloc(&ctx->d_dem_flag, sizeof(int) * 4));
     PB_CHECK(cudaMemset(ctx->d_dem_flag, 0, sizeof(int) * 4));
     if(ctx->pcap > 0) { PB_TRY(pb_dem_grow(ctx, (size_t) ctx->pcap, (size_t) ctx->pcap, (size_t) ctx->nlocal + ctx->nghost)); }

@@ -8,7 +8,7 @@
 //   interleaved sliced ELLPACK (PbNeighLayout in ctx.cuh: a warp reads 32 consecutive ints per iteration) instead of
 //   AoS [i][k]; inside a list, neighbours are in ascending cell order, ascending index inside a cell (deterministic).
 // The three z-adjacent stencil cells of one (dx,dy) row are consecutive flat indices, so each row is ONE
-// contiguous run of the CSR cell list: 9 runs + cell 0 per particle.
+// contiguous run of the CSR cell list: 9 runs + cell 0 per particle, each run narrowed to the z slabs within reach.
 //
 // HBM bytes per local particle: pos 32 + cell 4 + list write 4*K + count 4; candidates (~27 cells * occupancy)
 // are served from L1/L2 because the 32 lanes of a warp sit in the same 1-3 cells.
@@ -20,13 +20,24 @@ struct PbFaces {
     double lo[3], hi[3];   // subdom_min + margin, subdom_max - margin
 };
 
+struct PbBuildGeom {
+    double lo[3];          // origin of the cell grid (subdom_min - spacing)
+    double spacing, inv_slab;   // cell edge; zsub / spacing
+    int dim1, dim2, zsub, ncells;
+};
+
+// One thread per local particle.  For each of the 9 (dx,dy) rows of the stencil the three z-adjacent cells are ONE contiguous
+// run of the slab CSR; the run is opened only between the z slabs that can hold a neighbour:
+//     |z_j - z_i| <= w,   w = sqrt(cutoff^2 - d_xy^2),   d_xy = distance in the xy-plane from i to the row's cell column
+// (rows with d_xy >= cutoff are skipped altogether).  The window is widened by a relative 1e-9 and rounded outwards to whole
+// slabs, so it is conservative; membership is still decided by the exact reference test below.
 template<bool STORE>
-__global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncells, int dim1, int dim2, int ncap, PbNeighLayout lay,
-                                                            double cutsq, const double4 *__restrict__ pos,
-                                                            const int *__restrict__ flags, const int *__restrict__ particle_cell,
-                                                            const int *__restrict__ cell_start, const int *__restrict__ cell_list,
-                                                            int *__restrict__ neigh, int *__restrict__ numneigh,
-                                                            int *__restrict__ max_count, PbFaces faces, int *__restrict__ group_flag) {
+__global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncap, PbNeighLayout lay, PbBuildGeom g, double cutsq,
+                                                            const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                            const int *__restrict__ particle_cell, const int *__restrict__ sub_start,
+                                                            const int *__restrict__ cell_list, int *__restrict__ neigh,
+                                                            int *__restrict__ numneigh, int *__restrict__ max_count, PbFaces faces,
+                                                            int *__restrict__ group_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     int count = 0;
     int boundary = 0;     // has a ghost neighbour, or is itself a halo source (within `margin` of a sub-box face)
@@ -38,19 +49,38 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncel
         // list slot of neighbour k: base + (k / G) * 32 + k % G  (PbNeighLayout::idx with the per-particle part hoisted)
         int *const out = neigh + ((size_t) (i / lay.A) * lay.T * 32 + (size_t) ((i % lay.A) * lay.G));
         const int G = lay.G;
-        // run 0: cell 0; runs 1..9: rows (dx,dy) in stencil order, each covering dz = -1,0,+1
-        for(int run = 0; run < 10; run++) {
-            int c_lo, c_hi;   // inclusive cell range of this run
-            if(run == 0) {
-                c_lo = 0; c_hi = 0;
+        // cell coordinates of i (pc = (c0*dim1 + c1)*dim2 + c2 + 1) and its offsets inside the cell
+        const int flat = pc - 1;
+        const int c2 = flat % g.dim2, c1 = (flat / g.dim2) % g.dim1, c0 = flat / (g.dim2 * g.dim1);
+        const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing);   // in [0, spacing)
+        const double zrel = pi.z - g.lo[2];
+        const double slack = 1e-9 * g.spacing;
+        const int zslabs = g.dim2 * g.zsub;
+        // (an INFINITE local particle -- cell 0 -- would get the stencil around flat index 0 in the reference, a handful of
+        // cells at the grid origin; such particles are FIXED in practice and skipped above; here they see cell 0 only)
+        const int nruns = (pc == 0) ? 1 : 10;
+        for(int run = 0; run < nruns; run++) {
+            int b, e;
+            if(run == 0) {                      // cell 0: INFINITE particles (sim/interaction.py:93-95, disp = -1)
+                b = sub_start[0]; e = sub_start[g.zsub];
             } else {
                 const int r = run - 1;
-                const int mid = pc + ((r / 3 - 1) * dim1 + (r % 3 - 1)) * dim2;
-                c_lo = max(mid - 1, 1);
-                c_hi = min(mid + 1, ncells - 1);
-                if(c_lo > c_hi) { continue; }
+                const int dx = r / 3 - 1, dy = r % 3 - 1;
+                const double ddx = (dx == 0) ? 0.0 : ((dx < 0) ? fx : g.spacing - fx);
+                const double ddy = (dy == 0) ? 0.0 : ((dy < 0) ? fy : g.spacing - fy);
+                const double wsq = cutsq - (ddx * ddx + ddy * ddy);
+                if(wsq <= 0.0) { continue; }
+                const double w = sqrt(wsq) + slack;
+                // flat index of the row's cell at z-index 0, +1 for the reserved cell 0; the reference tests only
+                // 0 < cell < ncells on the flat index, which for a local particle (never in the outermost cell layer) always holds
+                const long col = ((long) (c0 + dx) * g.dim1 + (c1 + dy)) * g.dim2 + 1;
+                int gz_lo = (int) floor((zrel - w) * g.inv_slab), gz_hi = (int) floor((zrel + w) * g.inv_slab);
+                gz_lo = max(gz_lo, max((c2 - 1) * g.zsub, 0));
+                gz_hi = min(gz_hi, min((c2 + 1) * g.zsub + g.zsub - 1, zslabs - 1));
+                const long s_lo = col * g.zsub + gz_lo, s_hi = col * g.zsub + gz_hi;
+                if(gz_lo > gz_hi || s_lo < g.zsub || s_hi >= (long) g.ncells * g.zsub) { continue; }
+                b = sub_start[s_lo]; e = sub_start[s_hi + 1];
             }
-            const int b = cell_start[c_lo], e = cell_start[c_hi + 1];
             for(int k = b; k < e; k++) {
                 const int j = __ldg(cell_list + k);
                 const double4 pj = pb_ld_pos(pos + j);
@@ -147,14 +177,22 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
         faces.lo[d] = ctx->subdom[d * 2] + ctx->spacing;
         faces.hi[d] = ctx->subdom[d * 2 + 1] - ctx->spacing;
     }
-    ctx->groups_valid = false;   // neighbor_capacity default of pairs.simulation() (src/pairs/__init__.py:16)
+    ctx->groups_valid = false;
+    if(cutoff > ctx->spacing * (1.0 + 1e-12)) { ctx->set_error("pb_build_neighbor_lists: cutoff exceeds the cell spacing"); return -1; }
+    PbBuildGeom bg;
+    for(int d = 0; d < 3; d++) { bg.lo[d] = ctx->subdom[d * 2] - ctx->spacing; }
+    bg.spacing = ctx->spacing;
+    bg.inv_slab = (double) ctx->zsub_active / ctx->spacing;
+    bg.dim1 = ctx->dim_cells[1];
+    bg.dim2 = ctx->dim_cells[2];
+    bg.zsub = ctx->zsub_active;
+    bg.ncells = ctx->ncells;   // neighbor_capacity default of pairs.simulation() (src/pairs/__init__.py:16)
     for(int attempt = 0; attempt < 8; attempt++) {
         PB_TRY(pb_alloc_neigh(ctx, n));
         ctx->nslots = pb_layout(ctx).T;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
-        PB_LAUNCH(pb_k_build_neighbors<true>, pb_blocks(n, 128), 128, n, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], ctx->ncap,
-                  pb_layout(ctx), cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->neigh, ctx->numneigh,
-                  ctx->d_scalars, faces, ctx->group_flag);
+        PB_LAUNCH(pb_k_build_neighbors<true>, pb_blocks(n, 128), 128, n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags,
+                  ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh, ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag);
         PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->max_neigh = ctx->h_scalars[0];

@@ -359,3 +359,37 @@ def test_legacy_lj_onetype_kernels(capsys):
     assert "generating the same FCC system synthetically (864 atoms)" in out and "Number of local particles: 864 / 864" in out
     t, _ = c.compute_thermo()
     assert 0.5 < t < 1.5          # explicit Euler, 21 steps from T = 1.44
+
+
+def test_energy_and_virial_reductions():
+    """Potential energy and virial (warp-shuffle reductions; an addition, the reference computes neither) against a brute-force
+    minimum-image evaluation in numpy, and energy conservation of the velocity-Verlet loop."""
+    nx = 5
+    ctx, n = make_gpu(nx)
+    L = box(nx)[1]
+    rng = np.random.default_rng(3)
+    x = ctx.real("position") + 0.05 * (rng.random((n, 3)) - 0.5)
+    ctx.upload(x, ctx.real("linear_velocity"), ctx.real("mass"), ctx.ints("type"))
+    _reneighbor_gpu(ctx)
+    e, w = ctx.lj_energy_virial(CUT)
+    xs = ctx.real("position")
+    d = xs[:, None, :] - xs[None, :, :]
+    d -= L * np.round(d / L)
+    r2 = (d * d).sum(-1)
+    iu = np.triu_indices(n, 1)
+    r2 = r2[iu]
+    r2 = r2[r2 < CUT * CUT]
+    sr6 = 1.0 / r2 ** 3
+    e_ref = float((4.0 * (sr6 * sr6 - sr6)).sum())
+    w_ref = float((48.0 * sr6 * (sr6 - 0.5)).sum())
+    assert abs(e - e_ref) <= 1e-11 * abs(e_ref) and abs(w - w_ref) <= 1e-11 * abs(w_ref)
+    # total energy E_kin + E_pot over 200 velocity-Verlet steps (truncated LJ: small cutoff jumps only)
+    def total():
+        t, _ = ctx.compute_thermo()
+        ep, _ = ctx.lj_energy_virial(CUT)
+        return 0.5 * t * (3 * n - 3) + ep
+    ctx.md_run(0, 1, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)
+    e0 = total()
+    ctx.md_run(1, 201, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)
+    ctx.exchange(); ctx.borders(); ctx.build_cell_lists(); ctx.build_neighbor_lists(CUT + SKIN)
+    assert abs(total() - e0) <= 2e-3 * abs(e0)
