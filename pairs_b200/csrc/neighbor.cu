@@ -31,14 +31,20 @@ struct PbBuildGeom {
 //     |z_j - z_i| <= w,   w = sqrt(cutoff^2 - d_xy^2),   d_xy = distance in the xy-plane from i to the row's cell column
 // (rows with d_xy >= cutoff are skipped altogether).  The window is widened by a relative 1e-9 and rounded outwards to whole
 // slabs, so it is conservative; membership is still decided by the exact reference test below.
-template<bool STORE>
+// STAGE: each warp collects its 32 lists in shared memory ([k][lane], conflict-free) and writes them out afterwards row by
+// row, 128 contiguous bytes per row -- instead of ~75 scattered 4-byte stores per particle whose 32-byte sectors are completed
+// by eight different store instructions (ncu: 2.2 GB of DRAM writes for 1.25 GB of lists without staging).
+template<bool STAGE>
 __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncap, PbNeighLayout lay, PbBuildGeom g, double cutsq,
                                                             const double4 *__restrict__ pos, const int *__restrict__ flags,
                                                             const int *__restrict__ particle_cell, const int *__restrict__ sub_start,
                                                             const int *__restrict__ cell_list, int *__restrict__ neigh,
                                                             int *__restrict__ numneigh, int *__restrict__ max_count, PbFaces faces,
                                                             int *__restrict__ group_flag) {
+    extern __shared__ int s_stage[];                       // [warps per block][ncap][32]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int *const s_mine = s_stage + (size_t) (threadIdx.x >> 5) * ncap * 32 + lane;
     int count = 0;
     int boundary = 0;     // has a ghost neighbour, or is itself a halo source (within `margin` of a sub-box face)
     if(i < nlocal && (flags[i] & PB_FLAG_FIXED) == 0) {
@@ -89,14 +95,27 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncap
                 const double dz = __dsub_rn(pi.z, pj.z);
                 const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                 if(rsq < cutsq && j != i) {
-                    if(STORE && count < ncap) {
-                        if(G == 1) { out[(size_t) count * 32] = j; }
+                    if(count < ncap) {
+                        if(STAGE) { s_mine[count * 32] = j; }
+                        else if(G == 1) { out[(size_t) count * 32] = j; }
                         else { out[(size_t) (count / G) * 32 + (count % G)] = j; }
                     }
                     count++;
                     boundary |= (j >= nlocal);
                 }
             }
+        }
+    }
+    if(STAGE) {
+        // flush (all 32 lanes take part): row k of the warp's slice is 32 consecutive ints in global memory (G == 1 layout)
+        __syncwarp();
+        const int mine = min(count, ncap);
+        int rows = mine;
+#pragma unroll
+        for(int o = 16; o > 0; o >>= 1) { rows = max(rows, __shfl_xor_sync(0xffffffffu, rows, o)); }
+        int *const dst = neigh + ((size_t) (i >> 5) * lay.T * 32 + (size_t) lane);
+        for(int k = 0; k < rows; k++) {
+            if(k < mine) { dst[(size_t) k * 32] = s_mine[k * 32]; }
         }
     }
     if(i < nlocal) { numneigh[i] = count; }
@@ -191,8 +210,18 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
         PB_TRY(pb_alloc_neigh(ctx, n));
         ctx->nslots = pb_layout(ctx).T;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
-        PB_LAUNCH(pb_k_build_neighbors<true>, pb_blocks(n, 128), 128, n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags,
-                  ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh, ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag);
+        const size_t stage_bytes = (size_t) 4 * ctx->ncap * 32 * sizeof(int);      // 4 warps per block
+        if(ctx->lanes == 1 && stage_bytes <= 96 * 1024) {
+            PB_CHECK(cudaFuncSetAttribute(pb_k_build_neighbors<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stage_bytes));
+            pb_k_build_neighbors<true><<<pb_blocks(n, 128), 128, stage_bytes, ctx->stream>>>(
+                n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh,
+                ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag);
+            ctx->launches++;
+            PB_CHECK(cudaGetLastError());
+        } else {
+            PB_LAUNCH(pb_k_build_neighbors<false>, pb_blocks(n, 128), 128, n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags,
+                      ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh, ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag);
+        }
         PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->max_neigh = ctx->h_scalars[0];
