@@ -211,7 +211,7 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
         ctx->nslots = pb_layout(ctx).T;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
         const size_t stage_bytes = (size_t) 4 * ctx->ncap * 32 * sizeof(int);      // 4 warps per block
-        if(ctx->lanes == 1 && stage_bytes <= 96 * 1024) {
+        if(ctx->stage_lists && ctx->lanes == 1 && stage_bytes <= 96 * 1024) {
             PB_CHECK(cudaFuncSetAttribute(pb_k_build_neighbors<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stage_bytes));
             pb_k_build_neighbors<true><<<pb_blocks(n, 128), 128, stage_bytes, ctx->stream>>>(
                 n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh,
