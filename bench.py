@@ -47,7 +47,7 @@ def workload_config(n_gpus, nx):
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons streamed every 50 ms (one long-lived nvidia-smi -lms process) during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -56,17 +56,28 @@ class ClockSampler(threading.Thread):
         self.index = index
         self.rows = []
         self.stop_flag = threading.Event()
+        self.proc = None
+        self.recording = False
 
     def run(self):
-        while not self.stop_flag.is_set():
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag.is_set():
+                    break
+                if self.recording and line.strip():
+                    self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.proc.terminate()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -197,6 +208,13 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.4)           # let nvidia-smi come up before the timed region
+        run(W, W + 2)             # (two extra untimed iterations keep the GPU busy while it does)
+        W += 2
+        sampler.recording = True
+    elif world > 1:
+        run(W, W + 2)
+        W += 2
     ctx.timers_reset()
     ctx.timers_enable(True)
     launches0 = ctx.kernel_launches()
@@ -210,7 +228,8 @@ def run_ours(args):
     ctx.timers_enable(False)
     launches = ctx.kernel_launches() - launches0
     if rank == 0:
-        sampler.stop_flag.set()
+        sampler.recording = False
+        sampler.stop()
         sampler.join(timeout=3)
     if dist is not None:
         import torch
@@ -278,7 +297,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(world, nx), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
+                "warmup": args.warmup, "config": workload_config(world, nx), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms": stages, "atoms_global": n_global,
                 "nlocal_rank0": nl, "nghost_rank0": ng, "wall_s_timed_region": t_wall, "setup_s": t_setup,
                 "thermo_last": [float(x) for x in thermo[-1]] if len(thermo) else None}
@@ -297,7 +316,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=100, help="FCC cells per GPU and dimension (100 -> 4M atoms: BASELINE configs[1])")
