@@ -158,7 +158,7 @@ int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const d
     if(total_recv > ctx->recv_cap) {
         if(ctx->recv_buf != nullptr) { PB_CHECK(cudaFree(ctx->recv_buf)); }
         ctx->recv_cap = std::max(total_recv + total_recv / 4, 1024);
-        PB_CHECK(cudaMalloc(&ctx->recv_buf, sizeof(double) * (size_t) ctx->recv_cap * PB_MAX_ELEMS));
+        PB_CHECK(cudaMalloc(&ctx->recv_buf, sizeof(double) * (size_t) ctx->recv_cap * pb_record_elems(ctx)));
     }
     bool grouped = false;
     for(int d = dim_begin; d < dim_end; d++) {

@@ -160,7 +160,7 @@ int pb_ensure_send_capacity(pb_ctx *ctx, int needed) {
     newcap = (newcap + 255) / 256 * 256;
     PB_TRY(pb_regrow(ctx, &ctx->send_map, (size_t) ctx->nsend_all, newcap, true));
     PB_TRY(pb_regrow(ctx, &ctx->send_mult, (size_t) ctx->nsend_all * 3, newcap * 3, true));
-    PB_TRY(pb_regrow(ctx, &ctx->send_buf, 0, newcap * PB_MAX_ELEMS, false));
+    PB_TRY(pb_regrow(ctx, &ctx->send_buf, 0, newcap * pb_record_elems(ctx), false));
     ctx->send_cap = (int) newcap;
     return 0;
 }

@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <map>
 #include <string>
@@ -161,7 +162,9 @@ struct pb_ctx {
     void set_error(const std::string &e) { err = e; }
 };
 
-static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record (exchange: 12, borders: 11, sync: 6)
+static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record in MD (exchange: 12, borders: 11/15, sync: 6)
+// DEM exchange record: 12 base + radius 1 + angvel 3 + normal 3 + inv_inertia 9 + rotmat 9 + quat 4 + num_contacts 1 + 6 per slot
+static inline int pb_record_elems(const pb_ctx *ctx) { return ctx->dem ? std::max(PB_MAX_ELEMS, 42 + 6 * ctx->ccontacts) : PB_MAX_ELEMS; }
 static const int PB_NSCALARS = 16;
 
 // ---- helpers shared by the .cu files ----

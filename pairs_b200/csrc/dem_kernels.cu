@@ -12,8 +12,10 @@
 // pair forces are summed follow OUR cell-list order, not the reference's: contact history is compared as per-uid sets,
 // forces to 1e-12.
 //
-// Round 1 scope: single GPU (periodic images through pb_exchange / pb_borders), particles are NOT physically re-sorted
-// (contact rows stay with their particle index); multi-GPU migration of contact history is not implemented yet.
+// Particles are NOT physically re-sorted in DEM (contact rows stay with their particle index).  Between GPUs a migrating
+// particle takes its whole state along -- DEM properties and the contact table -- in one fixed-size record (migrate.cu);
+// unlike the reference (whose pack_contact_history runs after the leaver's slot was overwritten)
+// the history that arrives is the particle's own.
 #include <algorithm>
 #include <cstring>
 #include <random>
@@ -72,6 +74,12 @@ extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) {
     if(contact_capacity < 1 || contact_capacity > 64) { ctx->set_error("pb_dem_enable: 1 <= contact_capacity <= 64"); return -1; }
     ctx->ccontacts = contact_capacity;
     ctx->dem = true;
+    if(ctx->send_cap > 0) {        // wire records grow (contact history travels with migrating particles): re-size the buffers
+        const int keep = ctx->send_cap;
+        ctx->send_cap = 0;
+        PB_TRY(pb_ensure_send_capacity(ctx, keep));
+    }
+    if(ctx->recv_buf != nullptr) { PB_CHECK(cudaFree(ctx->recv_buf)); ctx->recv_buf = nullptr; ctx->recv_cap = 0; }
     ctx->cells_set = false;       // DEM bins without z slabs: cell arrays are re-sized by the next pb_setup_cells
     PB_CHECK(cudaMalloc(&ctx->d_dem_flag, sizeof(int) * 4));
     PB_CHECK(cudaMemset(ctx->d_dem_flag, 0, sizeof(int) * 4));
@@ -329,6 +337,115 @@ extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, 
     PB_CHECK(cudaMemcpy(tsd, d_tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyDeviceToHost));
     PB_CHECK(cudaMemcpy(ivm, d_ivm, sizeof(double) * (size_t) n * C, cudaMemcpyDeviceToHost));
     cudaFree(d_num); cudaFree(d_uid); cudaFree(d_us); cudaFree(d_st); cudaFree(d_tsd); cudaFree(d_ivm);
+    return 0;
+}
+
+// ---- migration support (called from migrate.cu) -------------------------------------------------------------------------
+// DEM part of an exchange record, appended after the 12 base elements: radius, angvel[3], normal[3], inv_inertia[9],
+// rotmat[9], quat[4], num_contacts, then per slot: uid, sticking, tsd[3], ivm.
+struct PbDemArrays {
+    double *radius, *angvel, *normal, *inv_inertia, *rotmat, *quat, *c_tsd, *c_ivm;
+    int *num_contacts, *c_uid, *c_used, *c_stick;
+    int cap, C;
+};
+
+static PbDemArrays pb_dem_arrays(const pb_ctx *ctx) {
+    PbDemArrays a;
+    a.radius = ctx->radius; a.angvel = ctx->angvel; a.normal = ctx->normal; a.inv_inertia = ctx->inv_inertia; a.rotmat = ctx->rotmat;
+    a.quat = ctx->quat; a.c_tsd = ctx->contact_tsd; a.c_ivm = ctx->contact_ivm; a.num_contacts = ctx->num_contacts;
+    a.c_uid = ctx->contact_uid; a.c_used = ctx->contact_used; a.c_stick = ctx->contact_stick; a.cap = ctx->pcap; a.C = ctx->ccontacts;
+    return a;
+}
+
+__device__ __forceinline__ void pb_dem_pack_one(const PbDemArrays &a, int p, double *b) {
+    const size_t cap = a.cap;
+    int k = 0;
+    b[k++] = a.radius[p];
+    for(int d = 0; d < 3; d++) { b[k++] = a.angvel[d * cap + p]; }
+    for(int d = 0; d < 3; d++) { b[k++] = a.normal[d * cap + p]; }
+    for(int d = 0; d < 9; d++) { b[k++] = a.inv_inertia[d * cap + p]; }
+    for(int d = 0; d < 9; d++) { b[k++] = a.rotmat[d * cap + p]; }
+    for(int d = 0; d < 4; d++) { b[k++] = a.quat[d * cap + p]; }
+    const int nc = a.num_contacts[p];
+    b[k++] = (double) nc;
+    for(int c = 0; c < a.C; c++) {
+        const bool live = c < nc;
+        b[k++] = live ? (double) a.c_uid[c * cap + p] : 0.0;
+        b[k++] = live ? (double) a.c_stick[c * cap + p] : 0.0;
+        for(int d = 0; d < 3; d++) { b[k++] = live ? a.c_tsd[((size_t) d * a.C + c) * cap + p] : 0.0; }
+        b[k++] = live ? a.c_ivm[c * cap + p] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void pb_dem_unpack_one(const PbDemArrays &a, int p, const double *b) {
+    const size_t cap = a.cap;
+    int k = 0;
+    a.radius[p] = b[k++];
+    for(int d = 0; d < 3; d++) { a.angvel[d * cap + p] = b[k++]; }
+    for(int d = 0; d < 3; d++) { a.normal[d * cap + p] = b[k++]; }
+    for(int d = 0; d < 9; d++) { a.inv_inertia[d * cap + p] = b[k++]; }
+    for(int d = 0; d < 9; d++) { a.rotmat[d * cap + p] = b[k++]; }
+    for(int d = 0; d < 4; d++) { a.quat[d * cap + p] = b[k++]; }
+    const int nc = (int) b[k++];
+    a.num_contacts[p] = nc;
+    for(int c = 0; c < a.C; c++) {
+        a.c_uid[c * cap + p] = (int) b[k++];
+        a.c_stick[c * cap + p] = (int) b[k++];
+        for(int d = 0; d < 3; d++) { a.c_tsd[((size_t) d * a.C + c) * cap + p] = b[k++]; }
+        a.c_ivm[c * cap + p] = b[k++];
+        a.c_used[c * cap + p] = (c < nc) ? 1 : 0;      // as the reference's unpack marks transferred contacts used
+    }
+}
+
+// records of the leavers: e = record index (same mapping as the base pack kernel of migrate.cu)
+__global__ void __launch_bounds__(128) pb_k_dem_pack_exchange(int n, int stride, int base_hi, const int *__restrict__ sel_lo,
+                                                              const int *__restrict__ scan_lo, const int *__restrict__ sel_hi,
+                                                              const int *__restrict__ scan_hi, PbDemArrays a, double *__restrict__ buf) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    int e;
+    if(sel_lo[i]) { e = scan_lo[i]; } else if(sel_hi[i]) { e = base_hi + scan_hi[i]; } else { return; }
+    pb_dem_pack_one(a, i, buf + (size_t) e * stride + 12);
+}
+
+__global__ void __launch_bounds__(128) pb_k_dem_unpack_exchange(int count, int dst0, int stride, PbDemArrays a, const double *__restrict__ buf) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    pb_dem_unpack_one(a, dst0 + k, buf + (size_t) k * stride + 12);
+}
+
+// hole filling: particle `src` (a stayer from the tail) moves into slot `dst` (a leaver's slot below the new nlocal)
+__global__ void __launch_bounds__(128) pb_k_dem_move(int count, const int *__restrict__ src_idx, const int *__restrict__ dst_idx, PbDemArrays a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    const int s = src_idx[k], t = dst_idx[k];
+    const size_t cap = a.cap;
+    a.radius[t] = a.radius[s];
+    for(int d = 0; d < 3; d++) { a.angvel[d * cap + t] = a.angvel[d * cap + s]; a.normal[d * cap + t] = a.normal[d * cap + s]; }
+    for(int d = 0; d < 9; d++) { a.inv_inertia[d * cap + t] = a.inv_inertia[d * cap + s]; a.rotmat[d * cap + t] = a.rotmat[d * cap + s]; }
+    for(int d = 0; d < 4; d++) { a.quat[d * cap + t] = a.quat[d * cap + s]; }
+    a.num_contacts[t] = a.num_contacts[s];
+    for(int c = 0; c < a.C; c++) {
+        a.c_uid[c * cap + t] = a.c_uid[c * cap + s];
+        a.c_used[c * cap + t] = a.c_used[c * cap + s];
+        a.c_stick[c * cap + t] = a.c_stick[c * cap + s];
+        a.c_ivm[c * cap + t] = a.c_ivm[c * cap + s];
+        for(int d = 0; d < 3; d++) { a.c_tsd[((size_t) d * a.C + c) * cap + t] = a.c_tsd[((size_t) d * a.C + c) * cap + s]; }
+    }
+}
+
+int pb_dem_pack_exchange(pb_ctx *ctx, int n, int stride, int base_hi, const int *sel_lo, const int *scan_lo, const int *sel_hi, const int *scan_hi) {
+    PB_LAUNCH(pb_k_dem_pack_exchange, pb_blocks(n, 128), 128, n, stride, base_hi, sel_lo, scan_lo, sel_hi, scan_hi, pb_dem_arrays(ctx), ctx->send_buf);
+    return 0;
+}
+
+int pb_dem_unpack_exchange(pb_ctx *ctx, int count, int dst0, int stride, const double *src) {
+    PB_LAUNCH(pb_k_dem_unpack_exchange, pb_blocks(count, 128), 128, count, dst0, stride, pb_dem_arrays(ctx), src);
+    return 0;
+}
+
+int pb_dem_move(pb_ctx *ctx, int count, const int *src_idx, const int *dst_idx) {
+    PB_LAUNCH(pb_k_dem_move, pb_blocks(count, 128), 128, count, src_idx, dst_idx, pb_dem_arrays(ctx));
     return 0;
 }
 
@@ -648,7 +765,6 @@ extern "C" int pb_dem_euler(pb_ctx *ctx) {
 extern "C" int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts_end) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(!ctx->dem) { ctx->set_error("DEM not enabled"); return -1; }
-    if(ctx->world > 1) { ctx->set_error("pb_dem_run: multi-GPU DEM (contact-history migration) is not implemented yet"); return -1; }
     if(!ctx->cells_set || ctx->spacing != cell_spacing) { PB_TRY(pb_setup_cells(ctx, cell_spacing)); }
     for(int ts = ts_begin; ts < ts_end; ts++) {
         PB_TRY(pb_exchange(ctx));

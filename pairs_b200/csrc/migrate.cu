@@ -10,7 +10,11 @@
 int pb_transport_sizes(pb_ctx *ctx, int dim);
 int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const double **recv_src);
 
-static const int EXCH_ELEMS = 12;
+static const int EXCH_ELEMS = 12;      // base record; DEM appends its properties and the contact table (dem_kernels.cu)
+
+int pb_dem_pack_exchange(pb_ctx *ctx, int n, int stride, int base_hi, const int *sel_lo, const int *scan_lo, const int *sel_hi, const int *scan_hi);
+int pb_dem_unpack_exchange(pb_ctx *ctx, int count, int dst0, int stride, const double *src);
+int pb_dem_move(pb_ctx *ctx, int count, const int *src_idx, const int *dst_idx);
 
 struct PbBox3 {
     double len[3];
@@ -33,7 +37,7 @@ __global__ void __launch_bounds__(256) pb_k_sel_leave(int n, int dim, double lo,
     stay[i] = !(a || b);
 }
 
-__global__ void __launch_bounds__(256) pb_k_pack_exchange(int n, int cap, int dim, int mult_lo, int mult_hi, int base_hi, double len,
+__global__ void __launch_bounds__(256) pb_k_pack_exchange(int n, int cap, int stride, int dim, int mult_lo, int mult_hi, int base_hi, double len,
                                                           const int *__restrict__ sel_lo, const int *__restrict__ scan_lo,
                                                           const int *__restrict__ sel_hi, const int *__restrict__ scan_hi,
                                                           const double4 *__restrict__ pos, const double *__restrict__ vel,
@@ -48,7 +52,7 @@ __global__ void __launch_bounds__(256) pb_k_pack_exchange(int n, int cap, int di
     else { return; }
     const double4 x = pos[i];
     const double sh = __dmul_rn((double) mult, len);
-    double *b = buf + (size_t) e * EXCH_ELEMS;
+    double *b = buf + (size_t) e * stride;
     b[0] = (double) uid[i];
     b[1] = (double) shape[i];
     b[2] = (double) flags[i];
@@ -87,13 +91,13 @@ __global__ void __launch_bounds__(256) pb_k_compact(int n, int cap, const int *_
     tag_o[k] = tag[i];
 }
 
-__global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0, int cap, const double *__restrict__ buf,
+__global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0, int cap, int stride, const double *__restrict__ buf,
                                                             double4 *__restrict__ pos, double *__restrict__ vel,
                                                             double *__restrict__ mass, int *__restrict__ type, int *__restrict__ flags,
                                                             int *__restrict__ uid, int *__restrict__ shape, int *__restrict__ tag) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= count) { return; }
-    const double *b = buf + (size_t) k * EXCH_ELEMS;
+    const double *b = buf + (size_t) k * stride;
     const int p = dst0 + k;
     const int t = (int) b[10];
     uid[p] = (int) b[0];
@@ -106,6 +110,34 @@ __global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0,
     vel[2 * cap + p] = b[9];
     type[p] = t;
     tag[p] = (int) b[11];
+}
+
+// ---- hole filling (DEM mode: per-particle state is large, leavers are few) ------------------------------------------------
+// new_n = n - L.  Holes = leavers below new_n, fillers = stayers at or above new_n; both in ascending order, k-th filler -> k-th
+// hole (deterministic).  rank_leave = scan_lo + scan_hi is the number of leavers before an index.
+__global__ void __launch_bounds__(256) pb_k_hole_list(int n, int new_n, const int *__restrict__ stay, const int *__restrict__ scan_lo,
+                                                      const int *__restrict__ scan_hi, int *__restrict__ hole_idx, int *__restrict__ fill_idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    const int before = scan_lo[i] + scan_hi[i];
+    if(i < new_n) {
+        if(!stay[i]) { hole_idx[before] = i; }
+    } else if(stay[i]) {
+        const int before_tail = scan_lo[new_n] + scan_hi[new_n];
+        fill_idx[(i - new_n) - (before - before_tail)] = i;
+    }
+}
+
+__global__ void __launch_bounds__(256) pb_k_move_base(int count, int cap, const int *__restrict__ src_idx, const int *__restrict__ dst_idx,
+                                                      double4 *__restrict__ pos, double *__restrict__ vel, double *__restrict__ mass,
+                                                      int *__restrict__ type, int *__restrict__ flags, int *__restrict__ uid,
+                                                      int *__restrict__ shape, int *__restrict__ tag) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= count) { return; }
+    const int s = src_idx[k], t = dst_idx[k];
+    pos[t] = pos[s];
+    vel[t] = vel[s]; vel[cap + t] = vel[cap + s]; vel[2 * cap + t] = vel[2 * cap + s];
+    mass[t] = mass[s]; type[t] = type[s]; flags[t] = flags[s]; uid[t] = uid[s]; shape[t] = shape[s]; tag[t] = tag[s];
 }
 
 int pb_exchange_multi(pb_ctx *ctx, int dim) {
@@ -140,17 +172,30 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
     ctx->send_offsets[j0] = 0;
     ctx->send_offsets[j1] = c_lo;
     PB_TRY(pb_ensure_send_capacity(ctx, c_lo + c_hi));
+    const int stride = ctx->dem ? pb_record_elems(ctx) : EXCH_ELEMS;
     if(c_lo + c_hi > 0) {
         const double len = ctx->grid[dim * 2 + 1] - ctx->grid[dim * 2];
-        PB_LAUNCH(pb_k_pack_exchange, pb_blocks(n, 256), 256, n, ctx->pcap, dim, ctx->pbc[j0], ctx->pbc[j1], c_lo, len, sel_lo, scan_lo,
+        PB_LAUNCH(pb_k_pack_exchange, pb_blocks(n, 256), 256, n, ctx->pcap, stride, dim, ctx->pbc[j0], ctx->pbc[j1], c_lo, len, sel_lo, scan_lo,
                   sel_hi, scan_hi, ctx->pos, ctx->vel, ctx->mass, ctx->flags, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf);
+        if(ctx->dem) { PB_TRY(pb_dem_pack_exchange(ctx, n, stride, c_lo, sel_lo, scan_lo, sel_hi, scan_hi)); }
     }
     PB_TRY(pb_transport_sizes(ctx, dim));
     ctx->recv_offsets[j0] = 0;
     ctx->recv_offsets[j1] = ctx->nrecv[j0];
     const int nr = ctx->nrecv[j0] + ctx->nrecv[j1];
-    PB_TRY(pb_ensure_particle_capacity(ctx, c_stay + nr));
-    if(n > 0 && c_stay < n) {
+    if(ctx->dem && n > 0 && c_stay < n) {
+        // hole filling: k-th stayer of the tail [c_stay, n) moves into the k-th leaver slot below c_stay
+        int *hole_idx = ctx->cell_key, *fill_idx = ctx->particle_cell;          // [pcap] scratch, free during exchange
+        PB_LAUNCH(pb_k_hole_list, pb_blocks(n, 256), 256, n, c_stay, stay, scan_lo, scan_hi, hole_idx, fill_idx);
+        PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 3, scan_stay + c_stay, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        const int nholes = c_stay - ctx->h_scalars[3];      // leavers below c_stay = c_stay - stayers below c_stay
+        if(nholes > 0) {
+            PB_LAUNCH(pb_k_move_base, pb_blocks(nholes, 256), 256, nholes, ctx->pcap, fill_idx, hole_idx, ctx->pos, ctx->vel, ctx->mass, ctx->type,
+                      ctx->flags, ctx->uid, ctx->shape, ctx->tag);
+            PB_TRY(pb_dem_move(ctx, nholes, fill_idx, hole_idx));
+        }
+    } else if(n > 0 && c_stay < n) {
         PB_LAUNCH(pb_k_compact, pb_blocks(n, 256), 256, n, ctx->pcap, stay, scan_stay, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
                   ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape,
                   ctx->shape_alt, ctx->tag, ctx->tag_alt);
@@ -163,11 +208,15 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
         std::swap(ctx->shape, ctx->shape_alt);
         std::swap(ctx->tag, ctx->tag_alt);
     }
+    // grow only now: the selection / scan scratch above is re-allocated (not kept) by a capacity change
+    ctx->nlocal = c_stay;
+    PB_TRY(pb_ensure_particle_capacity(ctx, c_stay + nr));
     const double *src = nullptr;
-    PB_TRY(pb_transport_data(ctx, dim, dim + 1, EXCH_ELEMS, &src));
+    PB_TRY(pb_transport_data(ctx, dim, dim + 1, stride, &src));
     if(nr > 0) {
-        PB_LAUNCH(pb_k_unpack_exchange, pb_blocks(nr, 256), 256, nr, c_stay, ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type,
+        PB_LAUNCH(pb_k_unpack_exchange, pb_blocks(nr, 256), 256, nr, c_stay, ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type,
                   ctx->flags, ctx->uid, ctx->shape, ctx->tag);
+        if(ctx->dem) { PB_TRY(pb_dem_unpack_exchange(ctx, nr, c_stay, stride, src)); }
     }
     ctx->nlocal = c_stay + nr;
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }

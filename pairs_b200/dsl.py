@@ -468,8 +468,6 @@ class Simulation:
                 or self.neighbor_cutoff is not None or self.reneighbor_frequency != 1:
             raise DslError("DEM: only the procedure list of examples/dem.py (gravity, linear_spring_dashpot, euler over cell lists, "
                            "contact history, reneighbouring every step) is implemented")
-        if world > 1:
-            raise DslError("DEM on several GPUs (contact-history migration) is not implemented yet")
         grav, lsd, eul = self.functions
         nk = 1
         fs_name, fd_name = lsd["roles"]["friction_static"], lsd["roles"]["friction_dynamic"]
@@ -495,7 +493,7 @@ class Simulation:
                 if rank == 0:
                     self._dem_banner(args, len(g["uid"]))
             elif kind == "read_particle_data":
-                parts.append(self._read_csv(*args))
+                parts.append(self._keep_own(ctx, self._read_csv(*args)))
             else:
                 raise DslError(f"DEM: unsupported set-up statement {kind}")
         n = sum(len(p["position"]) for p in parts)
@@ -524,6 +522,23 @@ class Simulation:
         all_ms = (time.perf_counter() - t0) * 1e3
         self._print_summary(ctx, all_ms, rank)
         return ctx
+
+    _FLAGS_KEEP = 1 | 4 | 8      # infinite | fixed | global (runtime/pairs_common.hpp flags; PB_FLAG_* in include/pairs_b200.h)
+
+    @staticmethod
+    def _keep_own(ctx, part):
+        """A rank keeps the rows inside its subdomain plus every infinite / fixed / global body (runtime/read_from_file.hpp:44-106;
+        the subdomain test is the partitioner's isWithinSubdomain, runtime/domain/regular_6d_stencil.cpp)."""
+        dec = ctx.decomposition()
+        if int(np.prod(dec["nranks"])) == 1:
+            return part
+        sd, x = dec["subdom"], np.asarray(part["position"], np.float64)
+        keep = np.ones(len(x), bool)
+        for d in range(3):
+            keep &= (x[:, d] >= sd[2 * d]) & (x[:, d] < sd[2 * d + 1] - 0.00001)
+        if "flags" in part:
+            keep |= (np.asarray(part["flags"]) & Simulation._FLAGS_KEEP) != 0
+        return {k: (np.asarray(v)[keep] if len(np.atleast_1d(v)) == len(x) else v) for k, v in part.items()}
 
     def _dem_banner(self, a, count):
         # runtime/dem_sc_grid.hpp:159-169

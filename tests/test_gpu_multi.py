@@ -25,3 +25,15 @@ def test_multi_gpu_md_matches_multirank_oracle(world):
            "--master-port", str(29600 + world), os.path.join(ROOT, "tests", "scripts", "mgpu_check.py"), "12", "45"]
     r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "mgpu_check ok" in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_dem_matches_single_gpu(world):
+    """DEM over N GPUs (particles migrate WITH their contact history) against the single-GPU run that test_gpu_dem.py pins
+    to the reference; see tests/scripts/mgpu_dem_check.py for what is compared and why the stock reference cannot be."""
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + world), os.path.join(ROOT, "tests", "scripts", "mgpu_dem_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "mgpu_dem_check ok" in r.stdout, r.stdout[-4000:]
