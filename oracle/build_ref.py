@@ -16,6 +16,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
   dem_t1    examples/dem.py on a 0.1 x 0.015 x 0.04 box (420 spheres + 2 planes), 700 steps, thermo hook every step
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
+  md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
             -> CPU-baseline sample for bench.py
@@ -45,8 +46,10 @@ def _sub(text, pattern, repl, count=1):
     return new
 
 
-def md_variant(nx, steps, thermo, reneigh, pcap=None):
+def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False):
     def patch(text):
+        if half:        # the line is present but commented out in the stock example (examples/md.py:58)
+            text = _sub(text, r"^#psim\.compute_half\(\)", "psim.compute_half()")
         text = _sub(text, r"^nx = \d+", f"nx = {nx}")
         text = _sub(text, r"^ny = \d+", f"ny = {nx}")
         text = _sub(text, r"^nz = \d+", f"nz = {nx}")
@@ -77,6 +80,8 @@ VARIANTS = {
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
+    # half neighbour lists + atomic update of the partner
+    "md_half_t1": ("examples/md.py", md_variant(8, 100, 1, 20, half=True), ["-DREF_IS_MD", "-DREF_HALF_LISTS"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
     "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
     "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),

@@ -54,6 +54,7 @@ typedef struct po_sim {
     int ntypes;
     double epsilon[64], sigma6[64];
     int reneigh_every, thermo_every;
+    int compute_half; /* Simulation.compute_half(), sim/simulation.py:119-120 */
     po_rank *r;
 } po_sim;
 
@@ -183,6 +184,8 @@ void po_set_params(po_sim *s, double cell_spacing, double cutoff_lists, double c
     s->reneigh_every = reneigh_every;
     s->thermo_every = thermo_every;
 }
+
+void po_set_compute_half(po_sim *s, int on) { s->compute_half = on; }
 
 /* ---- set-up: runtime/copper_fcc_lattice.hpp:18-26 (Park-Miller RNG) and :64-145 (lattice walk) ---- */
 static double po_myrandom(int *seed) {
@@ -416,7 +419,11 @@ int po_build_neighbor_lists(po_sim *s, po_rank *r) {
             const double xi = r->position[i * 3], yi = r->position[i * 3 + 1], zi = r->position[i * 3 + 2];
             for(int m = 0; m < ns; m++) {
                 const int j = r->cell_particles[cell * r->cell_capacity + m];
-                if(j == i) { continue; }
+                if(s->compute_half) { /* sim/interaction.py:107-113: shape[j] > shape_i || (shape[j] == shape_i && i < j) */
+                    if(!(r->shape[j] > r->shape[i] || (r->shape[j] == r->shape[i] && i < j))) { continue; }
+                } else if(j == i) {
+                    continue;
+                }
                 const double dx = xi - r->position[j * 3];
                 const double dy = yi - r->position[j * 3 + 1];
                 const double dz = zi - r->position[j * 3 + 2];
@@ -472,6 +479,13 @@ void po_lennard_jones(po_sim *s, po_rank *r) {
                 fx = fx + dx * f;
                 fy = fy + dy * f;
                 fz = fz + dz * f;
+                /* ir/apply.py:111-125: the partner of a half-list pair gets the opposite term, unless it is a ghost or FIXED
+                 * (atomic_add in the generated code; the serial build performs them in loop order) */
+                if(s->compute_half && j < r->nlocal && (r->flags[j] & PO_FLAG_FIXED) == 0) {
+                    r->force[j * 3 + 0] += -(dx * f);
+                    r->force[j * 3 + 1] += -(dy * f);
+                    r->force[j * 3 + 2] += -(dz * f);
+                }
             }
         }
         r->force[i * 3 + 0] = r->force[i * 3 + 0] + fx;

@@ -34,6 +34,7 @@ def _load():
     lib.po_create.restype = P
     lib.po_destroy.argtypes = [P]
     lib.po_set_params.argtypes = [P, D, D, D, D, I, DP, DP, I, I]
+    lib.po_set_compute_half.argtypes = [P, I]
     lib.po_copper_fcc_lattice.argtypes = [P, I, I, I, D, I]
     lib.po_adjust_thermo.argtypes = [P, D]
     lib.po_compute_thermo.argtypes = [P, DP]
@@ -184,6 +185,10 @@ class OracleSim:
         s6 = np.ascontiguousarray(sigma6, np.float64)
         lib().po_set_params(self.p, cell_spacing, cutoff_lists, cutoff_force, dt, ntypes, _dp(e), _dp(s6), reneigh_every, thermo_every)
         lib().po_setup_cells(self.p)
+
+    def compute_half(self, on=True):
+        """Simulation.compute_half() (sim/simulation.py:119-120): half neighbour lists, partner updated with the opposite term."""
+        lib().po_set_compute_half(self.p, 1 if on else 0)
 
     def copper_fcc_lattice(self, nx, ny, nz, rho, temp, ntypes):
         lib().po_copper_fcc_lattice(self.p, nx, ny, nz, rho, ntypes)

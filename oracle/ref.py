@@ -123,6 +123,10 @@ class RefProgram:
                 s[name] = self.prop(name, n, w)
             for name in int_props:
                 s[name] = self.prop(name, n, 1, np.int32)
+            if not snaps:        # the lists of the first iteration (built from the initial positions)
+                cap = self.array("neighborlists", np.int32).size // max(self.array("numneighs", np.int32).size, 1)
+                s["numneighs"] = self.array("numneighs", np.int32, nlocal)
+                s["neighborlists"] = self.array("neighborlists", np.int32, nlocal * cap).reshape(nlocal, cap)
             snaps.append(s)
 
         self.run(on_event)

@@ -178,12 +178,21 @@ void ref_md_partition_cell_lists(int cell_capacity, int ncells, int *cell_sizes,
     partition_cell_lists(nullptr, cell_capacity, ncells, cell_sizes, nshapes, shapes_buffer, cell_particles, shape);
 }
 
+#ifdef REF_HALF_LISTS      // compute_half(): the list builder additionally reads the shape ids (sim/interaction.py:107-113)
+void ref_md_build_neighbor_lists(int nlocal, int ncells, int cell_capacity, int neighbor_capacity, int nstencil, int *numneighs,
+                                 int *particle_cell, int *stencil, int *nshapes, int *cell_particles, int *neighborlists,
+                                 int *resizes, int *flags, double *position, int *shape) {
+    build_neighbor_lists(nullptr, nlocal, ncells, cell_capacity, neighbor_capacity, nstencil, numneighs, particle_cell, stencil,
+                         nshapes, cell_particles, neighborlists, resizes, flags, position, shape);
+}
+#else
 void ref_md_build_neighbor_lists(int nlocal, int ncells, int cell_capacity, int neighbor_capacity, int nstencil, int *numneighs,
                                  int *particle_cell, int *stencil, int *nshapes, int *cell_particles, int *neighborlists,
                                  int *resizes, int *flags, double *position) {
     build_neighbor_lists(nullptr, nlocal, ncells, cell_capacity, neighbor_capacity, nstencil, numneighs, particle_cell, stencil,
                          nshapes, cell_particles, neighborlists, resizes, flags, position);
 }
+#endif
 #endif
 
 }

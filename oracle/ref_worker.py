@@ -35,8 +35,12 @@ def dump(variant, out_path, nsteps=None):
         raise RuntimeError(f"ref_worker dump failed:\n{out}\n{err}")
     z = np.load(out_path)
     n = int(z["count"])
-    return [{k: z[f"{k}_{i}"] for k in ("position", "linear_velocity", "force", "mass", "type")} | {"nlocal": int(z["nlocal"][i]), "nghost": int(z["nghost"][i])}
-            for i in range(n)]
+    snaps = [{k: z[f"{k}_{i}"] for k in ("position", "linear_velocity", "force", "mass", "type")} | {"nlocal": int(z["nlocal"][i]), "nghost": int(z["nghost"][i])}
+             for i in range(n)]
+    for k in ("numneighs", "neighborlists"):
+        if k in z.files:
+            snaps[0][k] = z[k]
+    return snaps
 
 
 def dump_dem(variant, out_path, max_steps, keep):
@@ -72,6 +76,9 @@ def _main(argv):
         for i, s in enumerate(snaps):
             for k in ("position", "linear_velocity", "force", "mass", "type"):
                 d[f"{k}_{i}"] = s[k]
+        for k in ("numneighs", "neighborlists"):
+            if snaps and k in snaps[0]:
+                d[k] = snaps[0][k]
         np.savez(out_path, **d)
         return 0
     if mode == "dump_dem":

@@ -67,6 +67,7 @@ struct pb_ctx {
     int *type = nullptr, *type_alt = nullptr, *flags = nullptr, *flags_alt = nullptr;
     int *uid = nullptr, *uid_alt = nullptr, *shape = nullptr, *shape_alt = nullptr, *tag = nullptr, *tag_alt = nullptr;
     bool ghosts_in_alt = false;   // after a fused initial_integrate: ghosts of the last refresh still live in pos_alt
+    bool half_lists = false;      // compute_half(): lists hold j with i < j only, the force kernel updates both partners
     bool fuse_integrate = true;   // pb_md_run folds the integrator halves into the force kernel's epilogue
     bool force_is_zero = false;   // reset_volatile requested and not yet materialised (fused into the force kernel)
 

@@ -159,6 +159,93 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int
     }
 }
 
+
+// ---- compute_half(): half lists, both partners updated (ir/apply.py:111-125) ------------------------------------------------
+// A pair term is evaluated once, by the partner with the smaller index: +f goes to its own accumulator, -f to the
+// partner unless that is a ghost (j >= nlocal: its owner evaluates the mirrored pair itself) or FIXED.  All updates of the
+// force array are fp64 atomic adds (RED.ADD.F64), so the order of a particle's terms -- fixed by the loop order in the
+// reference's serial build -- is not reproducible here; every term itself is still computed with the reference's
+// operations (tested to 1e-12 relative).  The force array must hold the reset values when the kernel starts, the
+// integrator halves cannot be fused (a particle's force is complete only when the whole grid has finished).
+template<bool UNIFORM>
+__global__ void __launch_bounds__(128) pb_k_lennard_jones_half(int nlocal, int T, int cap, double cutsq, int ntypes, double eps_u,
+                                                               double sig6_u, const double *__restrict__ eps_t,
+                                                               const double *__restrict__ sig6_t, const double4 *__restrict__ pos,
+                                                               const int *__restrict__ flags, const int *__restrict__ numneigh,
+                                                               const int *__restrict__ neigh, double *__restrict__ force) {
+    __shared__ double s_eps[64], s_sig6[64];
+    if(!UNIFORM) {
+        for(int k = threadIdx.x; k < ntypes * ntypes; k += blockDim.x) { s_eps[k] = eps_t[k]; s_sig6[k] = sig6_t[k]; }
+        __syncthreads();
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal || (flags[i] & PB_FLAG_FIXED) != 0) { return; }
+    const double4 pi = pb_ld_pos(pos + i);
+    const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * ntypes;
+    const int nn = numneigh[i];
+    const int *nb = neigh + (size_t) (i >> 5) * T * 32 + (i & 31);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+#define PB_LJ_HALF_PAIR(J, PJ)                                                                                                 \
+    {                                                                                                                          \
+        const double dx = __dsub_rn(pi.x, (PJ).x);                                                                             \
+        const double dy = __dsub_rn(pi.y, (PJ).y);                                                                             \
+        const double dz = __dsub_rn(pi.z, (PJ).z);                                                                             \
+        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));                      \
+        if(rsq < cutsq) {                                                                                                      \
+            const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type((PJ).w)];                                             \
+            const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type((PJ).w)];                                                \
+            const double sr2 = __ddiv_rn(1.0, rsq);                                                                            \
+            const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);                                           \
+            const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);             \
+            const double tx = __dmul_rn(dx, f), ty = __dmul_rn(dy, f), tz = __dmul_rn(dz, f);                                  \
+            fx = __dadd_rn(fx, tx);                                                                                            \
+            fy = __dadd_rn(fy, ty);                                                                                            \
+            fz = __dadd_rn(fz, tz);                                                                                            \
+            if((J) < nlocal && (__ldg(flags + (J)) & PB_FLAG_FIXED) == 0) {                                                    \
+                atomicAdd(force + (J), -tx);                                                                                   \
+                atomicAdd(force + cap + (J), -ty);                                                                             \
+                atomicAdd(force + 2 * (size_t) cap + (J), -tz);                                                                \
+            }                                                                                                                  \
+        }                                                                                                                      \
+    }
+    int k = 0;
+    for(; k + 4 <= nn; k += 4) {
+        int j[4];
+        double4 pj[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++) { j[u] = __ldg(nb + (size_t) (k + u) * 32); }
+#pragma unroll
+        for(int u = 0; u < 4; u++) { pj[u] = pb_ld_pos(pos + j[u]); }
+#pragma unroll
+        for(int u = 0; u < 4; u++) { PB_LJ_HALF_PAIR(j[u], pj[u]) }
+    }
+    for(; k < nn; k++) {
+        const int j = __ldg(nb + (size_t) k * 32);
+        const double4 pj = pb_ld_pos(pos + j);
+        PB_LJ_HALF_PAIR(j, pj)
+    }
+#undef PB_LJ_HALF_PAIR
+    atomicAdd(force + i, fx);
+    atomicAdd(force + cap + i, fy);
+    atomicAdd(force + 2 * (size_t) cap + i, fz);
+}
+
+int pb_materialise_force_reset(pb_ctx *ctx);
+
+static int pb_lennard_jones_half(pb_ctx *ctx, double cutsq) {
+    if(ctx->lanes != 1) { ctx->set_error("compute_half needs lanes_per_particle = 1"); return -1; }
+    PB_TRY(pb_materialise_force_reset(ctx));
+    const int n = ctx->nlocal;
+    if(ctx->lj_uniform) {
+        PB_LAUNCH(pb_k_lennard_jones_half<true>, pb_blocks(n, 128), 128, n, ctx->nslots, ctx->pcap, cutsq, ctx->ntypes, ctx->h_eps[0],
+                  ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh, ctx->force);
+    } else {
+        PB_LAUNCH(pb_k_lennard_jones_half<false>, pb_blocks(n, 128), 128, n, ctx->nslots, ctx->pcap, cutsq, ctx->ntypes, ctx->h_eps[0],
+                  ctx->h_sig6[0], ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags, ctx->numneigh, ctx->neigh, ctx->force);
+    }
+    return 0;
+}
+
 extern "C" int pb_set_lj_params(pb_ctx *ctx, int ntypes, const double *epsilon, const double *sigma6) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(ntypes < 1 || ntypes > 8) { ctx->set_error("pb_set_lj_params: 1 <= ntypes <= 8 supported"); return -1; }
@@ -252,6 +339,10 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int 
     const double cutsq = cutoff * cutoff;
     ctx->lj_groups = nullptr;
     ctx->lj_ngroups = 0;
+    if(ctx->half_lists) {
+        if(fuse != 0 || part != 0) { ctx->set_error("compute_half: the integrators cannot be fused / the grid cannot be split"); return -1; }
+        return pb_lennard_jones_half(ctx, cutsq);
+    }
     if(part != 0) {
         if(!ctx->groups_valid || ctx->lanes != 1) { ctx->set_error("interior/boundary split not available"); return -1; }
         ctx->lj_groups = (part == 1) ? ctx->groups_interior : ctx->groups_boundary;
@@ -305,6 +396,11 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
         return 0;
     }
     if(nm == "fuse_integrate") { ctx->fuse_integrate = value != 0; return 0; }
+    if(nm == "compute_half") {
+        ctx->half_lists = value != 0;
+        ctx->neigh_n = -1;      // lists must be rebuilt
+        return 0;
+    }
     if(nm == "stage_lists") { ctx->stage_lists = value != 0; return 0; }
     if(nm == "cell_zsub") {
         if(value < 1 || value > 32) { ctx->set_error("cell_zsub must be in 1..32"); return -1; }
@@ -356,6 +452,7 @@ extern "C" int pb_lj_legacy(pb_ctx *ctx, double cutoff, double epsilon, double s
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "lj");
     if(ctx->neigh_n != ctx->nlocal || ctx->lanes != 1) { ctx->set_error("pb_lj_legacy: neighbour lists are stale (or lanes_per_particle != 1)"); return -1; }
+    if(ctx->half_lists) { ctx->set_error("pb_lj_legacy: half lists are not supported by the legacy kernel"); return -1; }
     if(ctx->nlocal == 0) { return 0; }
     PB_LAUNCH(pb_k_lj_legacy, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->nslots, ctx->pcap, cutoff * cutoff, epsilon, sigma6, ctx->pos,
               ctx->flags, ctx->numneigh, ctx->neigh, ctx->force, ctx->force_is_zero ? 0 : 1);
@@ -484,7 +581,7 @@ __global__ void __launch_bounds__(THERMO_T) pb_k_thermo_final(int nparts, const 
 __global__ void __launch_bounds__(128) pb_k_lj_energy_virial(int nlocal, int T, double cutsq, int ntypes, const double *__restrict__ eps_t,
                                                              const double *__restrict__ sig6_t, const double4 *__restrict__ pos,
                                                              const int *__restrict__ flags, const int *__restrict__ numneigh,
-                                                             const int *__restrict__ neigh, double *__restrict__ partial) {
+                                                             const int *__restrict__ neigh, double *__restrict__ partial, int half) {
     __shared__ double s_e[4], s_w[4];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double e = 0.0, w = 0.0;
@@ -494,15 +591,18 @@ __global__ void __launch_bounds__(128) pb_k_lj_energy_virial(int nlocal, int T, 
         const int nn = numneigh[i];
         const int *nb = neigh + (size_t) (i >> 5) * T * 32 + (i & 31);
         for(int k = 0; k < nn; k++) {
-            const double4 pj = pb_ld_pos(pos + __ldg(nb + (size_t) k * 32));
+            const int j = __ldg(nb + (size_t) k * 32);
+            const double4 pj = pb_ld_pos(pos + j);
             const double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
             const double rsq = (dx * dx + dy * dy) + dz * dz;
             if(rsq < cutsq) {
                 const int t = ti + pb_w_type(pj.w);
                 const double sr2 = 1.0 / rsq;
                 const double sr6 = sr2 * sr2 * sr2 * sig6_t[t];
-                e += 4.0 * eps_t[t] * (sr6 * sr6 - sr6);
-                w += rsq * (48.0 * sr6 * (sr6 - 0.5) * sr2 * eps_t[t]);
+                // half lists hold a local-local pair once (weight 2 before the global halving), a local-ghost pair at its local end
+                const double wt = (half && j < nlocal) ? 2.0 : 1.0;
+                e += wt * (4.0 * eps_t[t] * (sr6 * sr6 - sr6));
+                w += wt * (rsq * (48.0 * sr6 * (sr6 - 0.5) * sr2 * eps_t[t]));
             }
         }
     }
@@ -549,7 +649,7 @@ extern "C" int pb_lj_energy_virial(pb_ctx *ctx, double cutoff, double *epot, dou
     double *partial = nullptr;
     PB_CHECK(cudaMalloc(&partial, sizeof(double) * 2 * ((size_t) B + 1)));
     PB_LAUNCH(pb_k_lj_energy_virial, B, 128, n, ctx->nslots, cutoff * cutoff, ctx->ntypes, ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags,
-              ctx->numneigh, ctx->neigh, partial);
+              ctx->numneigh, ctx->neigh, partial, ctx->half_lists ? 1 : 0);
     PB_LAUNCH(pb_k_sum_pairs, 1, 256, B, partial, partial + 2 * (size_t) B);
     double h[2];
     PB_CHECK(cudaMemcpyAsync(h, partial + 2 * (size_t) B, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));

@@ -29,12 +29,14 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
         // Multi-rank steps without reneighbouring: the ghost refresh (pack -> NCCL -> unpack) runs on comm_stream while the
         // interior warp groups -- no ghost neighbour, no halo source -- already compute on the main stream; the boundary
         // groups follow once the refresh has landed.  (The reference's communication is blocking)
-        const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && ctx->fuse_integrate && ctx->groups_valid &&
+        // (half lists: a particle's force is complete only after the whole grid, so nothing is fused or split)
+        const bool fusing = ctx->fuse_integrate && !ctx->half_lists;
+        const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && fusing && ctx->groups_valid &&
                              ctx->neigh_n == ctx->nlocal;
         if(!reneigh && !overlap) { PB_TRY(pb_synchronize(ctx)); }
         PB_TRY(pb_reset_volatile(ctx));
         const bool thermo_now = p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0);
-        if(ctx->fuse_integrate) {
+        if(fusing) {
             // fold final_integrate(ts) and -- unless thermo must see the velocities in between, or the call ends here --
             // initial_integrate(ts + 1) into the force kernel
             int fuse = (ts > 0) ? 1 : 0;

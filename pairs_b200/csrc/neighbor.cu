@@ -10,6 +10,9 @@
 // The three z-adjacent stencil cells of one (dx,dy) row are consecutive flat indices, so each row is ONE
 // contiguous run of the CSR cell list: 9 runs + cell 0 per particle, each run narrowed to the z slabs within reach.
 //
+// Half lists (Simulation.compute_half(), sim/simulation.py:119-120): only partners with a larger index are stored -- each
+// local-local pair once, a local-ghost pair at its local end -- as UNORDERED pairs the same set as the reference's.
+//
 // HBM bytes per local particle: pos 32 + cell 4 + list write 4*K + count 4; candidates (~27 cells * occupancy)
 // are served from L1/L2 because the 32 lanes of a warp sit in the same 1-3 cells.
 #include <algorithm>
@@ -40,7 +43,7 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncap
                                                             const int *__restrict__ particle_cell, const int *__restrict__ sub_start,
                                                             const int *__restrict__ cell_list, int *__restrict__ neigh,
                                                             int *__restrict__ numneigh, int *__restrict__ max_count, PbFaces faces,
-                                                            int *__restrict__ group_flag) {
+                                                            int *__restrict__ group_flag, int half) {
     extern __shared__ int s_stage[];                       // [warps per block][ncap][32]
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -94,7 +97,9 @@ __global__ void __launch_bounds__(128) pb_k_build_neighbors(int nlocal, int ncap
                 const double dy = __dsub_rn(pi.y, pj.y);
                 const double dz = __dsub_rn(pi.z, pj.z);
                 const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if(rsq < cutsq && j != i) {
+                // compute_half() (sim/interaction.py:107-113) keeps shape[j] > shape[i] || (shape[j] == shape[i] && i < j); every
+                // particle on the neighbour-list path has the same shape, which leaves i < j (ghosts sit behind all locals)
+                if(rsq < cutsq && (half ? (j > i) : (j != i))) {
                     if(count < ncap) {
                         if(STAGE) { s_mine[count * 32] = j; }
                         else if(G == 1) { out[(size_t) count * 32] = j; }
@@ -215,12 +220,13 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
             PB_CHECK(cudaFuncSetAttribute(pb_k_build_neighbors<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stage_bytes));
             pb_k_build_neighbors<true><<<pb_blocks(n, 128), 128, stage_bytes, ctx->stream>>>(
                 n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags, ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh,
-                ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag);
+                ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag, ctx->half_lists ? 1 : 0);
             ctx->launches++;
             PB_CHECK(cudaGetLastError());
         } else {
             PB_LAUNCH(pb_k_build_neighbors<false>, pb_blocks(n, 128), 128, n, ctx->ncap, pb_layout(ctx), bg, cutsq, ctx->pos, ctx->flags,
-                      ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh, ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag);
+                      ctx->particle_cell, ctx->sub_start, ctx->cell_list, ctx->neigh, ctx->numneigh, ctx->d_scalars, faces, ctx->group_flag,
+                      ctx->half_lists ? 1 : 0);
         }
         PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CHECK(cudaStreamSynchronize(ctx->stream));

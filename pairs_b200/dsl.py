@@ -259,6 +259,7 @@ class Simulation:
         self.contact_props = {}
         self._target = None
         self._partitioner = DomainPartitioners.Regular
+        self._compute_half = False
         self._pbc = [True, True, True]
         self.grid = None
         self.reneighbor_frequency = 1            # sim/simulation.py:89
@@ -292,7 +293,8 @@ class Simulation:
         self._pbc = list(cfg)
 
     def compute_half(self):
-        raise DslError("compute_half() (Newton-3 half lists) is not implemented by this backend yet (SURVEY.md 8f rank 1)")
+        """sim/simulation.py:119-120: half neighbour lists, each pair term applied to both partners (ir/apply.py:111-125)."""
+        self._compute_half = True
 
     def add_property(self, name, ptype, value=0.0, volatile=False):
         assert name not in self.props, f"Property already defined: {name}"
@@ -427,7 +429,13 @@ class Simulation:
             raise DslError("build_cell_lists() / build_neighbor_lists() was not called")
         families = [e["family"] for e in self.pre_step + self.functions]
         if "linear_spring_dashpot" in families:
+            if self._compute_half:
+                raise DslError("compute_half() is implemented for the neighbour-list (md.py) path only")
             return self._generate_dem(ctx, rank, world)
+        if self._compute_half:
+            if "lj_legacy" in families:
+                raise DslError("compute_half() is not available for the legacy lj kernel")
+            ctx.set_option("compute_half", 1)
         ctx.reserve(0, self.neighbor_capacity)
 
         # ---- set-up ----

@@ -1,4 +1,4 @@
-"""Generates tests/golden/md_t1.npz and md_t2.npz from the REFERENCE ITSELF: the reference generator's own serial C++
+"""Generates tests/golden/md_t1.npz, md_t2.npz and md_half_t1.npz from the REFERENCE ITSELF: the reference generator's own serial C++
 for examples/md.py (variants md_t1 / md_t2 of oracle/build_ref.py, i.e. nx = 8 resp. 12, thermo every step), run in a
 fresh process.  Needs /root/reference (this container only); the fixtures are committed so that the oracle restatement
 and the CUDA path can be pinned where the reference is absent.
@@ -15,8 +15,10 @@ sys.path.insert(0, ROOT)
 from oracle import ref_worker  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-KEEP = {"md_t1": [0, 1, 19, 20, 100], "md_t2": [5, 60]}
-NAMES = {"md_t1": ("position", "linear_velocity", "force"), "md_t2": ("position", "force")}
+KEEP = {"md_t1": [0, 1, 19, 20, 100], "md_t2": [5, 60], "md_half_t1": [0, 1, 20, 100]}
+NAMES = {"md_t1": ("position", "linear_velocity", "force"), "md_t2": ("position", "force"),
+         "md_half_t1": ("position", "linear_velocity", "force")}
+ONLY = sys.argv[1:]
 
 
 def serial_thermo(s):
@@ -28,6 +30,8 @@ def serial_thermo(s):
 
 
 for variant, keep in KEEP.items():
+    if ONLY and variant not in ONLY:
+        continue
     snaps = ref_worker.dump(variant, f"/tmp/{variant}_golden_raw.npz")
     out = {"temperature": np.array([serial_thermo(s) for s in snaps]),
            "nlocal": np.array([s["nlocal"] for s in snaps]), "nghost": np.array([s["nghost"] for s in snaps]),
@@ -36,5 +40,9 @@ for variant, keep in KEEP.items():
         for name in NAMES[variant]:
             out[f"{name}_{k}"] = snaps[k][name]
     out["type"] = snaps[0]["type"]
+    if variant == "md_half_t1":      # compute_half(): the half lists of the first iteration, rows trimmed to the longest list
+        nn = snaps[0]["numneighs"]
+        out["numneighs_0"] = nn
+        out["neighborlists_0"] = snaps[0]["neighborlists"][:, :int(nn.max())].astype(np.int32)
     np.savez_compressed(os.path.join(HERE, f"{variant}.npz"), **out)
     print(variant, len(snaps), "steps;", os.path.getsize(os.path.join(HERE, f"{variant}.npz")) // 1024, "KiB")

@@ -85,8 +85,10 @@ def test_plan_and_error_behaviour():
     cpu = lj_script.build("cpu", 8, 10, 20, 10)
     with pytest.raises(dsl.DslError, match="B200 GPUs only"):
         cpu.generate()
-    with pytest.raises(dsl.DslError):
-        psim.compute_half()
+    assert psim._compute_half is False
+    half = lj_script.build("gpu", 8, 10, 20, 10)
+    half.compute_half()                      # sim/simulation.py:119-120
+    assert half._compute_half is True
     assert dsl._fmt(1.44) == "1.44" and dsl._fmt(1.215643219) == "1.21564" and dsl._fmt(0.6928049) == "0.692805"
     if not HAS_GPU:
         from pairs_b200.backend import BackendError

@@ -393,3 +393,98 @@ def test_energy_and_virial_reductions():
     ctx.md_run(1, 201, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)
     ctx.exchange(); ctx.borders(); ctx.build_cell_lists(); ctx.build_neighbor_lists(CUT + SKIN)
     assert abs(total() - e0) <= 2e-3 * abs(e0)
+
+
+# ---- compute_half(): half neighbour lists, both partners updated ---------------------------------------
+def _pair_rows(ids, pos, numneighs, neigh, nlocal):
+    """Unordered pairs {id_i, id_j} (+ the partner's exact coordinates when it is a ghost image) of a set of HALF lists: the
+    product stores a local-local pair at whichever partner comes first in ITS particle order, the reference in its own."""
+    ids = np.asarray(ids).astype(np.int64)
+    nn = np.asarray(numneighs)[:nlocal]
+    ii = np.repeat(np.arange(nlocal), nn)
+    kk = np.arange(int(nn.sum())) - np.repeat(np.cumsum(nn) - nn, nn)
+    jj = np.asarray(neigh)[ii, kk]
+    ghost = jj >= nlocal
+    a, b = ids[ii], ids[jj]
+    lo, hi = np.where(ghost, a, np.minimum(a, b)), np.where(ghost, b, np.maximum(a, b))
+    pj = np.where(ghost[:, None], f2i(pos[jj]), 0)
+    return rows_sorted(ghost.astype(np.int64), lo, hi, pj[:, 0], pj[:, 1], pj[:, 2])
+
+
+def test_half_lists_pairs_and_forces():
+    nx = 8
+    rng = np.random.default_rng(11)
+    ctx, n = make_gpu(nx)
+    ctx.set_option("compute_half", 1)
+    sim = make_oracle(nx)
+    sim.compute_half()
+    r = sim.ranks[0]
+    d = 0.05 * (rng.random((n, 3)) - 0.5)
+    r.real("position", n, view=True)[:] += d
+    ctx.upload(r.real("position"), r.real("linear_velocity"), r.real("mass"), r.ints("type"))
+    sim.step(0)
+    _reneighbor_gpu(ctx)
+    nl, ng = ctx.counts()
+    tot = nl + ng
+    nn_o, nl_o = r.neighbor_sets()
+    o = _pair_rows(r.ints("uid", tot), r.real("position", tot), nn_o, nl_o, nl)
+    g = _pair_rows(ctx.ints("tag", True), ctx.real("position", True), ctx.ints("numneighs"), ctx.neighbors(), nl)
+    assert g.shape == o.shape and np.array_equal(g, o)              # the same pairs, each exactly once
+    assert int(ctx.ints("numneighs").sum()) < 0.62 * 78 * n         # ... i.e. about half of the full lists (+ ghost partners)
+    ctx.reset_volatile()
+    ctx.lennard_jones(CUT)
+    f_o = by_id(r.ints("uid"), r.real("force"))
+    f_g = by_id(ctx.ints("tag"), ctx.real("force"))
+    assert rel_err_force(f_g, f_o) <= 1e-12
+    # the full-list evaluation of the same configuration gives the same forces (Newton's third law is exact in fp64:
+    # -(d*f) == (-d)*f), up to summation order
+    ctx.set_option("compute_half", 0)
+    _reneighbor_gpu(ctx)
+    ctx.reset_volatile()
+    ctx.lennard_jones(CUT)
+    assert rel_err_force(by_id(ctx.ints("tag"), ctx.real("force")), f_o) <= 1e-12
+    e_full = ctx.lj_energy_virial(CUT)
+    ctx.set_option("compute_half", 1)
+    _reneighbor_gpu(ctx)
+    e_half = ctx.lj_energy_virial(CUT)
+    assert abs(e_half[0] - e_full[0]) <= 1e-12 * abs(e_full[0]) and abs(e_half[1] - e_full[1]) <= 1e-12 * abs(e_full[1])
+
+
+def test_half_lists_run_matches_oracle_and_reference_golden():
+    """100 steps with half lists: thermo of every step within 1e-9 of the restatement AND of the golden produced by the
+    reference's own generated C++ with psim.compute_half() enabled (tests/golden/md_half_t1.npz)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "md_half_t1.npz"))
+    ctx, n = make_gpu(8)
+    ctx.set_option("compute_half", 1)
+    sim = make_oracle(8)
+    sim.compute_half()
+    r = sim.ranks[0]
+    th = ctx.md_run(0, 101, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
+    assert len(th) == 101
+    for ts in range(101):
+        sim.step(ts)
+        t_o = sim.thermo()[0]
+        assert abs(th[ts, 1] - t_o) <= 1e-9 * t_o, ts
+        assert abs(th[ts, 1] - z["temperature"][ts]) <= 1e-9 * z["temperature"][ts], ts
+    assert ctx.counts() == (r.nlocal, r.nghost) == (int(z["nlocal"][100]), int(z["nghost"][100]))
+    tag = ctx.ints("tag")
+    assert np.abs(by_id(tag, ctx.real("position")) - by_id(r.ints("uid"), r.real("position"))).max() <= 1e-9
+
+
+def test_dsl_script_with_compute_half_matches_reference_golden(capsys):
+    """examples/md.py with its `#psim.compute_half()` line enabled, through the DSL."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import lj_script
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "md_half_t1.npz"))
+    psim = lj_script.build("gpu", 8, 100, 20, 1)
+    psim.compute_half()
+    ctx = psim.generate()
+    capsys.readouterr()
+    assert len(psim.thermo_log) == 101
+    for (ts, t, p), t_ref in zip(psim.thermo_log, z["temperature"]):
+        assert abs(t - t_ref) <= 1e-9 * t_ref, ts
+    assert np.abs(np.sort(ctx.real("position"), axis=0) - np.sort(z["position_100"], axis=0)).max() <= 1e-9
+    assert int(ctx.ints("numneighs").sum()) < 0.62 * 78 * 2048

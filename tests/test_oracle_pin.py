@@ -13,14 +13,17 @@ from oracle import port, ref
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def run_port(nx, reneigh, steps, keep):
+def run_port(nx, reneigh, steps, keep, half=False):
     sim = port.md_example(nx, reneigh_every=reneigh, particle_capacity=60000, send_capacity=60000)
+    if half:
+        sim.compute_half()
     r = sim.ranks[0]
     temps, kept, counts, types0 = [], {}, [], None
     for ts in range(steps + 1):
         sim.step(ts)
         if ts == 0:
             types0 = r.ints("type")
+            kept["lists"] = (r.ints("numneighs", r.nlocal), r.ints("neighborlists", r.nlocal * r.neighbor_capacity).reshape(r.nlocal, -1))
         temps.append(sim.thermo()[0])
         counts.append((r.nlocal, r.nghost))
         if ts in keep:
@@ -40,6 +43,28 @@ def test_restatement_matches_reference_golden_bit_for_bit(variant, nx, reneigh, 
         for name in ("position", "linear_velocity", "force"):
             if f"{name}_{k}" in z:
                 assert np.array_equal(kept[k][name], z[f"{name}_{k}"]), (k, name)
+
+
+def test_half_list_restatement_matches_reference_golden_bit_for_bit():
+    """compute_half() (sim/interaction.py:107-113, ir/apply.py:111-125): the serial reference applies the partner updates in
+    loop order, the restatement does the same -> identical bits, including the half lists themselves."""
+    z = np.load(os.path.join(GOLD, "md_half_t1.npz"))
+    keep = [int(k) for k in z["steps_kept"]]
+    temps, counts, kept, types = run_port(8, 20, 100, keep, half=True)
+    assert np.array_equal(temps, z["temperature"])
+    assert [c[0] for c in counts] == list(z["nlocal"]) and [c[1] for c in counts] == list(z["nghost"])
+    for k in keep:
+        for name in ("position", "linear_velocity", "force"):
+            assert np.array_equal(kept[k][name], z[f"{name}_{k}"]), (k, name)
+    nn, lists = kept["lists"]
+    assert np.array_equal(nn, z["numneighs_0"])
+    w = z["neighborlists_0"].shape[1]
+    for i in range(len(nn)):
+        assert np.array_equal(lists[i, :nn[i]], z["neighborlists_0"][i, :nn[i]]) and nn[i] <= w
+    # half lists: every stored partner has a larger index; the full-list run of the same system sees the same physics
+    assert all((lists[i, :nn[i]] > i).all() for i in range(len(nn)))
+    full = np.load(os.path.join(GOLD, "md_t1.npz"))
+    assert np.abs(temps - full["temperature"]).max() <= 1e-12
 
 
 def test_golden_thermo_reproduces_reference_stdout():
