@@ -164,7 +164,10 @@ typedef struct pb_md_params {
 } pb_md_params;
 int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo);
 
-/* tuning knobs: "lanes_per_particle" (1,2,4,8,16; applies from the next neighbour-list build), "lj_unroll" (1,2,4,8) */
+/* Options.  Behaviour: "compute_half" (0/1) = Simulation.compute_half() (sim/simulation.py:119-120): half neighbour lists,
+ * pair terms applied to both partners (ir/apply.py:111-125); applies from the next neighbour-list build.
+ * Tuning knobs: "lanes_per_particle" (1,2,4,8; applies from the next build), "lj_unroll" (2,4,8), "fuse_integrate" (0/1),
+ * "overlap_comm" (0/1), "cell_zsub" (1..32, applies from the next pb_setup_cells), "stage_lists" (0/1). */
 int pb_set_option(pb_ctx *ctx, const char *name, int value);
 
 /* ---- streams / timing ---- */
