@@ -110,6 +110,56 @@ def ncu_traffic():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def reference_cuda_sample():
+    """SECONDARY baseline (BASELINE.json north_star): the reference's OWN CUDA target -- `examples/md.py gpu` through the
+    reference generator, nvcc -arch sm_100a with the reference's runtime (oracle/build_ref.py, variant md_1m_cuda) -- run as the
+    stock executable on this GPU; numbers are the reference's own timers.  1,048,576 atoms is the largest cube its fixed
+    capacities allow (at 4 M atoms it dies with an out-of-bounds write in determine_ghost_particles: 414 k ghosts against a
+    send capacity of 200 000)."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "md_1m_cuda")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe], cwd=os.path.dirname(exe), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:200]}
+    t = {}
+    for ln in r.stdout.splitlines():
+        k, _, v = ln.partition(": ")
+        try:
+            t[k.strip()] = float(v.split()[0])
+        except (ValueError, IndexError):
+            pass
+    if r.returncode != 0 or "all" not in t:
+        return {"error": r.stdout[-300:]}
+    n, iters = 4 * 64 ** 3, 201                  # timesteps=200 -> 201 loop iterations inside the `all` timer (sim/timestep.py:67-69)
+    return {"value": n * iters / (t["all"] * 1e-3), "unit": UNIT, "atoms": n, "iterations": iters, "ms_per_step": t["all"] / iters,
+            "lennard_jones_ms_per_call": t.get("lennard_jones", 0.0) / iters,
+            "force_kernel_atoms_per_s": n * iters / (t["lennard_jones"] * 1e-3) if t.get("lennard_jones") else None,
+            "what": "reference CUDA target (md.py gpu, generated md.cu + runtime/devices/cuda.cu, nvcc -O3 sm_100a, 1 rank), stock "
+                    "executable, the reference's own timers; same lattice generator, reneighbour every 20"}
+
+
+def ours_at(nx, steps, warmup):
+    """Our path on the same 1 M-atom cube as the reference CUDA target, for a like-for-like ratio."""
+    from pairs_b200 import backend
+    ctx = backend.Context(0)
+    a = pow(4.0 / RHO, 1.0 / 3.0)
+    ctx.init_domain([0.0, nx * a, 0.0, nx * a, 0.0, nx * a])
+    n = ctx.copper_fcc_lattice(nx, nx, nx, RHO, NTYPES)
+    ctx.adjust_thermo(TEMP)
+    ctx.set_lj_params(NTYPES, [1.0] * (NTYPES * NTYPES), [1.0] * (NTYPES * NTYPES))
+    ctx.md_run(0, warmup, DT, CUT, CUT + SKIN, CUT + SKIN, RENEIGH, THERMO)
+    ctx.timers_enable(True)
+    ctx.timers_reset()
+    ctx.stream_timer_start()
+    ctx.md_run(warmup, warmup + steps, DT, CUT, CUT + SKIN, CUT + SKIN, RENEIGH, THERMO)
+    ms = ctx.stream_timer_stop()
+    lj_ms, lj_calls = ctx.timer("lennard_jones")
+    return {"value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps, "lennard_jones_ms_per_call": lj_ms / max(lj_calls, 1)}
+
+
 def cpu_reference_sample(warmup, steps, replicas):
     """Times the reference's own generated serial C++ (oracle/_ref, kind 'reference') or, if that was not built, the
     restatement oracle/pairs_oracle.c (kind 'port') on a bounded 1,000,188-atom sample of the same workload."""
@@ -293,12 +343,19 @@ def run_ours(args):
         cb = cpu_reference_sample(1, 20, 1)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cpu_baseline["host_cores_available"] = os.cpu_count()
+    reference_cuda = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        reference_cuda = reference_cuda_sample()
+        if reference_cuda is not None and "value" in reference_cuda:
+            same = ours_at(64, 200, 20)
+            reference_cuda["ours_same_size"] = same
+            reference_cuda["speedup_same_size"] = same["value"] / reference_cuda["value"]
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "warmup": args.warmup, "config": workload_config(world, nx), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "stages_ms": stages, "atoms_global": n_global,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "stages_ms": stages, "atoms_global": n_global,
                 "nlocal_rank0": nl, "nghost_rank0": ng, "wall_s_timed_region": t_wall, "setup_s": t_setup,
                 "thermo_last": [float(x) for x in thermo[-1]] if len(thermo) else None}
         _JSON_OUT.write(json.dumps(line) + "\n")

@@ -15,11 +15,15 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md_t1     nx=ny=nz=8 (2048 atoms), 100 steps, thermo every step   -> per-step parity dumps
   md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
   dem_t1    examples/dem.py on a 0.1 x 0.015 x 0.04 box (420 spheres + 2 planes), 700 steps, thermo hook every step
+  dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
             -> CPU-baseline sample for bench.py
+
+  md_c1_cuda / md_c2_cuda   the reference's own CUDA target (`md.py gpu`) for configs C1 / C2, an executable for the GPU box:
+            the SECONDARY baseline (bench.py reports it next to the CPU baseline)
 
 Usage: python oracle/build_ref.py [variant ...]    (default: all; no-op if /root/reference is absent)
 """
@@ -61,8 +65,10 @@ def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False):
     return patch
 
 
-def dem_variant(domain, steps, pcap=None):
+def dem_variant(domain, steps, pcap=None, per_cell=False):
     def patch(text):
+        if per_cell:    # build_cell_lists(spacing, store_neighbors_per_cell=True), sim/simulation.py:250-253
+            text = _sub(text, r"^psim\.build_cell_lists\(linkedCellWidth\)", "psim.build_cell_lists(linkedCellWidth, store_neighbors_per_cell=True)")
         if pcap:
             text = _sub(text, r"particle_capacity=\d+", f"particle_capacity={pcap}")
         text = _sub(text, r"^domainSize_SI = \[[^\]]*\]", f"domainSize_SI = [{domain[0]}, {domain[1]}, {domain[2]}]")
@@ -72,6 +78,48 @@ def dem_variant(domain, steps, pcap=None):
         text = _sub(text, r"^psim\.generate\(\)", "psim.compute_thermo(1)\npsim.generate()")
         return text
     return patch
+
+
+# The reference's own CUDA target (SECONDARY baseline of BASELINE.json's north_star): `md.py gpu` -> md.cu, compiled with nvcc for
+# sm_100a together with the reference's runtime/devices/cuda.cu where they lie.  Stock semantics: nvcc's default FMA contraction
+# (the reference's Makefile does not disable it) and its -DENABLE_CUDA_AWARE_MPI; the image has no MPI, with one rank every
+# exchange is a copy inside the process and the MPI stand-in is never reached.  name -> (example script, patch)
+CUDA_VARIANTS = {
+    "md_c1": ("examples/md.py", None),                                                     # 131072 atoms, 200 steps (config C1)
+    "md_c2": ("examples/md.py", lambda t: md_variant(100, 200, 100, 20, pcap=4800000)(t)),   # 4 M atoms, 200 steps (config C2)
+    # 1 M atoms: the largest cube that stays inside the generator's fixed ncells_capacity (100000) and send capacity (200000)
+    "md_1m": ("examples/md.py", lambda t: md_variant(64, 200, 100, 20, pcap=1400000)(t)),
+}
+
+
+def build_cuda_variant(name):
+    import shutil
+    script, patch = CUDA_VARIANTS[name]
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        return "skipped (no nvcc)"
+    gdir = os.path.join(GEN, name + "_cuda")
+    os.makedirs(gdir, exist_ok=True)
+    src_script = os.path.join(REF, script)
+    gen_cu = os.path.join(gdir, "md.cu")
+    exe = os.path.join(OUT, f"{name}_cuda")
+    if newer(exe, [src_script, os.path.join(HERE, "mpi_stub", "mpi.h"), __file__]):
+        return "up to date"
+    text = open(src_script).read()
+    if patch is not None:
+        text = patch(text)
+    scratch_script = os.path.join(gdir, f"md_{name}_input.py")
+    with open(scratch_script, "w") as f:
+        f.write(text)
+    run([sys.executable, scratch_script, "gpu"], cwd=gdir, env=dict(os.environ, PYTHONPATH=os.path.join(REF, "src")))
+    if not os.path.exists(gen_cu):
+        raise RuntimeError(f"generator did not write {gen_cu}")
+    inc = ["-I" + os.path.join(HERE, "mpi_stub"), "-I" + REF, "-I" + os.path.join(REF, "runtime")]
+    srcs = [gen_cu] + [os.path.join(REF, s) for s in ("runtime/pairs.cpp", "runtime/domain/regular_6d_stencil.cpp", "runtime/devices/cuda.cu")]
+    # -DENABLE_CUDA_AWARE_MPI is the reference Makefile's own setting (Makefile:21); with one rank every transfer is then a
+    # device-to-device copy inside the process (the host-staged alternative overruns its size arrays, runtime/pairs.cpp:426)
+    run([nvcc, "-O3", "-w", "-DENABLE_CUDA_AWARE_MPI", "-gencode", "arch=compute_100a,code=sm_100a", *inc, *srcs, "-o", exe])
+    return "built"
 
 
 VARIANTS = {
@@ -84,6 +132,7 @@ VARIANTS = {
     "md_half_t1": ("examples/md.py", md_variant(8, 100, 1, 20, half=True), ["-DREF_IS_MD", "-DREF_HALF_LISTS"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
     "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
+    "dem_cn_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700, per_cell=True), [], False),
     "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),
 }
 
@@ -152,11 +201,14 @@ def main(argv):
     if not os.path.isdir(REF):
         print(f"[oracle/_ref] {REF} not present: keeping prebuilt artefacts")
         return 0
-    names = argv or list(VARIANTS)
+    names = argv or (list(VARIANTS) + [n + "_cuda" for n in CUDA_VARIANTS])
     os.makedirs(GEN, exist_ok=True)
     stage_data()
     for n in names:
-        print(f"[oracle/_ref] {n}: {build_variant(n)}")
+        if n.endswith("_cuda"):
+            print(f"[oracle/_ref] {n}: {build_cuda_variant(n[:-5])}")
+        else:
+            print(f"[oracle/_ref] {n}: {build_variant(n)}")
     return 0
 
 

@@ -376,11 +376,16 @@ class Simulation:
         self.setup_functions.append({"name": func.__name__, "family": family, "roles": roles, "symbols": dict(symbols)})
 
     def build_cell_lists(self, spacing, store_neighbors_per_cell=False):
-        if store_neighbors_per_cell:
-            raise DslError("store_neighbors_per_cell is not implemented (SURVEY.md 8f rank 2)")
+        # store_neighbors_per_cell (sim/cell_lists.py:174-206): the reference then walks one pre-concatenated list per cell
+        # -- cell 0, then the stencil cells in stencil order, i.e. the SAME candidate sequence as its direct stencil walk
+        # (its generated dem.cpp gives identical bits either way, tests/test_oracle_pin.py).  The CUDA kernels traverse the
+        # CSR cell lists directly in that order, so there is nothing to materialise: the flag is accepted and recorded.
+        self._store_neighbors_per_cell = bool(store_neighbors_per_cell)
         self.cell_spacing = spacing
 
     def build_neighbor_lists(self, spacing):
+        assert not getattr(self, "_store_neighbors_per_cell", False), \
+            "Using neighbor-lists with store_neighbors_per_cell option is invalid."      # sim/simulation.py:256-257
         self.cell_spacing = spacing                 # sim/simulation.py:255-261: cells and lists share the spacing
         self.neighbor_cutoff = spacing
 

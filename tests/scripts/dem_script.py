@@ -94,7 +94,7 @@ def gravity(i):
     force[i][2] = force[i][2] - (densityParticle_SI - densityFluid_SI) * volume * gravity_SI
 
 
-def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None):
+def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False):
     diameter_SI, gravity_SI, densityFluid_SI, densityParticle_SI = 0.0029, 9.81, 1000, 2550
     generationSpacing_SI, initialVelocity_SI, dt_SI = 0.005, 1, 5e-5
     frictionCoefficient, restitutionCoefficient, collisionTime_SI, poissonsRatio = 0.5, 0.1, 5e-4, 0.22
@@ -132,7 +132,10 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
     psim.read_particle_data(planes_file or os.path.join(os.path.dirname(os.path.abspath(__file__)), "planes.input"),
                             ['uid', 'type', 'mass', 'position', 'normal', 'flags'], pairs.halfspace())
     psim.setup(update_mass_and_inertia, {'densityParticle_SI': densityParticle_SI, 'pi': math.pi, 'infinity': math.inf})
-    psim.build_cell_lists(linkedCellWidth)
+    if per_cell:
+        psim.build_cell_lists(linkedCellWidth, store_neighbors_per_cell=True)
+    else:
+        psim.build_cell_lists(linkedCellWidth)
     psim.compute(gravity, symbols={'densityParticle_SI': densityParticle_SI, 'densityFluid_SI': densityFluid_SI,
                                    'gravity_SI': gravity_SI, 'pi': math.pi})
     psim.compute(linear_spring_dashpot, linkedCellWidth, symbols={'dt': dt_SI, 'pi': math.pi, 'kappa': kappa,

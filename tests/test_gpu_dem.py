@@ -145,7 +145,8 @@ def test_dem_loop_matches_reference_over_400_steps():
     assert z[f"end_399_num_contacts"].sum() > 100
 
 
-def test_dem_dsl_script_runs_on_gpu_and_matches_reference(capsys):
+@pytest.mark.parametrize("per_cell", [False, True])
+def test_dem_dsl_script_runs_on_gpu_and_matches_reference(capsys, per_cell):
     """The user-facing DEM path: a script against `import pairs` with the kernel bodies of the reference's examples/dem.py ->
     generate() -> CUDA; state after iteration 300 vs the reference's generated C++ (matched through uid)."""
     import os
@@ -153,7 +154,8 @@ def test_dem_dsl_script_runs_on_gpu_and_matches_reference(capsys):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
     import dem_script
     z = dc.gold()
-    psim = dem_script.build("gpu", dc.DOMAIN, 300)
+    # per_cell: build_cell_lists(..., store_neighbors_per_cell=True) -- same traversal, same results in the reference too
+    psim = dem_script.build("gpu", dc.DOMAIN, 300, per_cell=per_cell)
     ctx = psim.generate()
     out = capsys.readouterr().out.splitlines()
     assert out[0] == "DEM Simple-Cubic Grid" and "Number of particles: 420" in out

@@ -160,3 +160,16 @@ def test_multirank_emulation_consistent_with_single_rank():
             p = r.real("position")
             for d in range(3):
                 assert np.all(p[:, d] >= sub[2 * d] - 0.3) and np.all(p[:, d] <= sub[2 * d + 1] + 0.3)
+
+
+@pytest.mark.skipif(not (ref.available("dem_t1") and ref.available("dem_cn_t1")), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_per_cell_neighbor_lists_change_no_bit(tmp_path):
+    """build_cell_lists(..., store_neighbors_per_cell=True) (sim/cell_lists.py:174-206) is a storage variant of the same
+    traversal: the reference's generated dem.cpp produces identical state with and without it.  This is what allows the
+    backend to accept the flag without a second code path."""
+    from oracle import ref_worker
+    keep = [0, 100, 250]
+    a = ref_worker.dump_dem("dem_t1", str(tmp_path / "a.npz"), 251, keep)
+    b = ref_worker.dump_dem("dem_cn_t1", str(tmp_path / "b.npz"), 251, keep)
+    assert sorted(a.files) == sorted(b.files) and len(a.files) > 100
+    assert all(np.array_equal(a[k], b[k]) for k in a.files)

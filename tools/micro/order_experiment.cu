@@ -148,13 +148,58 @@ __global__ void __launch_bounds__(128) k_force(int n, const int *__restrict__ nu
     force[i] = fx; force[n + i] = fy; force[2 * (size_t) n + i] = fz;
 }
 
+// the same kernel with SoA positions (x[], y[], z[]): 16 particles per 128-byte line instead of 4, three 64-bit gathers per neighbour
+__global__ void __launch_bounds__(128) k_force_soa(int n, const int *__restrict__ numneigh, const int *__restrict__ neigh, const double *__restrict__ X,
+                                                   const double *__restrict__ Y, const double *__restrict__ Z, double *__restrict__ force) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const double px = X[i], py = Y[i], pz = Z[i];
+    const int nn = numneigh[i];
+    const int *nb = neigh + (size_t) (i / 32) * T * 32 + (i % 32);
+    double fx = 0, fy = 0, fz = 0;
+    int k = 0;
+    for(; k + 4 <= nn; k += 4) {
+        int j[4]; double qx[4], qy[4], qz[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++) j[u] = __ldg(nb + (size_t) (k + u) * 32);
+#pragma unroll
+        for(int u = 0; u < 4; u++) { qx[u] = __ldg(X + j[u]); qy[u] = __ldg(Y + j[u]); qz[u] = __ldg(Z + j[u]); }
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            double dx = px - qx[u], dy = py - qy[u], dz = pz - qz[u];
+            double r2 = dx * dx + dy * dy + dz * dz;
+            if(r2 < 6.25) {
+                double sr2 = 1.0 / r2, sr6 = sr2 * sr2 * sr2;
+                double f = 48.0 * sr6 * (sr6 - 0.5) * sr2;
+                fx += dx * f; fy += dy * f; fz += dz * f;
+            }
+        }
+    }
+    for(; k < nn; k++) {
+        int j = __ldg(nb + (size_t) k * 32);
+        double dx = px - __ldg(X + j), dy = py - __ldg(Y + j), dz = pz - __ldg(Z + j);
+        double r2 = dx * dx + dy * dy + dz * dz;
+        if(r2 < 6.25) {
+            double sr2 = 1.0 / r2, sr6 = sr2 * sr2 * sr2;
+            double f = 48.0 * sr6 * (sr6 - 0.5) * sr2;
+            fx += dx * f; fy += dy * f; fz += dz * f;
+        }
+    }
+    force[i] = fx; force[n + i] = fy; force[2 * (size_t) n + i] = fz;
+}
+
+__global__ void k_split(int n, const double4 *pos, double *X, double *Y, double *Z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) { double4 p = pos[i]; X[i] = p.x; Y[i] = p.y; Z[i] = p.z; }
+}
+
 // distinct 128-byte lines per warp-wide gather
 __global__ void __launch_bounds__(128) k_lines(int n, const int *__restrict__ numneigh, const int *__restrict__ neigh, unsigned long long *stats) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int nn = (i < n) ? numneigh[i] : 0;
     const int *nb = neigh + (size_t) (i / 32) * T * 32 + (i % 32);
     int lane = threadIdx.x & 31;
-    unsigned long long lines = 0, gathers = 0;
+    unsigned long long lines = 0, gathers = 0, lines16 = 0;
     for(int k = 0; k < T; k++) {
         unsigned act = __ballot_sync(0xffffffffu, k < nn);
         if(act == 0) break;
@@ -162,11 +207,14 @@ __global__ void __launch_bounds__(128) k_lines(int n, const int *__restrict__ nu
             int j = nb[(size_t) k * 32];
             unsigned m = __match_any_sync(act, j >> 2);
             if(__ffs(m) - 1 == lane) lines++;
+            unsigned m2 = __match_any_sync(act, j >> 4);
+            if(__ffs(m2) - 1 == lane) lines16++;
             if(__ffs(act) - 1 == lane) gathers++;
         }
     }
     atomicAdd(stats, lines);
     atomicAdd(stats + 1, gathers);
+    atomicAdd(stats + 2, lines16);
 }
 
 int main(int argc, char **argv) {
@@ -193,7 +241,8 @@ int main(int argc, char **argv) {
     thrust::device_vector<int> cell_start(nc * nc * nc + 1);
     thrust::device_vector<int> neigh((size_t) ((n + 31) / 32) * T * 32);
     thrust::device_vector<double> force(3 * (size_t) n);
-    thrust::device_vector<unsigned long long> stats(2);
+    thrust::device_vector<unsigned long long> stats(3);
+    thrust::device_vector<double> X(n), Y(n), Z(n);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     printf("n = %d, L = %.3f, coarse cells %d^3\n", n, L, nc);
@@ -213,8 +262,8 @@ int main(int argc, char **argv) {
         thrust::fill(stats.begin(), stats.end(), 0ULL);
         k_lines<<<(n + 127) / 128, 128>>>(n, thrust::raw_pointer_cast(numneigh.data()), thrust::raw_pointer_cast(neigh.data()), thrust::raw_pointer_cast(stats.data()));
         CK(cudaDeviceSynchronize());
-        unsigned long long hs[2];
-        cudaMemcpy(hs, thrust::raw_pointer_cast(stats.data()), 16, cudaMemcpyDeviceToHost);
+        unsigned long long hs[3];
+        cudaMemcpy(hs, thrust::raw_pointer_cast(stats.data()), 24, cudaMemcpyDeviceToHost);
         long long tot = thrust::reduce(numneigh.begin(), numneigh.end(), 0LL);
         for(int w = 0; w < 3; w++) k_force<<<(n + 127) / 128, 128>>>(n, thrust::raw_pointer_cast(numneigh.data()), thrust::raw_pointer_cast(neigh.data()), thrust::raw_pointer_cast(pos.data()), thrust::raw_pointer_cast(force.data()));
         cudaEventRecord(e0);
@@ -225,8 +274,17 @@ int main(int argc, char **argv) {
         float ms;
         cudaEventElapsedTime(&ms, e0, e1);
         double fsum = thrust::reduce(force.begin(), force.end(), 0.0);
-        printf("mode %d: mean neighbours %.2f, lines per warp gather %.2f, force kernel %.4f ms (%.3e atoms/s), checksum %.6e\n", mode,
-               tot / (double) n, hs[0] / (double) hs[1], ms / R, n / (ms / R * 1e-3), fsum);
+        k_split<<<(n + 255) / 256, 256>>>(n, thrust::raw_pointer_cast(pos.data()), thrust::raw_pointer_cast(X.data()), thrust::raw_pointer_cast(Y.data()), thrust::raw_pointer_cast(Z.data()));
+        for(int w = 0; w < 3; w++) k_force_soa<<<(n + 127) / 128, 128>>>(n, thrust::raw_pointer_cast(numneigh.data()), thrust::raw_pointer_cast(neigh.data()), thrust::raw_pointer_cast(X.data()), thrust::raw_pointer_cast(Y.data()), thrust::raw_pointer_cast(Z.data()), thrust::raw_pointer_cast(force.data()));
+        cudaEventRecord(e0);
+        for(int r = 0; r < R; r++) k_force_soa<<<(n + 127) / 128, 128>>>(n, thrust::raw_pointer_cast(numneigh.data()), thrust::raw_pointer_cast(neigh.data()), thrust::raw_pointer_cast(X.data()), thrust::raw_pointer_cast(Y.data()), thrust::raw_pointer_cast(Z.data()), thrust::raw_pointer_cast(force.data()));
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms2;
+        cudaEventElapsedTime(&ms2, e0, e1);
+        double fsum2 = thrust::reduce(force.begin(), force.end(), 0.0);
+        printf("mode %d: mean neighbours %.2f, lines per warp gather %.2f (AoS 32 B) / %.2f (SoA 8 B), force kernel AoS %.4f ms (%.3e atoms/s), SoA %.4f ms (%.3e atoms/s), checksums %.3e %.3e\n", mode,
+               tot / (double) n, hs[0] / (double) hs[1], hs[2] / (double) hs[1], ms / R, n / (ms / R * 1e-3), ms2 / R, n / (ms2 / R * 1e-3), fsum, fsum2);
     }
     return 0;
 }
