@@ -15,6 +15,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md_t1     nx=ny=nz=8 (2048 atoms), 100 steps, thermo every step   -> per-step parity dumps
   md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
   dem_t1    examples/dem.py on a 0.1 x 0.015 x 0.04 box (420 spheres + 2 planes), 700 steps, thermo hook every step
+  dem_vtk_t1 dem_t1 for 60 steps with the example's psim.vtk_output(..., frequency) kept, writing every 30 iterations
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
@@ -65,15 +66,18 @@ def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False):
     return patch
 
 
-def dem_variant(domain, steps, pcap=None, per_cell=False):
+def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None):
     def patch(text):
+        if vtk_every is not None:     # keep psim.vtk_output(...) (runtime/vtk.hpp) and write every `vtk_every` iterations
+            text = _sub(text, r"^visSpacing = \d+", f"visSpacing = {vtk_every}")
         if per_cell:    # build_cell_lists(spacing, store_neighbors_per_cell=True), sim/simulation.py:250-253
             text = _sub(text, r"^psim\.build_cell_lists\(linkedCellWidth\)", "psim.build_cell_lists(linkedCellWidth, store_neighbors_per_cell=True)")
         if pcap:
             text = _sub(text, r"particle_capacity=\d+", f"particle_capacity={pcap}")
         text = _sub(text, r"^domainSize_SI = \[[^\]]*\]", f"domainSize_SI = [{domain[0]}, {domain[1]}, {domain[2]}]")
         text = _sub(text, r"^timeSteps = \d+", f"timeSteps = {steps}")
-        text = _sub(text, r"^psim\.vtk_output\(", "#psim.vtk_output(")          # debug output, out of scope
+        if vtk_every is None:
+            text = _sub(text, r"^psim\.vtk_output\(", "#psim.vtk_output(")      # no files from the parity / timing variants
         # one compute_thermo call per iteration = the harness hook that exposes nlocal and the per-step state
         text = _sub(text, r"^psim\.generate\(\)", "psim.compute_thermo(1)\npsim.generate()")
         return text
@@ -133,6 +137,7 @@ VARIANTS = {
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
     "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
     "dem_cn_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700, per_cell=True), [], False),
+    "dem_vtk_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 60, vtk_every=30), [], False),
     "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),
 }
 

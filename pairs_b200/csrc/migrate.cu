@@ -1,8 +1,9 @@
 // Particle migration between ranks: the multi-rank branch of Comm.exchange (sim/comm.py:100-151) for one
 // dimension.  Reference: determine_exchange_particles (atomics) -> pack -> remove_exchanged_particles pt1 (HOST loop)
-// + pt2 (hole filling from the tail) -> MPI -> unpack (append).  Here: ordered select of the leavers, pack, an
-// ordered stream compaction of the stayers (device only, no host loop), NCCL, append.  The resulting SET of local
-// particles per rank is the reference's; their order is ours (and is replaced by cell order right afterwards).
+// + pt2 (hole filling from the tail) -> MPI -> unpack (append).  Here: ordered select of the leavers, pack, a
+// DETERMINISTIC hole filling (k-th staying particle of the tail into the k-th freed slot; device only, no host loop,
+// no atomics), transport, append.  The resulting SET of local particles per rank is the reference's; their order is
+// ours (MD: replaced by cell order right afterwards; DEM: kept, contact rows move with the particle).
 #include <algorithm>
 
 #include "ctx.cuh"
@@ -67,30 +68,6 @@ __global__ void __launch_bounds__(256) pb_k_pack_exchange(int n, int cap, int st
     b[11] = (double) tag[i];
 }
 
-__global__ void __launch_bounds__(256) pb_k_compact(int n, int cap, const int *__restrict__ stay, const int *__restrict__ scan,
-                                                    const double4 *__restrict__ pos, double4 *__restrict__ pos_o,
-                                                    const double *__restrict__ vel, double *__restrict__ vel_o,
-                                                    const double *__restrict__ mass, double *__restrict__ mass_o,
-                                                    const int *__restrict__ type, int *__restrict__ type_o,
-                                                    const int *__restrict__ flags, int *__restrict__ flags_o,
-                                                    const int *__restrict__ uid, int *__restrict__ uid_o,
-                                                    const int *__restrict__ shape, int *__restrict__ shape_o,
-                                                    const int *__restrict__ tag, int *__restrict__ tag_o) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n || !stay[i]) { return; }
-    const int k = scan[i];
-    pos_o[k] = pos[i];
-    vel_o[k] = vel[i];
-    vel_o[cap + k] = vel[cap + i];
-    vel_o[2 * cap + k] = vel[2 * cap + i];
-    mass_o[k] = mass[i];
-    type_o[k] = type[i];
-    flags_o[k] = flags[i];
-    uid_o[k] = uid[i];
-    shape_o[k] = shape[i];
-    tag_o[k] = tag[i];
-}
-
 __global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0, int cap, int stride, const double *__restrict__ buf,
                                                             double4 *__restrict__ pos, double *__restrict__ vel,
                                                             double *__restrict__ mass, int *__restrict__ type, int *__restrict__ flags,
@@ -112,7 +89,7 @@ __global__ void __launch_bounds__(256) pb_k_unpack_exchange(int count, int dst0,
     tag[p] = (int) b[11];
 }
 
-// ---- hole filling (DEM mode: per-particle state is large, leavers are few) ------------------------------------------------
+// ---- hole filling (leavers are few: ~0.5 % of the particles per reneighbouring; a full compaction would move everything) ----
 // new_n = n - L.  Holes = leavers below new_n, fillers = stayers at or above new_n; both in ascending order, k-th filler -> k-th
 // hole (deterministic).  rank_leave = scan_lo + scan_hi is the number of leavers before an index.
 __global__ void __launch_bounds__(256) pb_k_hole_list(int n, int new_n, const int *__restrict__ stay, const int *__restrict__ scan_lo,
@@ -183,7 +160,7 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
     ctx->recv_offsets[j0] = 0;
     ctx->recv_offsets[j1] = ctx->nrecv[j0];
     const int nr = ctx->nrecv[j0] + ctx->nrecv[j1];
-    if(ctx->dem && n > 0 && c_stay < n) {
+    if(n > 0 && c_stay < n) {
         // hole filling: k-th stayer of the tail [c_stay, n) moves into the k-th leaver slot below c_stay
         int *hole_idx = ctx->cell_key, *fill_idx = ctx->particle_cell;          // [pcap] scratch, free during exchange
         PB_LAUNCH(pb_k_hole_list, pb_blocks(n, 256), 256, n, c_stay, stay, scan_lo, scan_hi, hole_idx, fill_idx);
@@ -193,20 +170,8 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
         if(nholes > 0) {
             PB_LAUNCH(pb_k_move_base, pb_blocks(nholes, 256), 256, nholes, ctx->pcap, fill_idx, hole_idx, ctx->pos, ctx->vel, ctx->mass, ctx->type,
                       ctx->flags, ctx->uid, ctx->shape, ctx->tag);
-            PB_TRY(pb_dem_move(ctx, nholes, fill_idx, hole_idx));
+            if(ctx->dem) { PB_TRY(pb_dem_move(ctx, nholes, fill_idx, hole_idx)); }
         }
-    } else if(n > 0 && c_stay < n) {
-        PB_LAUNCH(pb_k_compact, pb_blocks(n, 256), 256, n, ctx->pcap, stay, scan_stay, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
-                  ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape,
-                  ctx->shape_alt, ctx->tag, ctx->tag_alt);
-        std::swap(ctx->pos, ctx->pos_alt);
-        std::swap(ctx->vel, ctx->vel_alt);
-        std::swap(ctx->mass, ctx->mass_alt);
-        std::swap(ctx->type, ctx->type_alt);
-        std::swap(ctx->flags, ctx->flags_alt);
-        std::swap(ctx->uid, ctx->uid_alt);
-        std::swap(ctx->shape, ctx->shape_alt);
-        std::swap(ctx->tag, ctx->tag_alt);
     }
     // grow only now: the selection / scan scratch above is re-allocated (not kept) by a capacity change
     ctx->nlocal = c_stay;

@@ -260,6 +260,8 @@ class Simulation:
         self._target = None
         self._partitioner = DomainPartitioners.Regular
         self._compute_half = False
+        self.vtk_file = None
+        self.vtk_frequency = 0
         self._pbc = [True, True, True]
         self.grid = None
         self.reneighbor_frequency = 1            # sim/simulation.py:89
@@ -338,7 +340,20 @@ class Simulation:
         self._compute_thermo = every
 
     def vtk_output(self, filename, frequency=0):
-        self.vtk_file = filename                   # VTK output is out of scope (debug output); ignored
+        """sim/simulation.py:365-367: <filename>_local_<ts>.vtk and <filename>_ghost_<ts>.vtk after every iteration whose
+        number is a multiple of `frequency` (every iteration for 0), written by vtk_write (runtime/vtk.hpp:11-86)."""
+        self.vtk_file = filename
+        self.vtk_frequency = frequency
+
+    def _vtk_due(self, ts):
+        return self.vtk_file is not None and (self.vtk_frequency == 0 or ts % self.vtk_frequency == 0)
+
+    def _vtk_write(self, ctx, ts, rank, world):
+        nl, ng = ctx.counts()
+        pos, mass, flags = ctx.real("position", True), ctx.real("mass", True), ctx.ints("flags", True)
+        infix = f"r{rank}_" if world > 1 else ""
+        vtk_write(f"{self.vtk_file}_local_{infix}{ts}.vtk", pos[:nl], mass[:nl], flags[:nl])
+        vtk_write(f"{self.vtk_file}_ghost_{infix}{ts}.vtk", pos[nl:nl + ng], mass[nl:nl + ng], flags[nl:nl + ng])
 
     def copper_fcc_lattice(self, nx, ny, nz, rho, temperature, ntypes):
         lattice = pow((4.0 / rho), (1.0 / 3.0))    # sim/copper_fcc_lattice.py:19-23
@@ -464,9 +479,16 @@ class Simulation:
         t0 = time.perf_counter()
         nsteps = self.ntimesteps + 1
         if native is not None:
-            th = ctx.md_run(0, nsteps, *native)
-            for row in th:
-                self._thermo_line(rank, int(row[0]), row[1], row[2])
+            # one native call per stretch between two VTK dumps (chunked calls are bit-identical to one call)
+            cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
+            begin = 0
+            for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
+                th = ctx.md_run(begin, end, *native)
+                for row in th:
+                    self._thermo_line(rank, int(row[0]), row[1], row[2])
+                if self._vtk_due(end - 1):
+                    self._vtk_write(ctx, end - 1, rank, world)
+                begin = end
         else:
             self._python_loop(ctx, plan_pre, plan_fn, nsteps, rank)
         ctx.sync()
@@ -530,7 +552,14 @@ class Simulation:
         ctx.timers_enable(True)
         ctx.sync()
         t0 = time.perf_counter()
-        ctx.dem_run(self.cell_spacing, 0, self.ntimesteps + 1)
+        nsteps = self.ntimesteps + 1
+        cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
+        begin = 0
+        for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
+            ctx.dem_run(self.cell_spacing, begin, end)
+            if self._vtk_due(end - 1):
+                self._vtk_write(ctx, end - 1, rank, world)
+            begin = end
         ctx.sync()
         all_ms = (time.perf_counter() - t0) * 1e3
         self._print_summary(ctx, all_ms, rank)
@@ -647,6 +676,8 @@ class Simulation:
             if self._compute_thermo > 0 and (((ts + 1) % self._compute_thermo) == 0 or ts == 0):
                 t, p = ctx.compute_thermo()
                 self._thermo_line(rank, ts, t, p)
+            if self._vtk_due(ts):
+                self._vtk_write(ctx, ts, rank, int(os.environ.get("WORLD_SIZE", 1)))
 
     def _thermo_line(self, rank, ts, t, p):
         self.thermo_log.append((ts, t, p))
@@ -694,6 +725,33 @@ class Simulation:
         ctx.upload(pos, arrays.get(vel_name), arrays.get("mass"), arrays.get("type"), arrays.get("flags"), arrays.get("uid"),
                    np.full(len(pos), shape_id, np.int32))
         return len(pos)
+
+
+def vtk_write(path, position, mass, flags):
+    """runtime/vtk.hpp:11-86, byte for byte: legacy ASCII unstructured grid of vertices, fixed notation with 8 decimals, INFINITE
+    particles left out -- while the CELLS section keeps the index a particle has in the written range (vtk.hpp:57-61).  If the
+    file cannot be opened nothing is written (vtk.hpp:42), e.g. when the output directory does not exist."""
+    keep = (np.asarray(flags) & 1) == 0
+    n = int(keep.sum())
+    try:
+        f = open(path, "w")
+    except OSError:
+        return False
+    with f:
+        f.write("# vtk DataFile Version 2.0\nParticle data\nASCII\nDATASET UNSTRUCTURED_GRID\n")
+        f.write(f"POINTS {n} double\n")
+        f.write("".join("%.8f %.8f %.8f\n" % (p[0], p[1], p[2]) for p in np.asarray(position)[keep]))
+        f.write("\n\n")
+        f.write(f"CELLS {n} {n * 2}\n")
+        f.write("".join(f"1 {i}\n" for i in np.nonzero(keep)[0]))
+        f.write("\n\n")
+        f.write(f"CELL_TYPES {n}\n")
+        f.write("1\n" * n)
+        f.write("\n\n")
+        f.write(f"POINT_DATA {n}\nSCALARS mass double\nLOOKUP_TABLE default\n")
+        f.write("".join("%.8f\n" % m for m in np.asarray(mass)[keep]))
+        f.write("\n\n")
+    return True
 
 
 def _broadcast_nccl_id(backend, rank, world):

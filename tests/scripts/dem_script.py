@@ -94,7 +94,7 @@ def gravity(i):
     force[i][2] = force[i][2] - (densityParticle_SI - densityFluid_SI) * volume * gravity_SI
 
 
-def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False):
+def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None):
     diameter_SI, gravity_SI, densityFluid_SI, densityParticle_SI = 0.0029, 9.81, 1000, 2550
     generationSpacing_SI, initialVelocity_SI, dt_SI = 0.005, 1, 5e-5
     frictionCoefficient, restitutionCoefficient, collisionTime_SI, poissonsRatio = 0.5, 0.1, 5e-4, 0.22
@@ -136,6 +136,8 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
         psim.build_cell_lists(linkedCellWidth, store_neighbors_per_cell=True)
     else:
         psim.build_cell_lists(linkedCellWidth)
+    if vtk is not None:
+        psim.vtk_output(vtk[0], frequency=vtk[1])          # examples/dem.py:194
     psim.compute(gravity, symbols={'densityParticle_SI': densityParticle_SI, 'densityFluid_SI': densityFluid_SI,
                                    'gravity_SI': gravity_SI, 'pi': math.pi})
     psim.compute(linear_spring_dashpot, linkedCellWidth, symbols={'dt': dt_SI, 'pi': math.pi, 'kappa': kappa,

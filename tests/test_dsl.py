@@ -4,6 +4,7 @@ import importlib.util
 import os
 import sys
 
+import numpy as np
 import pytest
 
 import pairs
@@ -131,3 +132,29 @@ def test_legacy_api_of_lj_onetype():
     a = pow(4.0 / 0.8442, 1.0 / 3.0)
     assert psim.grid == [0.0, 0.0, 0.0, 6 * a, 6 * a, 6 * a] and psim.setups[0][0] == "copper_fcc_lattice"
     assert psim.functions[0]["symbols"] == {"sigma6": 1.0, "epsilon": 1.0}
+
+
+def test_vtk_writer_reproduces_reference_file_bytes(tmp_path):
+    """vtk_write against a file runtime/vtk.hpp wrote (tests/golden/dem_vtk_t1_local_0.vtk, reference run of examples/dem.py):
+    parse the golden back into arrays, write them again, compare the bytes -- format, precision, INFINITE filtering, CELLS ids."""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dem_vtk_t1_local_0.vtk")
+    lines = open(gold).read().split("\n")
+    n = int(lines[4].split()[1])
+    pos = np.array([[float(x) for x in ln.split()] for ln in lines[5:5 + n]])
+    k = lines.index(f"CELLS {n} {2 * n}")
+    ids = [int(ln.split()[1]) for ln in lines[k + 1:k + 1 + n]]
+    m0 = lines.index("LOOKUP_TABLE default")
+    mass = np.array([float(x) for x in lines[m0 + 1:m0 + 1 + n]])
+    # the reference's range held 422 particles: 420 spheres followed by the two INFINITE planes, which it skips
+    assert n == 420 and ids == list(range(420))
+    position = np.vstack([pos, [[0.0, 0.0, 0.0], [0.8, 0.015, 0.2]]])
+    masses = np.concatenate([mass, [1.0, 1.0]])
+    flags = np.array([0] * 420 + [13, 13], np.int32)
+    out = tmp_path / "again.vtk"
+    assert dsl.vtk_write(str(out), position, masses, flags)
+    assert open(out, "rb").read() == open(gold, "rb").read()
+    # INFINITE particles in the middle keep their slot number in CELLS (runtime/vtk.hpp:57-61)
+    assert dsl.vtk_write(str(out), position[[0, 420, 1]], masses[[0, 420, 1]], flags[[0, 420, 1]])
+    txt = open(out).read()
+    assert "POINTS 2 double" in txt and "CELLS 2 4\n1 0\n1 2\n" in txt
+    assert not dsl.vtk_write(str(tmp_path / "missing_dir" / "x.vtk"), position, masses, flags)
