@@ -160,6 +160,21 @@ def ours_at(nx, steps, warmup):
     return {"value": n * steps / (ms * 1e-3), "ms_per_step": ms / steps, "lennard_jones_ms_per_call": lj_ms / max(lj_calls, 1)}
 
 
+def dem_sample():
+    """Second workload of BASELINE.json (configs[2]): examples/dem.py scaled to 998,400 spheres + 2 half-spaces on one GPU,
+    particle-steps/s while falling and after settling into contact (tools/bench_dem.py, run as its own process so that its
+    contexts do not share state with the timed LJ run), next to the reference's serial C++ on one host core."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_dem.py"), "6000"], cwd=ROOT, stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True, timeout=240)
+        if r.returncode != 0:
+            return {"error": r.stderr[-300:]}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:      # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
 def cpu_reference_sample(warmup, steps, replicas):
     """Times the reference's own generated serial C++ (oracle/_ref, kind 'reference') or, if that was not built, the
     restatement oracle/pairs_oracle.c (kind 'port') on a bounded 1,000,188-atom sample of the same workload."""
@@ -351,11 +366,15 @@ def run_ours(args):
             reference_cuda["ours_same_size"] = same
             reference_cuda["speedup_same_size"] = same["value"] / reference_cuda["value"]
 
+    dem = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_dem:
+        dem = dem_sample()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "warmup": args.warmup, "config": workload_config(world, nx), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "stages_ms": stages, "atoms_global": n_global,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "dem": dem, "stages_ms": stages, "atoms_global": n_global,
                 "nlocal_rank0": nl, "nghost_rank0": ng, "wall_s_timed_region": t_wall, "setup_s": t_setup,
                 "thermo_last": [float(x) for x in thermo[-1]] if len(thermo) else None}
         _JSON_OUT.write(json.dumps(line) + "\n")
@@ -379,6 +398,7 @@ def main():
     ap.add_argument("--nx", type=int, default=100, help="FCC cells per GPU and dimension (100 -> 4M atoms: BASELINE configs[1])")
     ap.add_argument("--ref-replicas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dem", action="store_true", help="skip the secondary DEM workload (tools/bench_dem.py)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -67,6 +67,7 @@ struct pb_ctx {
     int *type = nullptr, *type_alt = nullptr, *flags = nullptr, *flags_alt = nullptr;
     int *uid = nullptr, *uid_alt = nullptr, *shape = nullptr, *shape_alt = nullptr, *tag = nullptr, *tag_alt = nullptr;
     bool ghosts_in_alt = false;   // after a fused initial_integrate: ghosts of the last refresh still live in pos_alt
+    int dem_sort_every = 200;     // DEM: re-sort the locals into cell order every so many iterations (0 = never; option "dem_sort_every")
     bool half_lists = false;      // compute_half(): lists hold j with i < j only, the force kernel updates both partners
     bool fuse_integrate = true;   // pb_md_run folds the integrator halves into the force kernel's epilogue
     bool force_is_zero = false;   // reset_volatile requested and not yet materialised (fused into the force kernel)
@@ -174,6 +175,8 @@ int pb_ensure_send_capacity(pb_ctx *ctx, int needed);
 int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n);   // out[0..n], out[n] = total
 int pb_bin_particles(pb_ctx *ctx, int first, int n, bool write_particle_cell);
 int pb_dem_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used);
+int pb_dem_sort_locals(pb_ctx *ctx);
+int pb_sort_locals(pb_ctx *ctx);
 template<typename T> int pb_regrow(pb_ctx *ctx, T **p, size_t old_count, size_t new_count, bool keep);
 int pb_regrow_soa(pb_ctx *ctx, double **p, int comps, size_t old_cap, size_t new_cap, size_t used, bool keep);
 

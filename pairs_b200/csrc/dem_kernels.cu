@@ -449,6 +449,83 @@ int pb_dem_move(pb_ctx *ctx, int count, const int *src_idx, const int *dst_idx) 
     return 0;
 }
 
+// ---- spatial re-sort of the locals --------------------------------------------------------------------------------------
+// dem.py rebuilds its cell lists every iteration but never reorders particles; after the bed has mixed, a particle's 27
+// stencil cells point all over memory (ncu, settled 1 M-sphere bed: 6.6 % L1 hit rate in the detection kernel, L2 at 72 %).
+// Every `dem_sort_every` iterations the locals are therefore put into cell order, each DEM property and the whole contact
+// table travelling with its particle: 109 double rows and 61 int rows of [pcap] are gathered through the permutation, six rows
+// at a time, into the (volatile, currently unused) force / torque arrays and copied back -- about 1 ms per million particles,
+// i.e. ~1 % of the step time at the default interval.  Only the ORDER in which a particle meets its partners changes.
+__global__ void __launch_bounds__(256) pb_k_gather_rows_f64(int n, size_t cap, const int *__restrict__ perm, const double *__restrict__ src,
+                                                            double *__restrict__ dst) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= n) { return; }
+    const size_t row = blockIdx.y;
+    dst[row * cap + k] = src[row * cap + perm[k]];
+}
+
+__global__ void __launch_bounds__(256) pb_k_gather_rows_i32(int n, size_t cap, const int *__restrict__ perm, const int *__restrict__ src,
+                                                            int *__restrict__ dst) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= n) { return; }
+    const size_t row = blockIdx.y;
+    dst[row * cap + k] = src[row * cap + perm[k]];
+}
+
+static int pb_permute_f64(pb_ctx *ctx, double *base, int rows, const int *perm, int n) {
+    const size_t cap = (size_t) ctx->pcap;
+    for(int r0 = 0; r0 < rows; r0 += 3) {
+        const int c = std::min(3, rows - r0);
+        double *scratch = ctx->force;           // [3][pcap]
+        pb_k_gather_rows_f64<<<dim3(pb_blocks(n, 256), c), 256, 0, ctx->stream>>>(n, cap, perm, base + (size_t) r0 * cap, scratch);
+        ctx->launches++;
+        PB_CHECK(cudaGetLastError());
+        PB_CHECK(cudaMemcpy2DAsync(base + (size_t) r0 * cap, cap * sizeof(double), scratch, cap * sizeof(double), (size_t) n * sizeof(double), c,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+static int pb_permute_i32(pb_ctx *ctx, int *base, int rows, const int *perm, int n) {
+    const size_t cap = (size_t) ctx->pcap;
+    int *scratch = (int *) ctx->torque;          // [3][pcap] doubles = 6 int rows
+    for(int r0 = 0; r0 < rows; r0 += 6) {
+        const int c = std::min(6, rows - r0);
+        pb_k_gather_rows_i32<<<dim3(pb_blocks(n, 256), c), 256, 0, ctx->stream>>>(n, cap, perm, base + (size_t) r0 * cap, scratch);
+        ctx->launches++;
+        PB_CHECK(cudaGetLastError());
+        PB_CHECK(cudaMemcpy2DAsync(base + (size_t) r0 * cap, cap * sizeof(int), scratch, cap * sizeof(int), (size_t) n * sizeof(int), c,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+// called between exchange and borders (no ghosts exist); force / torque hold nothing that is still needed (volatile, reset
+// before the next evaluation)
+int pb_dem_sort_locals(pb_ctx *ctx) {
+    const int n = ctx->nlocal;
+    if(n == 0) { return 0; }
+    PbStage st(ctx, "dem_sort");
+    PB_TRY(pb_sort_locals(ctx));                 // base arrays; leaves the permutation (new index -> old index) in cell_list
+    const int *perm = ctx->cell_list;
+    const int C = ctx->ccontacts;
+    PB_TRY(pb_permute_f64(ctx, ctx->radius, 1, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->angvel, 3, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->normal, 3, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->inv_inertia, 9, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->rotmat, 9, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->quat, 4, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->contact_tsd, 3 * C, perm, n));
+    PB_TRY(pb_permute_f64(ctx, ctx->contact_ivm, C, perm, n));
+    PB_TRY(pb_permute_i32(ctx, ctx->num_contacts, 1, perm, n));
+    PB_TRY(pb_permute_i32(ctx, ctx->contact_uid, C, perm, n));
+    PB_TRY(pb_permute_i32(ctx, ctx->contact_used, C, perm, n));
+    PB_TRY(pb_permute_i32(ctx, ctx->contact_stick, C, perm, n));
+    ctx->force_is_zero = true;                   // the scratch rows are garbage now: make sure they are cleared before use
+    ctx->cells_n = 0;
+    return 0;
+}
+
 // ---- kernels ----------------------------------------------------------------------------------------------------
 // update_mass_and_inertia (examples/dem.py:6-15): runs once over all locals (a setup() function: no FIXED filter)
 __global__ void __launch_bounds__(256) pb_k_dem_update_mass_inertia(int n, int cap, const int *__restrict__ shape, double *__restrict__ mass,
@@ -768,6 +845,7 @@ extern "C" int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts
     if(!ctx->cells_set || ctx->spacing != cell_spacing) { PB_TRY(pb_setup_cells(ctx, cell_spacing)); }
     for(int ts = ts_begin; ts < ts_end; ts++) {
         PB_TRY(pb_exchange(ctx));
+        if(ctx->dem_sort_every > 0 && ts > 0 && ts % ctx->dem_sort_every == 0) { PB_TRY(pb_dem_sort_locals(ctx)); }
         PB_TRY(pb_borders(ctx));
         PB_TRY(pb_build_cell_lists(ctx));
         PB_TRY(pb_dem_reset_contact_usage(ctx));
