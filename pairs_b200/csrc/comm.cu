@@ -32,49 +32,140 @@ struct PbBox {
 };
 
 // ---- selection ---------------------------------------------------------------------------------------------
-// sim/domain_partitioning.py:31-65: side 0 -> pos < min + offset, side 1 -> pos > max - offset; INFINITE/GLOBAL skipped
-__global__ void __launch_bounds__(256) pb_k_select(int n, int dim, int side, double bound, const double4 *__restrict__ pos,
-                                                   const int *__restrict__ flags, int *__restrict__ sel) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n) { return; }
-    int hit = 0;
-    if((flags[i] & (PB_FLAG_INFINITE | PB_FLAG_GLOBAL)) == 0) {
+// sim/domain_partitioning.py:31-65: side 0 -> pos < min + offset, side 1 -> pos > max - offset; INFINITE/GLOBAL skipped.
+// Both sides of a dimension are selected in ONE ordered stream compaction: per-block counts -> scan of the block counts
+// (one block) -> scatter that re-evaluates the predicate and ranks inside the block with ballots.  Four launches and one
+// read-back per dimension (the reference needs the two counts on the host too, for its MPI message sizes).
+static const int SEL_T = 256;
+
+__device__ __forceinline__ void pb_sel_flags(int i, int n, int dim, int on_lo, int on_hi, double b_lo, double b_hi,
+                                             const double4 *__restrict__ pos, const int *__restrict__ flags, int *lo, int *hi) {
+    *lo = 0; *hi = 0;
+    if(i < n && (flags[i] & (PB_FLAG_INFINITE | PB_FLAG_GLOBAL)) == 0) {
         const double4 p = pos[i];
         const double x = (dim == 0) ? p.x : ((dim == 1) ? p.y : p.z);
-        hit = (side == 0) ? (x < bound) : (x > bound);
+        *lo = on_lo && (x < b_lo);
+        *hi = on_hi && (x > b_hi);
     }
-    sel[i] = hit;
 }
 
-__global__ void __launch_bounds__(256) pb_k_scatter_sel(int n, int dim, int mult, int base, const int *__restrict__ sel,
-                                                        const int *__restrict__ scan, int *__restrict__ send_map,
-                                                        int *__restrict__ send_mult) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n || sel[i] == 0) { return; }
-    const int k = base + scan[i];
-    send_map[k] = i;
-    send_mult[k * 3 + 0] = (dim == 0) ? mult : 0;
-    send_mult[k * 3 + 1] = (dim == 1) ? mult : 0;
-    send_mult[k * 3 + 2] = (dim == 2) ? mult : 0;
+__global__ void __launch_bounds__(SEL_T) pb_k_sel2_count(int n, int nblocks, int dim, int on_lo, int on_hi, double b_lo, double b_hi,
+                                                         const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                         int *__restrict__ block_counts) {
+    const int i = blockIdx.x * SEL_T + threadIdx.x;
+    int lo, hi;
+    pb_sel_flags(i, n, dim, on_lo, on_hi, b_lo, b_hi, pos, flags, &lo, &hi);
+    const int c_lo = __syncthreads_count(lo), c_hi = __syncthreads_count(hi);
+    if(threadIdx.x == 0) { block_counts[blockIdx.x] = c_lo; block_counts[nblocks + blockIdx.x] = c_hi; }
 }
 
-// Appends the particles of [0, n) selected for (dim, side) to the send lists; returns their number in *count.
-static int pb_select_side(pb_ctx *ctx, int n, int dim, int side, double offset, int *count) {
-    *count = 0;
-    const int j = dim * 2 + side;
-    if(n == 0 || (!ctx->pbc_flag[dim] && ctx->pbc[j] != 0)) { return 0; }
-    const double bound = (side == 0) ? (ctx->subdom[j] + offset) : (ctx->subdom[j] - offset);
-    PB_LAUNCH(pb_k_select, pb_blocks(n, 256), 256, n, dim, side, bound, ctx->pos, ctx->flags, ctx->sel_flag);
-    PB_TRY(pb_exclusive_scan(ctx, ctx->sel_flag, ctx->sel_scan, n));
-    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->sel_scan + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    const int c = ctx->h_scalars[0];
-    if(c > 0) {
-        PB_TRY(pb_ensure_send_capacity(ctx, ctx->nsend_all + c));
-        PB_LAUNCH(pb_k_scatter_sel, pb_blocks(n, 256), 256, n, dim, ctx->pbc[j], ctx->nsend_all, ctx->sel_flag, ctx->sel_scan,
-                  ctx->send_map, ctx->send_mult);
+// one block per side: in-place exclusive scan of that side's block counts, total -> totals[side]
+__global__ void __launch_bounds__(1024) pb_k_sel2_scan(int nblocks, int *__restrict__ block_counts, int *__restrict__ totals) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    int *c = block_counts + (size_t) blockIdx.x * nblocks;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if(threadIdx.x == 0) { carry_s = 0; }
+    __syncthreads();
+    for(int base = 0; base < nblocks; base += 1024) {
+        const int k = base + threadIdx.x;
+        const int v = (k < nblocks) ? c[k] : 0;
+        int x = v;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if(lane >= o) { x += y; }
+        }
+        if(lane == 31) { warp_sums[wid] = x; }
+        __syncthreads();
+        if(wid == 0) {
+            int w = warp_sums[lane];
+#pragma unroll
+            for(int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if(lane >= o) { w += y; }
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int excl = carry + ((wid == 0) ? 0 : warp_sums[wid - 1]) + x - v;
+        if(k < nblocks) { c[k] = excl; }
+        __syncthreads();
+        if(threadIdx.x == 1023) { carry_s = carry + warp_sums[31]; }
+        __syncthreads();
     }
-    *count = c;
+    if(threadIdx.x == 0) { totals[blockIdx.x] = carry_s; }
+}
+
+// entries of side 0 start at `base`, those of side 1 right behind them (base + totals[0]); nothing is written beyond `cap`
+__global__ void __launch_bounds__(SEL_T) pb_k_sel2_scatter(int n, int nblocks, int dim, int on_lo, int on_hi, double b_lo, double b_hi,
+                                                           int mult_lo, int mult_hi, int base, int cap,
+                                                           const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                           const int *__restrict__ block_offsets, const int *__restrict__ totals,
+                                                           int *__restrict__ send_map, int *__restrict__ send_mult) {
+    __shared__ int w_lo[SEL_T / 32], w_hi[SEL_T / 32];
+    const int i = blockIdx.x * SEL_T + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int lo, hi;
+    pb_sel_flags(i, n, dim, on_lo, on_hi, b_lo, b_hi, pos, flags, &lo, &hi);
+    const unsigned m_lo = __ballot_sync(0xffffffffu, lo), m_hi = __ballot_sync(0xffffffffu, hi);
+    if(lane == 0) { w_lo[wid] = __popc(m_lo); w_hi[wid] = __popc(m_hi); }
+    __syncthreads();
+    int off_lo = 0, off_hi = 0;
+    for(int w = 0; w < wid; w++) { off_lo += w_lo[w]; off_hi += w_hi[w]; }
+    const unsigned below = (1u << lane) - 1u;
+    if(lo) {
+        const int k = base + block_offsets[blockIdx.x] + off_lo + __popc(m_lo & below);
+        if(k < cap) {
+            send_map[k] = i;
+            send_mult[k * 3 + 0] = (dim == 0) ? mult_lo : 0;
+            send_mult[k * 3 + 1] = (dim == 1) ? mult_lo : 0;
+            send_mult[k * 3 + 2] = (dim == 2) ? mult_lo : 0;
+        }
+    }
+    if(hi) {
+        const int k = base + totals[0] + block_offsets[nblocks + blockIdx.x] + off_hi + __popc(m_hi & below);
+        if(k < cap) {
+            send_map[k] = i;
+            send_mult[k * 3 + 0] = (dim == 0) ? mult_hi : 0;
+            send_mult[k * 3 + 1] = (dim == 1) ? mult_hi : 0;
+            send_mult[k * 3 + 2] = (dim == 2) ? mult_hi : 0;
+        }
+    }
+}
+
+// Appends the particles of [0, n) selected for the two sides of `dim` to the send lists (side 0 first, ascending index
+// inside a side); returns their numbers.
+static int pb_select_dim(pb_ctx *ctx, int n, int dim, double offset, int *count_lo, int *count_hi) {
+    *count_lo = 0; *count_hi = 0;
+    const int j0 = dim * 2, j1 = dim * 2 + 1;
+    const int on_lo = !(!ctx->pbc_flag[dim] && ctx->pbc[j0] != 0), on_hi = !(!ctx->pbc_flag[dim] && ctx->pbc[j1] != 0);
+    if(n == 0 || (!on_lo && !on_hi)) { return 0; }
+    const double b_lo = ctx->subdom[j0] + offset, b_hi = ctx->subdom[j1] - offset;
+    const int nblocks = pb_blocks(n, SEL_T);
+    if(2 * nblocks + 2 > ctx->sel_blocks_cap) {
+        if(ctx->sel_blocks != nullptr) { PB_CHECK(cudaFree(ctx->sel_blocks)); }
+        ctx->sel_blocks_cap = 2 * nblocks + 2 + 4096;
+        PB_CHECK(cudaMalloc(&ctx->sel_blocks, sizeof(int) * (size_t) ctx->sel_blocks_cap));
+    }
+    int *totals = ctx->sel_blocks + 2 * (size_t) nblocks;
+    PB_LAUNCH(pb_k_sel2_count, nblocks, SEL_T, n, nblocks, dim, on_lo, on_hi, b_lo, b_hi, ctx->pos, ctx->flags, ctx->sel_blocks);
+    PB_LAUNCH(pb_k_sel2_scan, 2, 1024, nblocks, ctx->sel_blocks, totals);
+    for(int attempt = 0; attempt < 2; attempt++) {
+        // optimistic scatter into the current capacity; if the lists turn out too short, grow and scatter again
+        PB_LAUNCH(pb_k_sel2_scatter, nblocks, SEL_T, n, nblocks, dim, on_lo, on_hi, b_lo, b_hi, ctx->pbc[j0], ctx->pbc[j1], ctx->nsend_all,
+                  ctx->send_cap, ctx->pos, ctx->flags, ctx->sel_blocks, totals, ctx->send_map, ctx->send_mult);
+        if(attempt == 0) {
+            PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, totals, sizeof(int) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        }
+        const int need = ctx->nsend_all + ctx->h_scalars[0] + ctx->h_scalars[1];
+        if(need <= ctx->send_cap) { break; }
+        PB_TRY(pb_ensure_send_capacity(ctx, need));
+    }
+    *count_lo = ctx->h_scalars[0];
+    *count_hi = ctx->h_scalars[1];
     return 0;
 }
 
@@ -170,12 +261,11 @@ extern "C" int pb_borders(pb_ctx *ctx) {
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
     for(int step = 0; step < 3; step++) {
         const int n = ctx->nlocal + ctx->nghost;     // locals AND ghosts received so far: edges/corners are forwarded
-        for(int side = 0; side < 2; side++) {
-            int c = 0;
-            PB_TRY(pb_select_side(ctx, n, step, side, ctx->spacing, &c));
-            ctx->nsend[step * 2 + side] = c;
-            ctx->nsend_all += c;
-        }
+        int c_lo = 0, c_hi = 0;
+        PB_TRY(pb_select_dim(ctx, n, step, ctx->spacing, &c_lo, &c_hi));
+        ctx->nsend[step * 2] = c_lo;
+        ctx->nsend[step * 2 + 1] = c_hi;
+        ctx->nsend_all += c_lo + c_hi;
         PB_TRY(pb_transport_sizes(ctx, step));
         pb_set_offsets(ctx, step);
         const int ns = ctx->nsend[step * 2] + ctx->nsend[step * 2 + 1];

@@ -84,6 +84,8 @@ struct pb_ctx {
     int zsub = 8, zsub_active = 1;   // z slabs per cell (option "cell_zsub"); 1 in DEM mode
     int *cell_slot = nullptr;     // [pcap] slot of the particle inside its cell (arrival order, sorted later)
     int *cell_list = nullptr;     // [pcap]
+    int *sel_blocks = nullptr;    // [2][blocks] per-block selection counts of pb_borders + 2 totals
+    int sel_blocks_cap = 0;
     int *cell_key = nullptr;      // [pcap] counting-sort key cell*zsub + slab
     int *scan_tmp = nullptr;      // block sums for the scan
     int scan_tmp_cap = 0;

@@ -12,7 +12,7 @@ import numpy as np  # noqa: E402
 from pairs_b200.backend import Context  # noqa: E402
 from tests import dem_common as dc  # noqa: E402
 
-settle = int(sys.argv[1]) if len(sys.argv) > 1 else 6000
+settle = int(sys.argv[1]) if len(sys.argv) > 1 else 8000          # settled window = iterations 8000..9000
 DOMAIN = (0.8, 0.8, 0.2)
 ctx = Context(0)
 ctx.init_domain([0.0, DOMAIN[0], 0.0, DOMAIN[1], 0.0, DOMAIN[2]], pbc=(1, 1, 0), partitioner=1)
@@ -56,7 +56,7 @@ window("falling", 20, 220)
 t0 = time.time()
 ctx.dem_run(dc.CELL, 220, settle)
 res["settle_wall_s"] = time.time() - t0
-window("settled", settle, settle + 200)
+window("settled", settle, settle + 1000)
 try:
     from oracle import ref, ref_worker
     if ref.available("dem_bench"):
