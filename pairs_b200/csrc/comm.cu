@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(1024) pb_k_sel2_scan(int nblocks, int *__restr
     if(threadIdx.x == 0) { totals[blockIdx.x] = carry_s; }
 }
 
+int pb_sel2_scan(pb_ctx *ctx, int nblocks, int *block_counts, int *totals) {
+    PB_LAUNCH(pb_k_sel2_scan, 2, 1024, nblocks, block_counts, totals);
+    return 0;
+}
+
 // entries of side 0 start at `base`, those of side 1 right behind them (base + totals[0]); nothing is written beyond `cap`
 __global__ void __launch_bounds__(SEL_T) pb_k_sel2_scatter(int n, int nblocks, int dim, int on_lo, int on_hi, double b_lo, double b_hi,
                                                            int mult_lo, int mult_hi, int base, int cap,

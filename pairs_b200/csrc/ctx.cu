@@ -62,7 +62,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape, ctx->shape_alt, ctx->tag,
                     ctx->tag_alt, ctx->particle_cell, ctx->cell_count, ctx->cell_start, ctx->cell_slot, ctx->cell_list,
                     ctx->cell_key, ctx->sub_start, ctx->scan_tmp, ctx->neigh, ctx->numneigh, ctx->d_eps, ctx->d_sig6, ctx->send_map, ctx->send_mult,
-                    ctx->send_buf, ctx->recv_buf, ctx->sel_blocks, ctx->sel_flag, ctx->sel_scan, ctx->mig_scan_a, ctx->mig_scan_b, ctx->d_partial, ctx->d_scalars,
+                    ctx->send_buf, ctx->recv_buf, ctx->sel_blocks, ctx->sel_flag, ctx->sel_scan, ctx->d_partial, ctx->d_scalars,
                     ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
                     ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
                     ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->d_fric_static,
@@ -143,10 +143,6 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
     PB_TRY(pb_regrow(ctx, &ctx->cell_key, 0, newcap, false));
     PB_TRY(pb_regrow(ctx, &ctx->sel_flag, 0, newcap + 1, false));
     PB_TRY(pb_regrow(ctx, &ctx->sel_scan, 0, newcap + 1, false));
-    if(ctx->world > 1) {
-        PB_TRY(pb_regrow(ctx, &ctx->mig_scan_a, 0, newcap + 1, false));
-        PB_TRY(pb_regrow(ctx, &ctx->mig_scan_b, 0, newcap + 1, false));
-    }
     PB_TRY(pb_regrow(ctx, &ctx->numneigh, 0, newcap, false));
     if(ctx->dem) { PB_TRY(pb_dem_grow(ctx, oldcap, newcap, used)); }
     ctx->pcap = (int) newcap;

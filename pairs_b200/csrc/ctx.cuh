@@ -141,7 +141,6 @@ struct pb_ctx {
     double *send_buf = nullptr, *recv_buf = nullptr; // [send_cap][PB_MAX_ELEMS]
     int recv_cap = 0;
     int *sel_flag = nullptr, *sel_scan = nullptr; // [pcap+1] compaction scratch
-    int *mig_scan_a = nullptr, *mig_scan_b = nullptr; // [pcap+1] migration scratch (multi-rank exchange)
     void *nccl = nullptr;         // NcclState* (comm_nccl.cu), null on a single rank
 
     // ---- reductions / host mirrors ----

@@ -398,13 +398,12 @@ __device__ __forceinline__ void pb_dem_unpack_one(const PbDemArrays &a, int p, c
 }
 
 // records of the leavers: e = record index (same mapping as the base pack kernel of migrate.cu)
-__global__ void __launch_bounds__(128) pb_k_dem_pack_exchange(int n, int stride, int base_hi, const int *__restrict__ sel_lo,
-                                                              const int *__restrict__ scan_lo, const int *__restrict__ sel_hi,
-                                                              const int *__restrict__ scan_hi, PbDemArrays a, double *__restrict__ buf) {
+__global__ void __launch_bounds__(128) pb_k_dem_pack_exchange(int n, int stride, const int *__restrict__ rec, PbDemArrays a,
+                                                              double *__restrict__ buf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) { return; }
-    int e;
-    if(sel_lo[i]) { e = scan_lo[i]; } else if(sel_hi[i]) { e = base_hi + scan_hi[i]; } else { return; }
+    const int e = rec[i];
+    if(e < 0) { return; }
     pb_dem_pack_one(a, i, buf + (size_t) e * stride + 12);
 }
 
@@ -415,9 +414,10 @@ __global__ void __launch_bounds__(128) pb_k_dem_unpack_exchange(int count, int d
 }
 
 // hole filling: particle `src` (a stayer from the tail) moves into slot `dst` (a leaver's slot below the new nlocal)
-__global__ void __launch_bounds__(128) pb_k_dem_move(int count, const int *__restrict__ src_idx, const int *__restrict__ dst_idx, PbDemArrays a) {
+__global__ void __launch_bounds__(128) pb_k_dem_move(const int *__restrict__ count, const int *__restrict__ src_idx,
+                                                     const int *__restrict__ dst_idx, PbDemArrays a) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if(k >= count) { return; }
+    if(k >= *count) { return; }
     const int s = src_idx[k], t = dst_idx[k];
     const size_t cap = a.cap;
     a.radius[t] = a.radius[s];
@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(128) pb_k_dem_move(int count, const int *__res
     }
 }
 
-int pb_dem_pack_exchange(pb_ctx *ctx, int n, int stride, int base_hi, const int *sel_lo, const int *scan_lo, const int *sel_hi, const int *scan_hi) {
-    PB_LAUNCH(pb_k_dem_pack_exchange, pb_blocks(n, 128), 128, n, stride, base_hi, sel_lo, scan_lo, sel_hi, scan_hi, pb_dem_arrays(ctx), ctx->send_buf);
+int pb_dem_pack_exchange(pb_ctx *ctx, int n, int stride, const int *rec) {
+    PB_LAUNCH(pb_k_dem_pack_exchange, pb_blocks(n, 128), 128, n, stride, rec, pb_dem_arrays(ctx), ctx->send_buf);
     return 0;
 }
 
@@ -444,8 +444,8 @@ int pb_dem_unpack_exchange(pb_ctx *ctx, int count, int dst0, int stride, const d
     return 0;
 }
 
-int pb_dem_move(pb_ctx *ctx, int count, const int *src_idx, const int *dst_idx) {
-    PB_LAUNCH(pb_k_dem_move, pb_blocks(count, 128), 128, count, src_idx, dst_idx, pb_dem_arrays(ctx));
+int pb_dem_move(pb_ctx *ctx, int max_count, const int *count, const int *src_idx, const int *dst_idx) {
+    PB_LAUNCH(pb_k_dem_move, pb_blocks(max_count, 128), 128, count, src_idx, dst_idx, pb_dem_arrays(ctx));
     return 0;
 }
 
