@@ -28,6 +28,10 @@ def main():
         dist.init_process_group("gloo", rank=rank, world_size=world)
     gx, gy = GRIDS[world]
     domain = (0.8 * gx, 0.8 * gy, 0.2)
+    if len(sys.argv) > 2 and sys.argv[2] == "c5":
+        # BASELINE.json configs[4] / SURVEY.md C5: the 3.2 x 3.2 x 0.2 box = 15,974,400 spheres on 8 GPUs (2 x 4 x 1 ranks)
+        assert world == 8, "config C5 is defined for 8 GPUs"
+        domain = (3.2, 3.2, 0.2)
     ctx = backend.Context(local)
     ctx.init_domain([0.0, domain[0], 0.0, domain[1], 0.0, domain[2]], pbc=(1, 1, 0), partitioner=1, world_size=world, rank=rank)
     dec = ctx.decomposition()
