@@ -15,6 +15,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md_t1     nx=ny=nz=8 (2048 atoms), 100 steps, thermo every step   -> per-step parity dumps
   md_t2     nx=ny=nz=12 (6912 atoms), 60 steps, thermo every step, reneighbour every 5
   dem_t1    examples/dem.py on a 0.1 x 0.015 x 0.04 box (420 spheres + 2 planes), 700 steps, thermo hook every step
+  dem_nl_t1 dem_t1 with psim.build_neighbor_lists(linkedCellWidth) instead of build_cell_lists: Verlet lists + BuildContactHistory
   dem_vtk_t1 dem_t1 for 60 steps with the example's psim.vtk_output(..., frequency) kept, writing every 30 iterations
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
@@ -66,8 +67,10 @@ def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False):
     return patch
 
 
-def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None):
+def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None, verlet=False):
     def patch(text):
+        if verlet:      # Verlet lists + BuildContactHistory instead of the cell-list traversal (sim/simulation.py:255-261, 402-406)
+            text = _sub(text, r"^psim\.build_cell_lists\(linkedCellWidth\)", "psim.build_neighbor_lists(linkedCellWidth)")
         if vtk_every is not None:     # keep psim.vtk_output(...) (runtime/vtk.hpp) and write every `vtk_every` iterations
             text = _sub(text, r"^visSpacing = \d+", f"visSpacing = {vtk_every}")
         if per_cell:    # build_cell_lists(spacing, store_neighbors_per_cell=True), sim/simulation.py:250-253
@@ -137,6 +140,7 @@ VARIANTS = {
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
     "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
     "dem_cn_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700, per_cell=True), [], False),
+    "dem_nl_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700, verlet=True), [], False),
     "dem_vtk_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 60, vtk_every=30), [], False),
     "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),
 }
