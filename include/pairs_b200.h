@@ -164,6 +164,17 @@ typedef struct pb_md_params {
 } pb_md_params;
 int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo);
 
+/* ---- user-defined kernels (the reference generates code for arbitrary kernel bodies: src/pairs/mapping/funcs.py:39-334,
+ *      code_gen/cgen.py).  `source` is CUDA C++ printed by pairs_b200/kernelgen.py from the Python kernel; it starts with
+ *      pb_jit_prelude() and defines  extern "C" __global__ void <kernel_name>(PbJitArgs).  Compiled at run time with NVRTC for
+ *      sm_100a (--fmad=false).  pb_jit_check compiles only (no GPU needed): returns the cubin size, or -1 with the compiler
+ *      log in `log`.  pb_jit_launch: kind 0 = pair kernel over the current neighbour lists with interaction cutoff `cutoff`,
+ *      kind 1 = per-particle kernel. ---- */
+const char *pb_jit_prelude(void);
+int pb_jit_check(const char *source, char *log, int log_cap);
+int pb_jit_compile(pb_ctx *ctx, const char *source, const char *kernel_name, int *handle);
+int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff);
+
 /* Options.  Behaviour: "compute_half" (0/1) = Simulation.compute_half() (sim/simulation.py:119-120): half neighbour lists,
  * pair terms applied to both partners (ir/apply.py:111-125); applies from the next neighbour-list build.
  * Tuning knobs: "lanes_per_particle" (1,2,4,8; applies from the next build), "lj_unroll" (2,4,8), "fuse_integrate" (0/1),

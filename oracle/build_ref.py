@@ -19,6 +19,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   dem_vtk_t1 dem_t1 for 60 steps with the example's psim.vtk_output(..., frequency) kept, writing every 30 iterations
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
+  md_custom_t1  md_t1 with other kernel bodies (softened LJ using sqrt / select / symbols, integrators with drag) -> generic kernels
   md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
@@ -63,6 +64,41 @@ def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False):
         text = _sub(text, r"timesteps=\d+", f"timesteps={steps}{extra}")
         text = _sub(text, r"compute_thermo\(\d+\)", f"compute_thermo({thermo})")
         text = _sub(text, r"reneighbor_every\(\d+\)", f"reneighbor_every({reneigh})")
+        return text
+    return patch
+
+
+CUSTOM_KERNELS = '''def lennard_jones(i, j):
+    rsq = squared_distance(i, j)
+    r = sqrt(rsq)
+    sr2 = 1.0 / rsq
+    sr6 = sr2 * sr2 * sr2 * sigma6[i, j]
+    f = 48.0 * sr6 * (sr6 - 0.5) * sr2 * epsilon[i, j] + select(r < rsoft, kspring * (rsoft - r) / r, 0.0)
+    apply(force, delta(i, j) * f)
+
+
+def initial_integrate(i):
+    linear_velocity[i] += (dt * 0.5) * (force[i] - gamma * linear_velocity[i]) / mass[i]
+    position[i] += dt * linear_velocity[i]
+
+
+def final_integrate(i):
+    linear_velocity[i] += (dt * 0.5) * (force[i] - gamma * linear_velocity[i]) / mass[i]
+'''
+
+
+def md_custom_variant(nx, steps):
+    """examples/md.py with OTHER kernel bodies (a softened LJ with sqrt / select / extra symbols, integrators with a drag term)
+    and a non-uniform epsilon table: pins the generic kernel path (pairs_b200/kernelgen.py), same text as tests/scripts/custom_script.py."""
+    base = md_variant(nx, steps, 1, 20)
+
+    def patch(text):
+        text = base(text)
+        text = re.sub(r"def lennard_jones\(i, j\):.*?(?=\n\ncmd = )", CUSTOM_KERNELS.rstrip("\n") + "\n", text, count=1, flags=re.S)
+        text = _sub(text, r"\[sigma for i in range\(ntypes \* ntypes\)\]", "[1.0 + 0.05 * ((i % ntypes) + (i // ntypes)) for i in range(ntypes * ntypes)]")
+        text = _sub(text, r"symbols=\{'dt': dt\}, pre_step=True", "symbols={'dt': dt, 'gamma': 0.05}, pre_step=True")
+        text = _sub(text, r"psim\.compute\(lennard_jones, cutoff_radius\)", "psim.compute(lennard_jones, cutoff_radius, symbols={'kspring': 3.5, 'rsoft': 1.05})")
+        text = _sub(text, r"psim\.compute\(final_integrate, symbols=\{'dt': dt\}", "psim.compute(final_integrate, symbols={'dt': dt, 'gamma': 0.05}")
         return text
     return patch
 
@@ -135,6 +171,7 @@ VARIANTS = {
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
+    "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), [], False),
     # half neighbour lists + atomic update of the partner
     "md_half_t1": ("examples/md.py", md_variant(8, 100, 1, 20, half=True), ["-DREF_IS_MD", "-DREF_HALF_LISTS"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libpairs_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu"]
+SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu"]
 
 # --fmad=false: fp64 multiplies and adds are never contracted, so per-operation results equal the reference CPU
 # build compiled with -ffp-contract=off (the parity contract).
@@ -111,6 +111,10 @@ SIGNATURES = {
     "pb_nccl_init": (_I, [_P, _P]),
     "pb_md_run": (_I, [_P, ctypes.POINTER(MdParams), _I, _I, _DP, _I, _IP]),
     "pb_set_option": (_I, [_P, _S, _I]),
+    "pb_jit_prelude": (_S, []),
+    "pb_jit_check": (_I, [_S, ctypes.c_char_p, _I]),
+    "pb_jit_compile": (_I, [_P, _S, _S, _IP]),
+    "pb_jit_launch": (_I, [_P, _I, _I, _D]),
     "pb_synchronize_device": (_I, [_P]),
     "pb_timers_enable": (_I, [_P, _I]),
     "pb_timers_get": (_I, [_P, _S, _DP, ctypes.POINTER(ctypes.c_long)]),
@@ -407,6 +411,14 @@ class Context:
         self._ck(self.lib.pb_md_run(self.h, ctypes.byref(p), ts_begin, ts_end, _dp(out), cap, ctypes.byref(n)))
         return out[: min(n.value, cap) * 3].reshape(-1, 3)
 
+    def jit_compile(self, source, kernel_name):
+        h = _I(0)
+        self._ck(self.lib.pb_jit_compile(self.h, source.encode(), kernel_name.encode(), ctypes.byref(h)))
+        return h.value
+
+    def jit_launch(self, handle, kind, cutoff=0.0):
+        self._ck(self.lib.pb_jit_launch(self.h, handle, kind, cutoff))
+
     def set_option(self, name, value):
         self._ck(self.lib.pb_set_option(self.h, name.encode(), int(value)))
 
@@ -452,3 +464,17 @@ def nccl_unique_id():
     if load().pb_nccl_unique_id(ctypes.cast(buf, _P)) != 0:
         raise BackendError("ncclGetUniqueId failed")
     return buf.raw
+
+
+def jit_prelude():
+    """Source text every generated kernel starts with (struct PbJitArgs etc., csrc/jit.cu)."""
+    return load().pb_jit_prelude().decode()
+
+
+def jit_check(source):
+    """Compile-only check with NVRTC (no GPU needed): returns the cubin size, raises BackendError with the compiler log."""
+    log = ctypes.create_string_buffer(16384)
+    n = load().pb_jit_check(source.encode(), log, len(log))
+    if n < 0:
+        raise BackendError(log.value.decode(errors="replace"))
+    return n

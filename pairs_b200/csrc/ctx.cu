@@ -52,12 +52,14 @@ extern "C" int pb_create(pb_ctx **out, int device) {
 }
 
 void pb_nccl_destroy(pb_ctx *ctx);
+void pb_jit_destroy(pb_ctx *ctx);
 
 extern "C" void pb_destroy(pb_ctx *ctx) {
     if(ctx == nullptr) { return; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pb_nccl_destroy(ctx);
+    pb_jit_destroy(ctx);
     void *bufs[] = {ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt, ctx->force, ctx->mass, ctx->mass_alt, ctx->type,
                     ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt, ctx->shape, ctx->shape_alt, ctx->tag,
                     ctx->tag_alt, ctx->particle_cell, ctx->cell_count, ctx->cell_start, ctx->cell_slot, ctx->cell_list,

@@ -141,6 +141,7 @@ struct pb_ctx {
     double *send_buf = nullptr, *recv_buf = nullptr; // [send_cap][PB_MAX_ELEMS]
     int recv_cap = 0;
     int *sel_flag = nullptr, *sel_scan = nullptr; // [pcap+1] compaction scratch
+    void *jit = nullptr;          // table of NVRTC-compiled user kernels (jit.cu)
     void *nccl = nullptr;         // NcclState* (comm_nccl.cu), null on a single rank
 
     // ---- reductions / host mirrors ----

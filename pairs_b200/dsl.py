@@ -207,6 +207,9 @@ def _unify(t, u, binding):
     return True
 
 
+FORCE_GENERIC = False        # tests: send every kernel through the generic (NVRTC) path, also the recognised ones
+
+
 def recognise(func):
     """-> (family, {role: user name}) or raises DslError."""
     src = textwrap.dedent(inspect.getsource(func))
@@ -405,9 +408,19 @@ class Simulation:
         self.neighbor_cutoff = spacing
 
     def compute(self, func, cutoff_radius=None, symbols={}, pre_step=False, skip_first=False):
-        family, roles = recognise(func)
+        try:
+            if FORCE_GENERIC:
+                raise DslError("generic path forced")
+            family, roles = recognise(func)
+        except DslError:
+            # not one of the hand-written families: CUDA is generated for the body and compiled at run time (kernelgen.py,
+            # csrc/jit.cu) -- the reference's code generator handles arbitrary bodies too (mapping/funcs.py:39-334)
+            nparams = len(inspect.signature(func).parameters)
+            if nparams not in (1, 2):
+                raise
+            family, roles = ("generic_pair" if nparams == 2 else "generic_particle"), {}
         entry = {"name": func.__name__, "family": family, "roles": roles, "cutoff": cutoff_radius, "symbols": dict(symbols),
-                 "skip_first": skip_first, "globals": func.__globals__}
+                 "skip_first": skip_first, "globals": func.__globals__, "func": func}
         (self.pre_step if pre_step else self.functions).append(entry)
 
     # -- helpers --
@@ -646,7 +659,50 @@ class Simulation:
                     raise DslError(f"{e['name']}: '{e['roles']['position']}' is not the position property")
                 return dict(e, call=lambda: ctx.initial_integrate(dt), dt=dt)
             return dict(e, call=lambda: ctx.final_integrate(dt), dt=dt)
+        if fam in ("generic_pair", "generic_particle"):
+            return self._bind_generic(ctx, e)
         raise DslError(f"unbound kernel family {fam}")
+
+    def _device_storage(self):
+        """User property names -> the device arrays of the MD path (csrc/ctx.cuh): the position, ONE non-volatile vector
+        (velocity), ONE volatile vector (force), ONE non-volatile real (mass)."""
+        m = {}
+        for name, p in self.props.items():
+            if name == self.position_name:
+                m[name] = "pos"
+            elif p.type == Types.Vector:
+                slot = "force" if p.volatile else "vel"
+                if slot in m.values():
+                    raise DslError(f"property '{name}': this backend stores one velocity-like and one force-like vector property")
+                m[name] = slot
+            elif p.type == Types.Real and name not in self.feature_props:
+                if "mass" in m.values():
+                    raise DslError(f"property '{name}': this backend stores one real property (mass)")
+                m[name] = "mass"
+        return m
+
+    def _bind_generic(self, ctx, e):
+        from . import backend, kernelgen
+        if self._compute_half:
+            raise DslError("compute_half() is available for the built-in lennard_jones kernel only")
+        nk = 1
+        tables = {}
+        for name, (feat, data) in self.feature_props.items():
+            tables[name] = data
+            nk = self.features[feat]
+        try:
+            kind, kname, src = kernelgen.translate(e["func"], self._device_storage(), tables, nk, e["symbols"], backend.jit_prelude())
+        except kernelgen.KernelGenError as err:
+            raise DslError(f"kernel '{e['name']}': {err}") from None
+        handle = ctx.jit_compile(src, kname)
+        if kind == "pair":
+            if self.neighbor_cutoff is None:
+                raise DslError(f"kernel '{e['name']}': pair kernels run over neighbour lists (build_neighbor_lists)")
+            if e["cutoff"] is None:
+                raise DslError(f"kernel '{e['name']}': pair kernels need a cutoff_radius")
+            cutoff = _builtin_float(e["cutoff"])
+            return dict(e, call=lambda: ctx.jit_launch(handle, 0, cutoff), source=src)
+        return dict(e, call=lambda: ctx.jit_launch(handle, 1), source=src)
 
     def _native_md_params(self, pre, fn):
         """The standard md.py procedure list runs in the native loop (pb_md_run); anything else in the Python loop."""

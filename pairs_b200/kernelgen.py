@@ -1,0 +1,337 @@
+"""Generic kernels: CUDA source for kernel bodies that are not one of the hand-written families.
+
+The reference traces a kernel function into IR and prints code for it (src/pairs/mapping/funcs.py:39-334 BuildParticleIR,
+keywords in src/pairs/mapping/keywords.py, Apply in src/pairs/ir/apply.py, the pair loop of sim/interaction.py:168-295).  This
+module prints CUDA for the same vocabulary directly from the Python AST, for the properties the MD path stores on the device
+(position, one velocity-like vector, one volatile force-like vector, mass, the `type` feature and its feature properties):
+
+  pair kernels     def k(i, j): locals, delta(i, j), squared_distance(i, j) (or the legacy bare names delta / rsq),
+                   prop[i], prop[j], featprop[i, j], sqrt, select, min, max, abs, dot, length, squared_length, normalized,
+                   zero_vector, vector(x, y, z), + - * / unary -, comparisons, apply(prop, expr)
+  particle kernels def k(i): the same expressions, prop[i] = / += / -= expr
+
+Like the reference's generated code the output has ONE statement per operation, in Python's evaluation order, vectors
+scalarised per component, `select` evaluating both arms, symbols substituted as literals; compiled with --fmad=false every
+operation is the IEEE operation of the reference's C++ (-ffp-contract=off), so a pair term is bit-identical and only the
+order in which a particle's terms are summed is ours (the list order).  apply() accumulates in registers and adds to the
+property once after the loop (sim/interaction.py:280-292); FIXED particles are skipped (mapping/funcs.py:305-310).
+"""
+import ast
+import inspect
+import textwrap
+
+
+class KernelGenError(Exception):
+    pass
+
+
+def _lit(x):
+    if isinstance(x, bool):
+        return "true" if x else "false"
+    if isinstance(x, int):
+        return str(x)
+    r = repr(float(x))
+    if r in ("inf", "-inf", "nan"):
+        raise KernelGenError("non-finite symbol value")
+    return r if ("." in r or "e" in r or "E" in r) else r + ".0"
+
+
+class _Gen:
+    """Expression / statement printer.  Values are (type, code) with type in {'f', 'i', 'b'} or ('v', [c0, c1, c2])."""
+
+    def __init__(self, name, kind, storage, feature_tables, ntypes, symbols, glob):
+        self.name, self.kind = name, kind
+        self.storage = storage                # user property name -> 'pos' | 'vel' | 'force' | 'mass'
+        self.tables = feature_tables          # feature property name -> list of nk*nk floats
+        self.ntypes = ntypes
+        self.symbols, self.glob = symbols, glob
+        self.lines, self.locals, self.n = [], {}, 0
+        self.loaded = {}                      # (storage, who) -> value, loaded once per (pair) iteration
+        self.applied = {}                     # storage -> accumulator names
+        self.hoisted = []                     # statements before the neighbour loop (loads of i)
+        self.types_needed = False
+
+    # -- helpers --
+    def tmp(self, ctype, code, hoist=False):
+        self.n += 1
+        t = f"t{self.n}"
+        (self.hoisted if hoist else self.lines).append(f"const {ctype} {t} = {code};")
+        return t
+
+    def vec(self, comps):
+        return ("v", list(comps))
+
+    @staticmethod
+    def is_vec(v):
+        return isinstance(v, tuple) and v[0] == "v"
+
+    def load(self, store, who):
+        key = (store, who)
+        if key in self.loaded:
+            return self.loaded[key]
+        idx = "i" if who == "i" else "j"
+        hoist = who == "i" and self.kind == "pair"
+        if store == "pos":
+            src = "pi" if who == "i" else "pj"
+            val = self.vec([f"{src}.x", f"{src}.y", f"{src}.z"])
+        elif store in ("vel", "force"):
+            val = self.vec([self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(3)])
+        elif store == "mass":
+            val = ("f", self.tmp("double", f"a.mass[{idx}]", hoist))
+        else:
+            raise KernelGenError(f"no device storage for '{store}'")
+        self.loaded[key] = val
+        return val
+
+    # -- expressions --
+    def expr(self, node):
+        if isinstance(node, ast.Constant):
+            if isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+                return ("i" if isinstance(node.value, int) else "f", _lit(node.value))
+            raise KernelGenError(f"unsupported constant {node.value!r}")
+        if isinstance(node, ast.Name):
+            return self.name_value(node.id)
+        if isinstance(node, ast.UnaryOp):
+            v = self.expr(node.operand)
+            if isinstance(node.op, ast.USub):
+                if self.is_vec(v):
+                    return self.vec([self.tmp("double", f"-({c})") for c in v[1]])
+                return (v[0], self.tmp("double" if v[0] == "f" else "int", f"-({v[1]})"))
+            if isinstance(node.op, ast.UAdd):
+                return v
+            if isinstance(node.op, ast.Not):
+                return ("b", self.tmp("bool", f"!({v[1]})"))
+            raise KernelGenError("unsupported unary operator")
+        if isinstance(node, ast.BinOp):
+            ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
+            if type(node.op) not in ops:
+                raise KernelGenError(f"unsupported operator {type(node.op).__name__}")
+            return self.binop(ops[type(node.op)], self.expr(node.left), self.expr(node.right))
+        if isinstance(node, ast.Compare):
+            if len(node.ops) != 1:
+                raise KernelGenError("chained comparisons are not supported")
+            ops = {ast.Lt: "<", ast.LtE: "<=", ast.Gt: ">", ast.GtE: ">=", ast.Eq: "==", ast.NotEq: "!="}
+            a, b = self.expr(node.left), self.expr(node.comparators[0])
+            if self.is_vec(a) or self.is_vec(b):
+                raise KernelGenError("vectors cannot be compared")
+            return ("b", self.tmp("bool", f"{a[1]} {ops[type(node.ops[0])]} {b[1]}"))
+        if isinstance(node, ast.BoolOp):
+            vals = [self.expr(v) for v in node.values]
+            op = "&&" if isinstance(node.op, ast.And) else "||"
+            return ("b", self.tmp("bool", f" {op} ".join(v[1] for v in vals)))
+        if isinstance(node, ast.Subscript):
+            return self.subscript(node)
+        if isinstance(node, ast.Call):
+            return self.call(node)
+        raise KernelGenError(f"unsupported expression {type(node).__name__}")
+
+    def binop(self, op, a, b):
+        if self.is_vec(a) and self.is_vec(b):
+            if op in ("*", "/"):
+                raise KernelGenError("vector * vector is ambiguous: use dot()")
+            return self.vec([self.tmp("double", f"{x} {op} {y}") for x, y in zip(a[1], b[1])])
+        if self.is_vec(a):
+            if op in ("+", "-"):
+                raise KernelGenError("vector +- scalar is not defined")
+            return self.vec([self.tmp("double", f"{x} {op} {b[1]}") for x in a[1]])
+        if self.is_vec(b):
+            if op != "*":
+                raise KernelGenError("scalar op vector: only * is defined")
+            return self.vec([self.tmp("double", f"{a[1]} {op} {y}") for y in b[1]])
+        t = "i" if (a[0] == "i" and b[0] == "i" and op != "/") else "f"
+        if a[0] == "i" and b[0] == "i" and op == "/":
+            return ("f", self.tmp("double", f"(double) {a[1]} / (double) {b[1]}"))      # Python true division
+        return (t, self.tmp("double" if t == "f" else "int", f"{a[1]} {op} {b[1]}"))
+
+    def name_value(self, name):
+        if name in self.locals:
+            return self.locals[name]
+        if self.kind == "pair" and name == "rsq":            # legacy bare names of examples/lj_onetype.py
+            return ("f", "rsq")
+        if self.kind == "pair" and name == "delta":
+            return self.vec(["dx", "dy", "dz"])
+        if name in self.symbols:
+            v = self.symbols[name]
+        elif name in self.glob and isinstance(self.glob[name], (int, float)) and not isinstance(self.glob[name], bool):
+            v = self.glob[name]
+        else:
+            raise KernelGenError(f"symbol '{name}' has no value (pass it in symbols={{...}})")
+        return ("i" if isinstance(v, int) else "f", _lit(v))
+
+    def subscript(self, node):
+        if not isinstance(node.value, ast.Name):
+            raise KernelGenError("unsupported subscript")
+        prop = node.value.id
+        idx = node.slice
+        if isinstance(idx, ast.Tuple):                        # feature property: fp[i, j]
+            names = [e.id for e in idx.elts if isinstance(e, ast.Name)]
+            if prop not in self.tables or names != ["i", "j"] or self.kind != "pair":
+                raise KernelGenError(f"'{prop}[...]': only feature_property[i, j] inside a pair kernel is supported")
+            self.types_needed = True
+            return ("f", self.tmp("double", f"fp_{prop}[ti + tj]"))
+        if not isinstance(idx, ast.Name) or idx.id not in ("i", "j") or (idx.id == "j" and self.kind != "pair"):
+            raise KernelGenError(f"'{prop}[...]': index must be the particle argument")
+        if prop not in self.storage:
+            raise KernelGenError(f"property '{prop}' is not stored on the device by this backend (position, one velocity, one "
+                                 "volatile force, mass)")
+        return self.load(self.storage[prop], idx.id)
+
+    def call(self, node):
+        if not isinstance(node.func, ast.Name):
+            raise KernelGenError("unsupported call")
+        f = node.func.id
+        if f in ("delta", "squared_distance"):
+            if self.kind != "pair":
+                raise KernelGenError(f"{f}() needs a pair kernel")
+            return self.vec(["dx", "dy", "dz"]) if f == "delta" else ("f", "rsq")
+        args = [self.expr(a) for a in node.args]
+        if f == "sqrt":
+            return ("f", self.tmp("double", f"sqrt({args[0][1]})"))
+        if f == "abs":
+            return ("f", self.tmp("double", f"fabs({args[0][1]})"))
+        if f in ("min", "max"):                               # keywords.py:67-79: select(a < b, a, b) / select(a > b, a, b)
+            a, b = args
+            c = self.tmp("bool", f"{a[1]} {'<' if f == 'min' else '>'} {b[1]}")
+            return ("f", self.tmp("double", f"({c}) ? ({a[1]}) : ({b[1]})"))
+        if f == "select":
+            c, a, b = args
+            if self.is_vec(a) != self.is_vec(b):
+                raise KernelGenError("select(): both arms must have the same type")
+            if self.is_vec(a):
+                return self.vec([self.tmp("double", f"({c[1]}) ? ({x}) : ({y})") for x, y in zip(a[1], b[1])])
+            return ("f", self.tmp("double", f"({c[1]}) ? ({a[1]}) : ({b[1]})"))
+        if f == "dot":
+            a, b = args
+            p = [self.tmp("double", f"{x} * {y}") for x, y in zip(a[1], b[1])]
+            s = self.tmp("double", f"{p[0]} + {p[1]}")
+            return ("f", self.tmp("double", f"{s} + {p[2]}"))
+        if f in ("squared_length", "length", "normalized"):
+            v = args[0]
+            p = [self.tmp("double", f"{x} * {x}") for x in v[1]]
+            s = self.tmp("double", f"{p[0]} + {p[1]}")
+            sq = self.tmp("double", f"{s} + {p[2]}")
+            if f == "squared_length":
+                return ("f", sq)
+            ln = self.tmp("double", f"sqrt({sq})")
+            if f == "length":
+                return ("f", ln)
+            inv = self.tmp("double", f"1.0 / {ln}")          # keywords.py:105-112: v * (1.0 / length(v))
+            return self.vec([self.tmp("double", f"{x} * {inv}") for x in v[1]])
+        if f == "zero_vector":
+            return self.vec(["0.0", "0.0", "0.0"])
+        if f == "vector":
+            return self.vec([a[1] for a in args])
+        raise KernelGenError(f"unknown function '{f}'")
+
+    # -- statements --
+    def stmt(self, node):
+        if isinstance(node, ast.Expr) and isinstance(node.value, ast.Constant):
+            return                                            # docstring
+        if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
+            self.locals[node.targets[0].id] = self.expr(node.value)
+            return
+        if isinstance(node, ast.Expr) and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", None) == "apply":
+            if self.kind != "pair":
+                raise KernelGenError("apply() needs a pair kernel")
+            tgt, val = node.value.args
+            store = self.storage.get(getattr(tgt, "id", None))
+            if store not in ("force", "vel"):
+                raise KernelGenError("apply(): the target must be a vector property stored on the device")
+            v = self.expr(val)
+            if not self.is_vec(v):
+                raise KernelGenError("apply(): vector property needs a vector expression")
+            acc = self.applied.setdefault(store, [f"acc_{store}_{d}" for d in range(3)])
+            for a, c in zip(acc, v[1]):
+                self.lines.append(f"{a} = {a} + {c};")
+            return
+        if self.kind == "particle" and isinstance(node, (ast.Assign, ast.AugAssign)):
+            tgt = node.targets[0] if isinstance(node, ast.Assign) else node.target
+            if isinstance(tgt, ast.Subscript) and isinstance(tgt.value, ast.Name) and getattr(tgt.slice, "id", None) == "i":
+                store = self.storage.get(tgt.value.id)
+                if store is None:
+                    raise KernelGenError(f"property '{tgt.value.id}' is not stored on the device by this backend")
+                v = self.expr(node.value)
+                if isinstance(node, ast.AugAssign):
+                    ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
+                    v = self.binop(ops[type(node.op)], self.load(store, "i"), v)
+                self.store(store, v)
+                return
+        raise KernelGenError(f"unsupported statement: {ast.unparse(node)}")
+
+    def store(self, store, v):
+        if store == "mass":
+            if self.is_vec(v):
+                raise KernelGenError("mass is a scalar")
+            self.lines.append(f"a_mass_w[i] = {v[1]};")
+            self.loaded[(store, "i")] = v
+            return
+        if not self.is_vec(v):
+            raise KernelGenError(f"'{store}' is a vector property")
+        if store == "pos":
+            self.lines.append(f"pi.x = {v[1][0]}; pi.y = {v[1][1]}; pi.z = {v[1][2]}; a.pos_w[i] = pi;")
+            self.loaded[(store, "i")] = self.vec(["pi.x", "pi.y", "pi.z"])
+        else:
+            for d in range(3):
+                self.lines.append(f"a.{store}[{d} * (size_t) a.cap + i] = {v[1][d]};")
+            self.loaded[(store, "i")] = v
+
+
+def translate(func, storage, feature_tables, ntypes, symbols, prelude):
+    """-> (kind, kernel name, CUDA source).  `storage` maps the user's property names to device arrays."""
+    src = textwrap.dedent(inspect.getsource(func))
+    tree = ast.parse(src).body[0]
+    if not isinstance(tree, ast.FunctionDef):
+        raise KernelGenError(f"{func.__name__}: not a plain function")
+    params = [a.arg for a in tree.args.args]
+    if params == ["i", "j"]:
+        kind = "pair"
+    elif params == ["i"]:
+        kind = "particle"
+    else:
+        raise KernelGenError(f"{func.__name__}: kernels take (i) or (i, j)")
+    name = f"user_{func.__name__}"
+    g = _Gen(name, kind, storage, feature_tables, ntypes, symbols, func.__globals__)
+    for node in tree.body:
+        g.stmt(node)
+    out = [prelude]
+    for fp, table in feature_tables.items():
+        out.append(f"__device__ const double fp_{fp}[{len(table)}] = {{{', '.join(_lit(float(x)) for x in table)}}};")
+    out.append(f'extern "C" __global__ void __launch_bounds__(128) {name}(PbJitArgs a) {{')
+    out.append("    const int i = blockIdx.x * blockDim.x + threadIdx.x;")
+    out.append("    if(i >= a.nlocal || (a.flags[i] & PB_FLAG_FIXED) != 0) { return; }")
+    if kind == "pair":
+        out.append("    const double4 pi = pb_ld_pos(a.pos + i);")
+        if g.types_needed:
+            out.append(f"    const int ti = pb_w_type(pi.w) * {ntypes};")
+        out += ["    " + ln for ln in g.hoisted]
+        for store, acc in g.applied.items():
+            out += [f"    double {x} = 0.0;" for x in acc]
+        out.append("    const int nn = a.numneigh[i];")
+        out.append("    const int *nb = a.neigh + (size_t) (i >> 5) * a.nslots * 32 + (i & 31);")
+        out.append("    for(int k = 0; k < nn; k++) {")
+        out.append("        const int j = __ldg(nb + (size_t) k * 32);")
+        out.append("        const double4 pj = pb_ld_pos(a.pos + j);")
+        out.append("        const double dx = pi.x - pj.x;")          # delta(i, j) = position[i] - position[j]
+        out.append("        const double dy = pi.y - pj.y;")
+        out.append("        const double dz = pi.z - pj.z;")
+        out.append("        const double rsq_a = dx * dx;")           # (dx*dx + dy*dy) + dz*dz, one operation per statement
+        out.append("        const double rsq_b = dy * dy;")
+        out.append("        const double rsq_c = rsq_a + rsq_b;")
+        out.append("        const double rsq_d = dz * dz;")
+        out.append("        const double rsq = rsq_c + rsq_d;")
+        out.append("        if(rsq < a.cutsq) {")
+        if g.types_needed:
+            out.append("            const int tj = pb_w_type(pj.w);")
+        out += ["            " + ln for ln in g.lines]
+        out.append("        }")
+        out.append("    }")
+        for store, acc in g.applied.items():                          # prop[i] = prop[i] + acc (sim/interaction.py:280-292)
+            for d, x in enumerate(acc):
+                ref = f"a.{store}[{d} * (size_t) a.cap + i]" if d else f"a.{store}[i]"
+                out.append(f"    {ref} = {ref} + {x};")
+    else:
+        out.append("    double4 pi = a.pos_w[i];")
+        out.append("    double *a_mass_w = const_cast<double *>(a.mass);")
+        out += ["    " + ln for ln in g.lines]
+    out.append("}")
+    return kind, name, "\n".join(out) + "\n"

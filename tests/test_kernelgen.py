@@ -1,0 +1,59 @@
+"""Generic kernels (pairs_b200/kernelgen.py): translation of kernel bodies outside the hand-written families and compilation of the
+result with NVRTC for sm_100a -- neither needs a GPU.  Execution parity is in tests/test_gpu_md.py."""
+import os
+import sys
+
+import pytest
+
+from pairs_b200 import backend, dsl, kernelgen
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+
+
+def test_custom_kernels_take_the_generic_path_and_compile_for_sm100a():
+    import custom_script
+    psim = custom_script.build("gpu", 8, 10, 20, 1)
+    assert [e["family"] for e in psim.pre_step] == ["generic_particle"]
+    assert [e["family"] for e in psim.functions] == ["generic_pair", "generic_particle"]
+    storage = psim._device_storage()
+    assert storage == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force"}
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    kind, name, src = kernelgen.translate(custom_script.lennard_jones, storage, tables, 4, {"kspring": 3.5, "rsoft": 1.05}, backend.jit_prelude())
+    assert kind == "pair" and name == "user_lennard_jones"
+    # one statement per operation, symbols as literals, select with both arms evaluated, table lookup by type pair
+    assert "sqrt(rsq)" in src and "3.5 *" in src and "1.05 -" in src and "fp_epsilon[ti + tj]" in src and "? (" in src
+    assert "fp_epsilon[16] = {1.0, 1.05, 1.1," in src
+    assert backend.jit_check(src) > 1000          # cubin bytes
+    kind, name, src = kernelgen.translate(custom_script.initial_integrate, storage, tables, 4, {"dt": 0.005, "gamma": 0.05}, backend.jit_prelude())
+    assert kind == "particle" and "0.005 * 0.5" in src and "a.pos_w[i] = pi;" in src
+    assert backend.jit_check(src) > 1000
+
+
+def test_recognised_kernels_can_be_forced_through_the_generic_path():
+    import lj_script
+    dsl.FORCE_GENERIC = True
+    try:
+        psim = lj_script.build("gpu", 8, 10, 20, 1)
+    finally:
+        dsl.FORCE_GENERIC = False
+    assert [e["family"] for e in psim.functions] == ["generic_pair", "generic_particle"]
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    _, _, src = kernelgen.translate(lj_script.lennard_jones, psim._device_storage(), tables, 4, {}, backend.jit_prelude())
+    assert backend.jit_check(src) > 1000
+
+
+def test_errors_name_the_offending_construct():
+    def uses_unknown_property(i, j):
+        apply(force, delta(i, j) * charge[i])
+
+    def bad_statement(i):
+        while True:
+            pass
+
+    storage = {"position": "pos", "force": "force"}
+    with pytest.raises(kernelgen.KernelGenError, match="charge"):
+        kernelgen.translate(uses_unknown_property, storage, {}, 1, {}, "")
+    with pytest.raises(kernelgen.KernelGenError, match="unsupported statement"):
+        kernelgen.translate(bad_statement, storage, {}, 1, {}, "")
+    with pytest.raises(backend.BackendError, match="error"):
+        backend.jit_check("this is not CUDA")
