@@ -5,8 +5,9 @@ the B200 backend: examples/md.py runs unchanged, but generate() plans the per-ti
 User kernels are ordinary Python functions (examples/md.py:5-17).  The reference lowers them through an IR
 (mapping/funcs.py:285-334); this backend RECOGNISES them: the function's AST is unified with the templates of the
 hand-written kernel families below (names of properties / symbols are free, structure and literals must match) and
-bound to the corresponding CUDA kernel.  Anything else fails loudly -- there is no CPU fallback and no generic codegen
-(SURVEY.md section 8f row 3 is "next").
+bound to the corresponding CUDA kernel.  A body that matches no family is translated to CUDA and compiled at run time
+(kernelgen.py + csrc/jit.cu, for the properties the MD path stores); what cannot be translated fails loudly -- there is
+no CPU fallback.
 """
 import ast
 import inspect
@@ -223,7 +224,7 @@ def recognise(func):
             return family, {k[2:]: v for k, v in binding.items() if k.startswith("R_")}
     raise DslError(
         f"kernel '{func.__name__}' is not one of the kernel families this backend implements in CUDA "
-        f"({', '.join(TEMPLATES)}); there is no generic code generator and no CPU fallback")
+        f"({', '.join(TEMPLATES)})")
 
 
 def _unify_body(tb, ub, binding):
