@@ -148,6 +148,56 @@ __global__ void __launch_bounds__(128) k_force(int n, const int *__restrict__ nu
     force[i] = fx; force[n + i] = fy; force[2 * (size_t) n + i] = fz;
 }
 
+// the same kernel with one of every TEXMOD gathers routed through the texture path (2 x tex1Dfetch<int4>)
+__device__ __forceinline__ double4 ldtex(cudaTextureObject_t t, int j) {
+    int4 a = tex1Dfetch<int4>(t, 2 * j), b = tex1Dfetch<int4>(t, 2 * j + 1);
+    double4 r;
+    r.x = __hiloint2double(a.y, a.x); r.y = __hiloint2double(a.w, a.z);
+    r.z = __hiloint2double(b.y, b.x); r.w = __hiloint2double(b.w, b.z);
+    return r;
+}
+
+template<int TEXMOD>
+__global__ void __launch_bounds__(128) k_force_mix(int n, const int *__restrict__ numneigh, const int *__restrict__ neigh, const double4 *__restrict__ pos,
+                                                   cudaTextureObject_t tex, double *__restrict__ force) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const double4 p = ld256(pos + i);
+    const int nn = numneigh[i];
+    const int *nb = neigh + (size_t) (i / 32) * T * 32 + (i % 32);
+    double fx = 0, fy = 0, fz = 0;
+    int k = 0;
+    for(; k + 4 <= nn; k += 4) {
+        int j[4]; double4 q[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++) j[u] = __ldg(nb + (size_t) (k + u) * 32);
+#pragma unroll
+        for(int u = 0; u < 4; u++) q[u] = (u % TEXMOD == 0) ? ldtex(tex, j[u]) : ld256(pos + j[u]);
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            double dx = p.x - q[u].x, dy = p.y - q[u].y, dz = p.z - q[u].z;
+            double r2 = dx * dx + dy * dy + dz * dz;
+            if(r2 < 6.25) {
+                double sr2 = 1.0 / r2, sr6 = sr2 * sr2 * sr2;
+                double f = 48.0 * sr6 * (sr6 - 0.5) * sr2;
+                fx += dx * f; fy += dy * f; fz += dz * f;
+            }
+        }
+    }
+    for(; k < nn; k++) {
+        int j = __ldg(nb + (size_t) k * 32);
+        double4 q = ld256(pos + j);
+        double dx = p.x - q.x, dy = p.y - q.y, dz = p.z - q.z;
+        double r2 = dx * dx + dy * dy + dz * dz;
+        if(r2 < 6.25) {
+            double sr2 = 1.0 / r2, sr6 = sr2 * sr2 * sr2;
+            double f = 48.0 * sr6 * (sr6 - 0.5) * sr2;
+            fx += dx * f; fy += dy * f; fz += dz * f;
+        }
+    }
+    force[i] = fx; force[n + i] = fy; force[2 * (size_t) n + i] = fz;
+}
+
 // the same kernel with SoA positions (x[], y[], z[]): 16 particles per 128-byte line instead of 4, three 64-bit gathers per neighbour
 __global__ void __launch_bounds__(128) k_force_soa(int n, const int *__restrict__ numneigh, const int *__restrict__ neigh, const double *__restrict__ X,
                                                    const double *__restrict__ Y, const double *__restrict__ Z, double *__restrict__ force) {
@@ -283,6 +333,25 @@ int main(int argc, char **argv) {
         float ms2;
         cudaEventElapsedTime(&ms2, e0, e1);
         double fsum2 = thrust::reduce(force.begin(), force.end(), 0.0);
+        if(mode == 0) {
+            cudaResourceDesc rd = {}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = thrust::raw_pointer_cast(pos.data());
+            rd.res.linear.desc = cudaCreateChannelDesc<int4>(); rd.res.linear.sizeInBytes = (size_t) n * 32;
+            cudaTextureDesc td = {}; td.readMode = cudaReadModeElementType;
+            cudaTextureObject_t tex; CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+            auto timeit = [&](const char *name, auto kern) {
+                for(int w = 0; w < 3; w++) kern<<<(n + 127) / 128, 128>>>(n, thrust::raw_pointer_cast(numneigh.data()), thrust::raw_pointer_cast(neigh.data()), thrust::raw_pointer_cast(pos.data()), tex, thrust::raw_pointer_cast(force.data()));
+                cudaEventRecord(e0);
+                for(int r = 0; r < R; r++) kern<<<(n + 127) / 128, 128>>>(n, thrust::raw_pointer_cast(numneigh.data()), thrust::raw_pointer_cast(neigh.data()), thrust::raw_pointer_cast(pos.data()), tex, thrust::raw_pointer_cast(force.data()));
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                float t; cudaEventElapsedTime(&t, e0, e1);
+                printf("        %s: %.4f ms, checksum %.3e\n", name, t / R, thrust::reduce(force.begin(), force.end(), 0.0));
+            };
+            timeit("TEX 1 of 4", k_force_mix<4>);
+            timeit("TEX 1 of 2", k_force_mix<2>);
+            timeit("TEX all   ", k_force_mix<1>);
+            cudaDestroyTextureObject(tex);
+        }
         printf("mode %d: mean neighbours %.2f, lines per warp gather %.2f (AoS 32 B) / %.2f (SoA 8 B), force kernel AoS %.4f ms (%.3e atoms/s), SoA %.4f ms (%.3e atoms/s), checksums %.3e %.3e\n", mode,
                tot / (double) n, hs[0] / (double) hs[1], hs[2] / (double) hs[1], ms / R, n / (ms / R * 1e-3), ms2 / R, n / (ms2 / R * 1e-3), fsum, fsum2);
     }
