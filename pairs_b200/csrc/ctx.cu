@@ -304,8 +304,9 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     ctx->cells_n = 0;
     if(n == 0) { return 0; }
     const int T = 256, B = pb_blocks(n, T);
-    double *stage = nullptr;
-    PB_CHECK(cudaMalloc(&stage, sizeof(double) * 3 * (size_t) n));
+    PbScratch stage_buf;
+    PB_CHECK(stage_buf.alloc(sizeof(double) * 3 * (size_t) n));
+    double *const stage = stage_buf.as<double>();
     auto upload_int = [&](const int *src, int *dst, int dflt) -> int {
         if(src != nullptr) {
             PB_CHECK(cudaMemcpyAsync(dst, src, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
@@ -342,7 +343,6 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     }
     ctx->force_is_zero = false;
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(stage));
     return 0;
 }
 
@@ -365,8 +365,9 @@ extern "C" int pb_download_real(pb_ctx *ctx, const char *name, double *out, int 
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
         return 0;
     }
-    double *stage = nullptr;
-    PB_CHECK(cudaMalloc(&stage, sizeof(double) * 3 * (size_t) n));
+    PbScratch stage_buf;
+    PB_CHECK(stage_buf.alloc(sizeof(double) * 3 * (size_t) n));
+    double *const stage = stage_buf.as<double>();
     if(nm == "position") {
         PB_LAUNCH(pb_k_unpack_pos, B, T, n, ctx->pos, stage);
     } else if(nm == "linear_velocity") {
@@ -375,13 +376,11 @@ extern "C" int pb_download_real(pb_ctx *ctx, const char *name, double *out, int 
         PB_TRY(pb_materialise_force_reset(ctx));
         PB_LAUNCH(pb_k_soa3_to_aos, B, T, n, ctx->pcap, ctx->force, stage);
     } else {
-        cudaFree(stage);
         ctx->set_error("pb_download_real: unknown property " + nm);
         return -1;
     }
     PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(double) * 3 * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(stage));
     return 0;
 }
 

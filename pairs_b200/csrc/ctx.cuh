@@ -176,6 +176,17 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed);
 int pb_ensure_send_capacity(pb_ctx *ctx, int needed);
 int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n);   // out[0..n], out[n] = total
 int pb_bin_particles(pb_ctx *ctx, int first, int n, bool write_particle_cell);
+// Scratch device memory of the set-up / test paths (upload, download): released on every exit path, error returns included.
+struct PbScratch {
+    void *p = nullptr;
+    PbScratch() = default;
+    PbScratch(const PbScratch &) = delete;
+    PbScratch &operator=(const PbScratch &) = delete;
+    ~PbScratch() { if(p != nullptr) { cudaFree(p); } }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+    template<typename T> T *as() const { return (T *) p; }
+};
+
 int pb_dem_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used);
 int pb_dem_sort_locals(pb_ctx *ctx);
 int pb_sort_locals(pb_ctx *ctx);

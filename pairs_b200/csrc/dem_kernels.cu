@@ -224,12 +224,12 @@ extern "C" int pb_dem_upload_real(pb_ctx *ctx, const char *name, int first, int 
     if(!ctx->dem || !pb_dem_prop(ctx, name, &pr)) { ctx->set_error(std::string("pb_dem_upload_real: unknown property ") + name); return -1; }
     if(first + n > ctx->pcap) { ctx->set_error("pb_dem_upload_real: beyond capacity"); return -1; }
     if(n == 0) { return 0; }
-    double *stage = nullptr;
-    PB_CHECK(cudaMalloc(&stage, sizeof(double) * (size_t) n * pr.comps));
+    PbScratch stage_buf;
+    PB_CHECK(stage_buf.alloc(sizeof(double) * (size_t) n * pr.comps));
+    double *const stage = stage_buf.as<double>();
     PB_CHECK(cudaMemcpyAsync(stage, data, sizeof(double) * (size_t) n * pr.comps, cudaMemcpyHostToDevice, ctx->stream));
     PB_LAUNCH(pb_k_aos_to_soa, pb_blocks(n, 256), 256, n, ctx->pcap, pr.comps, stage, pr.ptr + first);
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(stage));
     if(std::string(name) == "force") { ctx->force_is_zero = false; }
     return 0;
 }
@@ -240,12 +240,12 @@ extern "C" int pb_dem_download_real(pb_ctx *ctx, const char *name, int first, in
     if(!ctx->dem || !pb_dem_prop(ctx, name, &pr)) { ctx->set_error(std::string("pb_dem_download_real: unknown property ") + name); return -1; }
     if(n == 0) { return 0; }
     if(std::string(name) == "force" || std::string(name) == "torque") { PB_TRY(pb_materialise_force_reset(ctx)); }
-    double *stage = nullptr;
-    PB_CHECK(cudaMalloc(&stage, sizeof(double) * (size_t) n * pr.comps));
+    PbScratch stage_buf;
+    PB_CHECK(stage_buf.alloc(sizeof(double) * (size_t) n * pr.comps));
+    double *const stage = stage_buf.as<double>();
     PB_LAUNCH(pb_k_soa_to_aos, pb_blocks(n, 256), 256, n, ctx->pcap, pr.comps, pr.ptr + first, stage);
     PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(double) * (size_t) n * pr.comps, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(stage));
     return 0;
 }
 
@@ -295,13 +295,14 @@ extern "C" int pb_dem_upload_contacts(pb_ctx *ctx, int n, const int *num, const 
     if(!ctx->dem || n > ctx->pcap) { ctx->set_error("pb_dem_upload_contacts: DEM not enabled / beyond capacity"); return -1; }
     if(n == 0) { return 0; }
     const int C = ctx->ccontacts;
-    int *d_num, *d_uid, *d_st;
-    double *d_tsd, *d_ivm;
-    PB_CHECK(cudaMalloc(&d_num, sizeof(int) * n));
-    PB_CHECK(cudaMalloc(&d_uid, sizeof(int) * (size_t) n * C));
-    PB_CHECK(cudaMalloc(&d_st, sizeof(int) * (size_t) n * C));
-    PB_CHECK(cudaMalloc(&d_tsd, sizeof(double) * (size_t) n * C * 3));
-    PB_CHECK(cudaMalloc(&d_ivm, sizeof(double) * (size_t) n * C));
+    PbScratch b_num, b_uid, b_st, b_tsd, b_ivm;
+    PB_CHECK(b_num.alloc(sizeof(int) * n));
+    PB_CHECK(b_uid.alloc(sizeof(int) * (size_t) n * C));
+    PB_CHECK(b_st.alloc(sizeof(int) * (size_t) n * C));
+    PB_CHECK(b_tsd.alloc(sizeof(double) * (size_t) n * C * 3));
+    PB_CHECK(b_ivm.alloc(sizeof(double) * (size_t) n * C));
+    int *d_num = b_num.as<int>(), *d_uid = b_uid.as<int>(), *d_st = b_st.as<int>();
+    double *d_tsd = b_tsd.as<double>(), *d_ivm = b_ivm.as<double>();
     PB_CHECK(cudaMemcpy(d_num, num, sizeof(int) * n, cudaMemcpyHostToDevice));
     PB_CHECK(cudaMemcpy(d_uid, uid, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice));
     PB_CHECK(cudaMemcpy(d_st, sticking, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice));
@@ -310,7 +311,6 @@ extern "C" int pb_dem_upload_contacts(pb_ctx *ctx, int n, const int *num, const 
     PB_LAUNCH(pb_k_contacts_in, pb_blocks(n, 128), 128, n, ctx->pcap, C, d_num, d_uid, d_st, d_tsd, d_ivm, ctx->num_contacts,
               ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm);
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_num); cudaFree(d_uid); cudaFree(d_st); cudaFree(d_tsd); cudaFree(d_ivm);
     return 0;
 }
 
@@ -319,14 +319,15 @@ extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, 
     if(!ctx->dem || n > ctx->pcap) { ctx->set_error("pb_dem_download_contacts: DEM not enabled / beyond capacity"); return -1; }
     if(n == 0) { return 0; }
     const int C = ctx->ccontacts;
-    int *d_num, *d_uid, *d_us, *d_st;
-    double *d_tsd, *d_ivm;
-    PB_CHECK(cudaMalloc(&d_num, sizeof(int) * n));
-    PB_CHECK(cudaMalloc(&d_uid, sizeof(int) * (size_t) n * C));
-    PB_CHECK(cudaMalloc(&d_us, sizeof(int) * (size_t) n * C));
-    PB_CHECK(cudaMalloc(&d_st, sizeof(int) * (size_t) n * C));
-    PB_CHECK(cudaMalloc(&d_tsd, sizeof(double) * (size_t) n * C * 3));
-    PB_CHECK(cudaMalloc(&d_ivm, sizeof(double) * (size_t) n * C));
+    PbScratch b_num, b_uid, b_us, b_st, b_tsd, b_ivm;
+    PB_CHECK(b_num.alloc(sizeof(int) * n));
+    PB_CHECK(b_uid.alloc(sizeof(int) * (size_t) n * C));
+    PB_CHECK(b_us.alloc(sizeof(int) * (size_t) n * C));
+    PB_CHECK(b_st.alloc(sizeof(int) * (size_t) n * C));
+    PB_CHECK(b_tsd.alloc(sizeof(double) * (size_t) n * C * 3));
+    PB_CHECK(b_ivm.alloc(sizeof(double) * (size_t) n * C));
+    int *d_num = b_num.as<int>(), *d_uid = b_uid.as<int>(), *d_us = b_us.as<int>(), *d_st = b_st.as<int>();
+    double *d_tsd = b_tsd.as<double>(), *d_ivm = b_ivm.as<double>();
     PB_LAUNCH(pb_k_contacts_out, pb_blocks(n, 128), 128, n, ctx->pcap, C, ctx->num_contacts, ctx->contact_uid, ctx->contact_used,
               ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, d_num, d_uid, d_us, d_st, d_tsd, d_ivm);
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -336,7 +337,6 @@ extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, 
     PB_CHECK(cudaMemcpy(sticking, d_st, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
     PB_CHECK(cudaMemcpy(tsd, d_tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyDeviceToHost));
     PB_CHECK(cudaMemcpy(ivm, d_ivm, sizeof(double) * (size_t) n * C, cudaMemcpyDeviceToHost));
-    cudaFree(d_num); cudaFree(d_uid); cudaFree(d_us); cudaFree(d_st); cudaFree(d_tsd); cudaFree(d_ivm);
     return 0;
 }
 

@@ -651,15 +651,15 @@ extern "C" int pb_lj_energy_virial(pb_ctx *ctx, double cutoff, double *epot, dou
     const int n = ctx->nlocal;
     if(n == 0) { return 0; }
     const int B = pb_blocks(n, 128);
-    double *partial = nullptr;
-    PB_CHECK(cudaMalloc(&partial, sizeof(double) * 2 * ((size_t) B + 1)));
+    PbScratch partial_buf;
+    PB_CHECK(partial_buf.alloc(sizeof(double) * 2 * ((size_t) B + 1)));
+    double *const partial = partial_buf.as<double>();
     PB_LAUNCH(pb_k_lj_energy_virial, B, 128, n, ctx->nslots, cutoff * cutoff, ctx->ntypes, ctx->d_eps, ctx->d_sig6, ctx->pos, ctx->flags,
               ctx->numneigh, ctx->neigh, partial, ctx->half_lists ? 1 : 0);
     PB_LAUNCH(pb_k_sum_pairs, 1, 256, B, partial, partial + 2 * (size_t) B);
     double h[2];
     PB_CHECK(cudaMemcpyAsync(h, partial + 2 * (size_t) B, sizeof(double) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(partial));
     *epot = 0.5 * h[0];
     *virial = 0.5 * h[1];
     return 0;

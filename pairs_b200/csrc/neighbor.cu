@@ -258,11 +258,11 @@ extern "C" int pb_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
     PB_CHECK(cudaSetDevice(ctx->device));
     const int n = ctx->neigh_n;
     if(n == 0) { return 0; }
-    int *stage = nullptr;
-    PB_CHECK(cudaMalloc(&stage, sizeof(int) * (size_t) n * (size_t) capacity));
+    PbScratch stage_buf;
+    PB_CHECK(stage_buf.alloc(sizeof(int) * (size_t) n * (size_t) capacity));
+    int *const stage = stage_buf.as<int>();
     PB_LAUNCH(pb_k_neigh_to_aos, pb_blocks(n, 128), 128, n, capacity, ctx->ncap, pb_layout(ctx), ctx->neigh, ctx->numneigh, stage);
     PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(int) * (size_t) n * (size_t) capacity, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaFree(stage));
     return 0;
 }
