@@ -67,6 +67,7 @@ struct pb_ctx {
     int *type = nullptr, *type_alt = nullptr, *flags = nullptr, *flags_alt = nullptr;
     int *uid = nullptr, *uid_alt = nullptr, *shape = nullptr, *shape_alt = nullptr, *tag = nullptr, *tag_alt = nullptr;
     bool ghosts_in_alt = false;   // after a fused initial_integrate: ghosts of the last refresh still live in pos_alt
+    bool dem_fuse = true;         // pb_dem_run folds usage reset / volatile reset / gravity / history clean-up into the contact kernel
     int dem_sort_every = 200;     // DEM: re-sort the locals into cell order every so many iterations (0 = never; option "dem_sort_every")
     bool half_lists = false;      // compute_half(): lists hold j with i < j only, the force kernel updates both partners
     bool fuse_integrate = true;   // pb_md_run folds the integrator halves into the force kernel's epilogue

@@ -688,6 +688,14 @@ __global__ void __launch_bounds__(128) pb_k_dem_detect(int nlocal, int cap, int 
     npairs[i] = np;
 }
 
+// FUSED folds the cheap per-particle modules around the contact evaluation of the generated loop into this kernel (the thread
+// owns particle i's force, torque and contact row anyway):
+//   reset_volatile_properties + gravity    f = 0; f.z = gravity(f.z)   before the contact sums are added, same operations
+//   reset_contact_history_usage_status     the "used" marks live in a register bit mask (contact capacity <= 32)
+//   clear_unused_contact_history           the swap-with-last compaction runs on the row at the end, driven by the mask
+// (euler sits between the contact kernel and the clean-up in the reference's list; it touches no contact data, so the order
+// does not matter).  Nine launches -- six memsets and three kernels -- and their passes over the arrays disappear.
+template<bool FUSED>
 __global__ void __launch_bounds__(128) pb_k_dem_force(int nlocal, int cap, int C, int ntypes, PbDemParams P, const double4 *__restrict__ pos,
                                                       const double *__restrict__ vel, const double *__restrict__ angvel,
                                                       const double *__restrict__ mass, const double *__restrict__ radius,
@@ -704,6 +712,8 @@ __global__ void __launch_bounds__(128) pb_k_dem_force(int nlocal, int cap, int C
     const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
     double Fs[3] = {0.0, 0.0, 0.0}, Ts[3] = {0.0, 0.0, 0.0}, Fh[3] = {0.0, 0.0, 0.0}, Th[3] = {0.0, 0.0, 0.0};
     const int np = npairs[i];
+    unsigned usedmask = 0u;
+    int ncont_end = FUSED ? num_contacts[i] : 0;
     if(!fixed && np > 0) {
         const double4 pi4 = pb_ld_pos(pos + i);
         const double xi[3] = {pi4.x, pi4.y, pi4.z};
@@ -738,7 +748,7 @@ __global__ void __launch_bounds__(128) pb_k_dem_force(int nlocal, int cap, int C
                 for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = 0.0; }
                 c_ivm[(size_t) slot * cap + i] = 0.0;
             }
-            c_used[(size_t) slot * cap + i] = 1;
+            if(FUSED) { usedmask |= 1u << slot; } else { c_used[(size_t) slot * cap + i] = 1; }
             double tsd[3] = {c_tsd[((size_t) 0 * C + slot) * cap + i], c_tsd[((size_t) 1 * C + slot) * cap + i],
                              c_tsd[((size_t) 2 * C + slot) * cap + i]};
             double ivm = c_ivm[(size_t) slot * cap + i];
@@ -754,12 +764,34 @@ __global__ void __launch_bounds__(128) pb_k_dem_force(int nlocal, int cap, int C
             c_stick[(size_t) slot * cap + i] = stick;
             for(int d = 0; d < 3; d++) { F[d] = F[d] + Fp[d]; T[d] = T[d] + Tp[d]; }
         }
-        num_contacts[i] = ncont;
+        if(FUSED) { ncont_end = ncont; } else { num_contacts[i] = ncont; }
+    }
+    if(FUSED) {
+        // clear_unused_contact_history (sim/contact_history.py:90-127): an unused slot is overwritten by the last one
+        int c = 0, cnt = ncont_end;
+        while(c < cnt) {
+            if(((usedmask >> c) & 1u) == 0u) {
+                const int last = cnt - 1;
+                if(last > 0) {
+                    c_stick[(size_t) c * cap + i] = c_stick[(size_t) last * cap + i];
+                    for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + c) * cap + i] = c_tsd[((size_t) d * C + last) * cap + i]; }
+                    c_ivm[(size_t) c * cap + i] = c_ivm[(size_t) last * cap + i];
+                    c_uid[(size_t) c * cap + i] = c_uid[(size_t) last * cap + i];
+                    usedmask = (usedmask & ~(1u << c)) | (((usedmask >> last) & 1u) << c);
+                }
+                cnt--;
+            } else {
+                c++;
+            }
+        }
+        for(int k = 0; k < cnt; k++) { c_used[(size_t) k * cap + i] = 1; }
+        num_contacts[i] = cnt;
     }
     // prop[i] = prop[i] + (acc_sphere + acc_halfspace)  (sim/interaction.py:280-292)
     for(int d = 0; d < 3; d++) {
-        const double f_old = accumulate ? force[(size_t) d * cap + i] : 0.0;
+        double f_old = accumulate ? force[(size_t) d * cap + i] : 0.0;
         const double t_old = accumulate ? torque[(size_t) d * cap + i] : 0.0;
+        if(FUSED && d == 2 && !fixed) { f_old = pb_dem_gravity(P, radius[i], f_old); }      // gravity on the freshly reset force
         if(!fixed) {
             force[(size_t) d * cap + i] = f_old + (Fs[d] + Fh[d]);
             torque[(size_t) d * cap + i] = t_old + (Ts[d] + Th[d]);
@@ -785,11 +817,10 @@ extern "C" int pb_dem_linear_spring_dashpot(pb_ctx *ctx) {
         PB_CHECK(cudaMalloc(&ctx->neigh, need));
         ctx->neigh_bytes = need;
     }
-    PB_CHECK(cudaMemsetAsync(ctx->d_dem_flag, 0, sizeof(int), ctx->stream));
     PB_LAUNCH(pb_k_dem_detect, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], C,
               ctx->pos, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->numneigh,
               ctx->neigh, ctx->d_dem_flag);
-    PB_LAUNCH(pb_k_dem_force, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, C, ctx->dem_ntypes, pb_dem_params(ctx), ctx->pos, ctx->vel,
+    PB_LAUNCH(pb_k_dem_force<false>, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, C, ctx->dem_ntypes, pb_dem_params(ctx), ctx->pos, ctx->vel,
               ctx->angvel, ctx->mass, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->uid, ctx->numneigh, ctx->neigh,
               ctx->d_fric_static, ctx->d_fric_dynamic, ctx->num_contacts, ctx->contact_uid, ctx->contact_used, ctx->contact_stick,
               ctx->contact_tsd, ctx->contact_ivm, ctx->force, ctx->torque, 1, ctx->d_dem_flag);
@@ -797,10 +828,36 @@ extern "C" int pb_dem_linear_spring_dashpot(pb_ctx *ctx) {
     return 0;
 }
 
-// returns > 0 (needed capacity) if a particle ran out of contact slots since the last check
+// reset_contact_history_usage_status + reset_volatile_properties + gravity + linear_spring_dashpot + clear_unused_contact_history
+// of one iteration of the generated loop, in two launches (pb_dem_run; contact capacity <= 32)
+static int pb_dem_contacts_fused(pb_ctx *ctx) {
+    PbStage st(ctx, "linear_spring_dashpot");
+    if(ctx->cells_n != ctx->nlocal + ctx->nghost) { ctx->set_error("pb_dem_run: cell lists are stale"); return -1; }
+    ctx->force_is_zero = false;
+    if(ctx->nlocal == 0) { return 0; }
+    const int C = ctx->ccontacts;
+    const size_t need = sizeof(int) * (size_t) C * (size_t) ctx->pcap;
+    if(need > ctx->neigh_bytes) {
+        if(ctx->neigh != nullptr) { PB_CHECK(cudaFree(ctx->neigh)); ctx->neigh = nullptr; }
+        PB_CHECK(cudaMalloc(&ctx->neigh, need));
+        ctx->neigh_bytes = need;
+    }
+    PB_LAUNCH(pb_k_dem_detect, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], C,
+              ctx->pos, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->numneigh,
+              ctx->neigh, ctx->d_dem_flag);
+    PB_LAUNCH(pb_k_dem_force<true>, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, C, ctx->dem_ntypes, pb_dem_params(ctx), ctx->pos, ctx->vel,
+              ctx->angvel, ctx->mass, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->uid, ctx->numneigh, ctx->neigh,
+              ctx->d_fric_static, ctx->d_fric_dynamic, ctx->num_contacts, ctx->contact_uid, ctx->contact_used, ctx->contact_stick,
+              ctx->contact_tsd, ctx->contact_ivm, ctx->force, ctx->torque, 0, ctx->d_dem_flag);
+    ctx->neigh_n = -1;
+    return 0;
+}
+
+// returns > 0 (needed capacity) if a particle ran out of contact slots since the last check (the mark is read and cleared)
 extern "C" int pb_dem_contact_overflow(pb_ctx *ctx) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_dem_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemsetAsync(ctx->d_dem_flag, 0, sizeof(int), ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     return ctx->h_scalars[0];
 }
@@ -848,12 +905,17 @@ extern "C" int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts
         if(ctx->dem_sort_every > 0 && ts > 0 && ts % ctx->dem_sort_every == 0) { PB_TRY(pb_dem_sort_locals(ctx)); }
         PB_TRY(pb_borders(ctx));
         PB_TRY(pb_build_cell_lists(ctx));
-        PB_TRY(pb_dem_reset_contact_usage(ctx));
-        PB_TRY(pb_reset_volatile(ctx));
-        PB_TRY(pb_dem_gravity(ctx));
-        PB_TRY(pb_dem_linear_spring_dashpot(ctx));
-        PB_TRY(pb_dem_euler(ctx));
-        PB_TRY(pb_dem_clear_unused_contacts(ctx));
+        if(ctx->ccontacts <= 32 && ctx->dem_fuse) {
+            PB_TRY(pb_dem_contacts_fused(ctx));      // usage reset + volatile reset + gravity + contacts + history clean-up
+            PB_TRY(pb_dem_euler(ctx));
+        } else {
+            PB_TRY(pb_dem_reset_contact_usage(ctx));
+            PB_TRY(pb_reset_volatile(ctx));
+            PB_TRY(pb_dem_gravity(ctx));
+            PB_TRY(pb_dem_linear_spring_dashpot(ctx));
+            PB_TRY(pb_dem_euler(ctx));
+            PB_TRY(pb_dem_clear_unused_contacts(ctx));
+        }
     }
     const int need = pb_dem_contact_overflow(ctx);
     if(need > 0) { ctx->set_error("contact capacity exceeded: a particle needs " + std::to_string(need) + " contact slots"); return -1; }
