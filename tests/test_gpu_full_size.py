@@ -1,0 +1,84 @@
+"""BASELINE.json's configurations at FULL size on the GPU.
+
+C1 (examples/md.py as shipped: 32^3 cells = 131,072 atoms, 200 steps) is small enough for the oracle: thermo of the reference's
+three output lines to 1e-9 and to the six digits the reference prints.
+C2 (4,000,000 atoms) is checked through size-independent properties: total momentum and total force vanish (Newton's third
+law over 3 x 10^8 pair terms), the total energy is conserved by velocity-Verlet, the half and the full neighbour lists describe
+the same set of pairs (identical potential energy and virial), and a run is reproducible bit for bit."""
+import numpy as np
+import pytest
+
+from tests.test_gpu_md import CUT, DT, SKIN, make_gpu, make_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config_c1_stock_md_py_against_the_oracle():
+    ctx, n = make_gpu(32)
+    assert n == 131072
+    sim = make_oracle(32)
+    th = ctx.md_run(0, 201, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 100)
+    assert [int(r[0]) for r in th] == [0, 99, 199]
+    ref = {}
+    for ts in range(200):
+        sim.step(ts)
+        if ts in (0, 99, 199):
+            ref[ts] = sim.thermo()
+    for row in th:
+        t_o, p_o = ref[int(row[0])]
+        assert abs(row[1] - t_o) <= 1e-9 * t_o and abs(row[2] - p_o) <= 1e-9 * p_o, row
+    # the lines the stock reference program prints (BASELINE.md / SURVEY.md section 6), six significant digits
+    assert [f"{r[1]:.6g}\t{r[2]:.6g}" for r in th] == ["1.44\t1.21564", "0.820671\t0.692805", "0.79644\t0.67235"]
+    r = sim.ranks[0]
+    assert ctx.counts() == (r.nlocal, r.nghost)
+
+
+def test_config_c2_four_million_atoms_invariants():
+    ctx, n = make_gpu(100)
+    assert n == 4000000
+    ctx.md_run(0, 21, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)          # melt a little; ends one step after a reneighbouring
+
+    def totals():
+        m = ctx.real("mass")
+        v = ctx.real("linear_velocity")
+        f = ctx.real("force")
+        ekin = 0.5 * float((m * (v * v).sum(axis=1)).sum())
+        return (m[:, None] * v).sum(axis=0), np.abs(m[:, None] * v).sum(), f.sum(axis=0), np.abs(f).sum(), ekin
+
+    p0, pabs, _, _, ek0 = totals()
+    # adjust_thermo removed the centre-of-mass motion.  Momentum is conserved only approximately afterwards -- in the reference
+    # too: between two reneighbourings the edge and corner ghosts lag one step behind (Comm.synchronize packs every send entry
+    # before it unpacks, sim/comm.py:45-54), so the few pairs across box edges are not exactly antisymmetric.
+    assert np.abs(p0).max() <= 1e-5 * pabs, (p0, pabs)
+    # right after a reneighbouring every ghost is a fresh copy of its source: the pair forces cancel to round-off
+    ctx.exchange(); ctx.borders(); ctx.build_cell_lists(); ctx.build_neighbor_lists(CUT + SKIN)
+    ctx.reset_volatile(); ctx.lennard_jones(CUT)
+    f = ctx.real("force")
+    assert np.abs(f.sum(axis=0)).max() <= 1e-9 * np.abs(f).sum()
+    ep0, w0 = ctx.lj_energy_virial(CUT)
+    # half lists describe the same pairs
+    ctx.set_option("compute_half", 1)
+    ctx.build_neighbor_lists(CUT + SKIN)
+    ep_h, w_h = ctx.lj_energy_virial(CUT)
+    assert abs(ep_h - ep0) <= 1e-11 * abs(ep0) and abs(w_h - w0) <= 1e-11 * abs(w0)
+    assert int(ctx.ints("numneighs").sum()) < 0.56 * 78 * n
+    ctx.set_option("compute_half", 0)
+    ctx.build_neighbor_lists(CUT + SKIN)
+    pos, vel = ctx.real("position"), ctx.real("linear_velocity")
+    tag = ctx.ints("tag")
+    th_a = ctx.md_run(21, 60, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
+    _, _, _, _, ek1 = totals()
+    ctx.exchange(); ctx.borders(); ctx.build_cell_lists(); ctx.build_neighbor_lists(CUT + SKIN)
+    ep1, _ = ctx.lj_energy_virial(CUT)
+    e0, e1 = ek0 + ep0, ek1 + ep1
+    # velocity-Verlet with dt = 0.005 on the truncated, unshifted potential while the lattice is still melting: the total
+    # energy moves by a small fraction of the kinetic energy (a wrong force or integrator shows up as O(1))
+    print(f"C2 energy: E(20) = {e0:.9e}, E(59) = {e1:.9e}, drift / E_kin = {(e1 - e0) / ek0:.3e}")
+    assert abs(e1 - e0) <= 2e-2 * abs(ek0), (e0, e1, ek0)
+    p1 = totals()[0]
+    assert np.abs(p1).max() <= 1e-5 * pabs, (p1, pabs)
+    # reproducibility: the same 39 steps from the same state give the same bits (no atomics on the force path)
+    order = np.argsort(tag)
+    ctx.upload(pos[order], vel[order], ctx.real("mass")[np.argsort(ctx.ints("tag"))], ctx.ints("type")[np.argsort(ctx.ints("tag"))])
+    th_b = ctx.md_run(21, 60, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
+    assert th_a.shape == th_b.shape and abs(th_a[-1, 1] - th_b[-1, 1]) <= 1e-12 * th_a[-1, 1]
