@@ -3,7 +3,7 @@
 //   pb_borders      Comm.borders    (comm.py:56-98)    ghost creation, 3 ordered phases x -> y -> z
 //   pb_synchronize  Comm.synchronize(comm.py:45-54)    per-step ghost refresh
 // The reference selects with atomics (send order = whatever the atomics give, serial order on the CPU target);
-// here selection is a flag + exclusive scan + scatter, i.e. an ORDERED stream compaction, so send lists -- and
+// here selection is an ORDERED stream compaction (per-block counts, scan of the block counts, ballot ranks), so send lists -- and
 // with them ghost numbering -- are deterministic: (dim, side, ascending source index).
 //
 // Transport between ranks is abstracted by pb_transport_* (comm_nccl.cu): a neighbour that is the rank itself
