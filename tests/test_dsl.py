@@ -158,3 +158,33 @@ def test_vtk_writer_reproduces_reference_file_bytes(tmp_path):
     txt = open(out).read()
     assert "POINTS 2 double" in txt and "CELLS 2 4\n1 0\n1 2\n" in txt
     assert not dsl.vtk_write(str(tmp_path / "missing_dir" / "x.vtk"), position, masses, flags)
+
+
+def test_multi_rank_read_particle_data_keeps_own_rows_and_global_bodies():
+    """runtime/read_from_file.hpp:44-106: a rank keeps the rows inside its sub-box (x < max - 1e-5) plus infinite / fixed / global bodies."""
+    class FakeCtx:
+        def decomposition(self):
+            return {"nranks": np.array([2, 1, 1]), "subdom": np.array([0.0, 0.5, 0.0, 1.0, 0.0, 1.0])}
+
+    part = {"position": np.array([[0.1, 0.5, 0.5], [0.5 - 1e-6, 0.5, 0.5], [0.7, 0.5, 0.5], [0.9, 0.2, 0.2]]),
+            "uid": np.array([1, 2, 3, 4], np.int32), "flags": np.array([0, 0, 0, 13], np.int32), "shape": np.array([0, 0, 0, 1], np.int32)}
+    kept = dsl.Simulation._keep_own(FakeCtx(), part)
+    assert list(kept["uid"]) == [1, 4]            # row 2 sits inside the 1e-5 exclusion band at the upper face, row 4 is a global plane
+    assert kept["position"].shape == (2, 3) and list(kept["shape"]) == [0, 1]
+
+    class OneRank(FakeCtx):
+        def decomposition(self):
+            return {"nranks": np.array([1, 1, 1]), "subdom": np.array([0.0, 1.0, 0.0, 1.0, 0.0, 1.0])}
+    assert dsl.Simulation._keep_own(OneRank(), part) is part
+
+
+def test_generic_kernels_need_the_md_path_properties():
+    import lj_script
+
+    def charged(i, j):
+        apply(force, delta(i, j) * charge[i] * charge[j])
+
+    psim = lj_script.build("gpu", 8, 10, 20, 1)
+    psim.add_property("charge", pairs.real(), 0.0)
+    with pytest.raises(dsl.DslError, match="one real property"):
+        psim._device_storage()

@@ -57,3 +57,55 @@ def test_errors_name_the_offending_construct():
         kernelgen.translate(bad_statement, storage, {}, 1, {}, "")
     with pytest.raises(backend.BackendError, match="error"):
         backend.jit_check("this is not CUDA")
+
+
+def test_vocabulary_translates_and_compiles():
+    """Every keyword the generic path knows, in one pair kernel and one particle kernel; operation order is Python's."""
+    def pair(i, j):
+        d = delta(i, j)
+        r2 = squared_distance(i, j)
+        u = normalized(d)
+        w = linear_velocity[i] - linear_velocity[j]
+        vn = dot(w, u)
+        s = select(vn < 0.0, -vn, 0.0)
+        a = min(r2, rcap) + max(length(d), 0.5) + abs(vn) + squared_length(w) + sqrt(r2)
+        apply(force, u * (kn * s / a) + zero_vector() - vector(0.0, 0.0, g) * mass[i] * mass[j])
+
+    def particle(i):
+        linear_velocity[i] = linear_velocity[i] * damp + force[i] * (dt / mass[i])
+        position[i] += linear_velocity[i] * dt
+        force[i] -= force[i]
+
+    storage = {"position": "pos", "linear_velocity": "vel", "force": "force", "mass": "mass"}
+    kind, name, src = kernelgen.translate(pair, storage, {}, 1, {"rcap": 4.0, "kn": 10.0, "g": 9.81}, backend.jit_prelude())
+    assert kind == "pair"
+    for piece in ("sqrt(", "fabs(", "? (", "4.0", "9.81", "a.vel[", "a.mass[j]", "acc_force_2 = acc_force_2 +"):
+        assert piece in src, piece
+    # u * (kn * s / a): the scalar is formed first ((kn * s) / a), then multiplied into each component
+    assert src.index("10.0 *") < src.index("acc_force_0 = acc_force_0 +")
+    assert backend.jit_check(src) > 1000
+    kind, name, src = kernelgen.translate(particle, storage, {}, 1, {"damp": 0.999, "dt": 0.005}, backend.jit_prelude())
+    assert kind == "particle" and src.count("a.pos_w[i] = pi;") == 1 and "a.force[2 * (size_t) a.cap + i] =" in src
+    assert backend.jit_check(src) > 1000
+
+
+def test_unsupported_constructs_are_rejected_with_a_reason():
+    storage = {"position": "pos", "force": "force", "linear_velocity": "vel", "mass": "mass"}
+
+    def vec_times_vec(i, j):
+        apply(force, delta(i, j) * delta(i, j))
+
+    def scalar_apply(i, j):
+        apply(force, squared_distance(i, j))
+
+    def three_args(i, j, k):
+        pass
+
+    def assigns_partner(i):
+        mass[j] = 1.0
+
+    for fn, msg in ((vec_times_vec, "dot"), (scalar_apply, "vector expression"), (assigns_partner, "unsupported statement")):
+        with pytest.raises(kernelgen.KernelGenError, match=msg):
+            kernelgen.translate(fn, storage, {}, 1, {}, "")
+    with pytest.raises(kernelgen.KernelGenError, match=r"\(i\) or \(i, j\)"):
+        kernelgen.translate(three_args, storage, {}, 1, {}, "")
