@@ -164,6 +164,12 @@ typedef struct pb_md_params {
 } pb_md_params;
 int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo);
 
+/* ---- host-only self-test of the shared-memory count board that replaces communicateSizes between the ranks of a node
+ *      (runtime/domain/regular_6d_stencil.cpp:113-127): `rounds` messages per dimension on a periodic ring of `world`
+ *      processes; returns 0 on success.  Needs no GPU; pb_board_unlink removes the named segment afterwards. ---- */
+int pb_board_selftest(const char *name, int world, int rank, int rounds);
+int pb_board_unlink(const char *name);
+
 /* ---- user-defined kernels (the reference generates code for arbitrary kernel bodies: src/pairs/mapping/funcs.py:39-334,
  *      code_gen/cgen.py).  `source` is CUDA C++ printed by pairs_b200/kernelgen.py from the Python kernel; it starts with
  *      pb_jit_prelude() and defines  extern "C" __global__ void <kernel_name>(PbJitArgs).  Compiled at run time with NVRTC for

@@ -111,6 +111,8 @@ SIGNATURES = {
     "pb_nccl_init": (_I, [_P, _P]),
     "pb_md_run": (_I, [_P, ctypes.POINTER(MdParams), _I, _I, _DP, _I, _IP]),
     "pb_set_option": (_I, [_P, _S, _I]),
+    "pb_board_selftest": (_I, [_S, _I, _I, _I]),
+    "pb_board_unlink": (_I, [_S]),
     "pb_jit_prelude": (_S, []),
     "pb_jit_check": (_I, [_S, ctypes.c_char_p, _I]),
     "pb_jit_compile": (_I, [_P, _S, _S, _IP]),

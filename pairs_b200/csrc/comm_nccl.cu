@@ -85,24 +85,72 @@ struct NcclState {
     unsigned long long msg[3] = {0, 0, 0};       // messages posted so far per dimension
 };
 
-static PbShmPost *pb_post(NcclState *st, int rank, int dim, unsigned long long m) { return st->board + ((size_t) rank * 3 + dim) * 2 + (m & 1ULL); }
+static PbShmPost *pb_post(PbShmPost *board, int rank, int dim, unsigned long long m) { return board + ((size_t) rank * 3 + dim) * 2 + (m & 1ULL); }
+
+// maps (creating it if needed) the board `name` for `world` ranks; nullptr if shared memory is not available
+static PbShmPost *pb_board_map(const char *name, int world, size_t *bytes_out) {
+    static_assert(sizeof(PbShmPost) == 24, "PbShmPost layout");
+    const size_t bytes = sizeof(PbShmPost) * (size_t) world * 3 * 2;
+    const int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+    if(fd < 0) { return nullptr; }
+    if(ftruncate(fd, (off_t) bytes) != 0) { close(fd); return nullptr; }        // new segments are zero-filled: seq = 0 everywhere
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if(p == MAP_FAILED) { return nullptr; }
+    *bytes_out = bytes;
+    return (PbShmPost *) p;
+}
+
+// message m of dimension `dim`: post my two counts, wait for the same message of both neighbours, read theirs.
+// recv[0] = what `next` sends towards its prev (= me), recv[1] = what `prev` sends towards its next (= me).  false on timeout.
+static bool pb_board_exchange(PbShmPost *board, int rank, int prev, int next, int dim, unsigned long long m, const int send[2], int recv[2],
+                              int timeout_s) {
+    PbShmPost *mine = pb_post(board, rank, dim, m);
+    mine->count[0] = send[0];
+    mine->count[1] = send[1];
+    mine->seq.store(m, std::memory_order_release);
+    PbShmPost *from_next = pb_post(board, next, dim, m), *from_prev = pb_post(board, prev, dim, m);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while(from_next->seq.load(std::memory_order_acquire) != m || from_prev->seq.load(std::memory_order_acquire) != m) {
+        if((++spins & 0xfffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(timeout_s)) { return false; }
+    }
+    recv[0] = from_next->count[0];
+    recv[1] = from_prev->count[1];
+    return true;
+}
 
 static void pb_board_open(pb_ctx *ctx, NcclState *st, const void *id128) {
     if(getenv("PB_NO_SHM_BOARD") != nullptr) { return; }
-    static_assert(sizeof(PbShmPost) == 24, "PbShmPost layout");
     unsigned long long h = 1469598103934665603ULL;           // FNV-1a of the job's NCCL id: the same on every rank, unique per job
     for(int k = 0; k < 128; k++) { h = (h ^ ((const unsigned char *) id128)[k]) * 1099511628211ULL; }
     snprintf(st->board_name, sizeof(st->board_name), "/pairs_b200_%016llx", h);
-    const size_t bytes = sizeof(PbShmPost) * (size_t) ctx->world * 3 * 2;
-    const int fd = shm_open(st->board_name, O_CREAT | O_RDWR, 0600);
-    if(fd < 0) { return; }
-    if(ftruncate(fd, (off_t) bytes) != 0) { close(fd); return; }        // new segments are zero-filled: seq = 0 everywhere
-    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-    close(fd);
-    if(p == MAP_FAILED) { return; }
-    st->board = (PbShmPost *) p;
-    st->board_bytes = bytes;
+    st->board = pb_board_map(st->board_name, ctx->world, &st->board_bytes);
 }
+
+// Host-only self-test of the board protocol (no GPU, no NCCL): `rounds` messages per dimension on a periodic ring of `world`
+// processes, every count checked against what the neighbour must have posted.  Run by tests/test_cabi_and_host.py with several
+// processes.  Returns 0, or the (1-based) round in which a wrong value / a timeout was seen (negative for timeouts).
+extern "C" int pb_board_selftest(const char *name, int world, int rank, int rounds) {
+    size_t bytes = 0;
+    PbShmPost *board = pb_board_map(name, world, &bytes);
+    if(board == nullptr) { return -1000000; }
+    const int prev = (rank + world - 1) % world, next = (rank + 1) % world;
+    auto value = [](int r, int round, int dim, int side) { return ((r * 1000 + round) * 3 + dim) * 2 + side; };
+    int rc = 0;
+    for(int round = 1; round <= rounds && rc == 0; round++) {
+        for(int dim = 0; dim < 3 && rc == 0; dim++) {
+            const int send[2] = {value(rank, round, dim, 0), value(rank, round, dim, 1)};
+            int recv[2] = {-1, -1};
+            if(!pb_board_exchange(board, rank, prev, next, dim, (unsigned long long) round, send, recv, 20)) { rc = -round; break; }
+            if(recv[0] != value(next, round, dim, 0) || recv[1] != value(prev, round, dim, 1)) { rc = round; }
+        }
+    }
+    munmap(board, bytes);
+    return rc;
+}
+
+extern "C" int pb_board_unlink(const char *name) { return shm_unlink(name); }
 
 #define PB_NCCL(call)                                                                                       \
     do {                                                                                                    \
@@ -185,22 +233,14 @@ int pb_transport_sizes(pb_ctx *ctx, int dim) {
     NcclState *st;
     PB_TRY(pb_require_comm(ctx, &st));
     if(st->board != nullptr) {
-        const unsigned long long m = ++st->msg[dim];
-        PbShmPost *mine = pb_post(st, ctx->rank, dim, m);
-        mine->count[0] = ctx->nsend[dim * 2];
-        mine->count[1] = ctx->nsend[dim * 2 + 1];
-        mine->seq.store(m, std::memory_order_release);
-        PbShmPost *from_next = pb_post(st, next, dim, m), *from_prev = pb_post(st, prev, dim, m);
-        const auto t0 = std::chrono::steady_clock::now();
-        unsigned spins = 0;
-        while(from_next->seq.load(std::memory_order_acquire) != m || from_prev->seq.load(std::memory_order_acquire) != m) {
-            if((++spins & 0xfffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120)) {
-                ctx->set_error("size exchange timed out: a neighbouring rank did not reach the same communication phase");
-                return -1;
-            }
+        const int send[2] = {ctx->nsend[dim * 2], ctx->nsend[dim * 2 + 1]};
+        int recv[2] = {0, 0};
+        if(!pb_board_exchange(st->board, ctx->rank, prev, next, dim, ++st->msg[dim], send, recv, 120)) {
+            ctx->set_error("size exchange timed out: a neighbouring rank did not reach the same communication phase");
+            return -1;
         }
-        ctx->nrecv[dim * 2] = from_next->count[0];        // what next sends towards its prev (= me)
-        ctx->nrecv[dim * 2 + 1] = from_prev->count[1];    // what prev sends towards its next (= me)
+        ctx->nrecv[dim * 2] = recv[0];
+        ctx->nrecv[dim * 2 + 1] = recv[1];
         return 0;
     }
     ctx->h_scalars[4] = ctx->nsend[dim * 2];

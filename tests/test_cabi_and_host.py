@@ -72,3 +72,27 @@ def test_timestep_guards_match_reference():
     assert hits[:4] == [0, 19, 39, 59] and len(hits) == 11      # 11 rebuilds in examples/md.py
     thermo = [ts for ts in range(201) if ((ts + 1) % 100 == 0) or ts == 0]
     assert thermo == [0, 99, 199]                               # the three thermo lines of the reference's stdout
+
+
+def _board_worker(args):
+    name, world, rank, rounds = args
+    from pairs_b200 import backend
+    return backend.load().pb_board_selftest(name.encode(), world, rank, rounds)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_count_board_protocol_between_processes(world):
+    """The shared-memory board that carries message counts between the ranks of a node (csrc/comm_nccl.cu): `world` real
+    processes on a periodic ring exchange 2000 messages per dimension; every received count is checked, a lost or reordered
+    post shows up as a wrong value or a timeout."""
+    import multiprocessing as mp
+    import os
+    from pairs_b200 import backend
+    name = f"/pairs_b200_test_{os.getpid()}_{world}"
+    ctx = mp.get_context("spawn")
+    try:
+        with ctx.Pool(world) as pool:
+            res = pool.map(_board_worker, [(name, world, r, 2000) for r in range(world)])
+    finally:
+        backend.load().pb_board_unlink(name.encode())
+    assert res == [0] * world
