@@ -129,7 +129,16 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
     psim.pbc([True, True, False])
     psim.dem_sc_grid(domain[0], domain[1], domain[2], generationSpacing_SI, diameter_SI, minDiameter_SI, maxDiameter_SI,
                      initialVelocity_SI, densityParticle_SI, ntypes)
-    psim.read_particle_data(planes_file or os.path.join(os.path.dirname(os.path.abspath(__file__)), "planes.input"),
+    if planes_file is None:
+        # the two half-spaces examples/dem.py reads from data/planes.input (uid, type, mass, position, normal, flags): floor at the
+        # origin, ceiling at the corner of the stock 0.8 x 0.015 x 0.2 box; infinite | fixed | global
+        import tempfile
+        rows = [(100000, 0, 1, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 13), (100001, 0, 1, (0.8, 0.015, 0.2), (0.0, 0.0, -1.0), 13)]
+        fd, planes_file = tempfile.mkstemp(prefix="planes_", suffix=".input")
+        with os.fdopen(fd, "w") as f:
+            for uid, typ, m, x, nrm, fl in rows:
+                f.write(",".join(str(v) for v in (uid, typ, m, *x, *nrm, fl)) + "\n")
+    psim.read_particle_data(planes_file,
                             ['uid', 'type', 'mass', 'position', 'normal', 'flags'], pairs.halfspace())
     psim.setup(update_mass_and_inertia, {'densityParticle_SI': densityParticle_SI, 'pi': math.pi, 'infinity': math.inf})
     if per_cell:
