@@ -7,8 +7,9 @@ module prints CUDA for the same vocabulary directly from the Python AST, for the
 
   pair kernels     def k(i, j): locals, delta(i, j), squared_distance(i, j) (or the legacy bare names delta / rsq),
                    prop[i], prop[j], featprop[i, j], sqrt, select, min, max, abs, dot, length, squared_length, normalized,
-                   zero_vector, vector(x, y, z), + - * / unary -, comparisons, apply(prop, expr)
-  particle kernels def k(i): the same expressions, prop[i] = / += / -= expr
+                   zero_vector, vector(x, y, z), + - * / unary -, comparisons, apply(prop, expr), local op= expr,
+                   if / else (mapping/funcs.py:179-195; a local assigned inside an arm lives in that arm)
+  particle kernels def k(i): the same expressions and statements, prop[i] = / += / -= expr
 
 Like the reference's generated code the output has ONE statement per operation, in Python's evaluation order, vectors
 scalarised per component, `select` evaluating both arms, symbols substituted as literals; compiled with --fmad=false every
@@ -50,6 +51,7 @@ class _Gen:
         self.applied = {}                     # storage -> accumulator names
         self.hoisted = []                     # statements before the neighbour loop (loads of i)
         self.types_needed = False
+        self.stored = set()                   # properties written so far (particle kernels)
 
     # -- helpers --
     def tmp(self, ctype, code, hoist=False):
@@ -224,11 +226,44 @@ class _Gen:
         raise KernelGenError(f"unknown function '{f}'")
 
     # -- statements --
+    def block(self, body):
+        """Statements of an if / else arm: temporaries, loads and locals created inside stay inside (C scope = Python use)."""
+        saved_locals, saved_loaded, before = dict(self.locals), dict(self.loaded), set(self.stored)
+        self.stored = set()
+        for st in body:
+            self.stmt(st)
+        written = self.stored
+        self.locals = saved_locals
+        # a property the arm stored to has to be read again afterwards (the store may or may not have happened)
+        self.loaded = {k: v for k, v in saved_loaded.items() if k[0] not in written}
+        self.stored = before | written
+
     def stmt(self, node):
         if isinstance(node, ast.Expr) and isinstance(node.value, ast.Constant):
             return                                            # docstring
         if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
             self.locals[node.targets[0].id] = self.expr(node.value)
+            return
+        if isinstance(node, ast.AugAssign) and isinstance(node.target, ast.Name):       # local op= expr
+            if node.target.id not in self.locals:
+                raise KernelGenError(f"'{node.target.id}' is used before it is assigned")
+            ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
+            if type(node.op) not in ops:
+                raise KernelGenError(f"unsupported operator {type(node.op).__name__}")
+            self.locals[node.target.id] = self.binop(ops[type(node.op)], self.locals[node.target.id], self.expr(node.value))
+            return
+        if isinstance(node, ast.If):
+            # mapping/funcs.py:179-195: Filter (one arm) / Branch (two arms).  A local assigned inside an arm is visible in
+            # that arm only; what an arm does to the outside world are apply() and property stores.
+            cond = self.expr(node.test)
+            if self.is_vec(cond):
+                raise KernelGenError("if: the condition must be a scalar")
+            self.lines.append(f"if({cond[1]}) {{")
+            self.block(node.body)
+            if node.orelse:
+                self.lines.append("} else {")
+                self.block(node.orelse)
+            self.lines.append("}")
             return
         if isinstance(node, ast.Expr) and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", None) == "apply":
             if self.kind != "pair":
@@ -259,6 +294,7 @@ class _Gen:
         raise KernelGenError(f"unsupported statement: {ast.unparse(node)}")
 
     def store(self, store, v):
+        self.stored.add(store)
         if store == "mass":
             if self.is_vec(v):
                 raise KernelGenError("mass is a scalar")

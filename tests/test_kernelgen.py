@@ -109,3 +109,40 @@ def test_unsupported_constructs_are_rejected_with_a_reason():
             kernelgen.translate(fn, storage, {}, 1, {}, "")
     with pytest.raises(kernelgen.KernelGenError, match=r"\(i\) or \(i, j\)"):
         kernelgen.translate(three_args, storage, {}, 1, {}, "")
+
+
+def test_if_statements_and_local_updates():
+    """mapping/funcs.py:179-195 (Filter / Branch) and augmented assignment of locals."""
+    def pair(i, j):
+        r2 = squared_distance(i, j)
+        f = 1.0 / r2
+        f *= 2.0
+        if r2 < rin * rin:
+            g = f * kin
+            apply(force, delta(i, j) * g)
+        else:
+            apply(force, delta(i, j) * f)
+
+    def particle(i):
+        if mass[i] > 2.0:
+            linear_velocity[i] = linear_velocity[i] * 0.5
+        position[i] += linear_velocity[i] * dt
+
+    storage = {"position": "pos", "linear_velocity": "vel", "force": "force", "mass": "mass"}
+    _, _, src = kernelgen.translate(pair, storage, {}, 1, {"rin": 1.1, "kin": 3.0}, backend.jit_prelude())
+    body = src[src.index("if(rsq < a.cutsq)"):]
+    assert body.count("} else {") == 1 and body.count("acc_force_0 = acc_force_0 +") == 2
+    assert backend.jit_check(src) > 1000
+    _, _, src = kernelgen.translate(particle, storage, {}, 1, {"dt": 0.005}, backend.jit_prelude())
+    # the velocity is read again after the conditional store
+    after = src[src.rindex("}", 0, src.index("a.pos_w[i] = pi;")):]
+    assert "a.vel[i]" in after
+    assert backend.jit_check(src) > 1000
+
+    def leaks(i, j):
+        if squared_distance(i, j) < 1.0:
+            g = 2.0
+        apply(force, delta(i, j) * g)
+
+    with pytest.raises(kernelgen.KernelGenError, match="'g'"):
+        kernelgen.translate(leaks, storage, {}, 1, {}, "")
