@@ -146,3 +146,85 @@ def test_if_statements_and_local_updates():
 
     with pytest.raises(kernelgen.KernelGenError, match="'g'"):
         kernelgen.translate(leaks, storage, {}, 1, {}, "")
+
+
+# ---- executing generated kernels on the host: bit-for-bit against the oracle --------------------------------------------------
+def _host_kernel(tmp_path, name, src):
+    """Compiles a generated kernel for the HOST (tests/host/jit_host_emulation.h stands in for the CUDA bits) together with a
+    driver that runs it for every particle; returns the ctypes function run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags,
+    numneigh, neigh)."""
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    cpp = tmp_path / f"{name}.cpp"
+    cpp.write_text('#include "jit_host_emulation.h"\n' + src + f'''
+extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, double *vel, double *force, double *mass, int *flags,
+                    int *numneigh, int *neigh) {{
+    PbJitArgs a;
+    a.nlocal = n; a.nslots = nslots; a.cap = cap; a.pad = 0; a.cutsq = cutsq; a.pos = pos; a.pos_w = pos; a.vel = vel; a.force = force;
+    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh;
+    blockDim.x = 128;
+    for(int i = 0; i < n; i++) {{ blockIdx.x = i / 128; threadIdx.x = i % 128; {name}(a); }}
+}}
+''')
+    so = tmp_path / f"{name}.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-I" + os.path.join(here, "host"), str(cpp), "-o", str(so)],
+                   check=True)
+    lib = ctypes.CDLL(str(so))
+    P = ctypes.c_void_p
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P]
+    return lib.run
+
+
+def _ptr(a):
+    return a.ctypes.data
+
+
+def test_generated_md_kernels_equal_the_oracle_bit_for_bit_on_the_host(tmp_path):
+    """examples/md.py's three kernels through kernelgen, compiled for the host and run on the oracle's own state and lists
+    (list order = the reference's, so even the summation order is the same): forces, velocities and positions are identical bits
+    to the restatement of the reference's generated C++ -- per operation, per particle."""
+    import numpy as np
+    import lj_script
+    from oracle import port
+    nx = 6
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    r = sim.ranks[0]
+    rng = np.random.default_rng(3)
+    n = r.nlocal
+    r.real("position", n, view=True)[:] += 0.05 * (rng.random((n, 3)) - 0.5)
+    sim.step(0)                                   # exchange, borders, lists, force at ts = 0
+    tot = n + r.nghost
+    psim = lj_script.build("gpu", nx, 10, 20, 1)
+    storage = psim._device_storage()
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    src = {}
+    for fn, sym in ((lj_script.lennard_jones, {}), (lj_script.initial_integrate, {"dt": 0.005}), (lj_script.final_integrate, {"dt": 0.005})):
+        _, name, code = kernelgen.translate(fn, storage, tables, 4, sym, backend.jit_prelude())
+        src[name] = _host_kernel(tmp_path, name, code)
+    # device-layout copies of the oracle's state
+    cap = tot
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = r.real("position", tot)
+    pos4[:, 3] = r.ints("type", tot).astype(np.int64).view(np.float64)          # type bits in w
+    vel = np.ascontiguousarray(r.real("linear_velocity", tot).T)
+    mass = r.real("mass", tot).copy()
+    flags = r.ints("flags", tot).copy()
+    nn, nl = r.neighbor_sets()
+    nslots = int(nn.max())
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    for i in range(n):
+        neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
+    numneigh = np.zeros(tot, np.int32)
+    numneigh[:n] = nn
+    force = np.zeros((3, cap))
+    src["user_lennard_jones"](n, nslots, cap, 2.5 * 2.5, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
+    f_oracle = r.real("force")
+    assert np.abs(f_oracle).max() > 1.0 and np.array_equal(force[:, :n].T, f_oracle)
+    # the integrators of iteration 1 on the same state
+    sim.initial_integrate()
+    src["user_initial_integrate"](n, nslots, cap, 0.0, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
+    assert np.array_equal(pos4[:n, :3], r.real("position")) and np.array_equal(vel[:, :n].T, r.real("linear_velocity"))
+    sim.final_integrate()
+    src["user_final_integrate"](n, nslots, cap, 0.0, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
+    assert np.array_equal(vel[:, :n].T, r.real("linear_velocity"))
