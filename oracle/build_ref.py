@@ -171,7 +171,7 @@ VARIANTS = {
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
-    "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), [], False),
+    "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), ["-DREF_LJ_MODULE"], False),
     # half neighbour lists + atomic update of the partner
     "md_half_t1": ("examples/md.py", md_variant(8, 100, 1, 20, half=True), ["-DREF_IS_MD", "-DREF_HALF_LISTS"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step

@@ -132,7 +132,7 @@ class RefProgram:
         self.run(on_event)
         return snaps
 
-    # ---- direct module calls (md programs) ----
+    # ---- direct module calls (md programs; variants built with -DREF_LJ_MODULE export only lennard_jones) ----
     def lennard_jones(self, neighbor_capacity, nlocal, numneighs, neighborlists, flags, position, type_, force, sigma6, epsilon):
         self.lib.ref_md_lennard_jones(ctypes.c_int(neighbor_capacity), ctypes.c_int(nlocal), _ip(numneighs), _ip(neighborlists),
                                       _ip(flags), _dp(position), _ip(type_), _dp(force), _dp(sigma6), _dp(epsilon))

@@ -145,6 +145,14 @@ long ref_array_size(const char *name) {
     return (long) g_ps->getArrayByName(name).getSize();
 }
 
+#if defined(REF_LJ_MODULE) && !defined(REF_IS_MD)
+// variants with other kernel bodies (md_custom_t1): only the pair module keeps the argument list of examples/md.py
+void ref_md_lennard_jones(int neighbor_capacity, int nlocal, int *numneighs, int *neighborlists, int *flags,
+                          double *position, int *type, double *force, double *sigma6, double *epsilon) {
+    lennard_jones(nullptr, neighbor_capacity, nlocal, numneighs, neighborlists, flags, position, type, force, sigma6, epsilon);
+}
+#endif
+
 #ifdef REF_IS_MD
 // Direct calls into single generated modules (signatures: generated md.cpp, which the
 // reference's generator emits deterministically for examples/md.py; `pairs` is unused inside

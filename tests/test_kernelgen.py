@@ -228,3 +228,56 @@ def test_generated_md_kernels_equal_the_oracle_bit_for_bit_on_the_host(tmp_path)
     sim.final_integrate()
     src["user_final_integrate"](n, nslots, cap, 0.0, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
     assert np.array_equal(vel[:, :n].T, r.real("linear_velocity"))
+
+
+def test_generated_custom_kernel_equals_the_reference_generators_module_on_the_host(tmp_path):
+    """The pair kernel of tests/scripts/custom_script.py: kernelgen's CUDA compiled for the host against the module the
+    REFERENCE's code generator printed for the same text (oracle/_ref variant md_custom_t1, called directly on the same arrays and
+    lists): identical bits, including the summation order."""
+    import numpy as np
+    import custom_script
+    from oracle import port, ref
+    if not ref.available("md_custom_t1"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    prog = ref.RefProgram("md_custom_t1")
+    if not hasattr(prog.lib, "ref_md_lennard_jones"):
+        pytest.skip("oracle/_ref/libref_md_custom_t1.so predates the module export")
+    nx = 6
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    r = sim.ranks[0]
+    rng = np.random.default_rng(9)
+    n = r.nlocal
+    # a liquid-like configuration with some pairs inside the softened core (r < 1.05)
+    r.real("position", n, view=True)[:] += 0.25 * (rng.random((n, 3)) - 0.5)
+    sim.step(0)
+    tot = n + r.nghost
+    nn, nl = r.neighbor_sets()
+    ntypes = 4
+    eps = np.array([1.0 + 0.05 * ((i % ntypes) + (i // ntypes)) for i in range(ntypes * ntypes)])
+    sig6 = np.ones(ntypes * ntypes)
+    # the reference's generated module on AoS arrays
+    f_ref = np.zeros((n, 3))
+    prog.lennard_jones(r.neighbor_capacity, n, nn.astype(np.int32), np.ascontiguousarray(nl, np.int32), r.ints("flags", tot),
+                       r.real("position", tot), r.ints("type", tot), f_ref, sig6, eps)
+    # kernelgen's kernel on the device layout
+    psim = custom_script.build("gpu", nx, 10, 20, 1)
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    assert np.array_equal(np.array(tables["epsilon"]), eps)
+    _, name, code = kernelgen.translate(custom_script.lennard_jones, psim._device_storage(), tables, ntypes, {"kspring": 3.5, "rsoft": 1.05},
+                                        backend.jit_prelude())
+    run = _host_kernel(tmp_path, name, code)
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = r.real("position", tot)
+    pos4[:, 3] = r.ints("type", tot).astype(np.int64).view(np.float64)
+    vel, mass, flags = np.zeros((3, tot)), np.ones(tot), r.ints("flags", tot).copy()
+    nslots = int(nn.max())
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    for i in range(n):
+        neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
+    numneigh = np.zeros(tot, np.int32)
+    numneigh[:n] = nn
+    force = np.zeros((3, tot))
+    run(n, nslots, tot, 2.5 * 2.5, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
+    d = r.real("position", tot)
+    assert np.abs(f_ref).max() > 10.0                         # pairs inside the softened core exist
+    assert np.array_equal(force[:, :n].T, f_ref)
