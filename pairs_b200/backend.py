@@ -27,7 +27,7 @@ class BackendError(RuntimeError):
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(INCLUDE, "pairs_b200.h")]
+    deps = srcs + [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(INCLUDE, "pairs_b200.h")]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)

@@ -19,6 +19,7 @@
 #include <cmath>
 
 #include "ctx.cuh"
+#include "md_math.h"
 
 // ---- BuildCellListsStencil (sim/cell_lists.py:46-87): host, same fp64 expression order ---------------------
 extern "C" int pb_setup_cells(pb_ctx *ctx, double spacing) {
@@ -175,27 +176,6 @@ int pb_exclusive_scan(pb_ctx *ctx, const int *in, int *out, int n) {
 }
 
 // ---- binning ----------------------------------------------------------------------------------------------
-struct PbCellGeom {
-    double lo[3];       // subdom_min - spacing
-    double spacing;
-    int dim[3];
-    int ncells;
-};
-
-// BuildCellLists index arithmetic (sim/cell_lists.py:111-127; generated md.cpp build_cell_lists):
-//   c_d = clamp((int)((x_d - (min_d - s)) / s), 0, dim_d - 1);  flat = (c0*dim1 + c1)*dim2 + c2 + 1;  INFINITE -> 0
-__device__ __forceinline__ int pb_cell_index(const PbCellGeom &g, double x, double y, double z, int flags) {
-    if(flags & PB_FLAG_INFINITE) { return 0; }
-    const double q0 = __ddiv_rn(__dsub_rn(x, g.lo[0]), g.spacing);
-    const double q1 = __ddiv_rn(__dsub_rn(y, g.lo[1]), g.spacing);
-    const double q2 = __ddiv_rn(__dsub_rn(z, g.lo[2]), g.spacing);
-    int c0 = (int) q0, c1 = (int) q1, c2 = (int) q2;      // truncation toward zero, as the C cast
-    c0 = (c0 >= 0) ? c0 : 0; c0 = (c0 < g.dim[0]) ? c0 : g.dim[0] - 1;
-    c1 = (c1 >= 0) ? c1 : 0; c1 = (c1 < g.dim[1]) ? c1 : g.dim[1] - 1;
-    c2 = (c2 >= 0) ? c2 : 0; c2 = (c2 < g.dim[2]) ? c2 : g.dim[2] - 1;
-    return (c0 * g.dim[1] + c1) * g.dim[2] + c2 + 1;
-}
-
 // z slab of a particle inside its cell (consistent with the reference cell index c2 computed above)
 __device__ __forceinline__ int pb_zslab(const PbCellGeom &g, double z, int zsub) {
     const double q2 = (z - g.lo[2]) / g.spacing;

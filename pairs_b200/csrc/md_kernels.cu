@@ -15,6 +15,7 @@
 #include <string>
 
 #include "ctx.cuh"
+#include "md_math.h"
 
 // ---- Lennard-Jones (examples/md.py:5-8, sim/interaction.py:201-292) -------------------------------------------
 // G lanes of a warp share one local particle (A = 32/G particles per warp).  Per iteration the warp reads 32
@@ -71,16 +72,12 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones(int nlocal, int T, int
         int t = 0;
 #define PB_LJ_PAIR(PJ, VALID)                                                                                                  \
         {                                                                                                                      \
-            const double dx = __dsub_rn(pi.x, (PJ).x);                                                                         \
-            const double dy = __dsub_rn(pi.y, (PJ).y);                                                                         \
-            const double dz = __dsub_rn(pi.z, (PJ).z);                                                                         \
-            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));                  \
+            double dx, dy, dz;                                                                                                 \
+            const double rsq = pb_pair_rsq(pi.x, pi.y, pi.z, (PJ).x, (PJ).y, (PJ).z, &dx, &dy, &dz);                           \
             if((VALID) && rsq < cutsq) {                                                                                       \
                 const double sig6 = UNIFORM ? sig6_u : s_sig6[ti + pb_w_type((PJ).w)];                                         \
                 const double eps = UNIFORM ? eps_u : s_eps[ti + pb_w_type((PJ).w)];                                            \
-                const double sr2 = __ddiv_rn(1.0, rsq);                                                                        \
-                const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), sig6);                                       \
-                const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), eps);         \
+                const double f = pb_lj_fpair(rsq, sig6, eps);                                                                  \
                 fx = __dadd_rn(fx, __dmul_rn(dx, f));                                                                          \
                 fy = __dadd_rn(fy, __dmul_rn(dy, f));                                                                          \
                 fz = __dadd_rn(fz, __dmul_rn(dz, f));                                                                          \
