@@ -118,7 +118,19 @@ int pb_exchange(pb_ctx *ctx);
 int pb_borders(pb_ctx *ctx);
 int pb_synchronize(pb_ctx *ctx);
 
-/* ---- DEM path of examples/dem.py (spheres + half-spaces, contact history, cell-list traversal).  Single GPU in round 1. ----
+/* ---- user-defined particle properties: Simulation.add_property() beyond the built-in set (sim/simulation.py:166-168; one array per
+ *      property in the reference, sim/properties.py:13-36).  ncomps = 1 (real), 3 (vector), up to 9; host layout [n][ncomps].
+ *      Non-volatile properties travel with their particle through the cell-order sort, migration (Comm.exchange carries every
+ *      non-volatile property, sim/comm.py:100-103) and ghost creation; volatile ones are zeroed by pb_reset_volatile
+ *      (sim/properties.py:61-70).  New particles start from `defaults` (NULL = zeros).  Generated kernels (pb_jit_*) address
+ *      component d as PbJitArgs.xdata[(row0 + d) * cap + i]; pb_property_info returns row0.  md.py path only (not with pb_dem_enable). ---- */
+int pb_add_property(pb_ctx *ctx, const char *name, int ncomps, int is_volatile, const double *defaults, int *prop_id);
+int pb_property_count(const pb_ctx *ctx);
+int pb_property_info(const pb_ctx *ctx, int prop_id, int *ncomps, int *row0, int *is_volatile);
+int pb_upload_property(pb_ctx *ctx, int prop_id, int n, const double *values);        /* the first n locals */
+int pb_download_property(pb_ctx *ctx, int prop_id, double *out, int with_ghosts);     /* device order, like pb_download_real */
+
+/* ---- DEM path of examples/dem.py (spheres + half-spaces, contact history, cell-list traversal), one or several GPUs. ----
  * pb_dem_enable            use_contact_history=True + the DEM property set (contact_capacity = neighbor_capacity of pairs.simulation())
  * pb_dem_set_params        symbols of the kernels (examples/dem.py:189-201) + feature properties friction_static/dynamic
  * pb_dem_sc_grid           pairs::dem_sc_grid (runtime/dem_sc_grid.hpp:62-172), host arrays out (NULL pointers: count only)

@@ -20,6 +20,8 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_custom_t1  md_t1 with other kernel bodies (softened LJ using sqrt / select / symbols, integrators with drag) -> generic kernels
+  md_props_t1   md_t1 with user-defined properties (a real entering the pair force, written by a setup() function; a second volatile
+              vector; reals and a vector integrated per particle) -> generic kernels on the user-property rows (csrc/props.cu)
   md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
@@ -103,6 +105,47 @@ def md_custom_variant(nx, steps):
     return patch
 
 
+PROPS_KERNELS = '''def init_scale(i):
+    scale[i] = 1.0 + 0.25 * (position[i][0] + 0.3719 * position[i][1] + 0.1137 * position[i][2]) / xlen
+
+
+def lennard_jones(i, j):
+    sr2 = 1.0 / squared_distance(i, j)
+    sr6 = sr2 * sr2 * sr2 * sigma6[i, j]
+    f = 48.0 * sr6 * (sr6 - 0.5) * sr2 * epsilon[i, j] * scale[i]
+    apply(force, delta(i, j) * f)
+    apply(pull, delta(i, j) * (sr6 * scale[i]))
+
+
+def initial_integrate(i):
+    linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
+    position[i] += dt * linear_velocity[i]
+    path[i] += dt * linear_velocity[i]
+    heat[i] += dt * dot(force[i], linear_velocity[i])
+
+
+def final_integrate(i):
+    linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
+    work[i] = work[i] + dot(pull[i], linear_velocity[i])
+'''
+
+
+def md_props_variant(nx, steps):
+    """examples/md.py with user-defined properties and kernels that use them: same text as tests/scripts/props_script.py."""
+    base = md_variant(nx, steps, 1, 20)
+
+    def patch(text):
+        text = base(text)
+        text = re.sub(r"def lennard_jones\(i, j\):.*?(?=\n\ncmd = )", PROPS_KERNELS.rstrip("\n") + "\n", text, count=1, flags=re.S)
+        text = _sub(text, r"^psim\.add_feature\('type', ntypes\)",
+                    "psim.add_property('scale', pairs.real(), 1.0)\npsim.add_property('heat', pairs.real(), 0.0)\n"
+                    "psim.add_property('work', pairs.real(), 0.0)\npsim.add_property('path', pairs.vector())\n"
+                    "psim.add_property('pull', pairs.vector(), volatile=True)\npsim.add_feature('type', ntypes)")
+        text = _sub(text, r"^psim\.reneighbor_every", "psim.setup(init_scale, symbols={'xlen': 13.0})\npsim.reneighbor_every")
+        return text
+    return patch
+
+
 def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None, verlet=False):
     def patch(text):
         if verlet:      # Verlet lists + BuildContactHistory instead of the cell-list traversal (sim/simulation.py:255-261, 402-406)
@@ -146,15 +189,16 @@ def build_cuda_variant(name):
     src_script = os.path.join(REF, script)
     gen_cu = os.path.join(gdir, "md.cu")
     exe = os.path.join(OUT, f"{name}_cuda")
-    if newer(exe, [src_script, os.path.join(HERE, "mpi_stub", "mpi.h"), __file__]):
-        return "up to date"
     text = open(src_script).read()
     if patch is not None:
         text = patch(text)
+    stamp, stamp_file = recipe_stamp(text, "cuda", nvcc), os.path.join(gdir, "recipe.stamp")
+    if stamp_matches(stamp_file, stamp) and os.path.exists(exe):
+        return "up to date"
     scratch_script = os.path.join(gdir, f"md_{name}_input.py")
     with open(scratch_script, "w") as f:
         f.write(text)
-    run([sys.executable, scratch_script, "gpu"], cwd=gdir, env=dict(os.environ, PYTHONPATH=os.path.join(REF, "src")))
+    run([sys.executable, scratch_script, "gpu"], cwd=gdir, env=dict(os.environ, PYTHONPATH=os.path.join(REF, "src"), PYTHONHASHSEED="0"))
     if not os.path.exists(gen_cu):
         raise RuntimeError(f"generator did not write {gen_cu}")
     inc = ["-I" + os.path.join(HERE, "mpi_stub"), "-I" + REF, "-I" + os.path.join(REF, "runtime")]
@@ -162,6 +206,8 @@ def build_cuda_variant(name):
     # -DENABLE_CUDA_AWARE_MPI is the reference Makefile's own setting (Makefile:21); with one rank every transfer is then a
     # device-to-device copy inside the process (the host-staged alternative overruns its size arrays, runtime/pairs.cpp:426)
     run([nvcc, "-O3", "-w", "-DENABLE_CUDA_AWARE_MPI", "-gencode", "arch=compute_100a,code=sm_100a", *inc, *srcs, "-o", exe])
+    with open(stamp_file, "w") as f:
+        f.write(stamp + "\n")
     return "built"
 
 
@@ -172,6 +218,7 @@ VARIANTS = {
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
     "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), ["-DREF_LJ_MODULE"], False),
+    "md_props_t1": ("examples/md.py", md_props_variant(8, 100), ["modules:init_scale,lennard_jones,initial_integrate,final_integrate"], False),
     # half neighbour lists + atomic update of the partner
     "md_half_t1": ("examples/md.py", md_variant(8, 100, 1, 20, half=True), ["-DREF_IS_MD", "-DREF_HALF_LISTS"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step
@@ -190,11 +237,46 @@ def run(cmd, **kw):
     return r.stdout
 
 
-def newer(target, deps):
-    if not os.path.exists(target):
-        return False
-    t = os.path.getmtime(target)
-    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+def recipe_stamp(*parts):
+    """What a built artefact depends on, as one hash: the (patched) input script, the flags, the harness and the MPI stand-in --
+    not this file's mtime, so that adding a variant does not rebuild the others."""
+    import hashlib
+    h = hashlib.sha1()
+    for p in parts:
+        h.update(repr(p).encode())
+    for f in (os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "mpi_stub", "mpi.h")):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def stamp_matches(path, stamp):
+    return os.path.exists(path) and open(path).read().strip() == stamp
+
+
+def write_module_wrappers(variant, gen_cpp, modules, gdir):
+    """The generator orders a module's arguments differently from script to script: read the printed signatures, write
+    `void ref_mod_<module>(void **args)` wrappers that forward args in that order, and record the order for oracle/ref.py."""
+    import json
+    text = open(gen_cpp).read()
+    sigs, lines = {}, []
+    for m in modules:
+        mt = re.search(rf"^void {m}\(PairsSimulation \*pairs(.*?)\) \{{$", text, flags=re.M)
+        if mt is None:
+            raise RuntimeError(f"module {m} not found in {gen_cpp}")
+        args = []
+        for a in [x.strip() for x in mt.group(1).split(",") if x.strip()]:
+            ctype, aname = a.rsplit(" ", 1)
+            ptr = aname.startswith("*")
+            args.append([ctype + (" *" if ptr else ""), aname.lstrip("*")])
+        sigs[m] = args
+        call = ", ".join(f"({t}) args[{k}]" if t.endswith("*") else f"*({t} *) args[{k}]" for k, (t, _) in enumerate(args))
+        lines.append(f"void ref_mod_{m}(void **args) {{ {m}(nullptr, {call}); }}")
+    inc_file = os.path.join(gdir, "module_wrappers.inc")
+    with open(inc_file, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    with open(os.path.join(OUT, f"modules_{variant}.json"), "w") as f:
+        json.dump(sigs, f, indent=1)
+    return inc_file
 
 
 def build_variant(name):
@@ -206,30 +288,37 @@ def build_variant(name):
     gen_cpp = os.path.join(gdir, f"{base}.cpp")
     lib = os.path.join(OUT, f"libref_{name}.so")
     exe = os.path.join(OUT, f"{name}_cpu")
-    deps = [src_script, os.path.join(HERE, "ref_harness.cpp"), os.path.join(HERE, "mpi_stub", "mpi.h"), __file__]
-    if newer(lib, deps) and (not want_exe or newer(exe, deps)):
-        return "up to date"
-
-    # 1. run the reference generator on (a scratch copy of) the reference's example script
     text = open(src_script).read()
     if patch is not None:
         text = patch(text)
+    stamp, stamp_file = recipe_stamp(text, defines, CXXFLAGS, want_exe), os.path.join(gdir, "recipe.stamp")
+    if stamp_matches(stamp_file, stamp) and os.path.exists(lib) and (not want_exe or os.path.exists(exe)):
+        return "up to date"
+
+    # 1. run the reference generator on (a scratch copy of) the reference's example script
     scratch_script = os.path.join(gdir, f"{base}_{name}_input.py")
     with open(scratch_script, "w") as f:
         f.write(text)
-    env = dict(os.environ, PYTHONPATH=os.path.join(REF, "src"))
+    env = dict(os.environ, PYTHONPATH=os.path.join(REF, "src"), PYTHONHASHSEED="0")
     run([sys.executable, scratch_script, "cpu"], cwd=gdir, env=env)
     if not os.path.exists(gen_cpp):
         raise RuntimeError(f"generator did not write {gen_cpp}")
 
     inc = ["-I" + os.path.join(HERE, "mpi_stub"), "-I" + REF, "-I" + os.path.join(REF, "runtime")]
     rt = [os.path.join(REF, s) for s in RUNTIME_SRCS]
+    mods = [d for d in defines if d.startswith("modules:")]
+    defines = [d for d in defines if not d.startswith("modules:")]
+    if mods:
+        inc_file = write_module_wrappers(name, gen_cpp, mods[0][len("modules:"):].split(","), gdir)
+        defines.append(f'-DREF_MODULES_INC="{inc_file}"')
     # 2. shared library with hooks + per-module wrappers
     run(["g++", *CXXFLAGS, "-shared", "-fPIC", *defines, f'-DREF_GENERATED="{gen_cpp}"', *inc,
          os.path.join(HERE, "ref_harness.cpp"), *rt, "-o", lib])
     # 3. stock executable (for wall-clock baselines; prints the reference's own timers)
     if want_exe:
         run(["g++", *CXXFLAGS, *inc, gen_cpp, *rt, "-o", exe])
+    with open(stamp_file, "w") as f:
+        f.write(stamp + "\n")
     return "built"
 
 

@@ -143,6 +143,33 @@ class RefProgram:
     def final_integrate(self, nlocal, flags, force, mass, vel):
         self.lib.ref_md_final_integrate(ctypes.c_int(nlocal), _ip(flags), _dp(force), _dp(mass), _dp(vel))
 
+    # ---- generic module access (variants built with "modules:..." in oracle/build_ref.py) ----
+    def call_module(self, module, **kw):
+        """Calls a generated module with arguments given BY NAME (numpy arrays for pointers, numbers for scalars); the order the
+        generator printed them in is read from oracle/_ref/modules_<variant>.json."""
+        import json
+        if not hasattr(self, "_modules"):
+            with open(os.path.join(REF_DIR, f"modules_{self.variant}.json")) as f:
+                self._modules = json.load(f)
+        sig = self._modules[module]
+        missing = [n for _, n in sig if n not in kw]
+        assert not missing and len(kw) == len(sig), f"{module}: arguments are {[n for _, n in sig]}"
+        keep, ptrs = [], (ctypes.c_void_p * len(sig))()
+        for k, (ctype, name) in enumerate(sig):
+            v = kw[name]
+            if ctype.endswith("*"):
+                want = np.int32 if ctype.startswith("int") else np.float64
+                assert isinstance(v, np.ndarray) and v.dtype == want and v.flags.c_contiguous, f"{module}: {name} must be a contiguous {want.__name__} array"
+                ptrs[k] = v.ctypes.data
+            else:
+                c = ctypes.c_int(int(v)) if ctype == "int" else ctypes.c_double(float(v))
+                keep.append(c)
+                ptrs[k] = ctypes.addressof(c)
+        fn = getattr(self.lib, f"ref_mod_{module}")
+        fn.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        fn.restype = None
+        fn(ptrs)
+
     def cell_stencil(self, subdom, ncells_capacity=1 << 30):
         ncells = ctypes.c_int(0)
         nstencil = ctypes.c_int(0)

@@ -153,6 +153,13 @@ void ref_md_lennard_jones(int neighbor_capacity, int nlocal, int *numneighs, int
 }
 #endif
 
+#ifdef REF_MODULES_INC
+// Generic module access: oracle/build_ref.py parses the argument lists the generator printed (their order is not the same for
+// every script) and writes one wrapper per requested module, `void ref_mod_<name>(void **args)`, args in the generated order
+// (scalars by address); the order is recorded next to the library (modules_<variant>.json) and oracle/ref.py passes by NAME.
+#include REF_MODULES_INC
+#endif
+
 #ifdef REF_IS_MD
 // Direct calls into single generated modules (signatures: generated md.cpp, which the
 // reference's generator emits deterministically for examples/md.py; `pairs` is unused inside

@@ -5,7 +5,8 @@ ghost part (runtime/allocate.hpp:14-45; ghost `flags` are read but never transmi
 its results depend on the heap being zero pages -- true for its own executable, not inside a long-lived pytest
 process.  MALLOC_MMAP_THRESHOLD_ forces those allocations to come from fresh zero-filled mmaps.
 
-  python -m oracle.ref_worker dump  <variant> <out.npz> [nsteps]   per-thermo-step snapshots (locals only)
+  python -m oracle.ref_worker dump  <variant> <out.npz> [nsteps] [name:width,...]   per-thermo-step snapshots (locals only;
+                                                                    the list names further real properties to record)
   python -m oracle.ref_worker bench <variant> <warmup> <steps>     prints JSON {"n": atoms, "seconds": t, "steps": k}
 """
 import ctypes
@@ -27,16 +28,20 @@ def spawn(args, **kw):
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, **kw)
 
 
-def dump(variant, out_path, nsteps=None):
-    """Snapshots of every thermo step of `variant`, produced in a fresh process; returns list of dicts."""
-    p = spawn(["dump", variant, out_path] + ([nsteps] if nsteps is not None else []))
+BASE_PROPS = (("position", 3), ("linear_velocity", 3), ("force", 3), ("mass", 1))
+
+
+def dump(variant, out_path, nsteps=None, extra=()):
+    """Snapshots of every thermo step of `variant`, produced in a fresh process; returns list of dicts.  `extra` = further
+    (property name, width) pairs to record (user-defined properties of the variant)."""
+    p = spawn(["dump", variant, out_path, nsteps if nsteps is not None else -1] + ([",".join(f"{n}:{w}" for n, w in extra)] if extra else []))
     out, err = p.communicate()
     if p.returncode != 0:
         raise RuntimeError(f"ref_worker dump failed:\n{out}\n{err}")
     z = np.load(out_path)
     n = int(z["count"])
-    snaps = [{k: z[f"{k}_{i}"] for k in ("position", "linear_velocity", "force", "mass", "type")} | {"nlocal": int(z["nlocal"][i]), "nghost": int(z["nghost"][i])}
-             for i in range(n)]
+    names = [k for k, _ in BASE_PROPS] + ["type"] + [k for k, _ in extra]
+    snaps = [{k: z[f"{k}_{i}"] for k in names} | {"nlocal": int(z["nlocal"][i]), "nghost": int(z["nghost"][i])} for i in range(n)]
     for k in ("numneighs", "neighborlists"):
         if k in z.files:
             snaps[0][k] = z[k]
@@ -70,11 +75,12 @@ def _main(argv):
     prog = RefProgram(variant)
     if mode == "dump":
         out_path = argv[2]
-        nsteps = int(argv[3]) if len(argv) > 3 else None
-        snaps = prog.run_collect_thermo(steps=nsteps)
+        nsteps = int(argv[3]) if len(argv) > 3 and int(argv[3]) >= 0 else None
+        extra = tuple((x.split(":")[0], int(x.split(":")[1])) for x in argv[4].split(",")) if len(argv) > 4 and argv[4] else ()
+        snaps = prog.run_collect_thermo(props=BASE_PROPS + extra, steps=nsteps)
         d = {"count": len(snaps), "nlocal": np.array([s["nlocal"] for s in snaps]), "nghost": np.array([s["nghost"] for s in snaps])}
         for i, s in enumerate(snaps):
-            for k in ("position", "linear_velocity", "force", "mass", "type"):
+            for k in [x for x, _ in BASE_PROPS + extra] + ["type"]:
                 d[f"{k}_{i}"] = s[k]
         for k in ("numneighs", "neighborlists"):
             if snaps and k in snaps[0]:
@@ -136,7 +142,7 @@ def _main(argv):
         t = list(buf)[:n]
         assert n >= warmup + steps + 1, (n, warmup, steps)
         seconds = t[warmup + steps] - t[warmup]
-        atoms = {"md_bench": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3, "dem_t1": 422, "dem_vtk_t1": 422, "dem_cn_t1": 422, "dem_nl_t1": 422, "md_half_t1": 4 * 8 ** 3, "md_custom_t1": 4 * 8 ** 3,
+        atoms = {"md_bench": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3, "dem_t1": 422, "dem_vtk_t1": 422, "dem_cn_t1": 422, "dem_nl_t1": 422, "md_half_t1": 4 * 8 ** 3, "md_custom_t1": 4 * 8 ** 3, "md_props_t1": 4 * 8 ** 3,
                  "dem_bench": 160 * 160 * 39 + 2}[variant]
         print(json.dumps({"n": atoms, "seconds": seconds, "steps": steps, "warmup": warmup}))
         return 0

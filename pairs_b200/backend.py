@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libpairs_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu"]
+SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu", "props.cu"]
 
 # --fmad=false: fp64 multiplies and adds are never contracted, so per-operation results equal the reference CPU
 # build compiled with -ffp-contract=off (the parity contract).
@@ -91,6 +91,11 @@ SIGNATURES = {
     "pb_exchange": (_I, [_P]),
     "pb_borders": (_I, [_P]),
     "pb_synchronize": (_I, [_P]),
+    "pb_add_property": (_I, [_P, _S, _I, _I, _DP, _IP]),
+    "pb_property_count": (_I, [_P]),
+    "pb_property_info": (_I, [_P, _I, _IP, _IP, _IP]),
+    "pb_upload_property": (_I, [_P, _I, _I, _DP]),
+    "pb_download_property": (_I, [_P, _I, _DP, _I]),
     "pb_dem_enable": (_I, [_P, _I]),
     "pb_dem_set_params": (_I, [_P, _D, _D, _D, _D, _D, _D, _D, _D, _I, _DP, _DP]),
     "pb_dem_sc_grid": (_I, [_P, _D, _D, _D, _D, _D, _D, _D, _D, _D, _I, _I, _IP, _IP, _DP, _DP, _DP, _DP, _IP]),
@@ -412,6 +417,32 @@ class Context:
         n = _I(0)
         self._ck(self.lib.pb_md_run(self.h, ctypes.byref(p), ts_begin, ts_end, _dp(out), cap, ctypes.byref(n)))
         return out[: min(n.value, cap) * 3].reshape(-1, 3)
+
+    # ---- user-defined properties (csrc/props.cu) ----
+    def add_property(self, name, ncomps, volatile=False, defaults=None):
+        """-> (property id, first row of the property in PbJitArgs.xdata)"""
+        d = np.zeros(ncomps) if defaults is None else np.ascontiguousarray(np.broadcast_to(np.asarray(defaults, np.float64), (ncomps,)))
+        pid, row0 = _I(0), _I(0)
+        self._ck(self.lib.pb_add_property(self.h, name.encode(), ncomps, 1 if volatile else 0, _dp(d), ctypes.byref(pid)))
+        self._ck(self.lib.pb_property_info(self.h, pid.value, None, ctypes.byref(row0), None))
+        self._xprops = getattr(self, "_xprops", {})
+        self._xprops[name] = (pid.value, ncomps)
+        return pid.value, row0.value
+
+    def upload_property(self, name, values):
+        pid, ncomps = self._xprops[name]
+        v = np.ascontiguousarray(values, np.float64)
+        n = v.shape[0]
+        assert v.size == n * ncomps, f"{name}: expected [n][{ncomps}] values"
+        self._ck(self.lib.pb_upload_property(self.h, pid, n, _dp(v)))
+
+    def download_property(self, name, with_ghosts=False):
+        pid, ncomps = self._xprops[name]
+        nl, ng = self.counts()
+        n = nl + (ng if with_ghosts else 0)
+        out = np.zeros((n, ncomps) if ncomps > 1 else n, np.float64)
+        self._ck(self.lib.pb_download_property(self.h, pid, _dp(out), 1 if with_ghosts else 0))
+        return out
 
     def jit_compile(self, source, kernel_name):
         h = _I(0)

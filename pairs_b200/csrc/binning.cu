@@ -339,5 +339,6 @@ int pb_sort_locals(pb_ctx *ctx) {
     std::swap(ctx->uid, ctx->uid_alt);
     std::swap(ctx->shape, ctx->shape_alt);
     std::swap(ctx->tag, ctx->tag_alt);
+    PB_TRY(pb_xprops_permute(ctx, ctx->cell_list, n));     // user-defined properties follow their particle
     return 0;
 }

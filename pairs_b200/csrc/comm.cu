@@ -188,7 +188,7 @@ static void pb_set_offsets(pb_ctx *ctx, int step) {
 
 // ---- borders -----------------------------------------------------------------------------------------------
 template<bool DEM>
-__global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, int cap, PbBox box, const int *__restrict__ send_map,
+__global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, int cap, int stride, PbBox box, const int *__restrict__ send_map,
                                                         const int *__restrict__ send_mult, const double4 *__restrict__ pos,
                                                         const double *__restrict__ vel, const double *__restrict__ mass,
                                                         const int *__restrict__ uid, const int *__restrict__ shape,
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, in
     const int e = first + k;
     const int p = send_map[e];
     const double4 x = pos[p];
-    double *b = buf + (size_t) e * (DEM ? BORDER_ELEMS_DEM : BORDER_ELEMS);
+    double *b = buf + (size_t) e * stride;
     if(DEM) {
         b[11] = radius[p];
         b[12] = angvel[p];
@@ -220,14 +220,14 @@ __global__ void __launch_bounds__(256) pb_k_pack_border(int first, int count, in
 }
 
 template<bool DEM>
-__global__ void __launch_bounds__(256) pb_k_unpack_border(int first_rec, int count, int dst0, int cap, const double *__restrict__ buf,
+__global__ void __launch_bounds__(256) pb_k_unpack_border(int first_rec, int count, int dst0, int cap, int stride, const double *__restrict__ buf,
                                                           double4 *__restrict__ pos, double *__restrict__ vel, double *__restrict__ mass,
                                                           int *__restrict__ type, int *__restrict__ flags, int *__restrict__ uid,
                                                           int *__restrict__ shape, int *__restrict__ tag, double *__restrict__ radius,
                                                           double *__restrict__ angvel) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= count) { return; }
-    const double *b = buf + (size_t) (first_rec + k) * (DEM ? BORDER_ELEMS_DEM : BORDER_ELEMS);
+    const double *b = buf + (size_t) (first_rec + k) * stride;
     const int p = dst0 + k;
     if(DEM) {
         radius[p] = b[11];
@@ -264,6 +264,9 @@ extern "C" int pb_borders(pb_ctx *ctx) {
     ctx->nghost = 0;
     ctx->cells_n = 0;
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
+    // record length: the built-in elements, then the non-volatile rows of the user-defined properties (props.cu)
+    const int base_elems = ctx->dem ? BORDER_ELEMS_DEM : BORDER_ELEMS;
+    const int stride = base_elems + (ctx->dem ? 0 : ctx->xrows_nv);
     for(int step = 0; step < 3; step++) {
         const int n = ctx->nlocal + ctx->nghost;     // locals AND ghosts received so far: edges/corners are forwarded
         int c_lo = 0, c_hi = 0;
@@ -278,26 +281,28 @@ extern "C" int pb_borders(pb_ctx *ctx) {
         PB_TRY(pb_ensure_particle_capacity(ctx, ctx->nlocal + ctx->nghost + nr));
         if(ns > 0) {
             if(ctx->dem) {
-                PB_LAUNCH(pb_k_pack_border<true>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, pb_box(ctx),
+                PB_LAUNCH(pb_k_pack_border<true>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
                           ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
                           ctx->radius, ctx->angvel);
             } else {
-                PB_LAUNCH(pb_k_pack_border<false>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, pb_box(ctx),
+                PB_LAUNCH(pb_k_pack_border<false>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
                           ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
                           nullptr, nullptr);
+                PB_TRY(pb_xprops_pack(ctx, ctx->send_offsets[step * 2], ns, stride, base_elems, ctx->send_map, ctx->send_buf));
             }
         }
         const double *src = nullptr;
-        PB_TRY(pb_transport_data(ctx, step, step + 1, ctx->dem ? BORDER_ELEMS_DEM : BORDER_ELEMS, &src));
+        PB_TRY(pb_transport_data(ctx, step, step + 1, stride, &src));
         if(nr > 0) {
             if(ctx->dem) {
                 PB_LAUNCH(pb_k_unpack_border<true>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
-                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
                           ctx->uid, ctx->shape, ctx->tag, ctx->radius, ctx->angvel);
             } else {
                 PB_LAUNCH(pb_k_unpack_border<false>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
-                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
                           ctx->uid, ctx->shape, ctx->tag, nullptr, nullptr);
+                PB_TRY(pb_xprops_unpack(ctx, ctx->recv_offsets[step * 2], nr, ctx->nlocal + ctx->recv_offsets[step * 2], stride, base_elems, src));
             }
         }
         ctx->nghost += nr;

@@ -68,7 +68,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
                     ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
                     ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->d_fric_static,
-                    ctx->d_fric_dynamic, ctx->d_dem_flag};
+                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
@@ -147,6 +147,7 @@ int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
     PB_TRY(pb_regrow(ctx, &ctx->sel_scan, 0, newcap + 1, false));
     PB_TRY(pb_regrow(ctx, &ctx->numneigh, 0, newcap, false));
     if(ctx->dem) { PB_TRY(pb_dem_grow(ctx, oldcap, newcap, used)); }
+    PB_TRY(pb_xprops_grow(ctx, oldcap, newcap, used));
     ctx->pcap = (int) newcap;
     return 0;
 }
@@ -341,6 +342,7 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
         PB_CHECK(cudaMemsetAsync(ctx->normal, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
         PB_CHECK(cudaMemsetAsync(ctx->num_contacts, 0, sizeof(int) * (size_t) ctx->pcap, ctx->stream));
     }
+    PB_TRY(pb_xprops_defaults(ctx));     // user-defined properties of the new particles: their declared defaults
     ctx->force_is_zero = false;
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -37,6 +37,9 @@
         if(rc_ < 0) { return rc_; }    \
     } while(0)
 
+static const int PB_XPROP_MAX_COMPS = 9;   // a matrix property
+static const int PB_XPROP_MAX_ROWS = 48;   // rows of user-defined properties per context (row lists are kernel arguments)
+
 struct PbTimer {
     double ms = 0.0;
     long calls = 0;
@@ -127,6 +130,19 @@ struct pb_ctx {
     double dem_params[16];        // PbDemParams, see dem_math.h
     int *d_dem_flag = nullptr;    // [0]: contact capacity overflow
 
+    // ---- user-defined properties (props.cu): what add_property() declares beyond the built-in set, as SoA rows
+    //      xdata[xrows][pcap] (a real = 1 row, a vector = 3 rows).  Non-volatile rows travel with their particle (cell-order
+    //      sort, migration, ghost creation); volatile rows are zeroed by reset_volatile. ----
+    struct XProp {
+        std::string name;
+        int comps = 1, row0 = 0;
+        bool is_volatile = false;
+        double dflt[PB_XPROP_MAX_COMPS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    };
+    std::vector<XProp> xprops;
+    int xrows = 0, xrows_nv = 0;  // all rows / rows of non-volatile properties
+    double *xdata = nullptr, *xdata_alt = nullptr;
+
     // ---- LJ feature properties ----
     int ntypes = 0;
     bool lj_uniform = false;
@@ -169,8 +185,27 @@ struct pb_ctx {
 
 static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record in MD (exchange: 12, borders: 11/15, sync: 6)
 // DEM exchange record: 12 base + radius 1 + angvel 3 + normal 3 + inv_inertia 9 + rotmat 9 + quat 4 + num_contacts 1 + 6 per slot
-static inline int pb_record_elems(const pb_ctx *ctx) { return ctx->dem ? std::max(PB_MAX_ELEMS, 42 + 6 * ctx->ccontacts) : PB_MAX_ELEMS; }
+// MD with user-defined properties: their non-volatile rows follow the 12 (exchange) / 11 (borders) built-in elements
+static inline int pb_record_elems(const pb_ctx *ctx) {
+    return ctx->dem ? std::max(PB_MAX_ELEMS, 42 + 6 * ctx->ccontacts) : std::max(PB_MAX_ELEMS, 12 + ctx->xrows_nv);
+}
 static const int PB_NSCALARS = 16;
+
+// ---- user-defined properties (props.cu) ----
+struct PbXRows {                   // the rows of the non-volatile user properties, in declaration order
+    int n;
+    int row[PB_XPROP_MAX_ROWS];
+};
+PbXRows pb_xprops_nv_rows(const pb_ctx *ctx);
+int pb_xprops_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used);
+int pb_xprops_defaults(pb_ctx *ctx);                                   // every slot back to the declared default
+int pb_xprops_permute(pb_ctx *ctx, const int *perm, int n);            // new index k <- old index perm[k], locals [0, n)
+int pb_xprops_reset_volatile(pb_ctx *ctx);
+// wire records: the non-volatile rows follow the `offset` built-in elements of a record of `stride` doubles
+int pb_xprops_pack(pb_ctx *ctx, int first, int count, int stride, int offset, const int *send_map, double *buf);
+int pb_xprops_pack_leavers(pb_ctx *ctx, int n, int stride, int offset, const int *rec, double *buf);
+int pb_xprops_unpack(pb_ctx *ctx, int first_rec, int count, int dst0, int stride, int offset, const double *buf);
+int pb_xprops_move(pb_ctx *ctx, int max_count, const int *count, const int *src_idx, const int *dst_idx);
 
 // ---- helpers shared by the .cu files ----
 int pb_ensure_particle_capacity(pb_ctx *ctx, int needed);

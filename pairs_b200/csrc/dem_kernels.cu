@@ -72,6 +72,7 @@ extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(ctx->dem) { return 0; }
     if(contact_capacity < 1 || contact_capacity > 64) { ctx->set_error("pb_dem_enable: 1 <= contact_capacity <= 64"); return -1; }
+    if(ctx->xrows > 0) { ctx->set_error("pb_dem_enable: user-defined properties (pb_add_property) are available on the md.py path only"); return -1; }
     ctx->ccontacts = contact_capacity;
     ctx->dem = true;
     if(ctx->send_cap > 0) {        // wire records grow (contact history travels with migrating particles): re-size the buffers

@@ -27,6 +27,7 @@ struct PbJitArgs {
     const int *flags;       // [cap]
     const int *numneigh;    // [cap]
     const int *neigh;       // sliced ELLPACK: ((i / 32) * nslots + k) * 32 + i % 32
+    double *xdata;          // user-defined properties, rows of [cap]: component d of a property at (row0 + d) * cap + i
 };
 
 static const char *PB_JIT_PRELUDE = R"PRELUDE(
@@ -41,6 +42,7 @@ struct PbJitArgs {
     const int *flags;
     const int *numneigh;
     const int *neigh;
+    double *xdata;
 };
 #define PB_FLAG_FIXED 4
 __device__ __forceinline__ int pb_w_type(double w) { return (int) (__double_as_longlong(w) & 0xffffffffLL); }
@@ -194,7 +196,7 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     a.nlocal = ctx->nlocal; a.nslots = ctx->nslots; a.cap = ctx->pcap; a.pad = 0;
     a.cutsq = cutoff * cutoff;
     a.pos = ctx->pos; a.pos_w = ctx->pos; a.vel = ctx->vel; a.force = ctx->force; a.mass = ctx->mass; a.flags = ctx->flags;
-    a.numneigh = ctx->numneigh; a.neigh = ctx->neigh;
+    a.numneigh = ctx->numneigh; a.neigh = ctx->neigh; a.xdata = ctx->xdata;
     void *params[] = {&a};
     PB_CHECK(cudaLaunchKernel((const void *) k.kernel, dim3(pb_blocks(ctx->nlocal, 128)), dim3(128), params, 0, ctx->stream));
     ctx->launches++;

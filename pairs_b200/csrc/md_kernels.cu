@@ -268,6 +268,10 @@ extern "C" int pb_set_lj_params(pb_ctx *ctx, int ntypes, const double *epsilon, 
 // ResetVolatileProperties (sim/properties.py:61-70) is deferred and fused into the next force kernel.
 extern "C" int pb_reset_volatile(pb_ctx *ctx) {
     ctx->force_is_zero = true;
+    if(ctx->xrows > ctx->xrows_nv) {      // volatile user-defined properties are cleared right away (no kernel to fold them into)
+        PB_CHECK(cudaSetDevice(ctx->device));
+        PB_TRY(pb_xprops_reset_volatile(ctx));
+    }
     return 0;
 }
 

@@ -389,10 +389,17 @@ class Simulation:
                                             particle_density, ntypes)))
 
     def setup(self, func, symbols={}):
-        family, roles = recognise(func)
-        if family != "update_mass_and_inertia":
-            raise DslError(f"setup(): '{func.__name__}' is not a set-up function this backend implements")
-        self.setup_functions.append({"name": func.__name__, "family": family, "roles": roles, "symbols": dict(symbols)})
+        """sim/simulation.py:266-267: a per-particle function run once over the locals after the set-up statements."""
+        try:
+            family, roles = recognise(func)
+            if family != "update_mass_and_inertia":
+                raise DslError("not a set-up family")
+        except DslError:
+            if len(inspect.signature(func).parameters) != 1:
+                raise DslError(f"setup(): '{func.__name__}' must take one particle argument") from None
+            family, roles = "generic_setup", {}       # generic path: kernelgen -> NVRTC, no FIXED filter
+        self.setup_functions.append({"name": func.__name__, "family": family, "roles": roles, "symbols": dict(symbols),
+                                     "globals": func.__globals__, "func": func})
 
     def build_cell_lists(self, spacing, store_neighbors_per_cell=False):
         # store_neighbors_per_cell (sim/cell_lists.py:174-206): the reference then walks one pre-concatenated list per cell
@@ -471,6 +478,9 @@ class Simulation:
                 raise DslError("compute_half() is not available for the legacy lj kernel")
             ctx.set_option("compute_half", 1)
         ctx.reserve(0, self.neighbor_capacity)
+        for k, (name, comps, volatile, dflt) in enumerate(self._user_props()):
+            _, row0 = ctx.add_property(name, comps, volatile, dflt)
+            assert row0 == self._device_storage()[name][1]
 
         # ---- set-up ----
         nlocal = 0
@@ -482,6 +492,10 @@ class Simulation:
             elif kind == "read_particle_data":
                 nlocal = self._read_particle_data(ctx, *args)
         ctx.setup_cells(self.cell_spacing)
+        for e in self.setup_functions:          # setup() functions: once over the locals, right after the set-up statements
+            if e["family"] != "generic_setup":
+                raise DslError(f"setup(): '{e['name']}' belongs to the DEM path")
+            self._bind_generic(ctx, e, skip_fixed=False)["call"]()
 
         # ---- bind kernels ----
         plan_pre, plan_fn = [self._bind(ctx, e) for e in self.pre_step], [self._bind(ctx, e) for e in self.functions]
@@ -562,6 +576,8 @@ class Simulation:
         ctx.dem_upload("radius", cat("radius", 1, np.float64))
         ctx.dem_upload("normal", cat("normal", 3, np.float64))
         for f in self.setup_functions:
+            if f["family"] != "update_mass_and_inertia":
+                raise DslError(f"DEM: setup() function '{f['name']}' is not the one of examples/dem.py (update_mass_and_inertia)")
             ctx.dem_stage("update_mass_and_inertia")
         ctx.timers_enable(True)
         ctx.sync()
@@ -665,24 +681,39 @@ class Simulation:
         raise DslError(f"unbound kernel family {fam}")
 
     def _device_storage(self):
-        """User property names -> the device arrays of the MD path (csrc/ctx.cuh): the position, ONE non-volatile vector
-        (velocity), ONE volatile vector (force), ONE non-volatile real (mass)."""
-        m = {}
+        """Property names -> device storage.  The MD path keeps dedicated arrays (csrc/ctx.cuh) for the position, ONE
+        non-volatile vector (the velocity: 'linear_velocity' if declared, else the first one), ONE volatile vector (the force:
+        'force' if declared, else the first one) and ONE non-volatile real ('mass', else the first one).  Every further real /
+        vector property is user-defined storage: ('x', first row, components) in the row block of csrc/props.cu, rows numbered in
+        declaration order."""
+        def pick(preferred, ptype, volatile):
+            names = [n for n, p in self.props.items() if p.type == ptype and p.volatile == volatile and n != self.position_name
+                     and n not in self.feature_props]
+            return preferred if preferred in names else (names[0] if names else None)
+        builtin = {self.position_name: "pos", pick("linear_velocity", Types.Vector, False): "vel",
+                   pick("force", Types.Vector, True): "force", pick("mass", Types.Real, False): "mass"}
+        m, row = {}, 0
         for name, p in self.props.items():
-            if name == self.position_name:
-                m[name] = "pos"
-            elif p.type == Types.Vector:
-                slot = "force" if p.volatile else "vel"
-                if slot in m.values():
-                    raise DslError(f"property '{name}': this backend stores one velocity-like and one force-like vector property")
-                m[name] = slot
-            elif p.type == Types.Real and name not in self.feature_props:
-                if "mass" in m.values():
-                    raise DslError(f"property '{name}': this backend stores one real property (mass)")
-                m[name] = "mass"
+            if name in builtin:
+                m[name] = builtin[name]
+            elif p.type in (Types.Real, Types.Vector) and name not in self.feature_props:
+                comps = 3 if p.type == Types.Vector else 1
+                m[name] = ("x", row, comps)
+                row += comps
         return m
 
-    def _bind_generic(self, ctx, e):
+    def _user_props(self):
+        """[(name, components, volatile, defaults)] of the user-defined properties, in row order."""
+        out = []
+        for name, st in self._device_storage().items():
+            if isinstance(st, tuple):
+                p = self.props[name]
+                v = p.value if isinstance(p.value, (list, tuple)) else [p.value] * st[2]     # add_property's default is the scalar 0.0
+                d = [_builtin_float(x) for x in v]
+                out.append((name, st[2], p.volatile, d))
+        return out
+
+    def _bind_generic(self, ctx, e, skip_fixed=True):
         from . import backend, kernelgen
         if self._compute_half:
             raise DslError("compute_half() is available for the built-in lennard_jones kernel only")
@@ -692,14 +723,15 @@ class Simulation:
             tables[name] = data
             nk = self.features[feat]
         try:
-            kind, kname, src = kernelgen.translate(e["func"], self._device_storage(), tables, nk, e["symbols"], backend.jit_prelude())
+            kind, kname, src = kernelgen.translate(e["func"], self._device_storage(), tables, nk, e["symbols"], backend.jit_prelude(),
+                                                   skip_fixed=skip_fixed)
         except kernelgen.KernelGenError as err:
             raise DslError(f"kernel '{e['name']}': {err}") from None
         handle = ctx.jit_compile(src, kname)
         if kind == "pair":
             if self.neighbor_cutoff is None:
                 raise DslError(f"kernel '{e['name']}': pair kernels run over neighbour lists (build_neighbor_lists)")
-            if e["cutoff"] is None:
+            if e.get("cutoff") is None:
                 raise DslError(f"kernel '{e['name']}': pair kernels need a cutoff_radius")
             cutoff = _builtin_float(e["cutoff"])
             return dict(e, call=lambda: ctx.jit_launch(handle, 0, cutoff), source=src)
@@ -778,9 +810,14 @@ class Simulation:
             arrays[n] = data[:, k:k + w] if w > 1 else data[:, k]
             k += w
         pos = arrays[self.position_name]
-        vel_name = next((n for n in arrays if "velocity" in n and self.props[n].type == Types.Vector), None)
-        ctx.upload(pos, arrays.get(vel_name), arrays.get("mass"), arrays.get("type"), arrays.get("flags"), arrays.get("uid"),
+        storage = self._device_storage()
+        vel_name = next((n for n in arrays if storage.get(n) == "vel"), None)
+        mass_name = next((n for n in arrays if storage.get(n) == "mass"), None)
+        ctx.upload(pos, arrays.get(vel_name), arrays.get(mass_name), arrays.get("type"), arrays.get("flags"), arrays.get("uid"),
                    np.full(len(pos), shape_id, np.int32))
+        for name, st in storage.items():          # columns of user-defined properties
+            if isinstance(st, tuple) and name in arrays:
+                ctx.upload_property(name, arrays[name])
         return len(pos)
 
 

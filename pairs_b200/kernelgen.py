@@ -3,12 +3,14 @@
 The reference traces a kernel function into IR and prints code for it (src/pairs/mapping/funcs.py:39-334 BuildParticleIR,
 keywords in src/pairs/mapping/keywords.py, Apply in src/pairs/ir/apply.py, the pair loop of sim/interaction.py:168-295).  This
 module prints CUDA for the same vocabulary directly from the Python AST, for the properties the MD path stores on the device
-(position, one velocity-like vector, one volatile force-like vector, mass, the `type` feature and its feature properties):
+(position, one velocity-like vector, one volatile force-like vector, mass, the `type` feature and its feature properties) and
+for every further real / vector property the script declares (rows of the user-property block, csrc/props.cu):
 
   pair kernels     def k(i, j): locals, delta(i, j), squared_distance(i, j) (or the legacy bare names delta / rsq),
                    prop[i], prop[j], featprop[i, j], sqrt, select, min, max, abs, dot, length, squared_length, normalized,
                    zero_vector, vector(x, y, z), + - * / unary -, comparisons, apply(prop, expr), local op= expr,
-                   if / else (mapping/funcs.py:179-195; a local assigned inside an arm lives in that arm)
+                   if / else (mapping/funcs.py:179-195; a local assigned inside an arm lives in that arm), v[0] / prop[i][2]
+                   (one component of a vector)
   particle kernels def k(i): the same expressions and statements, prop[i] = / += / -= expr
 
 Like the reference's generated code the output has ONE statement per operation, in Python's evaluation order, vectors
@@ -37,12 +39,21 @@ def _lit(x):
     return r if ("." in r or "e" in r or "E" in r) else r + ".0"
 
 
+def _xref(store, d, idx):
+    """Component d of a user-defined property (csrc/props.cu: SoA rows of [cap])."""
+    return f"a.xdata[{store[1] + d} * (size_t) a.cap + {idx}]"
+
+
+def _store_tag(store):
+    return store if isinstance(store, str) else f"x{store[1]}"
+
+
 class _Gen:
     """Expression / statement printer.  Values are (type, code) with type in {'f', 'i', 'b'} or ('v', [c0, c1, c2])."""
 
     def __init__(self, name, kind, storage, feature_tables, ntypes, symbols, glob):
         self.name, self.kind = name, kind
-        self.storage = storage                # user property name -> 'pos' | 'vel' | 'force' | 'mass'
+        self.storage = storage                # property name -> 'pos' | 'vel' | 'force' | 'mass' | ('x', first row, components)
         self.tables = feature_tables          # feature property name -> list of nk*nk floats
         self.ntypes = ntypes
         self.symbols, self.glob = symbols, glob
@@ -80,6 +91,9 @@ class _Gen:
             val = self.vec([self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(3)])
         elif store == "mass":
             val = ("f", self.tmp("double", f"a.mass[{idx}]", hoist))
+        elif isinstance(store, tuple):                        # user-defined property: rows of a.xdata
+            comps = [self.tmp("double", _xref(store, d, idx), hoist) for d in range(store[2])]
+            val = ("f", comps[0]) if store[2] == 1 else self.vec(comps)
         else:
             raise KernelGenError(f"no device storage for '{store}'")
         self.loaded[key] = val
@@ -161,10 +175,15 @@ class _Gen:
         return ("i" if isinstance(v, int) else "f", _lit(v))
 
     def subscript(self, node):
+        idx = node.slice
+        if isinstance(idx, ast.Constant) and isinstance(idx.value, int) and not isinstance(idx.value, bool):
+            base = self.expr(node.value)                      # v[0], position[i][2]: one component (ir/vectors.py VectorAccess)
+            if not self.is_vec(base) or not 0 <= idx.value < len(base[1]):
+                raise KernelGenError("component access needs a vector and an index 0..2")
+            return ("f", base[1][idx.value])
         if not isinstance(node.value, ast.Name):
             raise KernelGenError("unsupported subscript")
         prop = node.value.id
-        idx = node.slice
         if isinstance(idx, ast.Tuple):                        # feature property: fp[i, j]
             names = [e.id for e in idx.elts if isinstance(e, ast.Name)]
             if prop not in self.tables or names != ["i", "j"] or self.kind != "pair":
@@ -174,8 +193,7 @@ class _Gen:
         if not isinstance(idx, ast.Name) or idx.id not in ("i", "j") or (idx.id == "j" and self.kind != "pair"):
             raise KernelGenError(f"'{prop}[...]': index must be the particle argument")
         if prop not in self.storage:
-            raise KernelGenError(f"property '{prop}' is not stored on the device by this backend (position, one velocity, one "
-                                 "volatile force, mass)")
+            raise KernelGenError(f"'{prop}' is not a declared real / vector property")
         return self.load(self.storage[prop], idx.id)
 
     def call(self, node):
@@ -270,13 +288,21 @@ class _Gen:
                 raise KernelGenError("apply() needs a pair kernel")
             tgt, val = node.value.args
             store = self.storage.get(getattr(tgt, "id", None))
-            if store not in ("force", "vel"):
-                raise KernelGenError("apply(): the target must be a vector property stored on the device")
+            if store not in ("force", "vel") and not isinstance(store, tuple):
+                raise KernelGenError("apply(): the target must be a declared vector property")
             v = self.expr(val)
-            if not self.is_vec(v):
-                raise KernelGenError("apply(): vector property needs a vector expression")
-            acc = self.applied.setdefault(store, [f"acc_{store}_{d}" for d in range(3)])
-            for a, c in zip(acc, v[1]):
+            if isinstance(store, tuple) and store[2] == 1:
+                # a scalar target: the reference accepts it but prints code that does not compile (its reduction variable is
+                # always a 3-vector, ir/apply.py:41-42); here it accumulates the scalar, the evident meaning
+                if self.is_vec(v):
+                    raise KernelGenError("apply(): scalar property needs a scalar expression")
+                comps = [v[1]]
+            else:
+                if not self.is_vec(v):
+                    raise KernelGenError("apply(): vector property needs a vector expression")
+                comps = v[1]
+            acc = self.applied.setdefault(store, [f"acc_{_store_tag(store)}_{d}" for d in range(len(comps))])
+            for a, c in zip(acc, comps):
                 self.lines.append(f"{a} = {a} + {c};")
             return
         if self.kind == "particle" and isinstance(node, (ast.Assign, ast.AugAssign)):
@@ -284,7 +310,7 @@ class _Gen:
             if isinstance(tgt, ast.Subscript) and isinstance(tgt.value, ast.Name) and getattr(tgt.slice, "id", None) == "i":
                 store = self.storage.get(tgt.value.id)
                 if store is None:
-                    raise KernelGenError(f"property '{tgt.value.id}' is not stored on the device by this backend")
+                    raise KernelGenError(f"'{tgt.value.id}' is not a declared real / vector property")
                 v = self.expr(node.value)
                 if isinstance(node, ast.AugAssign):
                     ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
@@ -301,6 +327,14 @@ class _Gen:
             self.lines.append(f"a_mass_w[i] = {v[1]};")
             self.loaded[(store, "i")] = v
             return
+        if isinstance(store, tuple):
+            comps = [v[1]] if not self.is_vec(v) else v[1]
+            if len(comps) != store[2]:
+                raise KernelGenError("assignment: a real property takes a scalar, a vector property a vector")
+            for d, c in enumerate(comps):
+                self.lines.append(f"{_xref(store, d, 'i')} = {c};")
+            self.loaded[(store, "i")] = v
+            return
         if not self.is_vec(v):
             raise KernelGenError(f"'{store}' is a vector property")
         if store == "pos":
@@ -312,8 +346,10 @@ class _Gen:
             self.loaded[(store, "i")] = v
 
 
-def translate(func, storage, feature_tables, ntypes, symbols, prelude):
-    """-> (kind, kernel name, CUDA source).  `storage` maps the user's property names to device arrays."""
+def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixed=True):
+    """-> (kind, kernel name, CUDA source).  `storage` maps the user's property names to device arrays.  skip_fixed=False is
+    for setup() functions: the reference runs those over every local particle (no FIXED filter, mapping/funcs.py:305-310 applies
+    to compute() only)."""
     src = textwrap.dedent(inspect.getsource(func))
     tree = ast.parse(src).body[0]
     if not isinstance(tree, ast.FunctionDef):
@@ -334,7 +370,7 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude):
         out.append(f"__device__ const double fp_{fp}[{len(table)}] = {{{', '.join(_lit(float(x)) for x in table)}}};")
     out.append(f'extern "C" __global__ void __launch_bounds__(128) {name}(PbJitArgs a) {{')
     out.append("    const int i = blockIdx.x * blockDim.x + threadIdx.x;")
-    out.append("    if(i >= a.nlocal || (a.flags[i] & PB_FLAG_FIXED) != 0) { return; }")
+    out.append("    if(i >= a.nlocal || (a.flags[i] & PB_FLAG_FIXED) != 0) { return; }" if skip_fixed else "    if(i >= a.nlocal) { return; }")
     if kind == "pair":
         out.append("    const double4 pi = pb_ld_pos(a.pos + i);")
         if g.types_needed:
@@ -363,7 +399,10 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude):
         out.append("    }")
         for store, acc in g.applied.items():                          # prop[i] = prop[i] + acc (sim/interaction.py:280-292)
             for d, x in enumerate(acc):
-                ref = f"a.{store}[{d} * (size_t) a.cap + i]" if d else f"a.{store}[i]"
+                if isinstance(store, tuple):
+                    ref = _xref(store, d, "i")
+                else:
+                    ref = f"a.{store}[{d} * (size_t) a.cap + i]" if d else f"a.{store}[i]"
                 out.append(f"    {ref} = {ref} + {x};")
     else:
         out.append("    double4 pi = a.pos_w[i];")

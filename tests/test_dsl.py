@@ -178,13 +178,42 @@ def test_multi_rank_read_particle_data_keeps_own_rows_and_global_bodies():
     assert dsl.Simulation._keep_own(OneRank(), part) is part
 
 
-def test_generic_kernels_need_the_md_path_properties():
+def test_further_properties_become_user_defined_storage():
+    """Properties beyond the MD set get rows in the user-property block (csrc/props.cu), numbered in declaration order; the MD
+    slots go to the canonical names when they are declared, else to the first property of the matching type / volatility."""
     import lj_script
+    from pairs_b200 import backend, kernelgen
 
     def charged(i, j):
         apply(force, delta(i, j) * charge[i] * charge[j])
+        apply(field, delta(i, j) * charge[j])
 
     psim = lj_script.build("gpu", 8, 10, 20, 1)
-    psim.add_property("charge", pairs.real(), 0.0)
-    with pytest.raises(dsl.DslError, match="one real property"):
-        psim._device_storage()
+    psim.add_property("charge", pairs.real(), 0.5)
+    psim.add_property("field", pairs.vector(), volatile=True)
+    psim.add_property("dipole", pairs.vector(), (0.0, 0.0, 1.0))
+    st = psim._device_storage()
+    assert st == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force", "charge": ("x", 0, 1),
+                  "field": ("x", 1, 3), "dipole": ("x", 4, 3)}
+    assert psim._user_props() == [("charge", 1, False, [0.5]), ("field", 3, True, [0.0, 0.0, 0.0]), ("dipole", 3, False, [0.0, 0.0, 1.0])]
+    _, _, src = kernelgen.translate(charged, st, {}, 1, {}, backend.jit_prelude())
+    assert "a.xdata[0 * (size_t) a.cap + j]" in src and "acc_x1_2 = acc_x1_2 +" in src and "a.xdata[3 * (size_t) a.cap + i] =" in src
+    assert backend.jit_check(src) > 1000
+    # other names: the first non-volatile vector is the velocity, the first volatile one the force, the first real the mass
+    q = pairs.simulation("x", [pairs.point_mass()], timesteps=1, double_prec=True)
+    q.add_position("r")
+    q.add_property("m", pairs.real(), 1.0)
+    q.add_property("m2", pairs.real(), 2.0)
+    q.add_property("v", pairs.vector())
+    q.add_property("f", pairs.vector(), volatile=True)
+    q.add_property("g", pairs.vector(), volatile=True)
+    assert q._device_storage() == {"r": "pos", "m": "mass", "m2": ("x", 0, 1), "v": "vel", "f": "force", "g": ("x", 1, 3)}
+    # setup(): any per-particle function (generic path, no FIXED filter); pair functions are rejected
+    def init(i):
+        m2[i] = 2.0 * m[i]
+    q.setup(init)
+    assert q.setup_functions[0]["family"] == "generic_setup"
+    with pytest.raises(dsl.DslError, match="one particle argument"):
+        q.setup(charged)
+    _, _, src = kernelgen.translate(init, q._device_storage(), {}, 1, {}, backend.jit_prelude(), skip_fixed=False)
+    assert "PB_FLAG_FIXED) != 0" not in src.split('extern "C"')[1]

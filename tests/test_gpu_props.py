@@ -1,0 +1,120 @@
+"""User-defined particle properties (csrc/props.cu, kernelgen.py) on the GPU: tests/scripts/props_script.py -- examples/md.py plus
+five properties beyond the MD set, used by a setup() function, the pair kernel and both integrators -- against the run of the
+REFERENCE's code generator on the same text (oracle/build_ref.py variant md_props_t1 -> tests/golden/md_props_t1.npz), and the
+structural operations (sort, wrap, growth, ghosts, upload / download) through the C-ABI."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import props_common as pc
+from tests.util import by_id, rel_err_force
+
+# First GPU run pending: this file was written after the round's GPU budget was spent.  What runs on the CPU is pinned (the four
+# generated kernels equal the reference generator's modules bit for bit, tests/test_kernelgen.py); the device-side plumbing has
+# compiled for sm_100a but not executed yet, hence non-strict xfail: a pass is reported as XPASS, a failure does not hide the
+# verified suite.  Remove the marker after the first green run.
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="user-defined properties: first GPU run pending")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "scripts"))
+
+
+def _golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "md_props_t1.npz"))
+
+
+def test_user_property_script_matches_the_reference_generator_golden(capsys):
+    import props_script
+    z = _golden()
+    # the first two iterations: the reference has not permuted anything yet, lattice order of the golden = upload order = tag
+    psim1 = props_script.build("gpu", 8, 1, 20, 1)
+    ctx1 = psim1.generate()
+    capsys.readouterr()
+    tag = ctx1.ints("tag")
+    assert np.array_equal(by_id(tag, ctx1.download_property("scale")), z["scale_1"])          # the setup() function, bit for bit
+    assert np.array_equal(by_id(tag, ctx1.download_property("path")), z["path_1"])            # dt * v of one step, bit for bit
+    for name, arr in (("force", ctx1.real("force")), ("pull", ctx1.download_property("pull")), ("work", ctx1.download_property("work"))):
+        assert rel_err_force(by_id(tag, arr), z[f"{name}_1"]) <= 1e-12, name
+    assert np.abs(by_id(tag, ctx1.download_property("heat")) - z["heat_1"]).max() <= 1e-24     # dt * f.v with f = lattice round-off
+    # the whole run: 100 steps, 6 reneighbourings (sort + wrap each time)
+    psim = props_script.build("gpu", 8, 100, 20, 1)
+    ctx = psim.generate()
+    capsys.readouterr()
+    assert len(psim.thermo_log) == 101
+    for (ts, t, p), t_ref in zip(psim.thermo_log, z["temperature"]):
+        assert abs(t - t_ref) <= 1e-9 * t_ref, ts
+    assert ctx.counts() == (int(z["nlocal"][100]), int(z["nghost"][100]))
+    # scale is different for every lattice site and never changes: it is the identity both runs are ordered by
+    scale = ctx.download_property("scale")
+    og, orf = np.argsort(scale), np.argsort(z["scale_100"])
+    assert len(np.unique(scale)) == len(scale) and np.array_equal(scale[og], z["scale_100"][orf])
+    for name, arr in (("position", ctx.real("position")), ("linear_velocity", ctx.real("linear_velocity")),
+                      ("heat", ctx.download_property("heat")), ("work", ctx.download_property("work")),
+                      ("path", ctx.download_property("path")), ("pull", ctx.download_property("pull"))):
+        ref = z[f"{name}_100"][orf]
+        assert np.abs(ref).max() > 0.0 and np.abs(arr[og] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), name
+    box = 8 * pow(4.0 / 0.8442, 1.0 / 3.0)
+    pc.check_identity(ctx.real("position"), ctx.download_property("path"), scale, box, props_script.XLEN)
+
+
+def test_property_store_through_the_c_abi(capsys):
+    """add / upload / download, defaults, capacity growth, ghosts carrying their source's values, volatile reset, the cell-order
+    sort -- without any generated kernel."""
+    from pairs_b200 import backend
+    rng = np.random.default_rng(5)
+    L = 12.0
+    ctx = backend.Context(0)
+    ctx.init_domain([0.0, L, 0.0, L, 0.0, L])
+    ctx.add_property("q", 1, False, [1.5])
+    n = 3000
+    pos = rng.random((n, 3)) * L
+    ctx.upload(pos, None, None, None, None, None, None)
+    ctx.add_property("w", 3, False, [0.25, 0.5, 0.75])          # declared after the particles exist: rows are re-allocated
+    ctx.add_property("acc", 3, True, None)
+    assert np.all(ctx.download_property("q") == 1.5) and np.all(ctx.download_property("w") == [0.25, 0.5, 0.75])
+    q = rng.random(n)
+    w = rng.random((n, 3))
+    ctx.upload_property("q", q)
+    ctx.upload_property("w", w)
+    ctx.upload_property("acc", np.ones((n, 3)))
+    assert np.array_equal(ctx.download_property("q"), q) and np.array_equal(ctx.download_property("w"), w)
+    ctx.setup_cells(2.8)
+    ctx.exchange()                                   # wrap + cell-order sort
+    ctx.borders()                                    # ghosts; grows the particle capacity (n + n/4 + 1024 slots reserved at upload)
+    tag = ctx.ints("tag")
+    assert not np.array_equal(tag, np.arange(n)) and np.array_equal(by_id(tag, ctx.download_property("q")), q)
+    assert np.array_equal(by_id(tag, ctx.download_property("w")), w)
+    nl, ng = ctx.counts()
+    assert nl == n and ng > n // 2
+    # every ghost carries the non-volatile values of the particle it is an image of
+    tags_all = ctx.ints("tag", with_ghosts=True)
+    assert np.array_equal(ctx.download_property("q", with_ghosts=True), q[tags_all])
+    assert np.array_equal(ctx.download_property("w", with_ghosts=True), w[tags_all])
+    ctx.reset_volatile()
+    assert not ctx.download_property("acc").any() and np.array_equal(by_id(tag, ctx.download_property("w")), w)
+    # a second, larger upload: capacity growth re-strides the rows, new particles start from the declared defaults
+    n2 = 9000
+    ctx.upload(rng.random((n2, 3)) * L, None, None, None, None, None, None)
+    assert np.all(ctx.download_property("q") == 1.5) and np.all(ctx.download_property("w") == [0.25, 0.5, 0.75])
+    with pytest.raises(backend.BackendError, match="already defined"):
+        ctx.add_property("q", 1)
+
+
+def _ngpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], stdout=subprocess.PIPE, text=True, timeout=30).stdout
+        return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_user_properties_follow_their_particle_between_ranks(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29800 + world), os.path.join(ROOT, "tests", "scripts", "mgpu_props_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "mgpu_props_check ok" in r.stdout, r.stdout[-4000:]

@@ -151,18 +151,18 @@ def test_if_statements_and_local_updates():
 # ---- executing generated kernels on the host: bit-for-bit against the oracle --------------------------------------------------
 def _host_kernel(tmp_path, name, src):
     """Compiles a generated kernel for the HOST (tests/host/jit_host_emulation.h stands in for the CUDA bits) together with a
-    driver that runs it for every particle; returns the ctypes function run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags,
-    numneigh, neigh)."""
+    driver that runs it for every particle; returns run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags, numneigh, neigh,
+    xdata=None) taking array addresses."""
     import ctypes
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     cpp = tmp_path / f"{name}.cpp"
     cpp.write_text('#include "jit_host_emulation.h"\n' + src + f'''
 extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, double *vel, double *force, double *mass, int *flags,
-                    int *numneigh, int *neigh) {{
+                    int *numneigh, int *neigh, double *xdata) {{
     PbJitArgs a;
     a.nlocal = n; a.nslots = nslots; a.cap = cap; a.pad = 0; a.cutsq = cutsq; a.pos = pos; a.pos_w = pos; a.vel = vel; a.force = force;
-    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh;
+    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata;
     blockDim.x = 128;
     for(int i = 0; i < n; i++) {{ blockIdx.x = i / 128; threadIdx.x = i % 128; {name}(a); }}
 }}
@@ -172,8 +172,11 @@ extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, doub
                    check=True)
     lib = ctypes.CDLL(str(so))
     P = ctypes.c_void_p
-    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P]
-    return lib.run
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P, P]
+
+    def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None):
+        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata)
+    return run
 
 
 def _ptr(a):
@@ -281,3 +284,97 @@ def test_generated_custom_kernel_equals_the_reference_generators_module_on_the_h
     d = r.real("position", tot)
     assert np.abs(f_ref).max() > 10.0                         # pairs inside the softened core exist
     assert np.array_equal(force[:, :n].T, f_ref)
+
+
+def test_kernels_on_user_defined_properties_equal_the_reference_generators_modules_on_the_host(tmp_path):
+    """tests/scripts/props_script.py declares five properties beyond the MD set (reals, vectors, one volatile) and uses them in a
+    setup() function, the pair kernel and both integrators.  kernelgen's CUDA for the four kernels, compiled for the host and run
+    on the row layout of csrc/props.cu, against the modules the REFERENCE's generator printed for the same text (oracle/_ref
+    variant md_props_t1) on its own AoS arrays: every property is identical bit for bit after set-up, force evaluation and the
+    two integrator halves."""
+    import numpy as np
+    import props_script
+    from oracle import port, ref
+    if not ref.available("md_props_t1"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    prog = ref.RefProgram("md_props_t1")
+    nx = 6
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    r = sim.ranks[0]
+    rng = np.random.default_rng(21)
+    n = r.nlocal
+    r.real("position", n, view=True)[:] += 0.05 * (rng.random((n, 3)) - 0.5)
+    sim.step(0)                                   # lists and ghosts of the oracle at ts = 0
+    tot = n + r.nghost
+    nn, nl = r.neighbor_sets()
+    ntypes = 4
+    psim = props_script.build("gpu", nx, 10, 20, 1)
+    storage = psim._device_storage()
+    assert storage == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force", "scale": ("x", 0, 1),
+                       "heat": ("x", 1, 1), "work": ("x", 2, 1), "path": ("x", 3, 3), "pull": ("x", 6, 3)}
+    assert [e["family"] for e in psim.setup_functions] == ["generic_setup"]
+    assert psim._user_props() == [("scale", 1, False, [1.0]), ("heat", 1, False, [0.0]), ("work", 1, False, [0.0]),
+                                  ("path", 3, False, [0.0, 0.0, 0.0]), ("pull", 3, True, [0.0, 0.0, 0.0])]
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    kern = {}
+    for fn, sym, skip_fixed in ((props_script.init_scale, {"xlen": props_script.XLEN}, False), (props_script.lennard_jones, {}, True),
+                                (props_script.initial_integrate, {"dt": 0.005}, True), (props_script.final_integrate, {"dt": 0.005}, True)):
+        _, name, code = kernelgen.translate(fn, storage, tables, ntypes, sym, backend.jit_prelude(), skip_fixed=skip_fixed)
+        assert backend.jit_check(code) > 1000
+        kern[name] = _host_kernel(tmp_path, name, code)
+
+    # ---- the reference's arrays (AoS) and ours (device layout), same initial state; some FIXED particles ----
+    pos_r = r.real("position", tot).copy()
+    typ = r.ints("type", tot).copy()
+    flags = r.ints("flags", tot).copy()
+    flags[:n:17] |= 4
+    vel_r = r.real("linear_velocity", tot).copy()
+    mass = r.real("mass", tot).copy()
+    scale_r, heat_r, work_r = np.full(tot, 1.0), np.zeros(tot), np.zeros(tot)
+    path_r, pull_r, force_r = np.zeros((tot, 3)), np.zeros((tot, 3)), np.zeros((tot, 3))
+    cap = tot
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = pos_r
+    pos4[:, 3] = typ.astype(np.int64).view(np.float64)
+    vel = np.ascontiguousarray(vel_r.T)
+    force = np.zeros((3, cap))
+    xdata = np.zeros((9, cap))
+    xdata[0] = 1.0
+    nslots = int(nn.max())
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    for i in range(n):
+        neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
+    numneigh = np.zeros(tot, np.int32)
+    numneigh[:n] = nn
+    args = (_ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh), _ptr(xdata))
+
+    def same():
+        return (np.array_equal(pos4[:n, :3], pos_r[:n]) and np.array_equal(vel[:, :n].T, vel_r[:n]) and np.array_equal(force[:, :n].T, force_r[:n])
+                and np.array_equal(xdata[0, :n], scale_r[:n]) and np.array_equal(xdata[1, :n], heat_r[:n]) and np.array_equal(xdata[2, :n], work_r[:n])
+                and np.array_equal(xdata[3:6, :n].T, path_r[:n]) and np.array_equal(xdata[6:9, :n].T, pull_r[:n]))
+
+    # set-up function: every local, FIXED ones included
+    prog.call_module("init_scale", nlocal=n, position=pos_r, scale=scale_r)
+    kern["user_init_scale"](n, nslots, cap, 0.0, *args)
+    assert same() and scale_r[:n].min() < 1.05 and scale_r[:n].max() > 1.15 and scale_r[0] != 1.0
+    # ghosts carry the value of their source in this backend (the reference leaves them undefined; the kernels read scale[i] only)
+    sigma6, epsilon = np.ones(ntypes * ntypes), np.ones(ntypes * ntypes)
+    for it in range(2):
+        prog.call_module("lennard_jones", neighbor_capacity=r.neighbor_capacity, nlocal=n, numneighs=nn.astype(np.int32),
+                         neighborlists=np.ascontiguousarray(nl, np.int32), flags=flags, position=pos_r, type=typ, scale=scale_r, pull=pull_r,
+                         force=force_r, sigma6=sigma6, epsilon=epsilon)
+        kern["user_lennard_jones"](n, nslots, cap, 2.5 * 2.5, *args)
+        assert same() and np.abs(force_r).max() > 1.0 and np.abs(pull_r).max() > 0.1
+        assert not force_r[:n:17].any()               # FIXED particles are skipped by compute() kernels
+        prog.call_module("final_integrate", nlocal=n, flags=flags, force=force_r, mass=mass, linear_velocity=vel_r, work=work_r, pull=pull_r)
+        kern["user_final_integrate"](n, nslots, cap, 0.0, *args)
+        assert same() and np.abs(work_r).max() > 0.0
+        prog.call_module("initial_integrate", nlocal=n, flags=flags, force=force_r, mass=mass, linear_velocity=vel_r, position=pos_r,
+                         path=path_r, heat=heat_r)
+        kern["user_initial_integrate"](n, nslots, cap, 0.0, *args)
+        assert same() and np.abs(path_r).max() > 0.0 and np.abs(heat_r).max() > 0.0
+        # reset_volatile_properties: force and the volatile user property
+        force_r[:] = 0.0
+        pull_r[:] = 0.0
+        force[:] = 0.0
+        xdata[6:9] = 0.0
