@@ -270,7 +270,7 @@ class Simulation:
         self.grid = None
         self.reneighbor_frequency = 1            # sim/simulation.py:89
         self._compute_thermo = 0
-        self.cell_spacing = None
+        self._cell_spacing = None
         self.neighbor_cutoff = None
         self.setups = []
         self.setup_functions = []
@@ -297,6 +297,42 @@ class Simulation:
     def pbc(self, cfg):
         assert len(cfg) == 3, "PBC must be specified for each dimension."
         self._pbc = list(cfg)
+
+    # -- queries of the reference's Simulation object (sim/simulation.py:116-128, 159-201, 373-377) --
+    def enable_profiler(self):
+        """sim/simulation.py:116-117 switches on LIKWID marker regions around compute() kernels; here every stage is always
+        bracketed by CUDA-event timers (ctx.timer(name)), so the call only records the request."""
+        self._enable_profiler = True
+
+    def use_double_precision(self):
+        return self.double_prec
+
+    def get_shape_id(self, shape):
+        return self.shapes[shape]
+
+    def max_shapes(self):
+        return len(self.shapes)
+
+    def ndims(self):
+        return 3
+
+    def property(self, name):
+        return self.props.get(name)
+
+    def position(self):
+        return self.props.get(self.position_name)
+
+    def feature(self, name):
+        return self.features.get(name)
+
+    def feature_property(self, name):
+        return self.feature_props.get(name)
+
+    def contact_property(self, name):
+        return self.contact_props.get(name)
+
+    def cell_spacing(self):
+        return self._cell_spacing
 
     def compute_half(self):
         """sim/simulation.py:119-120: half neighbour lists, each pair term applied to both partners (ir/apply.py:111-125)."""
@@ -407,12 +443,12 @@ class Simulation:
         # (its generated dem.cpp gives identical bits either way, tests/test_oracle_pin.py).  The CUDA kernels traverse the
         # CSR cell lists directly in that order, so there is nothing to materialise: the flag is accepted and recorded.
         self._store_neighbors_per_cell = bool(store_neighbors_per_cell)
-        self.cell_spacing = spacing
+        self._cell_spacing = spacing
 
     def build_neighbor_lists(self, spacing):
         assert not getattr(self, "_store_neighbors_per_cell", False), \
             "Using neighbor-lists with store_neighbors_per_cell option is invalid."      # sim/simulation.py:256-257
-        self.cell_spacing = spacing                 # sim/simulation.py:255-261: cells and lists share the spacing
+        self._cell_spacing = spacing                 # sim/simulation.py:255-261: cells and lists share the spacing
         self.neighbor_cutoff = spacing
 
     def compute(self, func, cutoff_radius=None, symbols={}, pre_step=False, skip_first=False):
@@ -466,7 +502,7 @@ class Simulation:
         ctx.init_domain(grid, self._pbc, self._partitioner, world, rank)
         if world > 1:
             ctx.nccl_init(_broadcast_nccl_id(backend, rank, world))
-        if self.cell_spacing is None:
+        if self._cell_spacing is None:
             raise DslError("build_cell_lists() / build_neighbor_lists() was not called")
         families = [e["family"] for e in self.pre_step + self.functions]
         if "linear_spring_dashpot" in families:
@@ -491,7 +527,7 @@ class Simulation:
                 ctx.adjust_thermo(temp)
             elif kind == "read_particle_data":
                 nlocal = self._read_particle_data(ctx, *args)
-        ctx.setup_cells(self.cell_spacing)
+        ctx.setup_cells(self._cell_spacing)
         for e in self.setup_functions:          # setup() functions: once over the locals, right after the set-up statements
             if e["family"] != "generic_setup":
                 raise DslError(f"setup(): '{e['name']}' belongs to the DEM path")
@@ -586,7 +622,7 @@ class Simulation:
         cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
         begin = 0
         for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
-            ctx.dem_run(self.cell_spacing, begin, end)
+            ctx.dem_run(self._cell_spacing, begin, end)
             if self._vtk_due(end - 1):
                 self._vtk_write(ctx, end - 1, rank, world)
             begin = end
@@ -741,7 +777,7 @@ class Simulation:
         """The standard md.py procedure list runs in the native loop (pb_md_run); anything else in the Python loop."""
         if [p["family"] for p in pre] == ["initial_integrate"] and [f["family"] for f in fn] == ["lennard_jones", "final_integrate"] \
                 and pre[0]["skip_first"] and fn[1]["skip_first"] and not fn[0]["skip_first"] and pre[0]["dt"] == fn[1]["dt"]:
-            return (pre[0]["dt"], fn[0]["cutoff_value"], self.neighbor_cutoff, self.cell_spacing, self.reneighbor_frequency,
+            return (pre[0]["dt"], fn[0]["cutoff_value"], self.neighbor_cutoff, self._cell_spacing, self.reneighbor_frequency,
                     self._compute_thermo)
         return None
 

@@ -80,7 +80,12 @@ def test_plan_and_error_behaviour():
     psim = lj_script.build("gpu", 8, 100, 20, 10)
     assert [e["family"] for e in psim.pre_step] == ["initial_integrate"]
     assert [e["family"] for e in psim.functions] == ["lennard_jones", "final_integrate"]
-    assert psim.cell_spacing == 2.5 + 0.3 and psim.neighbor_cutoff == 2.5 + 0.3
+    assert psim.cell_spacing() == 2.5 + 0.3 and psim.neighbor_cutoff == 2.5 + 0.3
+    # the reference's query methods (sim/simulation.py:116-128, 159-201)
+    assert psim.use_double_precision() and psim.ndims() == 3 and psim.max_shapes() == 1 and psim.get_shape_id(0) == pairs.point_mass()
+    assert psim.position() is psim.property("position") and psim.property("mass").value == 1.0 and psim.property("nope") is None
+    assert psim.feature("type") == 4 and psim.feature_property("epsilon")[0] == "type" and psim.contact_property("x") is None
+    psim.enable_profiler()
     L = 8 * pow(4.0 / 0.8442, 1.0 / 3.0)
     assert psim.grid == [0.0, 0.0, 0.0, L, L, L]
     cpu = lj_script.build("cpu", 8, 10, 20, 10)
