@@ -25,19 +25,39 @@ class BackendError(RuntimeError):
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(INCLUDE, "pairs_b200.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
-        return LIB_PATH
-    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree).  One object per source, compiled
+    in parallel and only when the source or a header is newer, then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    headers = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(INCLUDE, "pairs_b200.h")]
+    objdir = os.path.join(os.path.dirname(LIB_PATH), "obj")
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-I" + INCLUDE, "-o", LIB_PATH, *srcs, "-ldl"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if verbose or r.returncode != 0:
-        print(r.stdout)
-    if r.returncode != 0:
-        raise BackendError("nvcc failed building libpairs_b200.so")
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def stale(target, deps):
+        return force or not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
+
+    def compile_one(name):
+        src, obj = os.path.join(CSRC, name), os.path.join(objdir, name[:-3] + ".o")
+        if not stale(obj, [src] + headers + [__file__]):
+            return obj, 0, ""
+        r = subprocess.run([nvcc, *flags, "-I" + INCLUDE, "-c", src, "-o", obj], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return obj, r.returncode, r.stdout
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for obj, rc, out in results:
+        if verbose or rc != 0:
+            print(out)
+        if rc != 0:
+            raise BackendError(f"nvcc failed compiling {os.path.basename(obj)[:-2]}.cu for libpairs_b200.so")
+    objs = [obj for obj, _, _ in results]
+    if stale(LIB_PATH, objs):
+        r = subprocess.run([nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *objs, "-ldl"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or r.returncode != 0:
+            print(r.stdout)
+        if r.returncode != 0:
+            raise BackendError("nvcc failed linking libpairs_b200.so")
     return LIB_PATH
 
 

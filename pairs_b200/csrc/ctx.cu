@@ -16,6 +16,8 @@ extern "C" const char *pb_last_error(const pb_ctx *ctx) {
     return ctx != nullptr ? ctx->err.c_str() : g_create_error.c_str();
 }
 
+extern "C" void pb_destroy(pb_ctx *ctx);
+
 extern "C" int pb_create(pb_ctx **out, int device) {
     *out = nullptr;
     int ndev = 0;
@@ -33,20 +35,31 @@ extern "C" int pb_create(pb_ctx **out, int device) {
     if(e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return -1; }
     pb_ctx *ctx = new pb_ctx();
     ctx->device = device;
-    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if(e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return -1; }
-    cudaEventCreate(&ctx->ev0);
-    cudaEventCreate(&ctx->ev1);
+    // every resource of the context, checked: a half-built context is destroyed again and the first error reported
+    auto fail = [&](cudaError_t err, const char *what) {
+        g_create_error = std::string("pairs_b200: ") + what + ": " + cudaGetErrorString(err);
+        pb_destroy(ctx);
+        return -1;
+    };
+#define PB_CREATE_CHECK(call)                                   \
+    do {                                                        \
+        e = (call);                                             \
+        if(e != cudaSuccess) { return fail(e, #call); }         \
+    } while(0)
+    PB_CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PB_CREATE_CHECK(cudaEventCreate(&ctx->ev0));
+    PB_CREATE_CHECK(cudaEventCreate(&ctx->ev1));
     {
         int prio_lo = 0, prio_hi = 0;      // comm stream gets the highest priority: its blocks are scheduled ahead of the force kernel's
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi);
+        PB_CREATE_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        PB_CREATE_CHECK(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
     }
-    cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
-    cudaMalloc(&ctx->d_scalars, sizeof(int) * PB_NSCALARS);
-    cudaMemset(ctx->d_scalars, 0, sizeof(int) * PB_NSCALARS);
-    cudaMallocHost(&ctx->h_scalars, sizeof(int) * PB_NSCALARS);
+    PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming));
+    PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+    PB_CREATE_CHECK(cudaMalloc(&ctx->d_scalars, sizeof(int) * PB_NSCALARS));
+    PB_CREATE_CHECK(cudaMemset(ctx->d_scalars, 0, sizeof(int) * PB_NSCALARS));
+    PB_CREATE_CHECK(cudaMallocHost(&ctx->h_scalars, sizeof(int) * PB_NSCALARS));
+#undef PB_CREATE_CHECK
     *out = ctx;
     return 0;
 }
@@ -57,7 +70,7 @@ void pb_jit_destroy(pb_ctx *ctx);
 extern "C" void pb_destroy(pb_ctx *ctx) {
     if(ctx == nullptr) { return; }
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if(ctx->stream != nullptr) { cudaStreamSynchronize(ctx->stream); }
     pb_nccl_destroy(ctx);
     pb_jit_destroy(ctx);
     void *bufs[] = {ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt, ctx->force, ctx->mass, ctx->mass_alt, ctx->type,
@@ -73,12 +86,9 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
     for(cudaEvent_t e : ctx->event_pool) { cudaEventDestroy(e); }
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
-    cudaEventDestroy(ctx->ev_prev);
-    cudaEventDestroy(ctx->ev_sync);
-    cudaStreamDestroy(ctx->comm_stream);
-    cudaStreamDestroy(ctx->stream);
+    for(cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_prev, ctx->ev_sync}) { if(e != nullptr) { cudaEventDestroy(e); } }
+    if(ctx->comm_stream != nullptr) { cudaStreamDestroy(ctx->comm_stream); }
+    if(ctx->stream != nullptr) { cudaStreamDestroy(ctx->stream); }
     delete ctx;
 }
 
