@@ -22,6 +22,8 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   md_custom_t1  md_t1 with other kernel bodies (softened LJ using sqrt / select / symbols, integrators with drag) -> generic kernels
   md_props_t1   md_t1 with user-defined properties (a real entering the pair force, written by a setup() function; a second volatile
               vector; reals and a vector integrated per particle) -> generic kernels on the user-property rows (csrc/props.cu)
+  md_vocab_t1   md_t1 with kernels that use the rest of the generic vocabulary (skip_when, cross, is_point_mass, integer properties
+              and operators, and / or / not, n-ary min / max, normalized, length, ...): module-level pin of pairs_b200/kernelgen.py
   md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
@@ -146,6 +148,42 @@ def md_props_variant(nx, steps):
     return patch
 
 
+VOCAB_KERNELS = '''def lennard_jones(i, j):
+    skip_when(uid[j] % 7 == 3)
+    d = delta(i, j)
+    dv = linear_velocity[j] - linear_velocity[i]
+    w = cross(linear_velocity[i], dv)
+    s = select(is_point_mass(j), 1.0, 0.5)
+    m = (uid[i] & 3) + (uid[j] | 1) + (type[i] ^ type[j]) + (~uid[j] & 1)
+    sr2 = 1.0 / squared_distance(i, j)
+    u = normalized(dv)
+    c = min(dot(u, linear_velocity[i]), length(dv), 1.5) + max(squared_length(dv), 0.25)
+    apply(force, w * s + d * (sr2 * m) + u * c + zero_vector())
+
+
+def initial_integrate(i):
+    linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
+    position[i] += dt * linear_velocity[i]
+
+
+def final_integrate(i):
+    skip_when(not is_point_mass(i))
+    if uid[i] % 2 == 0 and mass[i] > 0.5 or shape[i] == 1:
+        linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
+'''
+
+
+def md_vocab_variant(nx, steps):
+    """examples/md.py with kernels exercising the rest of the generic vocabulary: same text as tests/scripts/vocab_script.py.  Only its
+    modules are used (called on arrays the test provides); the program as a whole is not a meaningful simulation."""
+    base = md_variant(nx, steps, 1, 20)
+
+    def patch(text):
+        text = base(text)
+        return re.sub(r"def lennard_jones\(i, j\):.*?(?=\n\ncmd = )", VOCAB_KERNELS.rstrip("\n") + "\n", text, count=1, flags=re.S)
+    return patch
+
+
 def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None, verlet=False):
     def patch(text):
         if verlet:      # Verlet lists + BuildContactHistory instead of the cell-list traversal (sim/simulation.py:255-261, 402-406)
@@ -219,6 +257,7 @@ VARIANTS = {
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
     "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), ["-DREF_LJ_MODULE"], False),
     "md_props_t1": ("examples/md.py", md_props_variant(8, 100), ["modules:init_scale,lennard_jones,initial_integrate,final_integrate"], False),
+    "md_vocab_t1": ("examples/md.py", md_vocab_variant(8, 10), ["modules:lennard_jones,final_integrate"], False),
     # half neighbour lists + atomic update of the partner
     "md_half_t1": ("examples/md.py", md_variant(8, 100, 1, 20, half=True), ["-DREF_IS_MD", "-DREF_HALF_LISTS"], False),
     # examples/dem.py: spheres + 2 half-spaces, contact history, cell lists only, reneighbour every step

@@ -28,6 +28,8 @@ struct PbJitArgs {
     const int *numneigh;    // [cap]
     const int *neigh;       // sliced ELLPACK: ((i / 32) * nslots + k) * 32 + i % 32
     double *xdata;          // user-defined properties, rows of [cap]: component d of a property at (row0 + d) * cap + i
+    const int *uid;         // [cap]
+    const int *shape;       // [cap]
 };
 
 static const char *PB_JIT_PRELUDE = R"PRELUDE(
@@ -43,6 +45,8 @@ struct PbJitArgs {
     const int *numneigh;
     const int *neigh;
     double *xdata;
+    const int *uid;
+    const int *shape;
 };
 #define PB_FLAG_FIXED 4
 __device__ __forceinline__ int pb_w_type(double w) { return (int) (__double_as_longlong(w) & 0xffffffffLL); }
@@ -197,6 +201,7 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     a.cutsq = cutoff * cutoff;
     a.pos = ctx->pos; a.pos_w = ctx->pos; a.vel = ctx->vel; a.force = ctx->force; a.mass = ctx->mass; a.flags = ctx->flags;
     a.numneigh = ctx->numneigh; a.neigh = ctx->neigh; a.xdata = ctx->xdata;
+    a.uid = ctx->uid; a.shape = ctx->shape;
     void *params[] = {&a};
     PB_CHECK(cudaLaunchKernel((const void *) k.kernel, dim3(pb_blocks(ctx->nlocal, 128)), dim3(128), params, 0, ctx->stream));
     ctx->launches++;

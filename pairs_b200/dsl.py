@@ -732,6 +732,10 @@ class Simulation:
         for name, p in self.props.items():
             if name in builtin:
                 m[name] = builtin[name]
+            elif name in ("uid", "shape", "flags"):           # the implicit integer properties (sim/simulation.py:63-65): readable
+                m[name] = name
+            elif name in self.features:                       # the feature index of a particle ('type')
+                m[name] = "type"
             elif p.type in (Types.Real, Types.Vector) and name not in self.feature_props:
                 comps = 3 if p.type == Types.Vector else 1
                 m[name] = ("x", row, comps)

@@ -10,7 +10,9 @@ for every further real / vector property the script declares (rows of the user-p
                    prop[i], prop[j], featprop[i, j], sqrt, select, min, max, abs, dot, length, squared_length, normalized,
                    zero_vector, vector(x, y, z), + - * / unary -, comparisons, apply(prop, expr), local op= expr,
                    if / else (mapping/funcs.py:179-195; a local assigned inside an arm lives in that arm), v[0] / prop[i][2]
-                   (one component of a vector)
+                   (one component of a vector), cross, skip_when(cond) (keywords.py:62-65: `continue` with the next partner),
+                   is_point_mass / is_sphere / is_halfspace(i | j), the integer properties uid / shape / flags and the feature
+                   (`type`) as values, % & | ^ ~ on integers, and / or / not (both sides evaluated, as the reference prints them)
   particle kernels def k(i): the same expressions and statements, prop[i] = / += / -= expr
 
 Like the reference's generated code the output has ONE statement per operation, in Python's evaluation order, vectors
@@ -91,6 +93,10 @@ class _Gen:
             val = self.vec([self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(3)])
         elif store == "mass":
             val = ("f", self.tmp("double", f"a.mass[{idx}]", hoist))
+        elif store in ("uid", "shape", "flags"):
+            val = ("i", self.tmp("int", f"a.{store}[{idx}]", hoist))
+        elif store == "type":                                 # the feature index rides in the low bits of position.w
+            val = ("i", self.tmp("int", f"pb_w_type({'pi' if who == 'i' else 'pj'}.w)", hoist))
         elif isinstance(store, tuple):                        # user-defined property: rows of a.xdata
             comps = [self.tmp("double", _xref(store, d, idx), hoist) for d in range(store[2])]
             val = ("f", comps[0]) if store[2] == 1 else self.vec(comps)
@@ -117,9 +123,17 @@ class _Gen:
                 return v
             if isinstance(node.op, ast.Not):
                 return ("b", self.tmp("bool", f"!({v[1]})"))
+            if isinstance(node.op, ast.Invert) and v[0] == "i":
+                return ("i", self.tmp("int", f"~({v[1]})"))
             raise KernelGenError("unsupported unary operator")
         if isinstance(node, ast.BinOp):
             ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
+            int_ops = {ast.Mod: "%", ast.BitAnd: "&", ast.BitOr: "|", ast.BitXor: "^"}       # mapping/funcs.py:54-69, integers only
+            if type(node.op) in int_ops:
+                a, b = self.expr(node.left), self.expr(node.right)
+                if self.is_vec(a) or self.is_vec(b) or a[0] != "i" or b[0] != "i":
+                    raise KernelGenError(f"operator {int_ops[type(node.op)]} needs integer operands")
+                return ("i", self.tmp("int", f"{a[1]} {int_ops[type(node.op)]} {b[1]}"))
             if type(node.op) not in ops:
                 raise KernelGenError(f"unsupported operator {type(node.op).__name__}")
             return self.binop(ops[type(node.op)], self.expr(node.left), self.expr(node.right))
@@ -204,15 +218,20 @@ class _Gen:
             if self.kind != "pair":
                 raise KernelGenError(f"{f}() needs a pair kernel")
             return self.vec(["dx", "dy", "dz"]) if f == "delta" else ("f", "rsq")
-        args = [self.expr(a) for a in node.args]
+        args = [] if f in ("is_point_mass", "is_sphere", "is_halfspace") else [self.expr(a) for a in node.args]
         if f == "sqrt":
             return ("f", self.tmp("double", f"sqrt({args[0][1]})"))
         if f == "abs":
             return ("f", self.tmp("double", f"fabs({args[0][1]})"))
-        if f in ("min", "max"):                               # keywords.py:67-79: select(a < b, a, b) / select(a > b, a, b)
-            a, b = args
-            c = self.tmp("bool", f"{a[1]} {'<' if f == 'min' else '>'} {b[1]}")
-            return ("f", self.tmp("double", f"({c}) ? ({a[1]}) : ({b[1]})"))
+        if f in ("min", "max"):                               # keywords.py:67-79: e = a0; for a in rest: e = select(a < e, a, e)
+            if len(args) < 1 or any(self.is_vec(a) for a in args):
+                raise KernelGenError(f"{f}() takes scalars")
+            e = args[0]
+            for a in args[1:]:
+                c = self.tmp("bool", f"{a[1]} {'<' if f == 'min' else '>'} {e[1]}")
+                t = "i" if (a[0] == "i" and e[0] == "i") else "f"
+                e = (t, self.tmp("int" if t == "i" else "double", f"({c}) ? ({a[1]}) : ({e[1]})"))
+            return e
         if f == "select":
             c, a, b = args
             if self.is_vec(a) != self.is_vec(b):
@@ -220,6 +239,22 @@ class _Gen:
             if self.is_vec(a):
                 return self.vec([self.tmp("double", f"({c[1]}) ? ({x}) : ({y})") for x, y in zip(a[1], b[1])])
             return ("f", self.tmp("double", f"({c[1]}) ? ({a[1]}) : ({b[1]})"))
+        if f in ("is_point_mass", "is_sphere", "is_halfspace"):      # keywords.py:34-50: shape[p] == Shapes.<...>
+            if len(node.args) != 1 or not isinstance(node.args[0], ast.Name) or node.args[0].id not in ("i", "j") or \
+                    (node.args[0].id == "j" and self.kind != "pair"):
+                raise KernelGenError(f"{f}() takes the particle argument")
+            sh = self.load("shape", node.args[0].id)
+            return ("b", self.tmp("bool", f"{sh[1]} == {dict(is_sphere=0, is_halfspace=1, is_point_mass=2)[f]}"))
+        if f == "cross":                                      # keywords.py:95-103
+            a, b = args
+            if not (self.is_vec(a) and self.is_vec(b)):
+                raise KernelGenError("cross() takes two vectors")
+            out = []
+            for p, q in ((1, 2), (2, 0), (0, 1)):
+                l = self.tmp("double", f"{a[1][p]} * {b[1][q]}")
+                r = self.tmp("double", f"{a[1][q]} * {b[1][p]}")
+                out.append(self.tmp("double", f"{l} - {r}"))
+            return self.vec(out)
         if f == "dot":
             a, b = args
             p = [self.tmp("double", f"{x} * {y}") for x, y in zip(a[1], b[1])]
@@ -235,8 +270,11 @@ class _Gen:
             ln = self.tmp("double", f"sqrt({sq})")
             if f == "length":
                 return ("f", ln)
-            inv = self.tmp("double", f"1.0 / {ln}")          # keywords.py:105-112: v * (1.0 / length(v))
-            return self.vec([self.tmp("double", f"{x} * {inv}") for x in v[1]])
+            # keywords.py:105-112: select(length > 0.0, v * (1.0 / length), zero_vector())
+            pos = self.tmp("bool", f"{ln} > 0.0")
+            inv = self.tmp("double", f"1.0 / {ln}")
+            scaled = [self.tmp("double", f"{x} * {inv}") for x in v[1]]
+            return self.vec([self.tmp("double", f"({pos}) ? ({x}) : (0.0)") for x in scaled])
         if f == "zero_vector":
             return self.vec(["0.0", "0.0", "0.0"])
         if f == "vector":
@@ -283,6 +321,15 @@ class _Gen:
                 self.block(node.orelse)
             self.lines.append("}")
             return
+        if isinstance(node, ast.Expr) and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", None) == "skip_when":
+            if len(node.value.args) != 1:
+                raise KernelGenError("skip_when() takes one condition")
+            cond = self.expr(node.value.args[0])
+            if self.is_vec(cond):
+                raise KernelGenError("skip_when(): the condition must be a scalar")
+            # keywords.py:62-65 prints `continue`: the next partner in a pair kernel, the next particle otherwise
+            self.lines.append(f"if({cond[1]}) {{ {'continue' if self.kind == 'pair' else 'return'}; }}")
+            return
         if isinstance(node, ast.Expr) and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", None) == "apply":
             if self.kind != "pair":
                 raise KernelGenError("apply() needs a pair kernel")
@@ -320,6 +367,8 @@ class _Gen:
         raise KernelGenError(f"unsupported statement: {ast.unparse(node)}")
 
     def store(self, store, v):
+        if store in ("uid", "shape", "flags", "type"):
+            raise KernelGenError("integer properties (uid, shape, flags, the feature) are read-only in kernels")
         self.stored.add(store)
         if store == "mass":
             if self.is_vec(v):

@@ -199,7 +199,7 @@ def test_further_properties_become_user_defined_storage():
     psim.add_property("dipole", pairs.vector(), (0.0, 0.0, 1.0))
     st = psim._device_storage()
     assert st == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force", "charge": ("x", 0, 1),
-                  "field": ("x", 1, 3), "dipole": ("x", 4, 3)}
+                  "field": ("x", 1, 3), "dipole": ("x", 4, 3), "uid": "uid", "shape": "shape", "flags": "flags", "type": "type"}
     assert psim._user_props() == [("charge", 1, False, [0.5]), ("field", 3, True, [0.0, 0.0, 0.0]), ("dipole", 3, False, [0.0, 0.0, 1.0])]
     _, _, src = kernelgen.translate(charged, st, {}, 1, {}, backend.jit_prelude())
     assert "a.xdata[0 * (size_t) a.cap + j]" in src and "acc_x1_2 = acc_x1_2 +" in src and "a.xdata[3 * (size_t) a.cap + i] =" in src
@@ -212,7 +212,8 @@ def test_further_properties_become_user_defined_storage():
     q.add_property("v", pairs.vector())
     q.add_property("f", pairs.vector(), volatile=True)
     q.add_property("g", pairs.vector(), volatile=True)
-    assert q._device_storage() == {"r": "pos", "m": "mass", "m2": ("x", 0, 1), "v": "vel", "f": "force", "g": ("x", 1, 3)}
+    assert q._device_storage() == {"r": "pos", "m": "mass", "m2": ("x", 0, 1), "v": "vel", "f": "force", "g": ("x", 1, 3),
+                                   "uid": "uid", "shape": "shape", "flags": "flags"}
     # setup(): any per-particle function (generic path, no FIXED filter); pair functions are rejected
     def init(i):
         m2[i] = 2.0 * m[i]

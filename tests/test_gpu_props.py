@@ -1,4 +1,4 @@
-"""User-defined particle properties (csrc/props.cu, kernelgen.py) on the GPU: tests/scripts/props_script.py -- examples/md.py plus
+"""Features written after the round's GPU budget was spent.  User-defined particle properties (csrc/props.cu, kernelgen.py) on the GPU: tests/scripts/props_script.py -- examples/md.py plus
 five properties beyond the MD set, used by a setup() function, the pair kernel and both integrators -- against the run of the
 REFERENCE's code generator on the same text (oracle/build_ref.py variant md_props_t1 -> tests/golden/md_props_t1.npz), and the
 structural operations (sort, wrap, growth, ghosts, upload / download) through the C-ABI."""
@@ -57,6 +57,26 @@ def test_user_property_script_matches_the_reference_generator_golden(capsys):
         assert np.abs(ref).max() > 0.0 and np.abs(arr[og] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), name
     box = 8 * pow(4.0 / 0.8442, 1.0 / 3.0)
     pc.check_identity(ctx.real("position"), ctx.download_property("path"), scale, box, props_script.XLEN)
+
+
+def test_vocabulary_script_matches_the_reference_generator_golden(capsys):
+    """tests/scripts/vocab_script.py (skip_when, cross, is_point_mass, integer properties and operators, n-ary min / max,
+    normalized, ...) against the reference generator's run of the same text (variant md_vocab_t1): the module-level bit-for-bit
+    pin is tests/test_kernelgen.py; here the NVRTC-compiled kernels run the program's first iterations on the device."""
+    import vocab_script
+    z = np.load(os.path.join(ROOT, "tests", "golden", "md_vocab_t1.npz"))
+    psim = vocab_script.build("gpu", 8, 10, 20, 1)
+    ctx = psim.generate()
+    capsys.readouterr()
+    assert len(psim.thermo_log) == 11 and ctx.counts() == (int(z["nlocal"][10]), int(z["nghost"][10]))
+    for (ts, t, p), t_ref in zip(psim.thermo_log, z["temperature"]):
+        assert abs(t - t_ref) <= 1e-9 * t_ref, ts
+    psim1 = vocab_script.build("gpu", 8, 1, 20, 1)
+    ctx1 = psim1.generate()
+    capsys.readouterr()
+    tag = ctx1.ints("tag")
+    assert rel_err_force(by_id(tag, ctx1.real("force")), z["force_1"]) <= 1e-12
+    assert np.abs(by_id(tag, ctx1.real("linear_velocity")) - z["linear_velocity_1"]).max() <= 1e-12
 
 
 def test_property_store_through_the_c_abi(capsys):

@@ -16,7 +16,7 @@ def test_custom_kernels_take_the_generic_path_and_compile_for_sm100a():
     assert [e["family"] for e in psim.pre_step] == ["generic_particle"]
     assert [e["family"] for e in psim.functions] == ["generic_pair", "generic_particle"]
     storage = psim._device_storage()
-    assert storage == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force"}
+    assert storage == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force", "uid": "uid", "shape": "shape", "flags": "flags", "type": "type"}
     tables = {k: v[1] for k, v in psim.feature_props.items()}
     kind, name, src = kernelgen.translate(custom_script.lennard_jones, storage, tables, 4, {"kspring": 3.5, "rsoft": 1.05}, backend.jit_prelude())
     assert kind == "pair" and name == "user_lennard_jones"
@@ -152,17 +152,17 @@ def test_if_statements_and_local_updates():
 def _host_kernel(tmp_path, name, src):
     """Compiles a generated kernel for the HOST (tests/host/jit_host_emulation.h stands in for the CUDA bits) together with a
     driver that runs it for every particle; returns run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags, numneigh, neigh,
-    xdata=None) taking array addresses."""
+    xdata=None, uid=None, shape=None) taking array addresses."""
     import ctypes
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     cpp = tmp_path / f"{name}.cpp"
     cpp.write_text('#include "jit_host_emulation.h"\n' + src + f'''
 extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, double *vel, double *force, double *mass, int *flags,
-                    int *numneigh, int *neigh, double *xdata) {{
+                    int *numneigh, int *neigh, double *xdata, int *uid, int *shape) {{
     PbJitArgs a;
     a.nlocal = n; a.nslots = nslots; a.cap = cap; a.pad = 0; a.cutsq = cutsq; a.pos = pos; a.pos_w = pos; a.vel = vel; a.force = force;
-    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata;
+    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata; a.uid = uid; a.shape = shape;
     blockDim.x = 128;
     for(int i = 0; i < n; i++) {{ blockIdx.x = i / 128; threadIdx.x = i % 128; {name}(a); }}
 }}
@@ -172,10 +172,10 @@ extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, doub
                    check=True)
     lib = ctypes.CDLL(str(so))
     P = ctypes.c_void_p
-    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P, P]
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P, P, P, P]
 
-    def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None):
-        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata)
+    def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None, uid=None, shape=None):
+        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata, uid, shape)
     return run
 
 
@@ -311,7 +311,7 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
     psim = props_script.build("gpu", nx, 10, 20, 1)
     storage = psim._device_storage()
     assert storage == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force", "scale": ("x", 0, 1),
-                       "heat": ("x", 1, 1), "work": ("x", 2, 1), "path": ("x", 3, 3), "pull": ("x", 6, 3)}
+                       "heat": ("x", 1, 1), "work": ("x", 2, 1), "path": ("x", 3, 3), "pull": ("x", 6, 3), "uid": "uid", "shape": "shape", "flags": "flags", "type": "type"}
     assert [e["family"] for e in psim.setup_functions] == ["generic_setup"]
     assert psim._user_props() == [("scale", 1, False, [1.0]), ("heat", 1, False, [0.0]), ("work", 1, False, [0.0]),
                                   ("path", 3, False, [0.0, 0.0, 0.0]), ("pull", 3, True, [0.0, 0.0, 0.0])]
@@ -378,3 +378,64 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
         pull_r[:] = 0.0
         force[:] = 0.0
         xdata[6:9] = 0.0
+
+
+def test_rest_of_the_vocabulary_equals_the_reference_generators_modules_on_the_host(tmp_path):
+    """tests/scripts/vocab_script.py: skip_when, cross, is_point_mass, integer properties (uid, shape, the feature) with
+    % & | ^ ~, and / or / not, n-ary min / max, normalized (zero vectors included), length, squared_length, dot, zero_vector.
+    kernelgen's pair and particle kernel, compiled for the host, against the modules the REFERENCE's generator printed for the same
+    text (oracle/_ref variant md_vocab_t1), on the same arrays: identical bits."""
+    import numpy as np
+    import vocab_script
+    from oracle import port, ref
+    if not ref.available("md_vocab_t1"):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    prog = ref.RefProgram("md_vocab_t1")
+    nx = 6
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    r = sim.ranks[0]
+    rng = np.random.default_rng(33)
+    n = r.nlocal
+    r.real("position", n, view=True)[:] += 0.05 * (rng.random((n, 3)) - 0.5)
+    sim.step(0)
+    tot = n + r.nghost
+    nn, nl = r.neighbor_sets()
+    psim = vocab_script.build("gpu", nx, 10, 20, 1)
+    storage = psim._device_storage()
+    kern = {}
+    for fn, sym in ((vocab_script.lennard_jones, {}), (vocab_script.final_integrate, {"dt": 0.005})):
+        _, name, code = kernelgen.translate(fn, storage, {}, 4, sym, backend.jit_prelude())
+        assert backend.jit_check(code) > 1000
+        kern[name] = _host_kernel(tmp_path, name, code)
+    pos_r = r.real("position", tot).copy()
+    typ = r.ints("type", tot).copy()
+    flags = r.ints("flags", tot).copy()
+    flags[:n:13] |= 4
+    uid = rng.integers(0, 1000, tot).astype(np.int32)
+    shape = np.where(rng.random(tot) < 0.7, 2, rng.integers(0, 2, tot)).astype(np.int32)      # point masses, some spheres / half-spaces
+    vel_r = rng.standard_normal((tot, 3))
+    vel_r[5:tot:11] = vel_r[0]                    # partners with the SAME velocity as particle 0: normalized() of a zero vector
+    mass = np.where(rng.random(tot) < 0.5, 1.0, 0.25)
+    force_r = np.zeros((tot, 3))
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = pos_r
+    pos4[:, 3] = typ.astype(np.int64).view(np.float64)
+    vel = np.ascontiguousarray(vel_r.T)
+    force = np.zeros((3, tot))
+    nslots = int(nn.max())
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    for i in range(n):
+        neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
+    numneigh = np.zeros(tot, np.int32)
+    numneigh[:n] = nn
+    args = (_ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh), None, _ptr(uid), _ptr(shape))
+    prog.call_module("lennard_jones", neighbor_capacity=r.neighbor_capacity, nlocal=n, numneighs=nn.astype(np.int32),
+                     neighborlists=np.ascontiguousarray(nl, np.int32), flags=flags, position=pos_r, linear_velocity=vel_r, uid=uid, type=typ,
+                     shape=shape, force=force_r)
+    kern["user_lennard_jones"](n, nslots, tot, 2.5 * 2.5, *args)
+    assert np.isfinite(force_r).all() and np.abs(force_r).max() > 10.0 and np.array_equal(force[:, :n].T, force_r[:n])
+    v_before = vel_r.copy()
+    prog.call_module("final_integrate", nlocal=n, flags=flags, shape=shape, uid=uid, mass=mass, force=force_r, linear_velocity=vel_r)
+    kern["user_final_integrate"](n, nslots, tot, 0.0, *args)
+    changed = np.any(vel_r[:n] != v_before[:n], axis=1)
+    assert 0.1 * n < changed.sum() < 0.5 * n and np.array_equal(vel[:, :n].T, vel_r[:n])
