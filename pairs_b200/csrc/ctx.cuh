@@ -221,6 +221,7 @@ struct PbScratch {
     ~PbScratch() { if(p != nullptr) { cudaFree(p); } }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
     template<typename T> T *as() const { return (T *) p; }
+    template<typename T> T *release() { T *q = (T *) p; p = nullptr; return q; }     // the caller keeps the allocation
 };
 
 int pb_dem_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used);

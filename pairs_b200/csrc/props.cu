@@ -64,8 +64,10 @@ extern "C" int pb_add_property(pb_ctx *ctx, const char *name, int ncomps, int is
     const int new_rows = ctx->xrows + ncomps;
     if(cap > 0) {
         // rows are contiguous blocks of `cap` doubles: the existing rows are a prefix of the new allocation
-        double *q = nullptr;
-        PB_CHECK(cudaMalloc(&q, sizeof(double) * (size_t) new_rows * cap));
+        PbScratch fresh, fresh_alt;          // released to the context only when every step has succeeded
+        PB_CHECK(fresh.alloc(sizeof(double) * (size_t) new_rows * cap));
+        PB_CHECK(fresh_alt.alloc(sizeof(double) * (size_t) new_rows * cap));
+        double *q = fresh.as<double>();
         if(ctx->xdata != nullptr && ctx->xrows > 0) {
             PB_CHECK(cudaMemcpyAsync(q, ctx->xdata, sizeof(double) * (size_t) ctx->xrows * cap, cudaMemcpyDeviceToDevice, ctx->stream));
         }
@@ -73,10 +75,10 @@ extern "C" int pb_add_property(pb_ctx *ctx, const char *name, int ncomps, int is
             PB_LAUNCH(pb_k_xfill, pb_blocks((long) cap, 256), 256, (size_t) 0, cap, q + (size_t) (np.row0 + d) * cap, np.dflt[d]);
         }
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
-        if(ctx->xdata != nullptr) { PB_CHECK(cudaFree(ctx->xdata)); }
-        ctx->xdata = q;
+        if(ctx->xdata != nullptr) { PB_CHECK(cudaFree(ctx->xdata)); ctx->xdata = nullptr; }
         if(ctx->xdata_alt != nullptr) { PB_CHECK(cudaFree(ctx->xdata_alt)); ctx->xdata_alt = nullptr; }
-        PB_CHECK(cudaMalloc(&ctx->xdata_alt, sizeof(double) * (size_t) new_rows * cap));
+        ctx->xdata = fresh.release<double>();
+        ctx->xdata_alt = fresh_alt.release<double>();
     }
     ctx->xprops.push_back(np);
     ctx->xrows = new_rows;
@@ -105,21 +107,20 @@ extern "C" int pb_property_count(const pb_ctx *ctx) { return (int) ctx->xprops.s
 // capacity change (pb_ensure_particle_capacity): rows keep their first `used` entries, the rest takes the default
 int pb_xprops_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used) {
     if(ctx->xrows == 0) { return 0; }
-    double *q = nullptr;
-    PB_CHECK(cudaMalloc(&q, sizeof(double) * (size_t) ctx->xrows * newcap));
+    PbScratch fresh, fresh_alt;              // released to the context only when every step has succeeded
+    PB_CHECK(fresh.alloc(sizeof(double) * (size_t) ctx->xrows * newcap));
+    PB_CHECK(fresh_alt.alloc(sizeof(double) * (size_t) ctx->xrows * newcap));
+    double *q = fresh.as<double>();
     if(ctx->xdata != nullptr && used > 0) {
         PB_CHECK(cudaMemcpy2DAsync(q, newcap * sizeof(double), ctx->xdata, oldcap * sizeof(double), used * sizeof(double), (size_t) ctx->xrows,
                                    cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    {
-        int rc = pb_xprops_fill(ctx, q, newcap, used);
-        if(rc < 0) { cudaFree(q); return rc; }
-    }
+    PB_TRY(pb_xprops_fill(ctx, q, newcap, used));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    if(ctx->xdata != nullptr) { PB_CHECK(cudaFree(ctx->xdata)); }
-    ctx->xdata = q;
+    if(ctx->xdata != nullptr) { PB_CHECK(cudaFree(ctx->xdata)); ctx->xdata = nullptr; }
     if(ctx->xdata_alt != nullptr) { PB_CHECK(cudaFree(ctx->xdata_alt)); ctx->xdata_alt = nullptr; }
-    PB_CHECK(cudaMalloc(&ctx->xdata_alt, sizeof(double) * (size_t) ctx->xrows * newcap));
+    ctx->xdata = fresh.release<double>();
+    ctx->xdata_alt = fresh_alt.release<double>();
     return 0;
 }
 
