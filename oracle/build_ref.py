@@ -129,6 +129,8 @@ def initial_integrate(i):
 def final_integrate(i):
     linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
     work[i] = work[i] + dot(pull[i], linear_velocity[i])
+    if dot(pull[i], linear_velocity[i]) > 0.0:
+        ups[i] += 1 + (uid[i] & 1)
 '''
 
 
@@ -142,7 +144,8 @@ def md_props_variant(nx, steps):
         text = _sub(text, r"^psim\.add_feature\('type', ntypes\)",
                     "psim.add_property('scale', pairs.real(), 1.0)\npsim.add_property('heat', pairs.real(), 0.0)\n"
                     "psim.add_property('work', pairs.real(), 0.0)\npsim.add_property('path', pairs.vector())\n"
-                    "psim.add_property('pull', pairs.vector(), volatile=True)\npsim.add_feature('type', ntypes)")
+                    "psim.add_property('pull', pairs.vector(), volatile=True)\npsim.add_property('ups', pairs.int32(), 0)\n"
+                    "psim.add_feature('type', ntypes)")
         text = _sub(text, r"^psim\.reneighbor_every", "psim.setup(init_scale, symbols={'xlen': 13.0})\npsim.reneighbor_every")
         return text
     return patch

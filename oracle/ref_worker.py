@@ -5,7 +5,7 @@ ghost part (runtime/allocate.hpp:14-45; ghost `flags` are read but never transmi
 its results depend on the heap being zero pages -- true for its own executable, not inside a long-lived pytest
 process.  MALLOC_MMAP_THRESHOLD_ forces those allocations to come from fresh zero-filled mmaps.
 
-  python -m oracle.ref_worker dump  <variant> <out.npz> [nsteps] [name:width,...]   per-thermo-step snapshots (locals only;
+  python -m oracle.ref_worker dump  <variant> <out.npz> [nsteps] [name:width,...] [intname,...]   per-thermo-step snapshots (locals only;
                                                                     the list names further real properties to record)
   python -m oracle.ref_worker bench <variant> <warmup> <steps>     prints JSON {"n": atoms, "seconds": t, "steps": k}
 """
@@ -31,16 +31,16 @@ def spawn(args, **kw):
 BASE_PROPS = (("position", 3), ("linear_velocity", 3), ("force", 3), ("mass", 1))
 
 
-def dump(variant, out_path, nsteps=None, extra=()):
+def dump(variant, out_path, nsteps=None, extra=(), extra_int=()):
     """Snapshots of every thermo step of `variant`, produced in a fresh process; returns list of dicts.  `extra` = further
     (property name, width) pairs to record (user-defined properties of the variant)."""
-    p = spawn(["dump", variant, out_path, nsteps if nsteps is not None else -1] + ([",".join(f"{n}:{w}" for n, w in extra)] if extra else []))
+    p = spawn(["dump", variant, out_path, nsteps if nsteps is not None else -1, ",".join(f"{n}:{w}" for n, w in extra), ",".join(extra_int)])
     out, err = p.communicate()
     if p.returncode != 0:
         raise RuntimeError(f"ref_worker dump failed:\n{out}\n{err}")
     z = np.load(out_path)
     n = int(z["count"])
-    names = [k for k, _ in BASE_PROPS] + ["type"] + [k for k, _ in extra]
+    names = [k for k, _ in BASE_PROPS] + ["type"] + [k for k, _ in extra] + list(extra_int)
     snaps = [{k: z[f"{k}_{i}"] for k in names} | {"nlocal": int(z["nlocal"][i]), "nghost": int(z["nghost"][i])} for i in range(n)]
     for k in ("numneighs", "neighborlists"):
         if k in z.files:
@@ -77,10 +77,11 @@ def _main(argv):
         out_path = argv[2]
         nsteps = int(argv[3]) if len(argv) > 3 and int(argv[3]) >= 0 else None
         extra = tuple((x.split(":")[0], int(x.split(":")[1])) for x in argv[4].split(",")) if len(argv) > 4 and argv[4] else ()
-        snaps = prog.run_collect_thermo(props=BASE_PROPS + extra, steps=nsteps)
+        extra_int = tuple(x for x in argv[5].split(",") if x) if len(argv) > 5 else ()
+        snaps = prog.run_collect_thermo(props=BASE_PROPS + extra, int_props=("type", "flags") + extra_int, steps=nsteps)
         d = {"count": len(snaps), "nlocal": np.array([s["nlocal"] for s in snaps]), "nghost": np.array([s["nghost"] for s in snaps])}
         for i, s in enumerate(snaps):
-            for k in [x for x, _ in BASE_PROPS + extra] + ["type"]:
+            for k in [x for x, _ in BASE_PROPS + extra] + ["type"] + list(extra_int):
                 d[f"{k}_{i}"] = s[k]
         for k in ("numneighs", "neighborlists"):
             if snaps and k in snaps[0]:

@@ -720,8 +720,8 @@ class Simulation:
         """Property names -> device storage.  The MD path keeps dedicated arrays (csrc/ctx.cuh) for the position, ONE
         non-volatile vector (the velocity: 'linear_velocity' if declared, else the first one), ONE volatile vector (the force:
         'force' if declared, else the first one) and ONE non-volatile real ('mass', else the first one).  Every further real /
-        vector property is user-defined storage: ('x', first row, components) in the row block of csrc/props.cu, rows numbered in
-        declaration order."""
+        vector / integer property is user-defined storage: ('x', first row, components[, 'i']) in the row block of csrc/props.cu,
+        rows numbered in declaration order."""
         def pick(preferred, ptype, volatile):
             names = [n for n, p in self.props.items() if p.type == ptype and p.volatile == volatile and n != self.position_name
                      and n not in self.feature_props]
@@ -740,6 +740,9 @@ class Simulation:
                 comps = 3 if p.type == Types.Vector else 1
                 m[name] = ("x", row, comps)
                 row += comps
+            elif p.type == Types.Int32:                       # integers live in a double row too (exact below 2^53; the reference's
+                m[name] = ("x", row, 1, "i")                  # wire format carries them as doubles as well, sim/comm.py:328-329)
+                row += 1
         return m
 
     def _user_props(self):

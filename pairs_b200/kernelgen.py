@@ -98,8 +98,11 @@ class _Gen:
         elif store == "type":                                 # the feature index rides in the low bits of position.w
             val = ("i", self.tmp("int", f"pb_w_type({'pi' if who == 'i' else 'pj'}.w)", hoist))
         elif isinstance(store, tuple):                        # user-defined property: rows of a.xdata
-            comps = [self.tmp("double", _xref(store, d, idx), hoist) for d in range(store[2])]
-            val = ("f", comps[0]) if store[2] == 1 else self.vec(comps)
+            if len(store) > 3:                                # integer property kept in a double row
+                val = ("i", self.tmp("int", f"(int) {_xref(store, 0, idx)}", hoist))
+            else:
+                comps = [self.tmp("double", _xref(store, d, idx), hoist) for d in range(store[2])]
+                val = ("f", comps[0]) if store[2] == 1 else self.vec(comps)
         else:
             raise KernelGenError(f"no device storage for '{store}'")
         self.loaded[key] = val
@@ -335,7 +338,7 @@ class _Gen:
                 raise KernelGenError("apply() needs a pair kernel")
             tgt, val = node.value.args
             store = self.storage.get(getattr(tgt, "id", None))
-            if store not in ("force", "vel") and not isinstance(store, tuple):
+            if (store not in ("force", "vel") and not isinstance(store, tuple)) or (isinstance(store, tuple) and len(store) > 3):
                 raise KernelGenError("apply(): the target must be a declared vector property")
             v = self.expr(val)
             if isinstance(store, tuple) and store[2] == 1:
@@ -380,6 +383,11 @@ class _Gen:
             comps = [v[1]] if not self.is_vec(v) else v[1]
             if len(comps) != store[2]:
                 raise KernelGenError("assignment: a real property takes a scalar, a vector property a vector")
+            if len(store) > 3:                                # integer property: C conversion on assignment, as the reference's int array
+                iv = v if v[0] == "i" else ("i", self.tmp("int", f"(int) ({v[1]})"))
+                self.lines.append(f"{_xref(store, 0, 'i')} = (double) {iv[1]};")
+                self.loaded[(store, "i")] = iv
+                return
             for d, c in enumerate(comps):
                 self.lines.append(f"{_xref(store, d, 'i')} = {c};")
             self.loaded[(store, "i")] = v

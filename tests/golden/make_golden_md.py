@@ -18,10 +18,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 KEEP = {"md_t1": [0, 1, 19, 20, 100], "md_t2": [5, 60], "md_half_t1": [0, 1, 20, 100], "md_custom_t1": [0, 1, 20, 100], "md_props_t1": [0, 1, 20, 100], "md_vocab_t1": [0, 1, 10]}
 NAMES = {"md_t1": ("position", "linear_velocity", "force"), "md_t2": ("position", "force"),
          "md_half_t1": ("position", "linear_velocity", "force"), "md_custom_t1": ("position", "linear_velocity", "force"),
-         "md_props_t1": ("position", "linear_velocity", "force", "scale", "heat", "work", "path", "pull"),
+         "md_props_t1": ("position", "linear_velocity", "force", "scale", "heat", "work", "path", "pull", "ups"),
          "md_vocab_t1": ("position", "linear_velocity", "force")}
 # user-defined properties of a variant (tests/scripts/props_script.py), recorded next to the MD set
 EXTRA = {"md_props_t1": (("scale", 1), ("heat", 1), ("work", 1), ("path", 3), ("pull", 3))}
+EXTRA_INT = {"md_props_t1": ("ups",)}
 ONLY = sys.argv[1:]
 
 
@@ -36,7 +37,7 @@ def serial_thermo(s):
 for variant, keep in KEEP.items():
     if ONLY and variant not in ONLY:
         continue
-    snaps = ref_worker.dump(variant, f"/tmp/{variant}_golden_raw.npz", extra=EXTRA.get(variant, ()))
+    snaps = ref_worker.dump(variant, f"/tmp/{variant}_golden_raw.npz", extra=EXTRA.get(variant, ()), extra_int=EXTRA_INT.get(variant, ()))
     out = {"temperature": np.array([serial_thermo(s) for s in snaps]),
            "nlocal": np.array([s["nlocal"] for s in snaps]), "nghost": np.array([s["nghost"] for s in snaps]),
            "steps_kept": np.array(keep)}

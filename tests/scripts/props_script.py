@@ -2,7 +2,7 @@
 velocity / force the script declares a per-particle real that enters the pair force (scale, written once by a setup() function; its value is different for every
 lattice site, so it doubles as the particle identity when the final states are compared),
 a second volatile vector accumulated by the pair kernel (pull), two reals and a vector integrated by the per-particle kernels
-(heat, work, path).  The non-volatile ones have to follow their particle through the cell-order sort, the periodic wrap and the
+(heat, work, path) and an integer counter (ups).  The non-volatile ones have to follow their particle through the cell-order sort, the periodic wrap and the
 migration between ranks; none of the kernels is a hand-written family: they run through the generic path
 (pairs_b200/kernelgen.py -> NVRTC) on the user-property rows of csrc/props.cu."""
 import os
@@ -34,6 +34,8 @@ def initial_integrate(i):
 def final_integrate(i):
     linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
     work[i] = work[i] + dot(pull[i], linear_velocity[i])
+    if dot(pull[i], linear_velocity[i]) > 0.0:
+        ups[i] += 1 + (uid[i] & 1)
 
 
 XLEN = 13.0
@@ -60,6 +62,7 @@ def build(target="gpu", nx=8, timesteps=100, reneigh=20, thermo=1):
     psim.add_property('work', pairs.real(), 0.0)
     psim.add_property('path', pairs.vector())
     psim.add_property('pull', pairs.vector(), volatile=True)
+    psim.add_property('ups', pairs.int32(), 0)
     psim.add_feature('type', ntypes)
     psim.add_feature_property('type', 'epsilon', pairs.real(), [sigma for i in range(ntypes * ntypes)])
     psim.add_feature_property('type', 'sigma6', pairs.real(), [epsilon for i in range(ntypes * ntypes)])

@@ -1,5 +1,5 @@
 """Features written after the round's GPU budget was spent.  User-defined particle properties (csrc/props.cu, kernelgen.py) on the GPU: tests/scripts/props_script.py -- examples/md.py plus
-five properties beyond the MD set, used by a setup() function, the pair kernel and both integrators -- against the run of the
+six properties beyond the MD set, used by a setup() function, the pair kernel and both integrators -- against the run of the
 REFERENCE's code generator on the same text (oracle/build_ref.py variant md_props_t1 -> tests/golden/md_props_t1.npz), and the
 structural operations (sort, wrap, growth, ghosts, upload / download) through the C-ABI."""
 import os
@@ -38,6 +38,7 @@ def test_user_property_script_matches_the_reference_generator_golden(capsys):
     for name, arr in (("force", ctx1.real("force")), ("pull", ctx1.download_property("pull")), ("work", ctx1.download_property("work"))):
         assert rel_err_force(by_id(tag, arr), z[f"{name}_1"]) <= 1e-12, name
     assert np.abs(by_id(tag, ctx1.download_property("heat")) - z["heat_1"]).max() <= 1e-24     # dt * f.v with f = lattice round-off
+    assert np.array_equal(by_id(tag, ctx1.download_property("ups")), z["ups_1"].astype(np.float64))
     # the whole run: 100 steps, 6 reneighbourings (sort + wrap each time)
     psim = props_script.build("gpu", 8, 100, 20, 1)
     ctx = psim.generate()
@@ -52,7 +53,8 @@ def test_user_property_script_matches_the_reference_generator_golden(capsys):
     assert len(np.unique(scale)) == len(scale) and np.array_equal(scale[og], z["scale_100"][orf])
     for name, arr in (("position", ctx.real("position")), ("linear_velocity", ctx.real("linear_velocity")),
                       ("heat", ctx.download_property("heat")), ("work", ctx.download_property("work")),
-                      ("path", ctx.download_property("path")), ("pull", ctx.download_property("pull"))):
+                      ("path", ctx.download_property("path")), ("pull", ctx.download_property("pull")),
+                      ("ups", ctx.download_property("ups"))):
         ref = z[f"{name}_100"][orf]
         assert np.abs(ref).max() > 0.0 and np.abs(arr[og] - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), name
     box = 8 * pow(4.0 / 0.8442, 1.0 / 3.0)

@@ -287,7 +287,7 @@ def test_generated_custom_kernel_equals_the_reference_generators_module_on_the_h
 
 
 def test_kernels_on_user_defined_properties_equal_the_reference_generators_modules_on_the_host(tmp_path):
-    """tests/scripts/props_script.py declares five properties beyond the MD set (reals, vectors, one volatile) and uses them in a
+    """tests/scripts/props_script.py declares six properties beyond the MD set (reals, vectors, one volatile, an integer) and uses them in a
     setup() function, the pair kernel and both integrators.  kernelgen's CUDA for the four kernels, compiled for the host and run
     on the row layout of csrc/props.cu, against the modules the REFERENCE's generator printed for the same text (oracle/_ref
     variant md_props_t1) on its own AoS arrays: every property is identical bit for bit after set-up, force evaluation and the
@@ -311,10 +311,10 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
     psim = props_script.build("gpu", nx, 10, 20, 1)
     storage = psim._device_storage()
     assert storage == {"position": "pos", "mass": "mass", "linear_velocity": "vel", "force": "force", "scale": ("x", 0, 1),
-                       "heat": ("x", 1, 1), "work": ("x", 2, 1), "path": ("x", 3, 3), "pull": ("x", 6, 3), "uid": "uid", "shape": "shape", "flags": "flags", "type": "type"}
+                       "heat": ("x", 1, 1), "work": ("x", 2, 1), "path": ("x", 3, 3), "pull": ("x", 6, 3), "ups": ("x", 9, 1, "i"), "uid": "uid", "shape": "shape", "flags": "flags", "type": "type"}
     assert [e["family"] for e in psim.setup_functions] == ["generic_setup"]
     assert psim._user_props() == [("scale", 1, False, [1.0]), ("heat", 1, False, [0.0]), ("work", 1, False, [0.0]),
-                                  ("path", 3, False, [0.0, 0.0, 0.0]), ("pull", 3, True, [0.0, 0.0, 0.0])]
+                                  ("path", 3, False, [0.0, 0.0, 0.0]), ("pull", 3, True, [0.0, 0.0, 0.0]), ("ups", 1, False, [0.0])]
     tables = {k: v[1] for k, v in psim.feature_props.items()}
     kern = {}
     for fn, sym, skip_fixed in ((props_script.init_scale, {"xlen": props_script.XLEN}, False), (props_script.lennard_jones, {}, True),
@@ -331,6 +331,8 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
     vel_r = r.real("linear_velocity", tot).copy()
     mass = r.real("mass", tot).copy()
     scale_r, heat_r, work_r = np.full(tot, 1.0), np.zeros(tot), np.zeros(tot)
+    ups_r = np.zeros(tot, np.int32)
+    uid = rng.integers(0, 1000, tot).astype(np.int32)
     path_r, pull_r, force_r = np.zeros((tot, 3)), np.zeros((tot, 3)), np.zeros((tot, 3))
     cap = tot
     pos4 = np.zeros((tot, 4))
@@ -338,7 +340,7 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
     pos4[:, 3] = typ.astype(np.int64).view(np.float64)
     vel = np.ascontiguousarray(vel_r.T)
     force = np.zeros((3, cap))
-    xdata = np.zeros((9, cap))
+    xdata = np.zeros((10, cap))
     xdata[0] = 1.0
     nslots = int(nn.max())
     neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
@@ -346,12 +348,14 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
         neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
     numneigh = np.zeros(tot, np.int32)
     numneigh[:n] = nn
-    args = (_ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh), _ptr(xdata))
+    shape = np.full(tot, 2, np.int32)
+    args = (_ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh), _ptr(xdata), _ptr(uid), _ptr(shape))
 
     def same():
         return (np.array_equal(pos4[:n, :3], pos_r[:n]) and np.array_equal(vel[:, :n].T, vel_r[:n]) and np.array_equal(force[:, :n].T, force_r[:n])
                 and np.array_equal(xdata[0, :n], scale_r[:n]) and np.array_equal(xdata[1, :n], heat_r[:n]) and np.array_equal(xdata[2, :n], work_r[:n])
-                and np.array_equal(xdata[3:6, :n].T, path_r[:n]) and np.array_equal(xdata[6:9, :n].T, pull_r[:n]))
+                and np.array_equal(xdata[3:6, :n].T, path_r[:n]) and np.array_equal(xdata[6:9, :n].T, pull_r[:n])
+                and np.array_equal(xdata[9, :n], ups_r[:n].astype(np.float64)))
 
     # set-up function: every local, FIXED ones included
     prog.call_module("init_scale", nlocal=n, position=pos_r, scale=scale_r)
@@ -366,9 +370,10 @@ def test_kernels_on_user_defined_properties_equal_the_reference_generators_modul
         kern["user_lennard_jones"](n, nslots, cap, 2.5 * 2.5, *args)
         assert same() and np.abs(force_r).max() > 1.0 and np.abs(pull_r).max() > 0.1
         assert not force_r[:n:17].any()               # FIXED particles are skipped by compute() kernels
-        prog.call_module("final_integrate", nlocal=n, flags=flags, force=force_r, mass=mass, linear_velocity=vel_r, work=work_r, pull=pull_r)
+        prog.call_module("final_integrate", nlocal=n, flags=flags, force=force_r, mass=mass, linear_velocity=vel_r, work=work_r, pull=pull_r,
+                         uid=uid, ups=ups_r)
         kern["user_final_integrate"](n, nslots, cap, 0.0, *args)
-        assert same() and np.abs(work_r).max() > 0.0
+        assert same() and np.abs(work_r).max() > 0.0 and ups_r[:n].min() == 0 and ups_r[:n].max() == 2 * (it + 1)
         prog.call_module("initial_integrate", nlocal=n, flags=flags, force=force_r, mass=mass, linear_velocity=vel_r, position=pos_r,
                          path=path_r, heat=heat_r)
         kern["user_initial_integrate"](n, nslots, cap, 0.0, *args)
