@@ -193,6 +193,15 @@ int pb_jit_check(const char *source, char *log, int log_cap);
 int pb_jit_compile(pb_ctx *ctx, const char *source, const char *kernel_name, int *handle);
 int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff);
 
+/* User-defined DEM contact models: the contact KERNEL (detection, contact history keyed by the partner's uid, usage marks, clean-up,
+ * force / torque accumulation) stays the library's, the per-pair model of examples/dem.py:18-74 is exchanged for a device function
+ * `bool <model_name>(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, n, cp, delta, tij, tsd, ivm, sticking, F, T)` printed by
+ * pairs_b200/kernelgen.py from the user's kernel body (the reference generates code for any body: mapping/funcs.py:39-334, contact
+ * properties :230-263).  pb_jit_check_dem_model compiles only (cubin size or -1 + log, no GPU); pb_jit_set_dem_model installs the
+ * model for pb_dem_linear_spring_dashpot / pb_dem_run (source NULL: back to the built-in). */
+int pb_jit_check_dem_model(const char *model_source, const char *model_name, char *log, int log_cap);
+int pb_jit_set_dem_model(pb_ctx *ctx, const char *model_source, const char *model_name);
+
 /* Options.  Behaviour: "compute_half" (0/1) = Simulation.compute_half() (sim/simulation.py:119-120): half neighbour lists,
  * pair terms applied to both partners (ir/apply.py:111-125); applies from the next neighbour-list build.
  * Tuning knobs: "lanes_per_particle" (1,2,4,8; applies from the next build), "lj_unroll" (2,4,8), "fuse_integrate" (0/1),

@@ -28,11 +28,19 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree).  One object per source, compiled
     in parallel and only when the source or a header is newer, then linked."""
     from concurrent.futures import ThreadPoolExecutor
-    headers = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(INCLUDE, "pairs_b200.h")]
+    headers = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(CSRC, "dem_force_kernel.cuh"),
+               os.path.join(INCLUDE, "pairs_b200.h")]
     objdir = os.path.join(os.path.dirname(LIB_PATH), "obj")
     os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-I" + objdir]
+    # texts of the headers NVRTC needs at run time for user-defined DEM contact models (csrc/jit.cu), as raw string literals
+    emb = os.path.join(objdir, "embedded_sources.inc")
+    text = "".join(f'static const char *{sym} = R"PBSRC({open(os.path.join(CSRC, f)).read()})PBSRC";\n'
+                   for sym, f in (("PB_SRC_DEM_MATH", "dem_math.h"), ("PB_SRC_DEM_FORCE_KERNEL", "dem_force_kernel.cuh")))
+    if not os.path.exists(emb) or open(emb).read() != text:
+        with open(emb, "w") as f:
+            f.write(text)
 
     def stale(target, deps):
         return force or not os.path.exists(target) or any(os.path.getmtime(d) > os.path.getmtime(target) for d in deps)
@@ -142,6 +150,8 @@ SIGNATURES = {
     "pb_jit_check": (_I, [_S, ctypes.c_char_p, _I]),
     "pb_jit_compile": (_I, [_P, _S, _S, _IP]),
     "pb_jit_launch": (_I, [_P, _I, _I, _D]),
+    "pb_jit_check_dem_model": (_I, [_S, _S, ctypes.c_char_p, _I]),
+    "pb_jit_set_dem_model": (_I, [_P, _S, _S]),
     "pb_synchronize_device": (_I, [_P]),
     "pb_timers_enable": (_I, [_P, _I]),
     "pb_timers_get": (_I, [_P, _S, _DP, ctypes.POINTER(ctypes.c_long)]),
@@ -469,6 +479,11 @@ class Context:
         self._ck(self.lib.pb_jit_compile(self.h, source.encode(), kernel_name.encode(), ctypes.byref(h)))
         return h.value
 
+    def jit_set_dem_model(self, model_source, model_name):
+        """Installs a generated contact model into the DEM contact kernel (None: back to examples/dem.py's)."""
+        self._ck(self.lib.pb_jit_set_dem_model(self.h, None if model_source is None else model_source.encode(),
+                                               None if model_name is None else model_name.encode()))
+
     def jit_launch(self, handle, kind, cutoff=0.0):
         self._ck(self.lib.pb_jit_launch(self.h, handle, kind, cutoff))
 
@@ -522,6 +537,15 @@ def nccl_unique_id():
 def jit_prelude():
     """Source text every generated kernel starts with (struct PbJitArgs etc., csrc/jit.cu)."""
     return load().pb_jit_prelude().decode()
+
+
+def jit_check_dem_model(model_source, model_name):
+    """Compile-only check of the DEM contact kernel built around a generated contact model (no GPU needed)."""
+    log = ctypes.create_string_buffer(16384)
+    n = load().pb_jit_check_dem_model(model_source.encode(), model_name.encode(), log, len(log))
+    if n < 0:
+        raise BackendError(log.value.decode(errors="replace"))
+    return n
 
 
 def jit_check(source):

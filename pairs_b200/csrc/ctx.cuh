@@ -159,6 +159,7 @@ struct pb_ctx {
     int recv_cap = 0;
     int *sel_flag = nullptr, *sel_scan = nullptr; // [pcap+1] compaction scratch
     void *jit = nullptr;          // table of NVRTC-compiled user kernels (jit.cu)
+    void *dem_user_force = nullptr;   // DEM contact kernel built around a user-defined contact model (jit.cu), null = examples/dem.py's
     void *nccl = nullptr;         // NcclState* (comm_nccl.cu), null on a single rank
 
     // ---- reductions / host mirrors ----

@@ -1,0 +1,144 @@
+// The DEM contact kernel (pass 2 of linear_spring_dashpot, see dem_kernels.cu): history lookup / insert, the contact model, force and
+// torque accumulation.  This file is compiled twice: into libpairs_b200.so with the contact model of examples/dem.py
+// (pb_dem_pair_force, dem_math.h), and -- its text embedded in the library -- by NVRTC together with a contact model that
+// pairs_b200/kernelgen.py generated from a user's Python kernel body (PB_DEM_USER_PAIR, csrc/jit.cu pb_jit_compile_dem_force).  Both
+// take the same argument block, so the launch sites do not care which one runs.
+#pragma once
+
+struct PbDemForceArgs {
+    int nlocal, cap, C, ntypes;
+    PbDemParams P;
+    const double4 *pos;
+    const double *vel, *angvel, *mass, *radius, *normal;
+    const int *flags, *shape, *uid, *npairs, *pairs;
+    const double *fric_s, *fric_d;
+    int *num_contacts, *c_uid, *c_used, *c_stick;
+    double *c_tsd, *c_ivm, *force, *torque;
+    int accumulate;
+    int *overflow;
+};
+
+// FUSED folds the cheap per-particle modules around the contact evaluation of the generated loop into this kernel (the thread
+// owns particle i's force, torque and contact row anyway):
+//   reset_volatile_properties + gravity    f = 0; f.z = gravity(f.z)   before the contact sums are added, same operations
+//   reset_contact_history_usage_status     the "used" marks live in a register bit mask (contact capacity <= 32)
+//   clear_unused_contact_history           the swap-with-last compaction runs on the row at the end, driven by the mask
+// (euler sits between the contact kernel and the clean-up in the reference's list; it touches no contact data, so the order
+// does not matter).  Nine launches -- six memsets and three kernels -- and their passes over the arrays disappear.
+template<bool FUSED>
+__device__ __forceinline__ void pb_dem_force_body(const PbDemForceArgs &a) {
+    const int nlocal = a.nlocal, cap = a.cap, C = a.C, ntypes = a.ntypes;
+    const PbDemParams &P = a.P;
+    const double4 *__restrict__ pos = a.pos;
+    const double *__restrict__ vel = a.vel, *__restrict__ angvel = a.angvel, *__restrict__ mass = a.mass, *__restrict__ radius = a.radius,
+                 *__restrict__ normal = a.normal;
+    const int *__restrict__ flags = a.flags, *__restrict__ shape = a.shape, *__restrict__ uid = a.uid, *__restrict__ npairs = a.npairs,
+              *__restrict__ pairs = a.pairs;
+    const double *__restrict__ fric_s = a.fric_s, *__restrict__ fric_d = a.fric_d;
+    int *__restrict__ num_contacts = a.num_contacts, *__restrict__ c_uid = a.c_uid, *__restrict__ c_used = a.c_used, *__restrict__ c_stick = a.c_stick;
+    double *__restrict__ c_tsd = a.c_tsd, *__restrict__ c_ivm = a.c_ivm, *__restrict__ force = a.force, *__restrict__ torque = a.torque;
+    const int accumulate = a.accumulate;
+    int *__restrict__ overflow = a.overflow;
+    (void) P; (void) fric_s; (void) fric_d;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= nlocal) { return; }
+    const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
+    double Fs[3] = {0.0, 0.0, 0.0}, Ts[3] = {0.0, 0.0, 0.0}, Fh[3] = {0.0, 0.0, 0.0}, Th[3] = {0.0, 0.0, 0.0};
+    const int np = npairs[i];
+    unsigned usedmask = 0u;
+    int ncont_end = FUSED ? num_contacts[i] : 0;
+    if(!fixed && np > 0) {
+        const double4 pi4 = pb_ld_pos(pos + i);
+        const double xi[3] = {pi4.x, pi4.y, pi4.z};
+        const int ti = pb_w_type(pi4.w) * ntypes;
+        const double vi[3] = {vel[i], vel[(size_t) cap + i], vel[(size_t) 2 * cap + i]};
+        const double wi[3] = {angvel[i], angvel[(size_t) cap + i], angvel[(size_t) 2 * cap + i]};
+        const double ri = radius[i];
+        const double inv_mi = 1.0 / mass[i];
+        (void) inv_mi; (void) ri;
+        int ncont = num_contacts[i];
+        for(int q = 0; q < np; q++) {
+            const int j = pairs[(size_t) q * cap + i];
+            const int sh = shape[j];
+            double *F = (sh == 0) ? Fs : Fh, *T = (sh == 0) ? Ts : Th;
+            const double4 pj4 = pb_ld_pos(pos + j);
+            const double xj[3] = {pj4.x, pj4.y, pj4.z};
+            double n[3], cp[3], delta;
+            if(sh == PB_SHAPE_SPHERE) {
+                pb_dem_geom_sphere(xi, ri, xj, radius[j], n, cp, &delta);      // same function, same inputs as pass 1: same values
+            } else {
+                const double nj[3] = {normal[j], normal[(size_t) cap + j], normal[(size_t) 2 * cap + j]};
+                pb_dem_geom_halfspace(xi, ri, xj, nj, n, cp, &delta);
+            }
+            // contact-history slot keyed by uid[j] (mapping/funcs.py:240-263): last match wins, miss -> append defaults
+            const int uj = uid[j];
+            int slot = -1;
+            for(int c = 0; c < ncont; c++) { if(c_uid[(size_t) c * cap + i] == uj) { slot = c; } }
+            if(slot == -1) {
+                if(ncont >= C) { atomicMax(overflow, ncont + 1); continue; }
+                slot = ncont++;
+                c_uid[(size_t) slot * cap + i] = uj;
+                c_stick[(size_t) slot * cap + i] = 0;
+                for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = 0.0; }
+                c_ivm[(size_t) slot * cap + i] = 0.0;
+            }
+            if(FUSED) { usedmask |= 1u << slot; } else { c_used[(size_t) slot * cap + i] = 1; }
+            double tsd[3] = {c_tsd[((size_t) 0 * C + slot) * cap + i], c_tsd[((size_t) 1 * C + slot) * cap + i],
+                             c_tsd[((size_t) 2 * C + slot) * cap + i]};
+            double ivm = c_ivm[(size_t) slot * cap + i];
+            int stick = c_stick[(size_t) slot * cap + i];
+            const double vj[3] = {vel[j], vel[(size_t) cap + j], vel[(size_t) 2 * cap + j]};
+            const double wj[3] = {angvel[j], angvel[(size_t) cap + j], angvel[(size_t) 2 * cap + j]};
+            const int tj = pb_w_type(pj4.w);
+            double Fp[3], Tp[3];
+#ifdef PB_DEM_USER_PAIR
+            // a contact model generated from a user's kernel body; false = skip_when() left the pair (no force, no torque)
+            if(!PB_DEM_USER_PAIR(xi, vi, wi, mass[i], ri, xj, vj, wj, mass[j], radius[j], n, cp, delta, ti + tj, tsd, &ivm, &stick, Fp, Tp)) {
+                for(int d = 0; d < 3; d++) { Fp[d] = 0.0; Tp[d] = 0.0; }
+            }
+#else
+            pb_dem_pair_force(P, xi, vi, wi, inv_mi, xj, vj, wj, mass[j], n, cp, delta, fric_s[ti + tj], fric_d[ti + tj], tsd, &ivm, &stick,
+                              Fp, Tp);
+#endif
+            for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = tsd[d]; }
+            c_ivm[(size_t) slot * cap + i] = ivm;
+            c_stick[(size_t) slot * cap + i] = stick;
+            for(int d = 0; d < 3; d++) { F[d] = F[d] + Fp[d]; T[d] = T[d] + Tp[d]; }
+        }
+        if(FUSED) { ncont_end = ncont; } else { num_contacts[i] = ncont; }
+    }
+    if(FUSED) {
+        // clear_unused_contact_history (sim/contact_history.py:90-127): an unused slot is overwritten by the last one
+        int c = 0, cnt = ncont_end;
+        while(c < cnt) {
+            if(((usedmask >> c) & 1u) == 0u) {
+                const int last = cnt - 1;
+                if(last > 0) {
+                    c_stick[(size_t) c * cap + i] = c_stick[(size_t) last * cap + i];
+                    for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + c) * cap + i] = c_tsd[((size_t) d * C + last) * cap + i]; }
+                    c_ivm[(size_t) c * cap + i] = c_ivm[(size_t) last * cap + i];
+                    c_uid[(size_t) c * cap + i] = c_uid[(size_t) last * cap + i];
+                    usedmask = (usedmask & ~(1u << c)) | (((usedmask >> last) & 1u) << c);
+                }
+                cnt--;
+            } else {
+                c++;
+            }
+        }
+        for(int k = 0; k < cnt; k++) { c_used[(size_t) k * cap + i] = 1; }
+        num_contacts[i] = cnt;
+    }
+    // prop[i] = prop[i] + (acc_sphere + acc_halfspace)  (sim/interaction.py:280-292)
+    for(int d = 0; d < 3; d++) {
+        double f_old = accumulate ? force[(size_t) d * cap + i] : 0.0;
+        const double t_old = accumulate ? torque[(size_t) d * cap + i] : 0.0;
+        if(FUSED && d == 2 && !fixed) { f_old = pb_dem_gravity(P, radius[i], f_old); }      // gravity on the freshly reset force
+        if(!fixed) {
+            force[(size_t) d * cap + i] = f_old + (Fs[d] + Fh[d]);
+            torque[(size_t) d * cap + i] = t_old + (Ts[d] + Th[d]);
+        } else if(!accumulate) {
+            force[(size_t) d * cap + i] = 0.0;
+            torque[(size_t) d * cap + i] = 0.0;
+        }
+    }
+}

@@ -689,118 +689,34 @@ __global__ void __launch_bounds__(128) pb_k_dem_detect(int nlocal, int cap, int 
     npairs[i] = np;
 }
 
-// FUSED folds the cheap per-particle modules around the contact evaluation of the generated loop into this kernel (the thread
-// owns particle i's force, torque and contact row anyway):
-//   reset_volatile_properties + gravity    f = 0; f.z = gravity(f.z)   before the contact sums are added, same operations
-//   reset_contact_history_usage_status     the "used" marks live in a register bit mask (contact capacity <= 32)
-//   clear_unused_contact_history           the swap-with-last compaction runs on the row at the end, driven by the mask
-// (euler sits between the contact kernel and the clean-up in the reference's list; it touches no contact data, so the order
-// does not matter).  Nine launches -- six memsets and three kernels -- and their passes over the arrays disappear.
+#include "dem_force_kernel.cuh"
+
 template<bool FUSED>
-__global__ void __launch_bounds__(128) pb_k_dem_force(int nlocal, int cap, int C, int ntypes, PbDemParams P, const double4 *__restrict__ pos,
-                                                      const double *__restrict__ vel, const double *__restrict__ angvel,
-                                                      const double *__restrict__ mass, const double *__restrict__ radius,
-                                                      const double *__restrict__ normal, const int *__restrict__ flags,
-                                                      const int *__restrict__ shape, const int *__restrict__ uid,
-                                                      const int *__restrict__ npairs, const int *__restrict__ pairs,
-                                                      const double *__restrict__ fric_s, const double *__restrict__ fric_d,
-                                                      int *__restrict__ num_contacts, int *__restrict__ c_uid, int *__restrict__ c_used,
-                                                      int *__restrict__ c_stick, double *__restrict__ c_tsd, double *__restrict__ c_ivm,
-                                                      double *__restrict__ force, double *__restrict__ torque, int accumulate,
-                                                      int *__restrict__ overflow) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= nlocal) { return; }
-    const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
-    double Fs[3] = {0.0, 0.0, 0.0}, Ts[3] = {0.0, 0.0, 0.0}, Fh[3] = {0.0, 0.0, 0.0}, Th[3] = {0.0, 0.0, 0.0};
-    const int np = npairs[i];
-    unsigned usedmask = 0u;
-    int ncont_end = FUSED ? num_contacts[i] : 0;
-    if(!fixed && np > 0) {
-        const double4 pi4 = pb_ld_pos(pos + i);
-        const double xi[3] = {pi4.x, pi4.y, pi4.z};
-        const int ti = pb_w_type(pi4.w) * ntypes;
-        const double vi[3] = {vel[i], vel[(size_t) cap + i], vel[(size_t) 2 * cap + i]};
-        const double wi[3] = {angvel[i], angvel[(size_t) cap + i], angvel[(size_t) 2 * cap + i]};
-        const double ri = radius[i];
-        const double inv_mi = 1.0 / mass[i];
-        int ncont = num_contacts[i];
-        for(int q = 0; q < np; q++) {
-            const int j = pairs[(size_t) q * cap + i];
-            const int sh = shape[j];
-            double *F = (sh == 0) ? Fs : Fh, *T = (sh == 0) ? Ts : Th;
-            const double4 pj4 = pb_ld_pos(pos + j);
-            const double xj[3] = {pj4.x, pj4.y, pj4.z};
-            double n[3], cp[3], delta;
-            if(sh == PB_SHAPE_SPHERE) {
-                pb_dem_geom_sphere(xi, ri, xj, radius[j], n, cp, &delta);      // same function, same inputs as pass 1: same values
-            } else {
-                const double nj[3] = {normal[j], normal[(size_t) cap + j], normal[(size_t) 2 * cap + j]};
-                pb_dem_geom_halfspace(xi, ri, xj, nj, n, cp, &delta);
-            }
-            // contact-history slot keyed by uid[j] (mapping/funcs.py:240-263): last match wins, miss -> append defaults
-            const int uj = uid[j];
-            int slot = -1;
-            for(int c = 0; c < ncont; c++) { if(c_uid[(size_t) c * cap + i] == uj) { slot = c; } }
-            if(slot == -1) {
-                if(ncont >= C) { atomicMax(overflow, ncont + 1); continue; }
-                slot = ncont++;
-                c_uid[(size_t) slot * cap + i] = uj;
-                c_stick[(size_t) slot * cap + i] = 0;
-                for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = 0.0; }
-                c_ivm[(size_t) slot * cap + i] = 0.0;
-            }
-            if(FUSED) { usedmask |= 1u << slot; } else { c_used[(size_t) slot * cap + i] = 1; }
-            double tsd[3] = {c_tsd[((size_t) 0 * C + slot) * cap + i], c_tsd[((size_t) 1 * C + slot) * cap + i],
-                             c_tsd[((size_t) 2 * C + slot) * cap + i]};
-            double ivm = c_ivm[(size_t) slot * cap + i];
-            int stick = c_stick[(size_t) slot * cap + i];
-            const double vj[3] = {vel[j], vel[(size_t) cap + j], vel[(size_t) 2 * cap + j]};
-            const double wj[3] = {angvel[j], angvel[(size_t) cap + j], angvel[(size_t) 2 * cap + j]};
-            const int tj = pb_w_type(pj4.w);
-            double Fp[3], Tp[3];
-            pb_dem_pair_force(P, xi, vi, wi, inv_mi, xj, vj, wj, mass[j], n, cp, delta, fric_s[ti + tj], fric_d[ti + tj], tsd, &ivm, &stick,
-                              Fp, Tp);
-            for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = tsd[d]; }
-            c_ivm[(size_t) slot * cap + i] = ivm;
-            c_stick[(size_t) slot * cap + i] = stick;
-            for(int d = 0; d < 3; d++) { F[d] = F[d] + Fp[d]; T[d] = T[d] + Tp[d]; }
-        }
-        if(FUSED) { ncont_end = ncont; } else { num_contacts[i] = ncont; }
-    }
-    if(FUSED) {
-        // clear_unused_contact_history (sim/contact_history.py:90-127): an unused slot is overwritten by the last one
-        int c = 0, cnt = ncont_end;
-        while(c < cnt) {
-            if(((usedmask >> c) & 1u) == 0u) {
-                const int last = cnt - 1;
-                if(last > 0) {
-                    c_stick[(size_t) c * cap + i] = c_stick[(size_t) last * cap + i];
-                    for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + c) * cap + i] = c_tsd[((size_t) d * C + last) * cap + i]; }
-                    c_ivm[(size_t) c * cap + i] = c_ivm[(size_t) last * cap + i];
-                    c_uid[(size_t) c * cap + i] = c_uid[(size_t) last * cap + i];
-                    usedmask = (usedmask & ~(1u << c)) | (((usedmask >> last) & 1u) << c);
-                }
-                cnt--;
-            } else {
-                c++;
-            }
-        }
-        for(int k = 0; k < cnt; k++) { c_used[(size_t) k * cap + i] = 1; }
-        num_contacts[i] = cnt;
-    }
-    // prop[i] = prop[i] + (acc_sphere + acc_halfspace)  (sim/interaction.py:280-292)
-    for(int d = 0; d < 3; d++) {
-        double f_old = accumulate ? force[(size_t) d * cap + i] : 0.0;
-        const double t_old = accumulate ? torque[(size_t) d * cap + i] : 0.0;
-        if(FUSED && d == 2 && !fixed) { f_old = pb_dem_gravity(P, radius[i], f_old); }      // gravity on the freshly reset force
-        if(!fixed) {
-            force[(size_t) d * cap + i] = f_old + (Fs[d] + Fh[d]);
-            torque[(size_t) d * cap + i] = t_old + (Ts[d] + Th[d]);
-        } else if(!accumulate) {
-            force[(size_t) d * cap + i] = 0.0;
-            torque[(size_t) d * cap + i] = 0.0;
-        }
-    }
+__global__ void __launch_bounds__(128) pb_k_dem_force(PbDemForceArgs a) { pb_dem_force_body<FUSED>(a); }
+
+// the argument block of the contact kernel (dem_force_kernel.cuh), the same for the built-in and for a user-defined contact model
+static PbDemForceArgs pb_dem_force_args(pb_ctx *ctx, int accumulate) {
+    PbDemForceArgs a;
+    a.nlocal = ctx->nlocal; a.cap = ctx->pcap; a.C = ctx->ccontacts; a.ntypes = ctx->dem_ntypes;
+    a.P = pb_dem_params(ctx);
+    a.pos = ctx->pos; a.vel = ctx->vel; a.angvel = ctx->angvel; a.mass = ctx->mass; a.radius = ctx->radius; a.normal = ctx->normal;
+    a.flags = ctx->flags; a.shape = ctx->shape; a.uid = ctx->uid; a.npairs = ctx->numneigh; a.pairs = ctx->neigh;
+    a.fric_s = ctx->d_fric_static; a.fric_d = ctx->d_fric_dynamic;
+    a.num_contacts = ctx->num_contacts; a.c_uid = ctx->contact_uid; a.c_used = ctx->contact_used; a.c_stick = ctx->contact_stick;
+    a.c_tsd = ctx->contact_tsd; a.c_ivm = ctx->contact_ivm; a.force = ctx->force; a.torque = ctx->torque;
+    a.accumulate = accumulate;
+    a.overflow = ctx->d_dem_flag;
+    return a;
+}
+
+int pb_jit_launch_dem_force_raw(pb_ctx *ctx, int fused, void *args_struct);     // jit.cu: the user's contact model, if one is installed
+
+template<bool FUSED>
+static int pb_launch_dem_force(pb_ctx *ctx, int accumulate) {
+    const PbDemForceArgs a = pb_dem_force_args(ctx, accumulate);
+    if(ctx->dem_user_force != nullptr) { return pb_jit_launch_dem_force_raw(ctx, FUSED ? 1 : 0, (void *) &a); }
+    PB_LAUNCH(pb_k_dem_force<FUSED>, pb_blocks(ctx->nlocal, 128), 128, a);
+    return 0;
 }
 
 extern "C" int pb_dem_linear_spring_dashpot(pb_ctx *ctx) {
@@ -821,10 +737,7 @@ extern "C" int pb_dem_linear_spring_dashpot(pb_ctx *ctx) {
     PB_LAUNCH(pb_k_dem_detect, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], C,
               ctx->pos, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->numneigh,
               ctx->neigh, ctx->d_dem_flag);
-    PB_LAUNCH(pb_k_dem_force<false>, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, C, ctx->dem_ntypes, pb_dem_params(ctx), ctx->pos, ctx->vel,
-              ctx->angvel, ctx->mass, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->uid, ctx->numneigh, ctx->neigh,
-              ctx->d_fric_static, ctx->d_fric_dynamic, ctx->num_contacts, ctx->contact_uid, ctx->contact_used, ctx->contact_stick,
-              ctx->contact_tsd, ctx->contact_ivm, ctx->force, ctx->torque, 1, ctx->d_dem_flag);
+    PB_TRY(pb_launch_dem_force<false>(ctx, 1));
     ctx->neigh_n = -1;
     return 0;
 }
@@ -846,10 +759,7 @@ static int pb_dem_contacts_fused(pb_ctx *ctx) {
     PB_LAUNCH(pb_k_dem_detect, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, ctx->ncells, ctx->dim_cells[1], ctx->dim_cells[2], C,
               ctx->pos, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->particle_cell, ctx->cell_start, ctx->cell_list, ctx->numneigh,
               ctx->neigh, ctx->d_dem_flag);
-    PB_LAUNCH(pb_k_dem_force<true>, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->pcap, C, ctx->dem_ntypes, pb_dem_params(ctx), ctx->pos, ctx->vel,
-              ctx->angvel, ctx->mass, ctx->radius, ctx->normal, ctx->flags, ctx->shape, ctx->uid, ctx->numneigh, ctx->neigh,
-              ctx->d_fric_static, ctx->d_fric_dynamic, ctx->num_contacts, ctx->contact_uid, ctx->contact_used, ctx->contact_stick,
-              ctx->contact_tsd, ctx->contact_ivm, ctx->force, ctx->torque, 0, ctx->d_dem_flag);
+    PB_TRY(pb_launch_dem_force<true>(ctx, 0));
     ctx->neigh_n = -1;
     return 0;
 }

@@ -209,6 +209,7 @@ def _unify(t, u, binding):
 
 
 FORCE_GENERIC = False        # tests: send every kernel through the generic (NVRTC) path, also the recognised ones
+FORCE_GENERIC_CONTACT_MODEL = False      # tests: DEM scripts get their contact model generated even if it is examples/dem.py's
 
 
 def recognise(func):
@@ -453,7 +454,7 @@ class Simulation:
 
     def compute(self, func, cutoff_radius=None, symbols={}, pre_step=False, skip_first=False):
         try:
-            if FORCE_GENERIC:
+            if FORCE_GENERIC or (FORCE_GENERIC_CONTACT_MODEL and self.use_contact_history and len(inspect.signature(func).parameters) == 2):
                 raise DslError("generic path forced")
             family, roles = recognise(func)
         except DslError:
@@ -505,7 +506,7 @@ class Simulation:
         if self._cell_spacing is None:
             raise DslError("build_cell_lists() / build_neighbor_lists() was not called")
         families = [e["family"] for e in self.pre_step + self.functions]
-        if "linear_spring_dashpot" in families:
+        if "linear_spring_dashpot" in families or (self.use_contact_history and "generic_pair" in families):
             if self._compute_half:
                 raise DslError("compute_half() is implemented for the neighbour-list (md.py) path only")
             return self._generate_dem(ctx, rank, world)
@@ -563,24 +564,32 @@ class Simulation:
     # -- DEM (examples/dem.py): spheres + half-spaces, contact history, cell-list traversal, reneighbouring every step --
     def _generate_dem(self, ctx, rank, world):
         fams = [e["family"] for e in self.functions]
-        if self.pre_step or fams != ["gravity", "linear_spring_dashpot", "euler"] or not self.use_contact_history \
-                or self.neighbor_cutoff is not None or self.reneighbor_frequency != 1:
-            raise DslError("DEM: only the procedure list of examples/dem.py (gravity, linear_spring_dashpot, euler over cell lists, "
-                           "contact history, reneighbouring every step) is implemented")
+        if self.pre_step or fams not in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"]) \
+                or not self.use_contact_history or self.neighbor_cutoff is not None or self.reneighbor_frequency != 1:
+            raise DslError("DEM: the procedure list of examples/dem.py (gravity, a contact model, euler over cell lists, contact "
+                           "history, reneighbouring every step) is implemented; the contact model may be any kernel body")
         grav, lsd, eul = self.functions
-        nk = 1
-        fs_name, fd_name = lsd["roles"]["friction_static"], lsd["roles"]["friction_dynamic"]
-        for nme in (fs_name, fd_name):
-            if nme not in self.feature_props:
-                raise DslError(f"{lsd['name']}: '{nme}' must be a feature property")
-        nk = self.features[self.feature_props[fs_name][0]]
         ctx.dem_enable(self.neighbor_capacity)
-        dt = self._symbol(lsd, "dt")
-        if dt != self._symbol(eul, "dt"):
-            raise DslError("DEM: contact kernel and integrator use different dt")
-        ctx.dem_set_params(dt, self._symbol(lsd, "pi"), self._symbol(lsd, "kappa"), self._symbol(lsd, "ln_coeff"),
-                           self._symbol(lsd, "collision_time"), self._symbol(grav, "density_particle"), self._symbol(grav, "density_fluid"),
-                           self._symbol(grav, "gravity"), nk, self.feature_props[fs_name][1], self.feature_props[fd_name][1])
+        dt = self._symbol(eul, "dt")
+        if lsd["family"] == "generic_pair":
+            # a contact model other than examples/dem.py's: CUDA is generated for the body and the contact kernel is compiled
+            # around it at run time (kernelgen.translate_dem_model, csrc/jit.cu pb_jit_set_dem_model); feature properties and
+            # symbols become literals of the generated function, so the built-in model's parameters are not needed
+            name, src, nk = self._translate_dem_model(lsd)
+            ctx.jit_set_dem_model(src, name)
+            ctx.dem_set_params(dt, self._symbol(grav, "pi"), 0.0, 0.0, 1.0, self._symbol(grav, "density_particle"),
+                               self._symbol(grav, "density_fluid"), self._symbol(grav, "gravity"), nk, [0.0] * (nk * nk), [0.0] * (nk * nk))
+        else:
+            fs_name, fd_name = lsd["roles"]["friction_static"], lsd["roles"]["friction_dynamic"]
+            for nme in (fs_name, fd_name):
+                if nme not in self.feature_props:
+                    raise DslError(f"{lsd['name']}: '{nme}' must be a feature property")
+            nk = self.features[self.feature_props[fs_name][0]]
+            if dt != self._symbol(lsd, "dt"):
+                raise DslError("DEM: contact kernel and integrator use different dt")
+            ctx.dem_set_params(dt, self._symbol(lsd, "pi"), self._symbol(lsd, "kappa"), self._symbol(lsd, "ln_coeff"),
+                               self._symbol(lsd, "collision_time"), self._symbol(grav, "density_particle"), self._symbol(grav, "density_fluid"),
+                               self._symbol(grav, "gravity"), nk, self.feature_props[fs_name][1], self.feature_props[fd_name][1])
         # ---- set-up: particles are appended in the order of the setup statements (sim/simulation.py:238-247) ----
         parts = []
         for kind, args in self.setups:
@@ -630,6 +639,33 @@ class Simulation:
         all_ms = (time.perf_counter() - t0) * 1e3
         self._print_summary(ctx, all_ms, rank)
         return ctx
+
+    def _translate_dem_model(self, e):
+        """-> (function name, CUDA source, number of types) of a user-defined contact model (kernelgen.translate_dem_model).  The
+        kernel hands a model the DEM property set of examples/dem.py by these names; contact properties are told apart by type."""
+        from . import kernelgen
+        storage = {self.position_name: "pos"}
+        for name, slot in (("linear_velocity", "vel"), ("angular_velocity", "angvel"), ("mass", "mass"), ("radius", "radius"),
+                           ("force", "force"), ("torque", "torque")):
+            if name in self.props:
+                storage[name] = slot
+        for name in self.props:
+            storage.setdefault(name, name)               # anything else: named in the error message if the body touches it
+        contact = {}
+        for name, (ptype, _default) in self.contact_props.items():
+            kind = {Types.Int32: "c_stick", Types.Vector: "c_tsd", Types.Real: "c_ivm"}.get(ptype)
+            if kind is None or kind in contact.values():
+                raise DslError(f"contact property '{name}': the contact table holds one integer, one vector and one real per contact")
+            contact[name] = kind
+        nk, tables = 1, {}
+        for name, (feat, data) in self.feature_props.items():
+            tables[name] = data
+            nk = self.features[feat]
+        try:
+            name, src = kernelgen.translate_dem_model(e["func"], storage, contact, tables, e["symbols"])
+        except kernelgen.KernelGenError as err:
+            raise DslError(f"contact model '{e['name']}': {err}") from None
+        return name, src, nk
 
     _FLAGS_KEEP = 1 | 4 | 8      # infinite | fixed | global (runtime/pairs_common.hpp flags; PB_FLAG_* in include/pairs_b200.h)
 

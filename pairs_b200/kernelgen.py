@@ -15,6 +15,11 @@ for every further real / vector property the script declares (rows of the user-p
                    (`type`) as values, % & | ^ ~ on integers, and / or / not (both sides evaluated, as the reference prints them)
   particle kernels def k(i): the same expressions and statements, prop[i] = / += / -= expr
 
+  contact models   def k(i, j) of a DEM script (translate_dem_model): the same expressions plus penetration_depth / contact_point /
+                   contact_normal(i, j), contact properties cp[i, j] (read and assigned, mapping/funcs.py:230-263), apply() to
+                   force and torque; printed as a device function that the library's contact kernel calls per touching pair
+                   (csrc/dem_force_kernel.cuh)
+
 Like the reference's generated code the output has ONE statement per operation, in Python's evaluation order, vectors
 scalarised per component, `select` evaluating both arms, symbols substituted as literals; compiled with --fmad=false every
 operation is the IEEE operation of the reference's C++ (-ffp-contract=off), so a pair term is bit-identical and only the
@@ -65,6 +70,8 @@ class _Gen:
         self.hoisted = []                     # statements before the neighbour loop (loads of i)
         self.types_needed = False
         self.stored = set()                   # properties written so far (particle kernels)
+        self.contact = {}                     # contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick' (contact models)
+        self.depth = 0                        # nesting depth of if / else arms
 
     # -- helpers --
     def tmp(self, ctype, code, hoist=False):
@@ -86,6 +93,16 @@ class _Gen:
             return self.loaded[key]
         idx = "i" if who == "i" else "j"
         hoist = who == "i" and self.kind == "pair"
+        if self.kind == "dem":                                # contact model: the kernel hands the pair's data in as arguments
+            names = {"pos": "x", "vel": "v", "angvel": "w"}
+            if store in names:
+                val = self.vec([f"{names[store]}{idx}[{d}]" for d in range(3)])
+            elif store in ("mass", "radius"):
+                val = ("f", f"{'m' if store == 'mass' else 'r'}{idx}")
+            else:
+                raise KernelGenError(f"'{store}' is not available inside a contact model (position, linear and angular velocity, mass, radius)")
+            self.loaded[key] = val
+            return val
         if store == "pos":
             src = "pi" if who == "i" else "pj"
             val = self.vec([f"{src}.x", f"{src}.y", f"{src}.z"])
@@ -179,6 +196,8 @@ class _Gen:
     def name_value(self, name):
         if name in self.locals:
             return self.locals[name]
+        if self.kind == "dem" and name in self.storage and name not in self.symbols:
+            return self.load(self.storage[name], "i")         # a bare property inside apply() means prop[i] (ir/apply.py:99-100)
         if self.kind == "pair" and name == "rsq":            # legacy bare names of examples/lj_onetype.py
             return ("f", "rsq")
         if self.kind == "pair" and name == "delta":
@@ -201,13 +220,25 @@ class _Gen:
         if not isinstance(node.value, ast.Name):
             raise KernelGenError("unsupported subscript")
         prop = node.value.id
+        if isinstance(idx, ast.Tuple) and self.kind == "dem":
+            names = [e.id for e in idx.elts if isinstance(e, ast.Name)]
+            if names != ["i", "j"]:
+                raise KernelGenError(f"'{prop}[...]': contact and feature properties are indexed [i, j]")
+            if prop in self.contact:                          # contact property of this pair (mapping/funcs.py:230-263)
+                kind = self.contact[prop]
+                if kind == "c_tsd":
+                    return self.vec([self.tmp("double", f"tsd[{d}]") for d in range(3)])
+                return ("f", self.tmp("double", "*ivm")) if kind == "c_ivm" else ("i", self.tmp("int", "*sticking"))
+            if prop in self.tables:
+                return ("f", self.tmp("double", f"fp_{prop}[tij]"))
+            raise KernelGenError(f"'{prop}' is neither a contact property nor a feature property")
         if isinstance(idx, ast.Tuple):                        # feature property: fp[i, j]
             names = [e.id for e in idx.elts if isinstance(e, ast.Name)]
             if prop not in self.tables or names != ["i", "j"] or self.kind != "pair":
                 raise KernelGenError(f"'{prop}[...]': only feature_property[i, j] inside a pair kernel is supported")
             self.types_needed = True
             return ("f", self.tmp("double", f"fp_{prop}[ti + tj]"))
-        if not isinstance(idx, ast.Name) or idx.id not in ("i", "j") or (idx.id == "j" and self.kind != "pair"):
+        if not isinstance(idx, ast.Name) or idx.id not in ("i", "j") or (idx.id == "j" and self.kind not in ("pair", "dem")):
             raise KernelGenError(f"'{prop}[...]': index must be the particle argument")
         if prop not in self.storage:
             raise KernelGenError(f"'{prop}' is not a declared real / vector property")
@@ -217,6 +248,22 @@ class _Gen:
         if not isinstance(node.func, ast.Name):
             raise KernelGenError("unsupported call")
         f = node.func.id
+        if self.kind == "dem" and f in ("penetration_depth", "contact_point", "contact_normal", "delta", "squared_distance"):
+            # sim/interaction.py:234-264: the geometry of the touching pair, computed by the kernel (dem_math.h pb_dem_geom_*)
+            if f == "contact_point":
+                return self.vec(["cp[0]", "cp[1]", "cp[2]"])
+            if f == "contact_normal":
+                return self.vec(["n[0]", "n[1]", "n[2]"])
+            if f == "penetration_depth":
+                return ("f", self.tmp("double", "-(delta)"))   # the kernel passes delta = -penetration_depth; negation is exact
+            if "dem_delta" not in self.locals:
+                self.locals["dem_delta"] = self.vec([self.tmp("double", f"xi[{d}] - xj[{d}]") for d in range(3)])
+            dv = self.locals["dem_delta"]
+            if f == "delta":
+                return dv
+            p = [self.tmp("double", f"{x} * {x}") for x in dv[1]]
+            q = self.tmp("double", f"{p[0]} + {p[1]}")
+            return ("f", self.tmp("double", f"{q} + {p[2]}"))
         if f in ("delta", "squared_distance"):
             if self.kind != "pair":
                 raise KernelGenError(f"{f}() needs a pair kernel")
@@ -241,6 +288,8 @@ class _Gen:
                 raise KernelGenError("select(): both arms must have the same type")
             if self.is_vec(a):
                 return self.vec([self.tmp("double", f"({c[1]}) ? ({x}) : ({y})") for x, y in zip(a[1], b[1])])
+            if a[0] == "i" and b[0] == "i":
+                return ("i", self.tmp("int", f"({c[1]}) ? ({a[1]}) : ({b[1]})"))
             return ("f", self.tmp("double", f"({c[1]}) ? ({a[1]}) : ({b[1]})"))
         if f in ("is_point_mass", "is_sphere", "is_halfspace"):      # keywords.py:34-50: shape[p] == Shapes.<...>
             if len(node.args) != 1 or not isinstance(node.args[0], ast.Name) or node.args[0].id not in ("i", "j") or \
@@ -289,8 +338,10 @@ class _Gen:
         """Statements of an if / else arm: temporaries, loads and locals created inside stay inside (C scope = Python use)."""
         saved_locals, saved_loaded, before = dict(self.locals), dict(self.loaded), set(self.stored)
         self.stored = set()
+        self.depth += 1
         for st in body:
             self.stmt(st)
+        self.depth -= 1
         written = self.stored
         self.locals = saved_locals
         # a property the arm stored to has to be read again afterwards (the store may or may not have happened)
@@ -331,9 +382,23 @@ class _Gen:
             if self.is_vec(cond):
                 raise KernelGenError("skip_when(): the condition must be a scalar")
             # keywords.py:62-65 prints `continue`: the next partner in a pair kernel, the next particle otherwise
-            self.lines.append(f"if({cond[1]}) {{ {'continue' if self.kind == 'pair' else 'return'}; }}")
+            leave = {"pair": "continue", "dem": "return false"}.get(self.kind, "return")
+            self.lines.append(f"if({cond[1]}) {{ {leave}; }}")
             return
         if isinstance(node, ast.Expr) and isinstance(node.value, ast.Call) and getattr(node.value.func, "id", None) == "apply":
+            if self.kind == "dem":
+                tgt, val = node.value.args
+                out = {"force": "F", "torque": "T"}.get(self.storage.get(getattr(tgt, "id", None)))
+                if out is None:
+                    raise KernelGenError("apply(): a contact model applies to the force and the torque property")
+                v = self.expr(val)
+                if not self.is_vec(v):
+                    raise KernelGenError("apply(): vector property needs a vector expression")
+                first = out not in self.applied and self.depth == 0
+                self.applied[out] = True
+                for d, c in enumerate(v[1]):
+                    self.lines.append(f"{out}[{d}] = {c};" if first else f"{out}[{d}] = {out}[{d}] + {c};")
+                return
             if self.kind != "pair":
                 raise KernelGenError("apply() needs a pair kernel")
             tgt, val = node.value.args
@@ -354,6 +419,24 @@ class _Gen:
             acc = self.applied.setdefault(store, [f"acc_{_store_tag(store)}_{d}" for d in range(len(comps))])
             for a, c in zip(acc, comps):
                 self.lines.append(f"{a} = {a} + {c};")
+            return
+        if self.kind == "dem" and isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Subscript) \
+                and isinstance(node.targets[0].value, ast.Name) and node.targets[0].value.id in self.contact:
+            tgt = node.targets[0]
+            if not isinstance(tgt.slice, ast.Tuple) or [getattr(e, "id", None) for e in tgt.slice.elts] != ["i", "j"]:
+                raise KernelGenError("contact properties are assigned as prop[i, j] = ...")
+            kind, v = self.contact[tgt.value.id], self.expr(node.value)
+            if kind == "c_tsd":
+                if not self.is_vec(v):
+                    raise KernelGenError(f"'{tgt.value.id}' is a vector contact property")
+                for d, c in enumerate(v[1]):
+                    self.lines.append(f"tsd[{d}] = {c};")
+            elif self.is_vec(v):
+                raise KernelGenError(f"'{tgt.value.id}' is a scalar contact property")
+            elif kind == "c_ivm":
+                self.lines.append(f"*ivm = {v[1]};")
+            else:
+                self.lines.append(f"*sticking = (int) ({v[1]});")
             return
         if self.kind == "particle" and isinstance(node, (ast.Assign, ast.AugAssign)):
             tgt = node.targets[0] if isinstance(node, ast.Assign) else node.target
@@ -467,3 +550,36 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
         out += ["    " + ln for ln in g.lines]
     out.append("}")
     return kind, name, "\n".join(out) + "\n"
+
+
+def translate_dem_model(func, storage, contact, feature_tables, symbols):
+    """A DEM contact model (the body of a pair kernel over contact history, e.g. examples/dem.py:18-74) -> (function name, CUDA
+    source) of the device function the library's contact kernel calls for every touching pair (csrc/dem_force_kernel.cuh):
+
+        bool f(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, n, cp, delta, tij, tsd, ivm, sticking, F, T)
+
+    xi.. = position, linear velocity, angular velocity, mass, radius of i and j; n / cp / delta = contact normal, contact point and
+    -penetration_depth from the kernel's geometry pass; tij = type[i] * ntypes + type[j] (feature properties are literal tables);
+    tsd / ivm / sticking = this pair's contact properties (in / out); F / T = what the body apply()s to force / torque.
+    Returns false when a skip_when() left the pair.  `storage`: property name -> 'pos' | 'vel' | 'angvel' | 'mass' | 'radius' |
+    'force' | 'torque'; `contact`: contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick'."""
+    src = textwrap.dedent(inspect.getsource(func))
+    tree = ast.parse(src).body[0]
+    if not isinstance(tree, ast.FunctionDef) or [a.arg for a in tree.args.args] != ["i", "j"]:
+        raise KernelGenError(f"{func.__name__}: a contact model takes (i, j)")
+    name = f"user_model_{func.__name__}"
+    g = _Gen(name, "dem", storage, feature_tables, 0, symbols, func.__globals__)
+    g.contact = dict(contact)
+    for node in tree.body:
+        g.stmt(node)
+    out = []
+    for fp, table in feature_tables.items():
+        out.append(f"__device__ const double fp_{fp}[{len(table)}] = {{{', '.join(_lit(float(x)) for x in table)}}};")
+    out.append(f"__device__ __forceinline__ bool {name}(const double *xi, const double *vi, const double *wi, double mi, double ri, "
+               "const double *xj, const double *vj, const double *wj, double mj, double rj, const double *n, const double *cp, "
+               "double delta, int tij, double *tsd, double *ivm, int *sticking, double *F, double *T) {")
+    out.append("    F[0] = 0.0; F[1] = 0.0; F[2] = 0.0; T[0] = 0.0; T[1] = 0.0; T[2] = 0.0;")
+    out += ["    " + ln for ln in g.lines]
+    out.append("    return true;")
+    out.append("}")
+    return name, "\n".join(out) + "\n"

@@ -223,3 +223,23 @@ def test_further_properties_become_user_defined_storage():
         q.setup(charged)
     _, _, src = kernelgen.translate(init, q._device_storage(), {}, 1, {}, backend.jit_prelude(), skip_fixed=False)
     assert "PB_FLAG_FIXED) != 0" not in src.split('extern "C"')[1]
+
+
+def test_dem_script_with_a_generated_contact_model_plans_and_compiles():
+    """A DEM script whose pair kernel is not recognised (here: forced) gets its contact model generated: the procedure list stays
+    gravity / contact model / euler, the model is translated from the script's declared properties and the contact kernel built
+    around it compiles for sm_100a (no GPU needed)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    from pairs_b200 import backend
+    dsl.FORCE_GENERIC_CONTACT_MODEL = True
+    try:
+        psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10)
+    finally:
+        dsl.FORCE_GENERIC_CONTACT_MODEL = False
+    assert [e["family"] for e in psim.functions] == ["gravity", "generic_pair", "euler"]
+    name, src, nk = psim._translate_dem_model(psim.functions[1])
+    assert name == "user_model_linear_spring_dashpot" and nk == 1 and "fp_friction_dynamic[1] = {0.5}" in src
+    assert backend.jit_check_dem_model(src, name) > 10000
+    # the stock script is still recognised
+    assert [e["family"] for e in dem_script.build("gpu", (0.1, 0.015, 0.04), 10).functions] == ["gravity", "linear_spring_dashpot", "euler"]

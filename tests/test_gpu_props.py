@@ -81,6 +81,34 @@ def test_vocabulary_script_matches_the_reference_generator_golden(capsys):
     assert np.abs(by_id(tag, ctx1.real("linear_velocity")) - z["linear_velocity_1"]).max() <= 1e-12
 
 
+def test_generated_dem_contact_model_reproduces_the_built_in_run_bit_for_bit(capsys):
+    """examples/dem.py with its contact model GENERATED (kernelgen.translate_dem_model -> NVRTC build of the contact kernel around
+    it) instead of recognised: the model's arithmetic is the hand-written one's operation for operation
+    (tests/test_kernelgen.py), so 300 iterations of the 420-sphere case -- falling, first impacts, sticking contacts -- end in
+    identical bits: positions, velocities, angular velocities and the whole contact table."""
+    import dem_script
+    from pairs_b200 import dsl
+    from tests import dem_common as dc
+    ref_ctx = dem_script.build("gpu", dc.DOMAIN, 300).generate()
+    dsl.FORCE_GENERIC_CONTACT_MODEL = True
+    try:
+        psim = dem_script.build("gpu", dc.DOMAIN, 300)
+    finally:
+        dsl.FORCE_GENERIC_CONTACT_MODEL = False
+    assert [e["family"] for e in psim.functions] == ["gravity", "generic_pair", "euler"]
+    ctx = psim.generate()
+    capsys.readouterr()
+    n = ctx.counts()[0]
+    assert n == ref_ctx.counts()[0] == 422
+    for name in ("position", "linear_velocity"):
+        assert np.array_equal(ctx.real(name), ref_ctx.real(name)), name
+    assert np.array_equal(ctx.dem_download("angular_velocity", n), ref_ctx.dem_download("angular_velocity", n))
+    a, b = ctx.dem_download_contacts(n), ref_ctx.dem_download_contacts(n)
+    assert a["num_contacts"].sum() > 100
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_property_store_through_the_c_abi(capsys):
     """add / upload / download, defaults, capacity growth, ghosts carrying their source's values, volatile reset, the cell-order
     sort -- without any generated kernel."""

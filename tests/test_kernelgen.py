@@ -444,3 +444,117 @@ def test_rest_of_the_vocabulary_equals_the_reference_generators_modules_on_the_h
     kern["user_final_integrate"](n, nslots, tot, 0.0, *args)
     changed = np.any(vel_r[:n] != v_before[:n], axis=1)
     assert 0.1 * n < changed.sum() < 0.5 * n and np.array_equal(vel[:, :n].T, vel_r[:n])
+
+
+# ---- DEM contact models -----------------------------------------------------------------------------------------------------------
+DEM_STORAGE = {"position": "pos", "linear_velocity": "vel", "angular_velocity": "angvel", "mass": "mass", "radius": "radius",
+               "force": "force", "torque": "torque"}
+DEM_CONTACT = {"is_sticking": "c_stick", "tangential_spring_displacement": "c_tsd", "impact_velocity_magnitude": "c_ivm"}
+
+
+def _model_vs_builtin(tmp_path, name, code, params):
+    """Compiles a generated contact model for the host next to dem_math.h; returns run(n, seed) -> number of random pairs for which
+    the model's outputs (F, T, tsd, ivm, sticking) differ in any bit from pb_dem_pair_force's, and the largest |F| seen."""
+    import ctypes
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    cpp = tmp_path / f"{name}.cpp"
+    cpp.write_text('#include "jit_host_emulation.h"\n#include "dem_math.h"\n#include <random>\n' + code + f'''
+extern "C" int run(int n, unsigned seed, double *fmax) {{
+    PbDemParams P;
+    P.dt = {params["dt"]!r}; P.pi = {params["pi"]!r}; P.kappa = {params["kappa"]!r}; P.ln_coeff = {params["ln"]!r}; P.ct = {params["ct"]!r};
+    P.c_sum = P.pi * P.pi + P.ln_coeff * P.ln_coeff; P.ct2 = P.ct * P.ct; P.sqrt_kappa = sqrt(P.kappa);
+    std::mt19937_64 g(seed);
+    std::uniform_real_distribution<double> U(-1.0, 1.0);
+    int bad = 0;
+    *fmax = 0.0;
+    for(int k = 0; k < n; k++) {{
+        double xi[3], vi[3], wi[3], xj[3], vj[3], wj[3], nn[3], cp[3];
+        for(int d = 0; d < 3; d++) {{ xi[d] = U(g); vi[d] = U(g); wi[d] = 10.0 * U(g); vj[d] = U(g); wj[d] = 10.0 * U(g); nn[d] = U(g); }}
+        const double len = sqrt((nn[0] * nn[0] + nn[1] * nn[1]) + nn[2] * nn[2]);
+        for(int d = 0; d < 3; d++) {{ nn[d] /= len; }}
+        const double ri = 0.002 + 0.001 * (U(g) + 1.0), rj = 0.002 + 0.001 * (U(g) + 1.0), delta = 1e-4 * (U(g) + 1.0);
+        for(int d = 0; d < 3; d++) {{ xj[d] = xi[d] - nn[d] * (ri + rj - delta); cp[d] = xj[d] + nn[d] * (rj - 0.5 * delta); }}
+        const double mi = 1e-4 * (U(g) + 1.5), mj = (k % 7 == 0) ? INFINITY : 1e-4 * (U(g) + 1.5);     // half-spaces have infinite mass
+        double tsd_a[3], tsd_b[3];
+        const int mode = k % 4;        // fresh contact / live history / history parallel to the normal / sticking
+        for(int d = 0; d < 3; d++) {{ tsd_a[d] = (mode == 0) ? 0.0 : ((mode == 2) ? 1e-5 * nn[d] : 1e-5 * U(g)); tsd_b[d] = tsd_a[d]; }}
+        double ivm_a = (mode == 0) ? 0.0 : 0.3 * (U(g) + 1.0), ivm_b = ivm_a;
+        int st_a = (mode == 3) ? 1 : 0, st_b = st_a;
+        const double fs = (k % 3 == 0) ? 0.0 : 0.6, fd = 0.5;
+        static const double fs_tab[2] = {{0.0, 0.6}};
+        double Fa[3], Ta[3], Fb[3], Tb[3];
+        pb_dem_pair_force(P, xi, vi, wi, 1.0 / mi, xj, vj, wj, mj, nn, cp, delta, fs, fd, tsd_a, &ivm_a, &st_a, Fa, Ta);
+        const bool kept = {name}(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, nn, cp, delta, (k % 3 == 0) ? 0 : 1, tsd_b, &ivm_b, &st_b, Fb, Tb);
+        (void) fs_tab;
+        bool same = kept && st_a == st_b && memcmp(&ivm_a, &ivm_b, 8) == 0;
+        for(int d = 0; d < 3; d++) {{
+            same = same && Fa[d] == Fb[d] && Ta[d] == Tb[d] && memcmp(&tsd_a[d], &tsd_b[d], 8) == 0;
+            if(fabs(Fa[d]) > *fmax) {{ *fmax = fabs(Fa[d]); }}
+        }}
+        bad += same ? 0 : 1;
+    }}
+    return bad;
+}}
+''')
+    so = tmp_path / f"{name}.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-I" + os.path.join(here, "host"),
+                    "-I" + os.path.join(os.path.dirname(here), "pairs_b200", "csrc"), str(cpp), "-o", str(so)], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_uint, ctypes.POINTER(ctypes.c_double)]
+
+    def run(n, seed):
+        fmax = ctypes.c_double(0.0)
+        return lib.run(n, seed, ctypes.byref(fmax)), fmax.value
+    return run
+
+
+def test_generated_dem_contact_model_equals_the_hand_written_one_bit_for_bit(tmp_path):
+    """examples/dem.py's linear_spring_dashpot (tests/scripts/dem_script.py holds it verbatim) through kernelgen.translate_dem_model,
+    compiled for the host, against pb_dem_pair_force of csrc/dem_math.h -- the function the CUDA contact kernel calls and that
+    tests/test_dem_host.py pins to the reference's generated module: forces, torques and the three contact properties are the same
+    bits for 20000 random touching pairs (fresh and live contacts, history parallel to the normal, sticking, infinite partner mass,
+    zero static friction).  The whole contact kernel built around the generated model compiles with NVRTC for sm_100a."""
+    import math
+    import dem_script
+    params = {"dt": 5e-5, "pi": math.pi, "kappa": 2.0 * (1.0 - 0.22) / (2.0 - 0.22), "ln": -0.1053605156578263, "ct": 4.0 * 5e-5}
+    symbols = {"dt": params["dt"], "pi": params["pi"], "kappa": params["kappa"], "lnDryResCoeff": params["ln"], "collisionTime_SI": params["ct"]}
+    tables = {"friction_static": [0.0, 0.6], "friction_dynamic": [0.5, 0.5]}
+    name, code = kernelgen.translate_dem_model(dem_script.linear_spring_dashpot, DEM_STORAGE, DEM_CONTACT, tables, symbols)
+    assert name == "user_model_linear_spring_dashpot" and "return false;" in code and "fp_friction_static[tij]" in code
+    run = _model_vs_builtin(tmp_path, name, code, params)
+    bad, fmax = run(20000, 7)
+    assert bad == 0 and fmax > 0.1
+    assert backend.jit_check_dem_model(code, name) > 10000          # prelude + dem_math.h + model + dem_force_kernel.cuh, both variants
+
+
+def test_a_different_contact_model_translates_and_compiles():
+    """A body that is NOT examples/dem.py's: Hertz-like normal force with viscous damping, no tangential spring, the impact speed
+    remembered in a contact property, skip for slow approaches; errors name what a contact model cannot touch."""
+    def hertz(i, j):
+        d = -penetration_depth(i, j)
+        skip_when(d < 1e-9)
+        reff = 1.0 / (1.0 / radius[i] + 1.0 / radius[j])
+        rel = linear_velocity[i] - linear_velocity[j]
+        vn = dot(rel, contact_normal(i, j))
+        first = select(impact_velocity_magnitude[i, j] > 0.0, impact_velocity_magnitude[i, j], abs(vn))
+        impact_velocity_magnitude[i, j] = first
+        is_sticking[i, j] = select(abs(vn) < 1e-6, 1, 0)
+        fn = kn * sqrt(reff) * d * sqrt(d) - gamma_n * vn
+        if fn > 0.0:
+            apply(force, fn * contact_normal(i, j))
+            apply(torque, cross(contact_point(i, j) - position, fn * contact_normal(i, j)) * friction_dynamic[i, j])
+
+    name, code = kernelgen.translate_dem_model(hertz, DEM_STORAGE, DEM_CONTACT, {"friction_dynamic": [0.5]}, {"kn": 1e6, "gamma_n": 0.2})
+    assert "F[0] = F[0] +" in code and "*sticking = (int) (" in code and "*ivm =" in code and "ri" in code
+    assert backend.jit_check_dem_model(code, name) > 10000
+
+    def touches_user_state(i, j):
+        apply(force, contact_normal(i, j) * inv_inertia[i])
+
+    def applies_elsewhere(i, j):
+        apply(linear_velocity, contact_normal(i, j))
+
+    for fn, msg in ((touches_user_state, "inv_inertia"), (applies_elsewhere, "force and the torque")):
+        with pytest.raises(kernelgen.KernelGenError, match=msg):
+            kernelgen.translate_dem_model(fn, dict(DEM_STORAGE, inv_inertia="inv_inertia"), DEM_CONTACT, {}, {})
