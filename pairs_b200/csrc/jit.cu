@@ -30,6 +30,9 @@ struct PbJitArgs {
     double *xdata;          // user-defined properties, rows of [cap]: component d of a property at (row0 + d) * cap + i
     const int *uid;         // [cap]
     const int *shape;       // [cap]
+    double *radius;         // DEM scripts only (null otherwise): [cap]
+    double *angvel;         //                                    [3][cap]
+    double *torque;         //                                    [3][cap]
 };
 
 static const char *PB_JIT_PRELUDE = R"PRELUDE(
@@ -47,6 +50,9 @@ struct PbJitArgs {
     double *xdata;
     const int *uid;
     const int *shape;
+    double *radius;
+    double *angvel;
+    double *torque;
 };
 #define PB_FLAG_FIXED 4
 #define PB_SHAPE_SPHERE 0
@@ -214,6 +220,7 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     a.pos = ctx->pos; a.pos_w = ctx->pos; a.vel = ctx->vel; a.force = ctx->force; a.mass = ctx->mass; a.flags = ctx->flags;
     a.numneigh = ctx->numneigh; a.neigh = ctx->neigh; a.xdata = ctx->xdata;
     a.uid = ctx->uid; a.shape = ctx->shape;
+    a.radius = ctx->radius; a.angvel = ctx->angvel; a.torque = ctx->torque;
     void *params[] = {&a};
     PB_CHECK(cudaLaunchKernel((const void *) k.kernel, dim3(pb_blocks(ctx->nlocal, 128)), dim3(128), params, 0, ctx->stream));
     ctx->launches++;

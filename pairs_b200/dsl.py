@@ -209,6 +209,7 @@ def _unify(t, u, binding):
 
 
 FORCE_GENERIC = False        # tests: send every kernel through the generic (NVRTC) path, also the recognised ones
+FORCE_GENERIC_NAMES = set()  # tests: kernels with these function names are generated even if they would be recognised
 FORCE_GENERIC_CONTACT_MODEL = False      # tests: DEM scripts get their contact model generated even if it is examples/dem.py's
 
 
@@ -454,7 +455,7 @@ class Simulation:
 
     def compute(self, func, cutoff_radius=None, symbols={}, pre_step=False, skip_first=False):
         try:
-            if FORCE_GENERIC or (FORCE_GENERIC_CONTACT_MODEL and self.use_contact_history and len(inspect.signature(func).parameters) == 2):
+            if FORCE_GENERIC or func.__name__ in FORCE_GENERIC_NAMES or (FORCE_GENERIC_CONTACT_MODEL and self.use_contact_history and len(inspect.signature(func).parameters) == 2):
                 raise DslError("generic path forced")
             family, roles = recognise(func)
         except DslError:
@@ -564,32 +565,38 @@ class Simulation:
     # -- DEM (examples/dem.py): spheres + half-spaces, contact history, cell-list traversal, reneighbouring every step --
     def _generate_dem(self, ctx, rank, world):
         fams = [e["family"] for e in self.functions]
-        if self.pre_step or fams not in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"]) \
+        pair_at = [k for k, f in enumerate(fams) if f in ("linear_spring_dashpot", "generic_pair")]
+        if self.pre_step or len(pair_at) != 1 or any(f not in ("gravity", "euler", "generic_particle", "linear_spring_dashpot", "generic_pair")
+                                                     for f in fams) \
+                or fams.count("gravity") > 1 or fams.count("euler") > 1 \
                 or not self.use_contact_history or self.neighbor_cutoff is not None or self.reneighbor_frequency != 1:
-            raise DslError("DEM: the procedure list of examples/dem.py (gravity, a contact model, euler over cell lists, contact "
-                           "history, reneighbouring every step) is implemented; the contact model may be any kernel body")
-        grav, lsd, eul = self.functions
+            raise DslError("DEM: a procedure list like examples/dem.py's is implemented -- per-particle kernels (gravity, euler or any "
+                           "other body), ONE contact model (any body) over cell lists with contact history, reneighbouring every step")
+        lsd = self.functions[pair_at[0]]
+        grav = next((e for e in self.functions if e["family"] == "gravity"), None)
+        eul = next((e for e in self.functions if e["family"] == "euler"), None)
+        standard = fams in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"])
         ctx.dem_enable(self.neighbor_capacity)
-        dt = self._symbol(eul, "dt")
+        dt = self._symbol(eul, "dt") if eul is not None else 0.0
+        g_pi = self._symbol(grav, "pi") if grav is not None else math.pi
+        g_par = [self._symbol(grav, r) for r in ("density_particle", "density_fluid", "gravity")] if grav is not None else [0.0, 0.0, 0.0]
         if lsd["family"] == "generic_pair":
             # a contact model other than examples/dem.py's: CUDA is generated for the body and the contact kernel is compiled
             # around it at run time (kernelgen.translate_dem_model, csrc/jit.cu pb_jit_set_dem_model); feature properties and
             # symbols become literals of the generated function, so the built-in model's parameters are not needed
             name, src, nk = self._translate_dem_model(lsd)
             ctx.jit_set_dem_model(src, name)
-            ctx.dem_set_params(dt, self._symbol(grav, "pi"), 0.0, 0.0, 1.0, self._symbol(grav, "density_particle"),
-                               self._symbol(grav, "density_fluid"), self._symbol(grav, "gravity"), nk, [0.0] * (nk * nk), [0.0] * (nk * nk))
+            ctx.dem_set_params(dt, g_pi, 0.0, 0.0, 1.0, *g_par, nk, [0.0] * (nk * nk), [0.0] * (nk * nk))
         else:
             fs_name, fd_name = lsd["roles"]["friction_static"], lsd["roles"]["friction_dynamic"]
             for nme in (fs_name, fd_name):
                 if nme not in self.feature_props:
                     raise DslError(f"{lsd['name']}: '{nme}' must be a feature property")
             nk = self.features[self.feature_props[fs_name][0]]
-            if dt != self._symbol(lsd, "dt"):
+            if eul is not None and dt != self._symbol(lsd, "dt"):
                 raise DslError("DEM: contact kernel and integrator use different dt")
-            ctx.dem_set_params(dt, self._symbol(lsd, "pi"), self._symbol(lsd, "kappa"), self._symbol(lsd, "ln_coeff"),
-                               self._symbol(lsd, "collision_time"), self._symbol(grav, "density_particle"), self._symbol(grav, "density_fluid"),
-                               self._symbol(grav, "gravity"), nk, self.feature_props[fs_name][1], self.feature_props[fd_name][1])
+            ctx.dem_set_params(self._symbol(lsd, "dt"), self._symbol(lsd, "pi"), self._symbol(lsd, "kappa"), self._symbol(lsd, "ln_coeff"),
+                               self._symbol(lsd, "collision_time"), *g_par, nk, self.feature_props[fs_name][1], self.feature_props[fd_name][1])
         # ---- set-up: particles are appended in the order of the setup statements (sim/simulation.py:238-247) ----
         parts = []
         for kind, args in self.setups:
@@ -628,17 +635,60 @@ class Simulation:
         ctx.sync()
         t0 = time.perf_counter()
         nsteps = self.ntimesteps + 1
-        cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
-        begin = 0
-        for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
-            ctx.dem_run(self._cell_spacing, begin, end)
-            if self._vtk_due(end - 1):
-                self._vtk_write(ctx, end - 1, rank, world)
-            begin = end
+        if standard:
+            cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
+            begin = 0
+            for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
+                ctx.dem_run(self._cell_spacing, begin, end)
+                if self._vtk_due(end - 1):
+                    self._vtk_write(ctx, end - 1, rank, world)
+                begin = end
+        else:
+            self._dem_staged_loop(ctx, nsteps, rank, world)
         ctx.sync()
         all_ms = (time.perf_counter() - t0) * 1e3
         self._print_summary(ctx, all_ms, rank)
         return ctx
+
+    def _dem_staged_loop(self, ctx, nsteps, rank, world):
+        """A DEM procedure list with further per-particle kernels (or without gravity / euler): the modules of the generated
+        loop one by one (sim/simulation.py:387-417 with contact history), user bodies through the generic path."""
+        from . import backend, kernelgen
+        storage = {self.position_name: "pos"}
+        for name, slot in (("linear_velocity", "vel"), ("angular_velocity", "angvel"), ("mass", "mass"), ("radius", "radius"),
+                           ("force", "force"), ("torque", "torque"), ("uid", "uid"), ("shape", "shape"), ("flags", "flags")):
+            if name in self.props:
+                storage[name] = slot
+        for name in self.features:
+            storage[name] = "type"
+        calls = []
+        for e in self.functions:
+            if e["family"] in ("gravity", "euler", "linear_spring_dashpot", "generic_pair"):
+                stage = "linear_spring_dashpot" if e["family"] in ("linear_spring_dashpot", "generic_pair") else e["family"]
+                calls.append(lambda stage=stage: ctx.dem_stage(stage))
+                continue
+            try:
+                kind, kname, src = kernelgen.translate(e["func"], storage, {}, 1, e["symbols"], backend.jit_prelude())
+            except kernelgen.KernelGenError as err:
+                raise DslError(f"kernel '{e['name']}': {err}") from None
+            handle = ctx.jit_compile(src, kname)
+            calls.append(lambda handle=handle: ctx.jit_launch(handle, 1))
+        ctx.setup_cells(self._cell_spacing)
+        for ts in range(nsteps):
+            ctx.exchange()
+            ctx.borders()
+            ctx.build_cell_lists()
+            ctx.dem_stage("reset_contact_usage")
+            ctx.reset_volatile()
+            for e, call in zip(self.functions, calls):
+                if ts > 0 or not e["skip_first"]:
+                    call()
+            ctx.dem_stage("clear_unused_contacts")
+            if self._vtk_due(ts):
+                self._vtk_write(ctx, ts, rank, world)
+        need = ctx.lib.pb_dem_contact_overflow(ctx.h)
+        if need > 0:
+            raise DslError(f"contact capacity exceeded: a particle needs {need} contact slots (neighbor_capacity of pairs.simulation())")
 
     def _translate_dem_model(self, e):
         """-> (function name, CUDA source, number of types) of a user-defined contact model (kernelgen.translate_dem_model).  The
@@ -857,7 +907,9 @@ class Simulation:
         cats = {"communication": ("exchange", "borders", "synchronize"), "neighbors": ("build_cell_lists", "build_neighbor_lists")}
         lines = [("all", all_ms)]
         for e in self.pre_step + self.functions:
-            lines.append((e["name"], ctx.timer(e["family"])[0]))
+            timer = {"generic_pair": "linear_spring_dashpot" if self.use_contact_history else f"user_{e['name']}",
+                     "generic_particle": f"user_{e['name']}"}.get(e["family"], e["family"])
+            lines.append((e["name"], ctx.timer(timer)[0]))
         if self.use_contact_history:
             cats["contact_history"] = ("reset_contact_history_usage_status", "clear_unused_contact_history")
         for cat, names in cats.items():

@@ -106,10 +106,10 @@ class _Gen:
         if store == "pos":
             src = "pi" if who == "i" else "pj"
             val = self.vec([f"{src}.x", f"{src}.y", f"{src}.z"])
-        elif store in ("vel", "force"):
+        elif store in ("vel", "force", "angvel", "torque"):       # angvel / torque: DEM scripts
             val = self.vec([self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(3)])
-        elif store == "mass":
-            val = ("f", self.tmp("double", f"a.mass[{idx}]", hoist))
+        elif store in ("mass", "radius"):
+            val = ("f", self.tmp("double", f"a.{store}[{idx}]", hoist))
         elif store in ("uid", "shape", "flags"):
             val = ("i", self.tmp("int", f"a.{store}[{idx}]", hoist))
         elif store == "type":                                 # the feature index rides in the low bits of position.w
@@ -440,6 +440,23 @@ class _Gen:
             return
         if self.kind == "particle" and isinstance(node, (ast.Assign, ast.AugAssign)):
             tgt = node.targets[0] if isinstance(node, ast.Assign) else node.target
+            if isinstance(tgt, ast.Subscript) and isinstance(tgt.value, ast.Subscript) and isinstance(tgt.slice, ast.Constant) \
+                    and isinstance(tgt.value.value, ast.Name) and getattr(tgt.value.slice, "id", None) == "i":
+                # prop[i][k] = expr: one component of a vector property (examples/dem.py:90 force[i][2] = ...)
+                store, k = self.storage.get(tgt.value.value.id), tgt.slice.value
+                cur = self.load(store, "i") if store is not None else None
+                if cur is None or not self.is_vec(cur) or not isinstance(k, int) or not 0 <= k < 3:
+                    raise KernelGenError(f"'{ast.unparse(tgt)}': component assignment needs a declared vector property and an index 0..2")
+                v = self.expr(node.value)
+                if isinstance(node, ast.AugAssign):
+                    ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
+                    v = self.binop(ops[type(node.op)], ("f", cur[1][k]), v)
+                if self.is_vec(v):
+                    raise KernelGenError("a component takes a scalar")
+                comps = list(cur[1])
+                comps[k] = v[1]
+                self.store(store, self.vec(comps), only=k)
+                return
             if isinstance(tgt, ast.Subscript) and isinstance(tgt.value, ast.Name) and getattr(tgt.slice, "id", None) == "i":
                 store = self.storage.get(tgt.value.id)
                 if store is None:
@@ -452,14 +469,15 @@ class _Gen:
                 return
         raise KernelGenError(f"unsupported statement: {ast.unparse(node)}")
 
-    def store(self, store, v):
+    def store(self, store, v, only=None):
+        """prop[i] = v; `only` = k writes component k alone (the value's other components are what was loaded)."""
         if store in ("uid", "shape", "flags", "type"):
             raise KernelGenError("integer properties (uid, shape, flags, the feature) are read-only in kernels")
         self.stored.add(store)
-        if store == "mass":
+        if store in ("mass", "radius"):
             if self.is_vec(v):
-                raise KernelGenError("mass is a scalar")
-            self.lines.append(f"a_mass_w[i] = {v[1]};")
+                raise KernelGenError(f"{store} is a scalar")
+            self.lines.append(f"a_mass_w[i] = {v[1]};" if store == "mass" else f"a.radius[i] = {v[1]};")
             self.loaded[(store, "i")] = v
             return
         if isinstance(store, tuple):
@@ -472,7 +490,8 @@ class _Gen:
                 self.loaded[(store, "i")] = iv
                 return
             for d, c in enumerate(comps):
-                self.lines.append(f"{_xref(store, d, 'i')} = {c};")
+                if only is None or only == d:
+                    self.lines.append(f"{_xref(store, d, 'i')} = {c};")
             self.loaded[(store, "i")] = v
             return
         if not self.is_vec(v):
@@ -482,7 +501,8 @@ class _Gen:
             self.loaded[(store, "i")] = self.vec(["pi.x", "pi.y", "pi.z"])
         else:
             for d in range(3):
-                self.lines.append(f"a.{store}[{d} * (size_t) a.cap + i] = {v[1][d]};")
+                if only is None or only == d:
+                    self.lines.append(f"a.{store}[{d} * (size_t) a.cap + i] = {v[1][d]};")
             self.loaded[(store, "i")] = v
 
 

@@ -109,6 +109,30 @@ def test_generated_dem_contact_model_reproduces_the_built_in_run_bit_for_bit(cap
         assert np.array_equal(a[k], b[k]), k
 
 
+def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in_run(capsys):
+    """A DEM procedure list that is not exactly gravity / model / euler runs module by module with the user bodies generated: here
+    gravity itself is sent through the generic path, 150 iterations (before the native loop's first spatial re-sort) must end in
+    the bits of the native run."""
+    import dem_script
+    from pairs_b200 import dsl
+    from tests import dem_common as dc
+    ref_ctx = dem_script.build("gpu", dc.DOMAIN, 150).generate()
+    dsl.FORCE_GENERIC_NAMES = {"gravity"}
+    try:
+        psim = dem_script.build("gpu", dc.DOMAIN, 150)
+    finally:
+        dsl.FORCE_GENERIC_NAMES = set()
+    assert [e["family"] for e in psim.functions] == ["generic_particle", "linear_spring_dashpot", "euler"]
+    ctx = psim.generate()
+    capsys.readouterr()
+    n = ctx.counts()[0]
+    for name in ("position", "linear_velocity", "force"):
+        assert np.array_equal(ctx.real(name), ref_ctx.real(name)), name
+    a, b = ctx.dem_download_contacts(n), ref_ctx.dem_download_contacts(n)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_property_store_through_the_c_abi(capsys):
     """add / upload / download, defaults, capacity growth, ghosts carrying their source's values, volatile reset, the cell-order
     sort -- without any generated kernel."""

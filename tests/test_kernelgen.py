@@ -152,17 +152,17 @@ def test_if_statements_and_local_updates():
 def _host_kernel(tmp_path, name, src):
     """Compiles a generated kernel for the HOST (tests/host/jit_host_emulation.h stands in for the CUDA bits) together with a
     driver that runs it for every particle; returns run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags, numneigh, neigh,
-    xdata=None, uid=None, shape=None) taking array addresses."""
+    xdata=None, uid=None, shape=None, radius=None, angvel=None, torque=None) taking array addresses."""
     import ctypes
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     cpp = tmp_path / f"{name}.cpp"
     cpp.write_text('#include "jit_host_emulation.h"\n' + src + f'''
 extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, double *vel, double *force, double *mass, int *flags,
-                    int *numneigh, int *neigh, double *xdata, int *uid, int *shape) {{
+                    int *numneigh, int *neigh, double *xdata, int *uid, int *shape, double *radius, double *angvel, double *torque) {{
     PbJitArgs a;
     a.nlocal = n; a.nslots = nslots; a.cap = cap; a.pad = 0; a.cutsq = cutsq; a.pos = pos; a.pos_w = pos; a.vel = vel; a.force = force;
-    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata; a.uid = uid; a.shape = shape;
+    a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata; a.uid = uid; a.shape = shape; a.radius = radius; a.angvel = angvel; a.torque = torque;
     blockDim.x = 128;
     for(int i = 0; i < n; i++) {{ blockIdx.x = i / 128; threadIdx.x = i % 128; {name}(a); }}
 }}
@@ -172,10 +172,11 @@ extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, doub
                    check=True)
     lib = ctypes.CDLL(str(so))
     P = ctypes.c_void_p
-    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P, P, P, P]
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P, P, P, P, P, P, P]
 
-    def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None, uid=None, shape=None):
-        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata, uid, shape)
+    def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None, uid=None, shape=None, radius=None, angvel=None,
+            torque=None):
+        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata, uid, shape, radius, angvel, torque)
     return run
 
 
@@ -558,3 +559,31 @@ def test_a_different_contact_model_translates_and_compiles():
     for fn, msg in ((touches_user_state, "inv_inertia"), (applies_elsewhere, "force and the torque")):
         with pytest.raises(kernelgen.KernelGenError, match=msg):
             kernelgen.translate_dem_model(fn, dict(DEM_STORAGE, inv_inertia="inv_inertia"), DEM_CONTACT, {}, {})
+
+
+def test_generated_dem_per_particle_kernel_on_the_host(tmp_path):
+    """examples/dem.py's gravity through the generic path (DEM scripts may carry any per-particle kernel next to the contact model):
+    component assignment force[i][2] = ..., radius as a device array; the same bits as numpy doing the same IEEE operations."""
+    import math
+    import numpy as np
+    import dem_script
+    storage = dict(DEM_STORAGE, uid="uid", shape="shape", flags="flags")
+    sym = {"densityParticle_SI": 2550, "densityFluid_SI": 1000, "gravity_SI": 9.81, "pi": math.pi}
+    kind, name, code = kernelgen.translate(dem_script.gravity, storage, {}, 1, sym, backend.jit_prelude())
+    assert kind == "particle" and "a.force[2 * (size_t) a.cap + i] =" in code and "a.radius[i]" in code
+    assert "a.force[i] =" not in code and "a.force[1 * (size_t) a.cap + i] =" not in code          # only the z component is stored
+    assert backend.jit_check(code) > 1000
+    run = _host_kernel(tmp_path, name, code)
+    rng = np.random.default_rng(2)
+    n = 500
+    pos4, vel, mass = np.zeros((n, 4)), np.zeros((3, n)), np.ones(n)
+    force = rng.standard_normal((3, n))
+    radius = 0.001 + 0.001 * rng.random(n)
+    flags = np.zeros(n, np.int32)
+    flags[::9] = 4
+    f0 = force.copy()
+    run(n, 0, n, 0.0, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), None, None, None, None, None, _ptr(radius), None, None)
+    volume = (4.0 / 3.0) * math.pi * radius * radius * radius
+    expect = f0[2] - (2550 - 1000) * volume * 9.81
+    expect[::9] = f0[2, ::9]                       # FIXED particles are skipped
+    assert np.array_equal(force[2], expect) and np.array_equal(force[:2], f0[:2])
