@@ -979,15 +979,24 @@ def vtk_write(path, position, mass, flags):
     return True
 
 
+_ID_STORE, _ID_CALLS = None, 0
+
+
 def _broadcast_nccl_id(backend, rank, world):
-    """ncclUniqueId from rank 0 to all ranks through the launcher's TCP store (torchrun env: MASTER_ADDR / MASTER_PORT)."""
+    """ncclUniqueId from rank 0 to all ranks through a TCP store next to the launcher's (torchrun env: MASTER_ADDR / MASTER_PORT + 17).
+    The store lives as long as the process -- a reader may arrive after rank 0 has moved on -- and every generate() of the process
+    uses a key of its own (all ranks call generate() the same number of times)."""
+    global _ID_STORE, _ID_CALLS
     from torch.distributed import TCPStore
     from datetime import timedelta
-    store = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", 29500)) + 17, world,
-                     is_master=(rank == 0), timeout=timedelta(seconds=120))
+    if _ID_STORE is None:
+        _ID_STORE = TCPStore(os.environ.get("MASTER_ADDR", "127.0.0.1"), int(os.environ.get("MASTER_PORT", 29500)) + 17, world,
+                             is_master=(rank == 0), timeout=timedelta(seconds=120))
+    key = f"pairs_b200_nccl_id_{_ID_CALLS}"
+    _ID_CALLS += 1
     if rank == 0:
-        store.set("pairs_b200_nccl_id", backend.nccl_unique_id())
-    return bytes(store.get("pairs_b200_nccl_id"))
+        _ID_STORE.set(key, backend.nccl_unique_id())
+    return bytes(_ID_STORE.get(key))
 
 
 # ---- module-level factory functions (src/pairs/__init__.py:9-67) -------------------------------------------------------

@@ -66,3 +66,45 @@ def test_world2_rendezvous_id_broadcast_and_decomposition():
     assert list(d0["neighbor_ranks"]) == [0, 0, 0, 0, 1, 1] and list(d1["neighbor_ranks"]) == [1, 1, 1, 1, 0, 0]
     assert list(d0["pbc"]) == [1, -1, 1, -1, 1, 0] and list(d1["pbc"]) == [1, -1, 1, -1, 0, -1]
     assert d0["subdom"][5] == d1["subdom"][4] == 20 * a
+
+
+def _id_worker(rank, world, port_no, out):
+    sys.path.insert(0, ROOT)
+    import time
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    from pairs_b200 import dsl
+
+    class FakeBackend:                       # pb_nccl_unique_id needs no GPU, but a fixed pattern shows WHICH call's id arrived
+        calls = 0
+
+        @classmethod
+        def nccl_unique_id(cls):
+            cls.calls += 1
+            return bytes([cls.calls]) * 128
+
+    got = []
+    for k in range(3):
+        if rank == 1:
+            time.sleep(0.3)                  # the reader arrives late: rank 0 has long returned from the previous call
+        got.append(dsl._broadcast_nccl_id(FakeBackend, rank, world))
+    out.put((rank, got))
+    time.sleep(1.0 if rank == 0 else 0.0)    # (rank 0 hosts the store; in a real run the NCCL initialisation keeps it alive)
+
+
+@pytest.mark.timeout(120)
+def test_world2_dsl_id_broadcast_survives_late_readers_and_repeated_generate():
+    """dsl._broadcast_nccl_id (one call per generate()): three calls in two processes, the reader 0.3 s late each time -- every
+    call delivers ITS id to both ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port_no = _free_port()
+    procs = [ctx.Process(target=_id_worker, args=(r, 2, port_no, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    assert res[0] == res[1] == [bytes([k]) * 128 for k in (1, 2, 3)]
