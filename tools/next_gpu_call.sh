@@ -1,7 +1,9 @@
 #!/bin/bash
 # What has not run on a GPU yet, in one gpurun call (1 GPU, ~6 minutes):
 #   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_gpu_call.sh'
-# 1. user-defined properties (csrc/props.cu): the three tests of tests/test_gpu_props.py with the xfail marker ignored
+# 1. what was written after the GPU budget of round 1 was spent -- user-defined properties (csrc/props.cu), the rest of the generic
+#    vocabulary, generated DEM contact models and per-particle kernels in DEM scripts: tests/test_gpu_props.py with the xfail
+#    marker ignored
 # 2. the whole GPU suite (the border / exchange kernels got a run-time record stride)
 # 3. the headline bench line, to see that nothing moved
 # Outputs land in gpurun_out/.  For 2 or 4 GPUs: gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_props.py -q --runxfail -k between_ranks'
