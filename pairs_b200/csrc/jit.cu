@@ -33,6 +33,9 @@ struct PbJitArgs {
     double *radius;         // DEM scripts only (null otherwise): [cap]
     double *angvel;         //                                    [3][cap]
     double *torque;         //                                    [3][cap]
+    double *inv_inertia;    //                                    [9][cap]
+    double *rotmat;         //                                    [9][cap]
+    double *quat;           //                                    [4][cap]
 };
 
 static const char *PB_JIT_PRELUDE = R"PRELUDE(
@@ -53,7 +56,13 @@ struct PbJitArgs {
     double *radius;
     double *angvel;
     double *torque;
+    double *inv_inertia;
+    double *rotmat;
+    double *quat;
 };
+#ifndef PB_INFINITY
+#define PB_INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#endif
 #define PB_FLAG_FIXED 4
 #define PB_SHAPE_SPHERE 0
 __device__ __forceinline__ int pb_w_type(double w) { return (int) (__double_as_longlong(w) & 0xffffffffLL); }
@@ -221,6 +230,7 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     a.numneigh = ctx->numneigh; a.neigh = ctx->neigh; a.xdata = ctx->xdata;
     a.uid = ctx->uid; a.shape = ctx->shape;
     a.radius = ctx->radius; a.angvel = ctx->angvel; a.torque = ctx->torque;
+    a.inv_inertia = ctx->inv_inertia; a.rotmat = ctx->rotmat; a.quat = ctx->quat;
     void *params[] = {&a};
     PB_CHECK(cudaLaunchKernel((const void *) k.kernel, dim3(pb_blocks(ctx->nlocal, 128)), dim3(128), params, 0, ctx->stream));
     ctx->launches++;

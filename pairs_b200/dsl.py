@@ -429,6 +429,8 @@ class Simulation:
     def setup(self, func, symbols={}):
         """sim/simulation.py:266-267: a per-particle function run once over the locals after the set-up statements."""
         try:
+            if func.__name__ in FORCE_GENERIC_NAMES:
+                raise DslError("generic path forced")
             family, roles = recognise(func)
             if family != "update_mass_and_inertia":
                 raise DslError("not a set-up family")
@@ -628,9 +630,15 @@ class Simulation:
         ctx.dem_upload("radius", cat("radius", 1, np.float64))
         ctx.dem_upload("normal", cat("normal", 3, np.float64))
         for f in self.setup_functions:
-            if f["family"] != "update_mass_and_inertia":
-                raise DslError(f"DEM: setup() function '{f['name']}' is not the one of examples/dem.py (update_mass_and_inertia)")
-            ctx.dem_stage("update_mass_and_inertia")
+            if f["family"] == "update_mass_and_inertia":
+                ctx.dem_stage("update_mass_and_inertia")
+                continue
+            from . import backend, kernelgen              # any other set-up body: generated, run once over all locals
+            try:
+                _, kname, src = kernelgen.translate(f["func"], self._dem_storage(), {}, 1, f["symbols"], backend.jit_prelude(), skip_fixed=False)
+            except kernelgen.KernelGenError as err:
+                raise DslError(f"setup() function '{f['name']}': {err}") from None
+            ctx.jit_launch(ctx.jit_compile(src, kname), 1)
         ctx.timers_enable(True)
         ctx.sync()
         t0 = time.perf_counter()
@@ -650,17 +658,24 @@ class Simulation:
         self._print_summary(ctx, all_ms, rank)
         return ctx
 
-    def _dem_staged_loop(self, ctx, nsteps, rank, world):
-        """A DEM procedure list with further per-particle kernels (or without gravity / euler): the modules of the generated
-        loop one by one (sim/simulation.py:387-417 with contact history), user bodies through the generic path."""
-        from . import backend, kernelgen
+    def _dem_storage(self):
+        """Property names of a DEM script -> device arrays for generated per-particle kernels (the property set of examples/dem.py,
+        by its names)."""
         storage = {self.position_name: "pos"}
         for name, slot in (("linear_velocity", "vel"), ("angular_velocity", "angvel"), ("mass", "mass"), ("radius", "radius"),
-                           ("force", "force"), ("torque", "torque"), ("uid", "uid"), ("shape", "shape"), ("flags", "flags")):
+                           ("force", "force"), ("torque", "torque"), ("uid", "uid"), ("shape", "shape"), ("flags", "flags"),
+                           ("inv_inertia", "inv_inertia"), ("rotation_matrix", "rotmat"), ("rotation_quat", "quat")):
             if name in self.props:
                 storage[name] = slot
         for name in self.features:
             storage[name] = "type"
+        return storage
+
+    def _dem_staged_loop(self, ctx, nsteps, rank, world):
+        """A DEM procedure list with further per-particle kernels (or without gravity / euler): the modules of the generated
+        loop one by one (sim/simulation.py:387-417 with contact history), user bodies through the generic path."""
+        from . import backend, kernelgen
+        storage = self._dem_storage()
         calls = []
         for e in self.functions:
             if e["family"] in ("gravity", "euler", "linear_spring_dashpot", "generic_pair"):

@@ -41,8 +41,10 @@ def _lit(x):
     if isinstance(x, int):
         return str(x)
     r = repr(float(x))
-    if r in ("inf", "-inf", "nan"):
-        raise KernelGenError("non-finite symbol value")
+    if r in ("inf", "-inf"):
+        return "PB_INFINITY" if r == "inf" else "(-PB_INFINITY)"
+    if r == "nan":
+        raise KernelGenError("NaN symbol value")
     return r if ("." in r or "e" in r or "E" in r) else r + ".0"
 
 
@@ -87,6 +89,58 @@ class _Gen:
     def is_vec(v):
         return isinstance(v, tuple) and v[0] == "v"
 
+    @staticmethod
+    def is_mat(v):                           # 3x3 matrix, row-major, 9 components
+        return isinstance(v, tuple) and v[0] == "m"
+
+    @staticmethod
+    def is_quat(v):                          # quaternion (w, x, y, z)
+        return isinstance(v, tuple) and v[0] == "q"
+
+    def sum3(self, terms):
+        """(t0 + t1) + t2 (+ t3): Python's left-to-right sum of the reference's keyword implementations."""
+        acc = terms[0]
+        for t in terms[1:]:
+            acc = self.tmp("double", f"{acc} + {t}")
+        return acc
+
+    def mul(self, x, y):
+        return self.tmp("double", f"{x} * {y}")
+
+    def matmul(self, a, b):
+        """keywords.py:158-196 (matrix_multiplication) and :219-235 (quaternion_multiplication)."""
+        if self.is_quat(a) and self.is_quat(b):
+            l, r = a[1], b[1]
+
+            def comb(t0, t1, t2, t3, signs):
+                acc = self.mul(l[t0[0]], r[t0[1]])
+                for (x, y), sg in zip((t1, t2, t3), signs):
+                    acc = self.tmp("double", f"{acc} {sg} {self.mul(l[x], r[y])}")
+                return acc
+            rr = comb((0, 0), (1, 1), (2, 2), (3, 3), "---")
+            ii = comb((0, 1), (1, 0), (2, 3), (3, 2), "++-")
+            jj = comb((0, 2), (2, 0), (3, 1), (1, 3), "++-")
+            kk = comb((0, 3), (3, 0), (1, 2), (2, 1), "++-")
+            len2 = self.sum3([self.mul(x, x) for x in (rr, ii, jj, kk)])
+            off = self.tmp("double", f"{len2} - 1.0")
+            near = self.tmp("bool", f"fabs({off}) < 1e-08")
+            root = self.tmp("double", f"sqrt({len2})")
+            inv = self.tmp("double", f"1.0 / {root}")
+            ilen = self.tmp("double", f"({near}) ? (1.0) : ({inv})")
+            return ("q", [self.mul(x, ilen) for x in (rr, ii, jj, kk)])
+        if self.is_mat(a) and self.is_mat(b):
+            l, r = a[1], b[1]
+            return ("m", [self.sum3([self.mul(l[3 * i + k], r[3 * k + j]) for k in range(3)]) for i in range(3) for j in range(3)])
+        if self.is_mat(a) and self.is_vec(b):
+            return self.vec([self.sum3([self.mul(a[1][3 * i + k], b[1][k]) for k in range(3)]) for i in range(3)])
+        if self.is_vec(a) and self.is_mat(b):      # as the reference defines it: out[i] = sum_k v[k] * M[3 i + k]
+            return self.vec([self.sum3([self.mul(a[1][k], b[1][3 * i + k]) for k in range(3)]) for i in range(3)])
+        if self.is_mat(b) and not isinstance(a[1], list):
+            return ("m", [self.mul(x, a[1]) for x in b[1]])
+        if self.is_mat(a) and not isinstance(b[1], list):
+            return ("m", [self.mul(x, b[1]) for x in a[1]])
+        raise KernelGenError("unsupported product of matrices / quaternions")
+
     def load(self, store, who):
         key = (store, who)
         if key in self.loaded:
@@ -110,6 +164,10 @@ class _Gen:
             val = self.vec([self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(3)])
         elif store in ("mass", "radius"):
             val = ("f", self.tmp("double", f"a.{store}[{idx}]", hoist))
+        elif store in ("inv_inertia", "rotmat", "quat"):      # DEM scripts: matrix / quaternion properties, SoA rows of [cap]
+            n = 4 if store == "quat" else 9
+            val = ("q" if store == "quat" else "m",
+                   [self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(n)])
         elif store in ("uid", "shape", "flags"):
             val = ("i", self.tmp("int", f"a.{store}[{idx}]", hoist))
         elif store == "type":                                 # the feature index rides in the low bits of position.w
@@ -176,6 +234,10 @@ class _Gen:
         raise KernelGenError(f"unsupported expression {type(node).__name__}")
 
     def binop(self, op, a, b):
+        if any(self.is_mat(x) or self.is_quat(x) for x in (a, b)):
+            if op != "*":
+                raise KernelGenError("matrices and quaternions: only * is defined")
+            return self.matmul(a, b)
         if self.is_vec(a) and self.is_vec(b):
             if op in ("*", "/"):
                 raise KernelGenError("vector * vector is ambiguous: use dot()")
@@ -214,8 +276,8 @@ class _Gen:
         idx = node.slice
         if isinstance(idx, ast.Constant) and isinstance(idx.value, int) and not isinstance(idx.value, bool):
             base = self.expr(node.value)                      # v[0], position[i][2]: one component (ir/vectors.py VectorAccess)
-            if not self.is_vec(base) or not 0 <= idx.value < len(base[1]):
-                raise KernelGenError("component access needs a vector and an index 0..2")
+            if not isinstance(base[1], list) or not 0 <= idx.value < len(base[1]):
+                raise KernelGenError("component access needs a vector / matrix / quaternion and an index inside it")
             return ("f", base[1][idx.value])
         if not isinstance(node.value, ast.Name):
             raise KernelGenError("unsupported subscript")
@@ -297,6 +359,54 @@ class _Gen:
                 raise KernelGenError(f"{f}() takes the particle argument")
             sh = self.load("shape", node.args[0].id)
             return ("b", self.tmp("bool", f"{sh[1]} == {dict(is_sphere=0, is_halfspace=1, is_point_mass=2)[f]}"))
+        if f == "transposed":                                 # keywords.py:124-130
+            if not self.is_mat(args[0]):
+                raise KernelGenError("transposed() takes a matrix")
+            m = args[0][1]
+            return ("m", [m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8]])
+        if f == "inversed":                                   # keywords.py:132-149
+            if not self.is_mat(args[0]):
+                raise KernelGenError("inversed() takes a matrix")
+            m = args[0][1]
+
+            def minor(p, q, r, t):
+                return self.tmp("double", f"{self.mul(m[p], m[q])} - {self.mul(m[r], m[t])}")
+            det = self.sum3([self.mul(m[0], minor(4, 8, 7, 5)), self.mul(m[1], minor(5, 6, 8, 3)), self.mul(m[2], minor(3, 7, 4, 6))])
+            inv = self.tmp("double", f"1.0 / {det}")
+            idx = ((4, 8, 5, 7), (7, 2, 8, 1), (1, 5, 2, 4), (5, 6, 3, 8), (8, 0, 6, 2), (2, 3, 0, 5), (3, 7, 4, 6), (6, 1, 7, 0), (0, 4, 1, 3))
+            return ("m", [self.mul(inv, minor(*t)) for t in idx])
+        if f == "diagonal_matrix":                            # keywords.py:151-156
+            if isinstance(args[0][1], list):
+                raise KernelGenError("diagonal_matrix() takes a scalar")
+            return ("m", [args[0][1] if k % 4 == 0 else "0.0" for k in range(9)])
+        if f == "default_quaternion":
+            return ("q", ["1.0", "0.0", "0.0", "0.0"])
+        if f == "quaternion":                                 # keywords.py:202-217 (`A or B` on IR nodes keeps A: only the axis test)
+            axis, angle = args
+            if not self.is_vec(axis) or isinstance(angle[1], list):
+                raise KernelGenError("quaternion() takes an axis vector and an angle")
+            ln = self.tmp("double", f"sqrt({self.sum3([self.mul(x, x) for x in axis[1]])})")
+            zero = self.tmp("bool", f"fabs({ln}) < 1e-06")
+            half = self.mul(angle[1], "0.5")
+            sina = self.tmp("double", f"sin({half})")
+            cosa = self.tmp("double", f"cos({half})")
+            inv = self.tmp("double", f"1.0 / {ln}")
+            comps = [cosa] + [self.mul(sina, self.mul(x, inv)) for x in axis[1]]
+            return ("q", [self.tmp("double", f"({zero}) ? ({d}) : ({c})") for d, c in zip(("1.0", "0.0", "0.0", "0.0"), comps)])
+        if f == "quaternion_to_rotation_matrix":              # keywords.py:237-251
+            if not self.is_quat(args[0]):
+                raise KernelGenError("quaternion_to_rotation_matrix() takes a quaternion")
+            q = args[0][1]
+
+            def diag(x, y):
+                first = self.tmp("double", f"1.0 - {self.mul(self.mul('2.0', q[x]), q[x])}")
+                return self.tmp("double", f"{first} - {self.mul(self.mul('2.0', q[y]), q[y])}")
+
+            def off(x, y, sg, u, v):
+                inner = self.tmp("double", f"{self.mul(q[x], q[y])} {sg} {self.mul(q[u], q[v])}")
+                return self.mul("2.0", inner)
+            return ("m", [diag(2, 3), off(1, 2, "-", 0, 3), off(1, 3, "+", 0, 2), off(1, 2, "+", 0, 3), diag(1, 3), off(2, 3, "-", 0, 1),
+                          off(1, 3, "-", 0, 2), off(2, 3, "+", 0, 1), diag(1, 2)])
         if f == "cross":                                      # keywords.py:95-103
             a, b = args
             if not (self.is_vec(a) and self.is_vec(b)):
@@ -474,8 +584,18 @@ class _Gen:
         if store in ("uid", "shape", "flags", "type"):
             raise KernelGenError("integer properties (uid, shape, flags, the feature) are read-only in kernels")
         self.stored.add(store)
+        if store in ("inv_inertia", "rotmat", "quat"):
+            n = 4 if store == "quat" else 9
+            if not isinstance(v[1], list):                    # a scalar assigned to a matrix: every element (examples/dem.py:15)
+                v = ("q" if store == "quat" else "m", [v[1]] * n)
+            if len(v[1]) != n or self.is_vec(v):
+                raise KernelGenError(f"'{store}' takes a {'quaternion' if n == 4 else 'matrix'}")
+            for d in range(n):
+                self.lines.append(f"a.{store}[{d} * (size_t) a.cap + i] = {v[1][d]};")
+            self.loaded[(store, "i")] = v
+            return
         if store in ("mass", "radius"):
-            if self.is_vec(v):
+            if isinstance(v[1], list):
                 raise KernelGenError(f"{store} is a scalar")
             self.lines.append(f"a_mass_w[i] = {v[1]};" if store == "mass" else f"a.radius[i] = {v[1]};")
             self.loaded[(store, "i")] = v

@@ -10,6 +10,7 @@ struct double2 { double x, y; };
 struct double4 { double x, y, z, w; };
 struct PbHostIdx { int x; };
 static PbHostIdx blockIdx, blockDim, threadIdx;
+#define PB_INFINITY INFINITY
 #define __global__
 #define __device__
 #define __forceinline__ inline

@@ -113,23 +113,27 @@ def test_generated_dem_contact_model_reproduces_the_built_in_run_bit_for_bit(cap
 
 def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in_run(capsys):
     """A DEM procedure list that is not exactly gravity / model / euler runs module by module with the user bodies generated: here
-    gravity itself is sent through the generic path, 150 iterations (before the native loop's first spatial re-sort) must end in
+    gravity, euler and the set-up function update_mass_and_inertia are sent through the generic path (matrix / quaternion algebra
+    included; the built-in and the generated kernel call the same device sin / cos), 150 iterations (before the native loop's first spatial re-sort) must end in
     the bits of the native run."""
     import dem_script
     from pairs_b200 import dsl
     from tests import dem_common as dc
     ref_ctx = dem_script.build("gpu", dc.DOMAIN, 150).generate()
-    dsl.FORCE_GENERIC_NAMES = {"gravity"}
+    dsl.FORCE_GENERIC_NAMES = {"gravity", "euler", "update_mass_and_inertia"}
     try:
         psim = dem_script.build("gpu", dc.DOMAIN, 150)
     finally:
         dsl.FORCE_GENERIC_NAMES = set()
-    assert [e["family"] for e in psim.functions] == ["generic_particle", "linear_spring_dashpot", "euler"]
+    assert [e["family"] for e in psim.functions] == ["generic_particle", "linear_spring_dashpot", "generic_particle"]
+    assert [e["family"] for e in psim.setup_functions] == ["generic_setup"]
     ctx = psim.generate()
     capsys.readouterr()
     n = ctx.counts()[0]
     for name in ("position", "linear_velocity", "force"):
         assert np.array_equal(ctx.real(name), ref_ctx.real(name)), name
+    for name in ("angular_velocity", "rotation_quat", "rotation_matrix", "inv_inertia"):
+        assert np.array_equal(ctx.dem_download(name, n), ref_ctx.dem_download(name, n)), name
     a, b = ctx.dem_download_contacts(n), ref_ctx.dem_download_contacts(n)
     for k in a:
         assert np.array_equal(a[k], b[k]), k

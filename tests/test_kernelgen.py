@@ -152,17 +152,19 @@ def test_if_statements_and_local_updates():
 def _host_kernel(tmp_path, name, src):
     """Compiles a generated kernel for the HOST (tests/host/jit_host_emulation.h stands in for the CUDA bits) together with a
     driver that runs it for every particle; returns run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags, numneigh, neigh,
-    xdata=None, uid=None, shape=None, radius=None, angvel=None, torque=None) taking array addresses."""
+    xdata=None, uid=None, shape=None, radius=None, angvel=None, torque=None, inv_inertia=None, rotmat=None, quat=None) taking array addresses."""
     import ctypes
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     cpp = tmp_path / f"{name}.cpp"
     cpp.write_text('#include "jit_host_emulation.h"\n' + src + f'''
 extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, double *vel, double *force, double *mass, int *flags,
-                    int *numneigh, int *neigh, double *xdata, int *uid, int *shape, double *radius, double *angvel, double *torque) {{
+                    int *numneigh, int *neigh, double *xdata, int *uid, int *shape, double *radius, double *angvel, double *torque,
+                    double *inv_inertia, double *rotmat, double *quat) {{
     PbJitArgs a;
     a.nlocal = n; a.nslots = nslots; a.cap = cap; a.pad = 0; a.cutsq = cutsq; a.pos = pos; a.pos_w = pos; a.vel = vel; a.force = force;
     a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata; a.uid = uid; a.shape = shape; a.radius = radius; a.angvel = angvel; a.torque = torque;
+    a.inv_inertia = inv_inertia; a.rotmat = rotmat; a.quat = quat;
     blockDim.x = 128;
     for(int i = 0; i < n; i++) {{ blockIdx.x = i / 128; threadIdx.x = i % 128; {name}(a); }}
 }}
@@ -172,11 +174,12 @@ extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, doub
                    check=True)
     lib = ctypes.CDLL(str(so))
     P = ctypes.c_void_p
-    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, P, P, P, P, P, P, P, P, P, P, P, P, P]
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [P] * 16
 
     def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None, uid=None, shape=None, radius=None, angvel=None,
-            torque=None):
-        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata, uid, shape, radius, angvel, torque)
+            torque=None, inv_inertia=None, rotmat=None, quat=None):
+        lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata, uid, shape, radius, angvel, torque, inv_inertia,
+                rotmat, quat)
     return run
 
 
@@ -587,3 +590,78 @@ def test_generated_dem_per_particle_kernel_on_the_host(tmp_path):
     expect = f0[2] - (2550 - 1000) * volume * 9.81
     expect[::9] = f0[2, ::9]                       # FIXED particles are skipped
     assert np.array_equal(force[2], expect) and np.array_equal(force[:2], f0[:2])
+
+
+def test_generated_dem_integrator_and_setup_equal_dem_math_on_the_host(tmp_path):
+    """examples/dem.py's euler and update_mass_and_inertia through the generic path: matrix / quaternion properties and the
+    keywords transposed, inversed, diagonal_matrix, default_quaternion, quaternion, quaternion_to_rotation_matrix, the matrix *
+    vector / vector * matrix / quaternion * quaternion products, `mass[i] = infinity`, a scalar assigned to a matrix.  Compiled for
+    the host and compared with pb_dem_euler / pb_dem_sphere_inv_inertia of csrc/dem_math.h (pinned to the reference's generated code
+    by tests/test_dem_host.py): every array identical, bit for bit."""
+    import ctypes
+    import math
+    import subprocess
+    import numpy as np
+    import dem_script
+    here = os.path.dirname(os.path.abspath(__file__))
+    storage = dict(DEM_STORAGE, uid="uid", shape="shape", flags="flags", inv_inertia="inv_inertia", rotation_matrix="rotmat",
+                   rotation_quat="quat")
+    dt = 5e-5
+    _, n_eul, c_eul = kernelgen.translate(dem_script.euler, storage, {}, 1, {"dt": dt}, backend.jit_prelude())
+    _, n_upd, c_upd = kernelgen.translate(dem_script.update_mass_and_inertia, storage, {}, 1,
+                                          {"densityParticle_SI": 2550, "pi": math.pi, "infinity": math.inf}, backend.jit_prelude(), skip_fixed=False)
+    assert "PB_INFINITY" in c_upd and "sin(" in c_eul and "cos(" in c_eul
+    assert backend.jit_check(c_eul) > 1000 and backend.jit_check(c_upd) > 1000
+    run_eul, run_upd = _host_kernel(tmp_path, n_eul, c_eul), _host_kernel(tmp_path, n_upd, c_upd)
+    # the hand-written side: tests/host/dem_host.cpp (dem_math.h on AoS arrays)
+    so = tmp_path / "dem_host.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-I" + os.path.join(os.path.dirname(here), "pairs_b200", "csrc"),
+                    os.path.join(here, "host", "dem_host.cpp"), "-o", str(so)], check=True)
+    host = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(11)
+    n = 400
+    flags = np.zeros(n, np.int32)
+    flags[::7] = 4
+    shape = np.zeros(n, np.int32)
+    shape[3::50] = 1
+    mass = 1e-4 * (1.0 + rng.random(n))
+    radius = 0.001 * (1.0 + rng.random(n))
+    # ---- update_mass_and_inertia (a setup() function: FIXED particles included) ----
+    pos4 = np.zeros((n, 4))
+    m_g = mass.copy()
+    Iinv_g, R_g, q_g = (np.full((k, n), 7.0) for k in (9, 9, 4))
+    z3 = np.zeros((3, n))
+    run_upd(n, 0, n, 0.0, _ptr(pos4), _ptr(z3), _ptr(z3.copy()), _ptr(m_g), _ptr(flags), None, None, None, None, _ptr(shape), _ptr(radius), None, None,
+            _ptr(Iinv_g), _ptr(R_g), _ptr(q_g))
+    assert np.array_equal(R_g.T, np.tile(np.eye(3).ravel(), (n, 1))) and np.array_equal(q_g.T, np.tile([1.0, 0.0, 0.0, 0.0], (n, 1)))
+    assert np.all(np.isinf(m_g[shape == 1])) and np.array_equal(m_g[shape == 0], mass[shape == 0]) and not Iinv_g[:, shape == 1].any()
+    host.host_dem_sphere_inv_inertia.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    want = np.zeros(9)
+    for i in np.flatnonzero(shape == 0)[:60]:
+        host.host_dem_sphere_inv_inertia(mass[i], radius[i], _ptr(want))
+        assert np.array_equal(Iinv_g[:, i], want), i
+    # ---- euler: two steps on random states (tiny and large rotations) ----
+    pos = rng.random((n, 3))
+    vel, f, tau = rng.standard_normal((n, 3)), 1e-3 * rng.standard_normal((n, 3)), 1e-7 * rng.standard_normal((n, 3))
+    w = 50.0 * rng.standard_normal((n, 3))
+    w[::5] = 0.0
+    tau[::5] = 0.0                                         # no rotation at all: quaternion() takes its zero branch
+    Iinv = np.ascontiguousarray(Iinv_g.T.copy())
+    Iinv[shape == 1] = 0.0
+    q = np.tile([1.0, 0.0, 0.0, 0.0], (n, 1))
+    R = np.tile(np.eye(3).ravel(), (n, 1))
+    pos4[:, :3] = pos
+    vel_g, f_g, tau_g, w_g = (np.ascontiguousarray(a.T) for a in (vel, f, tau, w))
+    Iinv_g2, q_g2, R_g2 = (np.ascontiguousarray(a.T) for a in (Iinv, q, R))
+    mass_e = mass.copy()
+    P = (ctypes.c_double * 16)()
+    host.host_dem_params.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 8
+    host.host_dem_params(P, dt, math.pi, 0.8, -0.1, 2e-4, 2550.0, 1000.0, 9.81)
+    host.host_dem_euler.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 10
+    for step in range(2):
+        host.host_dem_euler(P, n, _ptr(flags), _ptr(mass_e), _ptr(f), _ptr(tau), _ptr(Iinv), _ptr(pos), _ptr(vel), _ptr(w), _ptr(q), _ptr(R))
+        run_eul(n, 0, n, 0.0, _ptr(pos4), _ptr(vel_g), _ptr(f_g), _ptr(mass_e), _ptr(flags), None, None, None, None, _ptr(shape), _ptr(radius), _ptr(w_g),
+                _ptr(tau_g), _ptr(Iinv_g2), _ptr(R_g2), _ptr(q_g2))
+        assert np.array_equal(pos4[:, :3], pos) and np.array_equal(vel_g.T, vel) and np.array_equal(w_g.T, w)
+        assert np.array_equal(q_g2.T, q) and np.array_equal(R_g2.T, R)
+    assert np.abs(q[1] - [1.0, 0.0, 0.0, 0.0]).max() > 1e-4 and np.array_equal(q[0], [1.0, 0.0, 0.0, 0.0])     # rotated / FIXED
