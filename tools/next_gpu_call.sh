@@ -5,7 +5,8 @@
 #    vocabulary, generated DEM contact models and per-particle kernels in DEM scripts: tests/test_gpu_props.py with the xfail
 #    marker ignored
 # 2. the whole GPU suite (the border / exchange kernels got a run-time record stride)
-# 3. the headline bench line, to see that nothing moved
+# 3. the generic path and the user-property rows next to the hand-written kernels (tools/bench_generic.py)
+# 4. the headline bench line, to see that nothing moved
 # Outputs land in gpurun_out/.  For 2 or 4 GPUs: gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_props.py -q --runxfail -k between_ranks'
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_props.py -q --runxfail -x > gpurun_out/props_gpu.log 2>&1
@@ -14,5 +15,7 @@ tail -30 gpurun_out/props_gpu.log
 timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/gpu_suite.log 2>&1
 echo "suite exit $?" >> gpurun_out/gpu_suite.log
 tail -5 gpurun_out/gpu_suite.log
+timeout 600 python tools/bench_generic.py 63 100 > gpurun_out/bench_generic.json 2> gpurun_out/bench_generic.err
+tail -c 1500 gpurun_out/bench_generic.json
 timeout 600 python bench.py --steps 100 --warmup 20 > gpurun_out/bench_next.json 2> gpurun_out/bench_next.err
 tail -c 600 gpurun_out/bench_next.json
