@@ -123,7 +123,7 @@ int pb_synchronize(pb_ctx *ctx);
  *      Non-volatile properties travel with their particle through the cell-order sort, migration (Comm.exchange carries every
  *      non-volatile property, sim/comm.py:100-103) and ghost creation; volatile ones are zeroed by pb_reset_volatile
  *      (sim/properties.py:61-70).  New particles start from `defaults` (NULL = zeros).  Generated kernels (pb_jit_*) address
- *      component d as PbJitArgs.xdata[(row0 + d) * cap + i]; pb_property_info returns row0.  md.py path only (not with pb_dem_enable). ---- */
+ *      component d as PbJitArgs.xdata[(row0 + d) * cap + i]; pb_property_info returns row0.  Available on the md.py and the DEM path. ---- */
 int pb_add_property(pb_ctx *ctx, const char *name, int ncomps, int is_volatile, const double *defaults, int *prop_id);
 int pb_property_count(const pb_ctx *ctx);
 int pb_property_info(const pb_ctx *ctx, int prop_id, int *ncomps, int *row0, int *is_volatile);

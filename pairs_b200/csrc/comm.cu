@@ -266,7 +266,7 @@ extern "C" int pb_borders(pb_ctx *ctx) {
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }
     // record length: the built-in elements, then the non-volatile rows of the user-defined properties (props.cu)
     const int base_elems = ctx->dem ? BORDER_ELEMS_DEM : BORDER_ELEMS;
-    const int stride = base_elems + (ctx->dem ? 0 : ctx->xrows_nv);
+    const int stride = base_elems + ctx->xrows_nv;
     for(int step = 0; step < 3; step++) {
         const int n = ctx->nlocal + ctx->nghost;     // locals AND ghosts received so far: edges/corners are forwarded
         int c_lo = 0, c_hi = 0;
@@ -288,8 +288,8 @@ extern "C" int pb_borders(pb_ctx *ctx) {
                 PB_LAUNCH(pb_k_pack_border<false>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
                           ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
                           nullptr, nullptr);
-                PB_TRY(pb_xprops_pack(ctx, ctx->send_offsets[step * 2], ns, stride, base_elems, ctx->send_map, ctx->send_buf));
             }
+            PB_TRY(pb_xprops_pack(ctx, ctx->send_offsets[step * 2], ns, stride, base_elems, ctx->send_map, ctx->send_buf));
         }
         const double *src = nullptr;
         PB_TRY(pb_transport_data(ctx, step, step + 1, stride, &src));
@@ -302,8 +302,8 @@ extern "C" int pb_borders(pb_ctx *ctx) {
                 PB_LAUNCH(pb_k_unpack_border<false>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
                           ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
                           ctx->uid, ctx->shape, ctx->tag, nullptr, nullptr);
-                PB_TRY(pb_xprops_unpack(ctx, ctx->recv_offsets[step * 2], nr, ctx->nlocal + ctx->recv_offsets[step * 2], stride, base_elems, src));
             }
+            PB_TRY(pb_xprops_unpack(ctx, ctx->recv_offsets[step * 2], nr, ctx->nlocal + ctx->recv_offsets[step * 2], stride, base_elems, src));
         }
         ctx->nghost += nr;
     }

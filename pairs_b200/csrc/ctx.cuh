@@ -186,10 +186,10 @@ struct pb_ctx {
 
 static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record in MD (exchange: 12, borders: 11/15, sync: 6)
 // DEM exchange record: 12 base + radius 1 + angvel 3 + normal 3 + inv_inertia 9 + rotmat 9 + quat 4 + num_contacts 1 + 6 per slot
-// MD with user-defined properties: their non-volatile rows follow the 12 (exchange) / 11 (borders) built-in elements
-static inline int pb_record_elems(const pb_ctx *ctx) {
-    return ctx->dem ? std::max(PB_MAX_ELEMS, 42 + 6 * ctx->ccontacts) : std::max(PB_MAX_ELEMS, 12 + ctx->xrows_nv);
-}
+// user-defined properties: their non-volatile rows follow the built-in elements of a record (MD: 12 exchange / 11 borders,
+// DEM: 42 + 6 C exchange / 15 borders)
+static inline int pb_exchange_base_elems(const pb_ctx *ctx) { return ctx->dem ? 42 + 6 * ctx->ccontacts : 12; }
+static inline int pb_record_elems(const pb_ctx *ctx) { return std::max(PB_MAX_ELEMS, pb_exchange_base_elems(ctx) + ctx->xrows_nv); }
 static const int PB_NSCALARS = 16;
 
 // ---- user-defined properties (props.cu) ----

@@ -72,7 +72,6 @@ extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(ctx->dem) { return 0; }
     if(contact_capacity < 1 || contact_capacity > 64) { ctx->set_error("pb_dem_enable: 1 <= contact_capacity <= 64"); return -1; }
-    if(ctx->xrows > 0) { ctx->set_error("pb_dem_enable: user-defined properties (pb_add_property) are available on the md.py path only"); return -1; }
     ctx->ccontacts = contact_capacity;
     ctx->dem = true;
     if(ctx->send_cap > 0) {        // wire records grow (contact history travels with migrating particles): re-size the buffers
@@ -817,6 +816,7 @@ extern "C" int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts
         PB_TRY(pb_borders(ctx));
         PB_TRY(pb_build_cell_lists(ctx));
         if(ctx->ccontacts <= 32 && ctx->dem_fuse) {
+            if(ctx->xrows > ctx->xrows_nv) { PB_TRY(pb_xprops_reset_volatile(ctx)); }      // volatile user-defined properties
             PB_TRY(pb_dem_contacts_fused(ctx));      // usage reset + volatile reset + gravity + contacts + history clean-up
             PB_TRY(pb_dem_euler(ctx));
         } else {

@@ -175,14 +175,15 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
     ctx->send_offsets[j0] = 0;
     ctx->send_offsets[j1] = c_lo;
     PB_TRY(pb_ensure_send_capacity(ctx, c_lo + c_hi));
-    const int stride = ctx->dem ? pb_record_elems(ctx) : EXCH_ELEMS + ctx->xrows_nv;   // + non-volatile user-defined rows (props.cu)
+    const int xoff = pb_exchange_base_elems(ctx);        // the non-volatile user-defined rows (props.cu) follow the built-in elements
+    const int stride = ctx->dem ? pb_record_elems(ctx) : EXCH_ELEMS + ctx->xrows_nv;
     if(c_lo + c_hi > 0) {
         const double len = ctx->grid[dim * 2 + 1] - ctx->grid[dim * 2];
         PB_LAUNCH(pb_k_pack_exchange, nblocks, MIG_T, n, nblocks, ctx->pcap, stride, dim, ctx->subdom[j0], ctx->subdom[j1], do_lo, do_hi,
                   ctx->pbc[j0], ctx->pbc[j1], len, ctx->send_cap, ctx->sel_blocks, totals, ctx->pos, ctx->vel, ctx->mass, ctx->flags, ctx->uid,
                   ctx->shape, ctx->tag, ctx->send_buf, rec, lb);
         if(ctx->dem) { PB_TRY(pb_dem_pack_exchange(ctx, n, stride, rec)); }
-        else { PB_TRY(pb_xprops_pack_leavers(ctx, n, stride, EXCH_ELEMS, rec, ctx->send_buf)); }
+        PB_TRY(pb_xprops_pack_leavers(ctx, n, stride, xoff, rec, ctx->send_buf));
     }
     PB_TRY(pb_transport_sizes(ctx, dim));
     ctx->recv_offsets[j0] = 0;
@@ -195,7 +196,7 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
         PB_LAUNCH(pb_k_move_base, pb_blocks(L, 256), 256, lb + c_stay, ctx->pcap, fill_idx, hole_idx, ctx->pos, ctx->vel, ctx->mass, ctx->type,
                   ctx->flags, ctx->uid, ctx->shape, ctx->tag);
         if(ctx->dem) { PB_TRY(pb_dem_move(ctx, L, lb + c_stay, fill_idx, hole_idx)); }
-        else { PB_TRY(pb_xprops_move(ctx, L, lb + c_stay, fill_idx, hole_idx)); }
+        PB_TRY(pb_xprops_move(ctx, L, lb + c_stay, fill_idx, hole_idx));
     }
     // grow only now: the scratch above is re-allocated (not kept) by a capacity change
     ctx->nlocal = c_stay;
@@ -206,7 +207,7 @@ int pb_exchange_multi(pb_ctx *ctx, int dim) {
         PB_LAUNCH(pb_k_unpack_exchange, pb_blocks(nr, 256), 256, nr, c_stay, ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type,
                   ctx->flags, ctx->uid, ctx->shape, ctx->tag);
         if(ctx->dem) { PB_TRY(pb_dem_unpack_exchange(ctx, nr, c_stay, stride, src)); }
-        else { PB_TRY(pb_xprops_unpack(ctx, 0, nr, c_stay, stride, EXCH_ELEMS, src)); }
+        PB_TRY(pb_xprops_unpack(ctx, 0, nr, c_stay, stride, xoff, src));
     }
     ctx->nlocal = c_stay + nr;
     for(int j = 0; j < 6; j++) { ctx->nsend[j] = 0; ctx->nrecv[j] = 0; ctx->send_offsets[j] = 0; ctx->recv_offsets[j] = 0; }

@@ -45,7 +45,6 @@ static int pb_xprops_fill(pb_ctx *ctx, double *data, size_t cap, size_t first) {
 
 extern "C" int pb_add_property(pb_ctx *ctx, const char *name, int ncomps, int is_volatile, const double *defaults, int *prop_id) {
     PB_CHECK(cudaSetDevice(ctx->device));
-    if(ctx->dem) { ctx->set_error("pb_add_property: user-defined properties are available on the neighbour-list (md.py) path only"); return -1; }
     if(name == nullptr || ncomps < 1 || ncomps > PB_XPROP_MAX_COMPS) { ctx->set_error("pb_add_property: a property has 1 to 9 components"); return -1; }
     if(ctx->xrows + ncomps > PB_XPROP_MAX_ROWS) {
         ctx->set_error("pb_add_property: more than " + std::to_string(PB_XPROP_MAX_ROWS) + " rows of user-defined properties");

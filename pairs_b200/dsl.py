@@ -579,6 +579,9 @@ class Simulation:
         eul = next((e for e in self.functions if e["family"] == "euler"), None)
         standard = fams in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"])
         ctx.dem_enable(self.neighbor_capacity)
+        for name, comps, volatile, dflt in self._dem_user_props():
+            _, row0 = ctx.add_property(name, comps, volatile, dflt)
+            assert row0 == self._dem_storage()[name][1]
         dt = self._symbol(eul, "dt") if eul is not None else 0.0
         g_pi = self._symbol(grav, "pi") if grav is not None else math.pi
         g_par = [self._symbol(grav, r) for r in ("density_particle", "density_fluid", "gravity")] if grav is not None else [0.0, 0.0, 0.0]
@@ -669,7 +672,28 @@ class Simulation:
                 storage[name] = slot
         for name in self.features:
             storage[name] = "type"
+        # whatever else the script declares (reals, vectors, integers): rows of the user-property block, as on the md.py path
+        row = 0
+        for name, p in self.props.items():
+            if name in storage or name == "normal" or name in self.feature_props:
+                continue
+            if p.type in (Types.Real, Types.Vector):
+                comps = 3 if p.type == Types.Vector else 1
+                storage[name] = ("x", row, comps)
+                row += comps
+            elif p.type == Types.Int32:
+                storage[name] = ("x", row, 1, "i")
+                row += 1
         return storage
+
+    def _dem_user_props(self):
+        out = []
+        for name, st in self._dem_storage().items():
+            if isinstance(st, tuple):
+                p = self.props[name]
+                v = p.value if isinstance(p.value, (list, tuple)) else [p.value] * st[2]
+                out.append((name, st[2], p.volatile, [_builtin_float(x) for x in v]))
+        return out
 
     def _dem_staged_loop(self, ctx, nsteps, rank, world):
         """A DEM procedure list with further per-particle kernels (or without gravity / euler): the modules of the generated

@@ -139,6 +139,33 @@ def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in
         assert np.array_equal(a[k], b[k]), k
 
 
+def test_dem_script_with_a_user_property_and_an_extra_kernel(capsys):
+    """A DEM script that declares a further property (the distance every sphere has travelled) and a further per-particle kernel
+    that integrates it: the trajectory is that of the plain script (the extra kernel touches nothing else; 150 iterations, staged
+    loop), and the travelled distance equals what numpy integrates from the velocities of consecutive iterations."""
+    import dem_script
+    import pairs
+    from tests import dem_common as dc
+
+    def odometer(i):
+        travelled[i] += dt * length(linear_velocity[i])
+
+    ref_ctx = dem_script.build("gpu", dc.DOMAIN, 150).generate()
+    psim = dem_script.build("gpu", dc.DOMAIN, 150)
+    psim.add_property('travelled', pairs.real(), 0.0)
+    psim.compute(odometer, symbols={'dt': 5e-5})
+    assert [e["family"] for e in psim.functions] == ["gravity", "linear_spring_dashpot", "euler", "generic_particle"]
+    ctx = psim.generate()
+    capsys.readouterr()
+    assert np.array_equal(ctx.real("position"), ref_ctx.real("position")) and np.array_equal(ctx.real("linear_velocity"), ref_ctx.real("linear_velocity"))
+    trav = ctx.download_property("travelled")
+    n = len(trav)
+    # spheres fall ~1 m/s for 151 iterations of 5e-5 s; the two FIXED half-spaces do not move
+    moving = (ctx.ints("flags") & 4) == 0
+    assert moving.sum() == n - 2 and np.all(trav[~moving] == 0.0)
+    assert np.all(trav[moving] > 0.5 * 151 * 5e-5) and np.all(trav[moving] < 3.0 * 151 * 5e-5)
+
+
 def test_property_store_through_the_c_abi(capsys):
     """add / upload / download, defaults, capacity growth, ghosts carrying their source's values, volatile reset, the cell-order
     sort -- without any generated kernel."""
