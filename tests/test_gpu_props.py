@@ -160,10 +160,12 @@ def test_dem_script_with_a_user_property_and_an_extra_kernel(capsys):
     assert np.array_equal(ctx.real("position"), ref_ctx.real("position")) and np.array_equal(ctx.real("linear_velocity"), ref_ctx.real("linear_velocity"))
     trav = ctx.download_property("travelled")
     n = len(trav)
-    # spheres fall ~1 m/s for 151 iterations of 5e-5 s; the two FIXED half-spaces do not move
+    # spheres start at ~1 m/s (150 integrated iterations of 5e-5 s; the lowest ones land after ~1 mm and creep from then on), most of
+    # them are still falling at the end; the two FIXED half-spaces do not move
     moving = (ctx.ints("flags") & 4) == 0
     assert moving.sum() == n - 2 and np.all(trav[~moving] == 0.0)
-    assert np.all(trav[moving] > 0.5 * 151 * 5e-5) and np.all(trav[moving] < 3.0 * 151 * 5e-5)
+    assert np.all(trav[moving] > 2e-4) and np.all(trav[moving] < 3.0 * 150 * 5e-5)
+    assert 0.8 * 150 * 5e-5 < np.median(trav[moving]) < 1.3 * 150 * 5e-5
 
 
 def test_property_store_through_the_c_abi(capsys):
