@@ -243,3 +243,26 @@ def test_dem_script_with_a_generated_contact_model_plans_and_compiles():
     assert backend.jit_check_dem_model(src, name) > 10000
     # the stock script is still recognised
     assert [e["family"] for e in dem_script.build("gpu", (0.1, 0.015, 0.04), 10).functions] == ["gravity", "linear_spring_dashpot", "euler"]
+
+
+def test_dem_script_with_a_user_property_plans_and_compiles():
+    """DEM scripts may declare further properties and per-particle kernels: storage rows, procedure list and NVRTC compilation."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    from pairs_b200 import backend, kernelgen
+
+    def odometer(i):
+        travelled[i] += dt * length(linear_velocity[i])
+        hits[i] = hits[i] + select(linear_velocity[i][2] > 0.0, 1, 0)
+
+    psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10)
+    psim.add_property('travelled', pairs.real(), 0.0)
+    psim.add_property('hits', pairs.int32(), 0)
+    psim.compute(odometer, symbols={'dt': 5e-5})
+    assert [e["family"] for e in psim.functions] == ["gravity", "linear_spring_dashpot", "euler", "generic_particle"]
+    st = psim._dem_storage()
+    assert st["travelled"] == ("x", 0, 1) and st["hits"] == ("x", 1, 1, "i") and st["rotation_quat"] == "quat" and "normal" not in st
+    assert psim._dem_user_props() == [("travelled", 1, False, [0.0]), ("hits", 1, False, [0.0])]
+    _, name, src = kernelgen.translate(odometer, st, {}, 1, {"dt": 5e-5}, backend.jit_prelude())
+    assert "a.xdata[0 * (size_t) a.cap + i] =" in src and "a.xdata[1 * (size_t) a.cap + i] = (double)" in src
+    assert backend.jit_check(src) > 1000
