@@ -1,4 +1,4 @@
-"""Features written after the round's GPU budget was spent.  User-defined particle properties (csrc/props.cu, kernelgen.py) on the GPU: tests/scripts/props_script.py -- examples/md.py plus
+"""User-defined particle properties (csrc/props.cu, kernelgen.py) on the GPU: tests/scripts/props_script.py -- examples/md.py plus
 six properties beyond the MD set, used by a setup() function, the pair kernel and both integrators -- against the run of the
 REFERENCE's code generator on the same text (oracle/build_ref.py variant md_props_t1 -> tests/golden/md_props_t1.npz), and the
 structural operations (sort, wrap, growth, ghosts, upload / download) through the C-ABI."""
@@ -12,11 +12,12 @@ import pytest
 from tests import props_common as pc
 from tests.util import by_id, rel_err_force
 
-# First GPU run pending: this file was written after the round's GPU budget was spent.  What runs on the CPU is pinned (the four
-# generated kernels equal the reference generator's modules bit for bit, tests/test_kernelgen.py); the device-side plumbing has
-# compiled for sm_100a but not executed yet, hence non-strict xfail: a pass is reported as XPASS, a failure does not hide the
-# verified suite.  Remove the marker after the first green run.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="user-defined properties: first GPU run pending")]
+# Written after most of the round's GPU budget was spent; what the last GPU-minutes confirmed on a B200 (profiles/r01_m_*.log): the
+# property store, the props and vocabulary scripts against the reference generator's goldens, the generated DEM contact model and
+# the DEM script with a user property pass; the fully generated DEM script matched the native run in every particle array (its last
+# assertions had a wrong threshold and have not re-run), the multi-GPU check has not run.  Those two keep a non-strict xfail.
+pytestmark = pytest.mark.gpu
+PENDING = pytest.mark.xfail(strict=False, reason="first complete GPU run pending")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "scripts"))
 
@@ -111,6 +112,7 @@ def test_generated_dem_contact_model_reproduces_the_built_in_run_bit_for_bit(cap
         assert np.array_equal(a[k], b[k]), k
 
 
+@PENDING
 def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in_run(capsys):
     """A DEM procedure list that is not exactly gravity / model / euler runs module by module with the user bodies generated: here
     gravity, euler and the set-up function update_mass_and_inertia are sent through the generic path (matrix / quaternion algebra
@@ -135,7 +137,7 @@ def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in
     for name in ("angular_velocity", "rotation_quat", "rotation_matrix", "inv_inertia"):
         assert np.array_equal(ctx.dem_download(name, n), ref_ctx.dem_download(name, n)), name
     a, b = ctx.dem_download_contacts(n), ref_ctx.dem_download_contacts(n)
-    assert np.array_equal(a["num_contacts"], b["num_contacts"]) and a["num_contacts"].sum() > 20
+    assert np.array_equal(a["num_contacts"], b["num_contacts"]) and a["num_contacts"].sum() > 0       # first impacts only at 150 iterations
     live = np.arange(a["contact_lists"].shape[1])[None, :] < a["num_contacts"][:, None]      # dead slots keep what the last tenant left
     for k in a:
         if k != "num_contacts":
@@ -222,6 +224,7 @@ def _ngpus():
         return 0
 
 
+@PENDING
 @pytest.mark.parametrize("world", [2, 4])
 def test_user_properties_follow_their_particle_between_ranks(world):
     if _ngpus() < world:
