@@ -36,6 +36,10 @@ struct PbJitArgs {
     double *inv_inertia;    //                                    [9][cap]
     double *rotmat;         //                                    [9][cap]
     double *quat;           //                                    [4][cap]
+    const int *particle_cell;   // pair kernels over CELL lists (no neighbour lists built): flat cell of every particle,
+    const int *cell_start;      // CSR over the reference's cells (cell 0 = INFINITE particles),
+    const int *cell_list;       // particle indices in cell order
+    int ncells, dim1, dim2, pad2;
 };
 
 static const char *PB_JIT_PRELUDE = R"PRELUDE(
@@ -59,6 +63,10 @@ struct PbJitArgs {
     double *inv_inertia;
     double *rotmat;
     double *quat;
+    const int *particle_cell;
+    const int *cell_start;
+    const int *cell_list;
+    int ncells, dim1, dim2, pad2;
 };
 #ifndef PB_INFINITY
 #define PB_INFINITY __longlong_as_double(0x7ff0000000000000LL)
@@ -210,7 +218,7 @@ extern "C" int pb_jit_compile(pb_ctx *ctx, const char *source, const char *kerne
 int pb_materialise_force_reset(pb_ctx *ctx);
 
 // kind 0: pair kernel over the neighbour lists (needs current lists; `cutoff` is the interaction cutoff of compute());
-// kind 1: per-particle kernel
+// kind 1: per-particle kernel; kind 2: pair kernel over the cell lists (needs current cell lists)
 extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     PB_CHECK(cudaSetDevice(ctx->device));
     auto *tab = pb_jit_table(ctx);
@@ -221,6 +229,7 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
         if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_jit_launch: neighbour lists are stale"); return -1; }
         if(ctx->lanes != 1 || ctx->half_lists) { ctx->set_error("pb_jit_launch: user pair kernels need full lists, one lane per particle"); return -1; }
     }
+    if(kind == 2 && ctx->cells_n != ctx->nlocal + ctx->nghost) { ctx->set_error("pb_jit_launch: cell lists are stale"); return -1; }
     PB_TRY(pb_materialise_force_reset(ctx));      // a deferred reset_volatile_properties must be visible to user code
     if(ctx->nlocal == 0) { return 0; }
     PbJitArgs a;
@@ -231,6 +240,8 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     a.uid = ctx->uid; a.shape = ctx->shape;
     a.radius = ctx->radius; a.angvel = ctx->angvel; a.torque = ctx->torque;
     a.inv_inertia = ctx->inv_inertia; a.rotmat = ctx->rotmat; a.quat = ctx->quat;
+    a.particle_cell = ctx->particle_cell; a.cell_start = ctx->cell_start; a.cell_list = ctx->cell_list;
+    a.ncells = ctx->ncells; a.dim1 = ctx->dim_cells[1]; a.dim2 = ctx->dim_cells[2]; a.pad2 = 0;
     void *params[] = {&a};
     PB_CHECK(cudaLaunchKernel((const void *) k.kernel, dim3(pb_blocks(ctx->nlocal, 128)), dim3(128), params, 0, ctx->stream));
     ctx->launches++;

@@ -806,9 +806,10 @@ class Simulation:
 
     def _bind(self, ctx, e):
         fam = e["family"]
+        if fam in ("lennard_jones", "lj_legacy") and self.neighbor_cutoff is None:
+            # build_cell_lists() only: the pair kernel walks the cell lists (sim/interaction.py:92-118) -- generated code
+            return self._bind_generic(ctx, dict(e, family="generic_pair"))
         if fam == "lennard_jones":
-            if self.neighbor_cutoff is None:
-                raise DslError("lennard_jones needs build_neighbor_lists()")
             eps_name, sig_name = e["roles"]["epsilon"], e["roles"]["sigma6"]
             for n in (eps_name, sig_name):
                 if n not in self.feature_props:
@@ -820,8 +821,6 @@ class Simulation:
             cutoff = _builtin_float(e["cutoff"])
             return dict(e, call=lambda: ctx.lennard_jones(cutoff), cutoff_value=cutoff)
         if fam == "lj_legacy":
-            if self.neighbor_cutoff is None:
-                raise DslError("lj needs build_neighbor_lists()")
             eps, sig6 = self._symbol(e, "epsilon"), self._symbol(e, "sigma6")
             cutoff = _builtin_float(e["cutoff"])
             return dict(e, call=lambda: ctx.lj_legacy(cutoff, eps, sig6))
@@ -892,17 +891,16 @@ class Simulation:
             nk = self.features[feat]
         try:
             kind, kname, src = kernelgen.translate(e["func"], self._device_storage(), tables, nk, e["symbols"], backend.jit_prelude(),
-                                                   skip_fixed=skip_fixed)
+                                                   skip_fixed=skip_fixed, traversal="lists" if self.neighbor_cutoff is not None else "cells")
         except kernelgen.KernelGenError as err:
             raise DslError(f"kernel '{e['name']}': {err}") from None
         handle = ctx.jit_compile(src, kname)
         if kind == "pair":
-            if self.neighbor_cutoff is None:
-                raise DslError(f"kernel '{e['name']}': pair kernels run over neighbour lists (build_neighbor_lists)")
             if e.get("cutoff") is None:
                 raise DslError(f"kernel '{e['name']}': pair kernels need a cutoff_radius")
             cutoff = _builtin_float(e["cutoff"])
-            return dict(e, call=lambda: ctx.jit_launch(handle, 0, cutoff), source=src)
+            launch_kind = 0 if self.neighbor_cutoff is not None else 2       # over the neighbour lists / over the cell lists
+            return dict(e, call=lambda: ctx.jit_launch(handle, launch_kind, cutoff), source=src)
         return dict(e, call=lambda: ctx.jit_launch(handle, 1), source=src)
 
     def _native_md_params(self, pre, fn):

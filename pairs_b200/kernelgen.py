@@ -626,10 +626,12 @@ class _Gen:
             self.loaded[(store, "i")] = v
 
 
-def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixed=True):
+def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixed=True, traversal="lists"):
     """-> (kind, kernel name, CUDA source).  `storage` maps the user's property names to device arrays.  skip_fixed=False is
     for setup() functions: the reference runs those over every local particle (no FIXED filter, mapping/funcs.py:305-310 applies
-    to compute() only)."""
+    to compute() only).  traversal: pair kernels walk the neighbour lists ("lists") or, for scripts that build cell lists only,
+    cell 0 and the 27 stencil cells of the particle's cell ("cells": sim/interaction.py:92-118, the three z-adjacent cells of a
+    stencil row being one run of the CSR)."""
     src = textwrap.dedent(inspect.getsource(func))
     tree = ast.parse(src).body[0]
     if not isinstance(tree, ast.FunctionDef):
@@ -658,10 +660,25 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
         out += ["    " + ln for ln in g.hoisted]
         for store, acc in g.applied.items():
             out += [f"    double {x} = 0.0;" for x in acc]
-        out.append("    const int nn = a.numneigh[i];")
-        out.append("    const int *nb = a.neigh + (size_t) (i >> 5) * a.nslots * 32 + (i & 31);")
-        out.append("    for(int k = 0; k < nn; k++) {")
-        out.append("        const int j = __ldg(nb + (size_t) k * 32);")
+        if traversal == "cells":
+            out.append("    const int pc = a.particle_cell[i];")
+            out.append("    for(int run = 0; run < 10; run++) {")
+            out.append("    int c_lo = 0, c_hi = 0;")                     # run 0: cell 0 (disp = -1 of the reference's loop)
+            out.append("    if(run > 0) {")
+            out.append("        const int mid = pc + (((run - 1) / 3 - 1) * a.dim1 + ((run - 1) % 3 - 1)) * a.dim2;")
+            out.append("        c_lo = (mid - 1 > 1) ? mid - 1 : 1;")      # 0 < cell < ncells
+            out.append("        c_hi = (mid + 1 < a.ncells - 1) ? mid + 1 : a.ncells - 1;")
+            out.append("        if(c_lo > c_hi) { continue; }")
+            out.append("    }")
+            out.append("    const int k_end = a.cell_start[c_hi + 1];")
+            out.append("    for(int k = a.cell_start[c_lo]; k < k_end; k++) {")
+            out.append("        const int j = __ldg(a.cell_list + k);")
+            out.append("        if(j == i) { continue; }")
+        else:
+            out.append("    const int nn = a.numneigh[i];")
+            out.append("    const int *nb = a.neigh + (size_t) (i >> 5) * a.nslots * 32 + (i & 31);")
+            out.append("    for(int k = 0; k < nn; k++) {")
+            out.append("        const int j = __ldg(nb + (size_t) k * 32);")
         out.append("        const double4 pj = pb_ld_pos(a.pos + j);")
         out.append("        const double dx = pi.x - pj.x;")          # delta(i, j) = position[i] - position[j]
         out.append("        const double dy = pi.y - pj.y;")
@@ -677,6 +694,8 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
         out += ["            " + ln for ln in g.lines]
         out.append("        }")
         out.append("    }")
+        if traversal == "cells":
+            out.append("    }")
         for store, acc in g.applied.items():                          # prop[i] = prop[i] + acc (sim/interaction.py:280-292)
             for d, x in enumerate(acc):
                 if isinstance(store, tuple):

@@ -20,7 +20,7 @@ def final_integrate(i):
     linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
 
 
-def build(target="gpu", nx=8, timesteps=100, reneighbor=20, thermo=10, ntypes=4):
+def build(target="gpu", nx=8, timesteps=100, reneighbor=20, thermo=10, ntypes=4, cells_only=False):
     dt = 0.005
     cutoff_radius = 2.5
     skin = 0.3
@@ -37,7 +37,10 @@ def build(target="gpu", nx=8, timesteps=100, reneighbor=20, thermo=10, ntypes=4)
     psim.set_domain_partitioner(pairs.regular_domain_partitioner())
     psim.compute_thermo(thermo)
     psim.reneighbor_every(reneighbor)
-    psim.build_neighbor_lists(cutoff_radius + skin)
+    if cells_only:          # no Verlet lists: pair kernels walk the cell lists (sim/interaction.py:92-118)
+        psim.build_cell_lists(cutoff_radius + skin)
+    else:
+        psim.build_neighbor_lists(cutoff_radius + skin)
     psim.compute(initial_integrate, symbols={'dt': dt}, pre_step=True, skip_first=True)
     psim.compute(lennard_jones, cutoff_radius)
     psim.compute(final_integrate, symbols={'dt': dt}, skip_first=True)

@@ -266,3 +266,37 @@ def test_dem_script_with_a_user_property_plans_and_compiles():
     _, name, src = kernelgen.translate(odometer, st, {}, 1, {"dt": 5e-5}, backend.jit_prelude())
     assert "a.xdata[0 * (size_t) a.cap + i] =" in src and "a.xdata[1 * (size_t) a.cap + i] = (double)" in src
     assert backend.jit_check(src) > 1000
+
+
+def test_md_script_with_cell_lists_only_plans_generated_pair_kernels():
+    """build_cell_lists() without build_neighbor_lists(): the recognised lennard_jones is generated with the cell-list traversal."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import lj_script
+    psim = lj_script.build("gpu", 8, 10, 20, 1, cells_only=True)
+    assert psim.neighbor_cutoff is None and psim.cell_spacing() == 2.5 + 0.3
+
+    class Ctx:                                   # records what would be compiled / launched
+        def __init__(self):
+            self.compiled, self.launched = [], []
+
+        def jit_compile(self, src, name):
+            self.compiled.append((name, src))
+            return len(self.compiled) - 1
+
+        def jit_launch(self, handle, kind, cutoff=0.0):
+            self.launched.append((handle, kind, cutoff))
+
+        def initial_integrate(self, dt):
+            pass
+
+        def final_integrate(self, dt):
+            pass
+
+    ctx = Ctx()
+    plan = [psim._bind(ctx, e) for e in psim.pre_step + psim.functions]
+    assert [p["family"] for p in plan] == ["initial_integrate", "generic_pair", "final_integrate"]
+    assert psim._native_md_params(plan[:1], plan[1:]) is None
+    name, src = ctx.compiled[0]
+    assert name == "user_lennard_jones" and "a.cell_start[c_lo]" in src
+    plan[1]["call"]()
+    assert ctx.launched == [(0, 2, 2.5)]

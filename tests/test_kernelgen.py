@@ -152,7 +152,8 @@ def test_if_statements_and_local_updates():
 def _host_kernel(tmp_path, name, src):
     """Compiles a generated kernel for the HOST (tests/host/jit_host_emulation.h stands in for the CUDA bits) together with a
     driver that runs it for every particle; returns run(n, nslots, cap, cutsq, pos4, vel, force, mass, flags, numneigh, neigh,
-    xdata=None, uid=None, shape=None, radius=None, angvel=None, torque=None, inv_inertia=None, rotmat=None, quat=None) taking array addresses."""
+    xdata=None, uid=None, shape=None, radius=None, angvel=None, torque=None, inv_inertia=None, rotmat=None, quat=None, cells=None) taking array addresses (cells = (particle_cell, cell_start, cell_list, ncells, dim1,
+    dim2) for pair kernels over cell lists)."""
     import ctypes
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
@@ -160,11 +161,13 @@ def _host_kernel(tmp_path, name, src):
     cpp.write_text('#include "jit_host_emulation.h"\n' + src + f'''
 extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, double *vel, double *force, double *mass, int *flags,
                     int *numneigh, int *neigh, double *xdata, int *uid, int *shape, double *radius, double *angvel, double *torque,
-                    double *inv_inertia, double *rotmat, double *quat) {{
+                    double *inv_inertia, double *rotmat, double *quat, int *particle_cell, int *cell_start, int *cell_list, int ncells, int dim1,
+                    int dim2) {{
     PbJitArgs a;
     a.nlocal = n; a.nslots = nslots; a.cap = cap; a.pad = 0; a.cutsq = cutsq; a.pos = pos; a.pos_w = pos; a.vel = vel; a.force = force;
     a.mass = mass; a.flags = flags; a.numneigh = numneigh; a.neigh = neigh; a.xdata = xdata; a.uid = uid; a.shape = shape; a.radius = radius; a.angvel = angvel; a.torque = torque;
     a.inv_inertia = inv_inertia; a.rotmat = rotmat; a.quat = quat;
+    a.particle_cell = particle_cell; a.cell_start = cell_start; a.cell_list = cell_list; a.ncells = ncells; a.dim1 = dim1; a.dim2 = dim2;
     blockDim.x = 128;
     for(int i = 0; i < n; i++) {{ blockIdx.x = i / 128; threadIdx.x = i % 128; {name}(a); }}
 }}
@@ -174,12 +177,13 @@ extern "C" void run(int n, int nslots, int cap, double cutsq, double4 *pos, doub
                    check=True)
     lib = ctypes.CDLL(str(so))
     P = ctypes.c_void_p
-    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [P] * 16
+    lib.run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [P] * 19 + [ctypes.c_int] * 3
 
     def run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata=None, uid=None, shape=None, radius=None, angvel=None,
-            torque=None, inv_inertia=None, rotmat=None, quat=None):
+            torque=None, inv_inertia=None, rotmat=None, quat=None, cells=None):
+        particle_cell, cell_start, cell_list, ncells, dim1, dim2 = cells if cells is not None else (None, None, None, 0, 0, 0)
         lib.run(n, nslots, cap, cutsq, pos, vel, force, mass, flags, numneigh, neigh, xdata, uid, shape, radius, angvel, torque, inv_inertia,
-                rotmat, quat)
+                rotmat, quat, particle_cell, cell_start, cell_list, ncells, dim1, dim2)
     return run
 
 
@@ -665,3 +669,46 @@ def test_generated_dem_integrator_and_setup_equal_dem_math_on_the_host(tmp_path)
         assert np.array_equal(pos4[:, :3], pos) and np.array_equal(vel_g.T, vel) and np.array_equal(w_g.T, w)
         assert np.array_equal(q_g2.T, q) and np.array_equal(R_g2.T, R)
     assert np.abs(q[1] - [1.0, 0.0, 0.0, 0.0]).max() > 1e-4 and np.array_equal(q[0], [1.0, 0.0, 0.0, 0.0])     # rotated / FIXED
+
+
+def test_generated_pair_kernel_over_cell_lists_on_the_host(tmp_path):
+    """A script that builds cell lists only (build_cell_lists, no build_neighbor_lists) has its pair kernels walk cell 0 and the 27
+    stencil cells of the particle's cell (sim/interaction.py:92-118).  md.py's lennard_jones generated with traversal="cells",
+    compiled for the host and run on the oracle's cell lists (as a CSR, in the oracle's in-cell order): the same pairs pass the
+    cutoff as through the oracle's neighbour lists, met in the same order -- identical bits."""
+    import numpy as np
+    import lj_script
+    from oracle import port
+    nx = 6
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    r = sim.ranks[0]
+    rng = np.random.default_rng(5)
+    n = r.nlocal
+    r.real("position", n, view=True)[:] += 0.05 * (rng.random((n, 3)) - 0.5)
+    sim.step(0)
+    tot = n + r.nghost
+    ncells, ccap = r.ncells, r.cell_capacity
+    sizes = r.ints("cell_sizes", ncells)
+    cp = r.ints("cell_particles", ncells * ccap).reshape(ncells, ccap)
+    cell_start = np.zeros(ncells + 1, np.int32)
+    cell_start[1:] = np.cumsum(sizes)
+    cell_list = np.concatenate([cp[c, :sizes[c]] for c in range(ncells)]).astype(np.int32)
+    assert len(cell_list) == tot and sizes[0] == 0
+    particle_cell = r.ints("particle_cell", tot).copy()
+    dc = r.decomposition()["dim_cells"]
+    psim = lj_script.build("gpu", nx, 10, 20, 1)
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    _, name, code = kernelgen.translate(lj_script.lennard_jones, psim._device_storage(), tables, 4, {}, backend.jit_prelude(), traversal="cells")
+    assert "a.cell_start[c_lo]" in code and "a.numneigh" not in code.split('extern "C"')[1] and backend.jit_check(code) > 1000
+    run = _host_kernel(tmp_path, name, code)
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = r.real("position", tot)
+    pos4[:, 3] = r.ints("type", tot).astype(np.int64).view(np.float64)
+    vel, mass, flags = np.zeros((3, tot)), np.ones(tot), r.ints("flags", tot).copy()
+    force = np.zeros((3, tot))
+    run(n, 0, tot, 2.5 * 2.5, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), None, None,
+        cells=(_ptr(particle_cell), _ptr(cell_start), _ptr(cell_list), ncells, int(dc[1]), int(dc[2])))
+    f_oracle = r.real("force")
+    assert np.abs(f_oracle).max() > 1.0
+    assert np.abs(force[:, :n].T - f_oracle).max() <= 1e-13 * np.abs(f_oracle).max()
+    assert np.array_equal(force[:, :n].T, f_oracle)
