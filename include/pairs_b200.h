@@ -205,7 +205,8 @@ int pb_jit_set_dem_model(pb_ctx *ctx, const char *model_source, const char *mode
 /* Options.  Behaviour: "compute_half" (0/1) = Simulation.compute_half() (sim/simulation.py:119-120): half neighbour lists,
  * pair terms applied to both partners (ir/apply.py:111-125); applies from the next neighbour-list build.
  * Tuning knobs: "lanes_per_particle" (1,2,4,8; applies from the next build), "lj_unroll" (2,4,8), "fuse_integrate" (0/1),
- * "overlap_comm" (0/1), "cell_zsub" (1..32, applies from the next pb_setup_cells), "stage_lists" (0/1), "dem_sort_every"
+ * "overlap_comm" (0/1), "profiler" (0/1: every stage also opens an NVTX range named like the reference's timers -- Simulation.enable_profiler(),
+ * sim/simulation.py:116-117, LIKWID markers there), "cell_zsub" (1..32, applies from the next pb_setup_cells), "stage_lists" (0/1), "dem_sort_every"
  * (DEM: iterations between two spatial re-sorts of the locals, 0 = never, default 200), "dem_fuse" (0/1: pb_dem_run folds the
  * per-particle modules around the contact evaluation into the contact kernel; results are identical). */
 int pb_set_option(pb_ctx *ctx, const char *name, int value);

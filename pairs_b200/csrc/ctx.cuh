@@ -12,6 +12,7 @@
 //   neigh  int[ncap][pitch]   padded column-major (ELLPACK) neighbour lists, pitch = nlocal rounded to 32
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <algorithm>
 #include <cstdio>
@@ -170,6 +171,7 @@ struct pb_ctx {
 
     // ---- timers: CUDA events on the launching stream, collected lazily (pb_timers_get) ----
     bool timers_on = false;
+    bool nvtx = false;            // option "profiler": every stage is also an NVTX range (what enable_profiler()'s LIKWID markers are in the reference)
     std::map<std::string, PbTimer> timers;
     std::vector<cudaEvent_t> event_pool;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // pb_stream_timer_start / stop
@@ -236,10 +238,13 @@ struct PbStage {
     pb_ctx *ctx;
     const char *name;
     cudaEvent_t a = nullptr;
+    bool ranged = false;
     PbStage(pb_ctx *c, const char *n) : ctx(c), name(n) {
+        if(ctx->nvtx) { nvtxRangePushA(n); ranged = true; }
         if(ctx->timers_on) { a = ctx->get_event(); cudaEventRecord(a, ctx->stream); }
     }
     ~PbStage() {
+        if(ranged) { nvtxRangePop(); }
         if(a != nullptr) {
             cudaEvent_t b = ctx->get_event();
             cudaEventRecord(b, ctx->stream);

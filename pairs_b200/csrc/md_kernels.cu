@@ -403,6 +403,7 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
         return 0;
     }
     if(nm == "stage_lists") { ctx->stage_lists = value != 0; return 0; }
+    if(nm == "profiler") { ctx->nvtx = value != 0; return 0; }
     if(nm == "dem_fuse") { ctx->dem_fuse = value != 0; return 0; }
     if(nm == "dem_sort_every") {
         if(value < 0) { ctx->set_error("dem_sort_every must be >= 0"); return -1; }

@@ -303,7 +303,7 @@ class Simulation:
     # -- queries of the reference's Simulation object (sim/simulation.py:116-128, 159-201, 373-377) --
     def enable_profiler(self):
         """sim/simulation.py:116-117 switches on LIKWID marker regions around compute() kernels; here every stage is always
-        bracketed by CUDA-event timers (ctx.timer(name)), so the call only records the request."""
+        bracketed by CUDA-event timers (ctx.timer(name)) and, with this call, also by an NVTX range of the same name."""
         self._enable_profiler = True
 
     def use_double_precision(self):
@@ -504,6 +504,8 @@ class Simulation:
         ctx = backend.Context(local)
         self.ctx = ctx
         ctx.init_domain(grid, self._pbc, self._partitioner, world, rank)
+        if getattr(self, "_enable_profiler", False):
+            ctx.set_option("profiler", 1)
         if world > 1:
             ctx.nccl_init(_broadcast_nccl_id(backend, rank, world))
         if self._cell_spacing is None:
