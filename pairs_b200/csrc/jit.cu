@@ -218,16 +218,21 @@ extern "C" int pb_jit_compile(pb_ctx *ctx, const char *source, const char *kerne
 int pb_materialise_force_reset(pb_ctx *ctx);
 
 // kind 0: pair kernel over the neighbour lists (needs current lists; `cutoff` is the interaction cutoff of compute());
-// kind 1: per-particle kernel; kind 2: pair kernel over the cell lists (needs current cell lists)
+// kind 1: per-particle kernel; kind 2: pair kernel over the cell lists (needs current cell lists);
+// kind 3: pair kernel generated for compute_half() over half neighbour lists
 extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     PB_CHECK(cudaSetDevice(ctx->device));
     auto *tab = pb_jit_table(ctx);
     if(handle < 0 || handle >= (int) tab->size()) { ctx->set_error("pb_jit_launch: bad kernel handle"); return -1; }
     PbJitKernel &k = (*tab)[handle];
     PbStage st(ctx, k.name.c_str());
-    if(kind == 0) {
+    if(kind == 0 || kind == 3) {
         if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_jit_launch: neighbour lists are stale"); return -1; }
-        if(ctx->lanes != 1 || ctx->half_lists) { ctx->set_error("pb_jit_launch: user pair kernels need full lists, one lane per particle"); return -1; }
+        if(ctx->lanes != 1) { ctx->set_error("pb_jit_launch: user pair kernels need one lane per particle"); return -1; }
+        if(ctx->half_lists != (kind == 3)) {
+            ctx->set_error("pb_jit_launch: the kernel was generated for the other kind of neighbour lists (compute_half)");
+            return -1;
+        }
     }
     if(kind == 2 && ctx->cells_n != ctx->nlocal + ctx->nghost) { ctx->set_error("pb_jit_launch: cell lists are stale"); return -1; }
     PB_TRY(pb_materialise_force_reset(ctx));      // a deferred reset_volatile_properties must be visible to user code

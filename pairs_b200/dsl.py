@@ -884,8 +884,8 @@ class Simulation:
 
     def _bind_generic(self, ctx, e, skip_fixed=True):
         from . import backend, kernelgen
-        if self._compute_half:
-            raise DslError("compute_half() is available for the built-in lennard_jones kernel only")
+        if self._compute_half and self.neighbor_cutoff is None:
+            raise DslError("compute_half() needs neighbour lists (build_neighbor_lists)")
         nk = 1
         tables = {}
         for name, (feat, data) in self.feature_props.items():
@@ -893,7 +893,8 @@ class Simulation:
             nk = self.features[feat]
         try:
             kind, kname, src = kernelgen.translate(e["func"], self._device_storage(), tables, nk, e["symbols"], backend.jit_prelude(),
-                                                   skip_fixed=skip_fixed, traversal="lists" if self.neighbor_cutoff is not None else "cells")
+                                                   skip_fixed=skip_fixed, traversal="lists" if self.neighbor_cutoff is not None else "cells",
+                                                   half=self._compute_half)
         except kernelgen.KernelGenError as err:
             raise DslError(f"kernel '{e['name']}': {err}") from None
         handle = ctx.jit_compile(src, kname)
@@ -901,7 +902,8 @@ class Simulation:
             if e.get("cutoff") is None:
                 raise DslError(f"kernel '{e['name']}': pair kernels need a cutoff_radius")
             cutoff = _builtin_float(e["cutoff"])
-            launch_kind = 0 if self.neighbor_cutoff is not None else 2       # over the neighbour lists / over the cell lists
+            # over the neighbour lists (full / half: compute_half()) or over the cell lists
+            launch_kind = (3 if self._compute_half else 0) if self.neighbor_cutoff is not None else 2
             return dict(e, call=lambda: ctx.jit_launch(handle, launch_kind, cutoff), source=src)
         return dict(e, call=lambda: ctx.jit_launch(handle, 1), source=src)
 

@@ -529,6 +529,12 @@ class _Gen:
             acc = self.applied.setdefault(store, [f"acc_{_store_tag(store)}_{d}" for d in range(len(comps))])
             for a, c in zip(acc, comps):
                 self.lines.append(f"{a} = {a} + {c};")
+            if getattr(self, "half", False):              # Newton's third law: the partner gets the opposite term (ir/apply.py:111-125)
+                self.lines.append("if(j < a.nlocal && (a.flags[j] & PB_FLAG_FIXED) == 0) {")
+                for d, c in enumerate(comps):
+                    ref = _xref(store, d, "j") if isinstance(store, tuple) else (f"a.{store}[{d} * (size_t) a.cap + j]" if d else f"a.{store}[j]")
+                    self.lines.append(f"    atomicAdd(&{ref}, -({c}));")
+                self.lines.append("}")
             return
         if self.kind == "dem" and isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Subscript) \
                 and isinstance(node.targets[0].value, ast.Name) and node.targets[0].value.id in self.contact:
@@ -626,12 +632,14 @@ class _Gen:
             self.loaded[(store, "i")] = v
 
 
-def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixed=True, traversal="lists"):
+def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixed=True, traversal="lists", half=False):
     """-> (kind, kernel name, CUDA source).  `storage` maps the user's property names to device arrays.  skip_fixed=False is
     for setup() functions: the reference runs those over every local particle (no FIXED filter, mapping/funcs.py:305-310 applies
     to compute() only).  traversal: pair kernels walk the neighbour lists ("lists") or, for scripts that build cell lists only,
     cell 0 and the 27 stencil cells of the particle's cell ("cells": sim/interaction.py:92-118, the three z-adjacent cells of a
-    stencil row being one run of the CSR)."""
+    stencil row being one run of the CSR).  half=True is Simulation.compute_half(): the lists hold every pair once and apply()
+    also subtracts the term from the partner with an atomic add unless it is a ghost or FIXED (ir/apply.py:111-125; the own
+    particle's sum is added atomically too, other threads may be updating it)."""
     src = textwrap.dedent(inspect.getsource(func))
     tree = ast.parse(src).body[0]
     if not isinstance(tree, ast.FunctionDef):
@@ -645,6 +653,9 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
         raise KernelGenError(f"{func.__name__}: kernels take (i) or (i, j)")
     name = f"user_{func.__name__}"
     g = _Gen(name, kind, storage, feature_tables, ntypes, symbols, func.__globals__)
+    g.half = bool(half) and kind == "pair"
+    if half and traversal != "lists":
+        raise KernelGenError("compute_half() needs neighbour lists")
     for node in tree.body:
         g.stmt(node)
     out = [prelude]
@@ -702,7 +713,7 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
                     ref = _xref(store, d, "i")
                 else:
                     ref = f"a.{store}[{d} * (size_t) a.cap + i]" if d else f"a.{store}[i]"
-                out.append(f"    {ref} = {ref} + {x};")
+                out.append(f"    atomicAdd(&{ref}, {x});" if g.half else f"    {ref} = {ref} + {x};")
     else:
         out.append("    double4 pi = a.pos_w[i];")
         out.append("    double *a_mass_w = const_cast<double *>(a.mass);")

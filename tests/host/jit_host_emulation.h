@@ -11,6 +11,7 @@ struct double4 { double x, y, z, w; };
 struct PbHostIdx { int x; };
 static PbHostIdx blockIdx, blockDim, threadIdx;
 #define PB_INFINITY INFINITY
+static inline double atomicAdd(double *p, double v) { const double old = *p; *p = old + v; return old; }     // one "thread" at a time
 #define __global__
 #define __device__
 #define __forceinline__ inline

@@ -300,3 +300,16 @@ def test_md_script_with_cell_lists_only_plans_generated_pair_kernels():
     assert name == "user_lennard_jones" and "a.cell_start[c_lo]" in src
     plan[1]["call"]()
     assert ctx.launched == [(0, 2, 2.5)]
+    # compute_half() with a generated pair kernel: half-list variant (launch kind 3), needs neighbour lists
+    dsl.FORCE_GENERIC_NAMES = {"lennard_jones"}
+    try:
+        half = lj_script.build("gpu", 8, 10, 20, 1)
+    finally:
+        dsl.FORCE_GENERIC_NAMES = set()
+    half.compute_half()
+    ctx2 = Ctx()
+    half._bind(ctx2, half.functions[0])["call"]()
+    assert ctx2.launched == [(0, 3, 2.5)] and "atomicAdd(&a.force[j]" in ctx2.compiled[0][1]
+    psim.compute_half()
+    with pytest.raises(dsl.DslError, match="needs neighbour lists"):
+        psim._bind(Ctx(), psim.functions[0])

@@ -194,6 +194,34 @@ def test_md_script_with_cell_lists_only_matches_the_neighbour_list_run(capsys):
     assert rel_err_force(f_b, f_a) <= 1e-12
 
 
+@PENDING
+def test_generated_pair_kernel_with_compute_half_matches_the_built_in_half_kernel(capsys):
+    """compute_half() with the pair kernel generated (every pair once, atomic update of the partner): thermo of 40 iterations to 1e-9
+    and the forces of iteration 1 to 1e-12 against the hand-written half-list kernel, which is pinned to the reference run with
+    compute_half() enabled (tests/golden/md_half_t1.npz)."""
+    import lj_script
+    from pairs_b200 import dsl
+    runs = {}
+    for generic in (False, True):
+        out = []
+        for steps in (40, 1):
+            dsl.FORCE_GENERIC_NAMES = {"lennard_jones"} if generic else set()
+            try:
+                psim = lj_script.build("gpu", 8, steps, 20, 1)
+            finally:
+                dsl.FORCE_GENERIC_NAMES = set()
+            psim.compute_half()
+            assert psim.functions[0]["family"] == ("generic_pair" if generic else "lennard_jones")
+            out.append((psim, psim.generate()))
+        runs[generic] = (out[0][0].thermo_log, by_id(out[1][1].ints("tag"), out[1][1].real("force")), out[0][1].ints("numneighs").mean())
+    capsys.readouterr()
+    (th_a, f_a, nn_a), (th_b, f_b, nn_b) = runs[False], runs[True]
+    assert len(th_a) == len(th_b) == 41 and nn_a == nn_b and nn_a < 60
+    for (ts, t, p), (_, t2, p2) in zip(th_a, th_b):
+        assert abs(t - t2) <= 1e-9 * t and abs(p - p2) <= 1e-9 * abs(p), ts
+    assert rel_err_force(f_b, f_a) <= 1e-12
+
+
 def test_property_store_through_the_c_abi(capsys):
     """add / upload / download, defaults, capacity growth, ghosts carrying their source's values, volatile reset, the cell-order
     sort -- without any generated kernel."""

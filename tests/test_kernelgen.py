@@ -712,3 +712,46 @@ def test_generated_pair_kernel_over_cell_lists_on_the_host(tmp_path):
     assert np.abs(f_oracle).max() > 1.0
     assert np.abs(force[:, :n].T - f_oracle).max() <= 1e-13 * np.abs(f_oracle).max()
     assert np.array_equal(force[:, :n].T, f_oracle)
+
+
+def test_generated_pair_kernel_for_half_lists_on_the_host(tmp_path):
+    """compute_half() with a generated pair kernel: every pair once, the partner gets the opposite term by an atomic add unless it
+    is a ghost or FIXED (ir/apply.py:111-125).  Run one "thread" after the other on the oracle's half lists this is exactly the
+    serial order of the reference's generated code -- identical bits with the oracle's force (the restatement of the reference run
+    with compute_half() enabled, pinned by tests/test_oracle_pin.py)."""
+    import numpy as np
+    import lj_script
+    from oracle import port
+    nx = 6
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    sim.compute_half(True)
+    r = sim.ranks[0]
+    rng = np.random.default_rng(6)
+    n = r.nlocal
+    r.real("position", n, view=True)[:] += 0.05 * (rng.random((n, 3)) - 0.5)
+    r.ints("flags", n, view=True)[::19] |= 4              # some FIXED particles: no own sum, no partner update
+    sim.step(0)
+    tot = n + r.nghost
+    nn, nl = r.neighbor_sets()
+    assert nn.mean() < 60                                  # half lists (full ones hold ~76; pairs with ghosts stay at the local end)
+    psim = lj_script.build("gpu", nx, 10, 20, 1)
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    _, name, code = kernelgen.translate(lj_script.lennard_jones, psim._device_storage(), tables, 4, {}, backend.jit_prelude(), half=True)
+    assert code.count("atomicAdd(") == 6 and "j < a.nlocal" in code and backend.jit_check(code) > 1000
+    run = _host_kernel(tmp_path, name, code)
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = r.real("position", tot)
+    pos4[:, 3] = r.ints("type", tot).astype(np.int64).view(np.float64)
+    vel, mass, flags = np.zeros((3, tot)), np.ones(tot), r.ints("flags", tot).copy()
+    nslots = int(nn.max())
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    for i in range(n):
+        neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
+    numneigh = np.zeros(tot, np.int32)
+    numneigh[:n] = nn
+    force = np.zeros((3, tot))
+    run(n, nslots, tot, 2.5 * 2.5, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
+    f_oracle = r.real("force")
+    fixed = (flags[:n] & 4) != 0
+    assert np.abs(f_oracle).max() > 1.0 and fixed.sum() > 20 and not f_oracle[fixed].any() and not force[:, n:].any()
+    assert np.array_equal(force[:, :n].T, f_oracle)
