@@ -235,6 +235,9 @@ def _unify_body(tb, ub, binding):
 
 
 # ---- the Simulation object ----------------------------------------------------------------------------------------------
+_CSV_WIDTH = {Types.Vector: 3, Types.Matrix: 9, Types.Quaternion: 4}      # columns per property, runtime/read_from_file.hpp:48-104
+
+
 class _Prop:
     def __init__(self, name, ptype, value, volatile):
         self.name, self.type, self.value, self.volatile = name, ptype, value, volatile
@@ -787,7 +790,8 @@ class Simulation:
         print(f"Number of particles: {count}")
 
     def _read_csv(self, filename, prop_names, shape_id):
-        """runtime/read_from_file.hpp:33-115 -> dict of host arrays (vectors = 3 columns, in the order of prop_names)."""
+        """runtime/read_from_file.hpp:33-115 -> dict of host arrays (vectors = 3 columns, matrices 9, quaternions 4, in the order of
+        prop_names)."""
         path = filename
         if not os.path.exists(path):
             alt = os.path.join(os.path.dirname(os.path.abspath(sys.argv[0])), "..", filename)
@@ -797,7 +801,7 @@ class Simulation:
         data = np.loadtxt(path, delimiter=",", ndmin=2)
         out, k = {}, 0
         for nme in prop_names:
-            w = 3 if self.props[nme].type == Types.Vector else 1
+            w = _CSV_WIDTH.get(self.props[nme].type, 1)
             col = data[:, k:k + w] if w > 1 else data[:, k]
             out[nme] = col.astype(np.int32) if self.props[nme].type == Types.Int32 else col
             k += w
@@ -973,7 +977,7 @@ class Simulation:
                 raise DslError(f"read_particle_data: {filename} not found")
         cols = []
         for n in prop_names:
-            w = 3 if self.props[n].type == Types.Vector else 1
+            w = _CSV_WIDTH.get(self.props[n].type, 1)
             cols.append((n, w))
         data = np.loadtxt(path, delimiter=",", ndmin=2)
         k = 0

@@ -554,6 +554,14 @@ class _Gen:
             else:
                 self.lines.append(f"*sticking = (int) ({v[1]});")
             return
+        if self.kind == "pair" and isinstance(node, ast.AugAssign) and isinstance(node.op, (ast.Add, ast.Sub)) \
+                and isinstance(node.target, ast.Subscript) and isinstance(node.target.value, ast.Name) \
+                and getattr(node.target.slice, "id", None) == "i":
+            # the older API of examples/lj_onetype.py writes `force[i] += expr` inside the pair kernel: the same accumulation as
+            # apply(force, expr)
+            value = node.value if isinstance(node.op, ast.Add) else ast.UnaryOp(op=ast.USub(), operand=node.value)
+            call = ast.Call(func=ast.Name(id="apply", ctx=ast.Load()), args=[ast.Name(id=node.target.value.id, ctx=ast.Load()), value], keywords=[])
+            return self.stmt(ast.Expr(value=call))
         if self.kind == "particle" and isinstance(node, (ast.Assign, ast.AugAssign)):
             tgt = node.targets[0] if isinstance(node, ast.Assign) else node.target
             if isinstance(tgt, ast.Subscript) and isinstance(tgt.value, ast.Subscript) and isinstance(tgt.slice, ast.Constant) \

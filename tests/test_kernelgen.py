@@ -89,6 +89,22 @@ def test_vocabulary_translates_and_compiles():
     assert backend.jit_check(src) > 1000
 
 
+def test_legacy_accumulation_in_a_pair_kernel_is_apply():
+    """`force[i] += expr` inside a pair kernel (the older API of examples/lj_onetype.py) generates what apply(force, expr) does."""
+    def new_style(i, j):
+        sr2 = 1.0 / squared_distance(i, j)
+        apply(force, delta(i, j) * (k * sr2))
+
+    def old_style(i, j):
+        sr2 = 1.0 / rsq
+        force[i] += delta * (k * sr2)
+
+    storage = {"position": "pos", "linear_velocity": "vel", "force": "force", "mass": "mass"}
+    a = kernelgen.translate(new_style, storage, {}, 1, {"k": 2.0}, "")[2].replace("user_new_style", "K")
+    b = kernelgen.translate(old_style, storage, {}, 1, {"k": 2.0}, "")[2].replace("user_old_style", "K")
+    assert a == b and "acc_force_2 = acc_force_2 +" in a
+
+
 def test_unsupported_constructs_are_rejected_with_a_reason():
     storage = {"position": "pos", "force": "force", "linear_velocity": "vel", "mass": "mass"}
 
