@@ -250,9 +250,9 @@ class _Gen:
             if op != "*":
                 raise KernelGenError("scalar op vector: only * is defined")
             return self.vec([self.tmp("double", f"{a[1]} {op} {y}") for y in b[1]])
-        t = "i" if (a[0] == "i" and b[0] == "i" and op != "/") else "f"
-        if a[0] == "i" and b[0] == "i" and op == "/":
-            return ("f", self.tmp("double", f"(double) {a[1]} / (double) {b[1]}"))      # Python true division
+        # two integers stay an integer, `/` included: the reference types the operation by its operands (ir/scalars.py:66-91) and
+        # prints C, so 7 / 2 is 3 there -- not Python's 3.5
+        t = "i" if (a[0] == "i" and b[0] == "i") else "f"
         return (t, self.tmp("double" if t == "f" else "int", f"{a[1]} {op} {b[1]}"))
 
     def name_value(self, name):

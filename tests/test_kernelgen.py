@@ -89,6 +89,15 @@ def test_vocabulary_translates_and_compiles():
     assert backend.jit_check(src) > 1000
 
 
+def test_integer_division_is_c_division_as_in_the_reference():
+    """ir/scalars.py:66-91 types an operation by its operands and the generator prints C: int / int truncates."""
+    def k(i):
+        mass[i] = mass[i] * (7 / 2) + (uid[i] / 2) * 1.0 + 7.0 / 2
+
+    src = kernelgen.translate(k, {"mass": "mass", "uid": "uid"}, {}, 1, {}, "")[2]
+    assert "const int t2 = 7 / 2;" in src and "7.0 / 2" in src and "(double)" not in src
+
+
 def test_legacy_accumulation_in_a_pair_kernel_is_apply():
     """`force[i] += expr` inside a pair kernel (the older API of examples/lj_onetype.py) generates what apply(force, expr) does."""
     def new_style(i, j):
