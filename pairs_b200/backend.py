@@ -542,7 +542,8 @@ def jit_prelude():
 def jit_check_dem_model(model_source, model_name):
     """Compile-only check of the DEM contact kernel built around a generated contact model (no GPU needed)."""
     log = ctypes.create_string_buffer(16384)
-    n = load().pb_jit_check_dem_model(model_source.encode(), model_name.encode(), log, len(log))
+    n = load().pb_jit_check_dem_model(None if model_source is None else model_source.encode(),
+                                      None if model_name is None else model_name.encode(), log, len(log))
     if n < 0:
         raise BackendError(log.value.decode(errors="replace"))
     return n

@@ -161,6 +161,7 @@ struct pb_ctx {
     int *sel_flag = nullptr, *sel_scan = nullptr; // [pcap+1] compaction scratch
     void *jit = nullptr;          // table of NVRTC-compiled user kernels (jit.cu)
     void *dem_user_force = nullptr;   // DEM contact kernel built around a user-defined contact model (jit.cu), null = examples/dem.py's
+    int dem_force_maxreg = 0;         // tuning option "dem_force_maxreg": > 0 re-builds the contact kernel at run time with this register cap
     void *nccl = nullptr;         // NcclState* (comm_nccl.cu), null on a single rank
 
     // ---- reductions / host mirrors ----

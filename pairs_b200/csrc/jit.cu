@@ -135,13 +135,16 @@ static bool pb_nvrtc_load(std::string *err) {
 }
 
 // source -> sm_100a cubin; returns false with the compiler log in *err
-static bool pb_nvrtc_compile(const char *source, std::vector<char> *cubin, std::string *err) {
+static bool pb_nvrtc_compile(const char *source, std::vector<char> *cubin, std::string *err, int maxreg = 0) {
     if(!pb_nvrtc_load(err)) { return false; }
     nvrtcProgram prog;
     nvrtcResult r = g_rtc.CreateProgram(&prog, source, "pairs_user_kernel.cu", 0, nullptr, nullptr);
     if(r != NVRTC_SUCCESS) { *err = std::string("nvrtcCreateProgram: ") + g_rtc.GetErrorString(r); return false; }
-    const char *opts[] = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo", "-DPB_HAVE_LD256"};
-    r = g_rtc.CompileProgram(prog, g_rtc.ld256 ? 5 : 4, opts);
+    const std::string reg_opt = "--maxrregcount=" + std::to_string(maxreg);
+    std::vector<const char *> opts = {"--gpu-architecture=sm_100a", "--fmad=false", "--std=c++17", "-lineinfo"};
+    if(g_rtc.ld256) { opts.push_back("-DPB_HAVE_LD256"); }
+    if(maxreg > 0) { opts.push_back(reg_opt.c_str()); }      // tuning: register cap of a re-built kernel (option "dem_force_maxreg")
+    r = g_rtc.CompileProgram(prog, (int) opts.size(), opts.data());
     if(r != NVRTC_SUCCESS) {
         size_t n = 0;
         g_rtc.GetProgramLogSize(prog, &n);
@@ -272,10 +275,12 @@ static std::string pb_dem_user_source(const char *model_source, const char *mode
     std::string src = PB_JIT_PRELUDE;
     src += PB_SRC_DEM_MATH;
     src += "\n";
-    src += model_source;
-    src += "\n#define PB_DEM_USER_PAIR ";
-    src += model_name;
-    src += "\n";
+    if(model_source != nullptr) {           // null: the contact model of examples/dem.py (pb_dem_pair_force), re-built at run time
+        src += model_source;
+        src += "\n#define PB_DEM_USER_PAIR ";
+        src += model_name;
+        src += "\n";
+    }
     src += PB_SRC_DEM_FORCE_KERNEL;
     src += PB_DEM_USER_WRAPPERS;
     return src;
@@ -297,10 +302,10 @@ extern "C" int pb_jit_set_dem_model(pb_ctx *ctx, const char *model_source, const
         delete old;
         ctx->dem_user_force = nullptr;
     }
-    if(model_source == nullptr) { return 0; }
+    if(model_source == nullptr && ctx->dem_force_maxreg <= 0) { return 0; }
     std::vector<char> cubin;
     std::string err;
-    if(!pb_nvrtc_compile(pb_dem_user_source(model_source, model_name).c_str(), &cubin, &err)) { ctx->set_error(err); return -1; }
+    if(!pb_nvrtc_compile(pb_dem_user_source(model_source, model_name).c_str(), &cubin, &err, ctx->dem_force_maxreg)) { ctx->set_error(err); return -1; }
     PbDemUserForce u;
     PB_CHECK(cudaLibraryLoadData(&u.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     cudaError_t e = cudaLibraryGetKernel(&u.staged, u.lib, "pb_user_dem_force_staged");

@@ -404,6 +404,11 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
     }
     if(nm == "stage_lists") { ctx->stage_lists = value != 0; return 0; }
     if(nm == "profiler") { ctx->nvtx = value != 0; return 0; }
+    if(nm == "dem_force_maxreg") {       // occupancy experiments: NVRTC re-build of the contact kernel (built-in model) with a register cap
+        if(value < 0 || value > 255) { ctx->set_error("dem_force_maxreg: 0 (off) .. 255"); return -1; }
+        ctx->dem_force_maxreg = value;
+        return pb_jit_set_dem_model(ctx, nullptr, nullptr);
+    }
     if(nm == "dem_fuse") { ctx->dem_fuse = value != 0; return 0; }
     if(nm == "dem_sort_every") {
         if(value < 0) { ctx->set_error("dem_sort_every must be >= 0"); return -1; }

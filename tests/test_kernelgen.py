@@ -559,6 +559,7 @@ def test_generated_dem_contact_model_equals_the_hand_written_one_bit_for_bit(tmp
     bad, fmax = run(20000, 7)
     assert bad == 0 and fmax > 0.1
     assert backend.jit_check_dem_model(code, name) > 10000          # prelude + dem_math.h + model + dem_force_kernel.cuh, both variants
+    assert backend.jit_check_dem_model(None, None) > 10000          # the same kernel around the hand-written model (option "dem_force_maxreg")
 
 
 def test_a_different_contact_model_translates_and_compiles():

@@ -17,6 +17,8 @@ DOMAIN = (0.8, 0.8, 0.2)
 ctx = Context(0)
 ctx.init_domain([0.0, DOMAIN[0], 0.0, DOMAIN[1], 0.0, DOMAIN[2]], pbc=(1, 1, 0), partitioner=1)
 ctx.dem_enable(dc.C)
+if os.environ.get("PB_DEM_MAXREG"):            # occupancy experiment: contact kernel re-built at run time with a register cap
+    ctx.set_option("dem_force_maxreg", int(os.environ["PB_DEM_MAXREG"]))
 ctx.dem_set_params(dc.DT, math.pi, dc.KAPPA, dc.LN_DRY, dc.COLLISION_TIME, dc.RHO_P, dc.RHO_F, dc.G, dc.NTYPES, dc.FS, dc.FD)
 ctx.setup_cells(dc.CELL)
 g = ctx.dem_sc_grid(DOMAIN[0], DOMAIN[1], DOMAIN[2], dc.SPACING, dc.DIAMETER, dc.MIN_D, dc.MAX_D, dc.V0, dc.RHO_P, dc.NTYPES)
