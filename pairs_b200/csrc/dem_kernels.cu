@@ -12,7 +12,8 @@
 // pair forces are summed follow OUR cell-list order, not the reference's: contact history is compared as per-uid sets,
 // forces to 1e-12.
 //
-// Particles are NOT physically re-sorted in DEM (contact rows stay with their particle index).  Between GPUs a migrating
+// Particles are not re-sorted at every reneighbouring in DEM (contact rows stay with their particle index; every `dem_sort_every`
+// iterations pb_dem_sort_locals puts them into cell order, rows and all).  Between GPUs a migrating
 // particle takes its whole state along -- DEM properties and the contact table -- in one fixed-size record (migrate.cu);
 // unlike the reference (whose pack_contact_history runs after the leaver's slot was overwritten)
 // the history that arrives is the particle's own.
