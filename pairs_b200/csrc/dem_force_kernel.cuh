@@ -5,6 +5,18 @@
 // take the same argument block, so the launch sites do not care which one runs.
 #pragma once
 
+// what a fresh contact slot starts from: the defaults of add_contact_property() (sim/contact_history.py:66, mapping/funcs.py:258);
+// examples/dem.py declares zeros, a generated contact model defines its script's values before this header
+#ifndef PB_DEM_DEFAULT_STICK
+#define PB_DEM_DEFAULT_STICK 0
+#endif
+#ifndef PB_DEM_DEFAULT_TSD
+#define PB_DEM_DEFAULT_TSD(d) 0.0
+#endif
+#ifndef PB_DEM_DEFAULT_IVM
+#define PB_DEM_DEFAULT_IVM 0.0
+#endif
+
 struct PbDemForceArgs {
     int nlocal, cap, C, ntypes;
     PbDemParams P;
@@ -78,9 +90,9 @@ __device__ __forceinline__ void pb_dem_force_body(const PbDemForceArgs &a) {
                 if(ncont >= C) { atomicMax(overflow, ncont + 1); continue; }
                 slot = ncont++;
                 c_uid[(size_t) slot * cap + i] = uj;
-                c_stick[(size_t) slot * cap + i] = 0;
-                for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = 0.0; }
-                c_ivm[(size_t) slot * cap + i] = 0.0;
+                c_stick[(size_t) slot * cap + i] = PB_DEM_DEFAULT_STICK;
+                for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = PB_DEM_DEFAULT_TSD(d); }
+                c_ivm[(size_t) slot * cap + i] = PB_DEM_DEFAULT_IVM;
             }
             if(FUSED) { usedmask |= 1u << slot; } else { c_used[(size_t) slot * cap + i] = 1; }
             double tsd[3] = {c_tsd[((size_t) 0 * C + slot) * cap + i], c_tsd[((size_t) 1 * C + slot) * cap + i],

@@ -745,18 +745,19 @@ class Simulation:
                 storage[name] = slot
         for name in self.props:
             storage.setdefault(name, name)               # anything else: named in the error message if the body touches it
-        contact = {}
-        for name, (ptype, _default) in self.contact_props.items():
+        contact, defaults = {}, {}
+        for name, (ptype, default) in self.contact_props.items():
             kind = {Types.Int32: "c_stick", Types.Vector: "c_tsd", Types.Real: "c_ivm"}.get(ptype)
             if kind is None or kind in contact.values():
                 raise DslError(f"contact property '{name}': the contact table holds one integer, one vector and one real per contact")
             contact[name] = kind
+            defaults[kind] = default
         nk, tables = 1, {}
         for name, (feat, data) in self.feature_props.items():
             tables[name] = data
             nk = self.features[feat]
         try:
-            name, src = kernelgen.translate_dem_model(e["func"], storage, contact, tables, e["symbols"])
+            name, src = kernelgen.translate_dem_model(e["func"], storage, contact, tables, e["symbols"], contact_defaults=defaults)
         except kernelgen.KernelGenError as err:
             raise DslError(f"contact model '{e['name']}': {err}") from None
         return name, src, nk

@@ -730,7 +730,7 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
     return kind, name, "\n".join(out) + "\n"
 
 
-def translate_dem_model(func, storage, contact, feature_tables, symbols):
+def translate_dem_model(func, storage, contact, feature_tables, symbols, contact_defaults=None):
     """A DEM contact model (the body of a pair kernel over contact history, e.g. examples/dem.py:18-74) -> (function name, CUDA
     source) of the device function the library's contact kernel calls for every touching pair (csrc/dem_force_kernel.cuh):
 
@@ -740,7 +740,8 @@ def translate_dem_model(func, storage, contact, feature_tables, symbols):
     -penetration_depth from the kernel's geometry pass; tij = type[i] * ntypes + type[j] (feature properties are literal tables);
     tsd / ivm / sticking = this pair's contact properties (in / out); F / T = what the body apply()s to force / torque.
     Returns false when a skip_when() left the pair.  `storage`: property name -> 'pos' | 'vel' | 'angvel' | 'mass' | 'radius' |
-    'force' | 'torque'; `contact`: contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick'."""
+    'force' | 'torque'; `contact`: contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick'; `contact_defaults`: kind -> the default of
+    add_contact_property() a fresh contact slot starts from (zeros if absent)."""
     src = textwrap.dedent(inspect.getsource(func))
     tree = ast.parse(src).body[0]
     if not isinstance(tree, ast.FunctionDef) or [a.arg for a in tree.args.args] != ["i", "j"]:
@@ -751,6 +752,14 @@ def translate_dem_model(func, storage, contact, feature_tables, symbols):
     for node in tree.body:
         g.stmt(node)
     out = []
+    for kind, value in (contact_defaults or {}).items():
+        if kind == "c_stick":
+            out.append(f"#define PB_DEM_DEFAULT_STICK {int(value)}")
+        elif kind == "c_ivm":
+            out.append(f"#define PB_DEM_DEFAULT_IVM {_lit(float(value))}")
+        elif kind == "c_tsd":
+            v = list(value) if isinstance(value, (list, tuple)) else [value] * 3
+            out.append(f"#define PB_DEM_DEFAULT_TSD(d) ((d) == 0 ? {_lit(float(v[0]))} : ((d) == 1 ? {_lit(float(v[1]))} : {_lit(float(v[2]))}))")
     for fp, table in feature_tables.items():
         out.append(f"__device__ const double fp_{fp}[{len(table)}] = {{{', '.join(_lit(float(x)) for x in table)}}};")
     out.append(f"__device__ __forceinline__ bool {name}(const double *xi, const double *vi, const double *wi, double mi, double ri, "
