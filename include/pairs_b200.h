@@ -187,7 +187,8 @@ int pb_board_unlink(const char *name);
  *      pb_jit_prelude() and defines  extern "C" __global__ void <kernel_name>(PbJitArgs).  Compiled at run time with NVRTC for
  *      sm_100a (--fmad=false).  pb_jit_check compiles only (no GPU needed): returns the cubin size, or -1 with the compiler
  *      log in `log`.  pb_jit_launch: kind 0 = pair kernel over the current neighbour lists with interaction cutoff `cutoff`,
- *      kind 1 = per-particle kernel. ---- */
+ *      kind 1 = per-particle kernel, kind 2 = pair kernel over the current CELL lists (scripts without build_neighbor_lists,
+ *      sim/interaction.py:92-118), kind 3 = pair kernel generated for compute_half() over half lists (ir/apply.py:111-125). ---- */
 const char *pb_jit_prelude(void);
 int pb_jit_check(const char *source, char *log, int log_cap);
 int pb_jit_compile(pb_ctx *ctx, const char *source, const char *kernel_name, int *handle);

@@ -227,6 +227,7 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     PB_CHECK(cudaSetDevice(ctx->device));
     auto *tab = pb_jit_table(ctx);
     if(handle < 0 || handle >= (int) tab->size()) { ctx->set_error("pb_jit_launch: bad kernel handle"); return -1; }
+    if(kind < 0 || kind > 3) { ctx->set_error("pb_jit_launch: kind is 0 (pair / lists), 1 (particle), 2 (pair / cells) or 3 (pair / half lists)"); return -1; }
     PbJitKernel &k = (*tab)[handle];
     PbStage st(ctx, k.name.c_str());
     if(kind == 0 || kind == 3) {
