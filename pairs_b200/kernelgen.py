@@ -72,6 +72,7 @@ class _Gen:
         self.hoisted = []                     # statements before the neighbour loop (loads of i)
         self.types_needed = False
         self.stored = set()                   # properties written so far (particle kernels)
+        self.mutable = {}                     # locals that an if / else arm assigns: name -> value held in mutable C variables
         self.contact = {}                     # contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick' (contact models)
         self.depth = 0                        # nesting depth of if / else arms
 
@@ -257,7 +258,11 @@ class _Gen:
 
     def name_value(self, name):
         if name in self.locals:
-            return self.locals[name]
+            v = self.locals[name]
+            if name in self.mutable:                          # a variable that if / else arms store into: read = snapshot of its value
+                ctype = {"f": "double", "i": "int", "b": "bool"}.get(v[0], "double")
+                return (v[0], [self.tmp("double", c) for c in v[1]]) if isinstance(v[1], list) else (v[0], self.tmp(ctype, v[1]))
+            return v
         if self.kind == "dem" and name in self.storage and name not in self.symbols:
             return self.load(self.storage[name], "i")         # a bare property inside apply() means prop[i] (ir/apply.py:99-100)
         if self.kind == "pair" and name == "rsq":            # legacy bare names of examples/lj_onetype.py
@@ -444,9 +449,41 @@ class _Gen:
         raise KernelGenError(f"unknown function '{f}'")
 
     # -- statements --
+    def make_mutable(self, name):
+        v = self.locals[name]
+        self.n += 1
+        if isinstance(v[1], list):
+            names = [f"m{self.n}_{d}" for d in range(len(v[1]))]
+            for nm, c in zip(names, v[1]):
+                self.lines.append(f"double {nm} = {c};")
+            self.locals[name] = (v[0], names)
+        else:
+            ctype = {"f": "double", "i": "int", "b": "bool"}[v[0]]
+            self.lines.append(f"{ctype} m{self.n} = {v[1]};")
+            self.locals[name] = (v[0], f"m{self.n}")
+        self.mutable[name] = self.locals[name]
+
+    def assign_local(self, name, value):
+        slot = self.mutable.get(name)
+        if slot is None or self.depth == 0:
+            self.mutable.pop(name, None)                  # re-bound at the top level: a fresh value, no storage needed
+            self.locals[name] = value
+            return
+        if slot[0] != value[0] and not (slot[0] == "f" and value[0] == "i"):
+            raise KernelGenError(f"'{name}' changes its type inside an if / else arm")
+        if isinstance(slot[1], list):
+            if not isinstance(value[1], list) or len(value[1]) != len(slot[1]):
+                raise KernelGenError(f"'{name}' changes its type inside an if / else arm")
+            # all components are evaluated before the first store (the value may be built from the old one)
+            for nm, c in zip(slot[1], [self.tmp("double", c) for c in value[1]]):
+                self.lines.append(f"{nm} = {c};")
+        else:
+            self.lines.append(f"{slot[1]} = {value[1]};")
+        self.locals[name] = slot
+
     def block(self, body):
         """Statements of an if / else arm: temporaries, loads and locals created inside stay inside (C scope = Python use)."""
-        saved_locals, saved_loaded, before = dict(self.locals), dict(self.loaded), set(self.stored)
+        saved_locals, saved_loaded, before, saved_mutable = dict(self.locals), dict(self.loaded), set(self.stored), dict(self.mutable)
         self.stored = set()
         self.depth += 1
         for st in body:
@@ -454,6 +491,7 @@ class _Gen:
         self.depth -= 1
         written = self.stored
         self.locals = saved_locals
+        self.mutable = saved_mutable                          # variables declared inside the arm end with its C scope
         # a property the arm stored to has to be read again afterwards (the store may or may not have happened)
         self.loaded = {k: v for k, v in saved_loaded.items() if k[0] not in written}
         self.stored = before | written
@@ -462,7 +500,7 @@ class _Gen:
         if isinstance(node, ast.Expr) and isinstance(node.value, ast.Constant):
             return                                            # docstring
         if isinstance(node, ast.Assign) and len(node.targets) == 1 and isinstance(node.targets[0], ast.Name):
-            self.locals[node.targets[0].id] = self.expr(node.value)
+            self.assign_local(node.targets[0].id, self.expr(node.value))
             return
         if isinstance(node, ast.AugAssign) and isinstance(node.target, ast.Name):       # local op= expr
             if node.target.id not in self.locals:
@@ -470,14 +508,21 @@ class _Gen:
             ops = {ast.Add: "+", ast.Sub: "-", ast.Mult: "*", ast.Div: "/"}
             if type(node.op) not in ops:
                 raise KernelGenError(f"unsupported operator {type(node.op).__name__}")
-            self.locals[node.target.id] = self.binop(ops[type(node.op)], self.locals[node.target.id], self.expr(node.value))
+            self.assign_local(node.target.id, self.binop(ops[type(node.op)], self.locals[node.target.id], self.expr(node.value)))
             return
         if isinstance(node, ast.If):
-            # mapping/funcs.py:179-195: Filter (one arm) / Branch (two arms).  A local assigned inside an arm is visible in
-            # that arm only; what an arm does to the outside world are apply() and property stores.
+            # mapping/funcs.py:179-195: Filter (one arm) / Branch (two arms).  A local FIRST assigned inside an arm is visible in
+            # that arm only; what an arm does to the outside world are apply(), property stores and new values of outer locals.
             cond = self.expr(node.test)
             if self.is_vec(cond):
                 raise KernelGenError("if: the condition must be a scalar")
+            # a local of the enclosing scope that an arm assigns keeps the new value afterwards (Python): it becomes a mutable
+            # variable here, the arms store into it
+            for sub_node in [n for arm in (node.body, node.orelse) for st in arm for n in ast.walk(st)]:
+                tgt = sub_node.targets[0] if isinstance(sub_node, ast.Assign) and len(sub_node.targets) == 1 else \
+                    (sub_node.target if isinstance(sub_node, ast.AugAssign) else None)
+                if isinstance(tgt, ast.Name) and tgt.id in self.locals and tgt.id not in self.mutable:
+                    self.make_mutable(tgt.id)
             self.lines.append(f"if({cond[1]}) {{")
             self.block(node.body)
             if node.orelse:
