@@ -935,3 +935,157 @@ def test_random_expressions_generated_code_equals_python_arithmetic(tmp_path):
                 np.array_equal(np.nan_to_num(got, nan=7.0), np.nan_to_num(want, nan=7.0)), (n, text.split("\n\n\n")[n])
         checked += 1
     assert checked >= 25
+
+
+def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path):
+    """The same differential test for pair kernels: 20 random bodies over delta / squared_distance, properties of both partners, a
+    feature table, locals, if / else, skip_when and one or two apply() -- the generated neighbour loop (hoisted loads of i, cached
+    loads of j, register accumulators, cutoff, FIXED filter) against CPython walking the same lists."""
+    import importlib.util
+    import math
+    import random
+    import numpy as np
+    rnd = random.Random(77)
+    names = {"s": [], "v": []}
+
+    def scalar(depth):
+        if depth <= 0 or rnd.random() < 0.25:
+            return rnd.choice(["mass[i]", "mass[j]", "squared_distance(i, j)", "eps[i, j]", "linear_velocity[j][1]", "0.5", "kk", "3"] + names["s"])
+        k = rnd.random()
+        if k < 0.5:
+            return f"({scalar(depth - 1)} {rnd.choice('+-*')} {scalar(depth - 1)})"
+        if k < 0.6:
+            return f"(1.0 / (0.5 + abs({scalar(depth - 1)})))"
+        if k < 0.7:
+            return f"select({scalar(depth - 1)} < {scalar(depth - 1)}, {scalar(depth - 1)}, {scalar(depth - 1)})"
+        if k < 0.8:
+            return f"dot({vector(depth - 1)}, {vector(depth - 1)})"
+        if k < 0.9:
+            return f"sqrt(squared_distance(i, j) + abs({scalar(depth - 1)}))"
+        return f"-{scalar(depth - 1)}"
+
+    def vector(depth):
+        if depth <= 0 or rnd.random() < 0.35:
+            return rnd.choice(["delta(i, j)", "linear_velocity[i]", "linear_velocity[j]", "position[j]"] + names["v"])
+        k = rnd.random()
+        if k < 0.4:
+            return f"({vector(depth - 1)} {rnd.choice('+-')} {vector(depth - 1)})"
+        if k < 0.8:
+            return f"({vector(depth - 1)} * {scalar(depth - 1)})"
+        return f"cross({vector(depth - 1)}, {vector(depth - 1)})"
+
+    bodies = []
+    for n in range(20):
+        names["s"], names["v"] = [], []
+        lines = [f"def p{n}(i, j):", f"    skip_when({scalar(1)} > 2.5)", f"    a = {scalar(2)}"]
+        names["s"].append("a")
+        lines.append(f"    w = {vector(1)}")
+        names["v"].append("w")
+        lines += [f"    if {scalar(1)} < {scalar(1)}:", f"        a = {scalar(2)}", f"        apply(force, {vector(2)})", "    else:", f"        w = {vector(1)}"]
+        lines.append(f"    apply(force, w * a + {vector(2)})")
+        bodies.append("\n".join(lines))
+    text = "\n\n\n".join(bodies) + "\n"
+    mod_path = tmp_path / "fuzz_pairs.py"
+    mod_path.write_text(text)
+    spec = importlib.util.spec_from_file_location("fuzz_pairs", mod_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class V:
+        def __init__(self, c):
+            self.c = [float(x) for x in c]
+
+        def __add__(self, o):
+            return V([x + y for x, y in zip(self.c, o.c)])
+
+        def __sub__(self, o):
+            return V([x - y for x, y in zip(self.c, o.c)])
+
+        def __mul__(self, s):
+            return V([x * s for x in self.c])
+
+        def __rmul__(self, s):
+            return V([s * x for x in self.c])
+
+        def __getitem__(self, k):
+            return self.c[k]
+
+    class Skip(Exception):
+        pass
+
+    # a small random system with explicit lists (some partners beyond the cutoff, some FIXED particles)
+    rng = np.random.default_rng(3)
+    n, nt, ntypes = 48, 64, 2
+    pos = rng.random((nt, 3)) * 3.0
+    typ = rng.integers(0, ntypes, nt)
+    vel = rng.standard_normal((3, nt))
+    mass = 0.5 + rng.random(nt)
+    flags = np.zeros(nt, np.int32)
+    flags[5:n:11] = 4
+    eps = [1.0, 1.5, 0.75, 2.0]
+    lists = [sorted(rng.choice([j for j in range(nt) if j != i], size=rng.integers(3, 12), replace=False)) for i in range(n)]
+    nslots = max(len(x) for x in lists)
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    numneigh = np.zeros(nt, np.int32)
+    for i, lst in enumerate(lists):
+        neigh[i // 32, :len(lst), i % 32] = lst
+        numneigh[i] = len(lst)
+    cutsq = 2.0 * 2.0
+    storage = {"position": "pos", "linear_velocity": "vel", "force": "force", "mass": "mass"}
+    checked = 0
+    for k in range(20):
+        fn = getattr(mod, f"p{k}")
+        try:
+            _, name, code = kernelgen.translate(fn, storage, {"eps": eps}, ntypes, {"kk": 1.25}, backend.jit_prelude())
+        except kernelgen.KernelGenError:
+            continue
+        run = _host_kernel(tmp_path, name, code)
+        pos4 = np.zeros((nt, 4))
+        pos4[:, :3] = pos
+        pos4[:, 3] = typ.astype(np.int64).view(np.float64)
+        g_vel, g_force, g_mass, g_flags = vel.copy(), np.zeros((3, nt)), mass.copy(), flags.copy()
+        run(n, nslots, nt, cutsq, _ptr(pos4), _ptr(g_vel), _ptr(g_force), _ptr(g_mass), _ptr(g_flags), _ptr(numneigh), _ptr(neigh))
+        want = np.zeros((3, nt))
+        state = {}
+
+        def apply_(_prop, v):
+            state["acc"] = [x + y for x, y in zip(state["acc"], v.c)]
+
+        def skip_when(c):
+            if c:
+                raise Skip()
+
+        class P:
+            def __init__(self, rows):
+                self.rows = rows
+
+            def __getitem__(self, idx):
+                return V(self.rows[:, idx]) if self.rows.ndim == 2 else float(self.rows[idx])
+
+        class FP:
+            def __getitem__(self, ij):
+                return eps[typ[ij[0]] * ntypes + typ[ij[1]]]
+
+        def dot(p, q):
+            return (p[0] * q[0] + p[1] * q[1]) + p[2] * q[2]
+
+        env = {"position": P(np.ascontiguousarray(pos.T)), "linear_velocity": P(vel), "mass": P(mass), "force": "force", "eps": FP(), "kk": 1.25,
+               "apply": apply_, "skip_when": skip_when, "select": lambda c, x, y: x if c else y, "sqrt": math.sqrt, "abs": abs, "dot": dot,
+               "cross": lambda p, q: V([p[1] * q[2] - p[2] * q[1], p[2] * q[0] - p[0] * q[2], p[0] * q[1] - p[1] * q[0]]),
+               "delta": lambda i, j: V(pos[i]) - V(pos[j]),
+               "squared_distance": lambda i, j: dot(V(pos[i]) - V(pos[j]), V(pos[i]) - V(pos[j]))}
+        fn.__globals__.update(env)
+        for i in range(n):
+            if flags[i] & 4:
+                continue
+            state["acc"] = [0.0, 0.0, 0.0]
+            for j in lists[i]:
+                if env["squared_distance"](i, j) < cutsq:
+                    try:
+                        fn(i, int(j))
+                    except Skip:
+                        pass
+            want[:, i] = [0.0 + x for x in state["acc"]]
+        assert np.array_equal(g_force, want), (k, bodies[k])
+        checked += 1
+    assert checked >= 10
