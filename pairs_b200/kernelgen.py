@@ -28,11 +28,18 @@ property once after the loop (sim/interaction.py:280-292); FIXED particles are s
 """
 import ast
 import inspect
+import os
 import textwrap
 
 
 class KernelGenError(Exception):
     pass
+
+
+# Pair kernels over neighbour lists fetch this many partners at a time -- their indices first, then their positions (independent
+# 256-bit gathers in flight), then the bodies in list order -- as the hand-written Lennard-Jones kernel does (csrc/md_kernels.cu,
+# `lj_unroll`); the order of the pair terms, hence every bit of the result, is that of the plain loop (1 = plain loop).
+PAIR_PREFETCH = int(os.environ.get("PAIRS_B200_PAIR_PREFETCH", "4"))
 
 
 def _lit(x):
@@ -738,12 +745,27 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
             out.append("    for(int k = a.cell_start[c_lo]; k < k_end; k++) {")
             out.append("        const int j = __ldg(a.cell_list + k);")
             out.append("        if(j == i) { continue; }")
+        elif PAIR_PREFETCH > 1:
+            U = PAIR_PREFETCH
+            out.append("    const int nn = a.numneigh[i];")
+            out.append("    const int *nb = a.neigh + (size_t) (i >> 5) * a.nslots * 32 + (i & 31);")
+            out.append(f"    for(int k0 = 0; k0 < nn; k0 += {U}) {{")
+            out.append(f"    int jj[{U}];")
+            out.append(f"    double4 pp[{U}];")
+            out.append("#pragma unroll")
+            out.append(f"    for(int u = 0; u < {U}; u++) {{ jj[u] = (k0 + u < nn) ? __ldg(nb + (size_t) (k0 + u) * 32) : i; }}")
+            out.append("#pragma unroll")
+            out.append(f"    for(int u = 0; u < {U}; u++) {{ pp[u] = pb_ld_pos(a.pos + jj[u]); }}")
+            out.append("#pragma unroll")
+            out.append(f"    for(int u = 0; u < {U}; u++) {{")
+            out.append("        if(k0 + u >= nn) { break; }")
+            out.append("        const int j = jj[u];")
         else:
             out.append("    const int nn = a.numneigh[i];")
             out.append("    const int *nb = a.neigh + (size_t) (i >> 5) * a.nslots * 32 + (i & 31);")
             out.append("    for(int k = 0; k < nn; k++) {")
             out.append("        const int j = __ldg(nb + (size_t) k * 32);")
-        out.append("        const double4 pj = pb_ld_pos(a.pos + j);")
+        out.append("        const double4 pj = pp[u];" if (traversal == "lists" and PAIR_PREFETCH > 1) else "        const double4 pj = pb_ld_pos(a.pos + j);")
         out.append("        const double dx = pi.x - pj.x;")          # delta(i, j) = position[i] - position[j]
         out.append("        const double dy = pi.y - pj.y;")
         out.append("        const double dz = pi.z - pj.z;")
@@ -758,7 +780,7 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
         out += ["            " + ln for ln in g.lines]
         out.append("        }")
         out.append("    }")
-        if traversal == "cells":
+        if traversal == "cells" or PAIR_PREFETCH > 1:
             out.append("    }")
         for store, acc in g.applied.items():                          # prop[i] = prop[i] + acc (sim/interaction.py:280-292)
             for d, x in enumerate(acc):
