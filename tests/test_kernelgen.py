@@ -1089,3 +1089,47 @@ def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path):
         assert np.array_equal(g_force, want), (k, bodies[k])
         checked += 1
     assert checked >= 10
+
+
+def test_partner_prefetch_does_not_change_a_bit(tmp_path):
+    """Generated pair kernels fetch partners four at a time (kernelgen.PAIR_PREFETCH); the plain loop gives the same bits."""
+    import numpy as np
+    import custom_script
+    from oracle import port
+    nx = 5
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=60000, send_capacity=60000)
+    r = sim.ranks[0]
+    n = r.nlocal
+    r.real("position", n, view=True)[:] += 0.2 * (np.random.default_rng(1).random((n, 3)) - 0.5)
+    sim.step(0)
+    tot = n + r.nghost
+    nn, nl = r.neighbor_sets()
+    psim = custom_script.build("gpu", nx, 10, 20, 1)
+    tables = {k: v[1] for k, v in psim.feature_props.items()}
+    pos4 = np.zeros((tot, 4))
+    pos4[:, :3] = r.real("position", tot)
+    pos4[:, 3] = r.ints("type", tot).astype(np.int64).view(np.float64)
+    vel, mass, flags = np.zeros((3, tot)), np.ones(tot), r.ints("flags", tot).copy()
+    nslots = int(nn.max())
+    neigh = np.zeros(((n + 31) // 32, nslots, 32), np.int32)
+    for i in range(n):
+        neigh[i // 32, :nn[i], i % 32] = nl[i, :nn[i]]
+    numneigh = np.zeros(tot, np.int32)
+    numneigh[:n] = nn
+    out = {}
+    saved = kernelgen.PAIR_PREFETCH
+    try:
+        for u in (1, 3, 4):
+            kernelgen.PAIR_PREFETCH = u
+            _, name, code = kernelgen.translate(custom_script.lennard_jones, psim._device_storage(), tables, 4, {"kspring": 3.5, "rsoft": 1.05},
+                                                backend.jit_prelude())
+            assert ("pp[u]" in code) == (u > 1)
+            force = np.zeros((3, tot))
+            sub = tmp_path / f"u{u}"                     # same kernel name for every depth: one build directory each
+            sub.mkdir()
+            run = _host_kernel(sub, name, code)
+            run(n, nslots, tot, 2.5 * 2.5, _ptr(pos4), _ptr(vel), _ptr(force), _ptr(mass), _ptr(flags), _ptr(numneigh), _ptr(neigh))
+            out[u] = force
+    finally:
+        kernelgen.PAIR_PREFETCH = saved
+    assert np.abs(out[1]).max() > 1.0 and np.array_equal(out[1], out[3]) and np.array_equal(out[1], out[4])
