@@ -18,6 +18,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   dem_nl_t1 dem_t1 with psim.build_neighbor_lists(linkedCellWidth) instead of build_cell_lists: Verlet lists + BuildContactHistory
   dem_vtk_t1 dem_t1 for 60 steps with the example's psim.vtk_output(..., frequency) kept, writing every 30 iterations
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
+  dem_rn3_t1 dem_t1 with psim.reneighbor_every(3): exchange / borders / cell lists every third iteration, synchronize in between
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_custom_t1  md_t1 with other kernel bodies (softened LJ using sqrt / select / symbols, integrators with drag) -> generic kernels
   md_props_t1   md_t1 with user-defined properties (a real entering the pair force, written by a setup() function; a second volatile
@@ -187,8 +188,10 @@ def md_vocab_variant(nx, steps):
     return patch
 
 
-def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None, verlet=False):
+def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None, verlet=False, reneigh=None):
     def patch(text):
+        if reneigh is not None:    # cell lists / ghosts rebuilt every `reneigh` iterations, ghosts refreshed by synchronize in between
+            text = _sub(text, r"^psim\.generate\(\)", f"psim.reneighbor_every({reneigh})\npsim.generate()")
         if verlet:      # Verlet lists + BuildContactHistory instead of the cell-list traversal (sim/simulation.py:255-261, 402-406)
             text = _sub(text, r"^psim\.build_cell_lists\(linkedCellWidth\)", "psim.build_neighbor_lists(linkedCellWidth)")
         if vtk_every is not None:     # keep psim.vtk_output(...) (runtime/vtk.hpp) and write every `vtk_every` iterations
@@ -267,6 +270,7 @@ VARIANTS = {
     "dem_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), [], False),
     "dem_cn_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700, per_cell=True), [], False),
     "dem_nl_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700, verlet=True), [], False),
+    "dem_rn3_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 400, reneigh=3), [], False),
     "dem_vtk_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 60, vtk_every=30), [], False),
     "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),
 }

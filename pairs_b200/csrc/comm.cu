@@ -15,6 +15,7 @@
 //                             borders : uid type mass x y z vx vy vz shape tag              (11 doubles)
 //                             borders (DEM): ... + radius wx wy wz                           (15 doubles)
 //                             sync    : x y z vx vy vz                                      ( 6 doubles)
+//                             sync (DEM): ... + wx wy wz                                     ( 9 doubles; comm.py:49 lists angular_velocity)
 // Positions are shifted by send_mult * L on ALL three axes exactly as comm.py:320-321 does (two of the
 // multipliers are zero), so ghost coordinates are bit-identical to the reference's.
 #include <algorithm>
@@ -25,7 +26,7 @@ int pb_sort_locals(pb_ctx *ctx);
 int pb_transport_sizes(pb_ctx *ctx, int dim);
 int pb_transport_data(pb_ctx *ctx, int dim_begin, int dim_end, int elem, const double **recv_src);
 
-static const int BORDER_ELEMS = 11, BORDER_ELEMS_DEM = 15, SYNC_ELEMS = 6;
+static const int BORDER_ELEMS = 11, BORDER_ELEMS_DEM = 15, SYNC_ELEMS = 6, SYNC_ELEMS_DEM = 9;
 
 struct PbBox {
     double len[3];
@@ -316,15 +317,20 @@ extern "C" int pb_borders(pb_ctx *ctx) {
 // corner image, whose source is itself a ghost) therefore carries the coordinates its source ghost had BEFORE this
 // refresh -- one step stale per forwarding level.  That behaviour is part of the reference's results and is
 // reproduced here by construction: one pack kernel over all entries, then one unpack kernel.
-__global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, int nlocal, PbBox box, const int *__restrict__ send_map,
+__global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, int nlocal, int stride, PbBox box, const int *__restrict__ send_map,
                                                       const int *__restrict__ send_mult, const double4 *__restrict__ pos,
                                                       const double4 *__restrict__ pos_ghost, const double *__restrict__ vel,
-                                                      double *__restrict__ buf) {
+                                                      const double *__restrict__ angvel, double *__restrict__ buf) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if(e >= count) { return; }
     const int p = send_map[e];
     const double4 x = (p < nlocal) ? pos[p] : pos_ghost[p];     // ghosts: the values of the previous refresh
-    double *b = buf + (size_t) e * SYNC_ELEMS;
+    double *b = buf + (size_t) e * stride;
+    if(angvel != nullptr) {                                     // DEM: angular velocity is refreshed too (comm.py:49)
+        b[6] = angvel[p];
+        b[7] = angvel[cap + p];
+        b[8] = angvel[2 * cap + p];
+    }
     b[0] = __dadd_rn(x.x, __dmul_rn((double) send_mult[e * 3 + 0], box.len[0]));
     b[1] = __dadd_rn(x.y, __dmul_rn((double) send_mult[e * 3 + 1], box.len[1]));
     b[2] = __dadd_rn(x.z, __dmul_rn((double) send_mult[e * 3 + 2], box.len[2]));
@@ -333,13 +339,18 @@ __global__ void __launch_bounds__(256) pb_k_pack_sync(int count, int cap, int nl
     b[5] = vel[2 * cap + p];
 }
 
-__global__ void __launch_bounds__(256) pb_k_unpack_sync(int count, int dst0, int cap, const double *__restrict__ buf,
+__global__ void __launch_bounds__(256) pb_k_unpack_sync(int count, int dst0, int cap, int stride, const double *__restrict__ buf,
                                                         const double4 *__restrict__ pos_ghost, double4 *__restrict__ pos,
-                                                        double *__restrict__ vel) {
+                                                        double *__restrict__ vel, double *__restrict__ angvel) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= count) { return; }
-    const double *b = buf + (size_t) k * SYNC_ELEMS;
+    const double *b = buf + (size_t) k * stride;
     const int p = dst0 + k;
+    if(angvel != nullptr) {
+        angvel[p] = b[6];
+        angvel[cap + p] = b[7];
+        angvel[2 * cap + p] = b[8];
+    }
     const double w = pos_ghost[p].w;
     pos[p] = make_double4(b[0], b[1], b[2], w);
     vel[p] = b[3];
@@ -351,14 +362,17 @@ extern "C" int pb_synchronize(pb_ctx *ctx) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "synchronize");
     const double4 *pos_ghost = ctx->ghosts_in_alt ? ctx->pos_alt : ctx->pos;
+    const int stride = ctx->dem ? SYNC_ELEMS_DEM : SYNC_ELEMS;
+    double *angvel = ctx->dem ? ctx->angvel : nullptr;
     if(ctx->nsend_all > 0) {
-        PB_LAUNCH(pb_k_pack_sync, pb_blocks(ctx->nsend_all, 256), 256, ctx->nsend_all, ctx->pcap, ctx->nlocal, pb_box(ctx), ctx->send_map,
-                  ctx->send_mult, ctx->pos, pos_ghost, ctx->vel, ctx->send_buf);
+        PB_LAUNCH(pb_k_pack_sync, pb_blocks(ctx->nsend_all, 256), 256, ctx->nsend_all, ctx->pcap, ctx->nlocal, stride, pb_box(ctx), ctx->send_map,
+                  ctx->send_mult, ctx->pos, pos_ghost, ctx->vel, angvel, ctx->send_buf);
     }
     const double *src = nullptr;
-    PB_TRY(pb_transport_data(ctx, 0, 3, SYNC_ELEMS, &src));
+    PB_TRY(pb_transport_data(ctx, 0, 3, stride, &src));
     if(ctx->nghost > 0) {
-        PB_LAUNCH(pb_k_unpack_sync, pb_blocks(ctx->nghost, 256), 256, ctx->nghost, ctx->nlocal, ctx->pcap, src, pos_ghost, ctx->pos, ctx->vel);
+        PB_LAUNCH(pb_k_unpack_sync, pb_blocks(ctx->nghost, 256), 256, ctx->nghost, ctx->nlocal, ctx->pcap, stride, src, pos_ghost, ctx->pos, ctx->vel,
+                  angvel);
     }
     ctx->ghosts_in_alt = false;
     return 0;

@@ -576,13 +576,14 @@ class Simulation:
         if self.pre_step or len(pair_at) != 1 or any(f not in ("gravity", "euler", "generic_particle", "linear_spring_dashpot", "generic_pair")
                                                      for f in fams) \
                 or fams.count("gravity") > 1 or fams.count("euler") > 1 \
-                or not self.use_contact_history or self.neighbor_cutoff is not None or self.reneighbor_frequency != 1:
+                or not self.use_contact_history or self.neighbor_cutoff is not None:
             raise DslError("DEM: a procedure list like examples/dem.py's is implemented -- per-particle kernels (gravity, euler or any "
-                           "other body), ONE contact model (any body) over cell lists with contact history, reneighbouring every step")
+                           "other body) and ONE contact model (any body) over cell lists with contact history")
         lsd = self.functions[pair_at[0]]
         grav = next((e for e in self.functions if e["family"] == "gravity"), None)
         eul = next((e for e in self.functions if e["family"] == "euler"), None)
-        standard = fams in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"])
+        # the native loop (pb_dem_run) is the generated loop of examples/dem.py: the standard list, reneighbouring every iteration
+        standard = fams in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"]) and self.reneighbor_frequency == 1
         ctx.dem_enable(self.neighbor_capacity)
         for name, comps, volatile, dflt in self._dem_user_props():
             _, row0 = ctx.add_property(name, comps, volatile, dflt)
@@ -719,9 +720,12 @@ class Simulation:
             calls.append(lambda handle=handle: ctx.jit_launch(handle, 1))
         ctx.setup_cells(self._cell_spacing)
         for ts in range(nsteps):
-            ctx.exchange()
-            ctx.borders()
-            ctx.build_cell_lists()
+            if ((ts + 1) % self.reneighbor_frequency) == 0 or ts == 0:      # sim/timestep.py:36-61, as on the md.py path
+                ctx.exchange()
+                ctx.borders()
+                ctx.build_cell_lists()
+            else:
+                ctx.synchronize()            # positions, linear and angular velocities of the ghosts (sim/comm.py:45-54)
             ctx.dem_stage("reset_contact_usage")
             ctx.reset_volatile()
             for e, call in zip(self.functions, calls):

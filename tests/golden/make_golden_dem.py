@@ -38,3 +38,14 @@ for ts in END_STEPS:
 path = os.path.join(HERE, "dem_t1.npz")
 np.savez_compressed(path, **out)
 print("dem_t1:", os.path.getsize(path) // 1024, "KiB,", int(z["nlocal"][0]), "locals,", int(z["nghost"][0]), "ghosts")
+
+
+# variant dem_rn3_t1 (reneighbor_every(3)): end-of-iteration states only
+z3 = ref_worker.dump_dem("dem_rn3_t1", "/tmp/dem_rn3_t1_golden_raw.npz", 301, [0, 150, 300])
+out3 = {"nlocal": z3["nlocal"], "nghost": z3["nghost"], "end_steps": np.array([0, 150, 300])}
+for ts in (0, 150, 300):
+    for k in END:
+        out3[f"end_{ts}_{k}"] = z3[f"end_{ts}_{k}"]
+path3 = os.path.join(HERE, "dem_rn3_t1.npz")
+np.savez_compressed(path3, **out3)
+print("dem_rn3_t1:", os.path.getsize(path3) // 1024, "KiB")

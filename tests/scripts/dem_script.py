@@ -94,7 +94,7 @@ def gravity(i):
     force[i][2] = force[i][2] - (densityParticle_SI - densityFluid_SI) * volume * gravity_SI
 
 
-def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None):
+def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None, reneighbor=None):
     diameter_SI, gravity_SI, densityFluid_SI, densityParticle_SI = 0.0029, 9.81, 1000, 2550
     generationSpacing_SI, initialVelocity_SI, dt_SI = 0.005, 1, 5e-5
     frictionCoefficient, restitutionCoefficient, collisionTime_SI, poissonsRatio = 0.5, 0.1, 5e-4, 0.22
@@ -152,6 +152,8 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
     psim.compute(linear_spring_dashpot, linkedCellWidth, symbols={'dt': dt_SI, 'pi': math.pi, 'kappa': kappa,
                                                                    'lnDryResCoeff': lnDryResCoeff, 'collisionTime_SI': collisionTime_SI})
     psim.compute(euler, symbols={'dt': dt_SI})
+    if reneighbor is not None:          # oracle variant dem_rn3_t1: cell lists / ghosts every `reneighbor` iterations
+        psim.reneighbor_every(reneighbor)
     return psim
 
 

@@ -313,3 +313,10 @@ def test_md_script_with_cell_lists_only_plans_generated_pair_kernels():
     psim.compute_half()
     with pytest.raises(dsl.DslError, match="needs neighbour lists"):
         psim._bind(Ctx(), psim.functions[0])
+
+
+def test_dem_script_with_a_reneighbouring_interval_is_planned_module_by_module():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10, reneighbor=3)
+    assert psim.reneighbor_frequency == 3 and [e["family"] for e in psim.functions] == ["gravity", "linear_spring_dashpot", "euler"]

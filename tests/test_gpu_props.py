@@ -222,6 +222,28 @@ def test_generated_pair_kernel_with_compute_half_matches_the_built_in_half_kerne
     assert rel_err_force(f_b, f_a) <= 1e-12
 
 
+@PENDING
+def test_dem_script_with_a_reneighbouring_interval_matches_the_reference(capsys):
+    """examples/dem.py with psim.reneighbor_every(3): exchange / borders / cell lists every third iteration, the ghosts' positions,
+    linear AND angular velocities refreshed by synchronize in between (module-by-module loop).  State after iteration 300 against the
+    reference's generated C++ for the same script (oracle variant dem_rn3_t1 -> tests/golden/dem_rn3_t1.npz), matched through uid."""
+    import dem_script
+    from tests import dem_common as dc
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dem_rn3_t1.npz"))
+    psim = dem_script.build("gpu", dc.DOMAIN, 300, reneighbor=3)
+    ctx = psim.generate()
+    capsys.readouterr()
+    n = 422
+    assert ctx.counts()[0] == n
+    o, r = np.argsort(ctx.ints("uid")), np.argsort(z["end_300_uid"])
+    pref = z["end_300_position"][r]
+    assert np.abs(ctx.real("position")[o] - pref).max() <= 1e-12 * np.abs(pref[:n - 2]).max()
+    vref = z["end_300_linear_velocity"][r]
+    assert np.abs(ctx.real("linear_velocity")[o] - vref).max() <= 1e-9 * np.abs(vref).max()
+    c = ctx.dem_download_contacts(n)
+    assert np.array_equal(c["num_contacts"][o], z["end_300_num_contacts"][r]) and c["num_contacts"].sum() > 50
+
+
 def test_property_store_through_the_c_abi(capsys):
     """add / upload / download, defaults, capacity growth, ghosts carrying their source's values, volatile reset, the cell-order
     sort -- without any generated kernel."""
