@@ -692,6 +692,16 @@ class _Gen:
             self.loaded[(store, "i")] = v
 
 
+def _function_ast(func):
+    """The kernel function's AST, as the reference obtains it (inspect.getsource, mapping/funcs.py:286-288)."""
+    try:
+        src = textwrap.dedent(inspect.getsource(func))
+    except (OSError, TypeError):
+        raise KernelGenError(f"the source text of '{getattr(func, '__name__', func)}' is not available (kernels are translated from their "
+                             "source: define them in a file)") from None
+    return ast.parse(src).body[0]
+
+
 def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixed=True, traversal="lists", half=False):
     """-> (kind, kernel name, CUDA source).  `storage` maps the user's property names to device arrays.  skip_fixed=False is
     for setup() functions: the reference runs those over every local particle (no FIXED filter, mapping/funcs.py:305-310 applies
@@ -700,8 +710,7 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
     stencil row being one run of the CSR).  half=True is Simulation.compute_half(): the lists hold every pair once and apply()
     also subtracts the term from the partner with an atomic add unless it is a ghost or FIXED (ir/apply.py:111-125; the own
     particle's sum is added atomically too, other threads may be updating it)."""
-    src = textwrap.dedent(inspect.getsource(func))
-    tree = ast.parse(src).body[0]
+    tree = _function_ast(func)
     if not isinstance(tree, ast.FunctionDef):
         raise KernelGenError(f"{func.__name__}: not a plain function")
     params = [a.arg for a in tree.args.args]
@@ -809,8 +818,7 @@ def translate_dem_model(func, storage, contact, feature_tables, symbols, contact
     Returns false when a skip_when() left the pair.  `storage`: property name -> 'pos' | 'vel' | 'angvel' | 'mass' | 'radius' |
     'force' | 'torque'; `contact`: contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick'; `contact_defaults`: kind -> the default of
     add_contact_property() a fresh contact slot starts from (zeros if absent)."""
-    src = textwrap.dedent(inspect.getsource(func))
-    tree = ast.parse(src).body[0]
+    tree = _function_ast(func)
     if not isinstance(tree, ast.FunctionDef) or [a.arg for a in tree.args.args] != ["i", "j"]:
         raise KernelGenError(f"{func.__name__}: a contact model takes (i, j)")
     name = f"user_model_{func.__name__}"

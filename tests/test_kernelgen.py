@@ -134,6 +134,10 @@ def test_unsupported_constructs_are_rejected_with_a_reason():
             kernelgen.translate(fn, storage, {}, 1, {}, "")
     with pytest.raises(kernelgen.KernelGenError, match=r"\(i\) or \(i, j\)"):
         kernelgen.translate(three_args, storage, {}, 1, {}, "")
+    ns = {}
+    exec("def made_at_run_time(i):\n    mass[i] = 1.0\n", ns)
+    with pytest.raises(kernelgen.KernelGenError, match="source text"):
+        kernelgen.translate(ns["made_at_run_time"], storage, {}, 1, {}, "")
 
 
 def test_if_statements_and_local_updates():
