@@ -941,8 +941,11 @@ def test_random_expressions_generated_code_equals_python_arithmetic(tmp_path):
     assert checked >= 25
 
 
-def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path):
-    """The same differential test for pair kernels: 20 random bodies over delta / squared_distance, properties of both partners, a
+@pytest.mark.parametrize("half", [False, True])
+def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path, half):
+    """(half = True: generated for compute_half() -- the partner receives the opposite term unless it is a ghost or FIXED; one thread
+    after the other on the host, so the "atomic" updates happen in the order Python performs them.)
+    The same differential test for pair kernels: 20 random bodies over delta / squared_distance, properties of both partners, a
     feature table, locals, if / else, skip_when and one or two apply() -- the generated neighbour loop (hoisted loads of i, cached
     loads of j, register accumulators, cutoff, FIXED filter) against CPython walking the same lists."""
     import importlib.util
@@ -1040,7 +1043,7 @@ def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path):
     for k in range(20):
         fn = getattr(mod, f"p{k}")
         try:
-            _, name, code = kernelgen.translate(fn, storage, {"eps": eps}, ntypes, {"kk": 1.25}, backend.jit_prelude())
+            _, name, code = kernelgen.translate(fn, storage, {"eps": eps}, ntypes, {"kk": 1.25}, backend.jit_prelude(), half=half)
         except kernelgen.KernelGenError:
             continue
         run = _host_kernel(tmp_path, name, code)
@@ -1054,6 +1057,10 @@ def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path):
 
         def apply_(_prop, v):
             state["acc"] = [x + y for x, y in zip(state["acc"], v.c)]
+            jj = state["j"]
+            if half and jj < n and not (flags[jj] & 4):
+                for d in range(3):
+                    want[d, jj] = want[d, jj] + -(v.c[d])
 
         def skip_when(c):
             if c:
@@ -1085,11 +1092,12 @@ def test_random_pair_kernels_generated_code_equals_python_arithmetic(tmp_path):
             state["acc"] = [0.0, 0.0, 0.0]
             for j in lists[i]:
                 if env["squared_distance"](i, j) < cutsq:
+                    state["j"] = int(j)
                     try:
                         fn(i, int(j))
                     except Skip:
                         pass
-            want[:, i] = [0.0 + x for x in state["acc"]]
+            want[:, i] = [want[d, i] + x for d, x in enumerate(state["acc"])]
         assert np.array_equal(g_force, want), (k, bodies[k])
         checked += 1
     assert checked >= 10
