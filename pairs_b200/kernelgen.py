@@ -343,9 +343,14 @@ class _Gen:
                 raise KernelGenError(f"{f}() needs a pair kernel")
             return self.vec(["dx", "dy", "dz"]) if f == "delta" else ("f", "rsq")
         args = [] if f in ("is_point_mass", "is_sphere", "is_halfspace") else [self.expr(a) for a in node.args]
+        if f in ("sqrt", "abs") and (len(args) != 1 or isinstance(args[0][1], list)):
+            raise KernelGenError(f"{f}() takes one scalar")
         if f == "sqrt":
-            return ("f", self.tmp("double", f"sqrt({args[0][1]})"))
+            x = args[0][1] if args[0][0] == "f" else f"(double) {args[0][1]}"        # an integer argument: no overload guessing
+            return ("f", self.tmp("double", f"sqrt({x})"))
         if f == "abs":
+            if args[0][0] == "i":
+                return ("i", self.tmp("int", f"({args[0][1]} < 0) ? -({args[0][1]}) : ({args[0][1]})"))
             return ("f", self.tmp("double", f"fabs({args[0][1]})"))
         if f in ("min", "max"):                               # keywords.py:67-79: e = a0; for a in rest: e = select(a < e, a, e)
             if len(args) < 1 or any(self.is_vec(a) for a in args):

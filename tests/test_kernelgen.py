@@ -1145,3 +1145,197 @@ def test_partner_prefetch_does_not_change_a_bit(tmp_path):
     finally:
         kernelgen.PAIR_PREFETCH = saved
     assert np.abs(out[1]).max() > 1.0 and np.array_equal(out[1], out[3]) and np.array_equal(out[1], out[4])
+
+
+def test_random_contact_models_generated_code_equals_python_arithmetic(tmp_path):
+    """Differential test of translate_dem_model: 15 random contact-model bodies (pair geometry symbols, properties of both partners,
+    the three contact properties read and assigned in statement order, skip_when, if / else, one or two apply() to force and torque)
+    compiled for the host against CPython evaluating the same source on the same random pairs: F, T, the contact properties and the
+    keep / skip decision are the same bits."""
+    import ctypes
+    import importlib.util
+    import math
+    import random
+    import subprocess
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    rnd = random.Random(5)
+    names = {"s": [], "v": []}
+
+    def scalar(depth):
+        if depth <= 0 or rnd.random() < 0.25:
+            return rnd.choice(["mass[i]", "mass[j]", "radius[i]", "radius[j]", "penetration_depth(i, j)", "impact_velocity_magnitude[i, j]",
+                               "fric[i, j]", "0.5", "kn", "2"] + names["s"])
+        k = rnd.random()
+        if k < 0.5:
+            return f"({scalar(depth - 1)} {rnd.choice('+-*')} {scalar(depth - 1)})"
+        if k < 0.6:
+            return f"(1.0 / (0.5 + abs({scalar(depth - 1)})))"
+        if k < 0.7:
+            return f"select({scalar(depth - 1)} < {scalar(depth - 1)}, {scalar(depth - 1)}, {scalar(depth - 1)})"
+        if k < 0.85:
+            return f"dot({vector(depth - 1)}, {vector(depth - 1)})"
+        return f"length({vector(depth - 1)})"
+
+    def vector(depth):
+        if depth <= 0 or rnd.random() < 0.35:
+            return rnd.choice(["contact_normal(i, j)", "contact_point(i, j)", "position[i]", "position[j]", "linear_velocity[i]", "linear_velocity[j]",
+                               "angular_velocity[i]", "angular_velocity[j]", "tangential_spring_displacement[i, j]"] + names["v"])
+        k = rnd.random()
+        if k < 0.4:
+            return f"({vector(depth - 1)} {rnd.choice('+-')} {vector(depth - 1)})"
+        if k < 0.8:
+            return f"({vector(depth - 1)} * {scalar(depth - 1)})"
+        return f"cross({vector(depth - 1)}, {vector(depth - 1)})"
+
+    bodies = []
+    for n in range(15):
+        names["s"], names["v"] = [], []
+        lines = [f"def m{n}(i, j):", f"    skip_when({scalar(1)} > 1.5)", f"    a = {scalar(2)}"]
+        names["s"].append("a")
+        lines.append(f"    w = {vector(1)}")
+        names["v"].append("w")
+        lines += [f"    tangential_spring_displacement[i, j] = {vector(2)}", f"    if is_sticking[i, j] == 1:", f"        a = {scalar(2)}",
+                  f"        impact_velocity_magnitude[i, j] = {scalar(2)}", "    else:", f"        apply(torque, {vector(2)})",
+                  f"    is_sticking[i, j] = select({scalar(1)} < {scalar(1)}, 1, 0)", f"    apply(force, w * a + tangential_spring_displacement[i, j])",
+                  f"    apply(torque, cross(contact_point(i, j) - position, {vector(1)}))"]
+        bodies.append("\n".join(lines))
+    mod_path = tmp_path / "fuzz_models.py"
+    mod_path.write_text("\n\n\n".join(bodies) + "\n")
+    spec = importlib.util.spec_from_file_location("fuzz_models", mod_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class V:
+        def __init__(self, c):
+            self.c = [float(x) for x in c]
+
+        def __add__(self, o):
+            return V([x + y for x, y in zip(self.c, o.c)])
+
+        def __sub__(self, o):
+            if not isinstance(o, V):
+                return NotImplemented                     # a bare property (apply context): Side.__rsub__
+            return V([x - y for x, y in zip(self.c, o.c)])
+
+        def __mul__(self, s):
+            return V([x * s for x in self.c])
+
+        def __rmul__(self, s):
+            return V([s * x for x in self.c])
+
+        def __getitem__(self, k):
+            return self.c[k]
+
+    class Skip(Exception):
+        pass
+
+    def dot(p, q):
+        return (p[0] * q[0] + p[1] * q[1]) + p[2] * q[2]
+
+    rng = np.random.default_rng(8)
+    npairs = 200
+    X = {k: rng.standard_normal((npairs, 3)) for k in ("xi", "vi", "wi", "xj", "vj", "wj", "n", "cp", "tsd")}
+    S = {k: 0.5 + rng.random(npairs) for k in ("mi", "ri", "mj", "rj", "delta", "ivm")}
+    stick = rng.integers(0, 2, npairs).astype(np.int32)
+    tij = rng.integers(0, 4, npairs).astype(np.int32)
+    fric = [0.1, 0.5, 0.25, 0.75]
+    checked = 0
+    for n in range(15):
+        fn = getattr(mod, f"m{n}")
+        try:
+            name, code = kernelgen.translate_dem_model(fn, DEM_STORAGE, DEM_CONTACT, {"fric": fric}, {"kn": 3.5})
+        except kernelgen.KernelGenError:
+            continue
+        assert backend.jit_check_dem_model(code, name) > 10000
+        cpp = tmp_path / f"{name}.cpp"
+        cpp.write_text('#include "jit_host_emulation.h"\n' + code + f'''
+extern "C" void run(int np_, const double *xi, const double *vi, const double *wi, const double *mi, const double *ri, const double *xj,
+                    const double *vj, const double *wj, const double *mj, const double *rj, const double *nn, const double *cp, const double *delta,
+                    const int *tij, double *tsd, double *ivm, int *stick, double *F, double *T, int *kept) {{
+    for(int k = 0; k < np_; k++) {{
+        kept[k] = {name}(xi + 3 * k, vi + 3 * k, wi + 3 * k, mi[k], ri[k], xj + 3 * k, vj + 3 * k, wj + 3 * k, mj[k], rj[k], nn + 3 * k, cp + 3 * k,
+                         delta[k], tij[k], tsd + 3 * k, ivm + k, stick + k, F + 3 * k, T + 3 * k) ? 1 : 0;
+    }}
+}}
+''')
+        so = tmp_path / f"{name}.so"
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-I" + os.path.join(here, "host"), str(cpp), "-o", str(so)],
+                       check=True)
+        lib = ctypes.CDLL(str(so))
+        lib.run.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 20
+        g_tsd, g_ivm, g_stick = X["tsd"].copy(), S["ivm"].copy(), stick.copy()
+        F, T, kept = np.zeros((npairs, 3)), np.zeros((npairs, 3)), np.zeros(npairs, np.int32)
+        lib.run(npairs, _ptr(X["xi"]), _ptr(X["vi"]), _ptr(X["wi"]), _ptr(S["mi"]), _ptr(S["ri"]), _ptr(X["xj"]), _ptr(X["vj"]), _ptr(X["wj"]),
+                _ptr(S["mj"]), _ptr(S["rj"]), _ptr(X["n"]), _ptr(X["cp"]), _ptr(S["delta"]), _ptr(tij), _ptr(g_tsd), _ptr(g_ivm), _ptr(g_stick), _ptr(F),
+                _ptr(T), _ptr(kept))
+        # ---- CPython on the same pairs ----
+        p_tsd, p_ivm, p_stick = X["tsd"].copy(), S["ivm"].copy(), stick.copy()
+        pF, pT, p_kept = np.zeros((npairs, 3)), np.zeros((npairs, 3)), np.zeros(npairs, np.int32)
+        for k in range(npairs):
+            acc = {"force": [0.0] * 3, "torque": [0.0] * 3, "first": {"force": True, "torque": True}}
+
+            class Side:
+                def __init__(self, a_i, a_j, vec):
+                    self.a_i, self.a_j, self.vec = a_i, a_j, vec
+
+                def __getitem__(self, who):
+                    a = self.a_i if who == "i" else self.a_j
+                    return V(a[k]) if self.vec else float(a[k])
+
+                # a bare property inside apply() means prop[i]
+                def __rsub__(self, other):
+                    return other - V(self.a_i[k])
+
+            class Contact:
+                def __init__(self, kind):
+                    self.kind = kind
+
+                def __getitem__(self, _ij):
+                    return V(p_tsd[k]) if self.kind == "tsd" else (float(p_ivm[k]) if self.kind == "ivm" else int(p_stick[k]))
+
+                def __setitem__(self, _ij, v):
+                    if self.kind == "tsd":
+                        p_tsd[k] = v.c
+                    elif self.kind == "ivm":
+                        p_ivm[k] = v
+                    else:
+                        p_stick[k] = int(v)
+
+            class Fric:
+                def __getitem__(self, _ij):
+                    return fric[tij[k]]
+
+            def apply_(target, v):
+                if acc["first"][target]:
+                    acc[target] = list(v.c)
+                    acc["first"][target] = False
+                else:
+                    acc[target] = [x + y for x, y in zip(acc[target], v.c)]
+
+            def skip_when(c):
+                if c:
+                    raise Skip()
+
+            env = {"i": "i", "j": "j", "position": Side(X["xi"], X["xj"], True), "linear_velocity": Side(X["vi"], X["vj"], True),
+                   "angular_velocity": Side(X["wi"], X["wj"], True), "mass": Side(S["mi"], S["mj"], False), "radius": Side(S["ri"], S["rj"], False),
+                   "tangential_spring_displacement": Contact("tsd"), "impact_velocity_magnitude": Contact("ivm"), "is_sticking": Contact("stick"),
+                   "fric": Fric(), "kn": 3.5, "force": "force", "torque": "torque", "apply": apply_, "skip_when": skip_when,
+                   "select": lambda c, x, y: x if c else y, "abs": abs, "dot": dot, "length": lambda p: math.sqrt(dot(p, p)),
+                   "cross": lambda p, q: V([p[1] * q[2] - p[2] * q[1], p[2] * q[0] - p[0] * q[2], p[0] * q[1] - p[1] * q[0]]),
+                   "contact_normal": lambda i, j: V(X["n"][k]), "contact_point": lambda i, j: V(X["cp"][k]),
+                   "penetration_depth": lambda i, j: -float(S["delta"][k])}
+            fn.__globals__.update(env)
+            try:
+                fn("i", "j")
+                p_kept[k] = 1
+            except Skip:
+                p_kept[k] = 0
+            pF[k], pT[k] = acc["force"], acc["torque"]
+        assert np.array_equal(kept, p_kept), (n, bodies[n])
+        kept_total = kept_total + int(kept.sum()) if "kept_total" in dir() else int(kept.sum())
+        live = kept == 1
+        for got, want in ((F[live], pF[live]), (T[live], pT[live]), (g_tsd, p_tsd), (g_ivm, p_ivm), (g_stick, p_stick)):
+            assert np.array_equal(got, want), (n, bodies[n])
+        checked += 1
+    assert checked >= 8 and kept_total > 500
