@@ -1339,3 +1339,66 @@ extern "C" void run(int np_, const double *xi, const double *vi, const double *w
             assert np.array_equal(got, want), (n, bodies[n])
         checked += 1
     assert checked >= 8 and kept_total > 500
+
+
+def _ints_kernel(i):
+    k = (uid[i] % 5) + (uid[i] & 6) * 2 - (uid[i] | 9) + (uid[i] ^ 3) + (~uid[i] & 7)
+    m = select(k > 3, k, 0 - k)
+    mass[i] = mass[i] * m + abs(0 - k) + min(k, 2, uid[i]) + max(k, 7) + sqrt(uid[i] + 1)
+    if uid[i] % 2 == 0 and not (k == 4) or shape[i] == 2:
+        linear_velocity[i] = linear_velocity[i] * (1 + k)
+    else:
+        m = m * 3
+    force[i] = force[i] * m
+
+
+def test_integer_expressions_generated_code_equals_python_arithmetic(tmp_path):
+    """Integer properties and operators (% & | ^ ~, comparisons, and / or / not, select / min / max / abs on integers, promotion
+    to real): the generated kernel against CPython running the same function on non-negative uids (where C and Python agree on %)."""
+    import math
+    import numpy as np
+    storage = {"position": "pos", "linear_velocity": "vel", "force": "force", "mass": "mass", "uid": "uid", "shape": "shape"}
+    _, name, code = kernelgen.translate(_ints_kernel, storage, {}, 1, {}, backend.jit_prelude())
+    assert backend.jit_check(code) > 1000
+    run = _host_kernel(tmp_path, name, code)
+    rng = np.random.default_rng(4)
+    n = 300
+    pos4 = np.zeros((n, 4))
+    vel, force, mass = rng.standard_normal((3, n)), rng.standard_normal((3, n)), 0.5 + rng.random(n)
+    uid = rng.integers(0, 5000, n).astype(np.int32)
+    shape = rng.integers(0, 3, n).astype(np.int32)
+    flags = np.zeros(n, np.int32)
+    g_vel, g_force, g_mass = vel.copy(), force.copy(), mass.copy()
+    run(n, 0, n, 0.0, _ptr(pos4), _ptr(g_vel), _ptr(g_force), _ptr(g_mass), _ptr(flags), None, None, None, _ptr(uid), _ptr(shape))
+
+    class Vec:
+        def __init__(self, rows, k):
+            self.rows, self.k = rows, k
+
+        def __mul__(self, s):
+            return [float(x) * s for x in self.rows[:, self.k]]
+
+    class VProp:
+        def __init__(self, rows):
+            self.rows = rows
+
+        def __getitem__(self, k):
+            return Vec(self.rows, k)
+
+        def __setitem__(self, k, v):
+            self.rows[:, k] = v
+
+    def fold(better):
+        def f(*args):
+            e = args[0]
+            for x in args[1:]:
+                e = x if better(x, e) else e
+            return e
+        return f
+
+    env = {"uid": [int(x) for x in uid], "shape": [int(x) for x in shape], "mass": mass, "linear_velocity": VProp(vel), "force": VProp(force),
+           "select": lambda c, x, y: x if c else y, "min": fold(lambda x, e: x < e), "max": fold(lambda x, e: x > e), "abs": abs, "sqrt": math.sqrt}
+    _ints_kernel.__globals__.update(env)
+    for i in range(n):
+        _ints_kernel(i)
+    assert np.array_equal(g_mass, mass) and np.array_equal(g_vel, vel) and np.array_equal(g_force, force)
