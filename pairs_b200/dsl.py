@@ -489,9 +489,59 @@ class Simulation:
             raise DslError(f"{entry['name']}: '{name}' is not a registered property")
         return name
 
+    def _roles_fit_the_storage(self, e):
+        """A recognised kernel runs as hand-written CUDA on FIXED arrays.  Recognition is structural (names are free), so the roles
+        it bound must be exactly the properties those arrays hold -- e.g. a body that integrates some other vector property with the
+        text of initial_integrate, or that multiplies torque * inv_inertia instead of inv_inertia * torque, matches the template but
+        is a different computation.  Such kernels are generated instead."""
+        roles = e["roles"]
+        if self.use_contact_history:
+            fixed = {"position": self.position_name, "velocity": "linear_velocity", "angular_velocity": "angular_velocity", "force": "force",
+                     "torque": "torque", "mass": "mass", "radius": "radius", "inv_inertia": "inv_inertia", "rotation_matrix": "rotation_matrix",
+                     "rotation_quat": "rotation_quat"}
+            types = {"position": Types.Vector, "velocity": Types.Vector, "angular_velocity": Types.Vector, "force": Types.Vector,
+                     "torque": Types.Vector, "mass": Types.Real, "radius": Types.Real, "inv_inertia": Types.Matrix,
+                     "rotation_matrix": Types.Matrix, "rotation_quat": Types.Quaternion}
+            contact = {"sticking": Types.Int32, "tsd": Types.Vector, "ivm": Types.Real}
+            for role, name in roles.items():
+                if role in fixed:
+                    if name != fixed[role] or name not in self.props or self.props[name].type != types[role]:
+                        return False
+                elif role in contact:
+                    if name not in self.contact_props or self.contact_props[name][0] != contact[role]:
+                        return False
+                elif role in ("friction_static", "friction_dynamic"):
+                    if name not in self.feature_props:
+                        return False
+                elif name in self.props or name in self.contact_props or name in self.feature_props:
+                    return False                      # a symbol role (dt, pi, kappa, ...) bound to a property
+            return True
+        storage = self._device_storage()
+        slots = {"position": "pos", "velocity": "vel", "force": "force", "mass": "mass"}
+        for role, name in roles.items():
+            if role in slots:
+                if storage.get(name) != slots[role]:
+                    return False
+            elif role in ("epsilon", "sigma6") and e["family"] == "lennard_jones":
+                if name not in self.feature_props:
+                    return False
+            elif name in self.props or name in self.feature_props:
+                return False
+        return True
+
+    def _reclassify(self):
+        """Recognised kernels whose roles do not fit the fixed arrays go through the generic path (see _roles_fit_the_storage)."""
+        for group, generic in ((self.pre_step, None), (self.functions, None), (self.setup_functions, "generic_setup")):
+            for e in group:
+                if e["family"].startswith("generic") or self._roles_fit_the_storage(e):
+                    continue
+                nparams = len(inspect.signature(e["func"]).parameters)
+                e["family"], e["roles"] = generic or ("generic_pair" if nparams == 2 else "generic_particle"), {}
+
     # -- generate(): plan + run on the GPU(s) --
     def generate(self):
         assert self._target is not None, "Target not specified!"
+        self._reclassify()
         if not self._target.is_gpu():
             raise DslError("this backend executes on B200 GPUs only: use pairs.target_gpu() (there is no CPU path; the "
                            "reference's own CPU build is available as the parity oracle under oracle/)")

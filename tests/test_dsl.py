@@ -320,3 +320,98 @@ def test_dem_script_with_a_reneighbouring_interval_is_planned_module_by_module()
     import dem_script
     psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10, reneighbor=3)
     assert psim.reneighbor_frequency == 3 and [e["family"] for e in psim.functions] == ["gravity", "linear_spring_dashpot", "euler"]
+
+
+def test_mutated_example_kernels_are_not_mistaken_for_the_hand_written_families(tmp_path):
+    """The hand-written CUDA kernels are bound by RECOGNISING the kernel text.  Every single-point mutation of the seven example
+    kernels -- a literal changed, an operator flipped, a comparison reversed, two different operands swapped -- must fall out of its
+    family (and go to the generic path) instead of silently running the unmodified hand-written kernel."""
+    import copy
+    import importlib.util
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    import lj_script
+    flip = {ast.Add: ast.Sub, ast.Sub: ast.Add, ast.Mult: ast.Div, ast.Div: ast.Mult, ast.Lt: ast.Gt, ast.Gt: ast.Lt, ast.LtE: ast.GtE,
+            ast.GtE: ast.LtE, ast.Eq: ast.NotEq, ast.And: ast.Or, ast.Or: ast.And}
+    total = by_roles = by_symbols = 0
+    for mod, names in ((lj_script, ("lennard_jones", "initial_integrate", "final_integrate")),
+                       (dem_script, ("update_mass_and_inertia", "linear_spring_dashpot", "euler", "gravity"))):
+        src = open(mod.__file__).read()
+        tree = ast.parse(src)
+        for fdef in [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]:
+            family, orig_roles = dsl.recognise(getattr(mod, fdef.name))
+            sites = [k for k, n in enumerate(ast.walk(fdef)) if isinstance(n, (ast.Constant, ast.BinOp, ast.Compare, ast.BoolOp, ast.AugAssign))]
+            mutants = []
+            for site in sites:
+                for kind in ("value", "swap"):
+                    m = copy.deepcopy(fdef)
+                    node = list(ast.walk(m))[site]
+                    if kind == "value":
+                        if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+                            node.value = node.value + 1
+                        elif isinstance(node, (ast.BinOp, ast.AugAssign)) and type(node.op) in flip:
+                            node.op = flip[type(node.op)]()
+                        elif isinstance(node, ast.BoolOp):
+                            node.op = flip[type(node.op)]()
+                        elif isinstance(node, ast.Compare) and type(node.ops[0]) in flip:
+                            node.ops = [flip[type(node.ops[0])]()]
+                        else:
+                            continue
+                    else:
+                        if not isinstance(node, ast.BinOp) or ast.dump(node.left) == ast.dump(node.right):
+                            continue
+                        node.left, node.right = node.right, node.left
+                    mutants.append(m)
+            assert len(mutants) >= 3, fdef.name
+            text = "\n\n\n".join(ast.unparse(ast.fix_missing_locations(m)).replace(f"def {fdef.name}(", f"def mutant_{k}(") for k, m in enumerate(mutants))
+            path = tmp_path / f"mutants_{fdef.name}.py"
+            path.write_text(text + "\n")
+            spec = importlib.util.spec_from_file_location(path.stem, path)
+            mm = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mm)
+            psim = mod.build("gpu") if mod is lj_script else mod.build("gpu", (0.1, 0.015, 0.04), 10)
+            for k in range(len(mutants)):
+                try:
+                    got, roles = dsl.recognise(getattr(mm, f"mutant_{k}"))
+                except dsl.DslError:
+                    got, roles = None, {}
+                # still the family's text up to names: then the names must be what gives it away (roles bound to the wrong arrays)
+                if got == family and psim._roles_fit_the_storage({"family": got, "roles": roles}):
+                    # ... or two SYMBOLS changed places (e.g. densityFluid_SI - densityParticle_SI): the hand-written kernel then
+                    # receives their values in the exchanged roles, which is what the mutant computes
+                    changed = [r for r in roles if roles[r] != orig_roles[r]]
+                    assert changed and all(roles[r] not in psim.props and roles[r] not in psim.feature_props and
+                                           roles[r] not in psim.contact_props for r in changed), (fdef.name, ast.unparse(mutants[k]))
+                    by_symbols += 1
+                elif got == family:
+                    by_roles += 1
+                total += 1
+    assert total > 150 and by_roles >= 1
+
+
+def test_recognised_kernels_keep_their_family_only_on_the_arrays_they_were_written_for():
+    """Stock scripts: every kernel stays a hand-written family.  The text of initial_integrate applied to ANOTHER vector property, or
+    dem.py's euler with torque and inv_inertia exchanged, is recognised structurally but re-classified as a generic kernel."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    import lj_legacy_script
+    import lj_script
+    for psim, want in ((lj_script.build("gpu"), ["initial_integrate", "lennard_jones", "final_integrate"]),
+                       (dem_script.build("gpu", (0.1, 0.015, 0.04), 10), ["gravity", "linear_spring_dashpot", "euler"])):
+        psim._reclassify()
+        assert [e["family"] for e in psim.pre_step + psim.functions] == want
+        assert all(not e["family"].startswith("generic") for e in psim.setup_functions)
+    legacy = lj_legacy_script.build("gpu", 4, 3)
+    legacy._reclassify()
+    assert [e["family"] for e in legacy.functions] == ["lj_legacy", "euler_legacy"]
+
+    def drift(i):
+        path[i] += (dt * 0.5) * force[i] / mass[i]
+        position[i] += dt * path[i]
+
+    psim = lj_script.build("gpu")
+    psim.add_property("path", pairs.vector())
+    psim.compute(drift, symbols={"dt": 0.005})
+    assert psim.functions[-1]["family"] == "initial_integrate" and psim.functions[-1]["roles"]["velocity"] == "path"
+    psim._reclassify()
+    assert [e["family"] for e in psim.functions] == ["lennard_jones", "final_integrate", "generic_particle"]
