@@ -209,7 +209,8 @@ int pb_jit_set_dem_model(pb_ctx *ctx, const char *model_source, const char *mode
  * "overlap_comm" (0/1), "profiler" (0/1: every stage also opens an NVTX range named like the reference's timers -- Simulation.enable_profiler(),
  * sim/simulation.py:116-117, LIKWID markers there), "cell_zsub" (1..32, applies from the next pb_setup_cells), "stage_lists" (0/1), "dem_sort_every"
  * (DEM: iterations between two spatial re-sorts of the locals, 0 = never, default 200), "dem_fuse" (0/1: pb_dem_run folds the
- * per-particle modules around the contact evaluation into the contact kernel; results are identical), "dem_force_maxreg" (0 = off: the DEM
+ * per-particle modules around the contact evaluation into the contact kernel; results are identical), "pair_lists" (0/1, experimental: the fused Lennard-Jones kernel of pb_md_run walks ONE union list per pair of consecutive cell-sorted
+ * particles -- fewer position gathers, the bound of the per-particle kernel; applies from the next list build), "dem_force_maxreg" (0 = off: the DEM
  * contact kernel is re-built at run time with this register cap -- occupancy experiments; after pb_dem_enable). */
 int pb_set_option(pb_ctx *ctx, const char *name, int value);
 

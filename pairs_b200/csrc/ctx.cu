@@ -81,7 +81,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
                     ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
                     ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->d_fric_static,
-                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt};
+                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt, ctx->pneigh, ctx->pnum};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }

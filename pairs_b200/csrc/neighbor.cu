@@ -19,6 +19,8 @@
 
 #include "ctx.cuh"
 
+int pb_build_pair_lists(pb_ctx *ctx, double cutsq_lists);      // pair_lists.cu (option "pair_lists")
+
 struct PbFaces {
     double lo[3], hi[3];   // subdom_min + margin, subdom_max - margin
 };
@@ -233,6 +235,8 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
         ctx->max_neigh = ctx->h_scalars[0];
         if(ctx->max_neigh <= ctx->ncap) {
             if(ctx->world > 1 && ctx->overlap_comm && ctx->lanes == 1) { PB_TRY(pb_split_groups(ctx, ngroups)); }
+            ctx->pairs_n = -1;
+            if(ctx->pair_lists && !ctx->half_lists && ctx->lanes == 1) { PB_TRY(pb_build_pair_lists(ctx, cutsq)); }
             return 0;
         }
         // capacity-overflow protocol (transformations/modules.py:159-203): grow to twice the need and re-run the module

@@ -5,7 +5,8 @@
 #    vocabulary, generated DEM contact models and per-particle kernels in DEM scripts: tests/test_gpu_props.py with the xfail
 #    marker ignored
 # 2. the whole GPU suite (the border / exchange kernels got a run-time record stride)
-# 3. the generic path and the user-property rows next to the hand-written kernels (tools/bench_generic.py)
+# 3. per-particle vs pair lists on the 4 M-atom workload (tools/bench_pair_lists.py): the experiment DESIGN.md 6b item 2 describes
+# 3b. the generic path and the user-property rows next to the hand-written kernels (tools/bench_generic.py)
 # 4. the headline bench line, to see that nothing moved
 # Outputs land in gpurun_out/.  For 2 or 4 GPUs: gpurun --gpus 2 -- 'python -m pytest tests/test_gpu_props.py -q --runxfail -k between_ranks'
 mkdir -p gpurun_out
@@ -15,6 +16,8 @@ tail -30 gpurun_out/props_gpu.log
 timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/gpu_suite.log 2>&1
 echo "suite exit $?" >> gpurun_out/gpu_suite.log
 tail -5 gpurun_out/gpu_suite.log
+timeout 300 python tools/bench_pair_lists.py 100 > gpurun_out/bench_pair_lists.json 2> gpurun_out/bench_pair_lists.err
+tail -c 1200 gpurun_out/bench_pair_lists.json
 timeout 600 python tools/bench_generic.py 63 100 > gpurun_out/bench_generic.json 2> gpurun_out/bench_generic.err
 tail -c 1500 gpurun_out/bench_generic.json
 timeout 600 python bench.py --steps 100 --warmup 20 > gpurun_out/bench_next.json 2> gpurun_out/bench_next.err
