@@ -25,17 +25,18 @@ sys.path.insert(0, ".")
 from pairs_b200 import backend
 nx = 63
 L = nx * pow(4.0 / 0.8442, 1.0 / 3.0)
-for on in (0, 1):
-    ctx = backend.Context(0)
-    ctx.init_domain([0, L, 0, L, 0, L])
-    ctx.set_option("pair_lists", on)
-    ctx.copper_fcc_lattice(nx, nx, nx, 0.8442, 4)
-    ctx.adjust_thermo(1.44)
-    ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
-    ctx.md_run(0, 30, 0.005, 2.5, 2.8, 2.8, 20, 0)
+ctx = backend.Context(0)
+ctx.init_domain([0, L, 0, L, 0, L])
+ctx.set_option("pair_lists", int(sys.argv[1]))
+ctx.copper_fcc_lattice(nx, nx, nx, 0.8442, 4)
+ctx.adjust_thermo(1.44)
+ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
+ctx.md_run(0, 30, 0.005, 2.5, 2.8, 2.8, 20, 0)
 PY
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pb_k_lj_pairs|pb_k_lennard_jones' -s 20 -c 2 -f \
-    -o gpurun_out/prof_pair_lists python /tmp/pl_prof.py > gpurun_out/ncu_pair_lists.log 2>&1
+for on in 0 1; do
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:'pb_k_lj_pairs|pb_k_lennard_jones' -s 22 -c 2 -f \
+        -o gpurun_out/prof_force_pairlists_$on python /tmp/pl_prof.py $on > gpurun_out/ncu_force_pairlists_$on.log 2>&1
+done
 timeout 600 python tools/bench_generic.py 63 100 > gpurun_out/bench_generic.json 2> gpurun_out/bench_generic.err
 tail -c 1500 gpurun_out/bench_generic.json
 timeout 600 python bench.py --steps 100 --warmup 20 > gpurun_out/bench_next.json 2> gpurun_out/bench_next.err
