@@ -25,6 +25,8 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
               vector; reals and a vector integrated per particle) -> generic kernels on the user-property rows (csrc/props.cu)
   md_vocab_t1   md_t1 with kernels that use the rest of the generic vocabulary (skip_when, cross, is_point_mass, integer properties
               and operators, and / or / not, n-ary min / max, normalized, length, ...): module-level pin of pairs_b200/kernelgen.py
+  md_cells_t1 md_t1 (60 steps) with psim.build_cell_lists(cutoff_radius + skin) instead of build_neighbor_lists: the pair kernel walks the
+              cell lists (sim/interaction.py:92-118), cells rebuilt at the reneighbouring interval
   md_half_t1  md_t1 with psim.compute_half() enabled (the line is commented out in the stock example)
   md_bench  nx=ny=nz=63 (1000188 atoms), up to 2000 steps, thermo every step (the hook that lets
             bench.py time a bounded number of loop iterations and then leave the loop)
@@ -58,8 +60,10 @@ def _sub(text, pattern, repl, count=1):
     return new
 
 
-def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False):
+def md_variant(nx, steps, thermo, reneigh, pcap=None, half=False, cells_only=False):
     def patch(text):
+        if cells_only:  # no Verlet lists: the pair kernel walks cell 0 + the 27 stencil cells (sim/interaction.py:92-118)
+            text = _sub(text, r"^psim\.build_neighbor_lists\(cutoff_radius \+ skin\)", "psim.build_cell_lists(cutoff_radius + skin)")
         if half:        # the line is present but commented out in the stock example (examples/md.py:58)
             text = _sub(text, r"^#psim\.compute_half\(\)", "psim.compute_half()")
         text = _sub(text, r"^nx = \d+", f"nx = {nx}")
@@ -261,6 +265,8 @@ VARIANTS = {
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
+    # cell lists without neighbour lists: every pair of the 27 stencil cells inside the cutoff, cells rebuilt every 20 iterations
+    "md_cells_t1": ("examples/md.py", md_variant(8, 60, 1, 20, cells_only=True), [], False),
     "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), ["-DREF_LJ_MODULE"], False),
     "md_props_t1": ("examples/md.py", md_props_variant(8, 100), ["modules:init_scale,lennard_jones,initial_integrate,final_integrate"], False),
     "md_vocab_t1": ("examples/md.py", md_vocab_variant(8, 10), ["modules:lennard_jones,final_integrate"], False),

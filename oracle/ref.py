@@ -102,7 +102,7 @@ class RefProgram:
         return self.lib.ref_run(cb, None, 1 if quiet else 0)
 
     def run_collect_thermo(self, props=(("position", 3), ("linear_velocity", 3), ("force", 3), ("mass", 1)),
-                           int_props=("type", "flags"), with_ghosts=False, steps=None):
+                           int_props=("type", "flags"), with_ghosts=False, steps=None, with_lists=True):
         """Full run; returns one snapshot dict per compute_thermo call (i.e. per thermo step).
 
         Snapshots are taken right after final_integrate of that step, so `force` is that step's
@@ -123,7 +123,7 @@ class RefProgram:
                 s[name] = self.prop(name, n, w)
             for name in int_props:
                 s[name] = self.prop(name, n, 1, np.int32)
-            if not snaps:        # the lists of the first iteration (built from the initial positions)
+            if not snaps and with_lists:        # the lists of the first iteration (built from the initial positions)
                 cap = self.array("neighborlists", np.int32).size // max(self.array("numneighs", np.int32).size, 1)
                 s["numneighs"] = self.array("numneighs", np.int32, nlocal)
                 s["neighborlists"] = self.array("neighborlists", np.int32, nlocal * cap).reshape(nlocal, cap)

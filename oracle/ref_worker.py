@@ -78,7 +78,9 @@ def _main(argv):
         nsteps = int(argv[3]) if len(argv) > 3 and int(argv[3]) >= 0 else None
         extra = tuple((x.split(":")[0], int(x.split(":")[1])) for x in argv[4].split(",")) if len(argv) > 4 and argv[4] else ()
         extra_int = tuple(x for x in argv[5].split(",") if x) if len(argv) > 5 else ()
-        snaps = prog.run_collect_thermo(props=BASE_PROPS + extra, int_props=("type", "flags") + extra_int, steps=nsteps)
+        # a program without Verlet lists (variant md_cells_t1) has no neighbour-list arrays to record
+        snaps = prog.run_collect_thermo(props=BASE_PROPS + extra, int_props=("type", "flags") + extra_int, steps=nsteps,
+                                        with_lists="cells" not in variant)
         d = {"count": len(snaps), "nlocal": np.array([s["nlocal"] for s in snaps]), "nghost": np.array([s["nghost"] for s in snaps])}
         for i, s in enumerate(snaps):
             for k in [x for x, _ in BASE_PROPS + extra] + ["type"] + list(extra_int):

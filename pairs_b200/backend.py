@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libpairs_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu", "props.cu", "pair_lists.cu"]
+SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu", "props.cu", "pair_lists.cu", "tile_lists.cu"]
 
 # --fmad=false: fp64 multiplies and adds are never contracted, so per-operation results equal the reference CPU
 # build compiled with -ffp-contract=off (the parity contract).

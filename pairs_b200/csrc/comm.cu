@@ -409,6 +409,7 @@ extern "C" int pb_exchange(pb_ctx *ctx) {
     ctx->nsend_all = 0;
     ctx->cells_n = 0;
     ctx->neigh_n = -1;
+    ctx->tiles_n = -1;
     ctx->ghosts_in_alt = false;
     for(int dim = 0; dim < 3; dim++) {
         if(ctx->nranks[dim] == 1) {

@@ -81,7 +81,9 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
                     ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
                     ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->d_fric_static,
-                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt, ctx->pneigh, ctx->pnum};
+                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt, ctx->pneigh, ctx->pnum,
+                    ctx->tiles, ctx->tile_lvl, ctx->tile_cnt, ctx->tile_off, ctx->tile_pad, ctx->tile_row, ctx->twords, ctx->tile_flag,
+                    ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
@@ -312,6 +314,7 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     ctx->nghost = 0;
     ctx->nsend_all = 0;
     ctx->neigh_n = 0;
+    ctx->tiles_n = -1;
     ctx->cells_n = 0;
     if(n == 0) { return 0; }
     const int T = 256, B = pb_blocks(n, T);
@@ -407,7 +410,7 @@ extern "C" int pb_download_int(pb_ctx *ctx, const char *name, int *out, int with
     else if(nm == "shape") { src = ctx->shape; }
     else if(nm == "tag") { src = ctx->tag; }
     else if(nm == "particle_cell") { src = ctx->particle_cell; n = std::min(n, ctx->cells_n); }
-    else if(nm == "numneighs") { src = ctx->numneigh; n = std::min(ctx->nlocal, ctx->neigh_n); }
+    else if(nm == "numneighs") { src = ctx->numneigh; n = std::min(ctx->nlocal, std::max(ctx->neigh_n, ctx->tiles_n)); }
     else { ctx->set_error("pb_download_int: unknown property " + nm); return -1; }
     if(n == 0) { return 0; }
     PB_CHECK(cudaMemcpyAsync(out, src, sizeof(int) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));

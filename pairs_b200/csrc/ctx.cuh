@@ -121,6 +121,26 @@ struct pb_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_sync = nullptr;
 
+    // ---- tile lists (tile_lists.cu): the list format of the MD hot path.  A tile = the cells [za, zb] of a 2 x 2 block of cell
+    //      columns holding <= PB_TILE_M particles; its CTA stages the 4 x 4 columns around it in shared memory and walks 16-bit
+    //      tile-relative neighbour lists (4 entries per 64-bit word, sliced ELLPACK over list ROWS = tile-major particle order).
+    //      The 32-bit per-particle lists above are then built only on demand (pb_require_neigh32). ----
+    bool tile_lists = true;       // option "tile_lists"
+    bool lj_fma = true;           // option "lj_fma": fused multiply-adds + Newton reciprocal in the pair term (md_math.h)
+    struct PbTile *tiles = nullptr;
+    int tiles_cap = 0, ntiles = 0, tile_rows = 0, tile_T4 = 0;
+    int *tile_lvl = nullptr;      // [2][nsc * dim2] particles per (super-column, z level): core cells / staged cells
+    int *tile_cnt = nullptr, *tile_off = nullptr;   // [nsc + 1] tiles per super-column and their prefix sums
+    int *tile_pad = nullptr, *tile_row = nullptr;   // [ntiles + 1] rows per tile (core rounded up to 32) and their prefix sums
+    int tile_sc_cap = 0, tile_lvl_cap = 0;
+    unsigned long long *twords = nullptr;
+    size_t twords_bytes = 0;
+    int tiles_n = -1;             // nlocal when the tile lists were built (-1: none)
+    double list_cutoff = 0.0;     // cutoff of the last pb_build_neighbor_lists (a lazy 32-bit build uses it)
+    int *tile_flag = nullptr, *tile_scan = nullptr, *tiles_interior = nullptr, *tiles_boundary = nullptr;   // overlap split, per tile
+    int tile_flag_cap = 0, n_tiles_interior = 0, n_tiles_boundary = 0;
+    bool tile_split_valid = false;
+
     // ---- DEM (examples/dem.py): extra particle properties + per-particle contact history ----
     bool dem = false;
     int ccontacts = 0;            // contact capacity per particle (neighbor_capacity of pairs.simulation(), 20 in dem.py)
@@ -192,6 +212,17 @@ struct pb_ctx {
 
     void set_error(const std::string &e) { err = e; }
 };
+
+// tile lists (tile_lists.cu)
+struct PbTile { int X0, Y0, za, zb, row_base, ncore; };
+static const int PB_TILE_M = 256;          // threads per CTA = most particles of a tile
+static const int PB_TILE_CAP = 2048;       // staged particles per tile (slots are 12-bit: <= 4096)
+int pb_build_tile_lists(pb_ctx *ctx, double cutoff);        // 0 built, 1 not applicable here (caller takes the per-particle path)
+int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int part);
+int pb_tile_finish_split(pb_ctx *ctx);
+int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity);
+int pb_require_neigh32(pb_ctx *ctx);                        // per-particle 32-bit lists for the kernels that walk them (built lazily)
+static inline bool pb_lists_valid(const pb_ctx *ctx) { return ctx->tiles_n == ctx->nlocal || ctx->neigh_n == ctx->nlocal; }
 
 static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record in MD (exchange: 12, borders: 11/15, sync: 6)
 // DEM exchange record: 12 base + radius 1 + angvel 3 + normal 3 + inv_inertia 9 + rotmat 9 + quat 4 + num_contacts 1 + 6 per slot

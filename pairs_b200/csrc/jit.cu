@@ -231,7 +231,8 @@ extern "C" int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff) {
     PbJitKernel &k = (*tab)[handle];
     PbStage st(ctx, k.name.c_str());
     if(kind == 0 || kind == 3) {
-        if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_jit_launch: neighbour lists are stale"); return -1; }
+        if(!pb_lists_valid(ctx)) { ctx->set_error("pb_jit_launch: neighbour lists are stale"); return -1; }
+        PB_TRY(pb_require_neigh32(ctx));      // generated pair kernels walk per-particle lists
         if(ctx->lanes != 1) { ctx->set_error("pb_jit_launch: user pair kernels need one lane per particle"); return -1; }
         if(ctx->half_lists != (kind == 3)) {
             ctx->set_error("pb_jit_launch: the kernel was generated for the other kind of neighbour lists (compute_half)");

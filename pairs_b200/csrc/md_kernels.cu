@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(128) pb_k_lennard_jones_half(int nlocal, int T
 int pb_materialise_force_reset(pb_ctx *ctx);
 
 static int pb_lennard_jones_half(pb_ctx *ctx, double cutsq) {
+    PB_TRY(pb_require_neigh32(ctx));
     if(ctx->lanes != 1) { ctx->set_error("compute_half needs lanes_per_particle = 1"); return -1; }
     PB_TRY(pb_materialise_force_reset(ctx));
     const int n = ctx->nlocal;
@@ -337,11 +338,21 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int 
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "lennard_jones");
     if(ctx->ntypes == 0) { ctx->set_error("pb_lennard_jones: pb_set_lj_params not called"); return -1; }
-    if(ctx->neigh_n != ctx->nlocal) { ctx->set_error("pb_lennard_jones: neighbour lists are stale"); return -1; }
+    if(!pb_lists_valid(ctx)) { ctx->set_error("pb_lennard_jones: neighbour lists are stale"); return -1; }
     if(ctx->nlocal == 0) { return 0; }
     const double cutsq = cutoff * cutoff;
     ctx->lj_groups = nullptr;
     ctx->lj_ngroups = 0;
+    if(ctx->tiles_n == ctx->nlocal) {          // the default path: tile lists (tile_lists.cu)
+        PB_TRY(pb_tile_lennard_jones(ctx, cutsq, dt, fuse, part));
+        if(part != 0) { return 0; }            // split launches: the caller finishes with pb_lj_finish_split once both are issued
+        ctx->force_is_zero = false;
+        if(fuse & 2) {
+            std::swap(ctx->pos, ctx->pos_alt);
+            ctx->ghosts_in_alt = true;
+        }
+        return 0;
+    }
     if(ctx->half_lists) {
         if(fuse != 0 || part != 0) { ctx->set_error("compute_half: the integrators cannot be fused / the grid cannot be split"); return -1; }
         return pb_lennard_jones_half(ctx, cutsq);
@@ -394,6 +405,7 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
         if(value != 1 && value != 2 && value != 4 && value != 8) { ctx->set_error("lanes_per_particle must be 1, 2, 4 or 8"); return -1; }
         ctx->lanes = value;
         ctx->neigh_n = -1;      // lists must be rebuilt in the new layout
+        ctx->tiles_n = -1;
         return 0;
     }
     if(nm == "lj_unroll") {
@@ -405,9 +417,12 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
     if(nm == "compute_half") {
         ctx->half_lists = value != 0;
         ctx->neigh_n = -1;      // lists must be rebuilt
+        ctx->tiles_n = -1;
         return 0;
     }
     if(nm == "stage_lists") { ctx->stage_lists = value != 0; return 0; }
+    if(nm == "tile_lists") { ctx->tile_lists = value != 0; ctx->tiles_n = -1; ctx->neigh_n = -1; return 0; }      // lists must be rebuilt
+    if(nm == "lj_fma") { ctx->lj_fma = value != 0; return 0; }
     if(nm == "profiler") { ctx->nvtx = value != 0; return 0; }
     if(nm == "pair_lists") { ctx->pair_lists = value != 0; ctx->pairs_n = -1; return 0; }      // applies from the next list build
     if(nm == "dem_force_maxreg") {       // occupancy experiments: NVRTC re-build of the contact kernel (built-in model) with a register cap
@@ -470,7 +485,8 @@ __global__ void __launch_bounds__(128) pb_k_lj_legacy(int nlocal, int T, int cap
 extern "C" int pb_lj_legacy(pb_ctx *ctx, double cutoff, double epsilon, double sigma6) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "lj");
-    if(ctx->neigh_n != ctx->nlocal || ctx->lanes != 1) { ctx->set_error("pb_lj_legacy: neighbour lists are stale (or lanes_per_particle != 1)"); return -1; }
+    if(!pb_lists_valid(ctx) || ctx->lanes != 1) { ctx->set_error("pb_lj_legacy: neighbour lists are stale (or lanes_per_particle != 1)"); return -1; }
+    PB_TRY(pb_require_neigh32(ctx));
     if(ctx->half_lists) { ctx->set_error("pb_lj_legacy: half lists are not supported by the legacy kernel"); return -1; }
     if(ctx->nlocal == 0) { return 0; }
     PB_LAUNCH(pb_k_lj_legacy, pb_blocks(ctx->nlocal, 128), 128, ctx->nlocal, ctx->nslots, ctx->pcap, cutoff * cutoff, epsilon, sigma6, ctx->pos,
@@ -660,7 +676,8 @@ __global__ void __launch_bounds__(256) pb_k_sum_pairs(int n, const double *__res
 extern "C" int pb_lj_energy_virial(pb_ctx *ctx, double cutoff, double *epot, double *virial) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "energy_virial");
-    if(ctx->ntypes == 0 || ctx->neigh_n != ctx->nlocal || ctx->lanes != 1) { ctx->set_error("pb_lj_energy_virial: LJ parameters / neighbour lists missing"); return -1; }
+    if(ctx->ntypes == 0 || !pb_lists_valid(ctx) || ctx->lanes != 1) { ctx->set_error("pb_lj_energy_virial: LJ parameters / neighbour lists missing"); return -1; }
+    PB_TRY(pb_require_neigh32(ctx));
     *epot = 0.0; *virial = 0.0;
     const int n = ctx->nlocal;
     if(n == 0) { return 0; }

@@ -31,8 +31,8 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
         // groups follow once the refresh has landed.  (The reference's communication is blocking)
         // (half lists: a particle's force is complete only after the whole grid, so nothing is fused or split)
         const bool fusing = ctx->fuse_integrate && !ctx->half_lists;
-        const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && fusing && ctx->groups_valid &&
-                             ctx->neigh_n == ctx->nlocal;
+        const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && fusing &&
+                             ((ctx->tiles_n == ctx->nlocal && ctx->tile_split_valid) || (ctx->groups_valid && ctx->neigh_n == ctx->nlocal));
         if(!reneigh && !overlap) { PB_TRY(pb_synchronize(ctx)); }
         PB_TRY(pb_reset_volatile(ctx));
         const bool thermo_now = p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0);

@@ -178,16 +178,11 @@ static int pb_split_groups(pb_ctx *ctx, int ngroups) {
     return 0;
 }
 
-extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
-    PB_CHECK(cudaSetDevice(ctx->device));
-    PbStage st(ctx, "build_neighbor_lists");
-    if(ctx->cells_n != ctx->nlocal + ctx->nghost) {
-        ctx->set_error("pb_build_neighbor_lists: cell lists are stale (call pb_build_cell_lists first)");
-        return -1;
-    }
+// The per-particle 32-bit lists (sliced ELLPACK): the list format of half lists, several lanes per particle, DEM-free contexts the
+// tile planner declines, and of every kernel that walks lists by particle (generated pair kernels, energy / virial, legacy lj).
+static int pb_build_neigh32(pb_ctx *ctx, double cutoff) {
     const int n = ctx->nlocal;
-    ctx->neigh_n = n;
-    if(n == 0) { ctx->max_neigh = 0; return 0; }
+    ctx->neigh_n = -1;
     const double cutsq = cutoff * cutoff;
     if(ctx->ncap <= 0) { ctx->ncap = 100; }
     const int ngroups = (n + 31) / 32;
@@ -204,7 +199,6 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
         faces.hi[d] = ctx->subdom[d * 2 + 1] - ctx->spacing;
     }
     ctx->groups_valid = false;
-    if(cutoff > ctx->spacing * (1.0 + 1e-12)) { ctx->set_error("pb_build_neighbor_lists: cutoff exceeds the cell spacing"); return -1; }
     PbBuildGeom bg;
     for(int d = 0; d < 3; d++) { bg.lo[d] = ctx->subdom[d * 2] - ctx->spacing; }
     bg.spacing = ctx->spacing;
@@ -236,6 +230,7 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
         if(ctx->max_neigh <= ctx->ncap) {
             if(ctx->world > 1 && ctx->overlap_comm && ctx->lanes == 1) { PB_TRY(pb_split_groups(ctx, ngroups)); }
             ctx->pairs_n = -1;
+            ctx->neigh_n = n;         // only now: an error return above must not leave half-built lists looking valid
             if(ctx->pair_lists && !ctx->half_lists && ctx->lanes == 1) { PB_TRY(pb_build_pair_lists(ctx, cutsq)); }
             return 0;
         }
@@ -244,6 +239,44 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
     }
     ctx->set_error("pb_build_neighbor_lists: capacity did not converge");
     return -1;
+}
+
+// BuildNeighborLists (sim/neighbor_lists.py:21-48).  Default: tile lists (tile_lists.cu); the per-particle format where those do
+// not apply.
+extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    PbStage st(ctx, "build_neighbor_lists");
+    if(ctx->cells_n != ctx->nlocal + ctx->nghost) {
+        ctx->set_error("pb_build_neighbor_lists: cell lists are stale (call pb_build_cell_lists first)");
+        return -1;
+    }
+    ctx->list_cutoff = cutoff;
+    ctx->neigh_n = -1;
+    ctx->tiles_n = -1;
+    ctx->pairs_n = -1;
+    ctx->groups_valid = false;
+    ctx->tile_split_valid = false;
+    if(ctx->nlocal == 0) { ctx->neigh_n = 0; ctx->max_neigh = 0; return 0; }
+    if(cutoff > ctx->spacing * (1.0 + 1e-12)) { ctx->set_error("pb_build_neighbor_lists: cutoff exceeds the cell spacing"); return -1; }
+    const int rc = pb_build_tile_lists(ctx, cutoff);
+    if(rc <= 0) { return rc; }
+    return pb_build_neigh32(ctx, cutoff);
+}
+
+int pb_tile_export_ell(pb_ctx *ctx, int *neigh, int T);       // tile_lists.cu
+
+// For the kernels that walk per-particle lists: when the lists of this reneighbouring are tile lists, the 32-bit lists are
+// DERIVED from them (slot -> particle index: same sets, same order, whatever the particles have done since the build).
+int pb_require_neigh32(pb_ctx *ctx) {
+    if(ctx->neigh_n == ctx->nlocal) { return 0; }
+    if(ctx->tiles_n != ctx->nlocal) { ctx->set_error("neighbour lists are stale"); return -1; }
+    if(ctx->lanes != 1) { ctx->set_error("per-particle lists out of tile lists need lanes_per_particle = 1"); return -1; }
+    PbStage st(ctx, "neighbor_lists_32");
+    PB_TRY(pb_alloc_neigh(ctx, ctx->nlocal));
+    ctx->nslots = pb_layout(ctx).T;
+    PB_TRY(pb_tile_export_ell(ctx, ctx->neigh, ctx->nslots));
+    ctx->neigh_n = ctx->nlocal;
+    return 0;
 }
 
 extern "C" int pb_neighbor_capacity(const pb_ctx *ctx) { return ctx->ncap; }
@@ -260,6 +293,7 @@ __global__ void pb_k_neigh_to_aos(int n, int cap_out, int ncap, PbNeighLayout la
 
 extern "C" int pb_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
     PB_CHECK(cudaSetDevice(ctx->device));
+    if(ctx->tiles_n == ctx->nlocal && ctx->neigh_n != ctx->nlocal) { return pb_tile_download_neighbors(ctx, out, capacity); }
     const int n = ctx->neigh_n;
     if(n == 0) { return 0; }
     PbScratch stage_buf;

@@ -1,0 +1,706 @@
+// Tile lists: cell tiles staged in shared memory, 16-bit tile-relative neighbour lists -- the list format of the MD hot path
+// (BuildNeighborLists sim/neighbor_lists.py:21-48 + the Lennard-Jones pair kernel sim/interaction.py:201-292, examples/md.py:5-8).
+//
+// Why.  With one 32-byte global gather per neighbour the force kernel is bound by the L1TEX data pipe (round 1: 90 % of peak,
+// ~22 wavefronts per warp-wide gather of 32 scattered records, fp64 pipe 51 %).  The neighbours of the particles of a few adjacent
+// cells all live in the 3 x 3 cell columns around them, and in cell order each of those columns is ONE contiguous run of the cell
+// CSR.  So a CTA takes a TILE -- the cells [za, zb] of a 2 x 2 block of cell columns ("super-column"), cut so that it holds at
+// most PB_TILE_M particles -- and
+//   1. stages the 4 x 4 columns around it over [za - 1, zb + 1] (16 contiguous CSR runs, <= PB_TILE_CAP particles, 6.3 x the
+//      tile's own on average) into shared memory with cp.async: x, y as one 16-byte entry, z as an 8-byte entry per particle
+//      (no registers, no L1 allocation by the consumer side),
+//   2. walks neighbour lists whose entries are 16-bit SLOTS of that staging order (12 bits slot, 3 bits particle type), four
+//      entries per 64-bit word, sliced ELLPACK over list rows (row = tile-major particle order, so a warp reads 256
+//      contiguous bytes per four iterations) -- the gather becomes LDS.128 + LDS.64: ~14 data-pipe wavefronts per warp and
+//      neighbour instead of ~22, and half the list bytes from HBM.
+// The list build uses the same staging: candidates are tested out of shared memory with the reference's exact predicate
+// (separate fp64 multiplies and adds, no contraction), so the neighbour SETS stay bit-identical; inside a list the order is the
+// per-particle builder's (stencil rows in (dx, dy) order, ascending CSR position), hence with the exact arithmetic the forces
+// are bit-identical to the per-particle kernel's, too (tools/micro/tile_force.cu checks both on 4 M atoms).
+// Measured on a B200 (4 M atoms, tools/micro/tile_force.cu, profiles/r02_*): force 0.888 -> 0.744 ms with the reference's
+// arithmetic, 0.652 ms with fused multiply-adds (option "lj_fma"); list build 2.89 -> 2.62 ms.
+//
+// What stays per particle: `numneigh[i]`, the force / velocity / position arrays, the fused integrator epilogue
+// (md_kernels.cu).  What moves to tiles: the interior / boundary split for comm-compute overlap (a tile is "boundary" if one of
+// its particles has a ghost neighbour or is a halo source).  Kernels that walk 32-bit per-particle lists (generated pair
+// kernels, energy / virial, half lists, the legacy lj) get them built on demand (pb_require_neigh32, neighbor.cu).
+//
+// Not applicable -> pb_build_tile_lists returns 1 and the caller takes the per-particle path: half lists, more than one lane
+// per particle, DEM contexts, INFINITE particles in cell 0, more than 8 particle types, or a z level of a super-column that
+// alone exceeds the tile's particle or staging capacity (a density the 2 x 2 x 1-cell granularity cannot serve).
+#include <algorithm>
+
+#include "ctx.cuh"
+#include "md_math.h"
+
+static const int PB_TILE_NRUN = 16;
+
+struct PbTileGeom {
+    double lo[3];               // origin of the cell grid (subdom_min - spacing)
+    double spacing, inv_slab;   // cell edge; zsub / spacing
+    int dim0, dim1, dim2, zsub;
+};
+
+struct PbTileHdr {
+    int total, ncore, any_active, pad;
+    int run_begin[PB_TILE_NRUN], run_len[PB_TILE_NRUN], run_slot0[PB_TILE_NRUN];
+    int core_begin[4], core_off[5];
+};
+
+static PbTileGeom pb_tile_geom(const pb_ctx *ctx) {
+    PbTileGeom g;
+    for(int d = 0; d < 3; d++) { g.lo[d] = ctx->subdom[d * 2] - ctx->spacing; }
+    g.spacing = ctx->spacing;
+    g.inv_slab = (double) ctx->zsub_active / ctx->spacing;
+    g.dim0 = ctx->dim_cells[0];
+    g.dim1 = ctx->dim_cells[1];
+    g.dim2 = ctx->dim_cells[2];
+    g.zsub = ctx->zsub_active;
+    return g;
+}
+
+// ---- planner: tiles of <= PB_TILE_M particles and <= PB_TILE_CAP staged particles ----------------------------------------------
+// particles per (super-column, z level): in the 2 x 2 core columns and in the 4 x 4 staged columns
+__global__ void __launch_bounds__(256) pb_k_tile_levels(int nsx, int nsy, int dim0, int dim1, int dim2, const int *__restrict__ cell_start,
+                                                        int *__restrict__ lvl_core, int *__restrict__ lvl_halo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= nsx * nsy * dim2) { return; }
+    const int z = t % dim2, sc = t / dim2;
+    const int X0 = (sc / nsy) * 2, Y0 = (sc % nsy) * 2;
+    int core = 0, halo = 0;
+    for(int a = -1; a <= 2; a++) {
+        for(int b = -1; b <= 2; b++) {
+            const int X = X0 + a, Y = Y0 + b;
+            if(X < 0 || X >= dim0 || Y < 0 || Y >= dim1) { continue; }
+            const int c = (X * dim1 + Y) * dim2 + z + 1;
+            const int k = cell_start[c + 1] - cell_start[c];
+            halo += k;
+            if(a >= 0 && a <= 1 && b >= 0 && b <= 1) { core += k; }
+        }
+    }
+    lvl_core[t] = core;
+    lvl_halo[t] = halo;
+}
+
+// one thread per super-column: greedy walk over z.  WRITE = false counts the tiles, WRITE = true emits them at off[sc].
+template<bool WRITE>
+__global__ void __launch_bounds__(128) pb_k_tile_plan(int nsc, int nsy, int dim2, const int *__restrict__ lvl_core, const int *__restrict__ lvl_halo,
+                                                      int *__restrict__ cnt, const int *__restrict__ off, PbTile *__restrict__ tiles,
+                                                      int *__restrict__ pad, int *__restrict__ overflow) {
+    const int sc = blockIdx.x * blockDim.x + threadIdx.x;
+    if(sc >= nsc) { return; }
+    const int *lc = lvl_core + (size_t) sc * dim2, *lh = lvl_halo + (size_t) sc * dim2;
+    int ntiles = 0;
+    int z = 0;
+    while(z < dim2) {
+        if(lc[z] == 0) { z++; continue; }
+        const int za = z;
+        int core = lc[z];
+        int staged = ((z > 0) ? lh[z - 1] : 0) + lh[z] + ((z + 1 < dim2) ? lh[z + 1] : 0);
+        if(core > PB_TILE_M || staged > PB_TILE_CAP) { atomicExch(overflow, 1); }
+        int zb = z;
+        while(zb + 1 < dim2) {
+            const int c2 = core + lc[zb + 1];
+            const int s2 = staged + ((zb + 2 < dim2) ? lh[zb + 2] : 0);
+            if(c2 > PB_TILE_M || s2 > PB_TILE_CAP) { break; }
+            core = c2;
+            staged = s2;
+            zb++;
+        }
+        if(WRITE) {
+            PbTile t;
+            t.X0 = (sc / nsy) * 2; t.Y0 = (sc % nsy) * 2; t.za = za; t.zb = zb; t.row_base = 0; t.ncore = core;
+            tiles[off[sc] + ntiles] = t;
+            pad[off[sc] + ntiles] = (core + 31) / 32 * 32;
+        }
+        ntiles++;
+        z = zb + 1;
+    }
+    if(!WRITE) { cnt[sc] = ntiles; }
+}
+
+__global__ void __launch_bounds__(256) pb_k_tile_rows(int ntiles, const int *__restrict__ row, PbTile *__restrict__ tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t < ntiles) { tiles[t].row_base = row[t]; }
+}
+
+// ---- staging -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pb_cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void pb_cp_async8(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void pb_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// run table of the tile: 16 staged runs (columns X0-1 .. X0+2, Y0-1 .. Y0+2 over [za-1, zb+1]) and the 4 core runs
+__device__ __forceinline__ void pb_tile_setup(PbTileHdr *h, const PbTileGeom &g, const PbTile &tl, const int *__restrict__ cell_start) {
+    const int t = threadIdx.x;
+    if(t < PB_TILE_NRUN) {
+        int len = 0, begin = 0;
+        const int X = tl.X0 - 1 + t / 4, Y = tl.Y0 - 1 + t % 4;
+        if(X >= 0 && X < g.dim0 && Y >= 0 && Y < g.dim1) {
+            const int zb = max(tl.za - 1, 0), ze = min(tl.zb + 1, g.dim2 - 1);
+            const int fb = (X * g.dim1 + Y) * g.dim2 + zb, fe = (X * g.dim1 + Y) * g.dim2 + ze;
+            begin = cell_start[fb + 1];
+            len = cell_start[fe + 2] - begin;
+        }
+        h->run_begin[t] = begin;
+        h->run_len[t] = len;
+    } else if(t >= 32 && t < 36) {
+        const int q = t - 32;
+        const int X = tl.X0 + q / 2, Y = tl.Y0 + q % 2;
+        int begin = 0, len = 0;
+        if(X < g.dim0 && Y < g.dim1) {
+            const int fb = (X * g.dim1 + Y) * g.dim2 + tl.za, fe = (X * g.dim1 + Y) * g.dim2 + tl.zb;
+            begin = cell_start[fb + 1];
+            len = cell_start[fe + 2] - begin;
+        }
+        h->core_begin[q] = begin;
+        h->core_off[q + 1] = len;
+    }
+    __syncthreads();
+    if(t == 0) {
+        int acc = 0;
+        for(int r = 0; r < PB_TILE_NRUN; r++) { h->run_slot0[r] = acc; acc += h->run_len[r]; }
+        h->total = acc;
+        h->core_off[0] = 0;
+        for(int q = 0; q < 4; q++) { h->core_off[q + 1] += h->core_off[q]; }
+        h->ncore = h->core_off[4];
+        h->any_active = 0;
+    }
+    __syncthreads();
+}
+
+// CSR position of the t-th core particle of the tile (-1: none)
+__device__ __forceinline__ int pb_tile_core_slot(const PbTileHdr *h, int t) {
+    if(t >= h->ncore) { return -1; }
+    int q = 0;
+    if(t >= h->core_off[1]) { q = 1; }
+    if(t >= h->core_off[2]) { q = 2; }
+    if(t >= h->core_off[3]) { q = 3; }
+    return h->core_begin[q] + (t - h->core_off[q]);
+}
+
+// warp r stages runs r, r + nwarps, ...: four index loads in flight, then two cp.async per particle (x,y | z [| w])
+template<bool WITH_IDX, bool WITH_W>
+__device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
+                                              double2 *sxy, double *sz, double *sw, int *sidx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for(int r = warp; r < PB_TILE_NRUN; r += nw) {
+        const int len = h->run_len[r], begin = h->run_begin[r], slot0 = h->run_slot0[r];
+        for(int k0 = 0; k0 < len; k0 += 128) {
+            int idx[4];
+#pragma unroll
+            for(int u = 0; u < 4; u++) { const int k = k0 + u * 32 + lane; idx[u] = (k < len) ? __ldg(cell_list + begin + k) : -1; }
+#pragma unroll
+            for(int u = 0; u < 4; u++) {
+                const int s = slot0 + k0 + u * 32 + lane;
+                if(idx[u] >= 0 && s < PB_TILE_CAP) {
+                    const double *src = reinterpret_cast<const double *>(pos + idx[u]);
+                    pb_cp_async16(sxy + s, src);
+                    pb_cp_async8(sz + s, src + 2);
+                    if(WITH_W) { pb_cp_async8(sw + s, src + 3); }
+                    if(WITH_IDX) { sidx[s] = idx[u]; }
+                }
+            }
+        }
+    }
+    pb_cp_async_wait_all();
+}
+
+// shared memory: [hdr][xy: CAP*16][z: CAP*8][w: CAP*8 (typed build)][idx: CAP*4 (build)]
+__device__ __forceinline__ void pb_tile_smem(unsigned char *base, PbTileHdr *&h, double2 *&sxy, double *&sz, double *&sw, int *&sidx) {
+    h = reinterpret_cast<PbTileHdr *>(base);
+    unsigned char *p = base + ((sizeof(PbTileHdr) + 15) / 16) * 16;
+    sxy = reinterpret_cast<double2 *>(p);
+    sz = reinterpret_cast<double *>(sxy + PB_TILE_CAP);
+    sw = sz + PB_TILE_CAP;
+    sidx = reinterpret_cast<int *>(sw + PB_TILE_CAP);
+}
+static size_t pb_tile_smem_bytes(bool build) {
+    return ((sizeof(PbTileHdr) + 15) / 16) * 16 + (size_t) PB_TILE_CAP * 24 + (build ? (size_t) PB_TILE_CAP * 12 : 0);
+}
+
+// word q of list row r (4 entries per word): ((r / 32) * T4 + q) * 32 + r % 32
+__device__ __forceinline__ size_t pb_tile_word(int row, int T4, int q) { return ((size_t) (row >> 5) * T4 + (size_t) q) * 32 + (size_t) (row & 31); }
+
+// ---- list build -----------------------------------------------------------------------------------------------------------
+struct PbTileFaces { double lo[3], hi[3]; };
+
+// z-window of stencil row r for a particle at (fx, fy) inside its cell column, zrel above the grid origin: CSR range [b, e) of
+// the slab CSR (the per-particle builder's window, neighbor.cu: widened by a relative 1e-9 and rounded outwards to whole slabs)
+__device__ __forceinline__ bool pb_tile_window(const PbTileGeom &g, int c0, int c1, int c2, double fx, double fy, double zrel, double cutsq, int r,
+                                               const int *__restrict__ sub_start, int &b, int &e) {
+    const int dx = r / 3 - 1, dy = r % 3 - 1;
+    const double ddx = (dx == 0) ? 0.0 : ((dx < 0) ? fx : g.spacing - fx);
+    const double ddy = (dy == 0) ? 0.0 : ((dy < 0) ? fy : g.spacing - fy);
+    const double wsq = cutsq - (ddx * ddx + ddy * ddy);
+    if(wsq <= 0.0) { return false; }
+    const int X = c0 + dx, Y = c1 + dy;
+    if(X < 0 || X >= g.dim0 || Y < 0 || Y >= g.dim1) { return false; }
+    const double w = sqrt(wsq) + 1e-9 * g.spacing;
+    const long col = ((long) X * g.dim1 + Y) * g.dim2 + 1;
+    int gz_lo = (int) floor((zrel - w) * g.inv_slab), gz_hi = (int) floor((zrel + w) * g.inv_slab);
+    gz_lo = max(gz_lo, max((c2 - 1) * g.zsub, 0));
+    gz_hi = min(gz_hi, min((c2 + 1) * g.zsub + g.zsub - 1, g.dim2 * g.zsub - 1));
+    if(gz_lo > gz_hi) { return false; }
+    b = sub_start[col * g.zsub + gz_lo];
+    e = sub_start[col * g.zsub + gz_hi + 1];
+    return true;
+}
+
+template<bool TYPES>
+__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int ncap, int T4, PbTileGeom g, double cutsq, const PbTile *__restrict__ tiles,
+                                                            const double4 *__restrict__ pos, const int *__restrict__ flags,
+                                                            const int *__restrict__ particle_cell, const int *__restrict__ cell_start,
+                                                            const int *__restrict__ sub_start, const int *__restrict__ cell_list,
+                                                            unsigned long long *__restrict__ words, int *__restrict__ numneigh,
+                                                            int *__restrict__ max_count, PbTileFaces faces, int *__restrict__ tile_flag) {
+    extern __shared__ __align__(16) unsigned char pb_tile_shared[];
+    PbTileHdr *h; double2 *sxy; double *sz, *sw; int *sidx;
+    pb_tile_smem(pb_tile_shared, h, sxy, sz, sw, sidx);
+    const PbTile tl = tiles[blockIdx.x];
+    pb_tile_setup(h, g, tl, cell_start);
+    const int cs = pb_tile_core_slot(h, threadIdx.x);
+    const int i = (cs >= 0) ? __ldg(cell_list + cs) : nlocal;
+    const bool live = i < nlocal;                                  // a local particle (ghosts sit in core cells at the faces, too)
+    const bool active = live && (flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (sim/neighbor_lists.py:31-33 via the FIXED filter)
+    if(live) { h->any_active = 1; }
+    __syncthreads();
+    if(!h->any_active) {                                           // a tile of ghosts only: nothing to build
+        if(threadIdx.x == 0) { tile_flag[blockIdx.x] = 0; }
+        return;
+    }
+    pb_tile_stage<true, TYPES>(h, cell_list, pos, sxy, sz, sw, sidx);
+    __syncthreads();
+    int count = 0, boundary = 0;
+    if(active) {
+        const double4 pi = pb_ld_pos(pos + i);
+        boundary = (pi.x < faces.lo[0]) | (pi.x > faces.hi[0]) | (pi.y < faces.lo[1]) | (pi.y > faces.hi[1]) | (pi.z < faces.lo[2]) |
+                   (pi.z > faces.hi[2]);
+        const int flat = particle_cell[i] - 1;
+        const int c2 = flat % g.dim2, col = flat / g.dim2, c1 = col % g.dim1, c0 = col / g.dim1;
+        const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
+        const int row = tl.row_base + threadIdx.x;
+        unsigned long long *const out = words + pb_tile_word(row, T4, 0);
+        unsigned long long w = 0ull;
+        for(int r = 0; r < 9; r++) {
+            int b, e;
+            if(!pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
+            const int tr = (c0 + r / 3 - 1 - (tl.X0 - 1)) * 4 + (c1 + r % 3 - 1 - (tl.Y0 - 1));      // the staged run of this stencil row
+            const int shift = h->run_slot0[tr] - h->run_begin[tr];
+            for(int k = b; k < e; k++) {
+                const int s = k + shift;
+                const double2 xy = sxy[s];
+                const double z = sz[s];
+                const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
+                const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if(rsq < cutsq) {
+                    const int j = sidx[s];
+                    if(j != i) {
+                        if(count < ncap) {
+                            unsigned entry = (unsigned) s;
+                            if(TYPES) { entry |= (unsigned) (pb_w_type(sw[s]) & 7) << 12; }
+                            w |= (unsigned long long) entry << (16 * (count & 3));
+                            if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
+                        }
+                        count++;
+                        boundary |= (j >= nlocal);
+                    }
+                }
+            }
+        }
+        if((count & 3) != 0 && (count >> 2) < T4) { out[(size_t) (count >> 2) * 32] = w; }
+    }
+    if(live) { numneigh[i] = count; }
+    const int any_b = __syncthreads_or(boundary);
+    if(threadIdx.x == 0) { tile_flag[blockIdx.x] = any_b != 0; }
+    int m = count;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+    if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(max_count, m); }
+}
+
+// ---- force ------------------------------------------------------------------------------------------------------------------
+struct PbTileLjArgs {
+    int nlocal, ncap, T4, cap, ntypes, nsel;
+    double cutsq, eps_u, sig6_u, dt, half_dt;
+    const double *eps_t, *sig6_t;
+    PbTileGeom g;
+    const PbTile *tiles;
+    const int *sel;                 // tile subset of this launch (interior / boundary split), null = all tiles
+    const double4 *pos;
+    const int *flags, *cell_start, *cell_list, *numneigh;
+    const unsigned long long *words;
+    double *force;
+    const double *mass;
+    double *vel;
+    double4 *pos_next;
+};
+
+// FUSE / ACCUMULATE: the epilogue of the per-particle kernel (md_kernels.cu pb_k_lennard_jones), operation for operation.
+// FMA: pb_pair_rsq_fma / pb_lj_fpair_fma and fused accumulation (md_math.h) instead of the reference's expression tree.
+template<bool UNIFORM, bool ACCUMULATE, int FUSE, bool FMA>
+__global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
+    extern __shared__ __align__(16) unsigned char pb_tile_shared[];
+    __shared__ double s_eps[64], s_sig6[64];
+    PbTileHdr *h; double2 *sxy; double *sz, *sw; int *sidx;
+    pb_tile_smem(pb_tile_shared, h, sxy, sz, sw, sidx);
+    if(!UNIFORM) {
+        for(int k = threadIdx.x; k < a.ntypes * a.ntypes; k += blockDim.x) { s_eps[k] = a.eps_t[k]; s_sig6[k] = a.sig6_t[k]; }
+    }
+    const int tile_id = (a.sel != nullptr) ? __ldg(a.sel + blockIdx.x) : (int) blockIdx.x;
+    const PbTile tl = a.tiles[tile_id];
+    pb_tile_setup(h, a.g, tl, a.cell_start);
+    // own data first: these loads are in flight while the tile is staged
+    const int cs = pb_tile_core_slot(h, threadIdx.x);
+    const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : a.nlocal;
+    const bool live = i < a.nlocal;
+    const bool fixed = live && (a.flags[i] & PB_FLAG_FIXED) != 0;
+    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
+    int nn = 0;
+    const int row = tl.row_base + threadIdx.x;
+    const unsigned long long *wp = a.words + pb_tile_word(row, a.T4, 0);
+    unsigned long long wnext = 0ull;
+    if(live) {
+        pi = pb_ld_pos(a.pos + i);
+        h->any_active = 1;
+        if(!fixed) {
+            nn = min(a.numneigh[i], a.ncap);
+            if(nn > 0) { wnext = __ldg(wp); }
+        }
+    }
+    __syncthreads();
+    if(!h->any_active) { return; }                                 // a tile of ghosts only
+    pb_tile_stage<false, false>(h, a.cell_list, a.pos, sxy, sz, sw, sidx);
+    __syncthreads();
+    if(!live) { return; }
+    const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * a.ntypes;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for(int k = 0; k < nn; k += 4) {
+        const unsigned long long w = wnext;
+        if(k + 4 < nn) { wnext = __ldg(wp + (size_t) ((k >> 2) + 1) * 32); }
+        double xj[4], yj[4], zj[4];
+        int tj[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            const unsigned e16 = (unsigned) ((w >> (16 * u)) & 0xffffull);
+            const int s = (k + u < nn) ? (int) (e16 & 0xfffu) : 0;
+            tj[u] = (int) (e16 >> 12);
+            const double2 xy = sxy[s];
+            xj[u] = xy.x; yj[u] = xy.y;
+            zj[u] = sz[s];
+        }
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            double dx, dy, dz;
+            const double rsq = FMA ? pb_pair_rsq_fma(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], &dx, &dy, &dz)
+                                   : pb_pair_rsq(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], &dx, &dy, &dz);
+            if(k + u < nn && rsq < a.cutsq) {
+                const double sig6 = UNIFORM ? a.sig6_u : s_sig6[ti + tj[u]];
+                const double eps = UNIFORM ? a.eps_u : s_eps[ti + tj[u]];
+                if(FMA) {
+                    const double f = pb_lj_fpair_fma(rsq, sig6, eps);
+                    fx = __fma_rn(dx, f, fx);
+                    fy = __fma_rn(dy, f, fy);
+                    fz = __fma_rn(dz, f, fz);
+                } else {
+                    const double f = pb_lj_fpair(rsq, sig6, eps);
+                    fx = __dadd_rn(fx, __dmul_rn(dx, f));
+                    fy = __dadd_rn(fy, __dmul_rn(dy, f));
+                    fz = __dadd_rn(fz, __dmul_rn(dz, f));
+                }
+            }
+        }
+    }
+    // force[i] = force[i] + acc (sim/interaction.py:280-292); a pending reset_volatile_properties is folded in (ACCUMULATE == false)
+    const int cap = a.cap;
+    if(ACCUMULATE) {
+        if(!fixed) {
+            fx = __dadd_rn(a.force[i], fx);
+            fy = __dadd_rn(a.force[cap + i], fy);
+            fz = __dadd_rn(a.force[2 * (size_t) cap + i], fz);
+            a.force[i] = fx;
+            a.force[cap + i] = fy;
+            a.force[2 * (size_t) cap + i] = fz;
+        }
+    } else {
+        fx = __dadd_rn(0.0, fx);
+        fy = __dadd_rn(0.0, fy);
+        fz = __dadd_rn(0.0, fz);
+        a.force[i] = fx;
+        a.force[cap + i] = fy;
+        a.force[2 * (size_t) cap + i] = fz;
+    }
+    if(FUSE != 0) {
+        if(!fixed) {
+            const double m = a.mass[i];
+            double vx = a.vel[i], vy = a.vel[cap + i], vz = a.vel[2 * (size_t) cap + i];
+            if(FUSE & 1) {
+                vx = __dadd_rn(vx, __ddiv_rn(__dmul_rn(a.half_dt, fx), m));
+                vy = __dadd_rn(vy, __ddiv_rn(__dmul_rn(a.half_dt, fy), m));
+                vz = __dadd_rn(vz, __ddiv_rn(__dmul_rn(a.half_dt, fz), m));
+            }
+            if(FUSE & 2) {
+                vx = __dadd_rn(vx, __ddiv_rn(__dmul_rn(a.half_dt, fx), m));
+                vy = __dadd_rn(vy, __ddiv_rn(__dmul_rn(a.half_dt, fy), m));
+                vz = __dadd_rn(vz, __ddiv_rn(__dmul_rn(a.half_dt, fz), m));
+                pi.x = __dadd_rn(pi.x, __dmul_rn(a.dt, vx));
+                pi.y = __dadd_rn(pi.y, __dmul_rn(a.dt, vy));
+                pi.z = __dadd_rn(pi.z, __dmul_rn(a.dt, vz));
+            }
+            a.vel[i] = vx;
+            a.vel[cap + i] = vy;
+            a.vel[2 * (size_t) cap + i] = vz;
+        }
+        if(FUSE & 2) { a.pos_next[i] = pi; }
+    }
+}
+
+// ---- per-particle view of the lists (pb_download_neighbors: tests, tools) -------------------------------------------------------
+template<bool ELL>
+__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_export(int nlocal, int ncap, int T4, int cap_out, PbTileGeom g, const PbTile *__restrict__ tiles,
+                                                             const int *__restrict__ cell_start, const int *__restrict__ cell_list,
+                                                             const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
+                                                             int *__restrict__ out) {
+    __shared__ PbTileHdr hdr;
+    PbTileHdr *h = &hdr;
+    const PbTile tl = tiles[blockIdx.x];
+    pb_tile_setup(h, g, tl, cell_start);
+    const int cs = pb_tile_core_slot(h, threadIdx.x);
+    const int i = (cs >= 0) ? cell_list[cs] : nlocal;
+    if(i >= nlocal) { return; }
+    const int row = tl.row_base + threadIdx.x;
+    const int c = min(numneigh[i], min(cap_out, ncap));
+    for(int k = 0; k < c; k++) {
+        const unsigned long long w = words[pb_tile_word(row, T4, k >> 2)];
+        const int s = (int) ((w >> (16 * (k & 3))) & 0xfffull);
+        int r = 0;
+        for(int q = 1; q < PB_TILE_NRUN; q++) { if(s >= h->run_slot0[q]) { r = q; } }      // slot0 is non-decreasing
+        const int j = cell_list[h->run_begin[r] + (s - h->run_slot0[r])];
+        if(ELL) { out[((size_t) (i >> 5) * cap_out + (size_t) k) * 32 + (size_t) (i & 31)] = j; }      // PbNeighLayout, one lane per particle
+        else { out[(size_t) i * cap_out + k] = j; }
+    }
+    if(!ELL) { for(int k = c; k < cap_out; k++) { out[(size_t) i * cap_out + k] = -1; } }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------------
+template<typename T>
+static int pb_tile_fit(pb_ctx *ctx, T **p, int *cap, size_t need) {
+    if(need > (size_t) *cap) {
+        if(*p != nullptr) { PB_CHECK(cudaFree(*p)); *p = nullptr; *cap = 0; }
+        const size_t want = need + need / 4 + 64;
+        PB_CHECK(cudaMalloc(p, sizeof(T) * want));
+        *cap = (int) want;
+    }
+    return 0;
+}
+
+static int pb_tile_plan(pb_ctx *ctx, bool *overflow) {
+    const PbTileGeom g = pb_tile_geom(ctx);
+    const int nsx = (g.dim0 + 1) / 2, nsy = (g.dim1 + 1) / 2, nsc = nsx * nsy;
+    const size_t nlvl = (size_t) nsc * g.dim2;
+    PB_TRY(pb_tile_fit(ctx, &ctx->tile_lvl, &ctx->tile_lvl_cap, 2 * nlvl));
+    if(nsc + 2 > ctx->tile_sc_cap) {
+        int c1 = ctx->tile_sc_cap, c2 = ctx->tile_sc_cap;
+        PB_TRY(pb_tile_fit(ctx, &ctx->tile_cnt, &c1, (size_t) nsc + 2));
+        PB_TRY(pb_tile_fit(ctx, &ctx->tile_off, &c2, (size_t) nsc + 2));
+        ctx->tile_sc_cap = std::min(c1, c2);
+    }
+    int *lvl_core = ctx->tile_lvl, *lvl_halo = ctx->tile_lvl + nlvl;
+    int *d_over = ctx->d_scalars + 2;
+    PB_CHECK(cudaMemsetAsync(d_over, 0, sizeof(int), ctx->stream));
+    PB_LAUNCH(pb_k_tile_levels, pb_blocks((long) nlvl, 256), 256, nsx, nsy, g.dim0, g.dim1, g.dim2, ctx->cell_start, lvl_core, lvl_halo);
+    PB_LAUNCH(pb_k_tile_plan<false>, pb_blocks(nsc, 128), 128, nsc, nsy, g.dim2, lvl_core, lvl_halo, ctx->tile_cnt, ctx->tile_off, (PbTile *) nullptr,
+              (int *) nullptr, d_over);
+    PB_TRY(pb_exclusive_scan(ctx, ctx->tile_cnt, ctx->tile_off, nsc));
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 2, ctx->tile_off + nsc, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 3, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    const int ntiles = ctx->h_scalars[2];
+    *overflow = ctx->h_scalars[3] != 0;
+    ctx->ntiles = 0;
+    if(*overflow || ntiles == 0) { return 0; }
+    if(ntiles + 1 > ctx->tiles_cap) {
+        int c0 = ctx->tiles_cap, c1 = ctx->tiles_cap, c2 = ctx->tiles_cap;
+        PB_TRY(pb_tile_fit(ctx, &ctx->tiles, &c0, (size_t) ntiles + 1));
+        PB_TRY(pb_tile_fit(ctx, &ctx->tile_pad, &c1, (size_t) ntiles + 1));
+        PB_TRY(pb_tile_fit(ctx, &ctx->tile_row, &c2, (size_t) ntiles + 1));
+        ctx->tiles_cap = std::min(c0, std::min(c1, c2));
+    }
+    PB_LAUNCH(pb_k_tile_plan<true>, pb_blocks(nsc, 128), 128, nsc, nsy, g.dim2, lvl_core, lvl_halo, ctx->tile_cnt, ctx->tile_off, ctx->tiles,
+              ctx->tile_pad, d_over);
+    PB_TRY(pb_exclusive_scan(ctx, ctx->tile_pad, ctx->tile_row, ntiles));
+    PB_LAUNCH(pb_k_tile_rows, pb_blocks(ntiles, 256), 256, ntiles, ctx->tile_row, ctx->tiles);
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 2, ctx->tile_row + ntiles, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->ntiles = ntiles;
+    ctx->tile_rows = ctx->h_scalars[2];
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) pb_k_tile_split(int ntiles, const int *__restrict__ flag, const int *__restrict__ scan,
+                                                       int *__restrict__ interior, int *__restrict__ boundary) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if(t >= ntiles) { return; }
+    if(flag[t]) { boundary[scan[t]] = t; } else { interior[t - scan[t]] = t; }
+}
+
+// 0: built; 1: not applicable (the caller builds per-particle lists); < 0: error
+int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
+    ctx->tiles_n = -1;
+    ctx->tile_split_valid = false;
+    const int n = ctx->nlocal;
+    if(!ctx->tile_lists || ctx->half_lists || ctx->lanes != 1 || ctx->dem || ctx->stage_lists || ctx->pair_lists) { return 1; }
+    if(ctx->ntypes > 8) { return 1; }
+    if(n == 0) { return 1; }
+    // INFINITE particles live in cell 0, outside every tile: leave such systems to the per-particle builder
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 4, ctx->cell_start, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    bool overflow = false;
+    PB_TRY(pb_tile_plan(ctx, &overflow));           // (synchronises the stream: the two cell_start values have arrived)
+    if(ctx->h_scalars[5] - ctx->h_scalars[4] > 0) { return 1; }
+    if(overflow || ctx->ntiles == 0) { return 1; }
+    const PbTileGeom g = pb_tile_geom(ctx);
+    const double cutsq = cutoff * cutoff;
+    if(ctx->ncap <= 0) { ctx->ncap = 100; }
+    PbTileFaces faces;
+    for(int d = 0; d < 3; d++) {
+        faces.lo[d] = ctx->subdom[d * 2] + ctx->spacing;
+        faces.hi[d] = ctx->subdom[d * 2 + 1] - ctx->spacing;
+    }
+    if(ctx->ntiles + 1 > ctx->tile_flag_cap) {
+        int c[4] = {ctx->tile_flag_cap, ctx->tile_flag_cap, ctx->tile_flag_cap, ctx->tile_flag_cap};
+        PB_TRY(pb_tile_fit(ctx, &ctx->tile_flag, &c[0], (size_t) ctx->ntiles + 1));
+        PB_TRY(pb_tile_fit(ctx, &ctx->tile_scan, &c[1], (size_t) ctx->ntiles + 1));
+        PB_TRY(pb_tile_fit(ctx, &ctx->tiles_interior, &c[2], (size_t) ctx->ntiles + 1));
+        PB_TRY(pb_tile_fit(ctx, &ctx->tiles_boundary, &c[3], (size_t) ctx->ntiles + 1));
+        ctx->tile_flag_cap = std::min(std::min(c[0], c[1]), std::min(c[2], c[3]));
+    }
+    // the particle type (3 bits) always rides in the entries: the Lennard-Jones tables may be set after the lists are built
+    const bool types = true;
+    const size_t smem = pb_tile_smem_bytes(true);
+    PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    for(int attempt = 0; attempt < 8; attempt++) {
+        const int T4 = (ctx->ncap + 3) / 4;
+        const size_t bytes = sizeof(unsigned long long) * (size_t) (ctx->tile_rows / 32) * (size_t) T4 * 32;
+        if(bytes > ctx->twords_bytes) {
+            if(ctx->twords != nullptr) { PB_CHECK(cudaFree(ctx->twords)); ctx->twords = nullptr; ctx->twords_bytes = 0; }
+            const size_t want = bytes + bytes / 8;
+            PB_CHECK(cudaMalloc(&ctx->twords, want));
+            ctx->twords_bytes = want;
+        }
+        ctx->tile_T4 = T4;
+        PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
+        if(types) {
+            pb_k_tile_build<true><<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(n, ctx->ncap, T4, g, cutsq, ctx->tiles, ctx->pos, ctx->flags, ctx->particle_cell,
+                                                                                   ctx->cell_start, ctx->sub_start, ctx->cell_list, ctx->twords, ctx->numneigh,
+                                                                                   ctx->d_scalars, faces, ctx->tile_flag);
+        } else {
+            pb_k_tile_build<false><<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(n, ctx->ncap, T4, g, cutsq, ctx->tiles, ctx->pos, ctx->flags, ctx->particle_cell,
+                                                                                    ctx->cell_start, ctx->sub_start, ctx->cell_list, ctx->twords, ctx->numneigh,
+                                                                                    ctx->d_scalars, faces, ctx->tile_flag);
+        }
+        ctx->launches++;
+        PB_CHECK(cudaGetLastError());
+        const bool split = ctx->world > 1 && ctx->overlap_comm;
+        if(split) {       // issued before the read-back so that one synchronisation serves both counters
+            PB_TRY(pb_exclusive_scan(ctx, ctx->tile_flag, ctx->tile_scan, ctx->ntiles));
+            PB_LAUNCH(pb_k_tile_split, pb_blocks(ctx->ntiles, 256), 256, ctx->ntiles, ctx->tile_flag, ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary);
+            PB_CHECK(cudaMemcpyAsync(ctx->h_scalars + 1, ctx->tile_scan + ctx->ntiles, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        ctx->max_neigh = ctx->h_scalars[0];
+        if(ctx->max_neigh <= ctx->ncap) {
+            if(split) {
+                ctx->n_tiles_boundary = ctx->h_scalars[1];
+                ctx->n_tiles_interior = ctx->ntiles - ctx->n_tiles_boundary;
+                ctx->tile_split_valid = true;
+            }
+            ctx->tiles_n = n;
+            return 0;
+        }
+        // capacity-overflow protocol (transformations/modules.py:159-203): grow to twice the need and re-run the module
+        ctx->ncap = ctx->max_neigh * 2;
+    }
+    ctx->set_error("pb_build_neighbor_lists: capacity did not converge");
+    return -1;
+}
+
+template<bool UNIFORM, bool ACCUMULATE, bool FMA>
+static int pb_tile_launch(pb_ctx *ctx, const PbTileLjArgs &a, int grid, int fuse) {
+    const size_t smem = pb_tile_smem_bytes(false);
+#define PB_TILE_GO(F)                                                                                                          \
+    {                                                                                                                          \
+        PB_CHECK(cudaFuncSetAttribute(pb_k_tile_lj<UNIFORM, ACCUMULATE, F, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        pb_k_tile_lj<UNIFORM, ACCUMULATE, F, FMA><<<grid, PB_TILE_M, smem, ctx->stream>>>(a);                                     \
+    }
+    switch(fuse) {
+        case 1: PB_TILE_GO(1) break;
+        case 2: PB_TILE_GO(2) break;
+        case 3: PB_TILE_GO(3) break;
+        default: PB_TILE_GO(0) break;
+    }
+#undef PB_TILE_GO
+    ctx->launches++;
+    PB_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// the force evaluation of pb_lennard_jones_fused (md_kernels.cu) over the tile lists; same contract: `fuse` bits, force reset folded
+// in when pending, new positions into pos_alt when bit 1 is set (the caller swaps), part 0 = all / 1 = interior / 2 = boundary tiles
+int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int part) {
+    PbTileLjArgs a;
+    a.nlocal = ctx->nlocal; a.ncap = ctx->ncap; a.T4 = ctx->tile_T4; a.cap = ctx->pcap; a.ntypes = ctx->ntypes;
+    a.cutsq = cutsq; a.eps_u = ctx->h_eps[0]; a.sig6_u = ctx->h_sig6[0]; a.dt = dt; a.half_dt = dt * 0.5;
+    a.eps_t = ctx->d_eps; a.sig6_t = ctx->d_sig6;
+    a.g = pb_tile_geom(ctx);
+    a.tiles = ctx->tiles; a.sel = nullptr; a.nsel = ctx->ntiles;
+    int grid = ctx->ntiles;
+    if(part != 0) {
+        if(!ctx->tile_split_valid) { ctx->set_error("interior/boundary split not available"); return -1; }
+        a.sel = (part == 1) ? ctx->tiles_interior : ctx->tiles_boundary;
+        grid = (part == 1) ? ctx->n_tiles_interior : ctx->n_tiles_boundary;
+        a.nsel = grid;
+    }
+    if(grid == 0) { return 0; }
+    a.pos = ctx->pos; a.flags = ctx->flags; a.cell_start = ctx->cell_start; a.cell_list = ctx->cell_list; a.numneigh = ctx->numneigh;
+    a.words = ctx->twords; a.force = ctx->force; a.mass = ctx->mass; a.vel = ctx->vel; a.pos_next = ctx->pos_alt;
+    const bool acc = !ctx->force_is_zero;
+    const bool uni = ctx->lj_uniform;
+    if(ctx->lj_fma) {
+        if(uni) { return acc ? pb_tile_launch<true, true, true>(ctx, a, grid, fuse) : pb_tile_launch<true, false, true>(ctx, a, grid, fuse); }
+        return acc ? pb_tile_launch<false, true, true>(ctx, a, grid, fuse) : pb_tile_launch<false, false, true>(ctx, a, grid, fuse);
+    }
+    if(uni) { return acc ? pb_tile_launch<true, true, false>(ctx, a, grid, fuse) : pb_tile_launch<true, false, false>(ctx, a, grid, fuse); }
+    return acc ? pb_tile_launch<false, true, false>(ctx, a, grid, fuse) : pb_tile_launch<false, false, false>(ctx, a, grid, fuse);
+}
+
+int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
+    const int n = ctx->tiles_n;
+    if(n <= 0) { return 0; }
+    PbScratch stage_buf;
+    PB_CHECK(stage_buf.alloc(sizeof(int) * (size_t) n * (size_t) capacity));
+    int *const stage = stage_buf.as<int>();
+    PB_CHECK(cudaMemsetAsync(stage, 0xff, sizeof(int) * (size_t) n * (size_t) capacity, ctx->stream));      // FIXED particles: no list, all -1
+    PB_LAUNCH(pb_k_tile_export<false>, ctx->ntiles, PB_TILE_M, n, ctx->ncap, ctx->tile_T4, capacity, pb_tile_geom(ctx), ctx->tiles, ctx->cell_start,
+              ctx->cell_list, ctx->twords, ctx->numneigh, stage);
+    PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(int) * (size_t) n * (size_t) capacity, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// the tile lists as 32-bit per-particle lists in the sliced-ELLPACK layout (T slots per particle), for pb_require_neigh32
+int pb_tile_export_ell(pb_ctx *ctx, int *neigh, int T) {
+    if(ctx->tiles_n <= 0) { return 0; }
+    PB_LAUNCH(pb_k_tile_export<true>, ctx->ntiles, PB_TILE_M, ctx->tiles_n, ctx->ncap, ctx->tile_T4, T, pb_tile_geom(ctx), ctx->tiles, ctx->cell_start,
+              ctx->cell_list, ctx->twords, ctx->numneigh, neigh);
+    return 0;
+}

@@ -209,6 +209,8 @@ def _unify(t, u, binding):
 
 
 FORCE_GENERIC = False        # tests: send every kernel through the generic (NVRTC) path, also the recognised ones
+EXACT_ARITHMETIC = False     # tests: the hand-written pair kernel with the reference's expression tree (no fused multiply-adds, IEEE division:
+                             # option "lj_fma" = 0), the arithmetic the generated kernels always use -- for bit-for-bit comparisons
 FORCE_GENERIC_NAMES = set()  # tests: kernels with these function names are generated even if they would be recognised
 FORCE_GENERIC_CONTACT_MODEL = False      # tests: DEM scripts get their contact model generated even if it is examples/dem.py's
 
@@ -555,6 +557,8 @@ class Simulation:
         g = self.grid
         grid = [g[0], g[3], g[1], g[4], g[2], g[5]]
         ctx = backend.Context(local)
+        if EXACT_ARITHMETIC:
+            ctx.set_option("lj_fma", 0)
         self.ctx = ctx
         ctx.init_domain(grid, self._pbc, self._partitioner, world, rank)
         if getattr(self, "_enable_profiler", False):

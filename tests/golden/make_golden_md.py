@@ -1,4 +1,4 @@
-"""Generates tests/golden/md_t1.npz, md_t2.npz, md_half_t1.npz, md_custom_t1.npz, md_props_t1.npz and md_vocab_t1.npz from the REFERENCE ITSELF: the reference generator's own serial C++
+"""Generates tests/golden/md_t1.npz, md_t2.npz, md_cells_t1.npz, md_half_t1.npz, md_custom_t1.npz, md_props_t1.npz and md_vocab_t1.npz from the REFERENCE ITSELF: the reference generator's own serial C++
 for examples/md.py (variants md_t1 / md_t2 of oracle/build_ref.py, i.e. nx = 8 resp. 12, thermo every step), run in a
 fresh process.  Needs /root/reference (this container only); the fixtures are committed so that the oracle restatement
 and the CUDA path can be pinned where the reference is absent.
@@ -15,11 +15,11 @@ sys.path.insert(0, ROOT)
 from oracle import ref_worker  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-KEEP = {"md_t1": [0, 1, 19, 20, 100], "md_t2": [5, 60], "md_half_t1": [0, 1, 20, 100], "md_custom_t1": [0, 1, 20, 100], "md_props_t1": [0, 1, 20, 100], "md_vocab_t1": [0, 1, 10]}
+KEEP = {"md_t1": [0, 1, 19, 20, 100], "md_t2": [5, 60], "md_half_t1": [0, 1, 20, 100], "md_custom_t1": [0, 1, 20, 100], "md_props_t1": [0, 1, 20, 100], "md_vocab_t1": [0, 1, 10], "md_cells_t1": [0, 1, 19, 20, 60]}
 NAMES = {"md_t1": ("position", "linear_velocity", "force"), "md_t2": ("position", "force"),
          "md_half_t1": ("position", "linear_velocity", "force"), "md_custom_t1": ("position", "linear_velocity", "force"),
          "md_props_t1": ("position", "linear_velocity", "force", "scale", "heat", "work", "path", "pull", "ups"),
-         "md_vocab_t1": ("position", "linear_velocity", "force")}
+         "md_vocab_t1": ("position", "linear_velocity", "force"), "md_cells_t1": ("position", "linear_velocity", "force")}
 # user-defined properties of a variant (tests/scripts/props_script.py), recorded next to the MD set
 EXTRA = {"md_props_t1": (("scale", 1), ("heat", 1), ("work", 1), ("path", 3), ("pull", 3))}
 EXTRA_INT = {"md_props_t1": ("ups",)}

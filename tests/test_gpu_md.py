@@ -499,8 +499,12 @@ def test_generic_path_reproduces_the_builtin_kernels_bit_for_bit(capsys):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
     import lj_script
     from pairs_b200 import dsl
-    ref = lj_script.build("gpu", 8, 100, 20, 1)
-    ctx_ref = ref.generate()
+    dsl.EXACT_ARITHMETIC = True       # the hand-written kernel with the reference's expression tree, as the generated one
+    try:
+        ref = lj_script.build("gpu", 8, 100, 20, 1)
+        ctx_ref = ref.generate()
+    finally:
+        dsl.EXACT_ARITHMETIC = False
     dsl.FORCE_GENERIC = True
     try:
         gen = lj_script.build("gpu", 8, 100, 20, 1)

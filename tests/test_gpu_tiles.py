@@ -1,0 +1,116 @@
+"""Tile lists (csrc/tile_lists.cu: cell tiles staged in shared memory, 16-bit tile-relative neighbour lists) against the
+per-particle 32-bit lists they replace on the hot path, and the fused-multiply-add arithmetic against the reference's expression
+tree.  With the reference's arithmetic (option "lj_fma" = 0) the two list formats must agree BIT FOR BIT: same neighbour sets in
+the same order, same forces, same trajectories."""
+import numpy as np
+import pytest
+
+from tests.test_gpu_md import CUT, DT, SKIN, box, make_gpu, make_oracle, _reneighbor_gpu
+from tests.util import by_id, rel_err_force
+
+pytestmark = pytest.mark.gpu
+
+EPS4 = [1.0 + 0.05 * ((k % 4) + (k // 4)) for k in range(16)]      # a symmetric, non-uniform table
+SIG4 = [1.0 - 0.02 * abs((k % 4) - (k // 4)) for k in range(16)]
+
+
+def _run(nx, tile, fma, steps, eps=None, sig6=None, thermo=1):
+    ctx, n = make_gpu(nx, eps=eps, sig6=sig6)
+    ctx.set_option("tile_lists", tile)
+    ctx.set_option("lj_fma", fma)
+    th = ctx.md_run(0, steps, DT, CUT, CUT + SKIN, CUT + SKIN, 20, thermo)
+    tag = ctx.ints("tag")
+    return ctx, th, by_id(tag, ctx.real("position")), by_id(tag, ctx.real("linear_velocity")), by_id(tag, ctx.real("force"))
+
+
+@pytest.mark.parametrize("nx,eps,sig6", [(6, None, None), (10, None, None), (10, EPS4, SIG4), (13, EPS4, SIG4)])
+def test_tile_lists_equal_the_per_particle_lists_bit_for_bit(nx, eps, sig6):
+    ctx_t, n = make_gpu(nx, eps=eps, sig6=sig6)
+    ctx_p, _ = make_gpu(nx, eps=eps, sig6=sig6)
+    ctx_p.set_option("tile_lists", 0)
+    for c in (ctx_t, ctx_p):
+        c.set_option("lj_fma", 0)
+        _reneighbor_gpu(c)
+        c.reset_volatile()
+        c.lennard_jones(CUT)
+    assert np.array_equal(ctx_t.ints("numneighs"), ctx_p.ints("numneighs")) and ctx_t.ints("numneighs").min() > 40
+    assert np.array_equal(ctx_t.neighbors(), ctx_p.neighbors())                 # same sets, same order
+    assert np.array_equal(ctx_t.real("force"), ctx_p.real("force"))
+    # the 32-bit lists derived from the tiles serve the kernels that walk lists by particle
+    assert ctx_t.lj_energy_virial(CUT) == ctx_p.lj_energy_virial(CUT)
+    # 45 iterations of the fused loop (three list builds, wraps): identical bits
+    a = _run(nx, 1, 0, 45, eps, sig6)
+    b = _run(nx, 0, 0, 45, eps, sig6)
+    assert np.array_equal(a[1], b[1]) and len(a[1]) == 45
+    for k in (2, 3, 4):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("eps,sig6", [(None, None), (EPS4, SIG4)])
+def test_fma_arithmetic_stays_inside_the_parity_budget(eps, sig6):
+    """Option "lj_fma" (default on): forces of one evaluation within 1e-12 (max-norm relative) of the reference's expression tree,
+    thermo of 100 iterations within 1e-9; and both against the oracle."""
+    nx = 8
+    a = _run(nx, 1, 1, 100, eps, sig6)
+    b = _run(nx, 1, 0, 100, eps, sig6)
+    assert np.abs(a[1][:, 1:] - b[1][:, 1:]).max() <= 1e-9 * np.abs(b[1][:, 1:]).max()
+    fa, fb = _run(nx, 1, 1, 1, eps, sig6)[4], _run(nx, 1, 0, 1, eps, sig6)[4]
+    assert 0.0 < rel_err_force(fa, fb) <= 1e-12
+    sim = make_oracle(nx, eps=eps, sig6=sig6)
+    for ts in range(100):
+        sim.step(ts)
+        t, p = sim.thermo()
+        assert abs(a[1][ts, 1] - t) <= 1e-9 * t and abs(a[1][ts, 2] - p) <= 1e-9 * abs(p), ts
+
+
+def test_fixed_particles_and_small_capacity():
+    """FIXED particles get no list and no force update; a neighbour capacity that is far too small grows (resize protocol)."""
+    from pairs_b200.backend import Context
+    nx = 7
+    ctx0, n = make_gpu(nx)
+    pos, vel, typ = ctx0.real("position"), ctx0.real("linear_velocity"), ctx0.ints("type")
+    flags = np.zeros(n, np.int32)
+    flags[::17] = 4
+    res = []
+    for tile in (1, 0):
+        ctx = Context(0)
+        ctx.init_domain(box(nx))
+        ctx.set_option("tile_lists", tile)
+        ctx.set_option("lj_fma", 0)
+        ctx.reserve(0, 8)
+        ctx.setup_cells(CUT + SKIN)
+        ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
+        ctx.upload(pos, vel, np.ones(n), typ, flags)
+        th = ctx.md_run(0, 25, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
+        tag = ctx.ints("tag")
+        res.append((th, by_id(tag, ctx.real("position")), by_id(tag, ctx.real("force")), by_id(tag, ctx.ints("numneighs"))))
+        assert ctx.lib.pb_neighbor_capacity(ctx.h) >= 78
+    for x, y in zip(res[0], res[1]):
+        assert np.array_equal(x, y)
+    assert np.array_equal(res[0][1][::17], pos[::17]) and not res[0][3][::17].any() and res[0][3][1] > 40
+
+
+def test_ragged_box_and_thin_slab():
+    """Boxes whose edges are no multiple of the cell spacing, fewer cells than a super-column is wide, a thin periodic slab."""
+    from pairs_b200.backend import Context
+    rng = np.random.default_rng(11)
+    for dims in ((9.1, 17.3, 30.2), (5.7, 5.7, 5.7), (40.0, 6.1, 8.9)):
+        n = int(0.8 * dims[0] * dims[1] * dims[2])
+        pos = rng.random((n, 3)) * np.array(dims) * (1 - 1e-9)
+        res = []
+        for tile in (1, 0):
+            ctx = Context(0)
+            ctx.init_domain([0.0, dims[0], 0.0, dims[1], 0.0, dims[2]])
+            ctx.set_option("tile_lists", tile)
+            ctx.set_option("lj_fma", 0)
+            ctx.setup_cells(CUT + SKIN)
+            ctx.set_lj_params(1, [1.0], [1.0])
+            ctx.upload(pos, np.zeros((n, 3)), np.ones(n), np.zeros(n, np.int32))
+            _reneighbor_gpu(ctx)
+            tag = ctx.ints("tag")
+            nb = ctx.neighbors()
+            tags_all = ctx.ints("tag", with_ghosts=True)
+            # compare as (identity of i, sorted identities / ghost indices of its neighbours): ghosts are ordered alike in both runs
+            res.append((by_id(tag, ctx.ints("numneighs")), by_id(tag, np.where(nb >= 0, nb, -1)), tags_all))
+        assert np.array_equal(res[0][0], res[1][0]) and res[0][0].sum() > 0, dims
+        assert np.array_equal(res[0][1], res[1][1]), dims

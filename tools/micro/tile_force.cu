@@ -1,0 +1,585 @@
+// Prototype / micro-benchmark behind the round-2 force-kernel design: cell TILES staged in shared memory.
+//
+// Question: the production force kernel (thread per particle, one 32-byte LDG.E.256 gather per neighbour) is bound by the
+// L1TEX data pipe (ncu: 90 % of peak, ~20 distinct 128-byte lines per warp-wide gather).  Does a CTA that first stages the
+// positions of its particles' whole stencil neighbourhood (a "tile": 9 cell columns x the z-range of the CTA's particles + 1
+// cell either side) in shared memory, and then walks 16-bit tile-relative neighbour lists with LDS, beat it?  And what does the
+// same tile do for the list build (candidates tested out of shared memory)?
+//
+// Everything the production path does is mirrored: (cell, z slab) counting-sort order, slab CSR, z-windowed list build, sliced
+// ELLPACK lists, the reference's pair arithmetic without contraction (compile with --fmad=false).  Variants:
+//   base        32-bit lists, LDG.E.256 gather                      (the production kernel)
+//   tile        16-bit lists (4 packed per 64-bit word), positions from shared memory, same arithmetic, same summation order
+//               -> forces must be BIT-IDENTICAL to base
+//   *_fma       fused multiply-adds + Newton reciprocal instead of the IEEE division (tolerance 1e-12)
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --fmad=false -lineinfo -o _bin/tile_force tile_force.cu
+// Run:    _bin/tile_force [nx=100] [jitter=0.12] [only tile variant 0..4]
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while(0)
+
+struct Geom {
+    double lo[3];
+    double spacing, inv_slab;
+    int dim0, dim1, dim2, zsub, ncells;   // ncells = dim0*dim1*dim2 + 1 (cell 0 reserved, as in the reference)
+};
+
+static const int NCAP = 96;               // list capacity per particle (multiple of 4)
+
+__device__ __forceinline__ double4 ld256(const double4 *p) {
+    double4 r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
+}
+
+// ---- pair arithmetic -------------------------------------------------------------------------------------------------------
+template<int FMA>
+__device__ __forceinline__ void lj_pair(double xi, double yi, double zi, double xj, double yj, double zj, bool valid, double cutsq,
+                                        double &fx, double &fy, double &fz) {
+    const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
+    if(!FMA) {
+        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if(valid && rsq < cutsq) {
+            const double sr2 = __ddiv_rn(1.0, rsq);
+            const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), 1.0);
+            const double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), 1.0);
+            fx = __dadd_rn(fx, __dmul_rn(dx, f));
+            fy = __dadd_rn(fy, __dmul_rn(dy, f));
+            fz = __dadd_rn(fz, __dmul_rn(dz, f));
+        }
+    } else {
+        const double rsq = fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx)));
+        if(valid && rsq < cutsq) {
+            double y;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
+            double e = fma(-rsq, y, 1.0);
+            y = fma(y, e, y);
+            if(FMA >= 3) {
+                e = fma(-rsq, y, 1.0);
+                y = fma(y, e, y);
+            }
+            e = fma(-rsq, y, 1.0);
+            const double sr2 = fma(y, e, y);
+            const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), 1.0);
+            const double f = __dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2);
+            fx = fma(dx, f, fx);
+            fy = fma(dy, f, fy);
+            fz = fma(dz, f, fz);
+        }
+    }
+}
+
+// ---- production-style list build: thread per particle, z-windowed runs of the slab CSR, 32-bit sliced ELLPACK ---------------
+__device__ __forceinline__ bool run_window(const Geom &g, int c0, int c1, int c2, double fx, double fy, double zrel, double cutsq, int r,
+                                           const int *__restrict__ sub_start, int &b, int &e) {
+    const int dx = r / 3 - 1, dy = r % 3 - 1;
+    const double ddx = (dx == 0) ? 0.0 : ((dx < 0) ? fx : g.spacing - fx);
+    const double ddy = (dy == 0) ? 0.0 : ((dy < 0) ? fy : g.spacing - fy);
+    const double wsq = cutsq - (ddx * ddx + ddy * ddy);
+    if(wsq <= 0.0) { return false; }
+    const int X = c0 + dx, Y = c1 + dy;
+    if(X < 0 || X >= g.dim0 || Y < 0 || Y >= g.dim1) { return false; }
+    const double w = sqrt(wsq) + 1e-9 * g.spacing;
+    const long col = ((long) X * g.dim1 + Y) * g.dim2 + 1;
+    int gz_lo = (int) floor((zrel - w) * g.inv_slab), gz_hi = (int) floor((zrel + w) * g.inv_slab);
+    gz_lo = max(gz_lo, max((c2 - 1) * g.zsub, 0));
+    gz_hi = min(gz_hi, min((c2 + 1) * g.zsub + g.zsub - 1, g.dim2 * g.zsub - 1));
+    if(gz_lo > gz_hi) { return false; }
+    b = sub_start[col * g.zsub + gz_lo];
+    e = sub_start[col * g.zsub + gz_hi + 1];
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_build_base(int n, Geom g, double cutsq, const double4 *__restrict__ pos, const int *__restrict__ pc,
+                                                    const int *__restrict__ sub_start, const int *__restrict__ cell_list,
+                                                    int *__restrict__ neigh, int *__restrict__ numneigh) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    const double4 pi = ld256(pos + i);
+    const int flat = pc[i] - 1;
+    const int c2 = flat % g.dim2, c1 = (flat / g.dim2) % g.dim1, c0 = flat / (g.dim2 * g.dim1);
+    const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
+    int *const out = neigh + (size_t) (i >> 5) * NCAP * 32 + (i & 31);
+    int count = 0;
+    for(int r = 0; r < 9; r++) {
+        int b, e;
+        if(!run_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
+        for(int k = b; k < e; k++) {
+            const int j = __ldg(cell_list + k);
+            const double4 pj = ld256(pos + j);
+            const double dx = __dsub_rn(pi.x, pj.x), dy = __dsub_rn(pi.y, pj.y), dz = __dsub_rn(pi.z, pj.z);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if(rsq < cutsq && j != i) {
+                if(count < NCAP) { out[(size_t) count * 32] = j; }
+                count++;
+            }
+        }
+    }
+    numneigh[i] = count;
+}
+
+template<int FMA>
+__global__ void __launch_bounds__(128) k_force_base(int n, double cutsq, const double4 *__restrict__ pos, const int *__restrict__ numneigh,
+                                                    const int *__restrict__ neigh, double *__restrict__ force) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    const double4 pi = ld256(pos + i);
+    const int nn = min(numneigh[i], NCAP);
+    const int *nb = neigh + (size_t) (i >> 5) * NCAP * 32 + (i & 31);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    int k = 0;
+    for(; k + 4 <= nn; k += 4) {
+        int j[4];
+        double4 q[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++) { j[u] = __ldg(nb + (size_t) (k + u) * 32); }
+#pragma unroll
+        for(int u = 0; u < 4; u++) { q[u] = ld256(pos + j[u]); }
+#pragma unroll
+        for(int u = 0; u < 4; u++) { lj_pair<FMA>(pi.x, pi.y, pi.z, q[u].x, q[u].y, q[u].z, true, cutsq, fx, fy, fz); }
+    }
+    for(; k < nn; k++) {
+        const double4 q = ld256(pos + __ldg(nb + (size_t) k * 32));
+        lj_pair<FMA>(pi.x, pi.y, pi.z, q.x, q.y, q.z, true, cutsq, fx, fy, fz);
+    }
+    force[i] = __dadd_rn(0.0, fx);
+    force[n + i] = __dadd_rn(0.0, fy);
+    force[2 * (size_t) n + i] = __dadd_rn(0.0, fz);
+}
+
+// ---- tiles -----------------------------------------------------------------------------------------------------------------
+// A tile = the cells [za, zb] of a SUPER-COLUMN (2 x 2 cell columns), cut by the planner so that it holds at most M particles.
+// The CTA stages the 4 x 4 columns around it over [za-1, zb+1] -- 16 contiguous runs of the cell CSR -- into shared memory
+// (cp.async, no registers), thread t owns the t-th particle of the 4 core runs, list row = row_base + t.
+struct Tile { int X0, Y0, za, zb, row_base, pad; };
+static const int NRUN = 16;
+struct TileHdr {
+    int total, ncore, pad0, pad1;
+    int run_begin[NRUN], run_len[NRUN], run_slot0[NRUN];
+    int core_begin[4], core_off[5];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void tile_setup(TileHdr *h, const Geom &g, const Tile &tl, const int *__restrict__ cell_start) {
+    const int t = threadIdx.x;
+    if(t < NRUN) {
+        int len = 0, begin = 0;
+        const int X = tl.X0 - 1 + t / 4, Y = tl.Y0 - 1 + t % 4;
+        if(X >= 0 && X < g.dim0 && Y >= 0 && Y < g.dim1) {
+            const int zb = max(tl.za - 1, 0), ze = min(tl.zb + 1, g.dim2 - 1);
+            const int fb = (X * g.dim1 + Y) * g.dim2 + zb, fe = (X * g.dim1 + Y) * g.dim2 + ze;
+            begin = cell_start[fb + 1];
+            len = cell_start[fe + 2] - begin;
+        }
+        h->run_begin[t] = begin;
+        h->run_len[t] = len;
+    } else if(t >= 32 && t < 36) {
+        const int q = t - 32;
+        const int X = tl.X0 + q / 2, Y = tl.Y0 + q % 2;
+        int begin = 0, len = 0;
+        if(X < g.dim0 && Y < g.dim1) {
+            const int fb = (X * g.dim1 + Y) * g.dim2 + tl.za, fe = (X * g.dim1 + Y) * g.dim2 + tl.zb;
+            begin = cell_start[fb + 1];
+            len = cell_start[fe + 2] - begin;
+        }
+        h->core_begin[q] = begin;
+        h->core_off[q + 1] = len;
+    }
+    __syncthreads();
+    if(t == 0) {
+        int acc = 0;
+        for(int r = 0; r < NRUN; r++) { h->run_slot0[r] = acc; acc += h->run_len[r]; }
+        h->total = acc;
+        h->core_off[0] = 0;
+        for(int q = 0; q < 4; q++) { h->core_off[q + 1] += h->core_off[q]; }
+        h->ncore = h->core_off[4];
+    }
+    __syncthreads();
+}
+
+// CSR position of the t-th core particle (-1: none)
+__device__ __forceinline__ int tile_core_slot(const TileHdr *h, int t) {
+    if(t >= h->ncore) { return -1; }
+    int q = 0;
+    if(t >= h->core_off[1]) { q = 1; }
+    if(t >= h->core_off[2]) { q = 2; }
+    if(t >= h->core_off[3]) { q = 3; }
+    return h->core_begin[q] + (t - h->core_off[q]);
+}
+
+template<bool WITH_IDX>
+__device__ __forceinline__ void tile_stage(const TileHdr *h, int cap, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
+                                           double2 *sxy, double *sz, int *sidx) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for(int r = warp; r < NRUN; r += nw) {
+        const int len = h->run_len[r], begin = h->run_begin[r], slot0 = h->run_slot0[r];
+        for(int k0 = 0; k0 < len; k0 += 128) {
+            int idx[4];
+#pragma unroll
+            for(int u = 0; u < 4; u++) { const int k = k0 + u * 32 + lane; idx[u] = (k < len) ? __ldg(cell_list + begin + k) : -1; }
+#pragma unroll
+            for(int u = 0; u < 4; u++) {
+                const int s = slot0 + k0 + u * 32 + lane;
+                if(idx[u] >= 0 && s < cap) {
+                    const double *src = reinterpret_cast<const double *>(pos + idx[u]);
+                    cp_async16(sxy + s, src);
+                    cp_async8(sz + s, src + 2);
+                    if(WITH_IDX) { sidx[s] = idx[u]; }
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
+// shared memory carve-up: [hdr][xy: cap*16][z: cap*8][idx: cap*4 (build only)]
+__device__ __forceinline__ void tile_smem(unsigned char *base, int cap, TileHdr *&h, double2 *&sxy, double *&sz, int *&sidx) {
+    h = reinterpret_cast<TileHdr *>(base);
+    unsigned char *p = base + ((sizeof(TileHdr) + 15) / 16) * 16;
+    sxy = reinterpret_cast<double2 *>(p);
+    sz = reinterpret_cast<double *>(sxy + cap);
+    sidx = reinterpret_cast<int *>(sz + cap);
+}
+static size_t tile_smem_bytes(int cap, bool with_idx) { return ((sizeof(TileHdr) + 15) / 16) * 16 + (size_t) cap * 24 + (with_idx ? (size_t) cap * 4 : 0); }
+
+// list words: 4 16-bit slots per 64-bit word; word q of row r at ((r/32)*T4 + q)*32 + r%32, T4 = NCAP/4
+template<int M>
+__global__ void __launch_bounds__(M) k_build_tile(int n, int cap, Geom g, double cutsq, const Tile *__restrict__ tiles, const double4 *__restrict__ pos,
+                                                  const int *__restrict__ pc, const int *__restrict__ cell_start, const int *__restrict__ sub_start,
+                                                  const int *__restrict__ cell_list, unsigned long long *__restrict__ words,
+                                                  int *__restrict__ numneigh, int *__restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileHdr *h; double2 *sxy; double *sz; int *sidx;
+    tile_smem(smem, cap, h, sxy, sz, sidx);
+    const Tile tl = tiles[blockIdx.x];
+    tile_setup(h, g, tl, cell_start);
+    if(threadIdx.x == 0) {
+        atomicMax(stats + 0, h->total);
+        atomicMax(stats + 1, h->ncore);
+        if(h->total > cap || h->ncore > M) { atomicAdd(stats + 2, 1); }
+    }
+    if(h->total > cap || h->ncore > M) { return; }
+    tile_stage<true>(h, cap, cell_list, pos, sxy, sz, sidx);
+    __syncthreads();
+    const int cs = tile_core_slot(h, threadIdx.x);
+    if(cs < 0) { return; }
+    const int i = __ldg(cell_list + cs);
+    if(i >= n) { return; }
+    const double4 pi = ld256(pos + i);
+    const int flat = pc[i] - 1;
+    const int c2 = flat % g.dim2, col = flat / g.dim2, c1 = col % g.dim1, c0 = col / g.dim1;
+    const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
+    const int row = tl.row_base + threadIdx.x;
+    unsigned long long *const out = words + (size_t) (row >> 5) * (NCAP / 4) * 32 + (row & 31);
+    unsigned long long w = 0ull;
+    int count = 0;
+    for(int r = 0; r < 9; r++) {
+        int b, e;
+        if(!run_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
+        const int tr = (c0 + r / 3 - 1 - (tl.X0 - 1)) * 4 + (c1 + r % 3 - 1 - (tl.Y0 - 1));      // the staged run of this stencil row
+        const int shift = h->run_slot0[tr] - h->run_begin[tr];
+        for(int k = b; k < e; k++) {
+            const int s = k + shift;
+            const double2 xy = sxy[s];
+            const double z = sz[s];
+            const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if(rsq < cutsq && sidx[s] != i) {
+                if(count < NCAP) {
+                    w |= (unsigned long long) (unsigned) s << (16 * (count & 3));
+                    if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
+                }
+                count++;
+            }
+        }
+    }
+    if((count & 3) != 0 && count < NCAP) { out[(size_t) (count >> 2) * 32] = w; }
+    numneigh[i] = count;
+}
+
+template<int M, int FMA, int PREFETCH>
+__global__ void __launch_bounds__(M) k_force_tile(int n, int cap, Geom g, double cutsq, const Tile *__restrict__ tiles, const double4 *__restrict__ pos,
+                                                  const int *__restrict__ cell_start, const int *__restrict__ cell_list,
+                                                  const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
+                                                  double *__restrict__ force) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileHdr *h; double2 *sxy; double *sz; int *sidx;
+    tile_smem(smem, cap, h, sxy, sz, sidx);
+    const Tile tl = tiles[blockIdx.x];
+    tile_setup(h, g, tl, cell_start);
+    if(h->total > cap || h->ncore > M) { return; }
+    // own data first: these loads fly while the tile is staged
+    const int cs = tile_core_slot(h, threadIdx.x);
+    int i = (cs >= 0) ? __ldg(cell_list + cs) : n;
+    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
+    int nn = 0;
+    const int row = tl.row_base + threadIdx.x;
+    const unsigned long long *wp = words + (size_t) (row >> 5) * (NCAP / 4) * 32 + (row & 31);
+    unsigned long long wnext = 0ull;
+    if(i < n) {
+        pi = ld256(pos + i);
+        nn = min(numneigh[i], NCAP);
+        if(nn > 0) { wnext = __ldg(wp); }
+    }
+    tile_stage<false>(h, cap, cell_list, pos, sxy, sz, sidx);
+    __syncthreads();
+    if(i >= n) { return; }
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for(int k = 0; k < nn; k += 4) {
+        unsigned long long w;
+        if(PREFETCH) {
+            w = wnext;
+            if(k + 4 < nn) { wnext = __ldg(wp + (size_t) ((k >> 2) + 1) * 32); }
+        } else {
+            w = __ldg(wp + (size_t) (k >> 2) * 32);
+        }
+        double xj[4], yj[4], zj[4];
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            const int s = (k + u < nn) ? (int) ((w >> (16 * u)) & 0xffffull) : 0;
+            const double2 xy = sxy[s];
+            xj[u] = xy.x; yj[u] = xy.y;
+            zj[u] = sz[s];
+        }
+#pragma unroll
+        for(int u = 0; u < 4; u++) { lj_pair<FMA>(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], k + u < nn, cutsq, fx, fy, fz); }
+    }
+    force[i] = __dadd_rn(0.0, fx);
+    force[n + i] = __dadd_rn(0.0, fy);
+    force[2 * (size_t) n + i] = __dadd_rn(0.0, fz);
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------------
+static unsigned long long lcg_state = 88172645463325252ull;
+static double urand() {
+    lcg_state ^= lcg_state << 13; lcg_state ^= lcg_state >> 7; lcg_state ^= lcg_state << 17;
+    return (double) (lcg_state >> 11) * (1.0 / 9007199254740992.0);
+}
+
+template<typename F>
+static float time_ms(int reps, F f) {
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    for(int w = 0; w < 2; w++) { f(); }
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a));
+    for(int r = 0; r < reps; r++) { f(); }
+    CK(cudaEventRecord(b));
+    CK(cudaEventSynchronize(b));
+    CK(cudaGetLastError());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    return ms / reps;
+}
+
+static double compare(const std::vector<double> &a, const std::vector<double> &b, size_t *ndiff_bits) {
+    double mx = 0.0, err = 0.0;
+    size_t nd = 0;
+    for(size_t k = 0; k < a.size(); k++) {
+        mx = std::max(mx, std::fabs(a[k]));
+        err = std::max(err, std::fabs(a[k] - b[k]));
+        nd += (memcmp(&a[k], &b[k], 8) != 0);
+    }
+    *ndiff_bits = nd;
+    return err / mx;
+}
+
+int main(int argc, char **argv) {
+    const int nx = argc > 1 ? atoi(argv[1]) : 100;
+    const double jitter = argc > 2 ? atof(argv[2]) : 0.12;
+    const double a = pow(4.0 / 0.8442, 1.0 / 3.0), L = nx * a, spacing = 2.8, cutl = 2.8, cutf = 2.5;
+    const int zsub = 8;
+    const int n = 4 * nx * nx * nx;
+    Geom g;
+    for(int d = 0; d < 3; d++) { g.lo[d] = -spacing; }
+    g.spacing = spacing; g.inv_slab = zsub / spacing; g.zsub = zsub;
+    const int dim = (int) ceil((L + 2 * spacing) / spacing) + 1;
+    g.dim0 = g.dim1 = g.dim2 = dim;
+    g.ncells = dim * dim * dim + 1;
+    printf("{\"nx\": %d, \"atoms\": %d, \"dim_cells\": %d, \"jitter\": %.3f}\n", nx, n, dim, jitter);
+
+    std::vector<double4> p0(n);
+    {
+        const double bx[4] = {0, 0.5, 0.5, 0}, by[4] = {0, 0.5, 0, 0.5}, bz[4] = {0, 0, 0.5, 0.5};
+        size_t k = 0;
+        for(int x = 0; x < nx; x++) for(int y = 0; y < nx; y++) for(int z = 0; z < nx; z++) for(int b = 0; b < 4; b++) {
+            double4 p;
+            p.x = std::min(std::max((x + bx[b] + 0.25) * a + (2 * urand() - 1) * jitter, 0.0), L * (1 - 1e-12));
+            p.y = std::min(std::max((y + by[b] + 0.25) * a + (2 * urand() - 1) * jitter, 0.0), L * (1 - 1e-12));
+            p.z = std::min(std::max((z + bz[b] + 0.25) * a + (2 * urand() - 1) * jitter, 0.0), L * (1 - 1e-12));
+            p.w = 0.0;
+            p0[k++] = p;
+        }
+    }
+    // (cell, z slab) keys, counting sort (stable), slab CSR + coarse CSR
+    const long nbins = (long) g.ncells * zsub;
+    std::vector<int> key(n), pcell(n);
+    std::vector<int> sub_start(nbins + 1, 0);
+    for(int i = 0; i < n; i++) {
+        const double q0 = (p0[i].x - g.lo[0]) / spacing, q1 = (p0[i].y - g.lo[1]) / spacing, q2 = (p0[i].z - g.lo[2]) / spacing;
+        const int c0 = std::min((int) q0, dim - 1), c1 = std::min((int) q1, dim - 1), c2 = std::min((int) q2, dim - 1);
+        const int cell = (c0 * dim + c1) * dim + c2 + 1;
+        const int zs = std::min(std::max((int) ((q2 - c2) * zsub), 0), zsub - 1);
+        pcell[i] = cell;
+        key[i] = cell * zsub + zs;
+        sub_start[key[i] + 1]++;
+    }
+    for(long b = 0; b < nbins; b++) { sub_start[b + 1] += sub_start[b]; }
+    std::vector<int> fill(sub_start.begin(), sub_start.end() - 1), perm(n);
+    for(int i = 0; i < n; i++) { perm[fill[key[i]]++] = i; }
+    std::vector<double4> pos(n);
+    std::vector<int> pc(n), cell_list(n);
+    for(int k = 0; k < n; k++) { pos[k] = p0[perm[k]]; pc[k] = pcell[perm[k]]; cell_list[k] = k; }
+    std::vector<int> cell_start(g.ncells + 1);
+    for(int c = 0; c <= g.ncells; c++) { cell_start[c] = sub_start[(long) c * zsub]; }
+
+    double4 *d_pos; int *d_pc, *d_sub, *d_cs, *d_cl, *d_neigh, *d_nn, *d_nn2, *d_stats; double *d_f0, *d_f1;
+    const size_t groups = (n + 31) / 32;
+    CK(cudaMalloc(&d_pos, sizeof(double4) * n)); CK(cudaMalloc(&d_pc, 4 * (size_t) n)); CK(cudaMalloc(&d_sub, 4 * (nbins + 1)));
+    CK(cudaMalloc(&d_cs, 4 * (size_t) (g.ncells + 1))); CK(cudaMalloc(&d_cl, 4 * (size_t) n));
+    CK(cudaMalloc(&d_neigh, 4 * groups * NCAP * 32));
+    CK(cudaMalloc(&d_nn, 4 * (size_t) n)); CK(cudaMalloc(&d_nn2, 4 * (size_t) n)); CK(cudaMalloc(&d_stats, 16));
+    CK(cudaMalloc(&d_f0, 24 * (size_t) n)); CK(cudaMalloc(&d_f1, 24 * (size_t) n));
+    CK(cudaMemcpy(d_pos, pos.data(), sizeof(double4) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_pc, pc.data(), 4 * (size_t) n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_sub, sub_start.data(), 4 * (nbins + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cs, cell_start.data(), 4 * (size_t) (g.ncells + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cl, cell_list.data(), 4 * (size_t) n, cudaMemcpyHostToDevice));
+
+    const double cutsq_l = cutl * cutl, cutsq_f = cutf * cutf;
+    const int B128 = (n + 127) / 128;
+    float ms = time_ms(3, [&] { k_build_base<<<B128, 128>>>(n, g, cutsq_l, d_pos, d_pc, d_sub, d_cl, d_neigh, d_nn); });
+    std::vector<int> nn(n);
+    CK(cudaMemcpy(nn.data(), d_nn, 4 * (size_t) n, cudaMemcpyDeviceToHost));
+    double kbar = 0; int kmax = 0;
+    for(int i = 0; i < n; i++) { kbar += nn[i]; kmax = std::max(kmax, nn[i]); }
+    kbar /= n;
+    printf("{\"kernel\": \"build_base\", \"ms\": %.4f, \"mean_neighbors\": %.2f, \"max_neighbors\": %d}\n", ms, kbar, kmax);
+    if(kmax > NCAP) { printf("list capacity exceeded\n"); return 1; }
+
+    std::vector<double> f0(3 * (size_t) n), f1(3 * (size_t) n);
+    ms = time_ms(10, [&] { k_force_base<0><<<B128, 128>>>(n, cutsq_f, d_pos, d_nn, d_neigh, d_f0); });
+    CK(cudaMemcpy(f0.data(), d_f0, 24 * (size_t) n, cudaMemcpyDeviceToHost));
+    printf("{\"kernel\": \"force_base\", \"ms\": %.4f}\n", ms);
+    size_t nd;
+    ms = time_ms(10, [&] { k_force_base<2><<<B128, 128>>>(n, cutsq_f, d_pos, d_nn, d_neigh, d_f1); });
+    CK(cudaMemcpy(f1.data(), d_f1, 24 * (size_t) n, cudaMemcpyDeviceToHost));
+    double err = compare(f0, f1, &nd);
+    printf("{\"kernel\": \"force_base_fma2\", \"ms\": %.4f, \"rel_err_vs_base\": %.3e}\n", ms, err);
+    ms = time_ms(10, [&] { k_force_base<3><<<B128, 128>>>(n, cutsq_f, d_pos, d_nn, d_neigh, d_f1); });
+    CK(cudaMemcpy(f1.data(), d_f1, 24 * (size_t) n, cudaMemcpyDeviceToHost));
+    err = compare(f0, f1, &nd);
+    printf("{\"kernel\": \"force_base_fma3\", \"ms\": %.4f, \"rel_err_vs_base\": %.3e}\n", ms, err);
+
+    // ---- planner (host here, a small kernel in production): per super-column a greedy walk over z, tiles of <= M particles ----
+    auto plan = [&](int M, std::vector<Tile> &tiles, int &rows) {
+        tiles.clear();
+        rows = 0;
+        int worst_staged = 0;
+        auto ccount = [&](int X, int Y, int z) {
+            if(X < 0 || Y < 0 || X >= dim || Y >= dim || z < 0 || z >= dim) { return 0; }
+            const int c = (X * dim + Y) * dim + z + 1;
+            return cell_start[c + 1] - cell_start[c];
+        };
+        for(int X0 = 0; X0 < dim; X0 += 2) for(int Y0 = 0; Y0 < dim; Y0 += 2) {
+            int za = 0;
+            while(za < dim) {
+                int core = 0, zb = za - 1;
+                while(zb + 1 < dim) {
+                    const int lvl = ccount(X0, Y0, zb + 1) + ccount(X0 + 1, Y0, zb + 1) + ccount(X0, Y0 + 1, zb + 1) + ccount(X0 + 1, Y0 + 1, zb + 1);
+                    if(zb >= za && core + lvl > M) { break; }
+                    core += lvl;
+                    zb++;
+                }
+                if(core > 0) {
+                    int staged = 0;
+                    for(int X = X0 - 1; X <= X0 + 2; X++) for(int Y = Y0 - 1; Y <= Y0 + 2; Y++) for(int z = za - 1; z <= zb + 1; z++) { staged += ccount(X, Y, z); }
+                    worst_staged = std::max(worst_staged, staged);
+                    Tile t; t.X0 = X0; t.Y0 = Y0; t.za = za; t.zb = zb; t.row_base = rows; t.pad = 0;
+                    tiles.push_back(t);
+                    rows += (core + 31) / 32 * 32;
+                }
+                za = zb + 1;
+            }
+        }
+        return worst_staged;
+    };
+
+    auto tile_variant = [&](auto Mtag, int cap) {
+        constexpr int M = decltype(Mtag)::value;
+        std::vector<Tile> tiles;
+        int rows = 0;
+        const int worst = plan(M, tiles, rows);
+        const int ntiles = (int) tiles.size();
+        Tile *d_tiles; unsigned long long *d_w;
+        CK(cudaMalloc(&d_tiles, sizeof(Tile) * ntiles));
+        CK(cudaMemcpy(d_tiles, tiles.data(), sizeof(Tile) * ntiles, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&d_w, 8 * (size_t) (rows / 32) * (NCAP / 4) * 32));
+        CK(cudaMemset(d_w, 0, 8 * (size_t) (rows / 32) * (NCAP / 4) * 32));
+        const size_t sb = tile_smem_bytes(cap, true), sf = tile_smem_bytes(cap, false);
+        CK(cudaFuncSetAttribute(k_build_tile<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sb));
+        CK(cudaFuncSetAttribute(k_force_tile<M, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sf));
+        CK(cudaFuncSetAttribute(k_force_tile<M, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sf));
+        CK(cudaFuncSetAttribute(k_force_tile<M, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sf));
+        CK(cudaMemset(d_stats, 0, 16));
+        CK(cudaMemset(d_nn2, 0, 4 * (size_t) n));
+        float msb = time_ms(3, [&] { k_build_tile<M><<<ntiles, M, sb>>>(n, cap, g, cutsq_l, d_tiles, d_pos, d_pc, d_cs, d_sub, d_cl, d_w, d_nn2, d_stats); });
+        int stats[4];
+        CK(cudaMemcpy(stats, d_stats, 16, cudaMemcpyDeviceToHost));
+        std::vector<int> nn2(n);
+        CK(cudaMemcpy(nn2.data(), d_nn2, 4 * (size_t) n, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        for(int i = 0; i < n; i++) { bad += nn2[i] != nn[i]; }
+        int occ_b = 0, occ_f = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_build_tile<M>, M, sb));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_f, k_force_tile<M, 0, 1>, M, sf));
+        printf("{\"kernel\": \"build_tile\", \"M\": %d, \"cap\": %d, \"ms\": %.4f, \"tiles\": %d, \"rows\": %d, \"planner_max_staged\": %d, \"max_staged\": %d, "
+               "\"max_core\": %d, \"tiles_over_capacity\": %d, \"count_mismatches\": %zu, \"smem_build\": %zu, \"smem_force\": %zu, "
+               "\"ctas_per_sm_build\": %d, \"ctas_per_sm_force\": %d}\n",
+               M, cap, msb, ntiles, rows, worst, stats[0], stats[1], stats[2], bad, sb, sf, occ_b, occ_f);
+        if(stats[2] == 0) {
+            auto report = [&](const char *name, float t, bool exact) {
+                CK(cudaMemcpy(f1.data(), d_f1, 24 * (size_t) n, cudaMemcpyDeviceToHost));
+                size_t ndiff;
+                const double e = compare(f0, f1, &ndiff);
+                printf("{\"kernel\": \"%s\", \"M\": %d, \"cap\": %d, \"ms\": %.4f, \"rel_err_vs_base\": %.3e, \"values_not_bit_identical\": %zu%s}\n", name, M, cap, t, e,
+                       ndiff, (exact && ndiff != 0) ? ", \"ERROR\": \"expected bit-identical\"" : "");
+            };
+            CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
+            float t = time_ms(10, [&] { k_force_tile<M, 0, 0><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w, d_nn2, d_f1); });
+            report("force_tile", t, true);
+            CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
+            t = time_ms(10, [&] { k_force_tile<M, 0, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w, d_nn2, d_f1); });
+            report("force_tile_prefetch", t, true);
+            CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
+            t = time_ms(10, [&] { k_force_tile<M, 2, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w, d_nn2, d_f1); });
+            report("force_tile_prefetch_fma2", t, false);
+        }
+        CK(cudaFree(d_tiles)); CK(cudaFree(d_w));
+    };
+    const int only = argc > 3 ? atoi(argv[3]) : -1;      // run one tile variant only (ncu captures)
+    if(only < 0 || only == 0) { tile_variant(std::integral_constant<int, 256>(), 2048); }
+    if(only < 0 || only == 1) { tile_variant(std::integral_constant<int, 256>(), 2304); }
+    if(only < 0 || only == 2) { tile_variant(std::integral_constant<int, 128>(), 1280); }
+    if(only < 0 || only == 3) { tile_variant(std::integral_constant<int, 192>(), 1792); }
+    if(only < 0 || only == 4) { tile_variant(std::integral_constant<int, 384>(), 3072); }
+    return 0;
+}
