@@ -37,7 +37,16 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def workload_config(n_gpus, nx):
+def workload_config(n_gpus, nx, reference_arm=False):
+    cfg = _workload_config(n_gpus, nx)
+    if reference_arm:
+        cfg["reference_sample"] = (f"the reference's serial C++ is timed on a {4 * REF_SAMPLE_NX ** 3}-atom cube (nx = {REF_SAMPLE_NX}) of the same "
+                                   "lattice generator per replica process, not on the 4,000,000-atom box: its cost per atom-step does not "
+                                   "depend on the box size, a 4 M-atom replica would take ~2 s per step and 6 GB per process")
+    return cfg
+
+
+def _workload_config(n_gpus, nx):
     return {"workload": f"lj_onetype-style synthetic FCC lattice, {4 * nx ** 3} atoms per GPU ({nx}^3 cells), rho 0.8442, "
                         f"cutoff 2.5 sigma + skin 0.3, reneighbour every {RENEIGH}, thermo every {THERMO}, fp64"
                         + (f"; weak scaling over {n_gpus} GPUs, regular partitioner, NCCL halo exchange" if n_gpus > 1 else ""),
@@ -47,29 +56,57 @@ def workload_config(n_gpus, nx):
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons streamed every 50 ms (one long-lived nvidia-smi -lms process) during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region.  NVML is polled every ~2 ms from a thread (a 20-step timed region
+    lasts ~20 ms: `nvidia-smi -lms 50` cannot see it); if the NVML binding is missing, one long-lived nvidia-smi process streams rows
+    every 50 ms instead.  The sampler starts before the warm-up; only rows taken while `recording` is set are kept."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.rows = []              # (sm MHz, max MHz, set of reasons)
         self.stop_flag = threading.Event()
         self.proc = None
         self.recording = False
+        self.source = None
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            if self.recording:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, mx, {k for k, b in bits.items() if r & b}))
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi -lms 50"
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            if self.stop_flag.is_set():
+                break
+            c = [x.strip() for x in line.split(",")]
+            if self.recording and len(c) >= 7 and c[0].replace(".", "").isdigit():
+                self.rows.append((float(c[0]), float(c[1]) if c[1].replace(".", "").isdigit() else None,
+                                  {n for k, n in enumerate(self.NAMES) if c[3 + k].lower().startswith("active")}))
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag.is_set():
-                    break
-                if self.recording and line.strip():
-                    self.rows.append([c.strip() for c in line.split(",")])
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
 
     def stop(self):
         self.stop_flag.set()
@@ -80,12 +117,11 @@ class ClockSampler(threading.Thread):
                 pass
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows if r[1]]
+        reasons = sorted(set().union(*[r[2] for r in self.rows])) if self.rows else []
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": self.source}
 
 
 def measured_peak():
@@ -219,7 +255,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * cb["seconds"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, args.nx),
+            "config": workload_config(args.gpus, args.nx, reference_arm=True),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
@@ -248,6 +284,15 @@ def run_ours(args):
     grid = [0.0, cells[0] * lattice, 0.0, cells[1] * lattice, 0.0, cells[2] * lattice]
     assert backend.rank_grid(world, grid) == gx, (backend.rank_grid(world, grid), gx)
 
+    # N > 1: the N-rank run against the SINGLE-RANK oracle of the same global system, before anything is timed (tests/mgpu_parity.py):
+    # a mismatch raises on every rank -> non-zero exit, no JSON line
+    parity_nranks = None
+    if world > 1 and not args.no_parity:
+        from tests import mgpu_parity
+        t_par = time.perf_counter()
+        parity_nranks = mgpu_parity.check(backend, dist, rank, world, local)
+        parity_nranks["seconds"] = time.perf_counter() - t_par
+
     ctx = backend.Context(local)
     ctx.init_domain(grid, world_size=world, rank=rank)
     if world > 1:
@@ -268,18 +313,13 @@ def run_ours(args):
 
     W, K = args.warmup, args.steps
     run = lambda a, b: ctx.md_run(a, b, DT, CUT, CUT + SKIN, CUT + SKIN, RENEIGH, THERMO)  # noqa: E731
-    run(0, W)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
-        time.sleep(0.4)           # let nvidia-smi come up before the timed region
-        run(W, W + 2)             # (two extra untimed iterations keep the GPU busy while it does)
-        W += 2
+        sampler.start()           # before the warm-up, so that it is up when the timed region begins
+    run(0, W)
+    barrier()
+    if rank == 0:
         sampler.recording = True
-    elif world > 1:
-        run(W, W + 2)
-        W += 2
     ctx.timers_reset()
     ctx.timers_enable(True)
     launches0 = ctx.kernel_launches()
@@ -310,7 +350,10 @@ def run_ours(args):
     kbar = float(nn.mean()) if len(nn) else 0.0
     bytes_per_atom = 4.0 * kbar + 60.0 + 24.0 * ng / max(nl, 1)     # ids + numneighs + x_i + type + flags + force write + ghost x
     peak, peak_src = measured_peak()
-    achieved = (bytes_per_atom * nl / 1e9) / (lj_ms / max(lj_calls, 1) * 1e-3) if lj_ms > 0 else None
+    # one force evaluation per step; with comm / compute overlap (N > 1) it is TWO launches (interior tiles on the main stream,
+    # boundary tiles on the comm stream): the per-step kernel time is their sum, whatever the number of recorded stages
+    lj_ms_per_step = lj_ms / K
+    achieved = (bytes_per_atom * nl / 1e9) / (lj_ms_per_step * 1e-3) if lj_ms > 0 else None
     stages = {}
     for name in ("lennard_jones", "initial_integrate", "final_integrate", "synchronize", "exchange", "borders", "build_cell_lists",
                  "build_neighbor_lists", "compute_thermo"):
@@ -322,11 +365,15 @@ def run_ours(args):
     reneighbor = {"every": RENEIGH, "rebuilds_in_timed_region": ren_calls, "ms_per_rebuild": ren_ms / ren_calls if ren_calls else None,
                   "ms_per_step_without_rebuilds": (ms - ren_ms) / K, "value_without_rebuilds": n_global * K / ((ms - ren_ms) * 1e-3),
                   "note": "rank 0 stage timers; rebuild = exchange + borders + cell lists + neighbour lists"}
-    roofline = {"bound": "hbm", "kernel": "pb_k_lennard_jones", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "pb_k_tile_lj", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "algorithmic_bytes_per_atom": bytes_per_atom, "mean_neighbors": kbar, "atoms_per_launch": nl,
-                "avg_launch_ms": lj_ms / max(lj_calls, 1), "force_kernel_atoms_per_s": nl / (lj_ms / max(lj_calls, 1) * 1e-3) if lj_ms > 0 else None,
-                "share_of_step": lj_ms / ms if ms > 0 else None}
+                "algorithmic_bytes_per_atom": bytes_per_atom, "mean_neighbors": kbar, "atoms_per_step": nl,
+                "launches_per_step": lj_calls / K, "ms_per_step_in_kernel": lj_ms_per_step,
+                "force_kernel_atoms_per_s": nl / (lj_ms_per_step * 1e-3) if lj_ms > 0 else None,
+                "share_of_step": lj_ms / ms if ms > 0 else None,
+                "note": "numerator = SURVEY.md 8(d): 4 B per list entry + 60 B per atom + ghost positions; the tile lists actually "
+                        "hold 2 B per entry (bytes_per_atom_as_stored), the staged tiles are re-read from L2, not HBM",
+                "bytes_per_atom_as_stored": 2.0 * kbar + 60.0 + 24.0 * ng / max(nl, 1)}
 
     # ---- end to end through the C-ABI with HOST buffers: upload (pinned) -> K loop iterations from ts = 0 (first list build
     #      included) with thermo read-backs -> download of positions and velocities ----
@@ -381,6 +428,7 @@ def run_ours(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "warmup": args.warmup, "config": workload_config(world, nx), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "reference_cuda": reference_cuda, "dem": dem, "reneighbor": reneighbor, "stages_ms": stages, "atoms_global": n_global,
+                "parity_nranks": parity_nranks,
                 "nlocal_rank0": nl, "nghost_rank0": ng, "wall_s_timed_region": t_wall, "setup_s": t_setup,
                 "thermo_last": [float(x) for x in thermo[-1]] if len(thermo) else None}
         _JSON_OUT.write(json.dumps(line) + "\n")
@@ -405,6 +453,7 @@ def main():
     ap.add_argument("--ref-replicas", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dem", action="store_true", help="skip the secondary DEM workload (tools/bench_dem.py)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the N-rank parity check against the single-rank oracle")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

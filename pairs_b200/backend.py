@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "lib", "libpairs_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu", "props.cu", "pair_lists.cu", "tile_lists.cu"]
+SOURCES = ["ctx.cu", "binning.cu", "neighbor.cu", "md_kernels.cu", "comm.cu", "comm_nccl.cu", "migrate.cu", "setup.cu", "md_run.cu", "dem_kernels.cu", "jit.cu", "props.cu", "tile_lists.cu"]
 
 # --fmad=false: fp64 multiplies and adds are never contracted, so per-operation results equal the reference CPU
 # build compiled with -ffp-contract=off (the parity contract).
@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into pairs_b200/lib/libpairs_b200.so (in-tree).  One object per source, compiled
     in parallel and only when the source or a header is newer, then linked."""
     from concurrent.futures import ThreadPoolExecutor
-    headers = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(CSRC, "dem_force_kernel.cuh"), os.path.join(CSRC, "pair_lists.h"),
+    headers = [os.path.join(CSRC, "ctx.cuh"), os.path.join(CSRC, "dem_math.h"), os.path.join(CSRC, "md_math.h"), os.path.join(CSRC, "dem_force_kernel.cuh"),
                os.path.join(INCLUDE, "pairs_b200.h")]
     objdir = os.path.join(os.path.dirname(LIB_PATH), "obj")
     os.makedirs(objdir, exist_ok=True)

@@ -81,7 +81,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
                     ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
                     ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->d_fric_static,
-                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt, ctx->pneigh, ctx->pnum,
+                    ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt,
                     ctx->tiles, ctx->tile_lvl, ctx->tile_cnt, ctx->tile_off, ctx->tile_pad, ctx->tile_row, ctx->twords, ctx->tile_flag,
                     ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }

@@ -112,12 +112,6 @@ struct pb_ctx {
     const int *lj_groups = nullptr;   // group list of the force launch being issued (null = all groups)
     int lj_ngroups = 0;
     bool overlap_comm = true;     // multi-rank: refresh ghosts on comm_stream while the interior groups compute
-    // pair lists (pair_lists.cu, option "pair_lists"): one union list per pair of consecutive particles, sliced ELLPACK over pairs
-    bool pair_lists = false;
-    int *pneigh = nullptr, *pnum = nullptr;
-    size_t pneigh_bytes = 0;
-    int pnum_cap = 0, pair_T2 = 0;
-    int pairs_n = -1;             // nlocal when the pair lists were built (-1: none)
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_sync = nullptr;
 

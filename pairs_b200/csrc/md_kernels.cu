@@ -332,8 +332,6 @@ static int pb_launch_lj_f(pb_ctx *ctx, double cutsq, double dt, int fuse) {
 // fuse: bit 0 = final_integrate of this step, bit 1 = initial_integrate of the next step (positions double-buffered)
 // part: 0 = all particles, 1 = interior warp groups only, 2 = boundary warp groups only (the buffer swap of a fused
 // initial_integrate happens after part 0 or part 2)
-int pb_lennard_jones_pairs(pb_ctx *ctx, double cutsq, double dt, int fuse);      // pair_lists.cu
-
 int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int part) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "lennard_jones");
@@ -363,9 +361,6 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int 
         ctx->lj_ngroups = (part == 1) ? ctx->n_interior : ctx->n_boundary;
     }
     int rc;
-    if(ctx->pair_lists && part == 0 && ctx->lanes == 1 && ctx->pairs_n == ctx->nlocal) {
-        rc = pb_lennard_jones_pairs(ctx, cutsq, dt, fuse);       // experimental: one union list per pair of particles (pair_lists.cu)
-    } else
     switch(ctx->lanes) {
         case 1: rc = pb_launch_lj_f<1>(ctx, cutsq, dt, fuse); break;
         case 2: rc = pb_launch_lj_f<2>(ctx, cutsq, dt, fuse); break;
@@ -424,7 +419,6 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
     if(nm == "tile_lists") { ctx->tile_lists = value != 0; ctx->tiles_n = -1; ctx->neigh_n = -1; return 0; }      // lists must be rebuilt
     if(nm == "lj_fma") { ctx->lj_fma = value != 0; return 0; }
     if(nm == "profiler") { ctx->nvtx = value != 0; return 0; }
-    if(nm == "pair_lists") { ctx->pair_lists = value != 0; ctx->pairs_n = -1; return 0; }      // applies from the next list build
     if(nm == "dem_force_maxreg") {       // occupancy experiments: NVRTC re-build of the contact kernel (built-in model) with a register cap
         if(value < 0 || value > 255) { ctx->set_error("dem_force_maxreg: 0 (off) .. 255"); return -1; }
         ctx->dem_force_maxreg = value;

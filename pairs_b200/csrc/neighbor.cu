@@ -19,8 +19,6 @@
 
 #include "ctx.cuh"
 
-int pb_build_pair_lists(pb_ctx *ctx, double cutsq_lists);      // pair_lists.cu (option "pair_lists")
-
 struct PbFaces {
     double lo[3], hi[3];   // subdom_min + margin, subdom_max - margin
 };
@@ -229,9 +227,7 @@ static int pb_build_neigh32(pb_ctx *ctx, double cutoff) {
         ctx->max_neigh = ctx->h_scalars[0];
         if(ctx->max_neigh <= ctx->ncap) {
             if(ctx->world > 1 && ctx->overlap_comm && ctx->lanes == 1) { PB_TRY(pb_split_groups(ctx, ngroups)); }
-            ctx->pairs_n = -1;
             ctx->neigh_n = n;         // only now: an error return above must not leave half-built lists looking valid
-            if(ctx->pair_lists && !ctx->half_lists && ctx->lanes == 1) { PB_TRY(pb_build_pair_lists(ctx, cutsq)); }
             return 0;
         }
         // capacity-overflow protocol (transformations/modules.py:159-203): grow to twice the need and re-run the module
@@ -253,7 +249,6 @@ extern "C" int pb_build_neighbor_lists(pb_ctx *ctx, double cutoff) {
     ctx->list_cutoff = cutoff;
     ctx->neigh_n = -1;
     ctx->tiles_n = -1;
-    ctx->pairs_n = -1;
     ctx->groups_valid = false;
     ctx->tile_split_valid = false;
     if(ctx->nlocal == 0) { ctx->neigh_n = 0; ctx->max_neigh = 0; return 0; }

@@ -290,31 +290,43 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int nca
         const int row = tl.row_base + threadIdx.x;
         unsigned long long *const out = words + pb_tile_word(row, T4, 0);
         unsigned long long w = 0ull;
+        // the 9 candidate windows as shared-memory slot ranges; then ONE flat loop over all of them: the lanes of a warp run through
+        // windows of different lengths, a loop per window would leave half of them idle (ncu: 15.6 of 32 lanes active)
+        int wb[9], we[9];
+#pragma unroll
         for(int r = 0; r < 9; r++) {
-            int b, e;
-            if(!pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
-            const int tr = (c0 + r / 3 - 1 - (tl.X0 - 1)) * 4 + (c1 + r % 3 - 1 - (tl.Y0 - 1));      // the staged run of this stencil row
-            const int shift = h->run_slot0[tr] - h->run_begin[tr];
-            for(int k = b; k < e; k++) {
-                const int s = k + shift;
-                const double2 xy = sxy[s];
-                const double z = sz[s];
-                const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
-                const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if(rsq < cutsq) {
-                    const int j = sidx[s];
-                    if(j != i) {
-                        if(count < ncap) {
-                            unsigned entry = (unsigned) s;
-                            if(TYPES) { entry |= (unsigned) (pb_w_type(sw[s]) & 7) << 12; }
-                            w |= (unsigned long long) entry << (16 * (count & 3));
-                            if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
-                        }
-                        count++;
-                        boundary |= (j >= nlocal);
+            int b = 0, e = 0;
+            if(pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) {
+                const int tr = (c0 + r / 3 - 1 - (tl.X0 - 1)) * 4 + (c1 + r % 3 - 1 - (tl.Y0 - 1));      // the staged run of this stencil row
+                const int shift = h->run_slot0[tr] - h->run_begin[tr];
+                b += shift;
+                e += shift;
+            }
+            wb[r] = b;
+            we[r] = e;
+        }
+        int r = 0, s = wb[0], end = we[0];
+        for(;;) {
+            while(s >= end && r < 8) { r++; s = wb[r]; end = we[r]; }
+            if(s >= end) { break; }
+            const double2 xy = sxy[s];
+            const double z = sz[s];
+            const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if(rsq < cutsq) {
+                const int j = sidx[s];
+                if(j != i) {
+                    if(count < ncap) {
+                        unsigned entry = (unsigned) s;
+                        if(TYPES) { entry |= (unsigned) (pb_w_type(sw[s]) & 7) << 12; }
+                        w |= (unsigned long long) entry << (16 * (count & 3));
+                        if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
                     }
+                    count++;
+                    boundary |= (j >= nlocal);
                 }
             }
+            s++;
         }
         if((count & 3) != 0 && (count >> 2) < T4) { out[(size_t) (count >> 2) * 32] = w; }
     }
@@ -382,6 +394,13 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     __syncthreads();
     if(!live) { return; }
     const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * a.ntypes;
+    const int cap = a.cap;
+    // the epilogue's operands are requested now, so that they have arrived when the pair loop is through
+    double m = 1.0, vx = 0.0, vy = 0.0, vz = 0.0;
+    if(FUSE != 0 && !fixed) {
+        m = a.mass[i];
+        vx = a.vel[i]; vy = a.vel[cap + i]; vz = a.vel[2 * (size_t) cap + i];
+    }
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for(int k = 0; k < nn; k += 4) {
         const unsigned long long w = wnext;
@@ -420,7 +439,6 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
         }
     }
     // force[i] = force[i] + acc (sim/interaction.py:280-292); a pending reset_volatile_properties is folded in (ACCUMULATE == false)
-    const int cap = a.cap;
     if(ACCUMULATE) {
         if(!fixed) {
             fx = __dadd_rn(a.force[i], fx);
@@ -440,8 +458,6 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     }
     if(FUSE != 0) {
         if(!fixed) {
-            const double m = a.mass[i];
-            double vx = a.vel[i], vy = a.vel[cap + i], vz = a.vel[2 * (size_t) cap + i];
             if(FUSE & 1) {
                 vx = __dadd_rn(vx, __ddiv_rn(__dmul_rn(a.half_dt, fx), m));
                 vy = __dadd_rn(vy, __ddiv_rn(__dmul_rn(a.half_dt, fy), m));
@@ -557,7 +573,7 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
     ctx->tiles_n = -1;
     ctx->tile_split_valid = false;
     const int n = ctx->nlocal;
-    if(!ctx->tile_lists || ctx->half_lists || ctx->lanes != 1 || ctx->dem || ctx->stage_lists || ctx->pair_lists) { return 1; }
+    if(!ctx->tile_lists || ctx->half_lists || ctx->lanes != 1 || ctx->dem || ctx->stage_lists) { return 1; }
     if(ctx->ntypes > 8) { return 1; }
     if(n == 0) { return 1; }
     // INFINITE particles live in cell 0, outside every tile: leave such systems to the per-particle builder

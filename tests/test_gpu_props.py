@@ -179,7 +179,7 @@ def test_md_script_with_cell_lists_only_matches_the_reference_run_without_neighb
     zl = np.load(os.path.join(ROOT, "tests", "golden", "md_t1.npz"))
     psim = lj_script.build("gpu", 8, 60, 20, 1, cells_only=True)
     ctx = psim.generate()
-    assert psim.functions[1]["family"] in ("generic_pair", "lennard_jones") and len(psim.thermo_log) == 61
+    assert psim.functions[0]["family"] in ("generic_pair", "lennard_jones") and len(psim.thermo_log) == 61
     for (ts, t, p), t_ref in zip(psim.thermo_log, z["temperature"]):
         assert abs(t - t_ref) <= 1e-9 * t_ref, (ts, t, t_ref)
     assert abs(psim.thermo_log[15][1] - zl["temperature"][15]) > 1e-8 * zl["temperature"][15]
@@ -243,33 +243,6 @@ def test_dem_script_with_a_reneighbouring_interval_matches_the_reference(capsys)
     assert np.abs(ctx.real("linear_velocity")[o] - vref).max() <= 1e-9 * np.abs(vref).max()
     c = ctx.dem_download_contacts(n)
     assert np.array_equal(c["num_contacts"][o], z["end_300_num_contacts"][r]) and c["num_contacts"].sum() > 50
-
-
-def test_pair_lists_match_the_per_particle_lists(capsys):
-    """Option "pair_lists" (one union list per pair of consecutive cell-sorted particles, csrc/pair_lists.h; host-pinned against the
-    oracle in tests/test_pair_lists_host.py): the native md.py loop with and without it -- 45 iterations incl. three list builds,
-    fused integrators -- gives thermo to 1e-9, end positions to 1e-9 and, after one iteration, forces to 1e-12."""
-    from pairs_b200.backend import Context
-    nx = 10
-    L = nx * pow(4.0 / 0.8442, 1.0 / 3.0)
-    out = {}
-    for pairs_on in (0, 1):
-        res = []
-        for steps in (45, 1):
-            ctx = Context(0)
-            ctx.init_domain([0.0, L, 0.0, L, 0.0, L])
-            ctx.set_option("pair_lists", pairs_on)
-            ctx.copper_fcc_lattice(nx, nx, nx, 0.8442, 4)
-            ctx.adjust_thermo(1.44)
-            ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
-            th = ctx.md_run(0, steps, 0.005, 2.5, 2.8, 2.8, 20, 1)
-            res.append((th, by_id(ctx.ints("tag"), ctx.real("force")), by_id(ctx.ints("tag"), ctx.real("position")), ctx.counts()))
-        out[pairs_on] = res
-    (a45, a1), (b45, b1) = out[0], out[1]
-    assert a45[3] == b45[3] and len(a45[0]) == len(b45[0]) == 45
-    assert np.abs(a45[0][:, 1:] - b45[0][:, 1:]).max() <= 1e-9 * np.abs(a45[0][:, 1:]).max()
-    assert np.abs(a45[2] - b45[2]).max() <= 1e-9
-    assert rel_err_force(b1[1], a1[1]) <= 1e-12
 
 
 def test_property_store_through_the_c_abi(capsys):

@@ -54,8 +54,21 @@ def test_fma_arithmetic_stays_inside_the_parity_budget(eps, sig6):
     a = _run(nx, 1, 1, 100, eps, sig6)
     b = _run(nx, 1, 0, 100, eps, sig6)
     assert np.abs(a[1][:, 1:] - b[1][:, 1:]).max() <= 1e-9 * np.abs(b[1][:, 1:]).max()
-    fa, fb = _run(nx, 1, 1, 1, eps, sig6)[4], _run(nx, 1, 0, 1, eps, sig6)[4]
-    assert 0.0 < rel_err_force(fa, fb) <= 1e-12
+    # one evaluation on the SAME positions (a molten state: on the initial lattice every force is zero by symmetry)
+    from pairs_b200.backend import Context
+    fs = []
+    for fma in (1, 0):
+        ctx = Context(0)
+        ctx.init_domain(box(nx))
+        ctx.set_option("lj_fma", fma)
+        ctx.setup_cells(CUT + SKIN)
+        ctx.set_lj_params(4, eps or [1.0] * 16, sig6 or [1.0] * 16)
+        ctx.upload(b[2], b[3], np.ones(len(b[2])), by_id(b[0].ints("tag"), b[0].ints("type")))
+        _reneighbor_gpu(ctx)
+        ctx.reset_volatile()
+        ctx.lennard_jones(CUT)
+        fs.append(by_id(ctx.ints("tag"), ctx.real("force")))
+    assert np.abs(fs[1]).max() > 10.0 and 0.0 < rel_err_force(fs[0], fs[1]) <= 1e-12
     sim = make_oracle(nx, eps=eps, sig6=sig6)
     for ts in range(100):
         sim.step(ts)
