@@ -19,6 +19,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   dem_vtk_t1 dem_t1 for 60 steps with the example's psim.vtk_output(..., frequency) kept, writing every 30 iterations
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_rn3_t1 dem_t1 with psim.reneighbor_every(3): exchange / borders / cell lists every third iteration, synchronize in between
+  dem_stock_t1 examples/dem.py as shipped (0.8 x 0.015 x 0.2 box, VTK every 100 iterations), cut to 103 iterations
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_custom_t1  md_t1 with other kernel bodies (softened LJ using sqrt / select / symbols, integrators with drag) -> generic kernels
   md_props_t1   md_t1 with user-defined properties (a real entering the pair force, written by a setup() function; a second volatile
@@ -279,6 +280,9 @@ VARIANTS = {
     "dem_rn3_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 400, reneigh=3), [], False),
     "dem_vtk_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 60, vtk_every=30), [], False),
     "dem_bench": ("examples/dem.py", dem_variant((0.8, 0.8, 0.2), 100000, pcap=1300000), [], False),
+    # the STOCK example (0.8 x 0.015 x 0.2 box, 18720 spheres, VTK every 100 iterations), only cut to 100 iterations: golden for the
+    # test that runs the example file itself on this backend (tests/test_gpu_examples.py)
+    "dem_stock_t1": ("examples/dem.py", dem_variant((0.8, 0.015, 0.2), 102, vtk_every=100), [], False),
 }
 
 
@@ -382,6 +386,14 @@ def stage_data():
     os.makedirs(ddir, exist_ok=True)
     os.makedirs(os.path.join(OUT, "output"), exist_ok=True)
     shutil.copyfile(os.path.join(REF, "data", "planes.input"), os.path.join(ddir, "planes.input"))
+    # The reference's example scripts themselves, verbatim, for tests/test_gpu_examples.py ("examples/md.py, lj_onetype.py and dem.py run
+    # unchanged", BASELINE.json): the GPU box has no /root/reference, and nothing of the reference is copied into the repository --
+    # like every other artefact under oracle/_ref/ these copies are git-ignored build outputs that travel with the snapshot.
+    edir = os.path.join(OUT, "examples")
+    os.makedirs(edir, exist_ok=True)
+    for name in ("md.py", "dem.py", "lj_onetype.py"):
+        shutil.copyfile(os.path.join(REF, "examples", name), os.path.join(edir, name))
+    shutil.copyfile(os.path.join(REF, "data", "minimd_setup_4x4x4_onetype.input"), os.path.join(ddir, "minimd_setup_4x4x4_onetype.input"))
 
 
 def main(argv):

@@ -187,10 +187,11 @@ __device__ __forceinline__ int pb_tile_core_slot(const PbTileHdr *h, int t) {
     return h->core_begin[q] + (t - h->core_off[q]);
 }
 
-// warp r stages runs r, r + nwarps, ...: four index loads in flight, then two cp.async per particle (x,y | z [| w])
-template<bool WITH_IDX, bool WITH_W>
-__device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
-                                              double2 *sxy, double *sz, double *sw, int *sidx) {
+// warp r stages runs r, r + nwarps, ...: four index loads in flight, then two cp.async per particle (x,y | z).
+// META (list build): one byte per slot = particle type (3 bits) | 8 for a ghost
+template<bool META>
+__device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, int nlocal, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
+                                              double2 *sxy, double *sz, unsigned char *smeta) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for(int r = warp; r < PB_TILE_NRUN; r += nw) {
         const int len = h->run_len[r], begin = h->run_begin[r], slot0 = h->run_slot0[r];
@@ -198,6 +199,11 @@ __device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, const int *__r
             int idx[4];
 #pragma unroll
             for(int u = 0; u < 4; u++) { const int k = k0 + u * 32 + lane; idx[u] = (k < len) ? __ldg(cell_list + begin + k) : -1; }
+            double wv[4];
+            if(META) {
+#pragma unroll
+                for(int u = 0; u < 4; u++) { wv[u] = (idx[u] >= 0) ? __ldg(reinterpret_cast<const double *>(pos + idx[u]) + 3) : 0.0; }
+            }
 #pragma unroll
             for(int u = 0; u < 4; u++) {
                 const int s = slot0 + k0 + u * 32 + lane;
@@ -205,8 +211,7 @@ __device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, const int *__r
                     const double *src = reinterpret_cast<const double *>(pos + idx[u]);
                     pb_cp_async16(sxy + s, src);
                     pb_cp_async8(sz + s, src + 2);
-                    if(WITH_W) { pb_cp_async8(sw + s, src + 3); }
-                    if(WITH_IDX) { sidx[s] = idx[u]; }
+                    if(META) { smeta[s] = (unsigned char) ((pb_w_type(wv[u]) & 7) | ((idx[u] >= nlocal) ? 8 : 0)); }
                 }
             }
         }
@@ -214,17 +219,16 @@ __device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, const int *__r
     pb_cp_async_wait_all();
 }
 
-// shared memory: [hdr][xy: CAP*16][z: CAP*8][w: CAP*8 (typed build)][idx: CAP*4 (build)]
-__device__ __forceinline__ void pb_tile_smem(unsigned char *base, PbTileHdr *&h, double2 *&sxy, double *&sz, double *&sw, int *&sidx) {
+// shared memory: [hdr][xy: CAP*16][z: CAP*8][meta: CAP (build)]
+__device__ __forceinline__ void pb_tile_smem(unsigned char *base, PbTileHdr *&h, double2 *&sxy, double *&sz, unsigned char *&smeta) {
     h = reinterpret_cast<PbTileHdr *>(base);
     unsigned char *p = base + ((sizeof(PbTileHdr) + 15) / 16) * 16;
     sxy = reinterpret_cast<double2 *>(p);
     sz = reinterpret_cast<double *>(sxy + PB_TILE_CAP);
-    sw = sz + PB_TILE_CAP;
-    sidx = reinterpret_cast<int *>(sw + PB_TILE_CAP);
+    smeta = reinterpret_cast<unsigned char *>(sz + PB_TILE_CAP);
 }
 static size_t pb_tile_smem_bytes(bool build) {
-    return ((sizeof(PbTileHdr) + 15) / 16) * 16 + (size_t) PB_TILE_CAP * 24 + (build ? (size_t) PB_TILE_CAP * 12 : 0);
+    return ((sizeof(PbTileHdr) + 15) / 16) * 16 + (size_t) PB_TILE_CAP * 24 + (build ? (size_t) PB_TILE_CAP : 0);
 }
 
 // word q of list row r (4 entries per word): ((r / 32) * T4 + q) * 32 + r % 32
@@ -255,7 +259,6 @@ __device__ __forceinline__ bool pb_tile_window(const PbTileGeom &g, int c0, int 
     return true;
 }
 
-template<bool TYPES>
 __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int ncap, int T4, PbTileGeom g, double cutsq, const PbTile *__restrict__ tiles,
                                                             const double4 *__restrict__ pos, const int *__restrict__ flags,
                                                             const int *__restrict__ particle_cell, const int *__restrict__ cell_start,
@@ -263,21 +266,21 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int nca
                                                             unsigned long long *__restrict__ words, int *__restrict__ numneigh,
                                                             int *__restrict__ max_count, PbTileFaces faces, int *__restrict__ tile_flag) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
-    PbTileHdr *h; double2 *sxy; double *sz, *sw; int *sidx;
-    pb_tile_smem(pb_tile_shared, h, sxy, sz, sw, sidx);
+    PbTileHdr *h; double2 *sxy; double *sz; unsigned char *smeta;
+    pb_tile_smem(pb_tile_shared, h, sxy, sz, smeta);
     const PbTile tl = tiles[blockIdx.x];
     pb_tile_setup(h, g, tl, cell_start);
     const int cs = pb_tile_core_slot(h, threadIdx.x);
     const int i = (cs >= 0) ? __ldg(cell_list + cs) : nlocal;
     const bool live = i < nlocal;                                  // a local particle (ghosts sit in core cells at the faces, too)
-    const bool active = live && (flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (sim/neighbor_lists.py:31-33 via the FIXED filter)
+    const bool active = live && (flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (the reference's FIXED filter)
     if(live) { h->any_active = 1; }
     __syncthreads();
     if(!h->any_active) {                                           // a tile of ghosts only: nothing to build
         if(threadIdx.x == 0) { tile_flag[blockIdx.x] = 0; }
         return;
     }
-    pb_tile_stage<true, TYPES>(h, cell_list, pos, sxy, sz, sw, sidx);
+    pb_tile_stage<true>(h, nlocal, cell_list, pos, sxy, sz, smeta);
     __syncthreads();
     int count = 0, boundary = 0;
     if(active) {
@@ -289,46 +292,34 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int nca
         const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
         const int row = tl.row_base + threadIdx.x;
         unsigned long long *const out = words + pb_tile_word(row, T4, 0);
+        // the particle's own slot in the staging order (its column is staged run `tr0`): what `j != i` becomes
+        const int tr0 = (c0 - (tl.X0 - 1)) * 4 + (c1 - (tl.Y0 - 1));
+        const int s_self = h->run_slot0[tr0] + (cs - h->run_begin[tr0]);
         unsigned long long w = 0ull;
-        // the 9 candidate windows as shared-memory slot ranges; then ONE flat loop over all of them: the lanes of a warp run through
-        // windows of different lengths, a loop per window would leave half of them idle (ncu: 15.6 of 32 lanes active)
-        int wb[9], we[9];
-#pragma unroll
+        unsigned meta_or = 0u;
         for(int r = 0; r < 9; r++) {
-            int b = 0, e = 0;
-            if(pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) {
-                const int tr = (c0 + r / 3 - 1 - (tl.X0 - 1)) * 4 + (c1 + r % 3 - 1 - (tl.Y0 - 1));      // the staged run of this stencil row
-                const int shift = h->run_slot0[tr] - h->run_begin[tr];
-                b += shift;
-                e += shift;
-            }
-            wb[r] = b;
-            we[r] = e;
-        }
-        int r = 0, s = wb[0], end = we[0];
-        for(;;) {
-            while(s >= end && r < 8) { r++; s = wb[r]; end = we[r]; }
-            if(s >= end) { break; }
-            const double2 xy = sxy[s];
-            const double z = sz[s];
-            const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
-            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-            if(rsq < cutsq) {
-                const int j = sidx[s];
-                if(j != i) {
+            int b, e;
+            if(!pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
+            const int tr = tr0 + (r / 3 - 1) * 4 + (r % 3 - 1);        // the staged run of this stencil row
+            const int shift = h->run_slot0[tr] - h->run_begin[tr];
+            for(int s = b + shift; s < e + shift; s++) {
+                const double2 xy = sxy[s];
+                const double z = sz[s];
+                const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
+                const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if(rsq < cutsq && s != s_self) {
+                    const unsigned meta = smeta[s];
                     if(count < ncap) {
-                        unsigned entry = (unsigned) s;
-                        if(TYPES) { entry |= (unsigned) (pb_w_type(sw[s]) & 7) << 12; }
-                        w |= (unsigned long long) entry << (16 * (count & 3));
+                        w |= (unsigned long long) ((unsigned) s | ((meta & 7u) << 12)) << (16 * (count & 3));
                         if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
                     }
                     count++;
-                    boundary |= (j >= nlocal);
+                    meta_or |= meta;
                 }
             }
-            s++;
         }
         if((count & 3) != 0 && (count >> 2) < T4) { out[(size_t) (count >> 2) * 32] = w; }
+        boundary |= (int) (meta_or >> 3);
     }
     if(live) { numneigh[i] = count; }
     const int any_b = __syncthreads_or(boundary);
@@ -362,8 +353,8 @@ template<bool UNIFORM, bool ACCUMULATE, int FUSE, bool FMA>
 __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
     __shared__ double s_eps[64], s_sig6[64];
-    PbTileHdr *h; double2 *sxy; double *sz, *sw; int *sidx;
-    pb_tile_smem(pb_tile_shared, h, sxy, sz, sw, sidx);
+    PbTileHdr *h; double2 *sxy; double *sz; unsigned char *smeta;
+    pb_tile_smem(pb_tile_shared, h, sxy, sz, smeta);
     if(!UNIFORM) {
         for(int k = threadIdx.x; k < a.ntypes * a.ntypes; k += blockDim.x) { s_eps[k] = a.eps_t[k]; s_sig6[k] = a.sig6_t[k]; }
     }
@@ -390,7 +381,7 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     }
     __syncthreads();
     if(!h->any_active) { return; }                                 // a tile of ghosts only
-    pb_tile_stage<false, false>(h, a.cell_list, a.pos, sxy, sz, sw, sidx);
+    pb_tile_stage<false>(h, a.nlocal, a.cell_list, a.pos, sxy, sz, smeta);
     __syncthreads();
     if(!live) { return; }
     const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * a.ntypes;
@@ -598,11 +589,8 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
         PB_TRY(pb_tile_fit(ctx, &ctx->tiles_boundary, &c[3], (size_t) ctx->ntiles + 1));
         ctx->tile_flag_cap = std::min(std::min(c[0], c[1]), std::min(c[2], c[3]));
     }
-    // the particle type (3 bits) always rides in the entries: the Lennard-Jones tables may be set after the lists are built
-    const bool types = true;
     const size_t smem = pb_tile_smem_bytes(true);
-    PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     for(int attempt = 0; attempt < 8; attempt++) {
         const int T4 = (ctx->ncap + 3) / 4;
         const size_t bytes = sizeof(unsigned long long) * (size_t) (ctx->tile_rows / 32) * (size_t) T4 * 32;
@@ -614,15 +602,10 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
         }
         ctx->tile_T4 = T4;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
-        if(types) {
-            pb_k_tile_build<true><<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(n, ctx->ncap, T4, g, cutsq, ctx->tiles, ctx->pos, ctx->flags, ctx->particle_cell,
-                                                                                   ctx->cell_start, ctx->sub_start, ctx->cell_list, ctx->twords, ctx->numneigh,
-                                                                                   ctx->d_scalars, faces, ctx->tile_flag);
-        } else {
-            pb_k_tile_build<false><<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(n, ctx->ncap, T4, g, cutsq, ctx->tiles, ctx->pos, ctx->flags, ctx->particle_cell,
-                                                                                    ctx->cell_start, ctx->sub_start, ctx->cell_list, ctx->twords, ctx->numneigh,
-                                                                                    ctx->d_scalars, faces, ctx->tile_flag);
-        }
+        // (the particle type, 3 bits, always rides in the entries: the Lennard-Jones tables may be set after the lists are built)
+        pb_k_tile_build<<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(n, ctx->ncap, T4, g, cutsq, ctx->tiles, ctx->pos, ctx->flags, ctx->particle_cell,
+                                                                       ctx->cell_start, ctx->sub_start, ctx->cell_list, ctx->twords, ctx->numneigh,
+                                                                       ctx->d_scalars, faces, ctx->tile_flag);
         ctx->launches++;
         PB_CHECK(cudaGetLastError());
         const bool split = ctx->world > 1 && ctx->overlap_comm;

@@ -26,3 +26,16 @@ for ts in (0, 30):
         print(dst, os.path.getsize(dst), "bytes")
 for f in glob.glob(os.path.join(OUT, "dem_cpu_*.vtk")):
     os.remove(f)
+
+# the STOCK example (0.8 x 0.015 x 0.2 box, 18720 spheres + 2 planes), cut to 100 iterations: what runtime/vtk.hpp writes after
+# iteration 100 -> tests/golden/dem_stock_local_100.vtk.gz (tests/test_gpu_examples.py runs the example FILE on this backend)
+import gzip  # noqa: E402
+
+ref_worker.bench_many("dem_stock_t1", 1, 100, 1)        # iterations 0..101: the file of iteration 100 is written at its end
+src = os.path.join(OUT, "dem_cpu_local_100.vtk")
+dst = os.path.join(HERE, "dem_stock_local_100.vtk.gz")
+with open(src, "rb") as f, gzip.GzipFile(dst, "wb", mtime=0) as gz:
+    gz.write(f.read())
+print(dst, os.path.getsize(dst), "bytes")
+for f in glob.glob(os.path.join(OUT, "dem_cpu_*.vtk")):
+    os.remove(f)
