@@ -439,6 +439,225 @@ def run_ours(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Second workload (BASELINE.json configs[2] / configs[4]): examples/dem.py's system -- simple-cubic grid of spheres with 10 % size
+# scatter between two half-spaces, linear spring-dashpot contacts with tangential history, reneighbouring EVERY iteration -- on a
+# 0.8 m x 0.8 m x 0.2 m box per GPU (998,400 spheres; RegularXY partitioner: 1x2x1, 2x2x1, 2x4x1 ranks).
+DEM_GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+DEM_METRIC, DEM_UNIT = "dem_particle_steps_per_s", "particle-steps/s"
+
+
+def dem_config(world, settle):
+    gx, gy = DEM_GRIDS[world]
+    return {"workload": f"examples/dem.py scaled to a {0.8 * gx:g} x {0.8 * gy:g} x 0.2 m box ({998400 * world} spheres + 2 half-spaces, 998,400 per GPU), "
+                        f"linear spring-dashpot with tangential contact history, dt 5e-5, exchange + ghosts + cell lists every iteration; timed in the "
+                        f"SETTLED bed (after {settle} iterations), fp64" + (f"; weak scaling over {world} GPUs, RegularXY partitioner ({gx}x{gy}x1 ranks), "
+                        "particles migrate with their contact history" if world > 1 else ""),
+            "spheres_per_gpu": 998400, "n_gpus": world,
+            "l2_policy": "inputs larger than L2 (~1.6 KB of particle state + contact rows per sphere and iteration vs 126 MB L2)"}
+
+
+def dem_setup(ctx, backend, dist, rank, world, domain):
+    import math
+    from tests import dem_common as dc
+    ctx.init_domain([0.0, domain[0], 0.0, domain[1], 0.0, domain[2]], pbc=(1, 1, 0), partitioner=1, world_size=world, rank=rank)
+    if world > 1:
+        ids = [backend.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.nccl_init(ids[0])
+    ctx.dem_enable(dc.C)
+    ctx.dem_set_params(dc.DT, math.pi, dc.KAPPA, dc.LN_DRY, dc.COLLISION_TIME, dc.RHO_P, dc.RHO_F, dc.G, dc.NTYPES, dc.FS, dc.FD)
+    ctx.setup_cells(dc.CELL)
+
+
+def run_dem(args):
+    import math
+    from pairs_b200 import backend
+    from tests import dem_common as dc
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    gx, gy = DEM_GRIDS[world]
+    domain = (0.8 * gx, 0.8 * gy, 0.2)
+    ctx = backend.Context(local)
+    dem_setup(ctx, backend, dist, rank, world, domain)
+    assert tuple(ctx.decomposition()["nranks"]) == (gx, gy, 1)
+    g = ctx.dem_sc_grid(domain[0], domain[1], domain[2], dc.SPACING, dc.DIAMETER, dc.MIN_D, dc.MAX_D, dc.V0, dc.RHO_P, dc.NTYPES)
+    ns = len(g["uid"])
+    n = ns + 2
+    pos, vel, normal = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+    mass, radius = np.ones(n), np.zeros(n)
+    uid, typ, flags, shape = (np.zeros(n, np.int32) for _ in range(4))
+    pos[:ns], vel[:ns], mass[:ns], radius[:ns], uid[:ns], typ[:ns] = g["position"], g["linear_velocity"], g["mass"], g["radius"], g["uid"], g["type"]
+    for k, (u, p_, nrm) in enumerate([(100000000, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0)), (100000001, domain, (0.0, 0.0, -1.0))]):
+        uid[ns + k], pos[ns + k], normal[ns + k], flags[ns + k], shape[ns + k] = u, p_, nrm, 13, 1
+    ctx.reserve(int(1.25 * n) + 65536)
+    ctx.upload(pos, vel, mass, typ, flags, uid, shape)
+    ctx.dem_upload("radius", radius)
+    ctx.dem_upload("normal", normal)
+    ctx.dem_stage("update_mass_and_inertia")
+
+    def allred(x, op="sum"):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t[0])
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    n_global = int(allred(ns))
+    W, K, settle = args.warmup, args.steps, args.dem_settle
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # the falling phase (no contacts yet) is reported next to the headline window
+    ctx.dem_run(dc.CELL, 0, 20)
+    barrier()
+    ctx.stream_timer_start()
+    ctx.dem_run(dc.CELL, 20, 120)
+    falling_ms = allred(ctx.stream_timer_stop(), "max") / 100
+    ctx.dem_run(dc.CELL, 120, settle)             # settle into a bed with dense, sticking contacts
+    ctx.dem_run(dc.CELL, settle, settle + W)
+    barrier()
+    if rank == 0:
+        sampler.recording = True
+    ctx.timers_reset()
+    ctx.timers_enable(True)
+    launches0 = ctx.kernel_launches()
+    barrier()
+    ctx.stream_timer_start()
+    ctx.dem_run(dc.CELL, settle + W, settle + W + K)
+    ms = allred(ctx.stream_timer_stop(), "max")
+    barrier()
+    ctx.timers_enable(False)
+    launches = ctx.kernel_launches() - launches0
+    if rank == 0:
+        sampler.recording = False
+        sampler.stop()
+        sampler.join(timeout=3)
+    value = n_global * K / (ms * 1e-3)
+    stages = {k: {"ms": round(ctx.timer(k)[0], 4), "calls": ctx.timer(k)[1]} for k in
+              ("exchange", "borders", "build_cell_lists", "gravity", "linear_spring_dashpot", "euler", "reset_contact_history_usage_status",
+               "clear_unused_contact_history")}
+
+    # ---- roofline of the contact kernels (pb_k_dem_detect + pb_k_dem_force = the module linear_spring_dashpot), SURVEY.md 8(d):
+    #      950 B + 88 B per active contact + 4 B per particle in the 27 stencil cells, measured on THIS state ----
+    nl, ng = ctx.counts()
+    c = ctx.dem_download_contacts(nl)
+    cbar = float(c["num_contacts"].mean())
+    cs, _ = ctx.cell_lists()
+    dcells, ncells, _ = ctx.cells()
+    occ = np.diff(cs)[1:].reshape(tuple(int(x) for x in dcells)).astype(np.float64)       # cell 0 holds the INFINITE half-spaces
+    box = np.zeros_like(occ)
+    padded = np.pad(occ, 1)
+    for a in range(3):
+        for b in range(3):
+            for d in range(3):
+                box += padded[a:a + occ.shape[0], b:b + occ.shape[1], d:d + occ.shape[2]]
+    p27 = float((box * occ).sum() / max(occ.sum(), 1.0))          # mean over particles of the particles in their 27 cells
+    bytes_per_particle = 950.0 + 88.0 * cbar + 4.0 * p27
+    lsd_ms = ctx.timer("linear_spring_dashpot")[0] / K
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_particle * nl / 1e9 / (lsd_ms * 1e-3) if lsd_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "pb_k_dem_detect + pb_k_dem_force (module linear_spring_dashpot)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_particle": bytes_per_particle, "mean_contacts": cbar, "mean_particles_in_27_cells": p27,
+                "particles_per_step": nl, "ms_per_step_in_kernels": lsd_ms, "share_of_step": lsd_ms * K / ms,
+                "note": "SURVEY.md 8(d): 950 B own state / force / euler streams + 88 B per live contact + 4 B per particle of the 27 stencil cells"}
+
+    # ---- end to end with HOST buffers: the settled state goes back to the host, a fresh context gets it through the C-ABI (particle
+    #      arrays, DEM arrays, contact history), runs K iterations and returns positions and velocities ----
+    names = ("radius", "angular_velocity", "normal", "inv_inertia", "rotation_matrix", "rotation_quat")
+    host = {"position": ctx.real("position"), "linear_velocity": ctx.real("linear_velocity"), "mass": ctx.real("mass")}
+    host_i = {k: ctx.ints(k) for k in ("type", "flags", "uid", "shape")}
+    host_d = {k: ctx.dem_download(k, nl) for k in names}
+    ctx.close()
+    ctx2 = backend.Context(local)
+    dem_setup(ctx2, backend, dist, rank, world, domain)
+    ctx2.reserve(int(1.25 * nl) + 65536)
+    out_pos, out_vel = np.empty((int(1.25 * nl) + 65536, 3)), np.empty((int(1.25 * nl) + 65536, 3))
+    barrier()
+    t0 = time.perf_counter()
+    ctx2.upload(host["position"], host["linear_velocity"], host["mass"], host_i["type"], host_i["flags"], host_i["uid"], host_i["shape"])
+    for k in names:
+        ctx2.dem_upload(k, host_d[k])
+    ctx2.dem_upload_contacts(c["num_contacts"], c["contact_lists"], c["is_sticking"], c["tangential_spring_displacement"],
+                             c["impact_velocity_magnitude"])
+    ctx2.dem_run(dc.CELL, settle + W, settle + W + K)
+    ctx2.real_into("position", out_pos)
+    ctx2.real_into("linear_velocity", out_vel)
+    ctx2.sync()
+    e2e_s = allred(time.perf_counter() - t0, "max")
+    h2d = sum(a.nbytes for a in host.values()) + sum(a.nbytes for a in host_i.values()) + sum(a.nbytes for a in host_d.values()) + \
+        sum(c[k].nbytes for k in ("num_contacts", "contact_lists", "is_sticking", "tangential_spring_displacement", "impact_velocity_magnitude"))
+    n_after = ctx2.counts()[0]
+    e2e = {"value": n_global * K / e2e_s, "unit": DEM_UNIT, "h2d_bytes_per_step": allred(h2d) / K, "d2h_bytes_per_step": allred(2 * n_after * 24) / K,
+           "what": "pb_upload_particles + pb_dem_upload_real x 6 + pb_dem_upload_contacts (host arrays of the settled state) + pb_dem_run over K "
+                   "iterations + pb_download_real(position, linear_velocity)"}
+    assert int(allred(n_after)) == n_global + 2 * world, "particles lost or duplicated"
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = dem_cpu_sample(1)
+    if rank == 0:
+        line = {"metric": DEM_METRIC, "value": value, "unit": DEM_UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dem_config(world, settle), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "falling_phase": {"ms_per_step": falling_ms, "value": n_global / (falling_ms * 1e-3)},
+                "stages_ms": stages, "spheres_global": n_global, "nlocal_rank0": nl, "nghost_rank0": ng}
+        _JSON_OUT.write(json.dumps(line) + "\n")
+        _JSON_OUT.flush()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def dem_cpu_sample(replicas):
+    """The reference's generated serial C++ for examples/dem.py on the same 998,402-particle box (oracle/_ref variant dem_bench):
+    loop iterations 3..10, i.e. the falling phase -- the settled bed is 8000 iterations = hours of CPU time away."""
+    from oracle import ref, ref_worker
+    if not ref.available("dem_bench"):
+        return None
+    res = ref_worker.bench_many("dem_bench", 2, 8, replicas)
+    return {"value": sum(r["n"] * r["steps"] / r["seconds"] for r in res), "unit": DEM_UNIT, "cores": replicas, "kind": "reference",
+            "sample": f"998,402 particles, loop iterations 3..10 (falling phase, no contacts yet: the cheapest iterations of the run), serial target, "
+                      f"g++ -O3 -ffp-contract=off; {replicas} independent replica process(es), aggregate throughput",
+            "seconds": max(r["seconds"] for r in res)}
+
+
+def run_dem_reference(args):
+    if env_int("RANK", 0) != 0:
+        return 0
+    replicas = args.ref_replicas or max(1, min(os.cpu_count() or 1, 32))
+    try:
+        avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+        replicas = max(1, min(replicas, int(avail_gb // 3.0)))
+    except (ValueError, OSError):
+        pass
+    t0 = time.perf_counter()
+    cb = dem_cpu_sample(replicas)
+    if cb is None:
+        _JSON_OUT.write(json.dumps({"impl": "reference", "unavailable": "oracle/_ref variant dem_bench not built"}) + "\n")
+        return 0
+    line = {"impl": "reference", "metric": DEM_METRIC, "value": cb["value"], "unit": DEM_UNIT, "n_gpus": args.gpus, "steps": 8, "warmup": 2,
+            "ms_per_step": 1e3 * cb["seconds"] / 8, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": dem_config(args.gpus, args.dem_settle),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": DEM_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "wall_s": time.perf_counter() - t0}
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+    return 0
+
+
 def main():
     # stdout carries exactly ONE JSON line: everything else a library prints there (e.g. NCCL's version banner) goes to stderr
     global _JSON_OUT
@@ -454,13 +673,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dem", action="store_true", help="skip the secondary DEM workload (tools/bench_dem.py)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the N-rank parity check against the single-rank oracle")
+    ap.add_argument("--workload", default="lj", choices=["lj", "dem"], help="lj: BASELINE configs[1] / [3] (the headline); dem: configs[2] / [4]")
+    ap.add_argument("--dem-settle", type=int, default=8000, help="DEM: untimed iterations before the timed window (SURVEY.md 8d: 8000)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        return run_reference(args)
+        return run_dem_reference(args) if args.workload == "dem" else run_reference(args)
     try:
-        return run_ours(args)
+        return run_dem(args) if args.workload == "dem" else run_ours(args)
     except BaseException:
         # a failing rank must not leave its peers blocked in a collective: report and hard-exit so the launcher tears down
         import traceback

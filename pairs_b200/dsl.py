@@ -1044,6 +1044,14 @@ class Simulation:
         for n, w in cols:
             arrays[n] = data[:, k:k + w] if w > 1 else data[:, k]
             k += w
+        # every rank reads the whole file and keeps the rows inside its sub-box (runtime/read_from_file.hpp:106, isWithinSubdomain):
+        # without this every rank would start with the whole system
+        part = dict(arrays)
+        part["position"] = arrays[self.position_name]
+        part = self._keep_own(ctx, part)
+        if self.position_name != "position":
+            part[self.position_name] = part.pop("position")
+        arrays = {k: v for k, v in part.items() if k in arrays}
         pos = arrays[self.position_name]
         storage = self._device_storage()
         vel_name = next((n for n in arrays if storage.get(n) == "vel"), None)

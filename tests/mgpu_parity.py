@@ -14,8 +14,9 @@ different rank grid is a (slightly) different trajectory -- in the reference its
   A  reneighbour EVERY step (exchange + borders + cell lists + neighbour lists each iteration, no synchronize): the N-rank run is
      the single-rank run up to summation order.  30 iterations: thermo every step <= 1e-9, every particle's end position <= 1e-9
      (particles identified by their exact initial lattice position), migration included.
-  B  the step-0 state of the standard loop (reneighbour every 20): GLOBAL directed neighbour-pair set identical, forces per
-     particle <= 1e-12 (max-norm relative) against the single-rank oracle.
+  B  one reneighbouring + force evaluation on IDENTICAL inputs: the single-rank oracle's (molten) state after 25 iterations is
+     dealt out to the ranks by sub-box; GLOBAL directed neighbour-pair set identical, forces per particle <= 1e-12 (max-norm
+     relative) against the oracle's own modules run on the same state.
   C  45 iterations of the standard loop, overlap of halo refresh and interior forces on and off: bit-identical to each other, and
      per-rank counts / thermo <= 1e-9 / end positions against the oracle restatement holding the SAME N-rank decomposition in one
      process (the restatement's single-rank mode is pinned bit for bit to the reference's generated C++, tests/test_oracle_pin.py).
@@ -81,19 +82,44 @@ def check(backend, dist, rank, world, local, nx=12, steps_a=30, steps_c=45):
                  "decomp": ctx.decomposition()})
     ctx.close()
 
-    # ---- case B: step 0 of the standard loop ----
+    # ---- case B: the oracle's state after 25 iterations, dealt out by sub-box; one reneighbouring + one force evaluation ----
+    state = [None]
+    if rank == 0:
+        from oracle import port
+        n_glob_b = 4 * nx ** 3
+        sim_b = port.md_example(nx, world_size=1, reneigh_every=20, particle_capacity=4 * n_glob_b + 4096, send_capacity=2 * n_glob_b + 4096)
+        rb = sim_b.ranks[0]
+        rb.ints("uid", rb.nlocal, view=True)[:] = np.arange(rb.nlocal)
+        for ts in range(25):
+            sim_b.step(ts)
+        ob = np.argsort(rb.ints("uid"))
+        state[0] = {"pos": rb.real("position")[ob], "vel": rb.real("linear_velocity")[ob], "mass": rb.real("mass")[ob], "type": rb.ints("type")[ob]}
+    dist.broadcast_object_list(state, src=0)
+    sb = state[0]
     ctx = _new_ctx(backend, dist, rank, world, local, grid)
-    _setup(ctx, nx)
-    ctx.md_run(0, 1, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
+    sub = ctx.decomposition()["subdom"]
+    mine = np.ones(len(sb["pos"]), bool)
+    for d in range(3):
+        # 5 iterations after the last reneighbouring some particles sit just outside the global box (the wrap happens in
+        # exchange): they belong to the rank at that face, whose exchange then wraps / hands them over like any other leaver
+        lo = -np.inf if sub[2 * d] <= grid[2 * d] + 1e-9 * L else sub[2 * d]
+        hi = np.inf if sub[2 * d + 1] >= grid[2 * d + 1] - 1e-9 * L else sub[2 * d + 1]
+        mine &= (sb["pos"][:, d] >= lo) & (sb["pos"][:, d] < hi)
+    gid_mine = np.nonzero(mine)[0].astype(np.int32)
+    ctx.setup_cells(CUT + SKIN)
+    ctx.set_lj_params(NTYPES, [1.0] * (NTYPES * NTYPES), [1.0] * (NTYPES * NTYPES))
+    ctx.upload(sb["pos"][mine], sb["vel"][mine], sb["mass"][mine], sb["type"][mine], None, gid_mine)
+    ctx.exchange(); ctx.borders(); ctx.build_cell_lists(); ctx.build_neighbor_lists(CUT + SKIN)
+    ctx.reset_volatile(); ctx.lennard_jones(CUT)
     nl, ng = ctx.counts()
-    tags_all = ctx.ints("tag", with_ghosts=True)
+    uid_all = ctx.ints("uid", with_ghosts=True)
     nb = ctx.neighbors()
     nn = ctx.ints("numneighs")
     f = ctx.real("force")
     mask = np.arange(nb.shape[1])[None, :] < nn[:, None]
     ii = np.broadcast_to(np.arange(nl)[:, None], nb.shape)[mask]
     jj = nb[mask]
-    gb = gather({"tag_i": tags_all[ii], "tag_j": tags_all[jj], "tag": tags_all[:nl], "force": f, "counts": (nl, ng)})
+    gb = gather({"uid_i": uid_all[ii], "uid_j": uid_all[jj], "uid": uid_all[:nl], "force": f, "counts": (nl, ng), "dealt": int(mine.sum())})
     ctx.close()
 
     # ---- case C: 45 iterations, overlap on / off, against the N-rank restatement ----
@@ -141,6 +167,7 @@ def check(backend, dist, rank, world, local, nx=12, steps_a=30, steps_c=45):
         gid_of_tag0 = np.empty(n_glob, np.int64)       # global id (= oracle uid) of the k-th gathered initial particle
         gid_of_tag0[og] = oo
         ox0_sorted = ox0[oo]
+        tag2gid = lambda tg: gid_of_tag0[_by_tag(tg, gtag0)]      # noqa: E731  (the lattice set-up gives the same tags in every case)
 
         def oo_sorted_lookup(px):
             """global ids of particles given by their exact initial positions"""
@@ -174,28 +201,29 @@ def check(backend, dist, rank, world, local, nx=12, steps_a=30, steps_c=45):
                        "nlocal_per_rank": [g["counts"][0] for g in ga], "net_migration": moved}
         sim.close()
 
-        # -- single-rank oracle, case B
-        sim = port.md_example(nx, world_size=1, reneigh_every=20, particle_capacity=4 * n_glob + 4096, send_capacity=2 * n_glob + 4096)
-        r = sim.ranks[0]
-        r.ints("uid", r.nlocal, view=True)[:] = np.arange(r.nlocal)
-        sim.step(0)
-        onn, onl = r.neighbor_sets()
-        ouid = r.ints("uid", r.nlocal + r.nghost)
+        # -- single-rank oracle, case B: its own modules on the state the ranks were dealt
+        sim_b.exchange(); sim_b.borders()
+        sim_b.build_cell_lists(); sim_b.partition_cell_lists(); sim_b.build_neighbor_lists()
+        sim_b.reset_volatile(); sim_b.lennard_jones()
+        assert sum(g["dealt"] for g in gb) == n_glob, ("dealt", [g["dealt"] for g in gb], n_glob)
+        assert sum(g["counts"][0] for g in gb) == n_glob, ("owned after exchange", [g["counts"] for g in gb], n_glob)
+        onn, onl = rb.neighbor_sets()
+        ouid = rb.ints("uid", rb.nlocal + rb.nghost)
         omask = np.arange(onl.shape[1])[None, :] < onn[:, None]
-        oi = np.broadcast_to(np.arange(r.nlocal)[:, None], onl.shape)[omask]
+        oi = np.broadcast_to(np.arange(rb.nlocal)[:, None], onl.shape)[omask]
         opairs = np.sort(ouid[oi].astype(np.int64) * n_glob + ouid[onl[omask]])
-        tag2gid = lambda tg: gid_of_tag0[_by_tag(tg, gtag0)]      # noqa: E731  (same set-up, hence the same tags as in case A)
-        gpairs = np.sort(np.concatenate([tag2gid(g["tag_i"]) * n_glob + tag2gid(g["tag_j"]) for g in gb]))
+        gpairs = np.sort(np.concatenate([g["uid_i"].astype(np.int64) * n_glob + g["uid_j"] for g in gb]))
         assert np.array_equal(gpairs, opairs), f"global neighbour-pair set differs ({len(gpairs)} vs {len(opairs)} pairs)"
         of = np.empty((n_glob, 3))
-        of[r.ints("uid")] = r.real("force")
+        of[rb.ints("uid")] = rb.real("force")
         gf = np.concatenate([g["force"] for g in gb])
-        ggid = tag2gid(np.concatenate([g["tag"] for g in gb]))
-        worst_f = float(np.abs(gf - of[ggid]).max() / np.abs(of).max())
-        assert worst_f <= 1e-12, worst_f
-        report["B"] = {"directed_pairs": int(len(opairs)), "pair_set_identical": True, "force_rel": worst_f,
-                       "nghost_per_rank": [g["counts"][1] for g in gb]}
-        sim.close()
+        guid = np.concatenate([g["uid"] for g in gb])
+        assert np.array_equal(np.sort(guid), np.arange(n_glob))
+        worst_f = float(np.abs(gf - of[guid]).max() / np.abs(of).max())
+        assert np.abs(of).max() > 10.0 and worst_f <= 1e-12, worst_f
+        report["B"] = {"state": "single-rank oracle after 25 iterations", "directed_pairs": int(len(opairs)), "pair_set_identical": True,
+                       "force_rel": worst_f, "nghost_per_rank": [g["counts"][1] for g in gb]}
+        sim_b.close()
 
         # -- N-rank restatement, case C
         assert all(g["same"] for g in gc), "overlap on / off are not bit-identical"

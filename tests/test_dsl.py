@@ -183,6 +183,42 @@ def test_multi_rank_read_particle_data_keeps_own_rows_and_global_bodies():
     assert dsl.Simulation._keep_own(OneRank(), part) is part
 
 
+def test_md_read_particle_data_uploads_only_the_rows_of_the_own_sub_box(tmp_path):
+    """The MD path of read_particle_data / from_file (examples/lj_onetype.py) with two ranks: each rank uploads the rows inside its
+    sub-box only (runtime/read_from_file.hpp:106) -- without the filter every rank would start with the whole system and the
+    particles would be duplicated `world` times."""
+    import pairs
+    rows = np.array([[1.0, 0.2, 0.3, 0.4, 0.01, 0.02, 0.03], [1.0, 3.1, 0.3, 0.4, 0.0, 0.0, 0.0], [1.0, 6.0, 5.0, 1.0, 0.1, 0.0, 0.0],
+                     [1.0, 6.6, 6.6, 6.6, 0.0, 0.0, 0.2]])
+    path = tmp_path / "minimd_setup_4x4x4_test.input"
+    np.savetxt(path, rows, delimiter=",")
+    psim = pairs.simulation("lj", debug=True, timesteps=1)
+    psim.add_real_property('mass', 1.0)
+    psim.add_position('position')
+    psim.add_vector_property('velocity')
+    psim.add_vector_property('force', vol=True)
+    psim.from_file(str(path), ['mass', 'position', 'velocity'])
+    L = 4 * pow(4.0 / 0.8442, 1.0 / 3.0)
+    uploads = []
+
+    class FakeCtx:
+        def __init__(self, lo, hi):
+            self.lo, self.hi = lo, hi
+
+        def decomposition(self):
+            return {"nranks": np.array([2, 1, 1]), "subdom": np.array([self.lo, self.hi, 0.0, L, 0.0, L])}
+
+        def upload(self, pos, vel, mass, *rest):
+            uploads.append((np.array(pos), np.array(vel), np.array(mass)))
+
+    kind, args = psim.setups[-1]
+    assert kind == "read_particle_data"
+    n0 = psim._read_particle_data(FakeCtx(0.0, L / 2), *args)
+    n1 = psim._read_particle_data(FakeCtx(L / 2, L), *args)
+    assert (n0, n1) == (2, 2) and np.array_equal(uploads[0][0][:, 0], [0.2, 3.1]) and np.array_equal(uploads[1][0][:, 0], [6.0, 6.6])
+    assert np.array_equal(uploads[0][1], rows[:2, 4:7]) and np.array_equal(uploads[1][2], [1.0, 1.0])
+
+
 def test_further_properties_become_user_defined_storage():
     """Properties beyond the MD set get rows in the user-property block (csrc/props.cu), numbered in declaration order; the MD
     slots go to the canonical names when they are declared, else to the first property of the matching type / volatility."""

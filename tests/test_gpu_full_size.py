@@ -92,3 +92,75 @@ def test_config_c2_four_million_atoms_invariants():
     th_b = ctx.md_run(21, 60, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 1)
     assert np.array_equal(th_a, th_b)
     assert np.array_equal(end_a[0], ctx.ints("tag")) and np.array_equal(end_a[1], ctx.real("position"))
+
+
+def _mix(tag, pos):
+    """order-independent identity key of a particle image: its tag and the exact bits of its coordinates"""
+    k = tag.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    for d in range(3):
+        b = (np.ascontiguousarray(pos[:, d]) + 0.0).view(np.uint64)
+        k = (k ^ (b + np.uint64(0x7F4A7C159E3779B9) + (k << np.uint64(6)) + (k >> np.uint64(2)))) * np.uint64(0xBF58476D1CE4E5B9)
+    return k
+
+
+def _row_hashes(keys, nn, nb, chunk=250000):
+    """per particle: the sum (mod 2^64) of the keys of its neighbours -- equal for equal neighbour SETS, whatever their order"""
+    out = np.zeros(len(nn), np.uint64)
+    cols = np.arange(nb.shape[1])[None, :]
+    for a in range(0, len(nn), chunk):
+        b = min(a + chunk, len(nn))
+        m = cols < nn[a:b, None]
+        k = keys[np.where(m, nb[a:b], 0)]
+        k[~m] = 0
+        out[a:b] = k.sum(axis=1, dtype=np.uint64)
+    return out
+
+
+def test_config_c2_four_million_atoms_against_the_oracle():
+    """C2 at size, iterations 0 and 1, against the oracle restatement (bit-identical to the reference's generated C++ on the small
+    cases, tests/test_oracle_pin.py): cell index of every particle, ghost set, the neighbour SET of every particle (a 64-bit
+    order-independent hash over (partner tag, exact partner coordinates), 3.1 x 10^8 entries), forces of both iterations to 1e-12
+    (max-norm relative), positions and velocities after iteration 1."""
+    from oracle import port
+    from tests.util import by_id
+    nx = 100
+    ctx, n = make_gpu(nx)
+    sim = port.md_example(nx, reneigh_every=20, particle_capacity=4700000, send_capacity=600000)
+    r = sim.ranks[0]
+    r.ints("uid", r.nlocal, view=True)[:] = np.arange(r.nlocal)
+    assert n == r.nlocal == 4000000
+    # iteration 0, module by module on the GPU
+    ctx.exchange(); ctx.borders(); ctx.build_cell_lists(); ctx.build_neighbor_lists(CUT + SKIN)
+    ctx.reset_volatile(); ctx.lennard_jones(CUT)
+    sim.step(0)
+    nl, ng = ctx.counts()
+    assert (nl, ng) == (r.nlocal, r.nghost)
+    tag_all = ctx.ints("tag", with_ghosts=True)
+    order = np.argsort(tag_all[:nl])
+    assert np.array_equal(tag_all[:nl][order], np.arange(nl))
+    # cells (locals by tag; ghosts as a multiset of (tag, exact coordinates, cell))
+    pc_g, pc_o = ctx.ints("particle_cell", with_ghosts=True), r.ints("particle_cell", nl + ng)
+    uid_o = r.ints("uid", nl + ng)
+    assert np.array_equal(pc_g[:nl][order], pc_o[:nl][np.argsort(uid_o[:nl])])
+    pos_g, pos_o = ctx.real("position", with_ghosts=True), r.real("position", nl + ng)
+    key_g, key_o = _mix(tag_all, pos_g), _mix(uid_o, pos_o)
+    gg = np.sort(key_g[nl:] ^ pc_g[nl:].astype(np.uint64))
+    go = np.sort(key_o[nl:] ^ pc_o[nl:].astype(np.uint64))
+    assert np.array_equal(gg, go)                                    # the same ghost images in the same cells
+    # neighbour sets
+    nn_g, nb_g = ctx.ints("numneighs"), ctx.neighbors()
+    nn_o, nb_o = r.neighbor_sets()
+    assert np.array_equal(nn_g[order], nn_o[np.argsort(uid_o[:nl])]) and 70 < nn_g.mean() < 80
+    h_g = _row_hashes(key_g, nn_g, nb_g)
+    del nb_g
+    h_o = _row_hashes(key_o, nn_o, nb_o)
+    assert np.array_equal(h_g[order], h_o[np.argsort(uid_o[:nl])])
+    # forces of iteration 0 (the perfect lattice: every component cancels to ~1e-14) and, after one full step, of iteration 1
+    f_o = by_id(uid_o[:nl], r.real("force"))
+    assert np.abs(ctx.real("force")[order] - f_o).max() <= 1e-12
+    ctx.md_run(1, 2, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)
+    sim.step(1)
+    o2, u2 = np.argsort(ctx.ints("tag")), np.argsort(r.ints("uid", nl))
+    for name, tol in (("position", 1e-13), ("linear_velocity", 1e-12), ("force", 1e-12)):
+        a, b = ctx.real(name)[o2], r.real(name)[u2]
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300) or np.abs(a - b).max() <= 1e-12, name

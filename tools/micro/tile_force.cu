@@ -367,6 +367,62 @@ __global__ void __launch_bounds__(M) k_force_tile(int n, int cap, Geom g, double
     force[2 * (size_t) n + i] = __dadd_rn(0.0, fz);
 }
 
+
+// ---- conflict-aware order of a list ---------------------------------------------------------------------------------------------
+// In iteration k the 16 lanes of a half-warp read 16 staged particles; two DIFFERENT slots collide in shared memory when they
+// agree modulo 16 (8-byte z entries: 16 bank pairs; the 16-byte xy entries of a quarter-warp: modulo 8).  Every list is a set, its
+// order is free: lane l puts at position k an entry whose slot is (k + l) mod 16 whenever it still has one -- then the lanes of a
+// half-warp ask for 16 different residues in every iteration.  Entries whose residue class is exhausted fill the remaining holes.
+template<int M>
+__global__ void __launch_bounds__(M) k_reorder_tile(int n, Geom g, const Tile *__restrict__ tiles, const int *__restrict__ cell_start,
+                                                    const int *__restrict__ cell_list, const int *__restrict__ numneigh,
+                                                    const unsigned long long *__restrict__ win, unsigned long long *__restrict__ wout) {
+    __shared__ TileHdr hdr;
+    const Tile tl = tiles[blockIdx.x];
+    tile_setup(&hdr, g, tl, cell_start);
+    const int cs = tile_core_slot(&hdr, threadIdx.x);
+    const int i = (cs >= 0) ? cell_list[cs] : n;
+    if(i >= n) { return; }
+    const int row = tl.row_base + threadIdx.x;
+    const int nn = min(numneigh[i], NCAP);
+    const size_t base = (size_t) (row >> 5) * (NCAP / 4) * 32 + (row & 31);
+    unsigned short e[NCAP], sorted[NCAP], out[NCAP];
+    int head[16], tail[16];
+    for(int r = 0; r < 16; r++) { head[r] = 0; }
+    for(int q = 0; q * 4 < nn; q++) {
+        const unsigned long long w = win[base + (size_t) q * 32];
+        for(int u = 0; u < 4 && q * 4 + u < nn; u++) {
+            const unsigned short v = (unsigned short) ((w >> (16 * u)) & 0xffffull);
+            e[q * 4 + u] = v;
+            head[v & 15]++;
+        }
+    }
+    int acc = 0;
+    for(int r = 0; r < 16; r++) { const int c = head[r]; head[r] = acc; acc += c; tail[r] = acc; }
+    {
+        int pos[16];
+        for(int r = 0; r < 16; r++) { pos[r] = head[r]; }
+        for(int k = 0; k < nn; k++) { sorted[pos[e[k] & 15]++] = e[k]; }
+    }
+    const int rot = row & 15;
+    for(int k = 0; k < nn; k++) {
+        const int r = (k + rot) & 15;
+        out[k] = (head[r] < tail[r]) ? sorted[head[r]++] : (unsigned short) 0xffff;
+    }
+    int hk = 0;
+    for(int r = 0; r < 16; r++) {
+        while(head[r] < tail[r]) {
+            while(out[hk] != 0xffff) { hk++; }
+            out[hk] = sorted[head[r]++];
+        }
+    }
+    for(int q = 0; q * 4 < nn; q++) {
+        unsigned long long w = 0ull;
+        for(int u = 0; u < 4 && q * 4 + u < nn; u++) { w |= (unsigned long long) out[q * 4 + u] << (16 * u); }
+        wout[base + (size_t) q * 32] = w;
+    }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------------------
 static unsigned long long lcg_state = 88172645463325252ull;
 static double urand() {
@@ -572,6 +628,19 @@ int main(int argc, char **argv) {
             CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
             t = time_ms(10, [&] { k_force_tile<M, 2, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w, d_nn2, d_f1); });
             report("force_tile_prefetch_fma2", t, false);
+            // the same lists in the conflict-aware order
+            unsigned long long *d_w2;
+            CK(cudaMalloc(&d_w2, 8 * (size_t) (rows / 32) * (NCAP / 4) * 32));
+            CK(cudaMemset(d_w2, 0, 8 * (size_t) (rows / 32) * (NCAP / 4) * 32));
+            float tr = time_ms(3, [&] { k_reorder_tile<M><<<ntiles, M>>>(n, g, d_tiles, d_cs, d_cl, d_nn2, d_w, d_w2); });
+            printf("{\"kernel\": \"reorder_tile\", \"M\": %d, \"ms\": %.4f}\n", M, tr);
+            CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
+            t = time_ms(10, [&] { k_force_tile<M, 0, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w2, d_nn2, d_f1); });
+            report("force_tile_prefetch_reordered", t, false);
+            CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
+            t = time_ms(10, [&] { k_force_tile<M, 2, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w2, d_nn2, d_f1); });
+            report("force_tile_prefetch_fma2_reordered", t, false);
+            CK(cudaFree(d_w2));
         }
         CK(cudaFree(d_tiles)); CK(cudaFree(d_w));
     };
@@ -581,5 +650,9 @@ int main(int argc, char **argv) {
     if(only < 0 || only == 2) { tile_variant(std::integral_constant<int, 128>(), 1280); }
     if(only < 0 || only == 3) { tile_variant(std::integral_constant<int, 192>(), 1792); }
     if(only < 0 || only == 4) { tile_variant(std::integral_constant<int, 384>(), 3072); }
+    if(only < 0 || only == 5) { tile_variant(std::integral_constant<int, 320>(), 2560); }
+    if(only < 0 || only == 6) { tile_variant(std::integral_constant<int, 448>(), 3584); }
+    if(only < 0 || only == 7) { tile_variant(std::integral_constant<int, 512>(), 4096); }
+    if(only < 0 || only == 8) { tile_variant(std::integral_constant<int, 384>(), 2816); }
     return 0;
 }
