@@ -66,11 +66,17 @@ PB_MD_HD double pb_lj_fpair(double rsq, double sig6, double eps) {
 }
 
 // ---- production arithmetic (option "lj_fma", the default of the force kernels) ---------------------------------------------------
-// The same expressions with fused multiply-adds where a product feeds a sum, and the reciprocal as MUFU.RCP64H + two Newton steps
-// instead of the IEEE division: 24 fp64 instructions per pair instead of 33 (the force kernel is co-limited by the fp64 pipe and
-// the shared-memory gathers).  Every result is within a few ulp of the reference's expression: measured
-// 1.5e-15 of the largest force component on 4 M atoms (tools/micro/tile_force.cu), against the 1e-12 of the parity contract.
-// The bit-exact expressions above stay the ones the parity tests pin (option "lj_fma" = 0).
+// The force kernel is co-limited by the fp64 pipe, the shared-memory gathers and the issue slots, so the
+// production variant spends as few fp64 instructions per pair as the 1e-12 parity budget allows -- 17 instead of the 33 of the
+// reference's expression tree:
+//   rsq = fma(dz, dz, fma(dy, dy, dx * dx))                                   3 + 3 (the differences)
+//   cutoff test on the BIT PATTERNS (rsq >= +0: doubles order like their bits)  0   (two integer compares on the ALU, no DSETP)
+//   sr2 = 1 / rsq: MUFU.RCP64H (~2^-20) + one CUBIC step y (1 + e + e^2)        3   (error e^3 ~ 2^-60; not correctly rounded)
+//   a = sr2^3;  f = sr2 * a * (c1 * a - c2),  c1 = 48 eps sigma^12, c2 = 24 eps sigma^6    5
+//   force += delta * f                                                        3 fmas
+// Every result is within a few ulp of the reference's expression: measured <= 2e-15 of the largest force component on 4 M atoms
+// (tools/micro/tile_force.cu), against the 1e-12 of the parity contract.  The bit-exact expressions above stay the ones the
+// parity tests pin (option "lj_fma" = 0).
 PB_MD_HD double pb_fma(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
     return __fma_rn(a, b, c);
@@ -79,14 +85,13 @@ PB_MD_HD double pb_fma(double a, double b, double c) {
 #endif
 }
 
-PB_MD_HD double pb_rcp_newton(double x) {
+PB_MD_HD double pb_rcp_cubic(double x) {
 #if defined(__CUDA_ARCH__)
     double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // ~20 bits
-    double e = __fma_rn(-x, y, 1.0);
-    y = __fma_rn(y, e, y);                                       // ~40 bits
-    e = __fma_rn(-x, y, 1.0);
-    return __fma_rn(y, e, y);                                    // full precision, not correctly rounded (<= 1 ulp)
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));      // MUFU.RCP64H: ~20 bits
+    const double e = __fma_rn(-x, y, 1.0);
+    const double t = __fma_rn(e, e, e);
+    return __fma_rn(y, t, y);
 #else
     return 1.0 / x;
 #endif
@@ -99,8 +104,18 @@ PB_MD_HD double pb_pair_rsq_fma(double xi, double yi, double zi, double xj, doub
     return pb_fma(*dz, *dz, pb_fma(*dy, *dy, PB_MUL(*dx, *dx)));
 }
 
-PB_MD_HD double pb_lj_fpair_fma(double rsq, double sig6, double eps) {
-    const double sr2 = pb_rcp_newton(rsq);
-    const double sr6 = PB_MUL(PB_MUL(PB_MUL(sr2, sr2), sr2), sig6);
-    return PB_MUL(PB_MUL(PB_MUL(PB_MUL(48.0, sr6), PB_SUB(sr6, 0.5)), sr2), eps);
+// rsq < cutsq for rsq >= +0 (NaN never: rsq is a sum of squares of finite numbers)
+PB_MD_HD bool pb_less_bits(double rsq, double cutsq) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(rsq) < __double_as_longlong(cutsq);
+#else
+    return rsq < cutsq;
+#endif
+}
+
+// c1 = 48 eps sigma6^2, c2 = 24 eps sigma6 (host side: pb_lj_fast_coeff)
+PB_MD_HD double pb_lj_fpair_fast(double rsq, double c1, double c2) {
+    const double sr2 = pb_rcp_cubic(rsq);
+    const double a = PB_MUL(PB_MUL(sr2, sr2), sr2);
+    return PB_MUL(PB_MUL(sr2, a), pb_fma(c1, a, -c2));
 }

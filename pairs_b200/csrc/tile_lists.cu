@@ -34,6 +34,10 @@
 #include "md_math.h"
 
 static const int PB_TILE_NRUN = 16;
+// The last staging slot holds no particle but a point far outside every cutoff: list rows are padded to whole words (four
+// entries) with it, so the force kernel needs no "is this entry valid" test -- a padding entry simply fails the cutoff test.
+static const int PB_TILE_DUMMY = PB_TILE_CAP - 1, PB_TILE_STAGED = PB_TILE_CAP - 1;
+static const double PB_TILE_FAR = 1e150;      // (x - 1e150)^2 * 3 is finite and > any cutoff^2
 
 struct PbTileGeom {
     double lo[3];               // origin of the cell grid (subdom_min - spacing)
@@ -97,12 +101,12 @@ __global__ void __launch_bounds__(128) pb_k_tile_plan(int nsc, int nsy, int dim2
         const int za = z;
         int core = lc[z];
         int staged = ((z > 0) ? lh[z - 1] : 0) + lh[z] + ((z + 1 < dim2) ? lh[z + 1] : 0);
-        if(core > PB_TILE_M || staged > PB_TILE_CAP) { atomicExch(overflow, 1); }
+        if(core > PB_TILE_M || staged > PB_TILE_STAGED) { atomicExch(overflow, 1); }
         int zb = z;
         while(zb + 1 < dim2) {
             const int c2 = core + lc[zb + 1];
             const int s2 = staged + ((zb + 2 < dim2) ? lh[zb + 2] : 0);
-            if(c2 > PB_TILE_M || s2 > PB_TILE_CAP) { break; }
+            if(c2 > PB_TILE_M || s2 > PB_TILE_STAGED) { break; }
             core = c2;
             staged = s2;
             zb++;
@@ -207,7 +211,7 @@ __device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, int nlocal, co
 #pragma unroll
             for(int u = 0; u < 4; u++) {
                 const int s = slot0 + k0 + u * 32 + lane;
-                if(idx[u] >= 0 && s < PB_TILE_CAP) {
+                if(idx[u] >= 0 && s < PB_TILE_STAGED) {
                     const double *src = reinterpret_cast<const double *>(pos + idx[u]);
                     pb_cp_async16(sxy + s, src);
                     pb_cp_async8(sz + s, src + 2);
@@ -318,7 +322,10 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int nca
                 }
             }
         }
-        if((count & 3) != 0 && (count >> 2) < T4) { out[(size_t) (count >> 2) * 32] = w; }
+        if((count & 3) != 0 && (count >> 2) < T4) {      // the last word is padded with the dummy slot
+            w |= 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY << (16 * (count & 3));
+            out[(size_t) (count >> 2) * 32] = w;
+        }
         boundary |= (int) (meta_or >> 3);
     }
     if(live) { numneigh[i] = count; }
@@ -333,7 +340,7 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int nca
 // ---- force ------------------------------------------------------------------------------------------------------------------
 struct PbTileLjArgs {
     int nlocal, ncap, T4, cap, ntypes, nsel;
-    double cutsq, eps_u, sig6_u, dt, half_dt;
+    double cutsq, eps_u, sig6_u, c1_u, c2_u, dt, half_dt;      // c1 = 48 eps sigma6^2, c2 = 24 eps sigma6 (md_math.h pb_lj_fpair_fast)
     const double *eps_t, *sig6_t;
     PbTileGeom g;
     const PbTile *tiles;
@@ -348,16 +355,26 @@ struct PbTileLjArgs {
 };
 
 // FUSE / ACCUMULATE: the epilogue of the per-particle kernel (md_kernels.cu pb_k_lennard_jones), operation for operation.
-// FMA: pb_pair_rsq_fma / pb_lj_fpair_fma and fused accumulation (md_math.h) instead of the reference's expression tree.
+// FMA: the production arithmetic of md_math.h (pb_pair_rsq_fma / pb_lj_fpair_fast, fused accumulation) instead of the reference's
+// expression tree.  Either way the pair loop is BRANCH-FREE: the term of a pair outside the cutoff (or of a padding entry) is
+// selected to +0 and added like any other -- x + (+-0) = x bit for bit (x = -0 cannot occur: the sums start at +0 and no term
+// rounds to zero), so the results are those of the branching loop, but the four pair chains of an iteration are straight-line
+// code that the scheduler interleaves (with one divergent region per pair the dependent fp64 chains ran one after the other:
+// ncu stall "wait" 3.5 of 11.9 cycles per instruction, 50 instructions per pair; now 35).
 template<bool UNIFORM, bool ACCUMULATE, int FUSE, bool FMA>
 __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
-    __shared__ double s_eps[64], s_sig6[64];
+    __shared__ double s_c1[64], s_c2[64];      // per type pair: (48 eps sigma6^2, 24 eps sigma6) with FMA, (sigma6, eps) without
     PbTileHdr *h; double2 *sxy; double *sz; unsigned char *smeta;
     pb_tile_smem(pb_tile_shared, h, sxy, sz, smeta);
     if(!UNIFORM) {
-        for(int k = threadIdx.x; k < a.ntypes * a.ntypes; k += blockDim.x) { s_eps[k] = a.eps_t[k]; s_sig6[k] = a.sig6_t[k]; }
+        for(int k = threadIdx.x; k < a.ntypes * a.ntypes; k += blockDim.x) {
+            const double e = a.eps_t[k], s6 = a.sig6_t[k];
+            s_c1[k] = FMA ? 48.0 * e * s6 * s6 : s6;
+            s_c2[k] = FMA ? 24.0 * e * s6 : e;
+        }
     }
+    if(threadIdx.x == 0) { sxy[PB_TILE_DUMMY] = make_double2(PB_TILE_FAR, PB_TILE_FAR); sz[PB_TILE_DUMMY] = PB_TILE_FAR; }
     const int tile_id = (a.sel != nullptr) ? __ldg(a.sel + blockIdx.x) : (int) blockIdx.x;
     const PbTile tl = a.tiles[tile_id];
     pb_tile_setup(h, a.g, tl, a.cell_start);
@@ -370,13 +387,17 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     int nn = 0;
     const int row = tl.row_base + threadIdx.x;
     const unsigned long long *wp = a.words + pb_tile_word(row, a.T4, 0);
-    unsigned long long wnext = 0ull;
+    constexpr int U = FMA ? 8 : 4, W = U / 4;      // pairs per iteration (the exact expression tree needs more registers per pair)
+    unsigned long long wnext[W];
+#pragma unroll
+    for(int q = 0; q < W; q++) { wnext[q] = 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY; }
     if(live) {
         pi = pb_ld_pos(a.pos + i);
         h->any_active = 1;
         if(!fixed) {
             nn = min(a.numneigh[i], a.ncap);
-            if(nn > 0) { wnext = __ldg(wp); }
+#pragma unroll
+            for(int q = 0; q < W; q++) { if(q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) q * 32); } }
         }
     }
     __syncthreads();
@@ -392,40 +413,46 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
         m = a.mass[i];
         vx = a.vel[i]; vy = a.vel[cap + i]; vz = a.vel[2 * (size_t) cap + i];
     }
+    const double k1 = FMA ? a.c1_u : a.sig6_u, k2 = FMA ? a.c2_u : a.eps_u;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    for(int k = 0; k < nn; k += 4) {
-        const unsigned long long w = wnext;
-        if(k + 4 < nn) { wnext = __ldg(wp + (size_t) ((k >> 2) + 1) * 32); }
-        double xj[4], yj[4], zj[4];
-        int tj[4];
+    for(int k = 0; k < nn; k += U) {
+        unsigned long long w[W];
 #pragma unroll
-        for(int u = 0; u < 4; u++) {
-            const unsigned e16 = (unsigned) ((w >> (16 * u)) & 0xffffull);
-            const int s = (k + u < nn) ? (int) (e16 & 0xfffu) : 0;
+        for(int q = 0; q < W; q++) {      // a word past the end of the row is replaced by padding entries
+            w[q] = wnext[q];
+            wnext[q] = 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY;
+            if(k + U + q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) (((k + U) >> 2) + q) * 32); }
+        }
+        double xj[U], yj[U], zj[U];
+        int tj[U];
+#pragma unroll
+        for(int u = 0; u < U; u++) {
+            const unsigned e16 = (unsigned) (w[u >> 2] >> (16 * (u & 3))) & 0xffffu;
+            const int s = (int) (e16 & 0xfffu);
             tj[u] = (int) (e16 >> 12);
             const double2 xy = sxy[s];
             xj[u] = xy.x; yj[u] = xy.y;
             zj[u] = sz[s];
         }
 #pragma unroll
-        for(int u = 0; u < 4; u++) {
+        for(int u = 0; u < U; u++) {
             double dx, dy, dz;
-            const double rsq = FMA ? pb_pair_rsq_fma(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], &dx, &dy, &dz)
-                                   : pb_pair_rsq(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], &dx, &dy, &dz);
-            if(k + u < nn && rsq < a.cutsq) {
-                const double sig6 = UNIFORM ? a.sig6_u : s_sig6[ti + tj[u]];
-                const double eps = UNIFORM ? a.eps_u : s_eps[ti + tj[u]];
-                if(FMA) {
-                    const double f = pb_lj_fpair_fma(rsq, sig6, eps);
-                    fx = __fma_rn(dx, f, fx);
-                    fy = __fma_rn(dy, f, fy);
-                    fz = __fma_rn(dz, f, fz);
-                } else {
-                    const double f = pb_lj_fpair(rsq, sig6, eps);
-                    fx = __dadd_rn(fx, __dmul_rn(dx, f));
-                    fy = __dadd_rn(fy, __dmul_rn(dy, f));
-                    fz = __dadd_rn(fz, __dmul_rn(dz, f));
-                }
+            const double p1 = UNIFORM ? k1 : s_c1[ti + tj[u]], p2 = UNIFORM ? k2 : s_c2[ti + tj[u]];
+            if(FMA) {
+                const double rsq = pb_pair_rsq_fma(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], &dx, &dy, &dz);
+                double f = pb_lj_fpair_fast(rsq, p1, p2);
+                f = pb_less_bits(rsq, a.cutsq) ? f : 0.0;
+                fx = __fma_rn(dx, f, fx);
+                fy = __fma_rn(dy, f, fy);
+                fz = __fma_rn(dz, f, fz);
+            } else {
+                const double rsq = pb_pair_rsq(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], &dx, &dy, &dz);
+                const bool in = rsq < a.cutsq;
+                double f = pb_lj_fpair(in ? rsq : 1.0, p1, p2);
+                f = in ? f : 0.0;
+                fx = __dadd_rn(fx, __dmul_rn(dx, f));
+                fy = __dadd_rn(fy, __dmul_rn(dy, f));
+                fz = __dadd_rn(fz, __dmul_rn(dz, f));
             }
         }
     }
@@ -659,6 +686,7 @@ int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int pa
     PbTileLjArgs a;
     a.nlocal = ctx->nlocal; a.ncap = ctx->ncap; a.T4 = ctx->tile_T4; a.cap = ctx->pcap; a.ntypes = ctx->ntypes;
     a.cutsq = cutsq; a.eps_u = ctx->h_eps[0]; a.sig6_u = ctx->h_sig6[0]; a.dt = dt; a.half_dt = dt * 0.5;
+    a.c1_u = 48.0 * a.eps_u * a.sig6_u * a.sig6_u; a.c2_u = 24.0 * a.eps_u * a.sig6_u;
     a.eps_t = ctx->d_eps; a.sig6_t = ctx->d_sig6;
     a.g = pb_tile_geom(ctx);
     a.tiles = ctx->tiles; a.sel = nullptr; a.nsel = ctx->ntiles;

@@ -256,7 +256,9 @@ def check(backend, dist, rank, world, local, nx=12, steps_a=30, steps_c=45):
         for k, rk in enumerate(sim.ranks):
             gid = tag2gid(gc[k]["tag"])
             ox = np.full((n_glob, 3), np.nan)
-            ox[o_gid_c[k][rk.ints("uid") - k * n_glob]] = rk.real("position")
+            u = rk.ints("uid").astype(np.int64)                # a migrated particle carries the uid its ORIGIN rank gave it
+            ogid = np.array([o_gid_c[q][j] for q, j in zip(u // n_glob, u % n_glob)], dtype=np.int64)
+            ox[ogid] = rk.real("position")
             dd = gc[k]["pos"] - ox[gid]            # NaN where the two runs disagree on the owner of a particle
             assert np.all(np.isfinite(dd)), f"rank {k}: particle sets differ from the restatement's"
             worst_xc = max(worst_xc, float(np.abs(dd).max()))

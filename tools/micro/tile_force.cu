@@ -43,7 +43,7 @@ template<int FMA>
 __device__ __forceinline__ void lj_pair(double xi, double yi, double zi, double xj, double yj, double zj, bool valid, double cutsq,
                                         double &fx, double &fy, double &fz) {
     const double dx = __dsub_rn(xi, xj), dy = __dsub_rn(yi, yj), dz = __dsub_rn(zi, zj);
-    if(!FMA) {
+    if(FMA == 0) {
         const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
         if(valid && rsq < cutsq) {
             const double sr2 = __ddiv_rn(1.0, rsq);
@@ -53,6 +53,38 @@ __device__ __forceinline__ void lj_pair(double xi, double yi, double zi, double 
             fy = __dadd_rn(fy, __dmul_rn(dy, f));
             fz = __dadd_rn(fz, __dmul_rn(dz, f));
         }
+    } else if(FMA == 1) {
+        // the reference's arithmetic WITHOUT a branch: the term of a pair outside the cutoff is selected to +0, and x + (+-0) = x
+        // bit for bit (x = -0 cannot occur: the sums start at +0 and a non-zero term never rounds to zero) -- so the four pair
+        // chains of an unrolled iteration are straight-line code that the scheduler can interleave
+        const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const bool in = valid && rsq < cutsq;
+        const double sr2 = __ddiv_rn(1.0, in ? rsq : 1.0);
+        const double sr6 = __dmul_rn(__dmul_rn(__dmul_rn(sr2, sr2), sr2), 1.0);
+        double f = __dmul_rn(__dmul_rn(__dmul_rn(__dmul_rn(48.0, sr6), __dsub_rn(sr6, 0.5)), sr2), 1.0);
+        f = in ? f : 0.0;
+        fx = __dadd_rn(fx, __dmul_rn(dx, f));
+        fy = __dadd_rn(fy, __dmul_rn(dy, f));
+        fz = __dadd_rn(fz, __dmul_rn(dz, f));
+    } else if(FMA == 4 || FMA == 5) {
+        // production arithmetic, branch-free: rsq with FMAs, cutoff test on the bit patterns (rsq >= +0: the order of the doubles is
+        // the order of their bits -- two integer compares on the ALU instead of a DSETP on the fp64 pipe), reciprocal = MUFU.RCP64H
+        // (~2^-20) + ONE cubic step (e + e^2: error e^3 ~ 2^-60), f = sr2 * a * (48 eps sig^12 * a - 24 eps sig^6), a = sr2^3:
+        // 17 fp64 instructions per pair instead of 22 (FMA == 2) / 33 (exact)
+        const double rsq = fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx)));
+        const bool in = valid && (FMA == 5 ? (rsq < cutsq) : (__double_as_longlong(rsq) < __double_as_longlong(cutsq)));
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(rsq));
+        const double e = fma(-rsq, y, 1.0);
+        const double t = fma(e, e, e);
+        const double sr2 = fma(y, t, y);
+        const double a = __dmul_rn(__dmul_rn(sr2, sr2), sr2);
+        const double g = fma(48.0, a, -24.0);
+        double f = __dmul_rn(__dmul_rn(sr2, a), g);
+        f = in ? f : 0.0;
+        fx = fma(dx, f, fx);
+        fy = fma(dy, f, fy);
+        fz = fma(dz, f, fz);
     } else {
         const double rsq = fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx)));
         if(valid && rsq < cutsq) {
@@ -315,7 +347,7 @@ __global__ void __launch_bounds__(M) k_build_tile(int n, int cap, Geom g, double
     numneigh[i] = count;
 }
 
-template<int M, int FMA, int PREFETCH>
+template<int M, int FMA, int PREFETCH, int U = 4>
 __global__ void __launch_bounds__(M) k_force_tile(int n, int cap, Geom g, double cutsq, const Tile *__restrict__ tiles, const double4 *__restrict__ pos,
                                                   const int *__restrict__ cell_start, const int *__restrict__ cell_list,
                                                   const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
@@ -333,34 +365,41 @@ __global__ void __launch_bounds__(M) k_force_tile(int n, int cap, Geom g, double
     int nn = 0;
     const int row = tl.row_base + threadIdx.x;
     const unsigned long long *wp = words + (size_t) (row >> 5) * (NCAP / 4) * 32 + (row & 31);
-    unsigned long long wnext = 0ull;
+    constexpr int W = U / 4;
+    unsigned long long wnext[W];
+#pragma unroll
+    for(int q = 0; q < W; q++) { wnext[q] = 0ull; }
     if(i < n) {
         pi = ld256(pos + i);
         nn = min(numneigh[i], NCAP);
-        if(nn > 0) { wnext = __ldg(wp); }
+#pragma unroll
+        for(int q = 0; q < W; q++) { if(q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) q * 32); } }
     }
     tile_stage<false>(h, cap, cell_list, pos, sxy, sz, sidx);
     __syncthreads();
     if(i >= n) { return; }
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    for(int k = 0; k < nn; k += 4) {
-        unsigned long long w;
-        if(PREFETCH) {
-            w = wnext;
-            if(k + 4 < nn) { wnext = __ldg(wp + (size_t) ((k >> 2) + 1) * 32); }
-        } else {
-            w = __ldg(wp + (size_t) (k >> 2) * 32);
-        }
-        double xj[4], yj[4], zj[4];
+    for(int k = 0; k < nn; k += U) {
+        unsigned long long w[W];
 #pragma unroll
-        for(int u = 0; u < 4; u++) {
-            const int s = (k + u < nn) ? (int) ((w >> (16 * u)) & 0xffffull) : 0;
+        for(int q = 0; q < W; q++) {
+            if(PREFETCH) {
+                w[q] = wnext[q];
+                if(k + U + q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) (((k + U) >> 2) + q) * 32); }
+            } else {
+                w[q] = (k + q * 4 < nn) ? __ldg(wp + (size_t) ((k >> 2) + q) * 32) : 0ull;
+            }
+        }
+        double xj[U], yj[U], zj[U];
+#pragma unroll
+        for(int u = 0; u < U; u++) {
+            const int s = (k + u < nn) ? (int) ((w[u >> 2] >> (16 * (u & 3))) & 0xffffull) : 0;
             const double2 xy = sxy[s];
             xj[u] = xy.x; yj[u] = xy.y;
             zj[u] = sz[s];
         }
 #pragma unroll
-        for(int u = 0; u < 4; u++) { lj_pair<FMA>(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], k + u < nn, cutsq, fx, fy, fz); }
+        for(int u = 0; u < U; u++) { lj_pair<FMA>(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], k + u < nn, cutsq, fx, fy, fz); }
     }
     force[i] = __dadd_rn(0.0, fx);
     force[n + i] = __dadd_rn(0.0, fy);
@@ -628,6 +667,16 @@ int main(int argc, char **argv) {
             CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
             t = time_ms(10, [&] { k_force_tile<M, 2, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w, d_nn2, d_f1); });
             report("force_tile_prefetch_fma2", t, false);
+#define VARIANT(NAME, F, UU, WORDS, EXACT)                                                                                                    \
+            CK(cudaFuncSetAttribute(k_force_tile<M, F, 1, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sf));                      \
+            CK(cudaMemset(d_f1, 0, 24 * (size_t) n));                                                                                         \
+            t = time_ms(10, [&] { k_force_tile<M, F, 1, UU><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, WORDS, d_nn2, d_f1); }); \
+            report(NAME, t, EXACT);
+            VARIANT("force_tile_branchless_exact", 1, 4, d_w, true)
+            VARIANT("force_tile_branchless_exact_u8", 1, 8, d_w, true)
+            VARIANT("force_tile_fast", 4, 4, d_w, false)
+            VARIANT("force_tile_fast_dsetp", 5, 4, d_w, false)
+            VARIANT("force_tile_fast_u8", 4, 8, d_w, false)
             // the same lists in the conflict-aware order
             unsigned long long *d_w2;
             CK(cudaMalloc(&d_w2, 8 * (size_t) (rows / 32) * (NCAP / 4) * 32));
@@ -640,6 +689,9 @@ int main(int argc, char **argv) {
             CK(cudaMemset(d_f1, 0, 24 * (size_t) n));
             t = time_ms(10, [&] { k_force_tile<M, 2, 1><<<ntiles, M, sf>>>(n, cap, g, cutsq_f, d_tiles, d_pos, d_cs, d_cl, d_w2, d_nn2, d_f1); });
             report("force_tile_prefetch_fma2_reordered", t, false);
+            VARIANT("force_tile_branchless_exact_reordered", 1, 4, d_w2, false)
+            VARIANT("force_tile_fast_reordered", 4, 4, d_w2, false)
+            VARIANT("force_tile_fast_u8_reordered", 4, 8, d_w2, false)
             CK(cudaFree(d_w2));
         }
         CK(cudaFree(d_tiles)); CK(cudaFree(d_w));
