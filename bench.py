@@ -385,26 +385,33 @@ def run_ours(args):
     out_pos, out_vel = np.empty((cap_out, 3)), np.empty((cap_out, 3))
     for a in (pos, vel, mass, typ, out_pos, out_vel):
         ctx.host_register(a)
-    barrier()
-    t0 = time.perf_counter()
-    ctx.upload(pos, vel, mass, typ)
-    th2 = run(0, K)
-    n_after = ctx.counts()[0]
-    assert n_after <= cap_out, (n_after, cap_out)
-    ctx.real_into("position", out_pos)
-    ctx.real_into("linear_velocity", out_vel)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    # three repetitions, the median counts: the GPU boxes share their host side (PCIe switch, memory bandwidth) with other jobs,
+    # and one and the same 240 MB upload has been seen to take 11 ms and 500 ms in two consecutive processes
+    e2e_samples = []
+    for _rep in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload(pos, vel, mass, typ)
+        th2 = run(0, K)
+        n_after = ctx.counts()[0]
+        assert n_after <= cap_out, (n_after, cap_out)
+        ctx.real_into("position", out_pos)
+        ctx.real_into("linear_velocity", out_vel)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            import torch
+            t = torch.tensor([e2e_s], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t[0])
+        e2e_samples.append(e2e_s)
+    e2e_s = sorted(e2e_samples)[1]
     h2d = (pos.nbytes + vel.nbytes + mass.nbytes + typ.nbytes) * world
     d2h = (2 * n_after * 24 + th2.nbytes) * world
     e2e = {"value": n_global * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
            "what": "pb_upload_particles (pinned host arrays) + pb_md_run over K iterations from ts=0 incl. first neighbour build "
-                   "+ thermo read-backs + pb_download_real(position, linear_velocity)"}
+                   "+ thermo read-backs + pb_download_real(position, linear_velocity); median of three repetitions",
+           "seconds_per_repetition": e2e_samples}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

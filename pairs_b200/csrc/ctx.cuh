@@ -120,6 +120,7 @@ struct pb_ctx {
     //      tile-relative neighbour lists (4 entries per 64-bit word, sliced ELLPACK over list ROWS = tile-major particle order).
     //      The 32-bit per-particle lists above are then built only on demand (pb_require_neigh32). ----
     bool tile_lists = true;       // option "tile_lists"
+    bool tile_reorder = true;     // option "tile_reorder": list rows in the conflict-aware order (tile_lists.cu pb_tile_reorder_row)
     bool lj_fma = true;           // option "lj_fma": fused multiply-adds + Newton reciprocal in the pair term (md_math.h)
     struct PbTile *tiles = nullptr;
     int tiles_cap = 0, ntiles = 0, tile_rows = 0, tile_T4 = 0;

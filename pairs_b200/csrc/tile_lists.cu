@@ -263,78 +263,158 @@ __device__ __forceinline__ bool pb_tile_window(const PbTileGeom &g, int c0, int 
     return true;
 }
 
-__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(int nlocal, int ncap, int T4, PbTileGeom g, double cutsq, const PbTile *__restrict__ tiles,
-                                                            const double4 *__restrict__ pos, const int *__restrict__ flags,
-                                                            const int *__restrict__ particle_cell, const int *__restrict__ cell_start,
-                                                            const int *__restrict__ sub_start, const int *__restrict__ cell_list,
-                                                            unsigned long long *__restrict__ words, int *__restrict__ numneigh,
-                                                            int *__restrict__ max_count, PbTileFaces faces, int *__restrict__ tile_flag) {
+// One thread per core particle of the tile:
+//   * the z windows of all nine stencil rows are computed first, so their 18 slab-CSR loads are in flight together;
+//   * an accepted candidate -- one in five -- enters the pending 64-bit word with one funnel shift; the list order is the
+//     per-particle builder's (stencil rows in (dx, dy) order, ascending CSR position).
+//   (Measured and dropped: branch-free tests that leave a bit per candidate in a mask, appended afterwards by walking the set
+//   bits -- the per-row append loops run to the longest lane's count, 12 of 32 lanes active: 5.5 ms instead of 3.0.)
+// REORDER (option "tile_reorder", the default): the finished row is re-read, put into the conflict-aware order below through
+// the (then idle) staging area, and written again -- see pb_tile_reorder_row.
+struct PbTileBuildArgs {
+    int nlocal, ncap, T4, reorder;
+    PbTileGeom g;
+    double cutsq;
+    const PbTile *tiles;
+    const double4 *pos;
+    const int *flags, *particle_cell, *cell_start, *sub_start, *cell_list;
+    unsigned long long *words;
+    int *numneigh, *max_count, *tile_flag;
+    PbTileFaces faces;
+};
+
+// Conflict-aware order of a list row.  In iteration k of the force kernel the 16 lanes of a half-warp read 16 staged particles:
+// two DIFFERENT slots collide in shared memory when they agree modulo 16 (8-byte z entries: 16 bank pairs; the 16-byte xy
+// entries of a quarter-warp: modulo 8).  A list is a set, its order is free: lane l puts at position k an entry whose slot is
+// (k + l) mod 16 whenever it still has one -- the n-th entry of residue class r goes to k = 16 n + ((r - l) mod 16) -- so the
+// lanes of a half-warp ask for 16 different residues in every iteration.  Entries whose class has more members than there are
+// positions of its residue fill the holes that smaller classes leave, in ascending order.  Measured (tools/micro/tile_force.cu,
+// 4 M atoms): shared-memory wavefronts per launch -38 %, force kernel 0.66 -> 0.58 ms.
+//   row: the thread's T4 * 4 entries in shared memory.  Three passes over the row's words (its own, just written: L2 hits):
+//   class sizes; the HOLES -- position 16 n + offset of a class with fewer than n + 1 members -- chained into a list through the
+//   row itself; placement (an entry whose class has run out of positions takes the next hole).
+__device__ __forceinline__ void pb_tile_reorder_row(const unsigned long long *__restrict__ in_words, int nn, int rot, unsigned short *row) {
+    unsigned long long hist_lo = 0ull, hist_hi = 0ull;           // entries per residue class: 16 x 8 bits
+    for(int q = 0; q * 4 < nn; q++) {
+        const unsigned long long w = __ldcg(in_words + (size_t) q * 32);
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            const unsigned e16 = (unsigned) (w >> (16 * u)) & 0xffffu;
+            const unsigned long long one = (q * 4 + u < nn) ? 1ull << ((e16 & 7u) * 8u) : 0ull;
+            if(e16 & 8u) { hist_hi += one; } else { hist_lo += one; }
+        }
+    }
+    int head = 0;
+#pragma unroll
+    for(int r = 0; r < 16; r++) {
+        const int c = (int) (((r & 8) ? hist_hi : hist_lo) >> ((r & 7) * 8)) & 0xff;
+        for(int k = 16 * c + ((r - rot) & 15); k < nn; k += 16) { row[k] = (unsigned short) head; head = k; }
+    }
+    unsigned long long seen_lo = 0ull, seen_hi = 0ull;
+    for(int q = 0; q * 4 < nn; q++) {
+        const unsigned long long w = __ldcg(in_words + (size_t) q * 32);
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            if(q * 4 + u < nn) {
+                const unsigned e16 = (unsigned) (w >> (16 * u)) & 0xffffu;
+                const int r = (int) (e16 & 15u), sh = (r & 7) * 8;
+                const int n = (int) (((r & 8) ? seen_hi : seen_lo) >> sh) & 0xff;
+                if(r & 8) { seen_hi += 1ull << sh; } else { seen_lo += 1ull << sh; }
+                int k = 16 * n + ((r - rot) & 15);
+                if(k >= nn) { k = head; head = row[k]; }      // no position of this residue left: the next hole
+                row[k] = (unsigned short) e16;
+            }
+        }
+    }
+    for(int k = nn; (k & 3) != 0; k++) { row[k] = (unsigned short) PB_TILE_DUMMY; }
+}
+
+__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
     PbTileHdr *h; double2 *sxy; double *sz; unsigned char *smeta;
     pb_tile_smem(pb_tile_shared, h, sxy, sz, smeta);
-    const PbTile tl = tiles[blockIdx.x];
-    pb_tile_setup(h, g, tl, cell_start);
+    const PbTileGeom &g = a.g;
+    const int nlocal = a.nlocal, ncap = a.ncap, T4 = a.T4;
+    const double cutsq = a.cutsq;
+    const PbTile tl = a.tiles[blockIdx.x];
+    pb_tile_setup(h, g, tl, a.cell_start);
     const int cs = pb_tile_core_slot(h, threadIdx.x);
-    const int i = (cs >= 0) ? __ldg(cell_list + cs) : nlocal;
+    const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : nlocal;
     const bool live = i < nlocal;                                  // a local particle (ghosts sit in core cells at the faces, too)
-    const bool active = live && (flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (the reference's FIXED filter)
+    const bool active = live && (a.flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (the reference's FIXED filter)
     if(live) { h->any_active = 1; }
     __syncthreads();
     if(!h->any_active) {                                           // a tile of ghosts only: nothing to build
-        if(threadIdx.x == 0) { tile_flag[blockIdx.x] = 0; }
+        if(threadIdx.x == 0) { a.tile_flag[blockIdx.x] = 0; }
         return;
     }
-    pb_tile_stage<true>(h, nlocal, cell_list, pos, sxy, sz, smeta);
+    pb_tile_stage<true>(h, nlocal, a.cell_list, a.pos, sxy, sz, smeta);
     __syncthreads();
     int count = 0, boundary = 0;
+    const int row = tl.row_base + threadIdx.x;
+    unsigned long long *const out = a.words + pb_tile_word(row, T4, 0);
     if(active) {
-        const double4 pi = pb_ld_pos(pos + i);
-        boundary = (pi.x < faces.lo[0]) | (pi.x > faces.hi[0]) | (pi.y < faces.lo[1]) | (pi.y > faces.hi[1]) | (pi.z < faces.lo[2]) |
-                   (pi.z > faces.hi[2]);
-        const int flat = particle_cell[i] - 1;
+        const double4 pi = pb_ld_pos(a.pos + i);
+        boundary = (pi.x < a.faces.lo[0]) | (pi.x > a.faces.hi[0]) | (pi.y < a.faces.lo[1]) | (pi.y > a.faces.hi[1]) | (pi.z < a.faces.lo[2]) |
+                   (pi.z > a.faces.hi[2]);
+        const int flat = a.particle_cell[i] - 1;
         const int c2 = flat % g.dim2, col = flat / g.dim2, c1 = col % g.dim1, c0 = col / g.dim1;
         const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
-        const int row = tl.row_base + threadIdx.x;
-        unsigned long long *const out = words + pb_tile_word(row, T4, 0);
         // the particle's own slot in the staging order (its column is staged run `tr0`): what `j != i` becomes
         const int tr0 = (c0 - (tl.X0 - 1)) * 4 + (c1 - (tl.Y0 - 1));
         const int s_self = h->run_slot0[tr0] + (cs - h->run_begin[tr0]);
-        unsigned long long w = 0ull;
-        unsigned meta_or = 0u;
+        // z windows of the nine stencil rows, as slot ranges of the staging order
+        int wb[9], we[9];
+#pragma unroll
         for(int r = 0; r < 9; r++) {
             int b, e;
-            if(!pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
-            const int tr = tr0 + (r / 3 - 1) * 4 + (r % 3 - 1);        // the staged run of this stencil row
-            const int shift = h->run_slot0[tr] - h->run_begin[tr];
-            for(int s = b + shift; s < e + shift; s++) {
+            wb[r] = 0; we[r] = 0;
+            if(pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, a.sub_start, b, e)) {
+                const int tr = tr0 + (r / 3 - 1) * 4 + (r % 3 - 1);        // the staged run of this stencil row
+                const int shift = h->run_slot0[tr] - h->run_begin[tr];
+                wb[r] = b + shift; we[r] = e + shift;
+            }
+        }
+        // entries enter a 64-bit word at the top and move down: after four appends the word holds them in list order
+        unsigned long long w = 0ull;
+        unsigned meta_or = 0u;
+#pragma unroll
+        for(int r = 0; r < 9; r++) {
+            for(int s = wb[r]; s < we[r]; s++) {
                 const double2 xy = sxy[s];
                 const double z = sz[s];
                 const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
                 const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if(rsq < cutsq && s != s_self) {
+                if(rsq < cutsq && (r != 4 || s != s_self)) {
                     const unsigned meta = smeta[s];
-                    if(count < ncap) {
-                        w |= (unsigned long long) ((unsigned) s | ((meta & 7u) << 12)) << (16 * (count & 3));
-                        if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
-                    }
+                    w = (w >> 16) | ((unsigned long long) ((unsigned) s | ((meta & 7u) << 12)) << 48);
                     count++;
+                    if((count & 3) == 0 && count <= ncap) { out[(size_t) ((count >> 2) - 1) * 32] = w; }
                     meta_or |= meta;
                 }
             }
         }
-        if((count & 3) != 0 && (count >> 2) < T4) {      // the last word is padded with the dummy slot
+        if((count & 3) != 0 && (count >> 2) < T4) {      // the last word: entries down to the bottom, padded with the dummy slot
+            w >>= 16 * (4 - (count & 3));
             w |= 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY << (16 * (count & 3));
             out[(size_t) (count >> 2) * 32] = w;
         }
         boundary |= (int) (meta_or >> 3);
     }
-    if(live) { numneigh[i] = count; }
-    const int any_b = __syncthreads_or(boundary);
-    if(threadIdx.x == 0) { tile_flag[blockIdx.x] = any_b != 0; }
+    if(live) { a.numneigh[i] = count; }
+    const int any_b = __syncthreads_or(boundary);                  // (also: every thread is through with the staged positions)
+    if(threadIdx.x == 0) { a.tile_flag[blockIdx.x] = any_b != 0; }
     int m = count;
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
-    if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(max_count, m); }
+    if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(a.max_count, m); }
+    if(a.reorder && active && count > 0 && count <= ncap) {
+        // the staging area is idle now: thread t assembles its row in its T4 * 8 bytes of it (host: PB_TILE_M * T4 * 8 <= staging bytes)
+        unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(sxy) + (size_t) threadIdx.x * (size_t) (T4 * 4);
+        pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf);
+        const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
+        for(int q = 0; q * 4 < count; q++) { out[(size_t) q * 32] = rw[q]; }
+    }
 }
 
 // ---- force ------------------------------------------------------------------------------------------------------------------
@@ -416,6 +496,13 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     const double k1 = FMA ? a.c1_u : a.sig6_u, k2 = FMA ? a.c2_u : a.eps_u;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for(int k = 0; k < nn; k += U) {
+        // the list words of the iteration after the next: into L1 now.  (The loads of the NEXT iteration's words are issued
+        // below, but with 62 of 64 registers live the compiler sinks them to the end of the loop body, ~20 instructions before
+        // their use -- ncu r2l: 26 % of the stall samples on that use.  A prefetch has no destination register to economise.)
+        if(k + 2 * U < nn) {
+#pragma unroll
+            for(int q = 0; q < W; q++) { asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (size_t) (((k + 2 * U) >> 2) + q) * 32)); }
+        }
         unsigned long long w[W];
 #pragma unroll
         for(int q = 0; q < W; q++) {      // a word past the end of the row is replaced by padding entries
@@ -630,9 +717,13 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
         ctx->tile_T4 = T4;
         PB_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int), ctx->stream));
         // (the particle type, 3 bits, always rides in the entries: the Lennard-Jones tables may be set after the lists are built)
-        pb_k_tile_build<<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(n, ctx->ncap, T4, g, cutsq, ctx->tiles, ctx->pos, ctx->flags, ctx->particle_cell,
-                                                                       ctx->cell_start, ctx->sub_start, ctx->cell_list, ctx->twords, ctx->numneigh,
-                                                                       ctx->d_scalars, faces, ctx->tile_flag);
+        PbTileBuildArgs ba;
+        ba.nlocal = n; ba.ncap = ctx->ncap; ba.T4 = T4; ba.g = g; ba.cutsq = cutsq; ba.tiles = ctx->tiles; ba.pos = ctx->pos; ba.flags = ctx->flags;
+        ba.particle_cell = ctx->particle_cell; ba.cell_start = ctx->cell_start; ba.sub_start = ctx->sub_start; ba.cell_list = ctx->cell_list;
+        ba.words = ctx->twords; ba.numneigh = ctx->numneigh; ba.max_count = ctx->d_scalars; ba.tile_flag = ctx->tile_flag; ba.faces = faces;
+        // the reorder pass assembles the rows in the staging area (positions + meta bytes): possible while a row fits its share
+        ba.reorder = ctx->tile_reorder && (size_t) PB_TILE_M * (size_t) T4 * 8 <= (size_t) PB_TILE_CAP * 25;
+        pb_k_tile_build<<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(ba);
         ctx->launches++;
         PB_CHECK(cudaGetLastError());
         const bool split = ctx->world > 1 && ctx->overlap_comm;

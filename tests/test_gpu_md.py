@@ -321,6 +321,7 @@ def test_fused_loop_is_bit_identical():
 def test_lanes_per_particle_layouts_agree(lanes):
     """The interleaved sliced-ELLPACK layouts (G lanes per particle) hold the same lists and give forces within 1e-12."""
     ctx, n = make_gpu(8)
+    ctx.set_option("tile_reorder", 0)           # the builder's own list order, which the per-particle layouts share
     _reneighbor_gpu(ctx)
     nb1 = ctx.neighbors()
     ctx.reset_volatile(); ctx.lennard_jones(CUT)

@@ -1,7 +1,8 @@
 """Tile lists (csrc/tile_lists.cu: cell tiles staged in shared memory, 16-bit tile-relative neighbour lists) against the
 per-particle 32-bit lists they replace on the hot path, and the fused-multiply-add arithmetic against the reference's expression
-tree.  With the reference's arithmetic (option "lj_fma" = 0) the two list formats must agree BIT FOR BIT: same neighbour sets in
-the same order, same forces, same trajectories."""
+tree.  With the reference's arithmetic (option "lj_fma" = 0) and the builder's own list order (option "tile_reorder" = 0) the two
+list formats must agree BIT FOR BIT: same neighbour sets in the same order, same forces, same trajectories.  The production
+default stores every list in a shared-memory-conflict-aware order (same sets, another summation order: forces to 1e-12)."""
 import numpy as np
 import pytest
 
@@ -14,10 +15,11 @@ EPS4 = [1.0 + 0.05 * ((k % 4) + (k // 4)) for k in range(16)]      # a symmetric
 SIG4 = [1.0 - 0.02 * abs((k % 4) - (k // 4)) for k in range(16)]
 
 
-def _run(nx, tile, fma, steps, eps=None, sig6=None, thermo=1):
+def _run(nx, tile, fma, steps, eps=None, sig6=None, thermo=1, reorder=0):
     ctx, n = make_gpu(nx, eps=eps, sig6=sig6)
     ctx.set_option("tile_lists", tile)
     ctx.set_option("lj_fma", fma)
+    ctx.set_option("tile_reorder", reorder)
     th = ctx.md_run(0, steps, DT, CUT, CUT + SKIN, CUT + SKIN, 20, thermo)
     tag = ctx.ints("tag")
     return ctx, th, by_id(tag, ctx.real("position")), by_id(tag, ctx.real("linear_velocity")), by_id(tag, ctx.real("force"))
@@ -30,6 +32,7 @@ def test_tile_lists_equal_the_per_particle_lists_bit_for_bit(nx, eps, sig6):
     ctx_p.set_option("tile_lists", 0)
     for c in (ctx_t, ctx_p):
         c.set_option("lj_fma", 0)
+        c.set_option("tile_reorder", 0)
         _reneighbor_gpu(c)
         c.reset_volatile()
         c.lennard_jones(CUT)
@@ -51,7 +54,7 @@ def test_fma_arithmetic_stays_inside_the_parity_budget(eps, sig6):
     """Option "lj_fma" (default on): forces of one evaluation within 1e-12 (max-norm relative) of the reference's expression tree,
     thermo of 100 iterations within 1e-9; and both against the oracle."""
     nx = 8
-    a = _run(nx, 1, 1, 100, eps, sig6)
+    a = _run(nx, 1, 1, 100, eps, sig6, reorder=1)        # the production default
     b = _run(nx, 1, 0, 100, eps, sig6)
     assert np.abs(a[1][:, 1:] - b[1][:, 1:]).max() <= 1e-9 * np.abs(b[1][:, 1:]).max()
     # one evaluation on the SAME positions (a molten state: on the initial lattice every force is zero by symmetry)
@@ -90,6 +93,7 @@ def test_fixed_particles_and_small_capacity():
         ctx.init_domain(box(nx))
         ctx.set_option("tile_lists", tile)
         ctx.set_option("lj_fma", 0)
+        ctx.set_option("tile_reorder", 0)
         ctx.reserve(0, 8)
         ctx.setup_cells(CUT + SKIN)
         ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
@@ -116,6 +120,7 @@ def test_ragged_box_and_thin_slab():
             ctx.init_domain([0.0, dims[0], 0.0, dims[1], 0.0, dims[2]])
             ctx.set_option("tile_lists", tile)
             ctx.set_option("lj_fma", 0)
+            ctx.set_option("tile_reorder", 0)
             ctx.setup_cells(CUT + SKIN)
             ctx.set_lj_params(1, [1.0], [1.0])
             ctx.upload(pos, np.zeros((n, 3)), np.ones(n), np.zeros(n, np.int32))
@@ -127,3 +132,39 @@ def test_ragged_box_and_thin_slab():
             res.append((by_id(tag, ctx.ints("numneighs")), by_id(tag, np.where(nb >= 0, nb, -1)), tags_all))
         assert np.array_equal(res[0][0], res[1][0]) and res[0][0].sum() > 0, dims
         assert np.array_equal(res[0][1], res[1][1]), dims
+
+
+@pytest.mark.parametrize("nx,eps,sig6", [(6, None, None), (11, EPS4, SIG4)])
+def test_conflict_aware_list_order_keeps_the_sets(nx, eps, sig6):
+    """Option "tile_reorder" (default on): every list holds the same neighbours as the builder's own order -- as sets, per
+    particle -- the 32-bit lists derived from the tiles follow the stored order, forces agree to 1e-12 (summation order), and 45
+    iterations of the loop (three builds) stay within 1e-9."""
+    from pairs_b200.backend import Context
+    m = _run(nx, 1, 0, 12, eps, sig6, thermo=0)             # a molten state, not the lattice (same positions for both orders)
+    typ = by_id(m[0].ints("tag"), m[0].ints("type"))
+    ctxs = []
+    for reorder in (1, 0):
+        ctx = Context(0)
+        ctx.init_domain(box(nx))
+        ctx.set_option("lj_fma", 0)
+        ctx.set_option("tile_reorder", reorder)
+        ctx.setup_cells(CUT + SKIN)
+        ctx.set_lj_params(4, eps or [1.0] * 16, sig6 or [1.0] * 16)
+        ctx.upload(m[2], m[3], np.ones(len(m[2])), typ)
+        _reneighbor_gpu(ctx)
+        ctx.reset_volatile()
+        ctx.lennard_jones(CUT)
+        ctxs.append(ctx)
+    a, b = ctxs
+    nn_a, nn_b = a.ints("numneighs"), b.ints("numneighs")
+    assert np.array_equal(nn_a, nn_b) and nn_a.min() > 40
+    nb_a, nb_b = a.neighbors(), b.neighbors()
+    assert not np.array_equal(nb_a, nb_b)                                      # the order did change ...
+    assert np.array_equal(np.sort(nb_a, axis=1), np.sort(nb_b, axis=1))        # ... the sets did not (-1 pads sort first in both)
+    fa, fb = a.real("force"), b.real("force")
+    assert np.abs(fb).max() > 10.0 and 0.0 < rel_err_force(fa, fb) <= 1e-12
+    assert abs(a.lj_energy_virial(CUT)[0] - b.lj_energy_virial(CUT)[0]) <= 1e-12 * abs(b.lj_energy_virial(CUT)[0])
+    x = _run(nx, 1, 0, 45, eps, sig6, reorder=1)
+    y = _run(nx, 1, 0, 45, eps, sig6, reorder=0)
+    assert np.abs(x[1][:, 1:] - y[1][:, 1:]).max() <= 1e-9 * np.abs(y[1][:, 1:]).max()
+    assert np.abs(x[2] - y[2]).max() <= 1e-9
