@@ -514,8 +514,8 @@ def run_dem(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t[0])
 
-    def barrier():
-        ctx.sync()
+    def barrier(c=None):
+        (c or ctx).sync()
         if dist is not None:
             dist.barrier()
 
@@ -590,7 +590,7 @@ def run_dem(args):
     dem_setup(ctx2, backend, dist, rank, world, domain)
     ctx2.reserve(int(1.25 * nl) + 65536)
     out_pos, out_vel = np.empty((int(1.25 * nl) + 65536, 3)), np.empty((int(1.25 * nl) + 65536, 3))
-    barrier()
+    barrier(ctx2)
     t0 = time.perf_counter()
     ctx2.upload(host["position"], host["linear_velocity"], host["mass"], host_i["type"], host_i["flags"], host_i["uid"], host_i["shape"])
     for k in names:

@@ -218,13 +218,20 @@ class Context:
         rc = self.lib.pb_create(ctypes.byref(h), device)
         if rc != 0:
             raise BackendError(self.lib.pb_last_error(None).decode())
-        self.h = h
+        self._h = h
         self.device = device
 
+    @property
+    def h(self):
+        """The library handle; a closed context raises instead of handing a null pointer to the library."""
+        if self._h is None:
+            raise BackendError("this Context has been closed")
+        return self._h
+
     def close(self):
-        if getattr(self, "h", None):
-            self.lib.pb_destroy(self.h)
-            self.h = None
+        if getattr(self, "_h", None) is not None:
+            self.lib.pb_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:

@@ -407,6 +407,183 @@ __global__ void __launch_bounds__(M) k_force_tile(int n, int cap, Geom g, double
 }
 
 
+// ---- variant "tma": precomputed tile headers, positions staged by TMA bulk copies from a cell-ordered mirror -----------------------
+// What the staging above costs per CTA is a chain of dependent global round trips: tile -> cell_start (run table) -> cell_list
+// (particle indices) -> positions.  Here (a) the run table of every tile is computed once at list-build time (64 ints per tile),
+// (b) positions live a second time in CSR order, split as xy (16 B) and z (8 B) arrays, so that every staged run is ONE contiguous
+// range: 2 x 16 bulk copies (cp.async.bulk, completion on an mbarrier) issued by 16 threads, no index loads, no per-particle
+// cp.async, and the particle's own position comes out of shared memory too.  The z copy needs 16-byte alignment: a run is copied
+// from the even CSR position below its begin to the even position above its end, and its first slot gets the parity of its begin.
+struct TileHdr2 {
+    int total_bytes, ncore, nslots, pad0;
+    int run_begin[NRUN], run_len[NRUN], run_slot0[NRUN];
+    int core_begin[4], core_off[5];
+    int pad1[3];
+};
+static_assert(sizeof(TileHdr2) == 256, "one header = 64 ints");
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, int parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"((unsigned) __cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, int bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned) __cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned) __cvta_generic_to_shared(bar)) : "memory");
+}
+
+__device__ __forceinline__ int tile_core_slot2(const TileHdr2 *h, int t) {
+    if(t >= h->ncore) { return -1; }
+    int q = 0;
+    if(t >= h->core_off[1]) { q = 1; }
+    if(t >= h->core_off[2]) { q = 2; }
+    if(t >= h->core_off[3]) { q = 3; }
+    return h->core_begin[q] + (t - h->core_off[q]);
+}
+// staged slot of the core particle at CSR position cs of core column q (its run is column (q/2 + 1, q%2 + 1) of the 4 x 4)
+__device__ __forceinline__ int tile_self_slot2(const TileHdr2 *h, int t, int cs) {
+    int q = 0;
+    if(t >= h->core_off[1]) { q = 1; }
+    if(t >= h->core_off[2]) { q = 2; }
+    if(t >= h->core_off[3]) { q = 3; }
+    const int tr = (q / 2 + 1) * 4 + (q % 2 + 1);
+    return h->run_slot0[tr] + (cs - h->run_begin[tr]);
+}
+// shared memory: [hdr 256][mbar 16][xy: cap*16][z: cap*8]
+__device__ __forceinline__ void tile_smem2(unsigned char *base, int cap, TileHdr2 *&h, unsigned long long *&bar, double2 *&sxy, double *&sz) {
+    h = reinterpret_cast<TileHdr2 *>(base);
+    bar = reinterpret_cast<unsigned long long *>(base + 256);
+    sxy = reinterpret_cast<double2 *>(base + 272);
+    sz = reinterpret_cast<double *>(sxy + cap);
+}
+static size_t tile_smem2_bytes(int cap) { return 272 + (size_t) cap * 24; }
+
+__device__ __forceinline__ void tile_stage_tma(const TileHdr2 *hg, TileHdr2 *h, unsigned long long *bar, const double2 *__restrict__ mxy,
+                                               const double *__restrict__ mz, double2 *sxy, double *sz) {
+    const int t = threadIdx.x;
+    if(t < 64) { reinterpret_cast<int *>(h)[t] = __ldg(reinterpret_cast<const int *>(hg) + t); }
+    if(t == 0) { mbar_init(bar, 1); }
+    __syncthreads();
+    if(t < NRUN) {
+        const int len = h->run_len[t], begin = h->run_begin[t], slot0 = h->run_slot0[t];
+        if(len > 0) {
+            bulk_g2s(sxy + slot0, mxy + begin, len * 16, bar);
+            const int zb = begin & ~1, ze = (begin + len + 1) & ~1;
+            bulk_g2s(sz + (slot0 - (begin & 1)), mz + zb, (ze - zb) * 8, bar);
+        }
+    }
+    if(t == 0) { mbar_expect_tx(bar, h->total_bytes); }
+}
+
+template<int M>
+__global__ void __launch_bounds__(M) k_build_tile2(int n, int cap, Geom g, double cutsq, const Tile *__restrict__ tiles, const TileHdr2 *__restrict__ hdrs,
+                                                   const double2 *__restrict__ mxy, const double *__restrict__ mz, const double4 *__restrict__ pos,
+                                                   const int *__restrict__ pc, const int *__restrict__ sub_start, const int *__restrict__ cell_list,
+                                                   unsigned long long *__restrict__ words, int *__restrict__ numneigh) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileHdr2 *h; unsigned long long *bar; double2 *sxy; double *sz;
+    tile_smem2(smem, cap, h, bar, sxy, sz);
+    const Tile tl = tiles[blockIdx.x];
+    tile_stage_tma(hdrs + blockIdx.x, h, bar, mxy, mz, sxy, sz);
+    const int cs = tile_core_slot2(h, threadIdx.x);
+    mbar_wait(bar, 0);
+    if(cs < 0) { return; }
+    const int i = __ldg(cell_list + cs);
+    if(i >= n) { return; }
+    const int s_self = tile_self_slot2(h, threadIdx.x, cs);
+    const double4 pi = ld256(pos + i);
+    const int flat = pc[i] - 1;
+    const int c2 = flat % g.dim2, col = flat / g.dim2, c1 = col % g.dim1, c0 = col / g.dim1;
+    const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
+    const int row = tl.row_base + threadIdx.x;
+    unsigned long long *const out = words + (size_t) (row >> 5) * (NCAP / 4) * 32 + (row & 31);
+    unsigned long long w = 0ull;
+    int count = 0;
+    for(int r = 0; r < 9; r++) {
+        int b, e;
+        if(!run_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, sub_start, b, e)) { continue; }
+        const int tr = (c0 + r / 3 - 1 - (tl.X0 - 1)) * 4 + (c1 + r % 3 - 1 - (tl.Y0 - 1));
+        const int shift = h->run_slot0[tr] - h->run_begin[tr];
+        for(int k = b; k < e; k++) {
+            const int s = k + shift;
+            const double2 xy = sxy[s];
+            const double z = sz[s];
+            const double dx = __dsub_rn(pi.x, xy.x), dy = __dsub_rn(pi.y, xy.y), dz = __dsub_rn(pi.z, z);
+            const double rsq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if(rsq < cutsq && s != s_self) {
+                if(count < NCAP) {
+                    w |= (unsigned long long) (unsigned) s << (16 * (count & 3));
+                    if((count & 3) == 3) { out[(size_t) (count >> 2) * 32] = w; w = 0ull; }
+                }
+                count++;
+            }
+        }
+    }
+    if((count & 3) != 0 && count < NCAP) { out[(size_t) (count >> 2) * 32] = w; }
+    numneigh[i] = count;
+}
+
+template<int M, int FMA, int U>
+__global__ void __launch_bounds__(M) k_force_tile_tma(int n, int cap, double cutsq, const Tile *__restrict__ tiles, const TileHdr2 *__restrict__ hdrs,
+                                                      const double2 *__restrict__ mxy, const double *__restrict__ mz, const int *__restrict__ cell_list,
+                                                      const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
+                                                      double *__restrict__ force) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileHdr2 *h; unsigned long long *bar; double2 *sxy; double *sz;
+    tile_smem2(smem, cap, h, bar, sxy, sz);
+    const int row = tiles[blockIdx.x].row_base + threadIdx.x;
+    tile_stage_tma(hdrs + blockIdx.x, h, bar, mxy, mz, sxy, sz);
+    // own data: in flight while the copies land
+    const int cs = tile_core_slot2(h, threadIdx.x);
+    const int i = (cs >= 0) ? __ldg(cell_list + cs) : n;
+    int nn = 0;
+    const unsigned long long *wp = words + (size_t) (row >> 5) * (NCAP / 4) * 32 + (row & 31);
+    constexpr int W = U / 4;
+    unsigned long long wnext[W];
+#pragma unroll
+    for(int q = 0; q < W; q++) { wnext[q] = 0ull; }
+    if(i < n) {
+        nn = min(numneigh[i], NCAP);
+#pragma unroll
+        for(int q = 0; q < W; q++) { if(q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) q * 32); } }
+    }
+    mbar_wait(bar, 0);
+    if(i >= n) { return; }
+    const int s_self = tile_self_slot2(h, threadIdx.x, cs);
+    const double2 pxy = sxy[s_self];
+    const double4 pi = make_double4(pxy.x, pxy.y, sz[s_self], 0.0);
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for(int k = 0; k < nn; k += U) {
+        if(k + 2 * U < nn) {
+#pragma unroll
+            for(int q = 0; q < W; q++) { asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (size_t) (((k + 2 * U) >> 2) + q) * 32)); }
+        }
+        unsigned long long w[W];
+#pragma unroll
+        for(int q = 0; q < W; q++) {
+            w[q] = wnext[q];
+            if(k + U + q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) (((k + U) >> 2) + q) * 32); }
+        }
+        double xj[U], yj[U], zj[U];
+#pragma unroll
+        for(int u = 0; u < U; u++) {
+            const int s = (k + u < nn) ? (int) ((w[u >> 2] >> (16 * (u & 3))) & 0xffffull) : 0;
+            const double2 xy = sxy[s];
+            xj[u] = xy.x; yj[u] = xy.y;
+            zj[u] = sz[s];
+        }
+#pragma unroll
+        for(int u = 0; u < U; u++) { lj_pair<FMA>(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], k + u < nn, cutsq, fx, fy, fz); }
+    }
+    force[i] = __dadd_rn(0.0, fx);
+    force[n + i] = __dadd_rn(0.0, fy);
+    force[2 * (size_t) n + i] = __dadd_rn(0.0, fz);
+}
+
 // ---- conflict-aware order of a list ---------------------------------------------------------------------------------------------
 // In iteration k the 16 lanes of a half-warp read 16 staged particles; two DIFFERENT slots collide in shared memory when they
 // agree modulo 16 (8-byte z entries: 16 bank pairs; the 16-byte xy entries of a quarter-warp: modulo 8).  Every list is a set, its
@@ -692,6 +869,76 @@ int main(int argc, char **argv) {
             VARIANT("force_tile_branchless_exact_reordered", 1, 4, d_w2, false)
             VARIANT("force_tile_fast_reordered", 4, 4, d_w2, false)
             VARIANT("force_tile_fast_u8_reordered", 4, 8, d_w2, false)
+            // ---- "tma": precomputed headers, cell-ordered split mirror, bulk copies ----
+            {
+                std::vector<TileHdr2> hdrs(ntiles);
+                int worst_slots = 0;
+                for(int t = 0; t < ntiles; t++) {
+                    const Tile &tl = tiles[t];
+                    TileHdr2 &h = hdrs[t];
+                    memset(&h, 0, sizeof(h));
+                    int acc = 0, bytes = 0;
+                    for(int r = 0; r < NRUN; r++) {
+                        const int X = tl.X0 - 1 + r / 4, Y = tl.Y0 - 1 + r % 4;
+                        int begin = 0, len = 0;
+                        if(X >= 0 && X < dim && Y >= 0 && Y < dim) {
+                            const int zb = std::max(tl.za - 1, 0), ze = std::min(tl.zb + 1, dim - 1);
+                            begin = cell_start[(X * dim + Y) * dim + zb + 1];
+                            len = cell_start[(X * dim + Y) * dim + ze + 2] - begin;
+                        }
+                        h.run_begin[r] = begin; h.run_len[r] = len;
+                        const int slot0 = acc + (begin & 1);
+                        h.run_slot0[r] = slot0;
+                        if(len > 0) {
+                            acc = (slot0 + len + 1) & ~1;
+                            bytes += len * 16 + (((begin + len + 1) & ~1) - (begin & ~1)) * 8;
+                        }
+                    }
+                    h.nslots = acc; h.total_bytes = bytes;
+                    worst_slots = std::max(worst_slots, acc);
+                    int off = 0;
+                    for(int q = 0; q < 4; q++) {
+                        const int X = tl.X0 + q / 2, Y = tl.Y0 + q % 2;
+                        int begin = 0, len = 0;
+                        if(X < dim && Y < dim) {
+                            begin = cell_start[(X * dim + Y) * dim + tl.za + 1];
+                            len = cell_start[(X * dim + Y) * dim + tl.zb + 2] - begin;
+                        }
+                        h.core_begin[q] = begin; h.core_off[q] = off; off += len;
+                    }
+                    h.core_off[4] = off; h.ncore = off;
+                }
+                if(worst_slots <= cap) {
+                    std::vector<double2> hxy(n + 2);
+                    std::vector<double> hz(n + 2, 0.0);
+                    for(int k = 0; k < n; k++) { hxy[k] = make_double2(pos[k].x, pos[k].y); hz[k] = pos[k].z; }
+                    TileHdr2 *d_h; double2 *d_mxy; double *d_mz; unsigned long long *d_w3, *d_w4;
+                    CK(cudaMalloc(&d_h, sizeof(TileHdr2) * ntiles)); CK(cudaMalloc(&d_mxy, 16 * (size_t) (n + 2))); CK(cudaMalloc(&d_mz, 8 * (size_t) (n + 2)));
+                    CK(cudaMemcpy(d_h, hdrs.data(), sizeof(TileHdr2) * ntiles, cudaMemcpyHostToDevice));
+                    CK(cudaMemcpy(d_mxy, hxy.data(), 16 * (size_t) (n + 2), cudaMemcpyHostToDevice));
+                    CK(cudaMemcpy(d_mz, hz.data(), 8 * (size_t) (n + 2), cudaMemcpyHostToDevice));
+                    const size_t wbytes = 8 * (size_t) (rows / 32) * (NCAP / 4) * 32;
+                    CK(cudaMalloc(&d_w3, wbytes)); CK(cudaMalloc(&d_w4, wbytes));
+                    CK(cudaMemset(d_w3, 0, wbytes)); CK(cudaMemset(d_w4, 0, wbytes));
+                    const size_t s2 = tile_smem2_bytes(cap);
+                    CK(cudaFuncSetAttribute(k_build_tile2<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s2));
+                    float tb = time_ms(3, [&] { k_build_tile2<M><<<ntiles, M, s2>>>(n, cap, g, cutsq_l, d_tiles, d_h, d_mxy, d_mz, d_pos, d_pc, d_sub, d_cl, d_w3, d_nn2); });
+                    printf("{\"kernel\": \"build_tile_tma\", \"M\": %d, \"ms\": %.4f, \"max_slots\": %d}\n", M, tb, worst_slots);
+                    time_ms(1, [&] { k_reorder_tile<M><<<ntiles, M>>>(n, g, d_tiles, d_cs, d_cl, d_nn2, d_w3, d_w4); });
+#define VARIANT_TMA(NAME, F, UU, WORDS, EXACT)                                                                                                \
+                    CK(cudaFuncSetAttribute(k_force_tile_tma<M, F, UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s2));              \
+                    CK(cudaMemset(d_f1, 0, 24 * (size_t) n));                                                                                 \
+                    t = time_ms(10, [&] { k_force_tile_tma<M, F, UU><<<ntiles, M, s2>>>(n, cap, cutsq_f, d_tiles, d_h, d_mxy, d_mz, d_cl, WORDS, d_nn2, d_f1); }); \
+                    report(NAME, t, EXACT);
+                    VARIANT_TMA("force_tma_exact", 1, 4, d_w3, true)
+                    VARIANT_TMA("force_tma_fast_u8", 4, 8, d_w3, false)
+                    VARIANT_TMA("force_tma_exact_reordered", 1, 4, d_w4, false)
+                    VARIANT_TMA("force_tma_fast_u8_reordered", 4, 8, d_w4, false)
+                    CK(cudaFree(d_h)); CK(cudaFree(d_mxy)); CK(cudaFree(d_mz)); CK(cudaFree(d_w3)); CK(cudaFree(d_w4));
+                } else {
+                    printf("{\"kernel\": \"build_tile_tma\", \"M\": %d, \"skipped\": \"%d slots > cap %d\"}\n", M, worst_slots, cap);
+                }
+            }
             CK(cudaFree(d_w2));
         }
         CK(cudaFree(d_tiles)); CK(cudaFree(d_w));
