@@ -375,6 +375,8 @@ extern "C" int pb_synchronize(pb_ctx *ctx) {
                   angvel);
     }
     ctx->ghosts_in_alt = false;
+    // inside pb_md_run the mirror of the tile lists follows the refreshed ghosts (tile_lists.cu)
+    if(ctx->mirror_scope && ctx->mirror_fresh && ctx->tiles_n == ctx->nlocal) { PB_TRY(pb_tile_mirror_ghosts(ctx)); }
     return 0;
 }
 

@@ -121,6 +121,16 @@ struct pb_ctx {
     //      The 32-bit per-particle lists above are then built only on demand (pb_require_neigh32). ----
     bool tile_lists = true;       // option "tile_lists"
     bool tile_reorder = true;     // option "tile_reorder": list rows in the conflict-aware order (tile_lists.cu pb_tile_reorder_row)
+    struct PbTileHdr *tile_hdrs = nullptr;   // [ntiles] run tables (tile_lists.cu)
+    int tile_hdrs_cap = 0;
+    // the mirror: positions in CSR order, split xy / z, double-buffered like pos / pos_alt; meta byte (type | 8 for a ghost) and the
+    // CSR position of every ghost.  `mirror_fresh` is honoured only while `mirror_scope` is set (inside pb_md_run).
+    double2 *mxy[2] = {nullptr, nullptr};
+    double *mz[2] = {nullptr, nullptr};
+    unsigned char *mmeta = nullptr;
+    int *ghost_csr = nullptr;
+    int mirror_cap = 0, mirror_cur = 0, mirror_n = -1;
+    bool mirror_scope = false, mirror_fresh = false;
     bool lj_fma = true;           // option "lj_fma": fused multiply-adds + Newton reciprocal in the pair term (md_math.h)
     struct PbTile *tiles = nullptr;
     int tiles_cap = 0, ntiles = 0, tile_rows = 0, tile_T4 = 0;
@@ -216,6 +226,8 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff);        // 0 built, 1 not ap
 int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int part);
 int pb_tile_finish_split(pb_ctx *ctx);
 int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity);
+int pb_tile_mirror_all(pb_ctx *ctx);
+int pb_tile_mirror_ghosts(pb_ctx *ctx);
 int pb_require_neigh32(pb_ctx *ctx);                        // per-particle 32-bit lists for the kernels that walk them (built lazily)
 static inline bool pb_lists_valid(const pb_ctx *ctx) { return ctx->tiles_n == ctx->nlocal || ctx->neigh_n == ctx->nlocal; }
 

@@ -348,6 +348,7 @@ int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int 
         if(fuse & 2) {
             std::swap(ctx->pos, ctx->pos_alt);
             ctx->ghosts_in_alt = true;
+            ctx->mirror_cur ^= 1;              // the mirror of the new positions (locals; the ghosts follow with the next refresh)
         }
         return 0;
     }
@@ -387,6 +388,7 @@ int pb_lj_finish_split(pb_ctx *ctx, int fuse) {
     if(fuse & 2) {
         std::swap(ctx->pos, ctx->pos_alt);
         ctx->ghosts_in_alt = true;
+        if(ctx->tiles_n == ctx->nlocal) { ctx->mirror_cur ^= 1; }
     }
     return 0;
 }

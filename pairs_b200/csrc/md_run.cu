@@ -16,11 +16,22 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
     if(!ctx->cells_set || ctx->spacing != p->cell_spacing) { PB_TRY(pb_setup_cells(ctx, p->cell_spacing)); }
     int nt = 0;
     bool initial_done = false;     // initial_integrate of this iteration was already applied by the previous force kernel
+    // The mirror of the tile lists (positions in CSR order, tile_lists.cu) is trusted only inside this loop, where every writer of
+    // positions is known: the fused force kernel and the ghost refresh keep it current, everything else marks it stale.
+    struct MirrorScope {
+        pb_ctx *c;
+        explicit MirrorScope(pb_ctx *c_) : c(c_) { c->mirror_scope = true; c->mirror_fresh = false; }
+        ~MirrorScope() { c->mirror_scope = false; c->mirror_fresh = false; }
+    } mirror_scope(ctx);
     for(int ts = ts_begin; ts < ts_end; ts++) {
         const bool reneigh = (((ts + 1) % p->reneighbor_every) == 0) || (ts == 0);
-        if(ts > 0 && !initial_done) { PB_TRY(pb_initial_integrate(ctx, p->dt)); }
+        if(ts > 0 && !initial_done) {
+            PB_TRY(pb_initial_integrate(ctx, p->dt));
+            ctx->mirror_fresh = false;
+        }
         initial_done = false;
         if(reneigh) {
+            ctx->mirror_fresh = false;      // (the tile build writes the mirror anew)
             PB_TRY(pb_exchange(ctx));
             PB_TRY(pb_borders(ctx));
             PB_TRY(pb_build_cell_lists(ctx));
@@ -31,8 +42,10 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
         // groups follow once the refresh has landed.  (The reference's communication is blocking)
         // (half lists: a particle's force is complete only after the whole grid, so nothing is fused or split)
         const bool fusing = ctx->fuse_integrate && !ctx->half_lists;
+        // (tile lists: only with a current mirror -- otherwise this step rebuilds it, in order, on one stream)
         const bool overlap = !reneigh && ctx->world > 1 && ctx->overlap_comm && fusing &&
-                             ((ctx->tiles_n == ctx->nlocal && ctx->tile_split_valid) || (ctx->groups_valid && ctx->neigh_n == ctx->nlocal));
+                             ((ctx->tiles_n == ctx->nlocal && ctx->tile_split_valid && ctx->mirror_fresh) ||
+                              (ctx->tiles_n != ctx->nlocal && ctx->groups_valid && ctx->neigh_n == ctx->nlocal));
         if(!reneigh && !overlap) { PB_TRY(pb_synchronize(ctx)); }
         PB_TRY(pb_reset_volatile(ctx));
         const bool thermo_now = p->thermo_every > 0 && ((((ts + 1) % p->thermo_every) == 0) || ts == 0);

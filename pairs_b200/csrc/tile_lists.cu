@@ -36,7 +36,8 @@
 static const int PB_TILE_NRUN = 16;
 // The last staging slot holds no particle but a point far outside every cutoff: list rows are padded to whole words (four
 // entries) with it, so the force kernel needs no "is this entry valid" test -- a padding entry simply fails the cutoff test.
-static const int PB_TILE_DUMMY = PB_TILE_CAP - 1, PB_TILE_STAGED = PB_TILE_CAP - 1;
+// (Up to two slots per staged run stay empty, see PbTileHdr: the planner keeps 32 slots back for them.)
+static const int PB_TILE_DUMMY = PB_TILE_CAP - 1, PB_TILE_STAGED = PB_TILE_CAP - 1 - 2 * PB_TILE_NRUN;
 static const double PB_TILE_FAR = 1e150;      // (x - 1e150)^2 * 3 is finite and > any cutoff^2
 
 struct PbTileGeom {
@@ -45,11 +46,17 @@ struct PbTileGeom {
     int dim0, dim1, dim2, zsub;
 };
 
+// Run table of a tile, computed ONCE per list build (pb_k_tile_headers) and read by every kernel that visits the tile: the 16
+// staged runs (columns X0-1 .. X0+2, Y0-1 .. Y0+2 over [za-1, zb+1]; CSR begin, length, first staging slot) and the 4 core runs.
+// Staging slots: run r starts at an even slot plus the parity of its CSR begin -- the 8-byte z entries of a run are then 16-byte
+// aligned in shared memory exactly where they are in the mirror (TMA bulk copies need 16-byte alignment on both sides).
 struct PbTileHdr {
-    int total, ncore, any_active, pad;
+    int total_bytes, ncore, any_local, nslots;
     int run_begin[PB_TILE_NRUN], run_len[PB_TILE_NRUN], run_slot0[PB_TILE_NRUN];
     int core_begin[4], core_off[5];
+    int pad[3];
 };
+static_assert(sizeof(PbTileHdr) == 256, "one tile header = 64 ints");
 
 static PbTileGeom pb_tile_geom(const pb_ctx *ctx) {
     PbTileGeom g;
@@ -128,111 +135,153 @@ __global__ void __launch_bounds__(256) pb_k_tile_rows(int ntiles, const int *__r
     if(t < ntiles) { tiles[t].row_base = row[t]; }
 }
 
-// ---- staging -----------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pb_cp_async16(void *smem, const void *gmem) {
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void pb_cp_async8(void *smem, const void *gmem) {
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void pb_cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-// run table of the tile: 16 staged runs (columns X0-1 .. X0+2, Y0-1 .. Y0+2 over [za-1, zb+1]) and the 4 core runs
-__device__ __forceinline__ void pb_tile_setup(PbTileHdr *h, const PbTileGeom &g, const PbTile &tl, const int *__restrict__ cell_start) {
-    const int t = threadIdx.x;
-    if(t < PB_TILE_NRUN) {
-        int len = 0, begin = 0;
-        const int X = tl.X0 - 1 + t / 4, Y = tl.Y0 - 1 + t % 4;
+// ---- headers, mirror ------------------------------------------------------------------------------------------------------------
+// one warp per tile: lanes 0..15 the staged runs, lanes 16..19 the core runs, all lanes look for a LOCAL particle in the core
+__global__ void __launch_bounds__(128) pb_k_tile_headers(int ntiles, int nlocal, PbTileGeom g, const PbTile *__restrict__ tiles,
+                                                         const int *__restrict__ cell_start, const int *__restrict__ cell_list,
+                                                         PbTileHdr *__restrict__ hdrs) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if(t >= ntiles) { return; }
+    const PbTile tl = tiles[t];
+    int begin = 0, len = 0;
+    if(lane < PB_TILE_NRUN) {
+        const int X = tl.X0 - 1 + lane / 4, Y = tl.Y0 - 1 + lane % 4;
         if(X >= 0 && X < g.dim0 && Y >= 0 && Y < g.dim1) {
             const int zb = max(tl.za - 1, 0), ze = min(tl.zb + 1, g.dim2 - 1);
-            const int fb = (X * g.dim1 + Y) * g.dim2 + zb, fe = (X * g.dim1 + Y) * g.dim2 + ze;
-            begin = cell_start[fb + 1];
-            len = cell_start[fe + 2] - begin;
+            begin = cell_start[(X * g.dim1 + Y) * g.dim2 + zb + 1];
+            len = cell_start[(X * g.dim1 + Y) * g.dim2 + ze + 2] - begin;
         }
-        h->run_begin[t] = begin;
-        h->run_len[t] = len;
-    } else if(t >= 32 && t < 36) {
-        const int q = t - 32;
+    } else if(lane < PB_TILE_NRUN + 4) {
+        const int q = lane - PB_TILE_NRUN;
         const int X = tl.X0 + q / 2, Y = tl.Y0 + q % 2;
-        int begin = 0, len = 0;
         if(X < g.dim0 && Y < g.dim1) {
-            const int fb = (X * g.dim1 + Y) * g.dim2 + tl.za, fe = (X * g.dim1 + Y) * g.dim2 + tl.zb;
-            begin = cell_start[fb + 1];
-            len = cell_start[fe + 2] - begin;
+            begin = cell_start[(X * g.dim1 + Y) * g.dim2 + tl.za + 1];
+            len = cell_start[(X * g.dim1 + Y) * g.dim2 + tl.zb + 2] - begin;
         }
-        h->core_begin[q] = begin;
-        h->core_off[q + 1] = len;
     }
-    __syncthreads();
-    if(t == 0) {
-        int acc = 0;
-        for(int r = 0; r < PB_TILE_NRUN; r++) { h->run_slot0[r] = acc; acc += h->run_len[r]; }
-        h->total = acc;
-        h->core_off[0] = 0;
-        for(int q = 0; q < 4; q++) { h->core_off[q + 1] += h->core_off[q]; }
-        h->ncore = h->core_off[4];
-        h->any_active = 0;
+    // staging slots and copy sizes: a sequential walk over the 16 runs (lane 0), core offsets (lane 16)
+    PbTileHdr *h = hdrs + t;
+    int slot0 = 0, acc = 0, bytes = 0;
+    for(int r = 0; r < PB_TILE_NRUN; r++) {
+        const int rb = __shfl_sync(0xffffffffu, begin, r), rl = __shfl_sync(0xffffffffu, len, r);
+        const int s0 = acc + (rb & 1);
+        if(lane == r) { slot0 = s0; }
+        if(rl > 0) {
+            acc = (s0 + rl + 1) & ~1;
+            bytes += rl * 16 + (((rb + rl + 1) & ~1) - (rb & ~1)) * 8;
+        }
     }
-    __syncthreads();
+    int off = 0, core_total = 0;
+    for(int q = 0; q < 4; q++) {
+        const int ql = __shfl_sync(0xffffffffu, len, PB_TILE_NRUN + q);
+        if(lane == PB_TILE_NRUN + q) { off = core_total; }
+        core_total += ql;
+    }
+    // any local particle among the core particles?  (tiles of ghosts only are skipped by every kernel)
+    int found = 0;
+    for(int q = 0; q < 4; q++) {
+        const int qb = __shfl_sync(0xffffffffu, begin, PB_TILE_NRUN + q), ql = __shfl_sync(0xffffffffu, len, PB_TILE_NRUN + q);
+        for(int k = lane; k < ql; k += 32) { found |= (cell_list[qb + k] < nlocal); }
+    }
+    found = __any_sync(0xffffffffu, found);
+    if(lane < PB_TILE_NRUN) { h->run_begin[lane] = begin; h->run_len[lane] = len; h->run_slot0[lane] = slot0; }
+    else if(lane < PB_TILE_NRUN + 4) { h->core_begin[lane - PB_TILE_NRUN] = begin; h->core_off[lane - PB_TILE_NRUN] = off; }
+    if(lane == 0) { h->total_bytes = bytes; h->ncore = core_total; h->any_local = found; h->nslots = acc; h->core_off[4] = core_total; }
 }
 
-// CSR position of the t-th core particle of the tile (-1: none)
-__device__ __forceinline__ int pb_tile_core_slot(const PbTileHdr *h, int t) {
+// The mirror: positions a second time in CSR order (locals and ghosts alike), split into xy (16 bytes) and z (8 bytes), so that
+// every staged run is ONE contiguous range of each array.  Written in full here (after every cell-list build, and whenever the
+// mirror is not known to be current), kept current inside pb_md_run by the fused force kernel (locals) and pb_tile_mirror_ghosts.
+__global__ void __launch_bounds__(256) pb_k_tile_mirror(int nall, int nlocal, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
+                                                        double2 *__restrict__ mxy, double *__restrict__ mz, unsigned char *__restrict__ mmeta,
+                                                        int *__restrict__ ghost_csr) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if(k >= nall) { return; }
+    const int i = __ldg(cell_list + k);
+    const double4 p = pb_ld_pos(pos + i);
+    mxy[k] = make_double2(p.x, p.y);
+    mz[k] = p.z;
+    mmeta[k] = (unsigned char) ((pb_w_type(p.w) & 7) | ((i >= nlocal) ? 8 : 0));
+    if(i >= nlocal) { ghost_csr[i - nlocal] = k; }
+}
+
+__global__ void __launch_bounds__(256) pb_k_tile_mirror_ghosts(int nghost, int nlocal, const int *__restrict__ ghost_csr, const double4 *__restrict__ pos,
+                                                               double2 *__restrict__ mxy, double *__restrict__ mz) {
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if(gidx >= nghost) { return; }
+    const int k = __ldg(ghost_csr + gidx);
+    const double4 p = pb_ld_pos(pos + nlocal + gidx);
+    mxy[k] = make_double2(p.x, p.y);
+    mz[k] = p.z;
+}
+
+// ---- staging: TMA bulk copies, completion on an mbarrier ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned pb_smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pb_mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pb_smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pb_mbar_expect_tx(unsigned long long *bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pb_mbar_wait(unsigned long long *bar, int parity) {
+    asm volatile("{\n.reg .pred p;\nPB_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra PB_DONE_%=;\nbra PB_WAIT_%=;\nPB_DONE_%=:\n}"
+                 ::"r"(pb_smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void pb_bulk_g2s(void *dst, const void *src, int bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pb_smem_addr(dst)), "l"(src), "r"(bytes), "r"(pb_smem_addr(bar)) : "memory");
+}
+
+// shared memory: [hdr 256][mbarrier 16][xy: CAP*16][z: CAP*8][meta: CAP (build)]
+__device__ __forceinline__ void pb_tile_smem(unsigned char *base, PbTileHdr *&h, unsigned long long *&bar, double2 *&sxy, double *&sz, unsigned char *&smeta) {
+    h = reinterpret_cast<PbTileHdr *>(base);
+    bar = reinterpret_cast<unsigned long long *>(base + 256);
+    sxy = reinterpret_cast<double2 *>(base + 272);
+    sz = reinterpret_cast<double *>(sxy + PB_TILE_CAP);
+    smeta = reinterpret_cast<unsigned char *>(sz + PB_TILE_CAP);
+}
+static size_t pb_tile_smem_bytes(bool build) { return 272 + (size_t) PB_TILE_CAP * 24 + (build ? (size_t) PB_TILE_CAP : 0); }
+
+// Header into shared memory, barrier armed, the 2 x 16 copies issued (threads 0..15, one run each).  Returns false -- for the
+// whole CTA, before anything is in flight -- when the tile holds ghosts only.  The caller waits with pb_mbar_wait(bar, 0).
+__device__ __forceinline__ bool pb_tile_stage(const PbTileHdr *__restrict__ hg, PbTileHdr *h, unsigned long long *bar, const double2 *__restrict__ mxy,
+                                              const double *__restrict__ mz, double2 *sxy, double *sz) {
+    const int t = threadIdx.x;
+    if(t < 64) { reinterpret_cast<int *>(h)[t] = __ldg(reinterpret_cast<const int *>(hg) + t); }
+    if(t == 0) {
+        pb_mbar_init(bar, 1);
+        sxy[PB_TILE_DUMMY] = make_double2(PB_TILE_FAR, PB_TILE_FAR);
+        sz[PB_TILE_DUMMY] = PB_TILE_FAR;
+    }
+    __syncthreads();
+    if(!h->any_local) { return false; }
+    if(t < PB_TILE_NRUN) {
+        const int len = h->run_len[t], begin = h->run_begin[t], slot0 = h->run_slot0[t];
+        if(len > 0) {
+            pb_bulk_g2s(sxy + slot0, mxy + begin, len * 16, bar);
+            const int zb = begin & ~1, ze = (begin + len + 1) & ~1;
+            pb_bulk_g2s(sz + (slot0 - (begin & 1)), mz + zb, (ze - zb) * 8, bar);
+        }
+    }
+    if(t == 0) { pb_mbar_expect_tx(bar, h->total_bytes); }
+    return true;
+}
+
+// core column of the t-th core particle of the tile (-1: none)
+__device__ __forceinline__ int pb_tile_core_q(const PbTileHdr *h, int t) {
     if(t >= h->ncore) { return -1; }
     int q = 0;
     if(t >= h->core_off[1]) { q = 1; }
     if(t >= h->core_off[2]) { q = 2; }
     if(t >= h->core_off[3]) { q = 3; }
-    return h->core_begin[q] + (t - h->core_off[q]);
+    return q;
 }
-
-// warp r stages runs r, r + nwarps, ...: four index loads in flight, then two cp.async per particle (x,y | z).
-// META (list build): one byte per slot = particle type (3 bits) | 8 for a ghost
-template<bool META>
-__device__ __forceinline__ void pb_tile_stage(const PbTileHdr *h, int nlocal, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
-                                              double2 *sxy, double *sz, unsigned char *smeta) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for(int r = warp; r < PB_TILE_NRUN; r += nw) {
-        const int len = h->run_len[r], begin = h->run_begin[r], slot0 = h->run_slot0[r];
-        for(int k0 = 0; k0 < len; k0 += 128) {
-            int idx[4];
-#pragma unroll
-            for(int u = 0; u < 4; u++) { const int k = k0 + u * 32 + lane; idx[u] = (k < len) ? __ldg(cell_list + begin + k) : -1; }
-            double wv[4];
-            if(META) {
-#pragma unroll
-                for(int u = 0; u < 4; u++) { wv[u] = (idx[u] >= 0) ? __ldg(reinterpret_cast<const double *>(pos + idx[u]) + 3) : 0.0; }
-            }
-#pragma unroll
-            for(int u = 0; u < 4; u++) {
-                const int s = slot0 + k0 + u * 32 + lane;
-                if(idx[u] >= 0 && s < PB_TILE_STAGED) {
-                    const double *src = reinterpret_cast<const double *>(pos + idx[u]);
-                    pb_cp_async16(sxy + s, src);
-                    pb_cp_async8(sz + s, src + 2);
-                    if(META) { smeta[s] = (unsigned char) ((pb_w_type(wv[u]) & 7) | ((idx[u] >= nlocal) ? 8 : 0)); }
-                }
-            }
-        }
-    }
-    pb_cp_async_wait_all();
-}
-
-// shared memory: [hdr][xy: CAP*16][z: CAP*8][meta: CAP (build)]
-__device__ __forceinline__ void pb_tile_smem(unsigned char *base, PbTileHdr *&h, double2 *&sxy, double *&sz, unsigned char *&smeta) {
-    h = reinterpret_cast<PbTileHdr *>(base);
-    unsigned char *p = base + ((sizeof(PbTileHdr) + 15) / 16) * 16;
-    sxy = reinterpret_cast<double2 *>(p);
-    sz = reinterpret_cast<double *>(sxy + PB_TILE_CAP);
-    smeta = reinterpret_cast<unsigned char *>(sz + PB_TILE_CAP);
-}
-static size_t pb_tile_smem_bytes(bool build) {
-    return ((sizeof(PbTileHdr) + 15) / 16) * 16 + (size_t) PB_TILE_CAP * 24 + (build ? (size_t) PB_TILE_CAP : 0);
+// its CSR position, and its own slot in the staging order (core column q is staged run (q / 2 + 1, q % 2 + 1) of the 4 x 4)
+__device__ __forceinline__ int pb_tile_core_csr(const PbTileHdr *h, int t, int q) { return h->core_begin[q] + (t - h->core_off[q]); }
+__device__ __forceinline__ int pb_tile_self_slot(const PbTileHdr *h, int q, int cs) {
+    const int tr = (q / 2 + 1) * 4 + (q % 2 + 1);
+    return h->run_slot0[tr] + (cs - h->run_begin[tr]);
 }
 
 // word q of list row r (4 entries per word): ((r / 32) * T4 + q) * 32 + r % 32
@@ -276,8 +325,12 @@ struct PbTileBuildArgs {
     PbTileGeom g;
     double cutsq;
     const PbTile *tiles;
+    const PbTileHdr *hdrs;
+    const double2 *mxy;
+    const double *mz;
+    const unsigned char *mmeta;
     const double4 *pos;
-    const int *flags, *particle_cell, *cell_start, *sub_start, *cell_list;
+    const int *flags, *particle_cell, *sub_start, *cell_list;
     unsigned long long *words;
     int *numneigh, *max_count, *tile_flag;
     PbTileFaces faces;
@@ -331,38 +384,45 @@ __device__ __forceinline__ void pb_tile_reorder_row(const unsigned long long *__
 
 __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
-    PbTileHdr *h; double2 *sxy; double *sz; unsigned char *smeta;
-    pb_tile_smem(pb_tile_shared, h, sxy, sz, smeta);
+    PbTileHdr *h; unsigned long long *bar; double2 *sxy; double *sz; unsigned char *smeta;
+    pb_tile_smem(pb_tile_shared, h, bar, sxy, sz, smeta);
     const PbTileGeom &g = a.g;
     const int nlocal = a.nlocal, ncap = a.ncap, T4 = a.T4;
     const double cutsq = a.cutsq;
     const PbTile tl = a.tiles[blockIdx.x];
-    pb_tile_setup(h, g, tl, a.cell_start);
-    const int cs = pb_tile_core_slot(h, threadIdx.x);
-    const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : nlocal;
-    const bool live = i < nlocal;                                  // a local particle (ghosts sit in core cells at the faces, too)
-    const bool active = live && (a.flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (the reference's FIXED filter)
-    if(live) { h->any_active = 1; }
-    __syncthreads();
-    if(!h->any_active) {                                           // a tile of ghosts only: nothing to build
+    if(!pb_tile_stage(a.hdrs + blockIdx.x, h, bar, a.mxy, a.mz, sxy, sz)) {      // a tile of ghosts only: nothing to build
         if(threadIdx.x == 0) { a.tile_flag[blockIdx.x] = 0; }
         return;
     }
-    pb_tile_stage<true>(h, nlocal, a.cell_list, a.pos, sxy, sz, smeta);
-    __syncthreads();
+    // while the positions land: the meta bytes of the staged slots (particle type, 3 bits | 8 for a ghost), warp r runs r, r + 8
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for(int r = warp; r < PB_TILE_NRUN; r += nw) {
+            const int len = h->run_len[r], begin = h->run_begin[r], slot0 = h->run_slot0[r];
+            for(int k = lane; k < len; k += 32) { smeta[slot0 + k] = __ldg(a.mmeta + begin + k); }
+        }
+    }
+    const int q = pb_tile_core_q(h, threadIdx.x);
+    const int cs = (q >= 0) ? pb_tile_core_csr(h, threadIdx.x, q) : -1;
+    const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : nlocal;
+    const bool live = i < nlocal;                                  // a local particle (ghosts sit in core cells at the faces, too)
+    const bool active = live && (a.flags[i] & PB_FLAG_FIXED) == 0;   // FIXED particles get no list (the reference's FIXED filter)
+    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
+    int flat = 0;
+    if(active) { pi = pb_ld_pos(a.pos + i); flat = a.particle_cell[i] - 1; }
+    pb_mbar_wait(bar, 0);
+    __syncthreads();                                               // (the meta bytes)
     int count = 0, boundary = 0;
     const int row = tl.row_base + threadIdx.x;
     unsigned long long *const out = a.words + pb_tile_word(row, T4, 0);
     if(active) {
-        const double4 pi = pb_ld_pos(a.pos + i);
         boundary = (pi.x < a.faces.lo[0]) | (pi.x > a.faces.hi[0]) | (pi.y < a.faces.lo[1]) | (pi.y > a.faces.hi[1]) | (pi.z < a.faces.lo[2]) |
                    (pi.z > a.faces.hi[2]);
-        const int flat = a.particle_cell[i] - 1;
         const int c2 = flat % g.dim2, col = flat / g.dim2, c1 = col % g.dim1, c0 = col / g.dim1;
         const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
         // the particle's own slot in the staging order (its column is staged run `tr0`): what `j != i` becomes
         const int tr0 = (c0 - (tl.X0 - 1)) * 4 + (c1 - (tl.Y0 - 1));
-        const int s_self = h->run_slot0[tr0] + (cs - h->run_begin[tr0]);
+        const int s_self = pb_tile_self_slot(h, q, cs);
         // z windows of the nine stencil rows, as slot ranges of the staging order
         int wb[9], we[9];
 #pragma unroll
@@ -424,9 +484,13 @@ struct PbTileLjArgs {
     const double *eps_t, *sig6_t;
     PbTileGeom g;
     const PbTile *tiles;
+    const PbTileHdr *hdrs;
     const int *sel;                 // tile subset of this launch (interior / boundary split), null = all tiles
-    const double4 *pos;
-    const int *flags, *cell_start, *cell_list, *numneigh;
+    const double2 *mxy;             // the mirror: positions in CSR order (this step's), and where the next step's go
+    const double *mz;
+    double2 *mxy_next;
+    double *mz_next;
+    const int *flags, *type, *cell_list, *numneigh;
     const unsigned long long *words;
     double *force;
     const double *mass;
@@ -445,8 +509,8 @@ template<bool UNIFORM, bool ACCUMULATE, int FUSE, bool FMA>
 __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
     __shared__ double s_c1[64], s_c2[64];      // per type pair: (48 eps sigma6^2, 24 eps sigma6) with FMA, (sigma6, eps) without
-    PbTileHdr *h; double2 *sxy; double *sz; unsigned char *smeta;
-    pb_tile_smem(pb_tile_shared, h, sxy, sz, smeta);
+    PbTileHdr *h; unsigned long long *bar; double2 *sxy; double *sz; unsigned char *smeta;
+    pb_tile_smem(pb_tile_shared, h, bar, sxy, sz, smeta);
     if(!UNIFORM) {
         for(int k = threadIdx.x; k < a.ntypes * a.ntypes; k += blockDim.x) {
             const double e = a.eps_t[k], s6 = a.sig6_t[k];
@@ -454,45 +518,42 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
             s_c2[k] = FMA ? 24.0 * e * s6 : e;
         }
     }
-    if(threadIdx.x == 0) { sxy[PB_TILE_DUMMY] = make_double2(PB_TILE_FAR, PB_TILE_FAR); sz[PB_TILE_DUMMY] = PB_TILE_FAR; }
     const int tile_id = (a.sel != nullptr) ? __ldg(a.sel + blockIdx.x) : (int) blockIdx.x;
-    const PbTile tl = a.tiles[tile_id];
-    pb_tile_setup(h, a.g, tl, a.cell_start);
-    // own data first: these loads are in flight while the tile is staged
-    const int cs = pb_tile_core_slot(h, threadIdx.x);
+    const int row = __ldg(&a.tiles[tile_id].row_base) + threadIdx.x;
+    if(!pb_tile_stage(a.hdrs + tile_id, h, bar, a.mxy, a.mz, sxy, sz)) { return; }      // a tile of ghosts only
+    // own data: in flight while the copies land
+    const int cq = pb_tile_core_q(h, threadIdx.x);
+    const int cs = (cq >= 0) ? pb_tile_core_csr(h, threadIdx.x, cq) : -1;
     const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : a.nlocal;
     const bool live = i < a.nlocal;
     const bool fixed = live && (a.flags[i] & PB_FLAG_FIXED) != 0;
-    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
-    int nn = 0;
-    const int row = tl.row_base + threadIdx.x;
+    int nn = 0, type_i = 0;
     const unsigned long long *wp = a.words + pb_tile_word(row, a.T4, 0);
     constexpr int U = FMA ? 8 : 4, W = U / 4;      // pairs per iteration (the exact expression tree needs more registers per pair)
     unsigned long long wnext[W];
 #pragma unroll
-    for(int q = 0; q < W; q++) { wnext[q] = 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY; }
+    for(int w_ = 0; w_ < W; w_++) { wnext[w_] = 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY; }
+    const int cap = a.cap;
+    double m = 1.0, vx = 0.0, vy = 0.0, vz = 0.0;
     if(live) {
-        pi = pb_ld_pos(a.pos + i);
-        h->any_active = 1;
+        if(!UNIFORM || (FUSE & 2)) { type_i = a.type[i]; }
         if(!fixed) {
             nn = min(a.numneigh[i], a.ncap);
 #pragma unroll
-            for(int q = 0; q < W; q++) { if(q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) q * 32); } }
+            for(int w_ = 0; w_ < W; w_++) { if(w_ * 4 < nn) { wnext[w_] = __ldg(wp + (size_t) w_ * 32); } }
+            if(FUSE != 0) {      // the epilogue's operands
+                m = a.mass[i];
+                vx = a.vel[i]; vy = a.vel[cap + i]; vz = a.vel[2 * (size_t) cap + i];
+            }
         }
     }
-    __syncthreads();
-    if(!h->any_active) { return; }                                 // a tile of ghosts only
-    pb_tile_stage<false>(h, a.nlocal, a.cell_list, a.pos, sxy, sz, smeta);
-    __syncthreads();
+    pb_mbar_wait(bar, 0);
     if(!live) { return; }
-    const int ti = UNIFORM ? 0 : pb_w_type(pi.w) * a.ntypes;
-    const int cap = a.cap;
-    // the epilogue's operands are requested now, so that they have arrived when the pair loop is through
-    double m = 1.0, vx = 0.0, vy = 0.0, vz = 0.0;
-    if(FUSE != 0 && !fixed) {
-        m = a.mass[i];
-        vx = a.vel[i]; vy = a.vel[cap + i]; vz = a.vel[2 * (size_t) cap + i];
-    }
+    // the particle's own position comes out of the staged tile as well
+    const int s_self = pb_tile_self_slot(h, cq, cs);
+    const double2 pxy = sxy[s_self];
+    double4 pi = make_double4(pxy.x, pxy.y, sz[s_self], pb_type_w(type_i));
+    const int ti = UNIFORM ? 0 : type_i * a.ntypes;
     const double k1 = FMA ? a.c1_u : a.sig6_u, k2 = FMA ? a.c2_u : a.eps_u;
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for(int k = 0; k < nn; k += U) {
@@ -580,21 +641,27 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
             a.vel[cap + i] = vy;
             a.vel[2 * (size_t) cap + i] = vz;
         }
-        if(FUSE & 2) { a.pos_next[i] = pi; }
+        if(FUSE & 2) {      // the next step's positions: the particle array and the mirror (same CSR position)
+            a.pos_next[i] = pi;
+            a.mxy_next[cs] = make_double2(pi.x, pi.y);
+            a.mz_next[cs] = pi.z;
+        }
     }
 }
 
 // ---- per-particle view of the lists (pb_download_neighbors: tests, tools) -------------------------------------------------------
 template<bool ELL>
-__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_export(int nlocal, int ncap, int T4, int cap_out, PbTileGeom g, const PbTile *__restrict__ tiles,
-                                                             const int *__restrict__ cell_start, const int *__restrict__ cell_list,
+__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_export(int nlocal, int ncap, int T4, int cap_out, const PbTile *__restrict__ tiles,
+                                                             const PbTileHdr *__restrict__ hdrs, const int *__restrict__ cell_list,
                                                              const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
                                                              int *__restrict__ out) {
     __shared__ PbTileHdr hdr;
     PbTileHdr *h = &hdr;
     const PbTile tl = tiles[blockIdx.x];
-    pb_tile_setup(h, g, tl, cell_start);
-    const int cs = pb_tile_core_slot(h, threadIdx.x);
+    if(threadIdx.x < 64) { reinterpret_cast<int *>(h)[threadIdx.x] = reinterpret_cast<const int *>(hdrs + blockIdx.x)[threadIdx.x]; }
+    __syncthreads();
+    const int cq = pb_tile_core_q(h, threadIdx.x);
+    const int cs = (cq >= 0) ? pb_tile_core_csr(h, threadIdx.x, cq) : -1;
     const int i = (cs >= 0) ? cell_list[cs] : nlocal;
     if(i >= nlocal) { return; }
     const int row = tl.row_base + threadIdx.x;
@@ -663,6 +730,49 @@ static int pb_tile_plan(pb_ctx *ctx, bool *overflow) {
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->ntiles = ntiles;
     ctx->tile_rows = ctx->h_scalars[2];
+    PB_TRY(pb_tile_fit(ctx, &ctx->tile_hdrs, &ctx->tile_hdrs_cap, (size_t) ntiles + 1));
+    PB_LAUNCH(pb_k_tile_headers, pb_blocks((long) ntiles * 32, 128), 128, ntiles, ctx->nlocal, g, ctx->tiles, ctx->cell_start, ctx->cell_list, ctx->tile_hdrs);
+    return 0;
+}
+
+// ---- the mirror (positions in CSR order) ---------------------------------------------------------------------------------------
+// everything: after a cell-list build, and before a force evaluation whenever the mirror is not known to be current
+int pb_tile_mirror_all(pb_ctx *ctx) {
+    const int nall = ctx->nlocal + ctx->nghost;
+    if(nall + 2 > ctx->mirror_cap) {
+        for(int b = 0; b < 2; b++) {
+            if(ctx->mxy[b] != nullptr) { PB_CHECK(cudaFree(ctx->mxy[b])); ctx->mxy[b] = nullptr; }
+            if(ctx->mz[b] != nullptr) { PB_CHECK(cudaFree(ctx->mz[b])); ctx->mz[b] = nullptr; }
+        }
+        if(ctx->mmeta != nullptr) { PB_CHECK(cudaFree(ctx->mmeta)); ctx->mmeta = nullptr; }
+        if(ctx->ghost_csr != nullptr) { PB_CHECK(cudaFree(ctx->ghost_csr)); ctx->ghost_csr = nullptr; }
+        ctx->mirror_cap = 0;
+        const size_t want = (size_t) nall + nall / 4 + 1024;
+        for(int b = 0; b < 2; b++) {
+            PB_CHECK(cudaMalloc(&ctx->mxy[b], sizeof(double2) * want));
+            PB_CHECK(cudaMalloc(&ctx->mz[b], sizeof(double) * want));
+            PB_CHECK(cudaMemsetAsync(ctx->mxy[b], 0, sizeof(double2) * want, ctx->stream));      // (the aligned z copies read up to two entries past a run)
+            PB_CHECK(cudaMemsetAsync(ctx->mz[b], 0, sizeof(double) * want, ctx->stream));
+        }
+        PB_CHECK(cudaMalloc(&ctx->mmeta, want));
+        PB_CHECK(cudaMalloc(&ctx->ghost_csr, sizeof(int) * want));
+        ctx->mirror_cap = (int) want;
+    }
+    if(nall > 0) {
+        PB_LAUNCH(pb_k_tile_mirror, pb_blocks(nall, 256), 256, nall, ctx->nlocal, ctx->cell_list, ctx->pos, ctx->mxy[0], ctx->mz[0], ctx->mmeta, ctx->ghost_csr);
+    }
+    ctx->mirror_cur = 0;
+    ctx->mirror_n = nall;
+    ctx->mirror_fresh = true;
+    return 0;
+}
+
+// the ghosts only: after the per-step refresh of their positions (pb_synchronize), inside pb_md_run
+int pb_tile_mirror_ghosts(pb_ctx *ctx) {
+    if(ctx->nghost > 0) {
+        PB_LAUNCH(pb_k_tile_mirror_ghosts, pb_blocks(ctx->nghost, 256), 256, ctx->nghost, ctx->nlocal, ctx->ghost_csr, ctx->pos, ctx->mxy[ctx->mirror_cur],
+                  ctx->mz[ctx->mirror_cur]);
+    }
     return 0;
 }
 
@@ -705,6 +815,7 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
     }
     const size_t smem = pb_tile_smem_bytes(true);
     PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PB_TRY(pb_tile_mirror_all(ctx));                // the tiles are staged out of the mirror
     for(int attempt = 0; attempt < 8; attempt++) {
         const int T4 = (ctx->ncap + 3) / 4;
         const size_t bytes = sizeof(unsigned long long) * (size_t) (ctx->tile_rows / 32) * (size_t) T4 * 32;
@@ -719,7 +830,8 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
         // (the particle type, 3 bits, always rides in the entries: the Lennard-Jones tables may be set after the lists are built)
         PbTileBuildArgs ba;
         ba.nlocal = n; ba.ncap = ctx->ncap; ba.T4 = T4; ba.g = g; ba.cutsq = cutsq; ba.tiles = ctx->tiles; ba.pos = ctx->pos; ba.flags = ctx->flags;
-        ba.particle_cell = ctx->particle_cell; ba.cell_start = ctx->cell_start; ba.sub_start = ctx->sub_start; ba.cell_list = ctx->cell_list;
+        ba.hdrs = ctx->tile_hdrs; ba.mxy = ctx->mxy[ctx->mirror_cur]; ba.mz = ctx->mz[ctx->mirror_cur]; ba.mmeta = ctx->mmeta;
+        ba.particle_cell = ctx->particle_cell; ba.sub_start = ctx->sub_start; ba.cell_list = ctx->cell_list;
         ba.words = ctx->twords; ba.numneigh = ctx->numneigh; ba.max_count = ctx->d_scalars; ba.tile_flag = ctx->tile_flag; ba.faces = faces;
         // the reorder pass assembles the rows in the staging area (positions + meta bytes): possible while a row fits its share
         ba.reorder = ctx->tile_reorder && (size_t) PB_TILE_M * (size_t) T4 * 8 <= (size_t) PB_TILE_CAP * 25;
@@ -789,7 +901,12 @@ int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int pa
         a.nsel = grid;
     }
     if(grid == 0) { return 0; }
-    a.pos = ctx->pos; a.flags = ctx->flags; a.cell_start = ctx->cell_start; a.cell_list = ctx->cell_list; a.numneigh = ctx->numneigh;
+    // the mirror is known to be current only inside pb_md_run (which keeps it so); any other caller gets it rebuilt here
+    if(!(ctx->mirror_scope && ctx->mirror_fresh && ctx->mirror_n == ctx->nlocal + ctx->nghost)) { PB_TRY(pb_tile_mirror_all(ctx)); }
+    a.hdrs = ctx->tile_hdrs;
+    a.mxy = ctx->mxy[ctx->mirror_cur]; a.mz = ctx->mz[ctx->mirror_cur];
+    a.mxy_next = ctx->mxy[ctx->mirror_cur ^ 1]; a.mz_next = ctx->mz[ctx->mirror_cur ^ 1];
+    a.flags = ctx->flags; a.type = ctx->type; a.cell_list = ctx->cell_list; a.numneigh = ctx->numneigh;
     a.words = ctx->twords; a.force = ctx->force; a.mass = ctx->mass; a.vel = ctx->vel; a.pos_next = ctx->pos_alt;
     const bool acc = !ctx->force_is_zero;
     const bool uni = ctx->lj_uniform;
@@ -808,8 +925,8 @@ int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
     PB_CHECK(stage_buf.alloc(sizeof(int) * (size_t) n * (size_t) capacity));
     int *const stage = stage_buf.as<int>();
     PB_CHECK(cudaMemsetAsync(stage, 0xff, sizeof(int) * (size_t) n * (size_t) capacity, ctx->stream));      // FIXED particles: no list, all -1
-    PB_LAUNCH(pb_k_tile_export<false>, ctx->ntiles, PB_TILE_M, n, ctx->ncap, ctx->tile_T4, capacity, pb_tile_geom(ctx), ctx->tiles, ctx->cell_start,
-              ctx->cell_list, ctx->twords, ctx->numneigh, stage);
+    PB_LAUNCH(pb_k_tile_export<false>, ctx->ntiles, PB_TILE_M, n, ctx->ncap, ctx->tile_T4, capacity, ctx->tiles, ctx->tile_hdrs, ctx->cell_list,
+              ctx->twords, ctx->numneigh, stage);
     PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(int) * (size_t) n * (size_t) capacity, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -818,7 +935,7 @@ int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
 // the tile lists as 32-bit per-particle lists in the sliced-ELLPACK layout (T slots per particle), for pb_require_neigh32
 int pb_tile_export_ell(pb_ctx *ctx, int *neigh, int T) {
     if(ctx->tiles_n <= 0) { return 0; }
-    PB_LAUNCH(pb_k_tile_export<true>, ctx->ntiles, PB_TILE_M, ctx->tiles_n, ctx->ncap, ctx->tile_T4, T, pb_tile_geom(ctx), ctx->tiles, ctx->cell_start,
-              ctx->cell_list, ctx->twords, ctx->numneigh, neigh);
+    PB_LAUNCH(pb_k_tile_export<true>, ctx->ntiles, PB_TILE_M, ctx->tiles_n, ctx->ncap, ctx->tile_T4, T, ctx->tiles, ctx->tile_hdrs, ctx->cell_list,
+              ctx->twords, ctx->numneigh, neigh);
     return 0;
 }
