@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     for(int k = 0; k < nn; k += U) {
         // the list words of the iteration after the next: into L1 now.  (The loads of the NEXT iteration's words are issued
         // below, but with 62 of 64 registers live the compiler sinks them to the end of the loop body, ~20 instructions before
-        // their use -- ncu r2l: 26 % of the stall samples on that use.  A prefetch has no destination register to economise.)
+        // their use -- ncu r2l: 26 % of the stall samples on that use.  A prefetch has no destination register to economise.
+        // It lands in L2 rather than L1 (ncu r2r: 3 % L1 hit rate of the global loads, the use still draws 14 % of the samples);
+        // a per-thread cp.async ring in shared memory, one iteration ahead, was measured SLOWER: 0.635 vs 0.572 ms.)
         if(k + 2 * U < nn) {
 #pragma unroll
             for(int q = 0; q < W; q++) { asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (size_t) (((k + 2 * U) >> 2) + q) * 32)); }
