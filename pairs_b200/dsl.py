@@ -273,6 +273,8 @@ class Simulation:
         self._compute_half = False
         self.vtk_file = None
         self.vtk_frequency = 0
+        self.ckpt_file = None
+        self.ckpt_frequency = 0
         self._pbc = [True, True, True]
         self.grid = None
         self.reneighbor_frequency = 1            # sim/simulation.py:89
@@ -392,10 +394,113 @@ class Simulation:
         self.vtk_file = filename
         self.vtk_frequency = frequency
 
-    def _vtk_due(self, ts):
+    def checkpoint_output(self, filename, frequency=0):
+        """Checkpoint dump of the per-uid state (the reference reads such files -- runtime/read_from_file.hpp:33-115
+        -- but cannot write them): after every iteration whose number is a multiple of `frequency` each rank writes
+          <filename>_<ts>[_r<rank>].csv    one row per local particle in the reference's CSV layout (Appendix A.3): every non-volatile
+                                           property in the column order the manifest lists (vectors 3 columns, matrices 9,
+                                           quaternions 4), 17 significant digits, i.e. every double survives the round trip
+          <filename>_<ts>[_r<rank>].contacts.csv   DEM: uid_i, uid_j, is_sticking, tangential_spring_displacement x 3,
+                                           impact_velocity_magnitude for every live contact
+          <filename>_<ts>.json             the manifest (columns, iteration, ranks, domain)
+        read_checkpoint(filename, ts) in a later script continues from it, on any number of ranks."""
+        self.ckpt_file = filename
+        self.ckpt_frequency = frequency
+
+    def read_checkpoint(self, filename, ts):
+        self.setups.append(("read_checkpoint", (filename, ts)))
+
+    def _ckpt_due(self, ts):
+        return self.ckpt_file is not None and (self.ckpt_frequency == 0 or ts % self.ckpt_frequency == 0)
+
+    def _vtk_only_due(self, ts):
         return self.vtk_file is not None and (self.vtk_frequency == 0 or ts % self.vtk_frequency == 0)
 
+    def _dumps(self):
+        return self.vtk_file is not None or self.ckpt_file is not None
+
+    def _vtk_due(self, ts):          # "something is written after iteration ts": VTK files and / or a checkpoint
+        return self._vtk_only_due(ts) or self._ckpt_due(ts)
+
+    _CKPT_DEM = (("angvel", "angular_velocity"), ("radius", "radius"), ("inv_inertia", "inv_inertia"), ("rotmat", "rotation_matrix"),
+                 ("quat", "rotation_quat"))
+
+    def _checkpoint_columns(self, ctx, dem):
+        """-> [(property name, host array of the locals)] of everything that is not volatile, in a fixed order"""
+        cols = [("uid", ctx.ints("uid")), ("type", ctx.ints("type")), ("flags", ctx.ints("flags")), ("shape", ctx.ints("shape"))]
+        storage = self._dem_storage() if dem else self._device_storage()
+        nl = ctx.counts()[0]
+        for name, st in storage.items():
+            if name in ("uid", "flags", "shape") or name in self.features:
+                continue
+            if name in self.props and self.props[name].volatile:
+                continue
+            if st == "pos":
+                cols.append((name, ctx.real("position")))
+            elif st == "vel":
+                cols.append((name, ctx.real("linear_velocity")))
+            elif st == "mass":
+                cols.append((name, ctx.real("mass")))
+            elif isinstance(st, tuple):
+                cols.append((name, ctx.download_property(name)))
+            elif dem and st in dict(self._CKPT_DEM):
+                cols.append((name, ctx.dem_download(dict(self._CKPT_DEM)[st], nl)))
+        if dem and "normal" in self.props:
+            cols.append(("normal", ctx.dem_download("normal", nl)))
+        return cols
+
+    def _checkpoint_write(self, ctx, ts, rank, world):
+        import json
+        dem = bool(getattr(ctx, "contact_capacity", 0))
+        cols = self._checkpoint_columns(ctx, dem)
+        infix = f"_r{rank}" if world > 1 else ""
+        table = np.column_stack([np.asarray(a, np.float64).reshape(len(a), -1) for _, a in cols]) if cols[0][1].size else np.zeros((0, 1))
+        np.savetxt(f"{self.ckpt_file}_{ts}{infix}.csv", table, delimiter=",", fmt="%.17g")
+        if dem:
+            c = ctx.dem_download_contacts(ctx.counts()[0])
+            uid = ctx.ints("uid")
+            rows = []
+            for i in np.nonzero(c["num_contacts"])[0]:
+                for k in range(int(c["num_contacts"][i])):
+                    rows.append([uid[i], c["contact_lists"][i, k], c["is_sticking"][i, k], *c["tangential_spring_displacement"][i, k],
+                                 c["impact_velocity_magnitude"][i, k]])
+            np.savetxt(f"{self.ckpt_file}_{ts}{infix}.contacts.csv", np.asarray(rows, np.float64).reshape(len(rows), 7), delimiter=",", fmt="%.17g")
+        if rank == 0:
+            manifest = {"iteration": ts, "ranks": world, "dem": dem, "domain": list(self.grid),
+                        "columns": [[n, int(np.asarray(a).reshape(len(a), -1).shape[1]) if len(a) else 1, "int" if np.asarray(a).dtype.kind == "i" else "real"]
+                                    for n, a in cols]}
+            with open(f"{self.ckpt_file}_{ts}.json", "w") as f:
+                json.dump(manifest, f)
+
+    def _checkpoint_read(self, ctx, filename, ts):
+        """-> dict of host arrays (this rank's rows) + 'contacts' (DEM) of the checkpoint written after iteration ts"""
+        import json
+        with open(f"{filename}_{ts}.json") as f:
+            man = json.load(f)
+        files = [f"{filename}_{ts}"] if man["ranks"] == 1 else [f"{filename}_{ts}_r{r}" for r in range(man["ranks"])]
+        tables = [np.loadtxt(fn + ".csv", delimiter=",", ndmin=2) for fn in files]
+        tables = [t for t in tables if t.size]
+        data = np.concatenate(tables) if tables else np.zeros((0, sum(w for _, w, _ in man["columns"])))
+        part, k = {}, 0
+        for name, w, kind in man["columns"]:
+            col = data[:, k:k + w] if w > 1 else data[:, k]
+            part[name] = col.astype(np.int32) if kind == "int" else np.ascontiguousarray(col)
+            k += w
+        if self.position_name not in part:
+            raise DslError(f"checkpoint {filename}_{ts}: no column for the position property '{self.position_name}'")
+        part["position"] = part[self.position_name]
+        part = self._keep_own(ctx, part)
+        if man["dem"]:
+            rows = [np.loadtxt(fn + ".contacts.csv", delimiter=",", ndmin=2) for fn in files if os.path.exists(fn + ".contacts.csv")]
+            rows = [r for r in rows if r.size]
+            part["contacts"] = np.concatenate(rows) if rows else np.zeros((0, 7))
+        return part
+
     def _vtk_write(self, ctx, ts, rank, world):
+        if self._ckpt_due(ts):
+            self._checkpoint_write(ctx, ts, rank, world)
+        if not self._vtk_only_due(ts):
+            return
         nl, ng = ctx.counts()
         pos, mass, flags = ctx.real("position", True), ctx.real("mass", True), ctx.ints("flags", True)
         infix = f"r{rank}_" if world > 1 else ""
@@ -590,6 +695,17 @@ class Simulation:
                 ctx.adjust_thermo(temp)
             elif kind == "read_particle_data":
                 nlocal = self._read_particle_data(ctx, *args)
+            elif kind == "read_checkpoint":
+                part = self._checkpoint_read(ctx, *args)
+                storage = self._device_storage()
+                vel_name = next((n for n in part if storage.get(n) == "vel"), None)
+                mass_name = next((n for n in part if storage.get(n) == "mass"), None)
+                ctx.upload(part["position"], part.get(vel_name), part.get(mass_name), part.get("type"), part.get("flags"), part.get("uid"),
+                           part.get("shape"))
+                for name, st in storage.items():
+                    if isinstance(st, tuple) and name in part:
+                        ctx.upload_property(name, part[name])
+                nlocal = len(part["position"])
         ctx.setup_cells(self._cell_spacing)
         for e in self.setup_functions:          # setup() functions: once over the locals, right after the set-up statements
             if e["family"] != "generic_setup":
@@ -607,7 +723,7 @@ class Simulation:
         nsteps = self.ntimesteps + 1
         if native is not None:
             # one native call per stretch between two VTK dumps (chunked calls are bit-identical to one call)
-            cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
+            cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self._dumps() else []
             begin = 0
             for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
                 th = ctx.md_run(begin, end, *native)
@@ -674,6 +790,10 @@ class Simulation:
                     self._dem_banner(args, len(g["uid"]))
             elif kind == "read_particle_data":
                 parts.append(self._keep_own(ctx, self._read_csv(*args)))
+            elif kind == "read_checkpoint":
+                if parts:
+                    raise DslError("DEM: read_checkpoint() must be the only set-up statement (it restores every particle)")
+                parts.append(self._checkpoint_read(ctx, *args))
             else:
                 raise DslError(f"DEM: unsupported set-up statement {kind}")
         n = sum(len(p["position"]) for p in parts)
@@ -692,6 +812,29 @@ class Simulation:
                    cat("type", 1, np.int32), cat("flags", 1, np.int32), cat("uid", 1, np.int32), cat("shape", 1, np.int32))
         ctx.dem_upload("radius", cat("radius", 1, np.float64))
         ctx.dem_upload("normal", cat("normal", 3, np.float64))
+        restored = parts[0] if len(parts) == 1 and "contacts" in parts[0] else None
+        if restored is not None:            # a checkpoint: the rigid-body state and the contact history come back as well
+            for _, canon in self._CKPT_DEM:
+                if canon in restored and canon != "radius":
+                    ctx.dem_upload(canon, restored[canon])
+            for name, st in self._dem_storage().items():
+                if isinstance(st, tuple) and name in restored:
+                    ctx.upload_property(name, restored[name])
+            C = ctx.contact_capacity
+            num = np.zeros(n, np.int32)
+            cuid, stick = np.zeros((n, C), np.int32), np.zeros((n, C), np.int32)
+            tsd, ivm = np.zeros((n, C, 3)), np.zeros((n, C))
+            row_of = {int(u): k for k, u in enumerate(restored["uid"])}
+            for r in restored["contacts"]:
+                i = row_of.get(int(r[0]))
+                if i is None:            # the owner of this contact row lives on another rank now
+                    continue
+                k = num[i]
+                if k >= C:
+                    raise DslError("read_checkpoint: more contacts per particle than the contact capacity (neighbor_capacity)")
+                cuid[i, k], stick[i, k], tsd[i, k], ivm[i, k] = int(r[1]), int(r[2]), r[3:6], r[6]
+                num[i] = k + 1
+            ctx.dem_upload_contacts(num, cuid, stick, tsd, ivm)
         for f in self.setup_functions:
             if f["family"] == "update_mass_and_inertia":
                 ctx.dem_stage("update_mass_and_inertia")
@@ -707,7 +850,7 @@ class Simulation:
         t0 = time.perf_counter()
         nsteps = self.ntimesteps + 1
         if standard:
-            cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self.vtk_file is not None else []
+            cuts = [ts + 1 for ts in range(nsteps) if self._vtk_due(ts)] if self._dumps() else []
             begin = 0
             for end in cuts + ([nsteps] if not cuts or cuts[-1] != nsteps else []):
                 ctx.dem_run(self._cell_spacing, begin, end)

@@ -94,7 +94,8 @@ def gravity(i):
     force[i][2] = force[i][2] - (densityParticle_SI - densityFluid_SI) * volume * gravity_SI
 
 
-def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None, reneighbor=None):
+def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None, reneighbor=None,
+          checkpoint=None, restart=None):
     diameter_SI, gravity_SI, densityFluid_SI, densityParticle_SI = 0.0029, 9.81, 1000, 2550
     generationSpacing_SI, initialVelocity_SI, dt_SI = 0.005, 1, 5e-5
     frictionCoefficient, restitutionCoefficient, collisionTime_SI, poissonsRatio = 0.5, 0.1, 5e-4, 0.22
@@ -127,9 +128,12 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
     psim.set_domain([0.0, 0.0, 0.0, domain[0], domain[1], domain[2]])
     psim.set_domain_partitioner(pairs.regular_domain_partitioner_xy())
     psim.pbc([True, True, False])
-    psim.dem_sc_grid(domain[0], domain[1], domain[2], generationSpacing_SI, diameter_SI, minDiameter_SI, maxDiameter_SI,
-                     initialVelocity_SI, densityParticle_SI, ntypes)
-    if planes_file is None:
+    if restart is not None:          # continue from a checkpoint: no generator, no plane file, no update_mass_and_inertia (it would
+        psim.read_checkpoint(*restart)          # reset the orientations)
+    else:
+        psim.dem_sc_grid(domain[0], domain[1], domain[2], generationSpacing_SI, diameter_SI, minDiameter_SI, maxDiameter_SI,
+                         initialVelocity_SI, densityParticle_SI, ntypes)
+    if restart is None and planes_file is None:
         # the two half-spaces examples/dem.py reads from data/planes.input (uid, type, mass, position, normal, flags): floor at the
         # origin, ceiling at the corner of the stock 0.8 x 0.015 x 0.2 box; infinite | fixed | global
         import tempfile
@@ -138,9 +142,12 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
         with os.fdopen(fd, "w") as f:
             for uid, typ, m, x, nrm, fl in rows:
                 f.write(",".join(str(v) for v in (uid, typ, m, *x, *nrm, fl)) + "\n")
-    psim.read_particle_data(planes_file,
-                            ['uid', 'type', 'mass', 'position', 'normal', 'flags'], pairs.halfspace())
-    psim.setup(update_mass_and_inertia, {'densityParticle_SI': densityParticle_SI, 'pi': math.pi, 'infinity': math.inf})
+    if restart is None:
+        psim.read_particle_data(planes_file,
+                                ['uid', 'type', 'mass', 'position', 'normal', 'flags'], pairs.halfspace())
+        psim.setup(update_mass_and_inertia, {'densityParticle_SI': densityParticle_SI, 'pi': math.pi, 'infinity': math.inf})
+    if checkpoint is not None:
+        psim.checkpoint_output(checkpoint[0], checkpoint[1])
     if per_cell:
         psim.build_cell_lists(linkedCellWidth, store_neighbors_per_cell=True)
     else:

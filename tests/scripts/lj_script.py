@@ -20,7 +20,7 @@ def final_integrate(i):
     linear_velocity[i] += (dt * 0.5) * force[i] / mass[i]
 
 
-def build(target="gpu", nx=8, timesteps=100, reneighbor=20, thermo=10, ntypes=4, cells_only=False):
+def build(target="gpu", nx=8, timesteps=100, reneighbor=20, thermo=10, ntypes=4, cells_only=False, checkpoint=None, restart=None):
     dt = 0.005
     cutoff_radius = 2.5
     skin = 0.3
@@ -33,7 +33,14 @@ def build(target="gpu", nx=8, timesteps=100, reneighbor=20, thermo=10, ntypes=4,
     psim.add_feature('type', ntypes)
     psim.add_feature_property('type', 'epsilon', pairs.real(), [1.0 for _ in range(ntypes * ntypes)])
     psim.add_feature_property('type', 'sigma6', pairs.real(), [1.0 for _ in range(ntypes * ntypes)])
-    psim.copper_fcc_lattice(nx, nx, nx, 0.8442, 1.44, ntypes)
+    if restart is not None:          # continue from a checkpoint written by checkpoint_output()
+        a = pow(4.0 / 0.8442, 1.0 / 3.0)
+        psim.set_domain([0.0, 0.0, 0.0, nx * a, nx * a, nx * a])
+        psim.read_checkpoint(*restart)
+    else:
+        psim.copper_fcc_lattice(nx, nx, nx, 0.8442, 1.44, ntypes)
+    if checkpoint is not None:
+        psim.checkpoint_output(checkpoint[0], checkpoint[1])
     psim.set_domain_partitioner(pairs.regular_domain_partitioner())
     psim.compute_thermo(thermo)
     psim.reneighbor_every(reneighbor)

@@ -451,3 +451,69 @@ def test_recognised_kernels_keep_their_family_only_on_the_arrays_they_were_writt
     assert psim.functions[-1]["family"] == "initial_integrate" and psim.functions[-1]["roles"]["velocity"] == "path"
     psim._reclassify()
     assert [e["family"] for e in psim.functions] == ["lennard_jones", "final_integrate", "generic_particle"]
+
+
+def test_checkpoint_files_round_trip_every_bit_and_split_over_ranks(tmp_path):
+    """checkpoint_output() / read_checkpoint() host side with a stand-in context: two ranks write their locals (plus DEM contact rows),
+    one rank -- and, separately, two other sub-boxes -- read them back: every double bit for bit, every row exactly once, contact rows
+    with their owner."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10)
+    psim._reclassify()
+    psim.checkpoint_output(str(tmp_path / "ck"), 5)
+    assert psim._vtk_due(5) and psim._vtk_due(10) and not psim._vtk_due(7)
+    rng = np.random.default_rng(3)
+    C = 20
+
+    class FakeCtx:
+        contact_capacity = C
+
+        def __init__(self, n, lo, hi, seed):
+            r = np.random.default_rng(seed)
+            self.n, self.lo, self.hi = n, lo, hi
+            self.pos = np.column_stack([lo + (hi - lo) * r.random(n), 0.015 * r.random(n), 0.04 * r.random(n)])
+            self.arr = {k: r.standard_normal((n, w)).squeeze() * 1e-3 for k, w in
+                        (("linear_velocity", 3), ("mass", 1), ("angular_velocity", 3), ("radius", 1), ("inv_inertia", 9),
+                         ("rotation_matrix", 9), ("rotation_quat", 4), ("normal", 3))}
+            self.i = {"uid": np.arange(n, dtype=np.int32) + 1000 * seed, "type": np.zeros(n, np.int32), "flags": np.zeros(n, np.int32),
+                      "shape": np.zeros(n, np.int32)}
+            self.num = r.integers(0, 4, n).astype(np.int32)
+
+        def counts(self):
+            return self.n, 0
+
+        def ints(self, name):
+            return self.i[name]
+
+        def real(self, name):
+            return self.pos if name == "position" else self.arr[name]
+
+        def dem_download(self, name, n):
+            return self.arr[name]
+
+        def dem_download_contacts(self, n):
+            r = np.random.default_rng(7)
+            return {"num_contacts": self.num, "contact_lists": r.integers(1, 999, (n, C)).astype(np.int32),
+                    "is_sticking": r.integers(0, 2, (n, C)).astype(np.int32), "tangential_spring_displacement": r.standard_normal((n, C, 3)),
+                    "impact_velocity_magnitude": r.standard_normal((n, C))}
+
+        def decomposition(self):
+            return {"nranks": np.array([2 if self.hi - self.lo < 0.09 else 1, 1, 1]), "subdom": np.array([self.lo, self.hi, 0.0, 0.015, 0.0, 0.04])}
+
+    a, b = FakeCtx(7, 0.0, 0.05, 1), FakeCtx(5, 0.05, 0.1, 2)
+    psim._checkpoint_write(a, 5, 0, 2)
+    psim._checkpoint_write(b, 5, 1, 2)
+    whole = psim._checkpoint_read(FakeCtx(0, 0.0, 0.1, 9), str(tmp_path / "ck"), 5)
+    assert np.array_equal(whole["uid"], np.concatenate([a.i["uid"], b.i["uid"]]))
+    assert np.array_equal(whole["position"], np.concatenate([a.pos, b.pos]))                 # bit for bit through "%.17g"
+    for k in ("linear_velocity", "angular_velocity", "inv_inertia", "rotation_quat", "radius", "mass"):
+        assert np.array_equal(whole[k], np.concatenate([a.arr[k], b.arr[k]])), k
+    assert len(whole["contacts"]) == int(a.num.sum() + b.num.sum())
+    assert set(whole["contacts"][:, 0].astype(int)) <= set(whole["uid"].tolist())
+    # re-split on other sub-boxes: every row lands on exactly one rank
+    left = psim._checkpoint_read(FakeCtx(0, 0.0, 0.03, 9), str(tmp_path / "ck"), 5)
+    right = psim._checkpoint_read(FakeCtx(0, 0.03, 0.1, 9), str(tmp_path / "ck"), 5)
+    assert len(left["uid"]) + len(right["uid"]) >= len(whole["uid"]) - 1            # (a row within 1e-5 of the cut belongs to nobody,
+    assert not set(left["uid"].tolist()) & set(right["uid"].tolist())               #  as in runtime/read_from_file.hpp:106)
+    assert rng is not None
