@@ -160,6 +160,11 @@ int pb_dem_gravity(pb_ctx *ctx);
 int pb_dem_linear_spring_dashpot(pb_ctx *ctx);
 int pb_dem_euler(pb_ctx *ctx);
 int pb_dem_contact_overflow(pb_ctx *ctx);
+/* contact-capacity growth (the reference's resize protocol for the contact-history arrays, transformations/modules.py:159-203):
+   reads the contact kernel's high-water mark and doubles the capacity (all ranks together, <= 64) once a row is nearly full;
+   < 0 if a contact was lost before that.  pb_dem_run calls it every 8 iterations; module-by-module loops call it themselves. */
+int pb_dem_check_contacts(pb_ctx *ctx);
+int pb_dem_contact_capacity(const pb_ctx *ctx);
 int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts_end);
 
 /* multi-GPU: NCCL communicator over the ranks of pb_init_domain.  id = 128-byte ncclUniqueId made by rank 0

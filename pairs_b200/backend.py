@@ -139,6 +139,8 @@ SIGNATURES = {
     "pb_dem_linear_spring_dashpot": (_I, [_P]),
     "pb_dem_euler": (_I, [_P]),
     "pb_dem_contact_overflow": (_I, [_P]),
+    "pb_dem_check_contacts": (_I, [_P]),
+    "pb_dem_contact_capacity": (_I, [_P]),
     "pb_dem_run": (_I, [_P, _D, _I, _I]),
     "pb_nccl_unique_id": (_I, [_P]),
     "pb_nccl_init": (_I, [_P, _P]),
@@ -386,7 +388,15 @@ class Context:
 
     def dem_enable(self, contact_capacity=20):
         self._ck(self.lib.pb_dem_enable(self.h, contact_capacity))
-        self.contact_capacity = contact_capacity
+        self._dem = True
+
+    @property
+    def contact_capacity(self):
+        """slots per contact row (0: not a DEM context); grows when a row comes close to full (pb_dem_check_contacts)"""
+        return int(self.lib.pb_dem_contact_capacity(self.h)) if getattr(self, "_dem", False) else 0
+
+    def dem_check_contacts(self):
+        self._ck(self.lib.pb_dem_check_contacts(self.h))
 
     def dem_set_params(self, dt, pi, kappa, ln_dry_res_coeff, collision_time, density_particle, density_fluid, gravity, ntypes,
                        friction_static, friction_dynamic):

@@ -17,6 +17,10 @@
 #define PB_DEM_DEFAULT_IVM 0.0
 #endif
 
+#ifndef PB_DEM_CONTACT_MARGIN
+#define PB_DEM_CONTACT_MARGIN 4      // free slots below which a contact row counts as "nearly full"
+#endif
+
 struct PbDemForceArgs {
     int nlocal, cap, C, ntypes;
     PbDemParams P;
@@ -118,6 +122,8 @@ __device__ __forceinline__ void pb_dem_force_body(const PbDemForceArgs &a) {
             for(int d = 0; d < 3; d++) { F[d] = F[d] + Fp[d]; T[d] = T[d] + Tp[d]; }
         }
         if(FUSED) { ncont_end = ncont; } else { num_contacts[i] = ncont; }
+        // high-water mark of the contact rows: the host grows the capacity AHEAD of need (pb_dem_check_contacts)
+        if(ncont + PB_DEM_CONTACT_MARGIN > C) { atomicMax(overflow + 1, ncont); }
     }
     if(FUSED) {
         // clear_unused_contact_history (sim/contact_history.py:90-127): an unused slot is overwritten by the last one

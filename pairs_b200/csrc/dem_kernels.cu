@@ -23,6 +23,8 @@
 #include <string>
 #include <vector>
 
+#include <type_traits>
+
 #include "ctx.cuh"
 #include "dem_math.h"
 
@@ -764,6 +766,73 @@ static int pb_dem_contacts_fused(pb_ctx *ctx) {
     return 0;
 }
 
+// Contact-capacity growth (the reference's resize protocol for `neighbor_capacity` of a contact-history simulation,
+// transformations/modules.py:159-203, re-runs the module after growing; the fused contact kernel cannot be re-run, so the
+// capacity grows AHEAD of need): the contact kernel records the fullest row it has seen once a row comes within
+// PB_DEM_CONTACT_MARGIN slots of the capacity; the loops check that mark (pb_dem_check_contacts) and double the capacity -- all
+// ranks together, the wire record of a migrating particle holds its whole row -- up to the 64 slots the kernels support.
+int pb_allreduce_sum(pb_ctx *ctx, double *vals, int n);      // comm_nccl.cu
+
+static int pb_dem_grow_contacts(pb_ctx *ctx, int newC) {
+    const size_t C = (size_t) ctx->ccontacts, cap = (size_t) ctx->pcap, NC = (size_t) newC;
+    auto grow = [&](auto **p, int blocks) -> int {
+        using T = std::remove_pointer_t<std::remove_pointer_t<decltype(p)>>;
+        T *q = nullptr;
+        PB_CHECK(cudaMalloc(&q, sizeof(T) * blocks * NC * cap));
+        PB_CHECK(cudaMemsetAsync(q, 0, sizeof(T) * blocks * NC * cap, ctx->stream));
+        if(*p != nullptr) {
+            for(int b = 0; b < blocks; b++) {      // [block][slot][particle]: the old slots are the first C of every block
+                PB_CHECK(cudaMemcpyAsync(q + (size_t) b * NC * cap, *p + (size_t) b * C * cap, sizeof(T) * C * cap, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        PB_CHECK(cudaStreamSynchronize(ctx->stream));
+        if(*p != nullptr) { PB_CHECK(cudaFree(*p)); }
+        *p = q;
+        return 0;
+    };
+    if(cap > 0) {
+        PB_TRY(grow(&ctx->contact_uid, 1));
+        PB_TRY(grow(&ctx->contact_used, 1));
+        PB_TRY(grow(&ctx->contact_stick, 1));
+        PB_TRY(grow(&ctx->contact_ivm, 1));
+        PB_TRY(grow(&ctx->contact_tsd, 3));
+    }
+    ctx->ccontacts = newC;
+    if(ctx->send_cap > 0) {        // the wire records grew with the rows
+        const int keep = ctx->send_cap;
+        ctx->send_cap = 0;
+        PB_TRY(pb_ensure_send_capacity(ctx, keep));
+    }
+    if(ctx->recv_buf != nullptr) { PB_CHECK(cudaFree(ctx->recv_buf)); ctx->recv_buf = nullptr; ctx->recv_cap = 0; }
+    return 0;
+}
+
+extern "C" int pb_dem_contact_capacity(const pb_ctx *ctx) { return ctx->ccontacts; }
+
+// 0: fine (possibly after growing); < 0: a contact was lost before the capacity could grow
+extern "C" int pb_dem_check_contacts(pb_ctx *ctx) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem) { return 0; }
+    PB_CHECK(cudaMemcpyAsync(ctx->h_scalars, ctx->d_dem_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemsetAsync(ctx->d_dem_flag, 0, 2 * sizeof(int), ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    double v[2] = {(double) ctx->h_scalars[0], (ctx->h_scalars[1] + PB_DEM_CONTACT_MARGIN > ctx->ccontacts) ? 1.0 : 0.0};
+    double lost = v[0];
+    if(ctx->world > 1) {
+        double s[2] = {v[0] > 0.0 ? 1.0 : 0.0, v[1]};
+        PB_TRY(pb_allreduce_sum(ctx, s, 2));
+        lost = (s[0] > 0.0) ? std::max(v[0], 1.0) : 0.0;
+        v[1] = s[1];
+    }
+    if(lost > 0.0) {
+        ctx->set_error("contact capacity exceeded: a particle needed " + std::to_string((int) lost) + " contact slots before the capacity (" +
+                       std::to_string(ctx->ccontacts) + ") could grow -- raise neighbor_capacity of pairs.simulation()");
+        return -1;
+    }
+    if(v[1] > 0.0 && ctx->ccontacts < 64) { PB_TRY(pb_dem_grow_contacts(ctx, std::min(64, ctx->ccontacts * 2))); }
+    return 0;
+}
+
 // returns > 0 (needed capacity) if a particle ran out of contact slots since the last check (the mark is read and cleared)
 extern "C" int pb_dem_contact_overflow(pb_ctx *ctx) {
     PB_CHECK(cudaSetDevice(ctx->device));
@@ -828,8 +897,7 @@ extern "C" int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts
             PB_TRY(pb_dem_euler(ctx));
             PB_TRY(pb_dem_clear_unused_contacts(ctx));
         }
+        if(((ts + 1) & 7) == 0) { PB_TRY(pb_dem_check_contacts(ctx)); }      // contact rows nearly full: grow ahead of need
     }
-    const int need = pb_dem_contact_overflow(ctx);
-    if(need > 0) { ctx->set_error("contact capacity exceeded: a particle needs " + std::to_string(need) + " contact slots"); return -1; }
-    return 0;
+    return pb_dem_check_contacts(ctx);
 }

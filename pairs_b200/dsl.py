@@ -929,11 +929,9 @@ class Simulation:
                 if ts > 0 or not e["skip_first"]:
                     call()
             ctx.dem_stage("clear_unused_contacts")
+            ctx.dem_check_contacts()          # contact rows nearly full: the capacity grows ahead of need (csrc/dem_kernels.cu)
             if self._vtk_due(ts):
                 self._vtk_write(ctx, ts, rank, world)
-        need = ctx.lib.pb_dem_contact_overflow(ctx.h)
-        if need > 0:
-            raise DslError(f"contact capacity exceeded: a particle needs {need} contact slots (neighbor_capacity of pairs.simulation())")
 
     def _translate_dem_model(self, e):
         """-> (function name, CUDA source, number of types) of a user-defined contact model (kernelgen.translate_dem_model).  The

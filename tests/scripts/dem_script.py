@@ -95,7 +95,7 @@ def gravity(i):
 
 
 def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None, reneighbor=None,
-          checkpoint=None, restart=None):
+          checkpoint=None, restart=None, contact_capacity=20):
     diameter_SI, gravity_SI, densityFluid_SI, densityParticle_SI = 0.0029, 9.81, 1000, 2550
     generationSpacing_SI, initialVelocity_SI, dt_SI = 0.005, 1, 5e-5
     frictionCoefficient, restitutionCoefficient, collisionTime_SI, poissonsRatio = 0.5, 0.1, 5e-4, 0.22
@@ -106,7 +106,7 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
     lnDryResCoeff = math.log(restitutionCoefficient)
 
     psim = pairs.simulation("dem", [pairs.sphere(), pairs.halfspace()], timesteps=timesteps, double_prec=True,
-                            use_contact_history=True, particle_capacity=1000000, neighbor_capacity=20)
+                            use_contact_history=True, particle_capacity=1000000, neighbor_capacity=contact_capacity)
     psim.target(pairs.target_gpu() if target == "gpu" else pairs.target_cpu())
     psim.add_position('position')
     psim.add_property('mass', pairs.real(), 1.0)

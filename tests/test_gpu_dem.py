@@ -215,3 +215,28 @@ def test_fused_dem_loop_is_bit_identical_to_the_staged_one():
                 assert np.array_equal(a[k][i, :m], b[k][i, :m]), (k, i)
         else:
             assert np.array_equal(a[k], b[k]), k
+
+
+def test_contact_capacity_grows_ahead_of_need(capsys):
+    """neighbor_capacity of a contact-history simulation is the capacity of the contact rows; the reference grows such capacities
+    through its resize protocol (transformations/modules.py:159-203).  Here the rows grow when one comes within four slots of the
+    capacity: a run that starts with 6 slots per particle ends in the bits of the run with dem.py's 20."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "scripts"))
+    import dem_script
+    small = dem_script.build("gpu", dc.DOMAIN, 300, contact_capacity=6).generate()
+    stock = dem_script.build("gpu", dc.DOMAIN, 300).generate()
+    capsys.readouterr()
+    assert small.contact_capacity >= 12 and stock.contact_capacity == 20
+    n = stock.counts()[0]
+    assert np.array_equal(small.ints("uid"), stock.ints("uid"))
+    for name in ("position", "linear_velocity"):
+        assert np.array_equal(small.real(name), stock.real(name)), name
+    a, b = small.dem_download_contacts(n), stock.dem_download_contacts(n)
+    assert np.array_equal(a["num_contacts"], b["num_contacts"]) and a["num_contacts"].max() >= 3
+    C = 6
+    for k in ("contact_lists", "is_sticking", "impact_velocity_magnitude", "tangential_spring_displacement"):
+        m = np.arange(a[k].shape[1])[None, :] < a["num_contacts"][:, None]
+        assert np.array_equal(a[k][m], b[k][:, :a[k].shape[1]][m]), k
+    assert C < small.contact_capacity
