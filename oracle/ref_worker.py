@@ -57,6 +57,15 @@ def dump_dem(variant, out_path, max_steps, keep):
     return np.load(out_path)
 
 
+def dump_dem_end(variant, out_path, ts, names):
+    """State at the end of iteration ts of a DEM program, the listed arrays only (fresh process); returns the loaded npz."""
+    p = spawn(["dump_dem_end", variant, out_path, ts, ",".join(names)])
+    out, err = p.communicate()
+    if p.returncode != 0:
+        raise RuntimeError(f"ref_worker dump_dem_end failed:\n{out[-3000:]}\n{err[-3000:]}")
+    return np.load(out_path)
+
+
 def bench_many(variant, warmup, steps, replicas):
     """`replicas` concurrent fresh processes, each timing `steps` loop iterations after `warmup`; list of results."""
     procs = [spawn(["bench", variant, warmup, steps]) for _ in range(replicas)]
@@ -127,6 +136,43 @@ def _main(argv):
         d["nlocal"] = np.array(d["nlocal"])
         d["nghost"] = np.array(d["nghost"])
         np.savez_compressed(out_path, **d)
+        return 0
+    if mode == "dump_dem_end":
+        # argv: dump_dem_end <variant> <out.npz> <ts> <name,name,...>  -- the state at the END of iteration ts, the listed arrays only
+        # (the full-size cases: a complete dem_state of 10^6 particles is 1.2 GB)
+        out_path, last = argv[2], int(argv[3])
+        names = [x for x in argv[4].split(",") if x]
+        os.chdir(os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref"))
+        st = {"ts": 0}
+        d = {}
+        widths = dict(RefProgram.DEM_REAL)
+
+        def on_event(ev, a):
+            if ev != "thermo":
+                return
+            if st["ts"] == last:
+                n = a
+                d["nlocal"] = np.array([n])
+                d["nghost"] = np.array([int(prog.array("nrecv", np.int32, 6).sum())])
+                for k in names:
+                    if k in widths:
+                        d[k] = prog.prop(k, n, widths[k])
+                    elif k in RefProgram.DEM_INT:
+                        d[k] = prog.prop(k, n, 1, np.int32)
+                    elif k == "contact_lists":
+                        d[k] = prog.array(k, np.int32, n * 20).reshape(n, 20)
+                    elif k == "is_sticking":
+                        d[k] = prog.contact_prop(k, n * 20, 1, np.int32).reshape(n, 20)
+                    else:
+                        d[k] = prog.array(k, np.int32, n)
+            st["ts"] += 1
+
+        import oracle.ref as _r
+        cb = _r.HOOK(lambda ev, a, _u: on_event(ev.decode(), a))
+        prog.lib.ref_set_limit.argtypes = [ctypes.c_int]
+        prog.lib.ref_set_limit(last + 1)
+        prog.lib.ref_run(cb, None, 1)
+        np.savez(out_path, **d)
         return 0
     if mode == "bench":
         warmup, steps = int(argv[2]), int(argv[3])

@@ -164,3 +164,88 @@ def test_config_c2_four_million_atoms_against_the_oracle():
     for name, tol in (("position", 1e-13), ("linear_velocity", 1e-12), ("force", 1e-12)):
         a, b = ctx.real(name)[o2], r.real(name)[u2]
         assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300) or np.abs(a - b).max() <= 1e-12, name
+
+
+def _dem_c3():
+    """BASELINE configs[2]: examples/dem.py on the 0.8 x 0.8 x 0.2 m box, 998,400 spheres + 2 half-spaces (bench.py --workload dem)."""
+    import math
+    from pairs_b200.backend import Context
+    from tests import dem_common as dc
+    domain = (0.8, 0.8, 0.2)
+    ctx = Context(0)
+    ctx.init_domain([0.0, domain[0], 0.0, domain[1], 0.0, domain[2]], pbc=(1, 1, 0), partitioner=1)
+    ctx.dem_enable(dc.C)
+    ctx.dem_set_params(dc.DT, math.pi, dc.KAPPA, dc.LN_DRY, dc.COLLISION_TIME, dc.RHO_P, dc.RHO_F, dc.G, dc.NTYPES, dc.FS, dc.FD)
+    ctx.setup_cells(dc.CELL)
+    g = ctx.dem_sc_grid(domain[0], domain[1], domain[2], dc.SPACING, dc.DIAMETER, dc.MIN_D, dc.MAX_D, dc.V0, dc.RHO_P, dc.NTYPES)
+    ns = len(g["uid"])
+    n = ns + 2
+    pos, vel, normal = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+    mass, radius = np.ones(n), np.zeros(n)
+    uid, typ, flags, shape = (np.zeros(n, np.int32) for _ in range(4))
+    pos[:ns], vel[:ns], mass[:ns], radius[:ns], uid[:ns], typ[:ns] = g["position"], g["linear_velocity"], g["mass"], g["radius"], g["uid"], g["type"]
+    # data/planes.input of the reference with the ceiling at the corner of THIS box (what oracle/build_ref.py writes for dem_bench)
+    for k, (u, p_, nrm) in enumerate([(100000, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0)), (100001, domain, (0.0, 0.0, -1.0))]):
+        uid[ns + k], pos[ns + k], normal[ns + k], flags[ns + k], shape[ns + k] = u, p_, nrm, 13, 1
+    ctx.upload(pos, vel, mass, typ, flags, uid, shape)
+    ctx.dem_upload("radius", radius)
+    ctx.dem_upload("normal", normal)
+    ctx.dem_stage("update_mass_and_inertia")
+    return ctx, n, dc
+
+
+def test_config_c3_one_million_spheres_against_the_reference(tmp_path):
+    """C3 at size against the reference's OWN generated C++ (oracle/_ref variant dem_bench, run here on a host core): after 21
+    iterations of the loop the same particles in the same order, bit-identical positions and linear velocities, the same ghost
+    count, the same cell of every particle, empty contact rows on both sides (the bed has not formed yet: the settled bed is
+    covered by invariants below and, against the reference, on the 420-sphere case of tests/test_gpu_dem.py)."""
+    from oracle import ref, ref_worker
+    if not ref.available("dem_bench"):
+        pytest.skip("oracle/_ref variant dem_bench not built")
+    last = 20
+    z = ref_worker.dump_dem_end("dem_bench", str(tmp_path / "c3.npz"), last, ["position", "linear_velocity", "uid", "num_contacts", "particle_cell"])
+    ctx, n, dc = _dem_c3()
+    ctx.dem_run(dc.CELL, 0, last + 1)
+    nl, ng = ctx.counts()
+    assert (nl, ng) == (int(z["nlocal"][0]), int(z["nghost"][0])) and nl == n == 998402
+    assert np.array_equal(ctx.ints("uid"), z["uid"])                        # DEM keeps the particle order (no re-sort before 200)
+    assert np.array_equal(ctx.real("position"), z["position"])               # bit for bit: the linear part of euler
+    assert np.array_equal(ctx.real("linear_velocity"), z["linear_velocity"])
+    assert np.array_equal(ctx.ints("particle_cell"), z["particle_cell"])
+    c = ctx.dem_download_contacts(nl)
+    assert not c["num_contacts"].any() and not z["num_contacts"].any()
+
+
+def test_config_c3_settled_bed_invariants():
+    """C3 at size, 4000 iterations (the bed has formed: ~5 contacts per sphere).  Properties that hold whatever the size: nothing is
+    lost or duplicated, every sphere lies between the two planes, contact rows are symmetric (j in the row of i <=> i in the row
+    of j, for sphere-sphere contacts), partners of a contact touch or nearly touch, no row exceeds the capacity."""
+    ctx, n, dc = _dem_c3()
+    ctx.dem_run(dc.CELL, 0, 4000)
+    nl, _ = ctx.counts()
+    assert nl == n
+    uid = ctx.ints("uid")
+    assert len(np.unique(uid)) == n
+    pos, shape = ctx.real("position"), ctx.ints("shape")
+    sph = shape == 0
+    radius = ctx.dem_download("radius", nl)
+    assert np.isfinite(pos[sph]).all() and (pos[sph, 2] > -1e-4).all() and (pos[sph, 2] < 0.2).all()
+    c = ctx.dem_download_contacts(nl)
+    num, lists = c["num_contacts"], c["contact_lists"]
+    assert num.max() <= dc.C and 3.0 < num[sph].mean() < 8.0
+    row_of = np.full(int(uid.max()) + 1, -1, np.int64)
+    row_of[uid] = np.arange(n)
+    m = np.arange(lists.shape[1])[None, :] < num[:, None]
+    i_idx = np.broadcast_to(np.arange(n)[:, None], lists.shape)[m]
+    j_idx = row_of[lists[m]]
+    assert (j_idx >= 0).all()
+    both = sph[i_idx] & sph[j_idx]                                            # (the half-spaces are FIXED: they keep no rows)
+    a, b = i_idx[both], j_idx[both]
+    fwd = np.unique(a.astype(np.int64) * n + b)
+    bwd = np.unique(b.astype(np.int64) * n + a)
+    assert np.array_equal(fwd, bwd)
+    d = pos[a] - pos[b]
+    d[:, 0] -= 0.8 * np.round(d[:, 0] / 0.8)                                  # periodic in x and y
+    d[:, 1] -= 0.8 * np.round(d[:, 1] / 0.8)
+    gap = np.sqrt((d * d).sum(axis=1)) - radius[a] - radius[b]
+    assert gap.max() < 0.05 * dc.DIAMETER                                      # a row entry outlives the contact by at most one step
