@@ -166,7 +166,7 @@ def test_config_c2_four_million_atoms_against_the_oracle():
         assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-300) or np.abs(a - b).max() <= 1e-12, name
 
 
-def _dem_c3():
+def _dem_c3(plane_uids=(100000, 100001), ceiling_at=(0.8, 0.015, 0.2)):
     """BASELINE configs[2]: examples/dem.py on the 0.8 x 0.8 x 0.2 m box, 998,400 spheres + 2 half-spaces (bench.py --workload dem)."""
     import math
     from pairs_b200.backend import Context
@@ -184,8 +184,9 @@ def _dem_c3():
     mass, radius = np.ones(n), np.zeros(n)
     uid, typ, flags, shape = (np.zeros(n, np.int32) for _ in range(4))
     pos[:ns], vel[:ns], mass[:ns], radius[:ns], uid[:ns], typ[:ns] = g["position"], g["linear_velocity"], g["mass"], g["radius"], g["uid"], g["type"]
-    # data/planes.input of the reference with the ceiling at the corner of THIS box (what oracle/build_ref.py writes for dem_bench)
-    for k, (u, p_, nrm) in enumerate([(100000, (0.0, 0.0, 0.0), (0.0, 0.0, 1.0)), (100001, domain, (0.0, 0.0, -1.0))]):
+    # data/planes.input of the reference as it is (oracle/build_ref.py copies it): the ceiling keeps the y of the stock thin box
+    # (at this size the uids of the plane file, 100000 and 100001, also belong to two spheres -- in the reference as well)
+    for k, (u, p_, nrm) in enumerate([(plane_uids[0], (0.0, 0.0, 0.0), (0.0, 0.0, 1.0)), (plane_uids[1], ceiling_at, (0.0, 0.0, -1.0))]):
         uid[ns + k], pos[ns + k], normal[ns + k], flags[ns + k], shape[ns + k] = u, p_, nrm, 13, 1
     ctx.upload(pos, vel, mass, typ, flags, uid, shape)
     ctx.dem_upload("radius", radius)
@@ -209,8 +210,10 @@ def test_config_c3_one_million_spheres_against_the_reference(tmp_path):
     nl, ng = ctx.counts()
     assert (nl, ng) == (int(z["nlocal"][0]), int(z["nghost"][0])) and nl == n == 998402
     assert np.array_equal(ctx.ints("uid"), z["uid"])                        # DEM keeps the particle order (no re-sort before 200)
-    assert np.array_equal(ctx.real("position"), z["position"])               # bit for bit: the linear part of euler
-    assert np.array_equal(ctx.real("linear_velocity"), z["linear_velocity"])
+    dx = np.abs(ctx.real("position") - z["position"]).max()
+    dv = np.abs(ctx.real("linear_velocity") - z["linear_velocity"]).max() / np.abs(z["linear_velocity"]).max()
+    print(f"C3 after {last + 1} iterations: max |dx| = {dx:.3e} m, max |dv| / max |v| = {dv:.3e}")
+    assert dx == 0.0 and dv == 0.0                                           # bit for bit: gravity + the linear part of euler
     assert np.array_equal(ctx.ints("particle_cell"), z["particle_cell"])
     c = ctx.dem_download_contacts(nl)
     assert not c["num_contacts"].any() and not z["num_contacts"].any()
@@ -220,7 +223,7 @@ def test_config_c3_settled_bed_invariants():
     """C3 at size, 4000 iterations (the bed has formed: ~5 contacts per sphere).  Properties that hold whatever the size: nothing is
     lost or duplicated, every sphere lies between the two planes, contact rows are symmetric (j in the row of i <=> i in the row
     of j, for sphere-sphere contacts), partners of a contact touch or nearly touch, no row exceeds the capacity."""
-    ctx, n, dc = _dem_c3()
+    ctx, n, dc = _dem_c3(plane_uids=(100000000, 100000001))
     ctx.dem_run(dc.CELL, 0, 4000)
     nl, _ = ctx.counts()
     assert nl == n
@@ -233,12 +236,12 @@ def test_config_c3_settled_bed_invariants():
     c = ctx.dem_download_contacts(nl)
     num, lists = c["num_contacts"], c["contact_lists"]
     assert num.max() <= dc.C and 3.0 < num[sph].mean() < 8.0
-    row_of = np.full(int(uid.max()) + 1, -1, np.int64)
-    row_of[uid] = np.arange(n)
+    order = np.argsort(uid)
+    row_of = lambda u: order[np.searchsorted(uid[order], u)]      # noqa: E731  (uid -> row; every listed uid exists)
     m = np.arange(lists.shape[1])[None, :] < num[:, None]
     i_idx = np.broadcast_to(np.arange(n)[:, None], lists.shape)[m]
-    j_idx = row_of[lists[m]]
-    assert (j_idx >= 0).all()
+    j_idx = row_of(lists[m])
+    assert np.array_equal(uid[j_idx], lists[m])
     both = sph[i_idx] & sph[j_idx]                                            # (the half-spaces are FIXED: they keep no rows)
     a, b = i_idx[both], j_idx[both]
     fwd = np.unique(a.astype(np.int64) * n + b)
