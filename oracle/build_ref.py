@@ -283,7 +283,72 @@ VARIANTS = {
     # the STOCK example (0.8 x 0.015 x 0.2 box, 18720 spheres, VTK every 100 iterations), only cut to 100 iterations: golden for the
     # test that runs the example file itself on this backend (tests/test_gpu_examples.py)
     "dem_stock_t1": ("examples/dem.py", dem_variant((0.8, 0.015, 0.2), 102, vtk_every=100), [], False),
+    # dem_t1 generated by a CORRECTED copy of the reference generator: see corrected_generator()
+    "dem_fix_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), ["generator:contact_history_fix"], False),
 }
+
+
+def corrected_generator(gdir):
+    """A scratch copy of /root/reference/src/pairs (under oracle/_ref/, never committed) whose sim/comm.py carries the minimal
+    fix of the contact-history transfer, the defects SURVEY.md Appendix A.2 lists:
+      * PackContactHistoryData runs BEFORE RemoveExchangedParticles has overwritten the leaver's slot with the hole filler's row
+        (stock: after -- the history of the WRONG particle is sent), into a send buffer of its own (at that point the shared one
+        still holds the particle records);
+      * every record carries its partner uid at `offset + disp + 0` (stock: all records write to `offset + 0`);
+      * unpack reads the uid of record k from `offset + disp + 0` and the contact properties from `offset + disp + 1` on, where
+        pack put them (stock: `offset + 0` and `cp_offset = 0`).
+    Returns the directory to put on PYTHONPATH."""
+    import shutil
+    dst = os.path.join(gdir, "src_fixed")
+    if os.path.exists(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(os.path.join(REF, "src"), dst)
+    path = os.path.join(dst, "pairs", "sim", "comm.py")
+    t = open(path).read()
+
+    def sub(old, new, count=1):
+        nonlocal t
+        assert t.count(old) >= count, f"corrected_generator: pattern not found in comm.py: {old[:60]}"
+        t = t.replace(old, new, count)
+
+    # ... into a buffer of its own: at that point send_buffer still holds the particle records CommunicateData is about to send
+    sub("""        self.send_buffer      = sim.add_array('send_buffer', [self.send_capacity, self.elem_capacity], Types.Real, arr_sync=False)
+""", """        self.send_buffer      = sim.add_array('send_buffer', [self.send_capacity, self.elem_capacity], Types.Real, arr_sync=False)
+        self.contact_send_buffer = sim.add_array('contact_send_buffer', [self.send_capacity, self.elem_capacity], Types.Real, arr_sync=False)
+""")
+    sub("""        send_buffer = self.comm.send_buffer
+        send_buffer.set_stride(1, 1)
+        contact_soffsets = self.comm.contact_soffsets""", """        send_buffer = self.comm.contact_send_buffer
+        send_buffer.set_stride(1, 1)
+        contact_soffsets = self.comm.contact_soffsets""")
+    sub("""                   self.comm.send_buffer, self.comm.contact_soffsets, self.comm.nsend_contact,""",
+        """                   self.comm.contact_send_buffer, self.comm.contact_soffsets, self.comm.nsend_contact,""")
+    # pack before the removal (the pack statement keeps its place in the class, only the call moves)
+    sub("""            RemoveExchangedParticles_part1(self)
+""", """            if self.sim._use_contact_history:
+                PackContactHistoryData(self, step)
+
+            RemoveExchangedParticles_part1(self)
+""")
+    sub("""            if self.sim._use_contact_history:
+                PackContactHistoryData(self, step)
+                CommunicateContactHistoryData(self, step)""", """            if self.sim._use_contact_history:
+                CommunicateContactHistoryData(self, step)""")
+    sub("""                    Assign(self.sim, send_buffer[soff][offset + 0],
+                                     Cast(self.sim, contact_lists[m][k], Types.Real))""",
+        """                    Assign(self.sim, send_buffer[soff][offset + disp + 0],
+                                     Cast(self.sim, contact_lists[m][k], Types.Real))""")
+    sub("""                    disp = k * nelems_per_contact
+                    cp_offset = 0
+
+                    Assign(self.sim, contact_lists[nlocal + i][k], recv_buffer[roff][offset + 0])""",
+        """                    disp = k * nelems_per_contact
+                    cp_offset = 1
+
+                    Assign(self.sim, contact_lists[nlocal + i][k], recv_buffer[roff][offset + disp + 0])""")
+    with open(path, "w") as f:
+        f.write(t)
+    return dst
 
 
 def run(cmd, **kw):
@@ -355,7 +420,10 @@ def build_variant(name):
     scratch_script = os.path.join(gdir, f"{base}_{name}_input.py")
     with open(scratch_script, "w") as f:
         f.write(text)
-    env = dict(os.environ, PYTHONPATH=os.path.join(REF, "src"), PYTHONHASHSEED="0")
+    gens = [d for d in defines if d.startswith("generator:")]
+    defines = [d for d in defines if not d.startswith("generator:")]
+    gen_src = corrected_generator(gdir) if gens else os.path.join(REF, "src")
+    env = dict(os.environ, PYTHONPATH=gen_src, PYTHONHASHSEED="0")
     run([sys.executable, scratch_script, "cpu"], cwd=gdir, env=env)
     if not os.path.exists(gen_cpp):
         raise RuntimeError(f"generator did not write {gen_cpp}")

@@ -49,3 +49,18 @@ for ts in (0, 150, 300):
 path3 = os.path.join(HERE, "dem_rn3_t1.npz")
 np.savez_compressed(path3, **out3)
 print("dem_rn3_t1:", os.path.getsize(path3) // 1024, "KiB")
+
+
+# variant dem_fix_t1: the same run from the CORRECTED copy of the reference generator (oracle/build_ref.py corrected_generator:
+# contact history packed before the leaver's slot is overwritten, into its own buffer, uid per record, matching offsets) --
+# end-of-iteration states past the first periodic wrap of a particle with live contacts (between iterations 350 and 400)
+FIX_STEPS = [300, 350, 400, 500, 600, 699]
+zf = ref_worker.dump_dem("dem_fix_t1", "/tmp/dem_fix_t1_golden_raw.npz", 700, FIX_STEPS)
+outf = {"nlocal": zf["nlocal"], "nghost": zf["nghost"], "end_steps": np.array(FIX_STEPS)}
+for ts in FIX_STEPS:
+    for k in ("position", "linear_velocity", "angular_velocity", "uid", "num_contacts", "contact_lists", "is_sticking",
+              "tangential_spring_displacement", "impact_velocity_magnitude"):
+        outf[f"end_{ts}_{k}"] = zf[f"end_{ts}_{k}"]
+pathf = os.path.join(HERE, "dem_fix_t1.npz")
+np.savez_compressed(pathf, **outf)
+print("dem_fix_t1:", os.path.getsize(pathf) // 1024, "KiB")
