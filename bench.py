@@ -236,7 +236,14 @@ def cpu_reference_sample(warmup, steps, replicas):
     sample = (f"{n_atoms} atoms (same lattice generator, nx={REF_SAMPLE_NX}), loop iterations {warmup + 1}..{warmup + steps} "
               f"timed after iteration 0 (set-up + first list build) and {warmup} warm-up iterations; reneighbour every {RENEIGH}; "
               f"serial target, g++ -O3 -ffp-contract=off; {replicas} independent replica process(es), aggregate throughput")
-    return {"value": value, "unit": UNIT, "cores": replicas, "kind": kind, "sample": sample, "seconds": secs}
+    out = {"value": value, "unit": UNIT, "cores": replicas, "kind": kind, "sample": sample, "seconds": secs}
+    # the same program built with the reference Makefile's flags (-O3 -mavx2 -mfma, contraction allowed): the parity build above
+    # forbids contraction, which is right for bit comparisons and slightly unkind for timing
+    if kind == "reference" and ref.available("md_bench_fma"):
+        from oracle import ref_worker
+        res2 = ref_worker.bench_many("md_bench_fma", warmup, steps, replicas)
+        out["value_o3_avx2_fma"] = sum(r["n"] * r["steps"] / r["seconds"] for r in res2)
+    return out
 
 
 def run_reference(args):
@@ -256,7 +263,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * cb["seconds"] / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus, args.nx, reference_arm=True),
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_o3_avx2_fma") if k in cb},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
     _JSON_OUT.write(json.dumps(line) + "\n")
@@ -416,7 +423,7 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_reference_sample(1, 20, 1)
-        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "value_o3_avx2_fma") if k in cb}
         cpu_baseline["host_cores_available"] = os.cpu_count()
     reference_cuda = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

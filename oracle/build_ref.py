@@ -266,6 +266,8 @@ VARIANTS = {
     "md_t1": ("examples/md.py", md_variant(8, 100, 1, 20), ["-DREF_IS_MD"], False),
     "md_t2": ("examples/md.py", md_variant(12, 60, 1, 5), ["-DREF_IS_MD"], False),
     "md_bench": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD"], False),
+    # the same program with the flags of the reference's own Makefile (contraction allowed, AVX2 + FMA): the kinder CPU baseline
+    "md_bench_fma": ("examples/md.py", md_variant(63, 2000, 1, 20, pcap=1400000), ["-DREF_IS_MD", "-ffp-contract=fast", "-mavx2", "-mfma"], False),
     # cell lists without neighbour lists: every pair of the 27 stencil cells inside the cutoff, cells rebuilt every 20 iterations
     "md_cells_t1": ("examples/md.py", md_variant(8, 60, 1, 20, cells_only=True), [], False),
     "md_custom_t1": ("examples/md.py", md_custom_variant(8, 100), ["-DREF_LJ_MODULE"], False),

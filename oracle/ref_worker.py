@@ -191,7 +191,7 @@ def _main(argv):
         t = list(buf)[:n]
         assert n >= warmup + steps + 1, (n, warmup, steps)
         seconds = t[warmup + steps] - t[warmup]
-        atoms = {"md_bench": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3, "dem_t1": 422, "dem_vtk_t1": 422, "dem_cn_t1": 422, "dem_nl_t1": 422, "dem_rn3_t1": 422, "md_half_t1": 4 * 8 ** 3, "md_custom_t1": 4 * 8 ** 3, "md_props_t1": 4 * 8 ** 3, "md_vocab_t1": 4 * 8 ** 3,
+        atoms = {"md_bench": 4 * 63 ** 3, "md_bench_fma": 4 * 63 ** 3, "md_t1": 4 * 8 ** 3, "md_t2": 4 * 12 ** 3, "md": 4 * 32 ** 3, "dem_t1": 422, "dem_vtk_t1": 422, "dem_cn_t1": 422, "dem_nl_t1": 422, "dem_rn3_t1": 422, "md_half_t1": 4 * 8 ** 3, "md_custom_t1": 4 * 8 ** 3, "md_props_t1": 4 * 8 ** 3, "md_vocab_t1": 4 * 8 ** 3,
                  "dem_bench": 160 * 160 * 39 + 2, "dem_stock_t1": 160 * 3 * 39 + 2, "md_cells_t1": 4 * 8 ** 3}[variant]
         print(json.dumps({"n": atoms, "seconds": seconds, "steps": steps, "warmup": warmup}))
         return 0
