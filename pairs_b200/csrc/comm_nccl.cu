@@ -188,10 +188,19 @@ extern "C" int pb_nccl_init(pb_ctx *ctx, const void *id128) {
     PB_CHECK(cudaMalloc(&st->d_red, sizeof(double) * 4));
     PB_CHECK(cudaMalloc(&st->d_counts, sizeof(int) * 8));
     pb_board_open(ctx, st, id128);
-    // every rank must agree on the way counts travel: sum of "I have a board" over the ranks
-    double have = st->board != nullptr ? 1.0 : 0.0;
+    // every rank must agree on the way counts travel: sum of "I have a board" over the ranks -- and the board is a POSIX
+    // shared-memory segment, i.e. one per NODE: ranks on different hosts would each map their own and wait for posts that never
+    // arrive.  All ranks on one host <=> world * sum(h^2) == sum(h)^2 for a 20-bit hash h of the host name (exact in doubles).
+    char host[256] = {0};
+    gethostname(host, sizeof(host) - 1);
+    unsigned hh = 2166136261u;
+    for(const char *c = host; *c != 0; c++) { hh = (hh ^ (unsigned char) *c) * 16777619u; }
+    const double hv = (double) (hh & 0xfffffu);
+    double agree[3] = {st->board != nullptr ? 1.0 : 0.0, hv, hv * hv};
     ctx->nccl = st;
-    PB_TRY(pb_allreduce_sum(ctx, &have, 1));
+    PB_TRY(pb_allreduce_sum(ctx, agree, 3));
+    const bool one_host = (double) ctx->world * agree[2] == agree[1] * agree[1];
+    const double have = one_host ? agree[0] : 0.0;
     if(have < ctx->world - 0.5 && st->board != nullptr) {
         munmap(st->board, st->board_bytes);
         st->board = nullptr;

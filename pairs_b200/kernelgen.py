@@ -167,7 +167,12 @@ class _Gen:
             return val
         if store == "pos":
             src = "pi" if who == "i" else "pj"
-            val = self.vec([f"{src}.x", f"{src}.y", f"{src}.z"])
+            if who == "i" and self.kind != "pair":
+                # a per-particle kernel may assign position[i]: what was read before the assignment keeps its value (as every other
+                # property: snapshots in const temporaries), `old = position[i]; position[i] = ...; position[i] - old` is not 0
+                val = self.vec([self.tmp("double", f"{src}.{c}", False) for c in "xyz"])
+            else:
+                val = self.vec([f"{src}.x", f"{src}.y", f"{src}.z"])
         elif store in ("vel", "force", "angvel", "torque"):       # angvel / torque: DEM scripts
             val = self.vec([self.tmp("double", f"a.{store}[{d} * (size_t) a.cap + {idx}]" if d else f"a.{store}[{idx}]", hoist) for d in range(3)])
         elif store in ("mass", "radius"):
@@ -689,7 +694,7 @@ class _Gen:
             raise KernelGenError(f"'{store}' is a vector property")
         if store == "pos":
             self.lines.append(f"pi.x = {v[1][0]}; pi.y = {v[1][1]}; pi.z = {v[1][2]}; a.pos_w[i] = pi;")
-            self.loaded[(store, "i")] = self.vec(["pi.x", "pi.y", "pi.z"])
+            self.loaded[(store, "i")] = v                      # later reads see the value just assigned (const temporaries)
         else:
             for d in range(3):
                 if only is None or only == d:

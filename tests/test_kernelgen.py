@@ -846,6 +846,8 @@ def test_random_expressions_generated_code_equals_python_arithmetic(tmp_path):
         lines.append(f"    b *= {scalar(1)}")
         lines += [f"    if {scalar(1)} > {scalar(1)}:", f"        a = {scalar(2)}", f"        mass[i] = a + b", "    else:", f"        mass[i] = {scalar(3)}"]
         lines += [f"    force[i] = {vector(2)}", f"    linear_velocity[i] += {vector(2)}"]
+        if n % 2 == 0:      # position read, assigned, read again: the first read keeps its value (snapshots, as for every property)
+            lines += ["    old = position[i]", f"    position[i] = position[i] + {vector(1)} * 0.5", "    linear_velocity[i] = (position[i] - old) * 2.0"]
         bodies.append("\n".join(lines))
     text = "\n\n\n".join(bodies) + "\n"
     mod_path = tmp_path / "fuzz_kernels.py"
@@ -926,7 +928,8 @@ def test_random_expressions_generated_code_equals_python_arithmetic(tmp_path):
         flags = np.zeros(npart, np.int32)
         g_pos, g_vel, g_force, g_mass = pos4.copy(), vel.copy(), force.copy(), mass.copy()
         run(npart, 0, npart, 0.0, _ptr(g_pos), _ptr(g_vel), _ptr(g_force), _ptr(g_mass), _ptr(flags), None, None)
-        env = {"position": Prop(np.ascontiguousarray(pos4[:, :3].T), True), "linear_velocity": Prop(vel, True), "force": Prop(force, True),
+        prow = np.ascontiguousarray(pos4[:, :3].T)
+        env = {"position": Prop(prow, True), "linear_velocity": Prop(vel, True), "force": Prop(force, True),
                "mass": Prop(mass, False), "c3": 0.75, "select": lambda c, x, y: x if c else y, "min": fold(lambda x, e: x < e),
                "max": fold(lambda x, e: x > e), "sqrt": math.sqrt, "abs": abs, "dot": dot, "cross": cross, "normalized": normalized,
                "squared_length": lambda p: dot(p, p), "length": lambda p: math.sqrt(dot(p, p))}
@@ -934,7 +937,7 @@ def test_random_expressions_generated_code_equals_python_arithmetic(tmp_path):
         with np.errstate(all="ignore"):
             for i in range(npart):
                 fn(i)
-        for got, want in ((g_mass, mass), (g_force, force), (g_vel, vel)):
+        for got, want in ((g_mass, mass), (g_force, force), (g_vel, vel), (np.ascontiguousarray(g_pos[:, :3].T), prow)):
             assert np.array_equal(got.view(np.int64), np.asarray(want).view(np.int64)) or \
                 np.array_equal(np.nan_to_num(got, nan=7.0), np.nan_to_num(want, nan=7.0)), (n, text.split("\n\n\n")[n])
         checked += 1
