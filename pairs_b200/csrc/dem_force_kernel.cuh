@@ -41,8 +41,58 @@ struct PbDemForceArgs {
 //   clear_unused_contact_history           the swap-with-last compaction runs on the row at the end, driven by the mask
 // (euler sits between the contact kernel and the clean-up in the reference's list; it touches no contact data, so the order
 // does not matter).  Nine launches -- six memsets and three kernels -- and their passes over the arrays disappear.
+// One thread per particle, but not thread t for particle t: a thread walks its particle's touching partners one after the other
+// (~1800 issued instructions per partner, 455 of them fp64, in one long dependent chain), and with 0 ... 12 partners per particle
+// a warp of 32 consecutive particles ran with 54 % of its lanes busy.  So a CTA takes PB_DEM_CTA_PARTICLES consecutive particles, sorts them by partner count in
+// shared memory (counting sort; the order inside a bucket is arbitrary and does not matter: particles are independent), and its
+// warps take groups of 32 from that order in boustrophedon fashion, so that every warp gets long and short groups.  Every particle is still evaluated
+// by the same serial code: identical bits.  Measured (10^6 settled spheres, both contact kernels): 0.995 -> 0.964 ms -- the warp
+// iterations halve (ncu: 140 k, 27 of 32 lanes), the time hardly moves: at 158 registers (12 warps per SM) the kernel issues 0.19
+// instructions per cycle and scheduler, each warp-iteration takes ~13 000 cycles of dependent fp64 and load latency.  Also
+// measured, without gain: 4 lanes per particle with ordered shuffles (same bits; 1.20 ms), prefetching the next partner's state
+// (0.959 ms), register caps of 80 ... 128 through NVRTC (0.997 ... 1.016 ms).
+#ifndef PB_DEM_CTA_PARTICLES
+#define PB_DEM_CTA_PARTICLES 512
+#endif
+
+template<bool FUSED>
+__device__ __forceinline__ void pb_dem_force_particle(const PbDemForceArgs &a, int i);
+
 template<bool FUSED>
 __device__ __forceinline__ void pb_dem_force_body(const PbDemForceArgs &a) {
+    constexpr int NP = PB_DEM_CTA_PARTICLES, NG = NP / 32;
+    __shared__ int s_off[34];
+    __shared__ short s_perm[NP];
+    const int base = blockIdx.x * NP, tid = threadIdx.x, nthreads = blockDim.x;
+    if(tid < 34) { s_off[tid] = 0; }
+    __syncthreads();
+    // bucket = partner count (a particle beyond the end, or without partners: bucket 0); clamped to 31
+    for(int k = tid; k < NP; k += nthreads) {
+        const int i = base + k;
+        const int key = (i < a.nlocal) ? min(a.npairs[i], 31) : 0;
+        atomicAdd(&s_off[key + 2], 1);
+    }
+    __syncthreads();
+    if(tid == 0) { for(int b = 2; b < 34; b++) { s_off[b] += s_off[b - 1]; } }      // s_off[key + 1] = first position of bucket key
+    __syncthreads();
+    for(int k = tid; k < NP; k += nthreads) {
+        const int i = base + k;
+        const int key = (i < a.nlocal) ? min(a.npairs[i], 31) : 0;
+        s_perm[atomicAdd(&s_off[key + 1], 1)] = (short) k;
+    }
+    __syncthreads();
+    // groups of 32 in sorted order; warp w of W takes them alternately from both ends, so that every warp gets long and short ones
+    const int warp = tid >> 5, lane = tid & 31, W = nthreads >> 5;
+    for(int p = 0; p * W < NG; p++) {
+        const int g = p * W + ((p & 1) ? (W - 1 - warp) : warp);      // boustrophedon over the sorted groups
+        if(g >= NG) { continue; }
+        const int i = base + (int) s_perm[g * 32 + lane];
+        if(i < a.nlocal) { pb_dem_force_particle<FUSED>(a, i); }
+    }
+}
+
+template<bool FUSED>
+__device__ __forceinline__ void pb_dem_force_particle(const PbDemForceArgs &a, const int i) {
     const int nlocal = a.nlocal, cap = a.cap, C = a.C, ntypes = a.ntypes;
     const PbDemParams &P = a.P;
     const double4 *__restrict__ pos = a.pos;
@@ -55,9 +105,7 @@ __device__ __forceinline__ void pb_dem_force_body(const PbDemForceArgs &a) {
     double *__restrict__ c_tsd = a.c_tsd, *__restrict__ c_ivm = a.c_ivm, *__restrict__ force = a.force, *__restrict__ torque = a.torque;
     const int accumulate = a.accumulate;
     int *__restrict__ overflow = a.overflow;
-    (void) P; (void) fric_s; (void) fric_d;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= nlocal) { return; }
+    (void) P; (void) fric_s; (void) fric_d; (void) nlocal;
     const bool fixed = (flags[i] & PB_FLAG_FIXED) != 0;
     double Fs[3] = {0.0, 0.0, 0.0}, Ts[3] = {0.0, 0.0, 0.0}, Fh[3] = {0.0, 0.0, 0.0}, Th[3] = {0.0, 0.0, 0.0};
     const int np = npairs[i];

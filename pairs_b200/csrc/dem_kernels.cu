@@ -717,7 +717,7 @@ template<bool FUSED>
 static int pb_launch_dem_force(pb_ctx *ctx, int accumulate) {
     const PbDemForceArgs a = pb_dem_force_args(ctx, accumulate);
     if(ctx->dem_user_force != nullptr) { return pb_jit_launch_dem_force_raw(ctx, FUSED ? 1 : 0, (void *) &a); }
-    PB_LAUNCH(pb_k_dem_force<FUSED>, pb_blocks(ctx->nlocal, 128), 128, a);
+    PB_LAUNCH(pb_k_dem_force<FUSED>, pb_blocks(ctx->nlocal, PB_DEM_CTA_PARTICLES), 128, a);
     return 0;
 }
 

@@ -327,7 +327,8 @@ int pb_jit_launch_dem_force_raw(pb_ctx *ctx, int fused, void *args_struct) {
     auto *u = (PbDemUserForce *) ctx->dem_user_force;
     if(u == nullptr) { ctx->set_error("no user-defined DEM contact model installed"); return -1; }
     void *params[] = {args_struct};
-    PB_CHECK(cudaLaunchKernel((const void *) (fused ? u->fused : u->staged), dim3(pb_blocks(ctx->nlocal, 128)), dim3(128), params, 0, ctx->stream));
+    PB_CHECK(cudaLaunchKernel((const void *) (fused ? u->fused : u->staged), dim3(pb_blocks(ctx->nlocal, 512)), dim3(128), params, 0,
+                              ctx->stream));      // PB_DEM_CTA_PARTICLES = 512 particles per CTA (dem_force_kernel.cuh)
     ctx->launches++;
     return 0;
 }
