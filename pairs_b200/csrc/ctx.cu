@@ -84,7 +84,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt,
                     ctx->tiles, ctx->tile_lvl, ctx->tile_cnt, ctx->tile_off, ctx->tile_pad, ctx->tile_row, ctx->twords, ctx->tile_flag,
                     ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary, ctx->tile_hdrs, ctx->mxy[0], ctx->mxy[1], ctx->mz[0], ctx->mz[1],
-                    ctx->mmeta, ctx->ghost_csr};
+                    ctx->mmeta, ctx->ghost_csr, ctx->io_stage};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
@@ -306,6 +306,17 @@ __global__ void pb_k_iota(int n, int *p, int base) {
     if(i < n) { p[i] = base + i; }
 }
 
+int pb_io_stage(pb_ctx *ctx, size_t bytes, double **out) {
+    if(bytes > ctx->io_stage_bytes) {
+        if(ctx->io_stage != nullptr) { PB_CHECK(cudaFree(ctx->io_stage)); ctx->io_stage = nullptr; ctx->io_stage_bytes = 0; }
+        const size_t want = bytes + bytes / 8;
+        PB_CHECK(cudaMalloc(&ctx->io_stage, want));
+        ctx->io_stage_bytes = want;
+    }
+    *out = ctx->io_stage;
+    return 0;
+}
+
 extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, const double *velocity, const double *mass,
                                    const int *type, const int *flags, const int *uid, const int *shape) {
     PB_CHECK(cudaSetDevice(ctx->device));
@@ -319,9 +330,11 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     ctx->cells_n = 0;
     if(n == 0) { return 0; }
     const int T = 256, B = pb_blocks(n, T);
-    PbScratch stage_buf;
-    PB_CHECK(stage_buf.alloc(sizeof(double) * 3 * (size_t) n));
-    double *const stage = stage_buf.as<double>();
+    // positions and velocities pass through the staging area (AoS -> double4 / SoA), one half each: all copies are issued back to
+    // back, the kernels behind them, ONE synchronisation at the end
+    double *stage = nullptr;
+    PB_TRY(pb_io_stage(ctx, sizeof(double) * 6 * (size_t) n, &stage));
+    double *const stage_v = stage + 3 * (size_t) n;
     auto upload_int = [&](const int *src, int *dst, int dflt) -> int {
         if(src != nullptr) {
             PB_CHECK(cudaMemcpyAsync(dst, src, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
@@ -338,9 +351,8 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     PB_CHECK(cudaMemcpyAsync(stage, position, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
     PB_LAUNCH(pb_k_pack_pos, B, T, n, stage, ctx->type, ctx->pos);
     if(velocity != nullptr) {
-        PB_CHECK(cudaStreamSynchronize(ctx->stream));
-        PB_CHECK(cudaMemcpyAsync(stage, velocity, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
-        PB_LAUNCH(pb_k_aos_to_soa3, B, T, n, ctx->pcap, stage, ctx->vel);
+        PB_CHECK(cudaMemcpyAsync(stage_v, velocity, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
+        PB_LAUNCH(pb_k_aos_to_soa3, B, T, n, ctx->pcap, stage_v, ctx->vel);
     } else {
         PB_CHECK(cudaMemsetAsync(ctx->vel, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
     }
@@ -381,9 +393,8 @@ extern "C" int pb_download_real(pb_ctx *ctx, const char *name, double *out, int 
         PB_CHECK(cudaStreamSynchronize(ctx->stream));
         return 0;
     }
-    PbScratch stage_buf;
-    PB_CHECK(stage_buf.alloc(sizeof(double) * 3 * (size_t) n));
-    double *const stage = stage_buf.as<double>();
+    double *stage = nullptr;
+    PB_TRY(pb_io_stage(ctx, sizeof(double) * 3 * (size_t) n, &stage));
     if(nm == "position") {
         PB_LAUNCH(pb_k_unpack_pos, B, T, n, ctx->pos, stage);
     } else if(nm == "linear_velocity") {

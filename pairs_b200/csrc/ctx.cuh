@@ -115,6 +115,11 @@ struct pb_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_sync = nullptr;
 
+    // persistent staging area of the bulk transfers (pb_upload_particles, pb_download_real): no allocation, no free and hence no
+    // device-wide synchronisation inside a transfer
+    double *io_stage = nullptr;
+    size_t io_stage_bytes = 0;
+
     // ---- tile lists (tile_lists.cu): the list format of the MD hot path.  A tile = the cells [za, zb] of a 2 x 2 block of cell
     //      columns holding <= PB_TILE_M particles; its CTA stages the 4 x 4 columns around it in shared memory and walks 16-bit
     //      tile-relative neighbour lists (4 entries per 64-bit word, sliced ELLPACK over list ROWS = tile-major particle order).
@@ -226,6 +231,7 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff);        // 0 built, 1 not ap
 int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int part);
 int pb_tile_finish_split(pb_ctx *ctx);
 int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity);
+int pb_io_stage(pb_ctx *ctx, size_t bytes, double **out);
 int pb_tile_mirror_all(pb_ctx *ctx);
 int pb_tile_mirror_ghosts(pb_ctx *ctx);
 int pb_require_neigh32(pb_ctx *ctx);                        // per-particle 32-bit lists for the kernels that walk them (built lazily)
