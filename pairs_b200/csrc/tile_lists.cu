@@ -343,36 +343,28 @@ struct PbTileBuildArgs {
 // lanes of a half-warp ask for 16 different residues in every iteration.  Entries whose class has more members than there are
 // positions of its residue fill the holes that smaller classes leave, in ascending order.  Measured (tools/micro/tile_force.cu,
 // 4 M atoms): shared-memory wavefronts per launch -38 %, force kernel 0.66 -> 0.58 ms.
-//   row: the thread's T4 * 4 entries in shared memory.  Three passes over the row's words (its own, just written: L2 hits):
-//   class sizes; the HOLES -- position 16 n + offset of a class with fewer than n + 1 members -- chained into a list through the
-//   row itself; placement (an entry whose class has run out of positions takes the next hole).
-__device__ __forceinline__ void pb_tile_reorder_row(const unsigned long long *__restrict__ in_words, int nn, int rot, unsigned short *row) {
-    unsigned long long hist_lo = 0ull, hist_hi = 0ull;           // entries per residue class: 16 x 8 bits
-    for(int q = 0; q * 4 < nn; q++) {
-        const unsigned long long w = __ldcg(in_words + (size_t) q * 32);
-#pragma unroll
-        for(int u = 0; u < 4; u++) {
-            const unsigned e16 = (unsigned) (w >> (16 * u)) & 0xffffu;
-            const unsigned long long one = (q * 4 + u < nn) ? 1ull << ((e16 & 7u) * 8u) : 0ull;
-            if(e16 & 8u) { hist_hi += one; } else { hist_lo += one; }
-        }
-    }
+//   row: the thread's T4 * 4 entries in shared memory; hist: entries per residue class, 16 x 4 bits, counted while the row was
+//   built (a class of 16 or more members -- not seen at liquid density -- leaves the row in builder order).  The HOLES -- position
+//   16 n + offset of a class with fewer than n + 1 members -- are chained into a list through the row itself; then one pass over
+//   the row's words (its own, just written: L2 hits) places every entry; one whose class has run out of positions takes the next hole.
+__device__ __forceinline__ void pb_tile_reorder_row(const unsigned long long *__restrict__ in_words, int nn, int rot, unsigned long long hist,
+                                                    unsigned short *row) {
     int head = 0;
 #pragma unroll
     for(int r = 0; r < 16; r++) {
-        const int c = (int) (((r & 8) ? hist_hi : hist_lo) >> ((r & 7) * 8)) & 0xff;
+        const int c = (int) (hist >> (r * 4)) & 15;
         for(int k = 16 * c + ((r - rot) & 15); k < nn; k += 16) { row[k] = (unsigned short) head; head = k; }
     }
-    unsigned long long seen_lo = 0ull, seen_hi = 0ull;
+    unsigned long long seen = 0ull;
     for(int q = 0; q * 4 < nn; q++) {
         const unsigned long long w = __ldcg(in_words + (size_t) q * 32);
 #pragma unroll
         for(int u = 0; u < 4; u++) {
             if(q * 4 + u < nn) {
                 const unsigned e16 = (unsigned) (w >> (16 * u)) & 0xffffu;
-                const int r = (int) (e16 & 15u), sh = (r & 7) * 8;
-                const int n = (int) (((r & 8) ? seen_hi : seen_lo) >> sh) & 0xff;
-                if(r & 8) { seen_hi += 1ull << sh; } else { seen_lo += 1ull << sh; }
+                const int r = (int) (e16 & 15u), sh = r * 4;
+                const int n = (int) (seen >> sh) & 15;
+                seen += 1ull << sh;
                 int k = 16 * n + ((r - rot) & 15);
                 if(k >= nn) { k = head; head = row[k]; }      // no position of this residue left: the next hole
                 row[k] = (unsigned short) e16;
@@ -413,6 +405,8 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
     pb_mbar_wait(bar, 0);
     __syncthreads();                                               // (the meta bytes)
     int count = 0, boundary = 0;
+    unsigned long long hist = 0ull;      // entries per residue class of the slot (16 x 4 bits), for the reorder pass
+    unsigned hist_full = 0u;             // set once a class with 15 members gets another one
     const int row = tl.row_base + threadIdx.x;
     unsigned long long *const out = a.words + pb_tile_word(row, T4, 0);
     if(active) {
@@ -440,6 +434,7 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
         unsigned meta_or = 0u;
 #pragma unroll
         for(int r = 0; r < 9; r++) {
+#pragma unroll 2
             for(int s = wb[r]; s < we[r]; s++) {
                 const double2 xy = sxy[s];
                 const double z = sz[s];
@@ -449,6 +444,8 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
                     const unsigned meta = smeta[s];
                     w = (w >> 16) | ((unsigned long long) ((unsigned) s | ((meta & 7u) << 12)) << 48);
                     count++;
+                    hist_full |= (((unsigned) (hist >> ((s & 15) * 4)) & 15u) == 15u) ? 1u : 0u;      // the nibble is about to overflow
+                    hist += 1ull << ((s & 15) * 4);
                     if((count & 3) == 0 && count <= ncap) { out[(size_t) ((count >> 2) - 1) * 32] = w; }
                     meta_or |= meta;
                 }
@@ -468,10 +465,10 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
     if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(a.max_count, m); }
-    if(a.reorder && active && count > 0 && count <= ncap) {
+    if(a.reorder && active && count > 0 && count <= ncap && hist_full == 0u) {
         // the staging area is idle now: thread t assembles its row in its T4 * 8 bytes of it (host: PB_TILE_M * T4 * 8 <= staging bytes)
         unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(sxy) + (size_t) threadIdx.x * (size_t) (T4 * 4);
-        pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf);
+        pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), hist, rowbuf);
         const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
         for(int q = 0; q * 4 < count; q++) { out[(size_t) q * 32] = rw[q]; }
     }
