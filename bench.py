@@ -71,6 +71,7 @@ class ClockSampler(threading.Thread):
         self.proc = None
         self.recording = False
         self.source = None
+        self.ready = threading.Event()      # set once the first query has succeeded (NVML start-up takes ~100 ms), or on failure
 
     def _run_nvml(self):
         import pynvml as nv
@@ -80,18 +81,23 @@ class ClockSampler(threading.Thread):
         bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
         self.source = "nvml"
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        self.ready.set()
         while not self.stop_flag.is_set():
-            if self.recording:
+            if self.recording:          # back to back while the timed region runs (a query takes ~1 ms; 20 steps last ~17 ms)
                 sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 self.rows.append((sm, mx, {k for k, b in bits.items() if r & b}))
-            time.sleep(0.002)
+                time.sleep(0)
+            else:
+                time.sleep(0.0005)
 
     def _run_smi(self):
         self.source = "nvidia-smi -lms 50"
         self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         for line in self.proc.stdout:
+            self.ready.set()
             if self.stop_flag.is_set():
                 break
             c = [x.strip() for x in line.split(",")]
@@ -107,6 +113,7 @@ class ClockSampler(threading.Thread):
                 self._run_smi()
             except Exception:
                 pass
+        self.ready.set()
 
     def stop(self):
         self.stop_flag.set()
@@ -323,6 +330,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()           # before the warm-up, so that it is up when the timed region begins
+        sampler.ready.wait(timeout=10)
     run(0, W)
     barrier()
     if rank == 0:
@@ -379,7 +387,10 @@ def run_ours(args):
                 "force_kernel_atoms_per_s": nl / (lj_ms_per_step * 1e-3) if lj_ms > 0 else None,
                 "share_of_step": lj_ms / ms if ms > 0 else None,
                 "note": "numerator = SURVEY.md 8(d): 4 B per list entry + 60 B per atom + ghost positions; the tile lists actually "
-                        "hold 2 B per entry (bytes_per_atom_as_stored), the staged tiles are re-read from L2, not HBM",
+                        "hold 2 B per entry (bytes_per_atom_as_stored), the staged tiles are re-read from L2, not HBM"
+                        + ("; N > 1: the interior and the boundary tiles of a step are two launches on two streams that run "
+                           "CONCURRENTLY (halo refresh overlapped), their event-timed durations are summed here -- an upper bound of the "
+                           "kernel time per step, hence a lower bound of frac" if world > 1 else ""),
                 "bytes_per_atom_as_stored": 2.0 * kbar + 60.0 + 24.0 * ng / max(nl, 1)}
 
     # ---- end to end through the C-ABI with HOST buffers: upload (pinned) -> K loop iterations from ts = 0 (first list build
@@ -531,6 +542,7 @@ def run_dem(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.ready.wait(timeout=10)
     # the falling phase (no contacts yet) is reported next to the headline window
     ctx.dem_run(dc.CELL, 0, 20)
     barrier()
