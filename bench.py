@@ -506,6 +506,18 @@ def run_dem(args):
         dist.init_process_group("gloo", rank=rank, world_size=world)
     gx, gy = DEM_GRIDS[world]
     domain = (0.8 * gx, 0.8 * gy, 0.2)
+    # N > 1: the N-rank run (particles migrate WITH their contact history) against the single-GPU run of the same particles, before
+    # anything is timed (tests/scripts/mgpu_dem_check.py: 840 spheres, 1300 iterations); a mismatch raises -> non-zero exit, no line
+    parity_nranks = None
+    if world > 1 and not args.no_parity:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("mgpu_dem_check", os.path.join(ROOT, "tests", "scripts", "mgpu_dem_check.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        t_par = time.perf_counter()
+        parity_nranks = mod.check(backend, dist, rank, world, local)
+        if rank == 0:
+            parity_nranks["seconds"] = time.perf_counter() - t_par
     ctx = backend.Context(local)
     dem_setup(ctx, backend, dist, rank, world, domain)
     assert tuple(ctx.decomposition()["nranks"]) == (gx, gy, 1)
@@ -637,7 +649,7 @@ def run_dem(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": dem_config(world, settle), "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "falling_phase": {"ms_per_step": falling_ms, "value": n_global / (falling_ms * 1e-3)},
-                "stages_ms": stages, "spheres_global": n_global, "nlocal_rank0": nl, "nghost_rank0": ng}
+                "stages_ms": stages, "spheres_global": n_global, "nlocal_rank0": nl, "nghost_rank0": ng, "parity_nranks": parity_nranks}
         _JSON_OUT.write(json.dumps(line) + "\n")
         _JSON_OUT.flush()
     if dist is not None:

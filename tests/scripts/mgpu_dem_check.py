@@ -69,12 +69,9 @@ def snapshot(ctx):
             "ivm": c["impact_velocity_magnitude"], "stick": c["is_sticking"]}
 
 
-def main():
-    import torch.distributed as dist
-    from pairs_b200 import backend
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1300
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def check(backend, dist, rank, world, local, steps=1300):
+    """-> report dict on rank 0 ({} elsewhere); AssertionError on any mismatch.  `dist` is an initialised process group (gloo)."""
+    report = {}
 
     # ---- single-GPU run of the whole box (rank 0 only needs it, but every rank has a GPU: keep ranks in lock-step) ----
     single = make_ctx(backend, local, 1, 0)
@@ -170,7 +167,10 @@ def main():
                         assert int(m["stick"][j, c]) == int(r["stick"][i, b[pu]])
                         worst["tsd"] = max(worst["tsd"], float(np.abs(m["tsd"][j, c] - r["tsd"][i, b[pu]]).max()))
             assert sorted(seen) == sorted(int(u) for u in r["uid"][sph]), "a particle is owned by no rank or by two"
-            print(f"mgpu_dem_check ts {cp}: {len(seen)} spheres, {ncontacts} live contacts, worst rel err {worst}, one-ulp control {drift}")
+            print(f"mgpu_dem_check ts {cp}: {len(seen)} spheres, {ncontacts} live contacts, worst rel err {worst}, one-ulp control {drift}",
+                  file=sys.stderr)
+            report[f"ts_{cp}"] = {"spheres": len(seen), "live_contacts": ncontacts, "strict": bool(strict), "worst_rel_err": worst,
+                                  "one_ulp_control": drift}
             if strict:
                 for k, v in drift.items():
                     assert worst[k] <= max(1e-12, 1000.0 * v), (cp, k, worst, drift)
@@ -180,8 +180,24 @@ def main():
                 assert abs(ncontacts - ref_contacts) <= 0.05 * ref_contacts, (cp, ncontacts, ref_contacts)
                 assert worst["position"] <= 0.05, (cp, worst)          # same pile, particle by particle, to 5 % of the box
         assert total_moved > 0, "no particle with live contacts changed owner: the test did not exercise history migration"
-        print(f"mgpu_dem_check ok: world {world}, {steps} steps, {total_moved} owner changes of particles with live contacts")
+        report.update({"ok": True, "world": world, "iterations": steps, "owner_changes_with_live_contacts": total_moved,
+                       "comparator": "single-GPU run of the same particles (pinned to the reference in tests/test_gpu_dem.py), tolerance "
+                                     "calibrated by a one-ulp control run"})
+    single.close(); nudged.close(); ctx.close()
     dist.barrier()
+    return report
+
+
+def main():
+    import torch.distributed as dist
+    from pairs_b200 import backend
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1300
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    report = check(backend, dist, rank, world, local, steps)
+    if rank == 0:
+        print(f"mgpu_dem_check ok: world {world}, {steps} steps, {report['owner_changes_with_live_contacts']} owner changes of particles "
+              "with live contacts")
     dist.destroy_process_group()
 
 
