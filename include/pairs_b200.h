@@ -164,6 +164,14 @@ int pb_dem_contact_overflow(pb_ctx *ctx);
    reads the contact kernel's high-water mark and doubles the capacity (all ranks together, <= 64) once a row is nearly full;
    < 0 if a contact was lost before that.  pb_dem_run calls it every 8 iterations; module-by-module loops call it themselves. */
 int pb_dem_check_contacts(pb_ctx *ctx);
+/* contact properties beyond examples/dem.py's three (add_contact_property, sim/simulation.py:185; mapping/funcs.py:230-263 gives
+   every declared contact property its own array): `extra_lanes` further doubles per contact (a real = 1, a vector = 3, an integer
+   = 1 exact double), `extra_defaults` = what a fresh contact starts from.  They migrate, sort and are cleaned up with the row; only
+   contact models compiled at run time (pb_jit_set_dem_model) read or write them.  pb_dem_contact_extras moves them between the
+   host layout [n][contact_capacity][extra_lanes] and the device. */
+int pb_dem_enable_ex(pb_ctx *ctx, int contact_capacity, int extra_lanes, const double *extra_defaults);
+int pb_dem_contact_extras(pb_ctx *ctx, int n, double *values, int upload);
+int pb_dem_contact_extra_lanes(const pb_ctx *ctx);
 int pb_dem_contact_capacity(const pb_ctx *ctx);
 int pb_dem_run(pb_ctx *ctx, double cell_spacing, int ts_begin, int ts_end);
 

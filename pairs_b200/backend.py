@@ -125,6 +125,9 @@ SIGNATURES = {
     "pb_upload_property": (_I, [_P, _I, _I, _DP]),
     "pb_download_property": (_I, [_P, _I, _DP, _I]),
     "pb_dem_enable": (_I, [_P, _I]),
+    "pb_dem_enable_ex": (_I, [_P, _I, _I, _DP]),
+    "pb_dem_contact_extras": (_I, [_P, _I, _DP, _I]),
+    "pb_dem_contact_extra_lanes": (_I, [_P]),
     "pb_dem_set_params": (_I, [_P, _D, _D, _D, _D, _D, _D, _D, _D, _I, _DP, _DP]),
     "pb_dem_sc_grid": (_I, [_P, _D, _D, _D, _D, _D, _D, _D, _D, _D, _I, _I, _IP, _IP, _DP, _DP, _DP, _DP, _IP]),
     "pb_dem_upload_real": (_I, [_P, _S, _I, _I, _DP]),
@@ -386,9 +389,29 @@ class Context:
     DEM_WIDTH = {"radius": 1, "angular_velocity": 3, "torque": 3, "normal": 3, "inv_inertia": 9, "rotation_matrix": 9, "rotation_quat": 4,
                  "force": 3, "mass": 1, "linear_velocity": 3}
 
-    def dem_enable(self, contact_capacity=20):
-        self._ck(self.lib.pb_dem_enable(self.h, contact_capacity))
+    def dem_enable(self, contact_capacity=20, extra_defaults=()):
+        """extra_defaults: one default per further double lane of a contact (contact properties beyond dem.py's three)"""
+        d = _f64(list(extra_defaults))
+        self._ck(self.lib.pb_dem_enable_ex(self.h, contact_capacity, len(d), _dp(d) if len(d) else None))
         self._dem = True
+
+    @property
+    def contact_extra_lanes(self):
+        return int(self.lib.pb_dem_contact_extra_lanes(self.h)) if getattr(self, "_dem", False) else 0
+
+    def dem_upload_contact_extras(self, values):
+        """values[n][contact_capacity][extra lanes]"""
+        a = _f64(values)
+        n = a.size // max(1, self.contact_capacity * self.contact_extra_lanes)
+        self._ck(self.lib.pb_dem_contact_extras(self.h, n, _dp(a), 1))
+
+    def dem_download_contact_extras(self, n=None):
+        nl, _ = self.counts()
+        n = nl if n is None else n
+        out = np.zeros((n, self.contact_capacity, self.contact_extra_lanes))
+        if out.size:
+            self._ck(self.lib.pb_dem_contact_extras(self.h, n, _dp(out), 0))
+        return out
 
     @property
     def contact_capacity(self):

@@ -166,6 +166,11 @@ struct pb_ctx {
     double *d_fric_static = nullptr, *d_fric_dynamic = nullptr;
     double dem_params[16];        // PbDemParams, see dem_math.h
     int *d_dem_flag = nullptr;    // [0]: contact capacity overflow
+    // contact properties beyond examples/dem.py's three (one integer, one vector, one real): `cx` further double lanes per contact,
+    // layout [lane][slot][particle] like the tangential displacement; only contact models compiled at run time use them
+    double *contact_x = nullptr;
+    int cx = 0;
+    double cx_default[16] = {0};
 
     // ---- user-defined properties (props.cu): what add_property() declares beyond the built-in set, as SoA rows
     //      xdata[xrows][pcap] (a real = 1 row, a vector = 3 rows).  Non-volatile rows travel with their particle (cell-order
@@ -241,7 +246,7 @@ static const int PB_MAX_ELEMS = 16;   // doubles per packed particle record in M
 // DEM exchange record: 12 base + radius 1 + angvel 3 + normal 3 + inv_inertia 9 + rotmat 9 + quat 4 + num_contacts 1 + 6 per slot
 // user-defined properties: their non-volatile rows follow the built-in elements of a record (MD: 12 exchange / 11 borders,
 // DEM: 42 + 6 C exchange / 15 borders)
-static inline int pb_exchange_base_elems(const pb_ctx *ctx) { return ctx->dem ? 42 + 6 * ctx->ccontacts : 12; }
+static inline int pb_exchange_base_elems(const pb_ctx *ctx) { return ctx->dem ? 42 + (6 + ctx->cx) * ctx->ccontacts : 12; }
 static inline int pb_record_elems(const pb_ctx *ctx) { return std::max(PB_MAX_ELEMS, pb_exchange_base_elems(ctx) + ctx->xrows_nv); }
 static const int PB_NSCALARS = 16;
 

@@ -32,7 +32,20 @@ struct PbDemForceArgs {
     double *c_tsd, *c_ivm, *force, *torque;
     int accumulate;
     int *overflow;
+    // further contact properties (pb_dem_enable_ex): nx double lanes per contact, [lane][slot][particle], and their defaults
+    double *c_x;
+    int nx;
+    double x_default[16];
 };
+
+// A generated contact model that declares further contact properties defines PB_DEM_NX (= their lane count, equal to a.nx) before
+// this header, so that the lanes of the contact at hand live in registers around the model call.  Without it (the library's build,
+// generated models without extras) the lanes are only initialised and compacted with their row, over the run-time count.
+#ifdef PB_DEM_NX
+#define PB_DEM_NX_LOOP(x, a) _Pragma("unroll") for(int x = 0; x < PB_DEM_NX; x++)
+#else
+#define PB_DEM_NX_LOOP(x, a) for(int x = 0; x < (a).nx; x++)
+#endif
 
 // FUSED folds the cheap per-particle modules around the contact evaluation of the generated loop into this kernel (the thread
 // owns particle i's force, torque and contact row anyway):
@@ -103,6 +116,7 @@ __device__ __forceinline__ void pb_dem_force_particle(const PbDemForceArgs &a, c
     const double *__restrict__ fric_s = a.fric_s, *__restrict__ fric_d = a.fric_d;
     int *__restrict__ num_contacts = a.num_contacts, *__restrict__ c_uid = a.c_uid, *__restrict__ c_used = a.c_used, *__restrict__ c_stick = a.c_stick;
     double *__restrict__ c_tsd = a.c_tsd, *__restrict__ c_ivm = a.c_ivm, *__restrict__ force = a.force, *__restrict__ torque = a.torque;
+    double *__restrict__ c_x = a.c_x;
     const int accumulate = a.accumulate;
     int *__restrict__ overflow = a.overflow;
     (void) P; (void) fric_s; (void) fric_d; (void) nlocal;
@@ -145,19 +159,27 @@ __device__ __forceinline__ void pb_dem_force_particle(const PbDemForceArgs &a, c
                 c_stick[(size_t) slot * cap + i] = PB_DEM_DEFAULT_STICK;
                 for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = PB_DEM_DEFAULT_TSD(d); }
                 c_ivm[(size_t) slot * cap + i] = PB_DEM_DEFAULT_IVM;
+                PB_DEM_NX_LOOP(x, a) { c_x[((size_t) x * C + slot) * cap + i] = a.x_default[x]; }
             }
             if(FUSED) { usedmask |= 1u << slot; } else { c_used[(size_t) slot * cap + i] = 1; }
             double tsd[3] = {c_tsd[((size_t) 0 * C + slot) * cap + i], c_tsd[((size_t) 1 * C + slot) * cap + i],
                              c_tsd[((size_t) 2 * C + slot) * cap + i]};
             double ivm = c_ivm[(size_t) slot * cap + i];
             int stick = c_stick[(size_t) slot * cap + i];
+#ifdef PB_DEM_NX
+            double cx[PB_DEM_NX];
+            PB_DEM_NX_LOOP(x, a) { cx[x] = c_x[((size_t) x * C + slot) * cap + i]; }
+#else
+            double *cx = nullptr;
+            (void) cx;
+#endif
             const double vj[3] = {vel[j], vel[(size_t) cap + j], vel[(size_t) 2 * cap + j]};
             const double wj[3] = {angvel[j], angvel[(size_t) cap + j], angvel[(size_t) 2 * cap + j]};
             const int tj = pb_w_type(pj4.w);
             double Fp[3], Tp[3];
 #ifdef PB_DEM_USER_PAIR
             // a contact model generated from a user's kernel body; false = skip_when() left the pair (no force, no torque)
-            if(!PB_DEM_USER_PAIR(xi, vi, wi, mass[i], ri, xj, vj, wj, mass[j], radius[j], n, cp, delta, ti + tj, tsd, &ivm, &stick, Fp, Tp)) {
+            if(!PB_DEM_USER_PAIR(xi, vi, wi, mass[i], ri, xj, vj, wj, mass[j], radius[j], n, cp, delta, ti + tj, tsd, &ivm, &stick, cx, Fp, Tp)) {
                 for(int d = 0; d < 3; d++) { Fp[d] = 0.0; Tp[d] = 0.0; }
             }
 #else
@@ -167,6 +189,9 @@ __device__ __forceinline__ void pb_dem_force_particle(const PbDemForceArgs &a, c
             for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + slot) * cap + i] = tsd[d]; }
             c_ivm[(size_t) slot * cap + i] = ivm;
             c_stick[(size_t) slot * cap + i] = stick;
+#ifdef PB_DEM_NX
+            PB_DEM_NX_LOOP(x, a) { c_x[((size_t) x * C + slot) * cap + i] = cx[x]; }
+#endif
             for(int d = 0; d < 3; d++) { F[d] = F[d] + Fp[d]; T[d] = T[d] + Tp[d]; }
         }
         if(FUSED) { ncont_end = ncont; } else { num_contacts[i] = ncont; }
@@ -183,6 +208,7 @@ __device__ __forceinline__ void pb_dem_force_particle(const PbDemForceArgs &a, c
                     c_stick[(size_t) c * cap + i] = c_stick[(size_t) last * cap + i];
                     for(int d = 0; d < 3; d++) { c_tsd[((size_t) d * C + c) * cap + i] = c_tsd[((size_t) d * C + last) * cap + i]; }
                     c_ivm[(size_t) c * cap + i] = c_ivm[(size_t) last * cap + i];
+                    PB_DEM_NX_LOOP(x, a) { c_x[((size_t) x * C + c) * cap + i] = c_x[((size_t) x * C + last) * cap + i]; }
                     c_uid[(size_t) c * cap + i] = c_uid[(size_t) last * cap + i];
                     usedmask = (usedmask & ~(1u << c)) | (((usedmask >> last) & 1u) << c);
                 }

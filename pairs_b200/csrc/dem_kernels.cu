@@ -67,14 +67,22 @@ int pb_dem_grow(pb_ctx *ctx, size_t oldcap, size_t newcap, size_t used) {
     PB_TRY(grow_int(&ctx->contact_stick, C));
     PB_TRY(pb_regrow_soa(ctx, &ctx->contact_tsd, 3 * C, oldcap, newcap, used, true));
     PB_TRY(pb_regrow_soa(ctx, &ctx->contact_ivm, C, oldcap, newcap, used, true));
+    if(ctx->cx > 0) { PB_TRY(pb_regrow_soa(ctx, &ctx->contact_x, ctx->cx * C, oldcap, newcap, used, true)); }
     return 0;
 }
 
 // use_contact_history=True path of pairs.simulation(): allocates the DEM property set.  contact_capacity = neighbor_capacity.
-extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) {
+extern "C" int pb_dem_enable(pb_ctx *ctx, int contact_capacity) { return pb_dem_enable_ex(ctx, contact_capacity, 0, nullptr); }
+
+// ... with `extra_lanes` further double lanes per contact (contact properties beyond dem.py's three, used by contact models
+// compiled at run time) and the values a fresh contact starts from
+extern "C" int pb_dem_enable_ex(pb_ctx *ctx, int contact_capacity, int extra_lanes, const double *extra_defaults) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(ctx->dem) { return 0; }
     if(contact_capacity < 1 || contact_capacity > 64) { ctx->set_error("pb_dem_enable: 1 <= contact_capacity <= 64"); return -1; }
+    if(extra_lanes < 0 || extra_lanes > 16) { ctx->set_error("pb_dem_enable_ex: 0 <= extra_lanes <= 16"); return -1; }
+    ctx->cx = extra_lanes;
+    for(int k = 0; k < extra_lanes; k++) { ctx->cx_default[k] = (extra_defaults != nullptr) ? extra_defaults[k] : 0.0; }
     ctx->ccontacts = contact_capacity;
     ctx->dem = true;
     if(ctx->send_cap > 0) {        // wire records grow (contact history travels with migrating particles): re-size the buffers
@@ -317,6 +325,35 @@ extern "C" int pb_dem_upload_contacts(pb_ctx *ctx, int n, const int *num, const 
     return 0;
 }
 
+// the extra lanes of the contact rows (pb_dem_enable_ex): host layout [n][contact_capacity][extra_lanes]
+__global__ void __launch_bounds__(128) pb_k_contact_extras(int n, int cap, int C, int nx, int to_device, double *__restrict__ host_layout,
+                                                           double *__restrict__ cx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) { return; }
+    for(int c = 0; c < C; c++) {
+        for(int x = 0; x < nx; x++) {
+            double *h = host_layout + ((size_t) i * C + c) * nx + x, *d = cx + ((size_t) x * C + c) * cap + i;
+            if(to_device) { *d = *h; } else { *h = *d; }
+        }
+    }
+}
+
+extern "C" int pb_dem_contact_extras(pb_ctx *ctx, int n, double *values, int upload) {
+    PB_CHECK(cudaSetDevice(ctx->device));
+    if(!ctx->dem || n > ctx->pcap) { ctx->set_error("pb_dem_contact_extras: DEM not enabled / beyond capacity"); return -1; }
+    if(n == 0 || ctx->cx == 0) { return 0; }
+    const size_t bytes = sizeof(double) * (size_t) n * ctx->ccontacts * ctx->cx;
+    PbScratch buf;
+    PB_CHECK(buf.alloc(bytes));
+    if(upload) { PB_CHECK(cudaMemcpyAsync(buf.as<double>(), values, bytes, cudaMemcpyHostToDevice, ctx->stream)); }
+    PB_LAUNCH(pb_k_contact_extras, pb_blocks(n, 128), 128, n, ctx->pcap, ctx->ccontacts, ctx->cx, upload, buf.as<double>(), ctx->contact_x);
+    if(!upload) { PB_CHECK(cudaMemcpyAsync(values, buf.as<double>(), bytes, cudaMemcpyDeviceToHost, ctx->stream)); }
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int pb_dem_contact_extra_lanes(const pb_ctx *ctx) { return ctx->cx; }
+
 extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, int *used, int *sticking, double *tsd, double *ivm) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(!ctx->dem || n > ctx->pcap) { ctx->set_error("pb_dem_download_contacts: DEM not enabled / beyond capacity"); return -1; }
@@ -347,9 +384,9 @@ extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, 
 // DEM part of an exchange record, appended after the 12 base elements: radius, angvel[3], normal[3], inv_inertia[9],
 // rotmat[9], quat[4], num_contacts, then per slot: uid, sticking, tsd[3], ivm.
 struct PbDemArrays {
-    double *radius, *angvel, *normal, *inv_inertia, *rotmat, *quat, *c_tsd, *c_ivm;
+    double *radius, *angvel, *normal, *inv_inertia, *rotmat, *quat, *c_tsd, *c_ivm, *c_x;
     int *num_contacts, *c_uid, *c_used, *c_stick;
-    int cap, C;
+    int cap, C, nx;
 };
 
 static PbDemArrays pb_dem_arrays(const pb_ctx *ctx) {
@@ -357,6 +394,7 @@ static PbDemArrays pb_dem_arrays(const pb_ctx *ctx) {
     a.radius = ctx->radius; a.angvel = ctx->angvel; a.normal = ctx->normal; a.inv_inertia = ctx->inv_inertia; a.rotmat = ctx->rotmat;
     a.quat = ctx->quat; a.c_tsd = ctx->contact_tsd; a.c_ivm = ctx->contact_ivm; a.num_contacts = ctx->num_contacts;
     a.c_uid = ctx->contact_uid; a.c_used = ctx->contact_used; a.c_stick = ctx->contact_stick; a.cap = ctx->pcap; a.C = ctx->ccontacts;
+    a.c_x = ctx->contact_x; a.nx = ctx->cx;
     return a;
 }
 
@@ -377,6 +415,7 @@ __device__ __forceinline__ void pb_dem_pack_one(const PbDemArrays &a, int p, dou
         b[k++] = live ? (double) a.c_stick[c * cap + p] : 0.0;
         for(int d = 0; d < 3; d++) { b[k++] = live ? a.c_tsd[((size_t) d * a.C + c) * cap + p] : 0.0; }
         b[k++] = live ? a.c_ivm[c * cap + p] : 0.0;
+        for(int x = 0; x < a.nx; x++) { b[k++] = live ? a.c_x[((size_t) x * a.C + c) * cap + p] : 0.0; }
     }
 }
 
@@ -396,6 +435,7 @@ __device__ __forceinline__ void pb_dem_unpack_one(const PbDemArrays &a, int p, c
         a.c_stick[c * cap + p] = (int) b[k++];
         for(int d = 0; d < 3; d++) { a.c_tsd[((size_t) d * a.C + c) * cap + p] = b[k++]; }
         a.c_ivm[c * cap + p] = b[k++];
+        for(int x = 0; x < a.nx; x++) { a.c_x[((size_t) x * a.C + c) * cap + p] = b[k++]; }
         a.c_used[c * cap + p] = (c < nc) ? 1 : 0;      // as the reference's unpack marks transferred contacts used
     }
 }
@@ -434,6 +474,7 @@ __global__ void __launch_bounds__(128) pb_k_dem_move(const int *__restrict__ cou
         a.c_stick[c * cap + t] = a.c_stick[c * cap + s];
         a.c_ivm[c * cap + t] = a.c_ivm[c * cap + s];
         for(int d = 0; d < 3; d++) { a.c_tsd[((size_t) d * a.C + c) * cap + t] = a.c_tsd[((size_t) d * a.C + c) * cap + s]; }
+        for(int x = 0; x < a.nx; x++) { a.c_x[((size_t) x * a.C + c) * cap + t] = a.c_x[((size_t) x * a.C + c) * cap + s]; }
     }
 }
 
@@ -520,6 +561,7 @@ int pb_dem_sort_locals(pb_ctx *ctx) {
     PB_TRY(pb_permute_f64(ctx, ctx->quat, 4, perm, n));
     PB_TRY(pb_permute_f64(ctx, ctx->contact_tsd, 3 * C, perm, n));
     PB_TRY(pb_permute_f64(ctx, ctx->contact_ivm, C, perm, n));
+    if(ctx->cx > 0) { PB_TRY(pb_permute_f64(ctx, ctx->contact_x, ctx->cx * C, perm, n)); }
     PB_TRY(pb_permute_i32(ctx, ctx->num_contacts, 1, perm, n));
     PB_TRY(pb_permute_i32(ctx, ctx->contact_uid, C, perm, n));
     PB_TRY(pb_permute_i32(ctx, ctx->contact_used, C, perm, n));
@@ -595,7 +637,7 @@ extern "C" int pb_dem_reset_contact_usage(pb_ctx *ctx) {
 // clear_unused_contact_history (sim/contact_history.py:90-127, cell-list branch): unused slots are overwritten by the last slot
 __global__ void __launch_bounds__(256) pb_k_dem_clear_unused(int n, int cap, int C, int *__restrict__ num, int *__restrict__ uid,
                                                             int *__restrict__ used, int *__restrict__ stick, double *__restrict__ tsd,
-                                                            double *__restrict__ ivm) {
+                                                            double *__restrict__ ivm, int nx, double *__restrict__ cx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i >= n) { return; }
     int c = 0, cnt = num[i];
@@ -606,6 +648,7 @@ __global__ void __launch_bounds__(256) pb_k_dem_clear_unused(int n, int cap, int
                 stick[(size_t) c * cap + i] = stick[(size_t) last * cap + i];
                 for(int d = 0; d < 3; d++) { tsd[((size_t) d * C + c) * cap + i] = tsd[((size_t) d * C + last) * cap + i]; }
                 ivm[(size_t) c * cap + i] = ivm[(size_t) last * cap + i];
+                for(int x = 0; x < nx; x++) { cx[((size_t) x * C + c) * cap + i] = cx[((size_t) x * C + last) * cap + i]; }
                 uid[(size_t) c * cap + i] = uid[(size_t) last * cap + i];
                 used[(size_t) c * cap + i] = used[(size_t) last * cap + i];
             }
@@ -622,7 +665,7 @@ extern "C" int pb_dem_clear_unused_contacts(pb_ctx *ctx) {
     PbStage st(ctx, "clear_unused_contact_history");
     if(ctx->nlocal == 0) { return 0; }
     PB_LAUNCH(pb_k_dem_clear_unused, pb_blocks(ctx->nlocal, 256), 256, ctx->nlocal, ctx->pcap, ctx->ccontacts, ctx->num_contacts,
-              ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm);
+              ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->cx, ctx->contact_x);
     return 0;
 }
 
@@ -706,6 +749,8 @@ static PbDemForceArgs pb_dem_force_args(pb_ctx *ctx, int accumulate) {
     a.fric_s = ctx->d_fric_static; a.fric_d = ctx->d_fric_dynamic;
     a.num_contacts = ctx->num_contacts; a.c_uid = ctx->contact_uid; a.c_used = ctx->contact_used; a.c_stick = ctx->contact_stick;
     a.c_tsd = ctx->contact_tsd; a.c_ivm = ctx->contact_ivm; a.force = ctx->force; a.torque = ctx->torque;
+    a.c_x = ctx->contact_x; a.nx = ctx->cx;
+    for(int k = 0; k < 16; k++) { a.x_default[k] = ctx->cx_default[k]; }
     a.accumulate = accumulate;
     a.overflow = ctx->d_dem_flag;
     return a;
@@ -796,6 +841,7 @@ static int pb_dem_grow_contacts(pb_ctx *ctx, int newC) {
         PB_TRY(grow(&ctx->contact_stick, 1));
         PB_TRY(grow(&ctx->contact_ivm, 1));
         PB_TRY(grow(&ctx->contact_tsd, 3));
+        if(ctx->cx > 0) { PB_TRY(grow(&ctx->contact_x, ctx->cx)); }
     }
     ctx->ccontacts = newC;
     if(ctx->send_cap > 0) {        // the wire records grew with the rows

@@ -401,7 +401,8 @@ class Simulation:
                                            property in the column order the manifest lists (vectors 3 columns, matrices 9,
                                            quaternions 4), 17 significant digits, i.e. every double survives the round trip
           <filename>_<ts>[_r<rank>].contacts.csv   DEM: uid_i, uid_j, is_sticking, tangential_spring_displacement x 3,
-                                           impact_velocity_magnitude for every live contact
+                                           impact_velocity_magnitude (and the lanes of any further contact property) for
+                                           every live contact
           <filename>_<ts>.json             the manifest (columns, iteration, ranks, domain)
         read_checkpoint(filename, ts) in a later script continues from it, on any number of ranks."""
         self.ckpt_file = filename
@@ -458,13 +459,15 @@ class Simulation:
         np.savetxt(f"{self.ckpt_file}_{ts}{infix}.csv", table, delimiter=",", fmt="%.17g")
         if dem:
             c = ctx.dem_download_contacts(ctx.counts()[0])
+            cx = ctx.dem_download_contact_extras(ctx.counts()[0])         # further contact properties: columns after the seven
             uid = ctx.ints("uid")
             rows = []
             for i in np.nonzero(c["num_contacts"])[0]:
                 for k in range(int(c["num_contacts"][i])):
                     rows.append([uid[i], c["contact_lists"][i, k], c["is_sticking"][i, k], *c["tangential_spring_displacement"][i, k],
-                                 c["impact_velocity_magnitude"][i, k]])
-            np.savetxt(f"{self.ckpt_file}_{ts}{infix}.contacts.csv", np.asarray(rows, np.float64).reshape(len(rows), 7), delimiter=",", fmt="%.17g")
+                                 c["impact_velocity_magnitude"][i, k], *cx[i, k]])
+            np.savetxt(f"{self.ckpt_file}_{ts}{infix}.contacts.csv", np.asarray(rows, np.float64).reshape(len(rows), 7 + cx.shape[2]),
+                       delimiter=",", fmt="%.17g")
         if rank == 0:
             manifest = {"iteration": ts, "ranks": world, "dem": dem, "domain": list(self.grid),
                         "columns": [[n, int(np.asarray(a).reshape(len(a), -1).shape[1]) if len(a) else 1, "int" if np.asarray(a).dtype.kind == "i" else "real"]
@@ -754,7 +757,7 @@ class Simulation:
         eul = next((e for e in self.functions if e["family"] == "euler"), None)
         # the native loop (pb_dem_run) is the generated loop of examples/dem.py: the standard list, reneighbouring every iteration
         standard = fams in (["gravity", "linear_spring_dashpot", "euler"], ["gravity", "generic_pair", "euler"]) and self.reneighbor_frequency == 1
-        ctx.dem_enable(self.neighbor_capacity)
+        ctx.dem_enable(self.neighbor_capacity, self._contact_layout()[2])
         for name, comps, volatile, dflt in self._dem_user_props():
             _, row0 = ctx.add_property(name, comps, volatile, dflt)
             assert row0 == self._dem_storage()[name][1]
@@ -824,6 +827,7 @@ class Simulation:
             num = np.zeros(n, np.int32)
             cuid, stick = np.zeros((n, C), np.int32), np.zeros((n, C), np.int32)
             tsd, ivm = np.zeros((n, C, 3)), np.zeros((n, C))
+            cx = np.zeros((n, C, ctx.contact_extra_lanes))
             row_of = {int(u): k for k, u in enumerate(restored["uid"])}
             for r in restored["contacts"]:
                 i = row_of.get(int(r[0]))
@@ -833,8 +837,11 @@ class Simulation:
                 if k >= C:
                     raise DslError("read_checkpoint: more contacts per particle than the contact capacity (neighbor_capacity)")
                 cuid[i, k], stick[i, k], tsd[i, k], ivm[i, k] = int(r[1]), int(r[2]), r[3:6], r[6]
+                cx[i, k] = r[7:7 + cx.shape[2]]
                 num[i] = k + 1
             ctx.dem_upload_contacts(num, cuid, stick, tsd, ivm)
+            if cx.size:
+                ctx.dem_upload_contact_extras(cx)
         for f in self.setup_functions:
             if f["family"] == "update_mass_and_inertia":
                 ctx.dem_stage("update_mass_and_inertia")
@@ -933,6 +940,28 @@ class Simulation:
             if self._vtk_due(ts):
                 self._vtk_write(ctx, ts, rank, world)
 
+    def _contact_layout(self):
+        """Where each contact property lives: the first integer, vector and real ones take the three columns examples/dem.py declares
+        (is_sticking, tangential_spring_displacement, impact_velocity_magnitude); any further one -- the reference gives every
+        add_contact_property() its own array, mapping/funcs.py:230-263 -- takes lanes of the contact's extra doubles
+        (pb_dem_enable_ex).  -> ({name: kind}, {kind: default} of the three, [default per extra lane])."""
+        contact, defaults, extra = {}, {}, []
+        for name, (ptype, default) in self.contact_props.items():
+            kind = {Types.Int32: "c_stick", Types.Vector: "c_tsd", Types.Real: "c_ivm"}.get(ptype)
+            if kind is None:
+                raise DslError(f"contact property '{name}': contact properties are integers, reals or vectors")
+            if kind in contact.values():
+                ctype, width = {"c_stick": ("int", 1), "c_tsd": ("vec", 3), "c_ivm": ("real", 1)}[kind]
+                if len(extra) + width > 16:
+                    raise DslError(f"contact property '{name}': at most 16 doubles per contact beyond the first integer, vector and real")
+                contact[name] = f"cx:{ctype}:{len(extra)}"
+                d = list(default) if isinstance(default, (list, tuple)) else [default] * width
+                extra += [np.float64(int(x) if ctype == "int" else x).item() for x in d[:width]]        # (float is the DSL type here)
+                continue
+            contact[name] = kind
+            defaults[kind] = default
+        return contact, defaults, extra
+
     def _translate_dem_model(self, e):
         """-> (function name, CUDA source, number of types) of a user-defined contact model (kernelgen.translate_dem_model).  The
         kernel hands a model the DEM property set of examples/dem.py by these names; contact properties are told apart by type."""
@@ -944,19 +973,14 @@ class Simulation:
                 storage[name] = slot
         for name in self.props:
             storage.setdefault(name, name)               # anything else: named in the error message if the body touches it
-        contact, defaults = {}, {}
-        for name, (ptype, default) in self.contact_props.items():
-            kind = {Types.Int32: "c_stick", Types.Vector: "c_tsd", Types.Real: "c_ivm"}.get(ptype)
-            if kind is None or kind in contact.values():
-                raise DslError(f"contact property '{name}': the contact table holds one integer, one vector and one real per contact")
-            contact[name] = kind
-            defaults[kind] = default
+        contact, defaults, extra_defaults = self._contact_layout()
         nk, tables = 1, {}
         for name, (feat, data) in self.feature_props.items():
             tables[name] = data
             nk = self.features[feat]
         try:
-            name, src = kernelgen.translate_dem_model(e["func"], storage, contact, tables, e["symbols"], contact_defaults=defaults)
+            name, src = kernelgen.translate_dem_model(e["func"], storage, contact, tables, e["symbols"], contact_defaults=defaults,
+                                                      extra_lanes=len(extra_defaults))
         except kernelgen.KernelGenError as err:
             raise DslError(f"contact model '{e['name']}': {err}") from None
         return name, src, nk

@@ -307,6 +307,11 @@ class _Gen:
                 kind = self.contact[prop]
                 if kind == "c_tsd":
                     return self.vec([self.tmp("double", f"tsd[{d}]") for d in range(3)])
+                if kind.startswith("cx:"):                    # a further contact property: lanes of cx[] (pb_dem_enable_ex)
+                    _, ctype, off = kind.split(":")
+                    if ctype == "vec":
+                        return self.vec([self.tmp("double", f"cx[{int(off) + d}]") for d in range(3)])
+                    return ("f", self.tmp("double", f"cx[{off}]")) if ctype == "real" else ("i", self.tmp("int", f"(int) cx[{off}]"))
                 return ("f", self.tmp("double", "*ivm")) if kind == "c_ivm" else ("i", self.tmp("int", "*sticking"))
             if prop in self.tables:
                 return ("f", self.tmp("double", f"fp_{prop}[tij]"))
@@ -604,7 +609,18 @@ class _Gen:
             if not isinstance(tgt.slice, ast.Tuple) or [getattr(e, "id", None) for e in tgt.slice.elts] != ["i", "j"]:
                 raise KernelGenError("contact properties are assigned as prop[i, j] = ...")
             kind, v = self.contact[tgt.value.id], self.expr(node.value)
-            if kind == "c_tsd":
+            if kind.startswith("cx:"):
+                _, ctype, off = kind.split(":")
+                if (ctype == "vec") != bool(self.is_vec(v)):
+                    raise KernelGenError(f"'{tgt.value.id}' is a {'vector' if ctype == 'vec' else 'scalar'} contact property")
+                if ctype == "vec":
+                    for d, c in enumerate(v[1]):
+                        self.lines.append(f"cx[{int(off) + d}] = {c};")
+                elif ctype == "real":
+                    self.lines.append(f"cx[{off}] = {v[1]};")
+                else:
+                    self.lines.append(f"cx[{off}] = (double) (int) ({v[1]});")
+            elif kind == "c_tsd":
                 if not self.is_vec(v):
                     raise KernelGenError(f"'{tgt.value.id}' is a vector contact property")
                 for d, c in enumerate(v[1]):
@@ -816,18 +832,21 @@ def translate(func, storage, feature_tables, ntypes, symbols, prelude, skip_fixe
     return kind, name, "\n".join(out) + "\n"
 
 
-def translate_dem_model(func, storage, contact, feature_tables, symbols, contact_defaults=None):
+def translate_dem_model(func, storage, contact, feature_tables, symbols, contact_defaults=None, extra_lanes=0):
     """A DEM contact model (the body of a pair kernel over contact history, e.g. examples/dem.py:18-74) -> (function name, CUDA
     source) of the device function the library's contact kernel calls for every touching pair (csrc/dem_force_kernel.cuh):
 
-        bool f(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, n, cp, delta, tij, tsd, ivm, sticking, F, T)
+        bool f(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, n, cp, delta, tij, tsd, ivm, sticking, cx, F, T)
 
     xi.. = position, linear velocity, angular velocity, mass, radius of i and j; n / cp / delta = contact normal, contact point and
     -penetration_depth from the kernel's geometry pass; tij = type[i] * ntypes + type[j] (feature properties are literal tables);
     tsd / ivm / sticking = this pair's contact properties (in / out); F / T = what the body apply()s to force / torque.
     Returns false when a skip_when() left the pair.  `storage`: property name -> 'pos' | 'vel' | 'angvel' | 'mass' | 'radius' |
-    'force' | 'torque'; `contact`: contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick'; `contact_defaults`: kind -> the default of
-    add_contact_property() a fresh contact slot starts from (zeros if absent)."""
+    'force' | 'torque'; `contact`: contact property name -> 'c_tsd' | 'c_ivm' | 'c_stick' (the three columns examples/dem.py
+    declares) or 'cx:real:<lane>' | 'cx:vec:<lane>' | 'cx:int:<lane>' for further contact properties, which live in the `extra_lanes`
+    double lanes cx[] of the contact (pb_dem_enable_ex; an integer is held as an exact double); `contact_defaults`: kind -> the
+    default of add_contact_property() a fresh contact slot starts from (zeros if absent; the extra lanes' defaults go to
+    pb_dem_enable_ex)."""
     tree = _function_ast(func)
     if not isinstance(tree, ast.FunctionDef) or [a.arg for a in tree.args.args] != ["i", "j"]:
         raise KernelGenError(f"{func.__name__}: a contact model takes (i, j)")
@@ -837,6 +856,8 @@ def translate_dem_model(func, storage, contact, feature_tables, symbols, contact
     for node in tree.body:
         g.stmt(node)
     out = []
+    if extra_lanes > 0:
+        out.append(f"#define PB_DEM_NX {int(extra_lanes)}")
     for kind, value in (contact_defaults or {}).items():
         if kind == "c_stick":
             out.append(f"#define PB_DEM_DEFAULT_STICK {int(value)}")
@@ -849,7 +870,7 @@ def translate_dem_model(func, storage, contact, feature_tables, symbols, contact
         out.append(f"__device__ const double fp_{fp}[{len(table)}] = {{{', '.join(_lit(float(x)) for x in table)}}};")
     out.append(f"__device__ __forceinline__ bool {name}(const double *xi, const double *vi, const double *wi, double mi, double ri, "
                "const double *xj, const double *vj, const double *wj, double mj, double rj, const double *n, const double *cp, "
-               "double delta, int tij, double *tsd, double *ivm, int *sticking, double *F, double *T) {")
+               "double delta, int tij, double *tsd, double *ivm, int *sticking, double *cx, double *F, double *T) {")
     out.append("    F[0] = 0.0; F[1] = 0.0; F[2] = 0.0; T[0] = 0.0; T[1] = 0.0; T[2] = 0.0;")
     out += ["    " + ln for ln in g.lines]
     out.append("    return true;")

@@ -78,6 +78,27 @@ def linear_spring_dashpot(i, j):
     apply(torque, cross(contact_point(i, j) - position, partial_force))
 
 
+def contact_model_with_more_properties():
+    """linear_spring_dashpot followed by three statements on FURTHER contact properties (a second vector, a second real, a second
+    integer; declared in build(more_contact_props=True)) -- the case SURVEY.md 8f names: the reference gives every
+    add_contact_property() its own array, so a model may keep any per-contact state.  The text is composed from the function above
+    and written to a file (kernels are translated from their source)."""
+    import importlib.util
+    import inspect
+    import tempfile
+    src = inspect.getsource(linear_spring_dashpot).replace("def linear_spring_dashpot(", "def spring_dashpot_more(")
+    src += ("\n    tsd_seen[i, j] = tangential_spring_displacement[i, j]\n"
+            "    contact_age[i, j] = contact_age[i, j] + 1.0\n"
+            "    hits[i, j] = hits[i, j] + 2\n")
+    fd, path = tempfile.mkstemp(prefix="dem_model_", suffix=".py")
+    with os.fdopen(fd, "w") as f:
+        f.write(src)
+    spec = importlib.util.spec_from_file_location(os.path.basename(path)[:-3], path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.spring_dashpot_more
+
+
 def euler(i):
     inv_mass = 1.0 / mass[i]
     position[i] += 0.5 * inv_mass * force[i] * dt * dt + linear_velocity[i] * dt
@@ -95,7 +116,7 @@ def gravity(i):
 
 
 def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=None, per_cell=False, vtk=None, reneighbor=None,
-          checkpoint=None, restart=None, contact_capacity=20):
+          checkpoint=None, restart=None, contact_capacity=20, more_contact_props=False):
     diameter_SI, gravity_SI, densityFluid_SI, densityParticle_SI = 0.0029, 9.81, 1000, 2550
     generationSpacing_SI, initialVelocity_SI, dt_SI = 0.005, 1, 5e-5
     frictionCoefficient, restitutionCoefficient, collisionTime_SI, poissonsRatio = 0.5, 0.1, 5e-4, 0.22
@@ -125,6 +146,10 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
     psim.add_contact_property('is_sticking', pairs.int32(), 0)
     psim.add_contact_property('tangential_spring_displacement', pairs.vector(), [0.0, 0.0, 0.0])
     psim.add_contact_property('impact_velocity_magnitude', pairs.real(), 0.0)
+    if more_contact_props:
+        psim.add_contact_property('tsd_seen', pairs.vector(), [0.0, 0.0, 0.0])
+        psim.add_contact_property('contact_age', pairs.real(), -1.0)          # -1: the first evaluation of a contact leaves age 0
+        psim.add_contact_property('hits', pairs.int32(), 3)
     psim.set_domain([0.0, 0.0, 0.0, domain[0], domain[1], domain[2]])
     psim.set_domain_partitioner(pairs.regular_domain_partitioner_xy())
     psim.pbc([True, True, False])
@@ -156,7 +181,7 @@ def build(target="gpu", domain=(0.1, 0.015, 0.04), timesteps=300, planes_file=No
         psim.vtk_output(vtk[0], frequency=vtk[1])          # examples/dem.py:194
     psim.compute(gravity, symbols={'densityParticle_SI': densityParticle_SI, 'densityFluid_SI': densityFluid_SI,
                                    'gravity_SI': gravity_SI, 'pi': math.pi})
-    psim.compute(linear_spring_dashpot, linkedCellWidth, symbols={'dt': dt_SI, 'pi': math.pi, 'kappa': kappa,
+    psim.compute(contact_model_with_more_properties() if more_contact_props else linear_spring_dashpot, linkedCellWidth, symbols={'dt': dt_SI, 'pi': math.pi, 'kappa': kappa,
                                                                    'lnDryResCoeff': lnDryResCoeff, 'collisionTime_SI': collisionTime_SI})
     psim.compute(euler, symbols={'dt': dt_SI})
     if reneighbor is not None:          # oracle variant dem_rn3_t1: cell lists / ghosts every `reneighbor` iterations

@@ -498,6 +498,9 @@ def test_checkpoint_files_round_trip_every_bit_and_split_over_ranks(tmp_path):
                     "is_sticking": r.integers(0, 2, (n, C)).astype(np.int32), "tangential_spring_displacement": r.standard_normal((n, C, 3)),
                     "impact_velocity_magnitude": r.standard_normal((n, C))}
 
+        def dem_download_contact_extras(self, n):          # two lanes of a further contact property
+            return np.random.default_rng(8).standard_normal((n, C, 2))
+
         def decomposition(self):
             return {"nranks": np.array([2 if self.hi - self.lo < 0.09 else 1, 1, 1]), "subdom": np.array([self.lo, self.hi, 0.0, 0.015, 0.0, 0.04])}
 
@@ -511,9 +514,27 @@ def test_checkpoint_files_round_trip_every_bit_and_split_over_ranks(tmp_path):
         assert np.array_equal(whole[k], np.concatenate([a.arr[k], b.arr[k]])), k
     assert len(whole["contacts"]) == int(a.num.sum() + b.num.sum())
     assert set(whole["contacts"][:, 0].astype(int)) <= set(whole["uid"].tolist())
+    first = np.nonzero(a.num)[0][0]                       # columns: the seven of dem.py's table, then the further lanes
+    assert whole["contacts"].shape[1] == 9 and np.array_equal(whole["contacts"][0, 7:], a.dem_download_contact_extras(7)[first, 0])
     # re-split on other sub-boxes: every row lands on exactly one rank
     left = psim._checkpoint_read(FakeCtx(0, 0.0, 0.03, 9), str(tmp_path / "ck"), 5)
     right = psim._checkpoint_read(FakeCtx(0, 0.03, 0.1, 9), str(tmp_path / "ck"), 5)
     assert len(left["uid"]) + len(right["uid"]) >= len(whole["uid"]) - 1            # (a row within 1e-5 of the cut belongs to nobody,
     assert not set(left["uid"].tolist()) & set(right["uid"].tolist())               #  as in runtime/read_from_file.hpp:106)
     assert rng is not None
+
+
+def test_contact_layout_puts_further_contact_properties_into_extra_lanes():
+    """The first integer / vector / real contact property take examples/dem.py's three columns; every further one gets lanes of the
+    contact's extra doubles (mapping/funcs.py:230-263 gives each add_contact_property() its own array), defaults included."""
+    import dem_script
+    psim = dem_script.build("gpu", (0.1, 0.015, 0.04), 10, more_contact_props=True)
+    contact, defaults, extra = psim._contact_layout()
+    assert contact == {"is_sticking": "c_stick", "tangential_spring_displacement": "c_tsd", "impact_velocity_magnitude": "c_ivm",
+                       "tsd_seen": "cx:vec:0", "contact_age": "cx:real:3", "hits": "cx:int:4"}
+    assert extra == [0.0, 0.0, 0.0, -1.0, 3.0] and defaults["c_ivm"] == 0.0
+    assert [e["family"] for e in psim.functions] == ["gravity", "generic_pair", "euler"]
+    name, src, nk = psim._translate_dem_model(psim.functions[1])
+    assert src.startswith("#define PB_DEM_NX 5\n") and "cx[3] = " in src and nk == 1
+    plain = dem_script.build("gpu", (0.1, 0.015, 0.04), 10)
+    assert plain._contact_layout()[2] == []

@@ -107,6 +107,42 @@ def test_generated_dem_contact_model_reproduces_the_built_in_run_bit_for_bit(cap
         assert np.array_equal(a[k], b[k]), k
 
 
+def test_contact_model_with_further_contact_properties_keeps_them_with_the_contact(capsys):
+    """a contact table with MORE than examples/dem.py's three properties.  dem_script.build(more_contact_props=True)
+    declares a second vector, a second real (default -1) and a second integer (default 3) contact property and appends
+    `tsd_seen = tsd; age += 1.0; hits += 2` to dem.py's model.  The extra state changes no force, so after 300 iterations the run
+    equals the built-in one bit for bit -- particles and the three standard columns -- while every live contact's further
+    properties hold what those statements say: the displacement copy is the displacement, hits = 3 + 2 (age + 1), and the ages are
+    the numbers of iterations the contacts have existed (their maximum reaches back to the first impacts).  Rows are compacted
+    (clear_unused_contact_history) and spatially re-sorted during the run, so lanes that did not follow their slot would show."""
+    import dem_script
+    from tests import dem_common as dc
+    ref_ctx = dem_script.build("gpu", dc.DOMAIN, 300).generate()
+    psim = dem_script.build("gpu", dc.DOMAIN, 300, more_contact_props=True)
+    assert [e["family"] for e in psim.functions] == ["gravity", "generic_pair", "euler"]
+    ctx = psim.generate()
+    capsys.readouterr()
+    n = ctx.counts()[0]
+    assert n == ref_ctx.counts()[0] == 422 and ctx.contact_extra_lanes == 5 and ref_ctx.contact_extra_lanes == 0
+    for name in ("position", "linear_velocity"):
+        assert np.array_equal(ctx.real(name), ref_ctx.real(name)), name
+    assert np.array_equal(ctx.dem_download("angular_velocity", n), ref_ctx.dem_download("angular_velocity", n))
+    a, b = ctx.dem_download_contacts(n), ref_ctx.dem_download_contacts(n)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    cx = ctx.dem_download_contact_extras(n)
+    live = np.arange(cx.shape[1])[None, :] < a["num_contacts"][:, None]
+    assert live.sum() > 100
+    assert np.array_equal(cx[live][:, :3], a["tangential_spring_displacement"][live])
+    age, hits = cx[live][:, 3], cx[live][:, 4]
+    assert np.array_equal(hits, 3.0 + 2.0 * (age + 1.0)) and age.min() >= 0.0 and np.array_equal(age, np.round(age))
+    assert 20 <= age.max() < 300 and len(np.unique(age)) > 10
+    # the host <-> device path of the lanes: what is uploaded comes back
+    back = np.random.default_rng(3).standard_normal(cx.shape)
+    ctx.dem_upload_contact_extras(back)
+    assert np.array_equal(ctx.dem_download_contact_extras(n), back)
+
+
 def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in_run(capsys):
     """A DEM procedure list that is not exactly gravity / model / euler runs module by module with the user bodies generated: here
     gravity, euler and the set-up function update_mass_and_inertia are sent through the generic path (matrix / quaternion algebra
@@ -294,6 +330,16 @@ def _ngpus():
         return sum(1 for line in out.splitlines() if line.startswith("GPU "))
     except Exception:
         return 0
+
+
+@pytest.mark.parametrize("world", [2])
+def test_further_contact_properties_migrate_with_their_contact(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29850 + world), os.path.join(ROOT, "tests", "scripts", "mgpu_contact_props_check.py")]
+    r = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "mgpu_contact_props_check ok" in r.stdout, r.stdout[-4000:]
 
 
 @pytest.mark.parametrize("world", [2, 4])

@@ -489,9 +489,11 @@ DEM_STORAGE = {"position": "pos", "linear_velocity": "vel", "angular_velocity": 
 DEM_CONTACT = {"is_sticking": "c_stick", "tangential_spring_displacement": "c_tsd", "impact_velocity_magnitude": "c_ivm"}
 
 
-def _model_vs_builtin(tmp_path, name, code, params):
+def _model_vs_builtin(tmp_path, name, code, params, more=False):
     """Compiles a generated contact model for the host next to dem_math.h; returns run(n, seed) -> number of random pairs for which
-    the model's outputs (F, T, tsd, ivm, sticking) differ in any bit from pb_dem_pair_force's, and the largest |F| seen."""
+    the model's outputs (F, T, tsd, ivm, sticking) differ in any bit from pb_dem_pair_force's, and the largest |F| seen.
+    more=True: the model of dem_script.contact_model_with_more_properties -- five further lanes cx[] (copy of the new tangential
+    displacement, an age that counts up by 1.0, an integer that counts up by 2) are handed in and checked as well."""
     import ctypes
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
@@ -522,9 +524,16 @@ extern "C" int run(int n, unsigned seed, double *fmax) {{
         static const double fs_tab[2] = {{0.0, 0.6}};
         double Fa[3], Ta[3], Fb[3], Tb[3];
         pb_dem_pair_force(P, xi, vi, wi, 1.0 / mi, xj, vj, wj, mj, nn, cp, delta, fs, fd, tsd_a, &ivm_a, &st_a, Fa, Ta);
-        const bool kept = {name}(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, nn, cp, delta, (k % 3 == 0) ? 0 : 1, tsd_b, &ivm_b, &st_b, Fb, Tb);
+        const double age0 = (double) (k % 11) - 1.0;
+        const int hits0 = 3 + 2 * (k % 5);
+        double cxv[5] = {{9.0, 9.0, 9.0, age0, (double) hits0}};
+        const bool kept = {name}(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, nn, cp, delta, (k % 3 == 0) ? 0 : 1, tsd_b, &ivm_b, &st_b,
+                                 {"cxv" if more else "nullptr"}, Fb, Tb);
         (void) fs_tab;
         bool same = kept && st_a == st_b && memcmp(&ivm_a, &ivm_b, 8) == 0;
+        if({"true" if more else "false"}) {{
+            same = same && memcmp(cxv, tsd_b, 24) == 0 && cxv[3] == age0 + 1.0 && cxv[4] == (double) (hits0 + 2);
+        }}
         for(int d = 0; d < 3; d++) {{
             same = same && Fa[d] == Fb[d] && Ta[d] == Tb[d] && memcmp(&tsd_a[d], &tsd_b[d], 8) == 0;
             if(fabs(Fa[d]) > *fmax) {{ *fmax = fabs(Fa[d]); }}
@@ -564,6 +573,32 @@ def test_generated_dem_contact_model_equals_the_hand_written_one_bit_for_bit(tmp
     assert bad == 0 and fmax > 0.1
     assert backend.jit_check_dem_model(code, name) > 10000          # prelude + dem_math.h + model + dem_force_kernel.cuh, both variants
     assert backend.jit_check_dem_model(None, None) > 10000          # the same kernel around the hand-written model (option "dem_force_maxreg")
+
+
+def test_contact_model_with_further_contact_properties(tmp_path):
+    """contact tables are not fixed to examples/dem.py's three.  The model of
+    dem_script.contact_model_with_more_properties (dem.py's body plus a second vector, a second real and a second integer contact
+    property) keeps the further properties in lanes of cx[]: its forces, torques and first three properties are still
+    pb_dem_pair_force's bits, the lanes hold what the three extra statements say, and the contact kernel compiles around it with the
+    lanes in registers (PB_DEM_NX)."""
+    import math
+    import dem_script
+    params = {"dt": 5e-5, "pi": math.pi, "kappa": 2.0 * (1.0 - 0.22) / (2.0 - 0.22), "ln": -0.1053605156578263, "ct": 4.0 * 5e-5}
+    symbols = {"dt": params["dt"], "pi": params["pi"], "kappa": params["kappa"], "lnDryResCoeff": params["ln"], "collisionTime_SI": params["ct"]}
+    tables = {"friction_static": [0.0, 0.6], "friction_dynamic": [0.5, 0.5]}
+    contact = dict(DEM_CONTACT, tsd_seen="cx:vec:0", contact_age="cx:real:3", hits="cx:int:4")
+    name, code = kernelgen.translate_dem_model(dem_script.contact_model_with_more_properties(), DEM_STORAGE, contact, tables, symbols,
+                                               extra_lanes=5)
+    assert name == "user_model_spring_dashpot_more" and code.startswith("#define PB_DEM_NX 5\n") and "cx[4] = (double) (int) (" in code
+    bad, fmax = _model_vs_builtin(tmp_path, name, code, params, more=True)(20000, 11)
+    assert bad == 0 and fmax > 0.1
+    assert backend.jit_check_dem_model(code, name) > 10000
+
+    def wrong_shape(i, j):
+        contact_age[i, j] = contact_normal(i, j)
+
+    with pytest.raises(kernelgen.KernelGenError, match="scalar contact property"):
+        kernelgen.translate_dem_model(wrong_shape, DEM_STORAGE, contact, {}, {}, extra_lanes=5)
 
 
 def test_a_different_contact_model_translates_and_compiles():
@@ -1258,7 +1293,7 @@ extern "C" void run(int np_, const double *xi, const double *vi, const double *w
                     const int *tij, double *tsd, double *ivm, int *stick, double *F, double *T, int *kept) {{
     for(int k = 0; k < np_; k++) {{
         kept[k] = {name}(xi + 3 * k, vi + 3 * k, wi + 3 * k, mi[k], ri[k], xj + 3 * k, vj + 3 * k, wj + 3 * k, mj[k], rj[k], nn + 3 * k, cp + 3 * k,
-                         delta[k], tij[k], tsd + 3 * k, ivm + k, stick + k, F + 3 * k, T + 3 * k) ? 1 : 0;
+                         delta[k], tij[k], tsd + 3 * k, ivm + k, stick + k, nullptr, F + 3 * k, T + 3 * k) ? 1 : 0;
     }}
 }}
 ''')
