@@ -188,6 +188,14 @@ typedef struct pb_md_params {
     int reneighbor_every, thermo_every;
 } pb_md_params;
 int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo);
+/* pb_upload_particles + pb_md_run in one call for state that lives in host memory (the reference keeps host and device copies of
+ * every property and moves them around each module, runtime/pairs.hpp copyArrayToDevice / copyPropertyToDevice): velocities and
+ * masses are copied while the first neighbour-list build already runs on the positions.  Same results as the two calls, bit for
+ * bit; falls back to them when the loop does not start with a reneighbouring iteration (ts_begin != 0), on several ranks, for DEM
+ * contexts and with user-defined properties.  Arrays as in pb_upload_particles (pinned host memory makes the overlap real). */
+int pb_md_run_from_host(pb_ctx *ctx, const pb_md_params *p, int n, const double *position, const double *velocity, const double *mass,
+                        const int *type, const int *flags, const int *uid, const int *shape, int ts_begin, int ts_end,
+                        double *thermo_out, int thermo_cap, int *n_thermo);
 
 /* ---- host-only self-test of the shared-memory count board that replaces communicateSizes between the ranks of a node
  *      (runtime/domain/regular_6d_stencil.cpp:113-127): `rounds` messages per dimension on a periodic ring of `world`

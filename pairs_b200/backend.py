@@ -148,6 +148,7 @@ SIGNATURES = {
     "pb_nccl_unique_id": (_I, [_P]),
     "pb_nccl_init": (_I, [_P, _P]),
     "pb_md_run": (_I, [_P, ctypes.POINTER(MdParams), _I, _I, _DP, _I, _IP]),
+    "pb_md_run_from_host": (_I, [_P, ctypes.POINTER(MdParams), _I, _DP, _DP, _DP, _IP, _IP, _IP, _IP, _I, _I, _DP, _I, _IP]),
     "pb_set_option": (_I, [_P, _S, _I]),
     "pb_board_selftest": (_I, [_S, _I, _I, _I]),
     "pb_board_unlink": (_I, [_S]),
@@ -486,6 +487,20 @@ class Context:
         out = np.zeros(cap * 3, np.float64)
         n = _I(0)
         self._ck(self.lib.pb_md_run(self.h, ctypes.byref(p), ts_begin, ts_end, _dp(out), cap, ctypes.byref(n)))
+        return out[: min(n.value, cap) * 3].reshape(-1, 3)
+
+    def md_run_from_host(self, position, velocity, mass, type_, ts_begin, ts_end, dt, cutoff_force, cutoff_lists, cell_spacing,
+                         reneighbor_every, thermo_every, flags=None, uid=None, shape=None):
+        """upload() + md_run() in one call: velocities and masses are copied while the first list build runs (pb_md_run_from_host)"""
+        pos = _f64(position)
+        vel, m = _f64(velocity), _f64(mass)
+        t, f, u, s = _i32(type_), _i32(flags), _i32(uid), _i32(shape)
+        p = MdParams(dt, cutoff_force, cutoff_lists, cell_spacing, reneighbor_every, thermo_every)
+        cap = max(8, (ts_end - ts_begin) // max(thermo_every, 1) + 4) if thermo_every > 0 else 1
+        out = np.zeros(cap * 3, np.float64)
+        n = _I(0)
+        self._ck(self.lib.pb_md_run_from_host(self.h, ctypes.byref(p), pos.size // 3, _dp(pos), _dp(vel), _dp(m), _ip(t), _ip(f), _ip(u), _ip(s),
+                                              ts_begin, ts_end, _dp(out), cap, ctypes.byref(n)))
         return out[: min(n.value, cap) * 3].reshape(-1, 3)
 
     # ---- user-defined properties (csrc/props.cu) ----

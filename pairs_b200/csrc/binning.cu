@@ -297,6 +297,8 @@ extern "C" int pb_download_cell_lists(pb_ctx *ctx, int *cell_start, int *cell_li
 }
 
 // ---- cell-order reordering of the locals ------------------------------------------------------------------
+// PART: 3 = every array; 1 = all but velocity and mass, 2 = velocity and mass (the split of an overlapped upload, see below)
+template<int PART>
 __global__ void __launch_bounds__(256) pb_k_reorder(int n, int cap, const int *__restrict__ perm,
                                                     const double4 *__restrict__ pos, double4 *__restrict__ pos_o,
                                                     const double *__restrict__ vel, double *__restrict__ vel_o,
@@ -309,16 +311,20 @@ __global__ void __launch_bounds__(256) pb_k_reorder(int n, int cap, const int *_
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= n) { return; }
     const int s = perm[k];
-    pos_o[k] = pos[s];
-    vel_o[k] = vel[s];
-    vel_o[cap + k] = vel[cap + s];
-    vel_o[2 * cap + k] = vel[2 * cap + s];
-    mass_o[k] = mass[s];
-    type_o[k] = type[s];
-    flags_o[k] = flags[s];
-    uid_o[k] = uid[s];
-    shape_o[k] = shape[s];
-    tag_o[k] = tag[s];
+    if(PART & 1) {
+        pos_o[k] = pos[s];
+        type_o[k] = type[s];
+        flags_o[k] = flags[s];
+        uid_o[k] = uid[s];
+        shape_o[k] = shape[s];
+        tag_o[k] = tag[s];
+    }
+    if(PART & 2) {
+        vel_o[k] = vel[s];
+        vel_o[cap + k] = vel[cap + s];
+        vel_o[2 * cap + k] = vel[2 * cap + s];
+        mass_o[k] = mass[s];
+    }
 }
 
 // Sort the locals into cell order (stable: ties keep ascending previous index).  Called from pb_exchange, before
@@ -328,9 +334,35 @@ int pb_sort_locals(pb_ctx *ctx) {
     const int n = ctx->nlocal;
     if(n == 0) { return 0; }
     PB_TRY(pb_bin_particles(ctx, 0, n, true));
-    PB_LAUNCH(pb_k_reorder, pb_blocks(n, 256), 256, n, ctx->pcap, ctx->cell_list, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
-              ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt,
-              ctx->shape, ctx->shape_alt, ctx->tag, ctx->tag_alt);
+    if(ctx->upload_pending) {
+        // pb_md_run_from_host: velocities and masses are still arriving on comm_stream.  Positions and the integer arrays are
+        // permuted here; velocities and masses follow on comm_stream, behind their copies, through a copy of the permutation
+        // (cell_list is rewritten by the cell-list build before they are through).
+        if((size_t) n > ctx->upload_perm_cap) {
+            if(ctx->upload_perm != nullptr) { PB_CHECK(cudaFree(ctx->upload_perm)); ctx->upload_perm = nullptr; ctx->upload_perm_cap = 0; }
+            PB_CHECK(cudaMalloc(&ctx->upload_perm, sizeof(int) * (size_t) ctx->pcap));
+            ctx->upload_perm_cap = (size_t) ctx->pcap;
+        }
+        PB_CHECK(cudaMemcpyAsync(ctx->upload_perm, ctx->cell_list, sizeof(int) * (size_t) n, cudaMemcpyDeviceToDevice, ctx->stream));
+        PB_CHECK(cudaEventRecord(ctx->ev_io[0], ctx->stream));
+        PB_LAUNCH(pb_k_reorder<1>, pb_blocks(n, 256), 256, n, ctx->pcap, ctx->cell_list, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
+                  ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt,
+                  ctx->shape, ctx->shape_alt, ctx->tag, ctx->tag_alt);
+        PB_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_io[0], 0));
+        std::swap(ctx->stream, ctx->comm_stream);
+        cudaError_t e = cudaSuccess;
+        pb_k_reorder<2><<<pb_blocks(n, 256), 256, 0, ctx->stream>>>(n, ctx->pcap, ctx->upload_perm, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
+                                                                     ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt,
+                                                                     ctx->uid, ctx->uid_alt, ctx->shape, ctx->shape_alt, ctx->tag, ctx->tag_alt);
+        e = cudaGetLastError();
+        if(e == cudaSuccess) { e = cudaEventRecord(ctx->ev_io[1], ctx->stream); }
+        std::swap(ctx->stream, ctx->comm_stream);
+        PB_CHECK(e);
+    } else {
+        PB_LAUNCH(pb_k_reorder<3>, pb_blocks(n, 256), 256, n, ctx->pcap, ctx->cell_list, ctx->pos, ctx->pos_alt, ctx->vel, ctx->vel_alt,
+                  ctx->mass, ctx->mass_alt, ctx->type, ctx->type_alt, ctx->flags, ctx->flags_alt, ctx->uid, ctx->uid_alt,
+                  ctx->shape, ctx->shape_alt, ctx->tag, ctx->tag_alt);
+    }
     std::swap(ctx->pos, ctx->pos_alt);
     std::swap(ctx->vel, ctx->vel_alt);
     std::swap(ctx->mass, ctx->mass_alt);

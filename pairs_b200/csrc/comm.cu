@@ -257,6 +257,8 @@ static PbBox pb_box(const pb_ctx *ctx) {
     return b;
 }
 
+static int pb_borders_move(pb_ctx *ctx, int step, int stride, int base_elems);
+
 extern "C" int pb_borders(pb_ctx *ctx) {
     PB_CHECK(cudaSetDevice(ctx->device));
     PbStage st(ctx, "borders");
@@ -277,36 +279,54 @@ extern "C" int pb_borders(pb_ctx *ctx) {
         ctx->nsend_all += c_lo + c_hi;
         PB_TRY(pb_transport_sizes(ctx, step));
         pb_set_offsets(ctx, step);
-        const int ns = ctx->nsend[step * 2] + ctx->nsend[step * 2 + 1];
         const int nr = ctx->nrecv[step * 2] + ctx->nrecv[step * 2 + 1];
         PB_TRY(pb_ensure_particle_capacity(ctx, ctx->nlocal + ctx->nghost + nr));
-        if(ns > 0) {
-            if(ctx->dem) {
-                PB_LAUNCH(pb_k_pack_border<true>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
-                          ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
-                          ctx->radius, ctx->angvel);
-            } else {
-                PB_LAUNCH(pb_k_pack_border<false>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
-                          ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
-                          nullptr, nullptr);
-            }
-            PB_TRY(pb_xprops_pack(ctx, ctx->send_offsets[step * 2], ns, stride, base_elems, ctx->send_map, ctx->send_buf));
-        }
-        const double *src = nullptr;
-        PB_TRY(pb_transport_data(ctx, step, step + 1, stride, &src));
-        if(nr > 0) {
-            if(ctx->dem) {
-                PB_LAUNCH(pb_k_unpack_border<true>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
-                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
-                          ctx->uid, ctx->shape, ctx->tag, ctx->radius, ctx->angvel);
-            } else {
-                PB_LAUNCH(pb_k_unpack_border<false>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
-                          ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
-                          ctx->uid, ctx->shape, ctx->tag, nullptr, nullptr);
-            }
-            PB_TRY(pb_xprops_unpack(ctx, ctx->recv_offsets[step * 2], nr, ctx->nlocal + ctx->recv_offsets[step * 2], stride, base_elems, src));
-        }
+        PB_TRY(pb_borders_move(ctx, step, stride, base_elems));
         ctx->nghost += nr;
+    }
+    return 0;
+}
+
+// pb_md_run_from_host: the ghosts of the first list build were created while velocities and masses were still on their way, so
+// their records carried whatever the arrays held.  Once the arrays are complete the three phases move the records again -- same
+// send lists, same order (a forwarded ghost takes its values from the ghost of the earlier phase) -- and every ghost holds what
+// pb_borders would have given it.
+int pb_borders_refill(pb_ctx *ctx) {
+    const int base_elems = ctx->dem ? BORDER_ELEMS_DEM : BORDER_ELEMS;
+    const int stride = base_elems + ctx->xrows_nv;
+    for(int step = 0; step < 3; step++) { PB_TRY(pb_borders_move(ctx, step, stride, base_elems)); }
+    return 0;
+}
+
+// pack -> transport -> unpack of one phase of the ghost creation, over the send lists pb_select_dim left
+static int pb_borders_move(pb_ctx *ctx, int step, int stride, int base_elems) {
+    const int ns = ctx->nsend[step * 2] + ctx->nsend[step * 2 + 1];
+    const int nr = ctx->nrecv[step * 2] + ctx->nrecv[step * 2 + 1];
+    if(ns > 0) {
+        if(ctx->dem) {
+            PB_LAUNCH(pb_k_pack_border<true>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
+                      ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
+                      ctx->radius, ctx->angvel);
+        } else {
+            PB_LAUNCH(pb_k_pack_border<false>, pb_blocks(ns, 256), 256, ctx->send_offsets[step * 2], ns, ctx->pcap, stride, pb_box(ctx),
+                      ctx->send_map, ctx->send_mult, ctx->pos, ctx->vel, ctx->mass, ctx->uid, ctx->shape, ctx->tag, ctx->send_buf,
+                      nullptr, nullptr);
+        }
+        PB_TRY(pb_xprops_pack(ctx, ctx->send_offsets[step * 2], ns, stride, base_elems, ctx->send_map, ctx->send_buf));
+    }
+    const double *src = nullptr;
+    PB_TRY(pb_transport_data(ctx, step, step + 1, stride, &src));
+    if(nr > 0) {
+        if(ctx->dem) {
+            PB_LAUNCH(pb_k_unpack_border<true>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
+                      ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                      ctx->uid, ctx->shape, ctx->tag, ctx->radius, ctx->angvel);
+        } else {
+            PB_LAUNCH(pb_k_unpack_border<false>, pb_blocks(nr, 256), 256, ctx->recv_offsets[step * 2], nr,
+                      ctx->nlocal + ctx->recv_offsets[step * 2], ctx->pcap, stride, src, ctx->pos, ctx->vel, ctx->mass, ctx->type, ctx->flags,
+                      ctx->uid, ctx->shape, ctx->tag, nullptr, nullptr);
+        }
+        PB_TRY(pb_xprops_unpack(ctx, ctx->recv_offsets[step * 2], nr, ctx->nlocal + ctx->recv_offsets[step * 2], stride, base_elems, src));
     }
     return 0;
 }

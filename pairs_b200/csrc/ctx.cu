@@ -56,6 +56,8 @@ extern "C" int pb_create(pb_ctx **out, int device) {
     }
     PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_prev, cudaEventDisableTiming));
     PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming));
+    PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_io[0], cudaEventDisableTiming));
+    PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_io[1], cudaEventDisableTiming));
     PB_CREATE_CHECK(cudaMalloc(&ctx->d_scalars, sizeof(int) * PB_NSCALARS));
     PB_CREATE_CHECK(cudaMemset(ctx->d_scalars, 0, sizeof(int) * PB_NSCALARS));
     PB_CREATE_CHECK(cudaMallocHost(&ctx->h_scalars, sizeof(int) * PB_NSCALARS));
@@ -89,7 +91,8 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }
     for(auto &kv : ctx->timers) { for(auto &pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); } }
     for(cudaEvent_t e : ctx->event_pool) { cudaEventDestroy(e); }
-    for(cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_prev, ctx->ev_sync}) { if(e != nullptr) { cudaEventDestroy(e); } }
+    for(cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->ev_prev, ctx->ev_sync, ctx->ev_io[0], ctx->ev_io[1]}) { if(e != nullptr) { cudaEventDestroy(e); } }
+    if(ctx->upload_perm != nullptr) { cudaFree(ctx->upload_perm); }
     if(ctx->comm_stream != nullptr) { cudaStreamDestroy(ctx->comm_stream); }
     if(ctx->stream != nullptr) { cudaStreamDestroy(ctx->stream); }
     delete ctx;
@@ -134,6 +137,9 @@ static int pb_regrow_soa3(pb_ctx *ctx, double **p, size_t old_cap, size_t new_ca
 
 int pb_ensure_particle_capacity(pb_ctx *ctx, int needed) {
     if(needed <= ctx->pcap) { return 0; }
+    if(ctx->upload_pending) {      // the arrays move: the deferred half of the upload must have landed in the old ones
+        PB_CHECK(cudaStreamSynchronize(ctx->comm_stream));
+    }
     // the reference doubles (transformations/modules.py:159-203); 1.5x keeps the 180 GB budget for 4M-atom boxes
     size_t newcap = std::max<size_t>((size_t) needed, (size_t) ctx->pcap + (size_t) ctx->pcap / 2);
     newcap = (newcap + 255) / 256 * 256;
@@ -317,8 +323,10 @@ int pb_io_stage(pb_ctx *ctx, size_t bytes, double **out) {
     return 0;
 }
 
-extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, const double *velocity, const double *mass,
-                                   const int *type, const int *flags, const int *uid, const int *shape) {
+// defer: velocities and masses travel on comm_stream behind the positions and nothing is waited for -- the caller
+// (pb_md_run_from_host) joins the streams once the first list build, which needs positions only, is under way
+static int pb_upload_impl(pb_ctx *ctx, int n, const double *position, const double *velocity, const double *mass,
+                          const int *type, const int *flags, const int *uid, const int *shape, bool defer) {
     PB_CHECK(cudaSetDevice(ctx->device));
     if(position == nullptr && n > 0) { ctx->set_error("pb_upload_particles: position is required"); return -1; }
     PB_TRY(pb_ensure_particle_capacity(ctx, std::max(n + n / 4 + 1024, 1024)));
@@ -350,6 +358,11 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     PB_LAUNCH(pb_k_iota, B, T, n, ctx->tag, ctx->tag_base);
     PB_CHECK(cudaMemcpyAsync(stage, position, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
     PB_LAUNCH(pb_k_pack_pos, B, T, n, stage, ctx->type, ctx->pos);
+    if(defer) {
+        PB_CHECK(cudaEventRecord(ctx->ev_io[0], ctx->stream));
+        PB_CHECK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_io[0], 0));      // the link carries the positions first
+        std::swap(ctx->stream, ctx->comm_stream);
+    }
     if(velocity != nullptr) {
         PB_CHECK(cudaMemcpyAsync(stage_v, velocity, sizeof(double) * 3 * (size_t) n, cudaMemcpyHostToDevice, ctx->stream));
         PB_LAUNCH(pb_k_aos_to_soa3, B, T, n, ctx->pcap, stage_v, ctx->vel);
@@ -361,6 +374,12 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     } else {
         PB_LAUNCH(pb_k_fill_real, B, T, n, ctx->mass, 1.0);
     }
+    if(defer) {
+        const cudaError_t e = cudaEventRecord(ctx->ev_io[1], ctx->stream);
+        std::swap(ctx->stream, ctx->comm_stream);
+        PB_CHECK(e);
+        ctx->upload_pending = true;
+    }
     PB_CHECK(cudaMemsetAsync(ctx->force, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
     if(ctx->dem) {   // DEM extras start zeroed (defaults of add_property); contact tables are emptied
         PB_CHECK(cudaMemsetAsync(ctx->torque, 0, sizeof(double) * 3 * (size_t) ctx->pcap, ctx->stream));
@@ -370,8 +389,41 @@ extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, c
     }
     PB_TRY(pb_xprops_defaults(ctx));     // user-defined properties of the new particles: their declared defaults
     ctx->force_is_zero = false;
-    PB_CHECK(cudaStreamSynchronize(ctx->stream));
+    if(!defer) { PB_CHECK(cudaStreamSynchronize(ctx->stream)); }
     return 0;
+}
+
+extern "C" int pb_upload_particles(pb_ctx *ctx, int n, const double *position, const double *velocity, const double *mass,
+                                   const int *type, const int *flags, const int *uid, const int *shape) {
+    return pb_upload_impl(ctx, n, position, velocity, mass, type, flags, uid, shape, false);
+}
+
+// main stream waits for the deferred half of an upload (no-op otherwise)
+int pb_upload_join(pb_ctx *ctx) {
+    if(ctx->upload_pending) {
+        ctx->upload_pending = false;
+        PB_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_io[1], 0));
+    }
+    return 0;
+}
+
+// pb_upload_particles + pb_md_run in one call, for callers whose state lives in HOST memory: the copies of velocities and masses
+// (more than half of the bytes) overlap the first neighbour-list build, which works on positions alone.  The loop must start with
+// a reneighbouring iteration (ts_begin == 0) on a single-rank, non-DEM context without user-defined properties; otherwise the two
+// calls simply run one after the other.  Results are those of the two separate calls, bit for bit.  Returns with both streams idle:
+// the host arrays are free again.
+extern "C" int pb_md_run_from_host(pb_ctx *ctx, const pb_md_params *p, int n, const double *position, const double *velocity, const double *mass,
+                                   const int *type, const int *flags, const int *uid, const int *shape, int ts_begin, int ts_end,
+                                   double *thermo_out, int thermo_cap, int *n_thermo) {
+    const bool defer = ctx->world == 1 && !ctx->dem && ctx->xprops.empty() && velocity != nullptr && n > 0 && ts_begin == 0 && ts_end > 0;
+    PB_TRY(pb_upload_impl(ctx, n, position, velocity, mass, type, flags, uid, shape, defer));
+    const int rc = pb_md_run(ctx, p, ts_begin, ts_end, thermo_out, thermo_cap, n_thermo);
+    if(defer) {
+        ctx->upload_pending = false;
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->comm_stream), e2 = cudaStreamSynchronize(ctx->stream);
+        if(rc >= 0) { PB_CHECK(e1); PB_CHECK(e2); }
+    }
+    return rc;
 }
 
 extern "C" int pb_counts(const pb_ctx *ctx, int *nlocal, int *nghost) {

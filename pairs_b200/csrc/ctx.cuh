@@ -114,6 +114,12 @@ struct pb_ctx {
     bool overlap_comm = true;     // multi-rank: refresh ghosts on comm_stream while the interior groups compute
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_prev = nullptr, ev_sync = nullptr;
+    // pb_md_run_from_host: velocities and masses are still on their way (comm_stream) while the first list build runs on the
+    // positions; ev_io[0] main -> comm_stream (positions copied / permutation ready), ev_io[1] comm_stream -> main (arrays complete)
+    bool upload_pending = false;
+    cudaEvent_t ev_io[2] = {nullptr, nullptr};
+    int *upload_perm = nullptr;
+    size_t upload_perm_cap = 0;
 
     // persistent staging area of the bulk transfers (pb_upload_particles, pb_download_real): no allocation, no free and hence no
     // device-wide synchronisation inside a transfer

@@ -10,6 +10,8 @@
 
 int pb_lennard_jones_fused(pb_ctx *ctx, double cutoff, double dt, int fuse, int part);
 int pb_lj_finish_split(pb_ctx *ctx, int fuse);
+int pb_upload_join(pb_ctx *ctx);      // ctx.cu: the deferred half of pb_md_run_from_host's upload
+int pb_borders_refill(pb_ctx *ctx);   // comm.cu: ... and the ghosts' copies of those arrays
 
 extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int ts_end, double *thermo_out, int thermo_cap, int *n_thermo) {
     PB_CHECK(cudaSetDevice(ctx->device));
@@ -25,6 +27,7 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
     } mirror_scope(ctx);
     for(int ts = ts_begin; ts < ts_end; ts++) {
         const bool reneigh = (((ts + 1) % p->reneighbor_every) == 0) || (ts == 0);
+        if(!reneigh || ts > 0) { PB_TRY(pb_upload_join(ctx)); }      // (only the list build of iteration 0 runs without velocities)
         if(ts > 0 && !initial_done) {
             PB_TRY(pb_initial_integrate(ctx, p->dt));
             ctx->mirror_fresh = false;
@@ -36,6 +39,10 @@ extern "C" int pb_md_run(pb_ctx *ctx, const pb_md_params *p, int ts_begin, int t
             PB_TRY(pb_borders(ctx));
             PB_TRY(pb_build_cell_lists(ctx));
             PB_TRY(pb_build_neighbor_lists(ctx, p->cutoff_lists));
+            if(ctx->upload_pending) {          // pb_md_run_from_host: velocities and masses have arrived meanwhile
+                PB_TRY(pb_upload_join(ctx));
+                PB_TRY(pb_borders_refill(ctx));
+            }
         }
         // Multi-rank steps without reneighbouring: the ghost refresh (pack -> NCCL -> unpack) runs on comm_stream while the
         // interior warp groups -- no ghost neighbour, no halo source -- already compute on the main stream; the boundary

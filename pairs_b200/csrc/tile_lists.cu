@@ -343,12 +343,27 @@ struct PbTileBuildArgs {
 // lanes of a half-warp ask for 16 different residues in every iteration.  Entries whose class has more members than there are
 // positions of its residue fill the holes that smaller classes leave, in ascending order.  Measured (tools/micro/tile_force.cu,
 // 4 M atoms): shared-memory wavefronts per launch -38 %, force kernel 0.66 -> 0.58 ms.
-//   row: the thread's T4 * 4 entries in shared memory; hist: entries per residue class, 16 x 4 bits, counted while the row was
-//   built (a class of 16 or more members -- not seen at liquid density -- leaves the row in builder order).  The HOLES -- position
+//   row: the thread's T4 * 4 entries in shared memory; hist: entries per residue class, 16 x 4 bits, counted in a first pass over
+//   the finished row (counting them while the row was built cost a dozen instructions in the accept path, which runs with 5 of 32
+//   lanes; here 27 are busy: build 3.4 -> see DESIGN.md section 6).  A class of 16 or more members -- not seen at liquid density --
+//   leaves the row in builder order (-> false).  The HOLES -- position
 //   16 n + offset of a class with fewer than n + 1 members -- are chained into a list through the row itself; then one pass over
 //   the row's words (its own, just written: L2 hits) places every entry; one whose class has run out of positions takes the next hole.
-__device__ __forceinline__ void pb_tile_reorder_row(const unsigned long long *__restrict__ in_words, int nn, int rot, unsigned long long hist,
-                                                    unsigned short *row) {
+__device__ __forceinline__ bool pb_tile_reorder_row(const unsigned long long *__restrict__ in_words, int nn, int rot, unsigned short *row) {
+    unsigned long long hist = 0ull;
+    unsigned full = 0u;                  // set once a class with 15 members gets another one
+    for(int q = 0; q * 4 < nn; q++) {
+        const unsigned long long w = __ldcg(in_words + (size_t) q * 32);
+#pragma unroll
+        for(int u = 0; u < 4; u++) {
+            if(q * 4 + u < nn) {
+                const int sh = (int) ((unsigned) (w >> (16 * u)) & 15u) * 4;
+                full |= (((unsigned) (hist >> sh) & 15u) == 15u) ? 1u : 0u;
+                hist += 1ull << sh;
+            }
+        }
+    }
+    if(full != 0u) { return false; }
     int head = 0;
 #pragma unroll
     for(int r = 0; r < 16; r++) {
@@ -372,6 +387,7 @@ __device__ __forceinline__ void pb_tile_reorder_row(const unsigned long long *__
         }
     }
     for(int k = nn; (k & 3) != 0; k++) { row[k] = (unsigned short) PB_TILE_DUMMY; }
+    return true;
 }
 
 __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) {
@@ -405,10 +421,9 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
     pb_mbar_wait(bar, 0);
     __syncthreads();                                               // (the meta bytes)
     int count = 0, boundary = 0;
-    unsigned long long hist = 0ull;      // entries per residue class of the slot (16 x 4 bits), for the reorder pass
-    unsigned hist_full = 0u;             // set once a class with 15 members gets another one
     const int row = tl.row_base + threadIdx.x;
     unsigned long long *const out = a.words + pb_tile_word(row, T4, 0);
+    unsigned long long *outp = out;
     if(active) {
         boundary = (pi.x < a.faces.lo[0]) | (pi.x > a.faces.hi[0]) | (pi.y < a.faces.lo[1]) | (pi.y > a.faces.hi[1]) | (pi.z < a.faces.lo[2]) |
                    (pi.z > a.faces.hi[2]);
@@ -444,9 +459,7 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
                     const unsigned meta = smeta[s];
                     w = (w >> 16) | ((unsigned long long) ((unsigned) s | ((meta & 7u) << 12)) << 48);
                     count++;
-                    hist_full |= (((unsigned) (hist >> ((s & 15) * 4)) & 15u) == 15u) ? 1u : 0u;      // the nibble is about to overflow
-                    hist += 1ull << ((s & 15) * 4);
-                    if((count & 3) == 0 && count <= ncap) { out[(size_t) ((count >> 2) - 1) * 32] = w; }
+                    if((count & 3) == 0 && count <= ncap) { *outp = w; outp += 32; }
                     meta_or |= meta;
                 }
             }
@@ -465,12 +478,13 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
     if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(a.max_count, m); }
-    if(a.reorder && active && count > 0 && count <= ncap && hist_full == 0u) {
+    if(a.reorder && active && count > 0 && count <= ncap) {
         // the staging area is idle now: thread t assembles its row in its T4 * 8 bytes of it (host: PB_TILE_M * T4 * 8 <= staging bytes)
         unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(sxy) + (size_t) threadIdx.x * (size_t) (T4 * 4);
-        pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), hist, rowbuf);
-        const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
-        for(int q = 0; q * 4 < count; q++) { out[(size_t) q * 32] = rw[q]; }
+        if(pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf)) {
+            const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
+            for(int q = 0; q * 4 < count; q++) { out[(size_t) q * 32] = rw[q]; }
+        }
     }
 }
 

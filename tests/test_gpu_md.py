@@ -317,6 +317,49 @@ def test_fused_loop_is_bit_identical():
     assert np.array_equal(by_id(tag, ctx.real("linear_velocity")), res[0][2])
 
 
+@pytest.mark.parametrize("nx", [8, 24])
+def test_md_run_from_host_equals_upload_then_run(nx):
+    """pb_md_run_from_host copies velocities and masses while the first list build already runs on the positions (permutation of
+    the cell-order sort applied to them afterwards, ghosts' copies refilled): everything -- thermo, locals, GHOSTS (their velocity
+    and mass come from the refill), tags -- must equal pb_upload_particles + pb_md_run bit for bit.  Pinned (registered) and
+    pageable host arrays, a second call on the same context (buffers in place), and the fall-back (ts_begin != 0)."""
+    ctx0, n = make_gpu(nx)
+    ctx0.md_run(0, 7, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)           # some state that is not the lattice
+    state = [np.ascontiguousarray(a) for a in (ctx0.real("position"), ctx0.real("linear_velocity"), ctx0.real("mass"), ctx0.ints("type"))]
+    args = (DT, CUT, CUT + SKIN, CUT + SKIN, 20, 10)
+
+    def snapshot(ctx, th):
+        return [th, ctx.counts(), ctx.ints("tag", True), ctx.real("position", True), ctx.real("linear_velocity", True), ctx.real("mass", True),
+                ctx.ints("type", True), ctx.real("force")]
+
+    ref, _ = make_gpu(nx)
+    ref.upload(*state)
+    want = snapshot(ref, ref.md_run(0, 45, *args))
+    assert want[1][1] > 0                                               # there are ghosts to get wrong
+    got, _ = make_gpu(nx)
+    for rep, pinned in enumerate((False, True, True)):
+        if pinned and rep == 1:
+            for a in state:
+                got.host_register(a)
+        have = snapshot(got, got.md_run_from_host(*state, 0, 45, *args))
+        for k, (a, b) in enumerate(zip(have, want)):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), (rep, k)
+    # one iteration only: the call ends right behind the overlapped list build
+    one, _ = make_gpu(nx)
+    one.upload(*state)
+    w1 = snapshot(one, one.md_run(0, 1, *args))
+    h1 = snapshot(got, got.md_run_from_host(*state, 0, 1, *args))
+    for k, (a, b) in enumerate(zip(h1, w1)):
+        assert np.array_equal(np.asarray(a), np.asarray(b)), ("one", k)
+    # a loop that starts with an integration (ts_begin > 0): nothing is deferred, same calls on both sides
+    a = got.md_run_from_host(*state, 19, 45, *args)
+    ref.upload(*state)
+    b = ref.md_run(19, 45, *args)
+    assert np.array_equal(a, b) and np.array_equal(got.real("position", True), ref.real("position", True))
+    for x in state:
+        got.host_unregister(x)
+
+
 @pytest.mark.parametrize("lanes", [2, 4, 8])
 def test_lanes_per_particle_layouts_agree(lanes):
     """The interleaved sliced-ELLPACK layouts (G lanes per particle) hold the same lists and give forces within 1e-12."""
