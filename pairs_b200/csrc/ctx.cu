@@ -82,7 +82,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->send_buf, ctx->recv_buf, ctx->sel_blocks, ctx->sel_flag, ctx->sel_scan, ctx->d_partial, ctx->d_scalars,
                     ctx->group_flag, ctx->group_scan, ctx->groups_interior, ctx->groups_boundary,
                     ctx->radius, ctx->angvel, ctx->torque, ctx->normal, ctx->inv_inertia, ctx->rotmat, ctx->quat, ctx->num_contacts,
-                    ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->contact_x, ctx->d_fric_static,
+                    ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->contact_x, ctx->m32, ctx->d_fric_static,
                     ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt,
                     ctx->tiles, ctx->tile_lvl, ctx->tile_cnt, ctx->tile_off, ctx->tile_pad, ctx->tile_row, ctx->twords, ctx->tile_flag,
                     ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary, ctx->tile_hdrs, ctx->mxy[0], ctx->mxy[1], ctx->mz[0], ctx->mz[1],

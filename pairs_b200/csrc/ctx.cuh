@@ -131,6 +131,8 @@ struct pb_ctx {
     //      tile-relative neighbour lists (4 entries per 64-bit word, sliced ELLPACK over list ROWS = tile-major particle order).
     //      The 32-bit per-particle lists above are then built only on demand (pb_require_neigh32). ----
     bool tile_lists = true;       // option "tile_lists"
+    bool tile_prefilter = true;   // option "tile_prefilter": the tile build tests candidates in fp32 first, exact fp64 only near the cutoff (same lists)
+    float4 *m32 = nullptr;        // fp32 copy of the mirror + meta byte, valid during a list build only
     bool tile_reorder = true;     // option "tile_reorder": list rows in the conflict-aware order (tile_lists.cu pb_tile_reorder_row)
     struct PbTileHdr *tile_hdrs = nullptr;   // [ntiles] run tables (tile_lists.cu)
     int tile_hdrs_cap = 0;
@@ -243,7 +245,7 @@ int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int pa
 int pb_tile_finish_split(pb_ctx *ctx);
 int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity);
 int pb_io_stage(pb_ctx *ctx, size_t bytes, double **out);
-int pb_tile_mirror_all(pb_ctx *ctx);
+int pb_tile_mirror_all(pb_ctx *ctx, bool with_f32 = false);
 int pb_tile_mirror_ghosts(pb_ctx *ctx);
 int pb_require_neigh32(pb_ctx *ctx);                        // per-particle 32-bit lists for the kernels that walk them (built lazily)
 static inline bool pb_lists_valid(const pb_ctx *ctx) { return ctx->tiles_n == ctx->nlocal || ctx->neigh_n == ctx->nlocal; }

@@ -420,6 +420,7 @@ extern "C" int pb_set_option(pb_ctx *ctx, const char *name, int value) {
     if(nm == "stage_lists") { ctx->stage_lists = value != 0; return 0; }
     if(nm == "tile_lists") { ctx->tile_lists = value != 0; ctx->tiles_n = -1; ctx->neigh_n = -1; return 0; }      // lists must be rebuilt
     if(nm == "lj_fma") { ctx->lj_fma = value != 0; return 0; }
+    if(nm == "tile_prefilter") { ctx->tile_prefilter = value != 0; return 0; }      // (the lists are the same either way)
     if(nm == "tile_reorder") { ctx->tile_reorder = value != 0; ctx->tiles_n = -1; ctx->neigh_n = -1; return 0; }     // lists must be rebuilt
     if(nm == "profiler") { ctx->nvtx = value != 0; return 0; }
     if(nm == "dem_force_maxreg") {       // occupancy experiments: NVRTC re-build of the contact kernel (built-in model) with a register cap

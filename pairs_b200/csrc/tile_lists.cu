@@ -54,7 +54,8 @@ struct PbTileHdr {
     int total_bytes, ncore, any_local, nslots;
     int run_begin[PB_TILE_NRUN], run_len[PB_TILE_NRUN], run_slot0[PB_TILE_NRUN];
     int core_begin[4], core_off[5];
-    int pad[3];
+    int bytes32;      // sum of run_len * 16: the float4 staging of the list build's pre-filter
+    int pad[2];
 };
 static_assert(sizeof(PbTileHdr) == 256, "one tile header = 64 ints");
 
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(128) pb_k_tile_headers(int ntiles, int nlocal,
     }
     // staging slots and copy sizes: a sequential walk over the 16 runs (lane 0), core offsets (lane 16)
     PbTileHdr *h = hdrs + t;
-    int slot0 = 0, acc = 0, bytes = 0;
+    int slot0 = 0, acc = 0, bytes = 0, bytes32 = 0;
     for(int r = 0; r < PB_TILE_NRUN; r++) {
         const int rb = __shfl_sync(0xffffffffu, begin, r), rl = __shfl_sync(0xffffffffu, len, r);
         const int s0 = acc + (rb & 1);
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(128) pb_k_tile_headers(int ntiles, int nlocal,
         if(rl > 0) {
             acc = (s0 + rl + 1) & ~1;
             bytes += rl * 16 + (((rb + rl + 1) & ~1) - (rb & ~1)) * 8;
+            bytes32 += rl * 16;
         }
     }
     int off = 0, core_total = 0;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(128) pb_k_tile_headers(int ntiles, int nlocal,
     found = __any_sync(0xffffffffu, found);
     if(lane < PB_TILE_NRUN) { h->run_begin[lane] = begin; h->run_len[lane] = len; h->run_slot0[lane] = slot0; }
     else if(lane < PB_TILE_NRUN + 4) { h->core_begin[lane - PB_TILE_NRUN] = begin; h->core_off[lane - PB_TILE_NRUN] = off; }
-    if(lane == 0) { h->total_bytes = bytes; h->ncore = core_total; h->any_local = found; h->nslots = acc; h->core_off[4] = core_total; }
+    if(lane == 0) { h->bytes32 = bytes32; h->total_bytes = bytes; h->ncore = core_total; h->any_local = found; h->nslots = acc; h->core_off[4] = core_total; }
 }
 
 // The mirror: positions a second time in CSR order (locals and ghosts alike), split into xy (16 bytes) and z (8 bytes), so that
@@ -194,14 +196,20 @@ __global__ void __launch_bounds__(128) pb_k_tile_headers(int ntiles, int nlocal,
 // mirror is not known to be current), kept current inside pb_md_run by the fused force kernel (locals) and pb_tile_mirror_ghosts.
 __global__ void __launch_bounds__(256) pb_k_tile_mirror(int nall, int nlocal, const int *__restrict__ cell_list, const double4 *__restrict__ pos,
                                                         double2 *__restrict__ mxy, double *__restrict__ mz, unsigned char *__restrict__ mmeta,
-                                                        int *__restrict__ ghost_csr) {
+                                                        int *__restrict__ ghost_csr, float4 *__restrict__ m32) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if(k >= nall) { return; }
     const int i = __ldg(cell_list + k);
     const double4 p = pb_ld_pos(pos + i);
     mxy[k] = make_double2(p.x, p.y);
     mz[k] = p.z;
-    mmeta[k] = (unsigned char) ((pb_w_type(p.w) & 7) | ((i >= nlocal) ? 8 : 0));
+    const int meta = (pb_w_type(p.w) & 7) | ((i >= nlocal) ? 8 : 0);
+    mmeta[k] = (unsigned char) meta;
+    // the list build's pre-filter: the position rounded to fp32, the meta byte in the fourth lane (valid at build time only)
+    // (fourth lane: the type where a list entry carries it, bits 12..14, and the ghost flag in bit 15)
+    if(m32 != nullptr) {
+        m32[k] = make_float4(__double2float_rn(p.x), __double2float_rn(p.y), __double2float_rn(p.z), __int_as_float(((meta & 7) << 12) | ((meta & 8) << 12)));
+    }
     if(i >= nlocal) { ghost_csr[i - nlocal] = k; }
 }
 
@@ -329,6 +337,7 @@ struct PbTileBuildArgs {
     const double2 *mxy;
     const double *mz;
     const unsigned char *mmeta;
+    const float4 *m32;
     const double4 *pos;
     const int *flags, *particle_cell, *sub_start, *cell_list;
     unsigned long long *words;
@@ -365,7 +374,7 @@ __device__ __forceinline__ bool pb_tile_reorder_row(const unsigned long long *__
     }
     if(full != 0u) { return false; }
     int head = 0;
-#pragma unroll
+#pragma unroll 1
     for(int r = 0; r < 16; r++) {
         const int c = (int) (hist >> (r * 4)) & 15;
         for(int k = 16 * c + ((r - rot) & 15); k < nn; k += 16) { row[k] = (unsigned short) head; head = k; }
@@ -484,6 +493,139 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
         if(pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf)) {
             const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
             for(int q = 0; q * 4 < count; q++) { out[(size_t) q * 32] = rw[q]; }
+        }
+    }
+}
+
+// The same build with an fp32 PRE-FILTER (option "tile_prefilter", the default).  The staged tile holds float4 (x, y, z rounded to
+// fp32, meta byte) -- one 128-bit shared-memory load and seven fp32 instructions per candidate instead of two loads and nine fp64
+// instructions.  The filter only ever decides candidates it cannot get wrong: with coordinates |x| <= A the rounded difference is
+// off by at most 2 * 2^-24 * A + 2^-24 * |d|, so the fp32 squared distance of a pair closer than the cutoff is within
+//     err = 2 sqrt(3) rc (2^-23 A + 2^-24 rc) + 8 * 2^-24 rc^2 + 3 (2^-23 A)^2
+// of the exact one.  Candidates below cutsq - 2 err are in, candidates above cutsq + 2 err are out (a pair that is truly inside
+// cannot land there), and the few in between -- about one per hundred particles -- are decided by the fp64 expression of the
+// reference on the exact positions of the mirror.  A is taken per particle (its own largest coordinate plus the cutoff), so no
+// assumption on the box enters.  The lists are the fp64 kernel's, entry for entry.
+__global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build32(PbTileBuildArgs a) {
+    extern __shared__ __align__(16) unsigned char pb_tile_shared[];
+    PbTileHdr *h; unsigned long long *bar; double2 *sxy; double *sz; unsigned char *smeta;
+    pb_tile_smem(pb_tile_shared, h, bar, sxy, sz, smeta);
+    float4 *const s32 = reinterpret_cast<float4 *>(sxy);
+    const PbTileGeom &g = a.g;
+    const int nlocal = a.nlocal, ncap = a.ncap, T4 = a.T4;
+    const double cutsq = a.cutsq;
+    const PbTile tl = a.tiles[blockIdx.x];
+    {
+        const int t = threadIdx.x;
+        if(t < 64) { reinterpret_cast<int *>(h)[t] = __ldg(reinterpret_cast<const int *>(a.hdrs + blockIdx.x) + t); }
+        if(t == 0) {
+            pb_mbar_init(bar, 1);
+            s32[PB_TILE_DUMMY] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+        }
+        __syncthreads();
+        if(!h->any_local) {                                            // a tile of ghosts only: nothing to build
+            if(t == 0) { a.tile_flag[blockIdx.x] = 0; }
+            return;
+        }
+        if(t < PB_TILE_NRUN) {
+            const int len = h->run_len[t];
+            if(len > 0) { pb_bulk_g2s(s32 + h->run_slot0[t], a.m32 + h->run_begin[t], len * 16, bar); }
+        }
+        if(t == 0) { pb_mbar_expect_tx(bar, h->bytes32); }
+    }
+    const int q = pb_tile_core_q(h, threadIdx.x);
+    const int cs = (q >= 0) ? pb_tile_core_csr(h, threadIdx.x, q) : -1;
+    const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : nlocal;
+    const bool live = i < nlocal;
+    const bool active = live && (a.flags[i] & PB_FLAG_FIXED) == 0;
+    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
+    int flat = 0;
+    if(active) { pi = pb_ld_pos(a.pos + i); flat = a.particle_cell[i] - 1; }
+    pb_mbar_wait(bar, 0);
+    int count = 0, boundary = 0;
+    const int row = tl.row_base + threadIdx.x;
+    unsigned long long *const out = a.words + pb_tile_word(row, T4, 0);
+    int widx = 0;                             // index of the next word of the row (32 apart: sliced layout)
+    if(active) {
+        boundary = (pi.x < a.faces.lo[0]) | (pi.x > a.faces.hi[0]) | (pi.y < a.faces.lo[1]) | (pi.y > a.faces.hi[1]) | (pi.z < a.faces.lo[2]) |
+                   (pi.z > a.faces.hi[2]);
+        const int c2 = flat % g.dim2, col = flat / g.dim2, c1 = col % g.dim1, c0 = col / g.dim1;
+        const double fx = pi.x - (g.lo[0] + c0 * g.spacing), fy = pi.y - (g.lo[1] + c1 * g.spacing), zrel = pi.z - g.lo[2];
+        const int tr0 = (c0 - (tl.X0 - 1)) * 4 + (c1 - (tl.Y0 - 1));
+        const int s_self = pb_tile_self_slot(h, q, cs);
+        // the nine z windows go to shared memory (begin | end << 16; the float4 staging leaves the upper third of the staging area
+        // free until the reorder pass), so that the loop over the stencil rows stays ROLLED: the kernel with nine unrolled copies of
+        // the test loop stalled on instruction fetch (ncu: no_instruction 1.5 warps per issue cycle)
+        unsigned *const swin = reinterpret_cast<unsigned *>(s32 + PB_TILE_CAP) + threadIdx.x;
+#pragma unroll 1
+        for(int r = 0; r < 9; r++) {
+            int b, e;
+            unsigned packed = 0u;
+            if(pb_tile_window(g, c0, c1, c2, fx, fy, zrel, cutsq, r, a.sub_start, b, e)) {
+                const int tr = tr0 + (r / 3 - 1) * 4 + (r % 3 - 1);
+                const int shift = h->run_slot0[tr] - h->run_begin[tr];
+                packed = (unsigned) (b + shift) | ((unsigned) (e + shift) << 16);
+            }
+            swin[r * PB_TILE_M] = packed;
+        }
+        // the band of the pre-filter for this particle (see above), bounds rounded outwards
+        const double rc = sqrt(cutsq), A = fmax(fmax(fabs(pi.x), fabs(pi.y)), fabs(pi.z)) + rc;
+        const double u = 5.9604644775390625e-08;                                      // 2^-24
+        const double err = 2.0 * 1.7320508075688774 * rc * (2.0 * u * A + u * rc) + 8.0 * u * cutsq + 3.0 * (2.0 * u * A) * (2.0 * u * A);
+        const float cut_lo = __double2float_rd(cutsq - 2.0 * err), cut_hi = __double2float_ru(cutsq + 2.0 * err);
+        const float xf = __double2float_rn(pi.x), yf = __double2float_rn(pi.y), zf = __double2float_rn(pi.z);
+        unsigned long long w = 0ull;
+        unsigned meta_or = 0u;
+#pragma unroll 1
+        for(int r = 0; r < 9; r++) {
+            const unsigned packed = swin[r * PB_TILE_M];
+            const int s_end = (int) (packed >> 16);
+            // (four candidates per trip with their loads and fp32 chains issued together, decisions afterwards, was measured SLOWER:
+            // 3.73 vs 3.26 ms per build -- the window tails and the second range check cost more than the chains' latency)
+#pragma unroll 4
+            for(int s = (int) (packed & 0xffffu); s < s_end; s++) {
+                const float4 c = s32[s];
+                const float dx = xf - c.x, dy = yf - c.y, dz = zf - c.z;
+                const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if(rsq < cut_hi) {
+                    bool in = s != s_self;                             // (a slot belongs to one run: no need to ask for the row)
+                    if(rsq > cut_lo) {                                 // too close to call in fp32: the reference's fp64 expression
+                        const int tr = tr0 + (r / 3 - 1) * 4 + (r % 3 - 1);
+                        const int kk = s - (h->run_slot0[tr] - h->run_begin[tr]);
+                        const double2 xy = __ldg(a.mxy + kk);
+                        const double z = __ldg(a.mz + kk);
+                        const double ex = __dsub_rn(pi.x, xy.x), ey = __dsub_rn(pi.y, xy.y), ez = __dsub_rn(pi.z, z);
+                        in = in && __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez)) < cutsq;
+                    }
+                    if(in) {
+                        const unsigned meta = (unsigned) __float_as_int(c.w);
+                        w = (w >> 16) | ((unsigned long long) ((unsigned) s | (meta & 0x7000u)) << 48);
+                        count++;
+                        if((count & 3) == 0 && count <= ncap) { out[widx] = w; widx += 32; }
+                        meta_or |= meta;
+                    }
+                }
+            }
+        }
+        if((count & 3) != 0 && (count >> 2) < T4) {
+            w >>= 16 * (4 - (count & 3));
+            w |= 0x0001000100010001ull * (unsigned long long) PB_TILE_DUMMY << (16 * (count & 3));
+            out[(size_t) (count >> 2) * 32] = w;
+        }
+        boundary |= (int) (meta_or >> 15);
+    }
+    if(live) { a.numneigh[i] = count; }
+    const int any_b = __syncthreads_or(boundary);                  // (also: every thread is through with the staged positions)
+    if(threadIdx.x == 0) { a.tile_flag[blockIdx.x] = any_b != 0; }
+    int m = count;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+    if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(a.max_count, m); }
+    if(a.reorder && active && count > 0 && count <= ncap) {
+        unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(sxy) + (size_t) threadIdx.x * (size_t) (T4 * 4);
+        if(pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf)) {
+            const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
+            for(int q2 = 0; q2 * 4 < count; q2++) { out[(size_t) q2 * 32] = rw[q2]; }
         }
     }
 }
@@ -750,7 +892,7 @@ static int pb_tile_plan(pb_ctx *ctx, bool *overflow) {
 
 // ---- the mirror (positions in CSR order) ---------------------------------------------------------------------------------------
 // everything: after a cell-list build, and before a force evaluation whenever the mirror is not known to be current
-int pb_tile_mirror_all(pb_ctx *ctx) {
+int pb_tile_mirror_all(pb_ctx *ctx, bool with_f32) {
     const int nall = ctx->nlocal + ctx->nghost;
     if(nall + 2 > ctx->mirror_cap) {
         for(int b = 0; b < 2; b++) {
@@ -758,6 +900,7 @@ int pb_tile_mirror_all(pb_ctx *ctx) {
             if(ctx->mz[b] != nullptr) { PB_CHECK(cudaFree(ctx->mz[b])); ctx->mz[b] = nullptr; }
         }
         if(ctx->mmeta != nullptr) { PB_CHECK(cudaFree(ctx->mmeta)); ctx->mmeta = nullptr; }
+        if(ctx->m32 != nullptr) { PB_CHECK(cudaFree(ctx->m32)); ctx->m32 = nullptr; }
         if(ctx->ghost_csr != nullptr) { PB_CHECK(cudaFree(ctx->ghost_csr)); ctx->ghost_csr = nullptr; }
         ctx->mirror_cap = 0;
         const size_t want = (size_t) nall + nall / 4 + 1024;
@@ -768,11 +911,13 @@ int pb_tile_mirror_all(pb_ctx *ctx) {
             PB_CHECK(cudaMemsetAsync(ctx->mz[b], 0, sizeof(double) * want, ctx->stream));
         }
         PB_CHECK(cudaMalloc(&ctx->mmeta, want));
+        PB_CHECK(cudaMalloc(&ctx->m32, sizeof(float4) * want));
         PB_CHECK(cudaMalloc(&ctx->ghost_csr, sizeof(int) * want));
         ctx->mirror_cap = (int) want;
     }
     if(nall > 0) {
-        PB_LAUNCH(pb_k_tile_mirror, pb_blocks(nall, 256), 256, nall, ctx->nlocal, ctx->cell_list, ctx->pos, ctx->mxy[0], ctx->mz[0], ctx->mmeta, ctx->ghost_csr);
+        PB_LAUNCH(pb_k_tile_mirror, pb_blocks(nall, 256), 256, nall, ctx->nlocal, ctx->cell_list, ctx->pos, ctx->mxy[0], ctx->mz[0], ctx->mmeta, ctx->ghost_csr,
+                  with_f32 ? ctx->m32 : nullptr);
     }
     ctx->mirror_cur = 0;
     ctx->mirror_n = nall;
@@ -828,7 +973,8 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
     }
     const size_t smem = pb_tile_smem_bytes(true);
     PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    PB_TRY(pb_tile_mirror_all(ctx));                // the tiles are staged out of the mirror
+    PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    PB_TRY(pb_tile_mirror_all(ctx, ctx->tile_prefilter));                // the tiles are staged out of the mirror
     for(int attempt = 0; attempt < 8; attempt++) {
         const int T4 = (ctx->ncap + 3) / 4;
         const size_t bytes = sizeof(unsigned long long) * (size_t) (ctx->tile_rows / 32) * (size_t) T4 * 32;
@@ -848,7 +994,12 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
         ba.words = ctx->twords; ba.numneigh = ctx->numneigh; ba.max_count = ctx->d_scalars; ba.tile_flag = ctx->tile_flag; ba.faces = faces;
         // the reorder pass assembles the rows in the staging area (positions + meta bytes): possible while a row fits its share
         ba.reorder = ctx->tile_reorder && (size_t) PB_TILE_M * (size_t) T4 * 8 <= (size_t) PB_TILE_CAP * 25;
-        pb_k_tile_build<<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(ba);
+        ba.m32 = ctx->m32;
+        if(ctx->tile_prefilter) {
+            pb_k_tile_build32<<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(ba);
+        } else {
+            pb_k_tile_build<<<ctx->ntiles, PB_TILE_M, smem, ctx->stream>>>(ba);
+        }
         ctx->launches++;
         PB_CHECK(cudaGetLastError());
         const bool split = ctx->world > 1 && ctx->overlap_comm;

@@ -168,3 +168,50 @@ def test_conflict_aware_list_order_keeps_the_sets(nx, eps, sig6):
     y = _run(nx, 1, 0, 45, eps, sig6, reorder=0)
     assert np.abs(x[1][:, 1:] - y[1][:, 1:]).max() <= 1e-9 * np.abs(y[1][:, 1:]).max()
     assert np.abs(x[2] - y[2]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("origin", [0.0, 4000.0])
+def test_fp32_prefilter_of_the_tile_build_leaves_the_lists_unchanged(origin):
+    """Option "tile_prefilter" (default on): the tile build tests candidates on fp32 copies first and decides only what fp32 cannot
+    get wrong; pairs within the error band of the cutoff go through the reference's fp64 expression.  The adversarial case: 400
+    particles moved to a distance of cutoff * (1 +- 0, 1e-15 ... 1e-5) from another one, in a box whose coordinates start at `origin`
+    (large coordinates = coarse fp32 grid = wide band).  Lists with the pre-filter, without it, and the per-particle builder's must
+    be identical, entry for entry."""
+    from pairs_b200.backend import Context
+    nx = 10
+    src, n = make_gpu(nx)
+    src.md_run(0, 30, DT, CUT, CUT + SKIN, CUT + SKIN, 20, 0)                  # a molten state
+    pos, vel, mass, typ = src.real("position"), src.real("linear_velocity"), src.real("mass"), src.ints("type")
+    L = box(nx)[1]
+    rng = np.random.default_rng(5)
+    rc = CUT + SKIN
+    inner = np.nonzero(np.all((pos > rc + 0.5) & (pos < L - rc - 0.5), axis=1))[0]
+    picks = rng.choice(inner, 800, replace=False)
+    eps = [0.0, 1e-15, -1e-15, 1e-13, -1e-13, 1e-11, -1e-11, 1e-9, -1e-9, 1e-7, -1e-7, 1e-5, -1e-5]
+    pos = pos + origin
+    for k in range(400):
+        i, j = picks[2 * k], picks[2 * k + 1]
+        u = rng.standard_normal(3)
+        u /= np.linalg.norm(u)
+        pos[j] = pos[i] + rc * (1.0 + eps[k % len(eps)]) * u
+    d = pos[picks[0::2]] - pos[picks[1::2]]
+    near = np.abs((d * d).sum(axis=1) - rc * rc) < 1e-3
+    assert near.sum() >= 390
+    res = []
+    for tiles, prefilter in ((1, 1), (1, 0), (0, 0)):
+        ctx = Context(0)
+        ctx.init_domain([origin, origin + L] * 3)
+        ctx.upload(pos, vel, mass, typ)
+        ctx.setup_cells(rc)
+        ctx.set_lj_params(4, [1.0] * 16, [1.0] * 16)
+        ctx.set_option("tile_lists", tiles)
+        ctx.set_option("tile_prefilter", prefilter)
+        ctx.set_option("tile_reorder", 0)
+        _reneighbor_gpu(ctx)
+        tag = ctx.ints("tag", True)
+        nn, rows = ctx.ints("numneighs"), ctx.neighbors()
+        order = np.argsort(tag[:len(nn)])
+        res.append((nn[order], [tuple(tag[rows[i, :nn[i]]]) for i in order]))
+    for other in res[1:]:
+        assert np.array_equal(res[0][0], other[0])
+        assert res[0][1] == other[1]
