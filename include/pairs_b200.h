@@ -217,7 +217,7 @@ int pb_jit_launch(pb_ctx *ctx, int handle, int kind, double cutoff);
 
 /* User-defined DEM contact models: the contact KERNEL (detection, contact history keyed by the partner's uid, usage marks, clean-up,
  * force / torque accumulation) stays the library's, the per-pair model of examples/dem.py:18-74 is exchanged for a device function
- * `bool <model_name>(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, n, cp, delta, tij, tsd, ivm, sticking, F, T)` printed by
+ * `bool <model_name>(xi, vi, wi, mi, ri, xj, vj, wj, mj, rj, n, cp, delta, tij, tsd, ivm, sticking, cx, F, T)` printed by
  * pairs_b200/kernelgen.py from the user's kernel body (the reference generates code for any body: mapping/funcs.py:39-334, contact
  * properties :230-263).  pb_jit_check_dem_model compiles only (cubin size or -1 + log, no GPU); pb_jit_set_dem_model installs the
  * model for pb_dem_linear_spring_dashpot / pb_dem_run (source NULL: back to the built-in). */
@@ -230,8 +230,12 @@ int pb_jit_set_dem_model(pb_ctx *ctx, const char *model_source, const char *mode
  * "overlap_comm" (0/1), "profiler" (0/1: every stage also opens an NVTX range named like the reference's timers -- Simulation.enable_profiler(),
  * sim/simulation.py:116-117, LIKWID markers there), "cell_zsub" (1..32, applies from the next pb_setup_cells), "stage_lists" (0/1), "dem_sort_every"
  * (DEM: iterations between two spatial re-sorts of the locals, 0 = never, default 200), "dem_fuse" (0/1: pb_dem_run folds the
- * per-particle modules around the contact evaluation into the contact kernel; results are identical), "pair_lists" (0/1, experimental: the fused Lennard-Jones kernel of pb_md_run walks ONE union list per pair of consecutive cell-sorted
- * particles -- fewer position gathers, the bound of the per-particle kernel; applies from the next list build), "dem_force_maxreg" (0 = off: the DEM
+ * per-particle modules around the contact evaluation into the contact kernel; results are identical), "tile_lists" (0/1, default 1: the force kernel works on cell TILES staged in shared memory by TMA with 16-bit tile-relative
+ * neighbour lists; 0 = per-particle 32-bit lists; applies from the next list build), "tile_reorder" (0/1, default 1: list rows in a
+ * shared-memory-conflict-aware order -- same sets, another summation order; 0 = the reference's list order), "tile_prefilter" (0/1,
+ * default 1: the tile build tests candidates in fp32 first and decides in fp64 only inside the rounding-error band of the cutoff;
+ * the lists are identical either way), "lj_fma" (0/1, default 1: fused-multiply-add pair arithmetic, within 1e-12 of the
+ * reference's expression tree; 0 = that expression tree operation for operation, bit-identical forces), "dem_force_maxreg" (0 = off: the DEM
  * contact kernel is re-built at run time with this register cap -- occupancy experiments; after pb_dem_enable). */
 int pb_set_option(pb_ctx *ctx, const char *name, int value);
 
