@@ -527,8 +527,15 @@ __global__ void __launch_bounds__(M) k_build_tile2(int n, int cap, Geom g, doubl
     numneigh[i] = count;
 }
 
-template<int M, int FMA, int U>
-__global__ void __launch_bounds__(M) k_force_tile_tma(int n, int cap, double cutsq, const Tile *__restrict__ tiles, const TileHdr2 *__restrict__ hdrs,
+// LD: how the list words are loaded (0 = ld.global.nc, 1 = ld.global.cs streaming / evict-first); PD: prefetch distance in iterations
+template<int LD>
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long *p) {
+    if(LD == 1) { return __ldcs(p); }
+    return __ldg(p);
+}
+
+template<int M, int FMA, int U, int LD = 0, int PD = 2, int MB = 1>
+__global__ void __launch_bounds__(M, MB) k_force_tile_tma(int n, int cap, double cutsq, const Tile *__restrict__ tiles, const TileHdr2 *__restrict__ hdrs,
                                                       const double2 *__restrict__ mxy, const double *__restrict__ mz, const int *__restrict__ cell_list,
                                                       const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
                                                       double *__restrict__ force) {
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(M) k_force_tile_tma(int n, int cap, double cut
     if(i < n) {
         nn = min(numneigh[i], NCAP);
 #pragma unroll
-        for(int q = 0; q < W; q++) { if(q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) q * 32); } }
+        for(int q = 0; q < W; q++) { if(q * 4 < nn) { wnext[q] = ld_word<LD>(wp + (size_t) q * 32); } }
     }
     mbar_wait(bar, 0);
     if(i >= n) { return; }
@@ -558,15 +565,15 @@ __global__ void __launch_bounds__(M) k_force_tile_tma(int n, int cap, double cut
     const double4 pi = make_double4(pxy.x, pxy.y, sz[s_self], 0.0);
     double fx = 0.0, fy = 0.0, fz = 0.0;
     for(int k = 0; k < nn; k += U) {
-        if(k + 2 * U < nn) {
+        if(k + PD * U < nn) {
 #pragma unroll
-            for(int q = 0; q < W; q++) { asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (size_t) (((k + 2 * U) >> 2) + q) * 32)); }
+            for(int q = 0; q < W; q++) { asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + (size_t) (((k + PD * U) >> 2) + q) * 32)); }
         }
         unsigned long long w[W];
 #pragma unroll
         for(int q = 0; q < W; q++) {
             w[q] = wnext[q];
-            if(k + U + q * 4 < nn) { wnext[q] = __ldg(wp + (size_t) (((k + U) >> 2) + q) * 32); }
+            if(k + U + q * 4 < nn) { wnext[q] = ld_word<LD>(wp + (size_t) (((k + U) >> 2) + q) * 32); }
         }
         double xj[U], yj[U], zj[U];
 #pragma unroll
@@ -762,7 +769,7 @@ int main(int argc, char **argv) {
     printf("{\"kernel\": \"force_base_fma3\", \"ms\": %.4f, \"rel_err_vs_base\": %.3e}\n", ms, err);
 
     // ---- planner (host here, a small kernel in production): per super-column a greedy walk over z, tiles of <= M particles ----
-    auto plan = [&](int M, std::vector<Tile> &tiles, int &rows) {
+    auto plan = [&](int M, std::vector<Tile> &tiles, int &rows, int staged_limit) {
         tiles.clear();
         rows = 0;
         int worst_staged = 0;
@@ -778,6 +785,11 @@ int main(int argc, char **argv) {
                 while(zb + 1 < dim) {
                     const int lvl = ccount(X0, Y0, zb + 1) + ccount(X0 + 1, Y0, zb + 1) + ccount(X0, Y0 + 1, zb + 1) + ccount(X0 + 1, Y0 + 1, zb + 1);
                     if(zb >= za && core + lvl > M) { break; }
+                    if(zb >= za) {      // the halo of the longer tile must fit the staging area as well
+                        int staged = 0;
+                        for(int X = X0 - 1; X <= X0 + 2; X++) for(int Y = Y0 - 1; Y <= Y0 + 2; Y++) for(int z = za - 1; z <= zb + 2; z++) { staged += ccount(X, Y, z); }
+                        if(staged > staged_limit) { break; }
+                    }
                     core += lvl;
                     zb++;
                 }
@@ -799,7 +811,7 @@ int main(int argc, char **argv) {
         constexpr int M = decltype(Mtag)::value;
         std::vector<Tile> tiles;
         int rows = 0;
-        const int worst = plan(M, tiles, rows);
+        const int worst = plan(M, tiles, rows, cap - 2 * NRUN - 1);
         const int ntiles = (int) tiles.size();
         Tile *d_tiles; unsigned long long *d_w;
         CK(cudaMalloc(&d_tiles, sizeof(Tile) * ntiles));
@@ -934,6 +946,28 @@ int main(int argc, char **argv) {
                     VARIANT_TMA("force_tma_fast_u8", 4, 8, d_w3, false)
                     VARIANT_TMA("force_tma_exact_reordered", 1, 4, d_w4, false)
                     VARIANT_TMA("force_tma_fast_u8_reordered", 4, 8, d_w4, false)
+#define VARIANT_TMA2(NAME, LD_, PD_)                                                                                                          \
+                    CK(cudaFuncSetAttribute(k_force_tile_tma<M, 4, 8, LD_, PD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s2));    \
+                    CK(cudaMemset(d_f1, 0, 24 * (size_t) n));                                                                                 \
+                    t = time_ms(10, [&] { k_force_tile_tma<M, 4, 8, LD_, PD_><<<ntiles, M, s2>>>(n, cap, cutsq_f, d_tiles, d_h, d_mxy, d_mz, d_cl, d_w4, d_nn2, d_f1); }); \
+                    report(NAME, t, false);
+                    // (measured, no effect beyond 0.5 %: streaming loads of the list words, prefetch distances of 3 and 4 iterations)
+#define VARIANT_TMA3(NAME, UU, MB_)                                                                                                           \
+                    {                                                                                                                         \
+                        CK(cudaFuncSetAttribute(k_force_tile_tma<M, 4, UU, 0, 2, MB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) s2)); \
+                        int occ = 0;                                                                                                          \
+                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_tile_tma<M, 4, UU, 0, 2, MB_>, M, s2));                \
+                        cudaFuncAttributes fa;                                                                                                \
+                        CK(cudaFuncGetAttributes(&fa, k_force_tile_tma<M, 4, UU, 0, 2, MB_>));                                                \
+                        CK(cudaMemset(d_f1, 0, 24 * (size_t) n));                                                                             \
+                        t = time_ms(10, [&] { k_force_tile_tma<M, 4, UU, 0, 2, MB_><<<ntiles, M, s2>>>(n, cap, cutsq_f, d_tiles, d_h, d_mxy, d_mz, d_cl, d_w4, d_nn2, d_f1); }); \
+                        printf("{\"occupancy_blocks\": %d, \"registers\": %d, \"local_bytes\": %d}\n", occ, fa.numRegs, (int) fa.localSizeBytes);  \
+                        report(NAME, t, false);                                                                                               \
+                    }
+                    VARIANT_TMA3("force_tma_fast_u8_reordered_minblocks4", 8, 4)
+                    VARIANT_TMA3("force_tma_fast_u8_reordered_minblocks5", 8, 5)
+                    VARIANT_TMA3("force_tma_fast_u4_reordered_minblocks5", 4, 5)
+                    VARIANT_TMA3("force_tma_fast_u4_reordered_minblocks6", 4, 6)
                     CK(cudaFree(d_h)); CK(cudaFree(d_mxy)); CK(cudaFree(d_mz)); CK(cudaFree(d_w3)); CK(cudaFree(d_w4));
                 } else {
                     printf("{\"kernel\": \"build_tile_tma\", \"M\": %d, \"skipped\": \"%d slots > cap %d\"}\n", M, worst_slots, cap);
@@ -953,5 +987,7 @@ int main(int argc, char **argv) {
     if(only < 0 || only == 6) { tile_variant(std::integral_constant<int, 448>(), 3584); }
     if(only < 0 || only == 7) { tile_variant(std::integral_constant<int, 512>(), 4096); }
     if(only < 0 || only == 8) { tile_variant(std::integral_constant<int, 384>(), 2816); }
+    if(only < 0 || only == 9) { tile_variant(std::integral_constant<int, 256>(), 1792); }       // 43 KB of staging: five CTAs per SM
+    if(only < 0 || only == 10) { tile_variant(std::integral_constant<int, 224>(), 1536); }     // 37 KB: six
     return 0;
 }
