@@ -85,7 +85,7 @@ extern "C" void pb_destroy(pb_ctx *ctx) {
                     ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, ctx->contact_x, ctx->m32, ctx->d_fric_static,
                     ctx->d_fric_dynamic, ctx->d_dem_flag, ctx->xdata, ctx->xdata_alt,
                     ctx->tiles, ctx->tile_lvl, ctx->tile_cnt, ctx->tile_off, ctx->tile_pad, ctx->tile_row, ctx->twords, ctx->tile_flag,
-                    ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary, ctx->tile_hdrs, ctx->mxy[0], ctx->mxy[1], ctx->mz[0], ctx->mz[1],
+                    ctx->tile_scan, ctx->tiles_interior, ctx->tiles_boundary, ctx->tile_hdrs, ctx->tile_rowsrc, ctx->mxy[0], ctx->mxy[1], ctx->mz[0], ctx->mz[1],
                     ctx->mmeta, ctx->ghost_csr, ctx->io_stage};
     for(void *b : bufs) { if(b != nullptr) { cudaFree(b); } }
     if(ctx->h_scalars != nullptr) { cudaFreeHost(ctx->h_scalars); }

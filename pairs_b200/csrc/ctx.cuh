@@ -136,6 +136,8 @@ struct pb_ctx {
     bool tile_reorder = true;     // option "tile_reorder": list rows in the conflict-aware order (tile_lists.cu pb_tile_reorder_row)
     struct PbTileHdr *tile_hdrs = nullptr;   // [ntiles] run tables (tile_lists.cu)
     int tile_hdrs_cap = 0;
+    unsigned char *tile_rowsrc = nullptr;    // [tile_rows + PB_TILE_M] list row -> the core thread (= core particle of its tile) the row belongs to
+    int tile_rowsrc_cap = 0;
     // the mirror: positions in CSR order, split xy / z, double-buffered like pos / pos_alt; meta byte (type | 8 for a ghost) and the
     // CSR position of every ghost.  `mirror_fresh` is honoured only while `mirror_scope` is set (inside pb_md_run).
     double2 *mxy[2] = {nullptr, nullptr};

@@ -341,6 +341,7 @@ struct PbTileBuildArgs {
     const double4 *pos;
     const int *flags, *particle_cell, *sub_start, *cell_list;
     unsigned long long *words;
+    unsigned char *rowsrc;
     int *numneigh, *max_count, *tile_flag;
     PbTileFaces faces;
 };
@@ -399,8 +400,65 @@ __device__ __forceinline__ bool pb_tile_reorder_row(const unsigned long long *__
     return true;
 }
 
+
+// ---- rows sorted by length ------------------------------------------------------------------------------------------------------
+// The force kernel's warp runs as long as its longest row (rows of 60 ... 92 entries, 8 per iteration: a warp of 32 arbitrary rows
+// makes 11 iterations for a mean of 9.9 useful ones).  So the build hands the rows of a tile out in ascending order of their
+// iteration count: thread t of the force kernel works on the row of core thread rowsrc[row_base + t].  Stable counting sort over
+// the tile's core threads (key = iterations, 15 = no list), deterministic: ties keep the thread order.
+// s_cnt: 128 ints of shared memory.  Returns the rank (threads outside the core: their own index).
+__device__ __forceinline__ int pb_tile_rank(int key, bool in_core, int *s_cnt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if(threadIdx.x < 128) { s_cnt[threadIdx.x] = 0; }
+    __syncthreads();
+    const unsigned peers = __match_any_sync(0xffffffffu, in_core ? key : 99);
+    const int intra = __popc(peers & ((1u << lane) - 1u));
+    if(in_core && intra == 0) { s_cnt[key * 8 + warp] = __popc(peers); }      // (key-major: all warps of key 0, then key 1, ...)
+    __syncthreads();
+    if(warp == 0) {      // exclusive prefix over the 128 counters, four per lane
+        int v[4], sum = 0;
+#pragma unroll
+        for(int k = 0; k < 4; k++) { v[k] = s_cnt[lane * 4 + k]; sum += v[k]; }
+        int incl = sum;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, o); if(lane >= o) { incl += up; } }
+        int run = incl - sum;
+#pragma unroll
+        for(int k = 0; k < 4; k++) { s_cnt[lane * 4 + k] = run; run += v[k]; }
+    }
+    __syncthreads();
+    return in_core ? s_cnt[key * 8 + warp] + intra : (int) threadIdx.x;
+}
+
+// End of a build: rows sorted by length and re-assembled in the conflict-aware order (both only with option "tile_reorder": the
+// exact mode keeps the builder's rows where the builder's order puts them).  Every thread of the CTA calls this.
+//   out: the thread's row as pass A wrote it (natural position row_base + threadIdx.x); stage: the idle staging area.
+__device__ __forceinline__ void pb_tile_finish_rows(const PbTileBuildArgs &a, const PbTile &tl, bool in_core, bool active, int count,
+                                                    const unsigned long long *out, unsigned char *stage, int *s_cnt) {
+    if(!a.reorder) {
+        if(in_core) { a.rowsrc[tl.row_base + threadIdx.x] = (unsigned char) threadIdx.x; }
+        return;
+    }
+    const int key = active ? min((count + 7) >> 3, 14) : 15;
+    const int rank = pb_tile_rank(key, in_core, s_cnt);
+    if(in_core) { a.rowsrc[tl.row_base + rank] = (unsigned char) threadIdx.x; }
+    const bool have = active && count > 0 && count <= a.ncap;
+    // thread t assembles its row in its T4 * 8 bytes of the staging area (host: PB_TILE_M * T4 * 8 <= staging bytes)
+    unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(stage) + (size_t) threadIdx.x * (size_t) (a.T4 * 4);
+    unsigned long long *const rw = reinterpret_cast<unsigned long long *>(rowbuf);
+    if(have && !pb_tile_reorder_row(out, count, rank & 15, rowbuf)) {
+        for(int q = 0; q * 4 < count; q++) { rw[q] = __ldcg(out + (size_t) q * 32); }      // (a class of 16: builder order)
+    }
+    __syncthreads();                                                // every row has been read: the rows may change places
+    if(have) {
+        unsigned long long *const dst = a.words + pb_tile_word(tl.row_base + rank, a.T4, 0);
+        for(int q = 0; q * 4 < count; q++) { dst[(size_t) q * 32] = rw[q]; }
+    }
+}
+
 __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
+    __shared__ int s_cnt[128];
     PbTileHdr *h; unsigned long long *bar; double2 *sxy; double *sz; unsigned char *smeta;
     pb_tile_smem(pb_tile_shared, h, bar, sxy, sz, smeta);
     const PbTileGeom &g = a.g;
@@ -487,14 +545,7 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
     if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(a.max_count, m); }
-    if(a.reorder && active && count > 0 && count <= ncap) {
-        // the staging area is idle now: thread t assembles its row in its T4 * 8 bytes of it (host: PB_TILE_M * T4 * 8 <= staging bytes)
-        unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(sxy) + (size_t) threadIdx.x * (size_t) (T4 * 4);
-        if(pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf)) {
-            const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
-            for(int q = 0; q * 4 < count; q++) { out[(size_t) q * 32] = rw[q]; }
-        }
-    }
+    pb_tile_finish_rows(a, tl, q >= 0, active, count, out, reinterpret_cast<unsigned char *>(sxy), s_cnt);
 }
 
 // The same build with an fp32 PRE-FILTER (option "tile_prefilter", the default).  The staged tile holds float4 (x, y, z rounded to
@@ -508,6 +559,7 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build(PbTileBuildArgs a) 
 // assumption on the box enters.  The lists are the fp64 kernel's, entry for entry.
 __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build32(PbTileBuildArgs a) {
     extern __shared__ __align__(16) unsigned char pb_tile_shared[];
+    __shared__ int s_cnt[128];
     PbTileHdr *h; unsigned long long *bar; double2 *sxy; double *sz; unsigned char *smeta;
     pb_tile_smem(pb_tile_shared, h, bar, sxy, sz, smeta);
     float4 *const s32 = reinterpret_cast<float4 *>(sxy);
@@ -621,13 +673,7 @@ __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_build32(PbTileBuildArgs a
 #pragma unroll
     for(int o = 16; o > 0; o >>= 1) { m = max(m, __shfl_xor_sync(0xffffffffu, m, o)); }
     if((threadIdx.x & 31) == 0 && m > 0) { atomicMax(a.max_count, m); }
-    if(a.reorder && active && count > 0 && count <= ncap) {
-        unsigned short *const rowbuf = reinterpret_cast<unsigned short *>(sxy) + (size_t) threadIdx.x * (size_t) (T4 * 4);
-        if(pb_tile_reorder_row(out, count, (int) (threadIdx.x & 15), rowbuf)) {
-            const unsigned long long *const rw = reinterpret_cast<const unsigned long long *>(rowbuf);
-            for(int q2 = 0; q2 * 4 < count; q2++) { out[(size_t) q2 * 32] = rw[q2]; }
-        }
-    }
+    pb_tile_finish_rows(a, tl, q >= 0, active, count, out, reinterpret_cast<unsigned char *>(sxy), s_cnt);
 }
 
 // ---- force ------------------------------------------------------------------------------------------------------------------
@@ -645,6 +691,7 @@ struct PbTileLjArgs {
     double *mz_next;
     const int *flags, *type, *cell_list, *numneigh;
     const unsigned long long *words;
+    const unsigned char *rowsrc;      // list row -> core thread of its tile (rows are sorted by length, pb_tile_finish_rows)
     double *force;
     const double *mass;
     double *vel;
@@ -673,10 +720,12 @@ __global__ void __launch_bounds__(PB_TILE_M, 4) pb_k_tile_lj(PbTileLjArgs a) {
     }
     const int tile_id = (a.sel != nullptr) ? __ldg(a.sel + blockIdx.x) : (int) blockIdx.x;
     const int row = __ldg(&a.tiles[tile_id].row_base) + threadIdx.x;
+    const int src = (int) __ldg(a.rowsrc + row);      // whose row this thread works on (read before the header is known: the array is padded)
     if(!pb_tile_stage(a.hdrs + tile_id, h, bar, a.mxy, a.mz, sxy, sz)) { return; }      // a tile of ghosts only
     // own data: in flight while the copies land
-    const int cq = pb_tile_core_q(h, threadIdx.x);
-    const int cs = (cq >= 0) ? pb_tile_core_csr(h, threadIdx.x, cq) : -1;
+    const int core_t = ((int) threadIdx.x < h->ncore) ? src : (int) threadIdx.x;
+    const int cq = pb_tile_core_q(h, core_t);
+    const int cs = (cq >= 0) ? pb_tile_core_csr(h, core_t, cq) : -1;
     const int i = (cs >= 0) ? __ldg(a.cell_list + cs) : a.nlocal;
     const bool live = i < a.nlocal;
     const bool fixed = live && (a.flags[i] & PB_FLAG_FIXED) != 0;
@@ -809,14 +858,16 @@ template<bool ELL>
 __global__ void __launch_bounds__(PB_TILE_M) pb_k_tile_export(int nlocal, int ncap, int T4, int cap_out, const PbTile *__restrict__ tiles,
                                                              const PbTileHdr *__restrict__ hdrs, const int *__restrict__ cell_list,
                                                              const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
-                                                             int *__restrict__ out) {
+                                                             const unsigned char *__restrict__ rowsrc, int *__restrict__ out) {
     __shared__ PbTileHdr hdr;
     PbTileHdr *h = &hdr;
     const PbTile tl = tiles[blockIdx.x];
     if(threadIdx.x < 64) { reinterpret_cast<int *>(h)[threadIdx.x] = reinterpret_cast<const int *>(hdrs + blockIdx.x)[threadIdx.x]; }
     __syncthreads();
-    const int cq = pb_tile_core_q(h, threadIdx.x);
-    const int cs = (cq >= 0) ? pb_tile_core_csr(h, threadIdx.x, cq) : -1;
+    if(!h->any_local) { return; }                       // (no rows were written for a tile of ghosts only)
+    const int core_t = ((int) threadIdx.x < h->ncore) ? (int) rowsrc[tl.row_base + threadIdx.x] : (int) threadIdx.x;
+    const int cq = pb_tile_core_q(h, core_t);
+    const int cs = (cq >= 0) ? pb_tile_core_csr(h, core_t, cq) : -1;
     const int i = (cs >= 0) ? cell_list[cs] : nlocal;
     if(i >= nlocal) { return; }
     const int row = tl.row_base + threadIdx.x;
@@ -975,6 +1026,7 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
     PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     PB_CHECK(cudaFuncSetAttribute(pb_k_tile_build32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     PB_TRY(pb_tile_mirror_all(ctx, ctx->tile_prefilter));                // the tiles are staged out of the mirror
+    PB_TRY(pb_tile_fit(ctx, &ctx->tile_rowsrc, &ctx->tile_rowsrc_cap, (size_t) ctx->tile_rows + PB_TILE_M));      // (padded: read before the tile's row count is known)
     for(int attempt = 0; attempt < 8; attempt++) {
         const int T4 = (ctx->ncap + 3) / 4;
         const size_t bytes = sizeof(unsigned long long) * (size_t) (ctx->tile_rows / 32) * (size_t) T4 * 32;
@@ -991,7 +1043,7 @@ int pb_build_tile_lists(pb_ctx *ctx, double cutoff) {
         ba.nlocal = n; ba.ncap = ctx->ncap; ba.T4 = T4; ba.g = g; ba.cutsq = cutsq; ba.tiles = ctx->tiles; ba.pos = ctx->pos; ba.flags = ctx->flags;
         ba.hdrs = ctx->tile_hdrs; ba.mxy = ctx->mxy[ctx->mirror_cur]; ba.mz = ctx->mz[ctx->mirror_cur]; ba.mmeta = ctx->mmeta;
         ba.particle_cell = ctx->particle_cell; ba.sub_start = ctx->sub_start; ba.cell_list = ctx->cell_list;
-        ba.words = ctx->twords; ba.numneigh = ctx->numneigh; ba.max_count = ctx->d_scalars; ba.tile_flag = ctx->tile_flag; ba.faces = faces;
+        ba.words = ctx->twords; ba.rowsrc = ctx->tile_rowsrc; ba.numneigh = ctx->numneigh; ba.max_count = ctx->d_scalars; ba.tile_flag = ctx->tile_flag; ba.faces = faces;
         // the reorder pass assembles the rows in the staging area (positions + meta bytes): possible while a row fits its share
         ba.reorder = ctx->tile_reorder && (size_t) PB_TILE_M * (size_t) T4 * 8 <= (size_t) PB_TILE_CAP * 25;
         ba.m32 = ctx->m32;
@@ -1071,7 +1123,7 @@ int pb_tile_lennard_jones(pb_ctx *ctx, double cutsq, double dt, int fuse, int pa
     a.mxy = ctx->mxy[ctx->mirror_cur]; a.mz = ctx->mz[ctx->mirror_cur];
     a.mxy_next = ctx->mxy[ctx->mirror_cur ^ 1]; a.mz_next = ctx->mz[ctx->mirror_cur ^ 1];
     a.flags = ctx->flags; a.type = ctx->type; a.cell_list = ctx->cell_list; a.numneigh = ctx->numneigh;
-    a.words = ctx->twords; a.force = ctx->force; a.mass = ctx->mass; a.vel = ctx->vel; a.pos_next = ctx->pos_alt;
+    a.words = ctx->twords; a.rowsrc = ctx->tile_rowsrc; a.force = ctx->force; a.mass = ctx->mass; a.vel = ctx->vel; a.pos_next = ctx->pos_alt;
     const bool acc = !ctx->force_is_zero;
     const bool uni = ctx->lj_uniform;
     if(ctx->lj_fma) {
@@ -1090,7 +1142,7 @@ int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
     int *const stage = stage_buf.as<int>();
     PB_CHECK(cudaMemsetAsync(stage, 0xff, sizeof(int) * (size_t) n * (size_t) capacity, ctx->stream));      // FIXED particles: no list, all -1
     PB_LAUNCH(pb_k_tile_export<false>, ctx->ntiles, PB_TILE_M, n, ctx->ncap, ctx->tile_T4, capacity, ctx->tiles, ctx->tile_hdrs, ctx->cell_list,
-              ctx->twords, ctx->numneigh, stage);
+              ctx->twords, ctx->numneigh, ctx->tile_rowsrc, stage);
     PB_CHECK(cudaMemcpyAsync(out, stage, sizeof(int) * (size_t) n * (size_t) capacity, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -1100,6 +1152,6 @@ int pb_tile_download_neighbors(pb_ctx *ctx, int *out, int capacity) {
 int pb_tile_export_ell(pb_ctx *ctx, int *neigh, int T) {
     if(ctx->tiles_n <= 0) { return 0; }
     PB_LAUNCH(pb_k_tile_export<true>, ctx->ntiles, PB_TILE_M, ctx->tiles_n, ctx->ncap, ctx->tile_T4, T, ctx->tiles, ctx->tile_hdrs, ctx->cell_list,
-              ctx->twords, ctx->numneigh, neigh);
+              ctx->twords, ctx->numneigh, ctx->tile_rowsrc, neigh);
     return 0;
 }

@@ -596,7 +596,9 @@ __global__ void __launch_bounds__(M, MB) k_force_tile_tma(int n, int cap, double
 // agree modulo 16 (8-byte z entries: 16 bank pairs; the 16-byte xy entries of a quarter-warp: modulo 8).  Every list is a set, its
 // order is free: lane l puts at position k an entry whose slot is (k + l) mod 16 whenever it still has one -- then the lanes of a
 // half-warp ask for 16 different residues in every iteration.  Entries whose residue class is exhausted fill the remaining holes.
-template<int M>
+// IDEAL: a timing experiment only -- the low four bits of every entry are REPLACED by the residue the position asks for, i.e. a list
+// without a single bank conflict (and with wrong partners): how fast would the force kernel be with a perfect schedule?
+template<int M, int IDEAL = 0>
 __global__ void __launch_bounds__(M) k_reorder_tile(int n, Geom g, const Tile *__restrict__ tiles, const int *__restrict__ cell_start,
                                                     const int *__restrict__ cell_list, const int *__restrict__ numneigh,
                                                     const unsigned long long *__restrict__ win, unsigned long long *__restrict__ wout) {
@@ -639,6 +641,7 @@ __global__ void __launch_bounds__(M) k_reorder_tile(int n, Geom g, const Tile *_
             out[hk] = sorted[head[r]++];
         }
     }
+    if(IDEAL) { for(int k = 0; k < nn; k++) { out[k] = (unsigned short) ((out[k] & ~15) | ((k + rot) & 15)); } }
     for(int q = 0; q * 4 < nn; q++) {
         unsigned long long w = 0ull;
         for(int u = 0; u < 4 && q * 4 + u < nn; u++) { w |= (unsigned long long) out[q * 4 + u] << (16 * u); }
@@ -965,6 +968,11 @@ int main(int argc, char **argv) {
                         report(NAME, t, false);                                                                                               \
                     }
                     VARIANT_TMA3("force_tma_fast_u8_reordered_minblocks4", 8, 4)
+                    {   // the ceiling of any better list order: no bank conflict at all (wrong partners, timing only)
+                        time_ms(1, [&] { k_reorder_tile<M, 1><<<ntiles, M>>>(n, g, d_tiles, d_cs, d_cl, d_nn2, d_w3, d_w4); });
+                        VARIANT_TMA3("force_tma_fast_u8_IDEAL_ORDER_timing_only", 8, 4)
+                        time_ms(1, [&] { k_reorder_tile<M><<<ntiles, M>>>(n, g, d_tiles, d_cs, d_cl, d_nn2, d_w3, d_w4); });
+                    }
                     VARIANT_TMA3("force_tma_fast_u8_reordered_minblocks5", 8, 5)
                     VARIANT_TMA3("force_tma_fast_u4_reordered_minblocks5", 4, 5)
                     VARIANT_TMA3("force_tma_fast_u4_reordered_minblocks6", 4, 6)
