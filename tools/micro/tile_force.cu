@@ -591,6 +591,76 @@ __global__ void __launch_bounds__(M, MB) k_force_tile_tma(int n, int cap, double
     force[2 * (size_t) n + i] = __dadd_rn(0.0, fz);
 }
 
+// ---- variant "ring": the list words of a warp's 32 rows arrive through a warp-private TMA ring in shared memory ---------------------
+// Word q of 32 consecutive rows is one 256-byte line of the sliced layout, words q and q + 1 are adjacent: the 16 entries per lane
+// of one iteration (U = 8: two words) are ONE 512-byte bulk copy per warp, issued by lane 0 S iterations ahead and awaited on a
+// warp-private mbarrier.  No register holds a word across the loop body, no global load is waited for inside it.
+template<int M, int FMA, int S>
+__global__ void __launch_bounds__(M, 4) k_force_tile_ring(int n, int cap, double cutsq, const Tile *__restrict__ tiles, const TileHdr2 *__restrict__ hdrs,
+                                                          const double2 *__restrict__ mxy, const double *__restrict__ mz, const int *__restrict__ cell_list,
+                                                          const unsigned long long *__restrict__ words, const int *__restrict__ numneigh,
+                                                          double *__restrict__ force) {
+    constexpr int U = 8;
+    extern __shared__ __align__(16) unsigned char smem[];
+    TileHdr2 *h; unsigned long long *bar; double2 *sxy; double *sz;
+    tile_smem2(smem, cap, h, bar, sxy, sz);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *const ring = reinterpret_cast<unsigned long long *>(smem + 272 + (size_t) cap * 24) + (size_t) warp * S * 64;
+    unsigned long long *const rbar = reinterpret_cast<unsigned long long *>(smem + 272 + (size_t) cap * 24 + (size_t) (M / 32) * S * 512) + warp * S;
+    const int row = tiles[blockIdx.x].row_base + threadIdx.x;
+    if(lane == 0) { for(int st = 0; st < S; st++) { mbar_init(rbar + st, 1); } }
+    tile_stage_tma(hdrs + blockIdx.x, h, bar, mxy, mz, sxy, sz);      // (its __syncthreads also publishes the ring barriers)
+    const int cs = tile_core_slot2(h, threadIdx.x);
+    const int i = (cs >= 0) ? __ldg(cell_list + cs) : n;
+    const int nn = (i < n) ? min(numneigh[i], NCAP) : 0;
+    int nw = nn;
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1) { nw = max(nw, __shfl_xor_sync(0xffffffffu, nw, o)); }
+    const int iters = (nw + U - 1) / U;
+    const unsigned long long *const wline = words + (size_t) (row >> 5) * (NCAP / 4) * 32;      // the warp's 32 rows: word q at wline + q * 32
+    if(lane == 0) {
+        for(int st = 0; st < S && st < iters; st++) {
+            mbar_expect_tx(rbar + st, 512);
+            bulk_g2s(ring + st * 64, wline + (size_t) st * 64, 512, rbar + st);
+        }
+    }
+    mbar_wait(bar, 0);
+    double4 pi = make_double4(0.0, 0.0, 0.0, 0.0);
+    if(i < n) {
+        const int s_self = tile_self_slot2(h, threadIdx.x, cs);
+        const double2 pxy = sxy[s_self];
+        pi = make_double4(pxy.x, pxy.y, sz[s_self], 0.0);
+    }
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    for(int it = 0; it < iters; it++) {
+        const int st = it % S, k = it * U;
+        mbar_wait(rbar + st, (it / S) & 1);
+        unsigned long long w[2];
+        w[0] = ring[st * 64 + lane];
+        w[1] = ring[st * 64 + 32 + lane];
+        __syncwarp();
+        if(lane == 0 && it + S < iters) {
+            mbar_expect_tx(rbar + st, 512);
+            bulk_g2s(ring + st * 64, wline + (size_t) (it + S) * 64, 512, rbar + st);
+        }
+        double xj[U], yj[U], zj[U];
+#pragma unroll
+        for(int u = 0; u < U; u++) {
+            const int s = (k + u < nn) ? (int) ((w[u >> 2] >> (16 * (u & 3))) & 0xffffull) : 0;
+            const double2 xy = sxy[s];
+            xj[u] = xy.x; yj[u] = xy.y;
+            zj[u] = sz[s];
+        }
+#pragma unroll
+        for(int u = 0; u < U; u++) { lj_pair<FMA>(pi.x, pi.y, pi.z, xj[u], yj[u], zj[u], k + u < nn, cutsq, fx, fy, fz); }
+    }
+    if(i < n) {
+        force[i] = __dadd_rn(0.0, fx);
+        force[n + i] = __dadd_rn(0.0, fy);
+        force[2 * (size_t) n + i] = __dadd_rn(0.0, fz);
+    }
+}
+
 // ---- conflict-aware order of a list ---------------------------------------------------------------------------------------------
 // In iteration k the 16 lanes of a half-warp read 16 staged particles; two DIFFERENT slots collide in shared memory when they
 // agree modulo 16 (8-byte z entries: 16 bank pairs; the 16-byte xy entries of a quarter-warp: modulo 8).  Every list is a set, its
@@ -968,6 +1038,22 @@ int main(int argc, char **argv) {
                         report(NAME, t, false);                                                                                               \
                     }
                     VARIANT_TMA3("force_tma_fast_u8_reordered_minblocks4", 8, 4)
+#define VARIANT_RING(NAME, S_)                                                                                                                \
+                    {                                                                                                                         \
+                        const size_t sr = s2 + (size_t) (M / 32) * S_ * 512 + (size_t) (M / 32) * S_ * 8;                                     \
+                        CK(cudaFuncSetAttribute(k_force_tile_ring<M, 4, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sr));         \
+                        int occ = 0;                                                                                                          \
+                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_force_tile_ring<M, 4, S_>, M, sr));                          \
+                        cudaFuncAttributes fa;                                                                                                \
+                        CK(cudaFuncGetAttributes(&fa, k_force_tile_ring<M, 4, S_>));                                                          \
+                        CK(cudaMemset(d_f1, 0, 24 * (size_t) n));                                                                             \
+                        t = time_ms(10, [&] { k_force_tile_ring<M, 4, S_><<<ntiles, M, sr>>>(n, cap, cutsq_f, d_tiles, d_h, d_mxy, d_mz, d_cl, d_w4, d_nn2, d_f1); }); \
+                        printf("{\"occupancy_blocks\": %d, \"registers\": %d, \"local_bytes\": %d, \"smem\": %d}\n", occ, fa.numRegs, (int) fa.localSizeBytes, (int) sr);  \
+                        report(NAME, t, false);                                                                                               \
+                    }
+                    VARIANT_RING("force_ring_s2", 2)
+                    VARIANT_RING("force_ring_s3", 3)
+                    VARIANT_RING("force_ring_s4", 4)
                     {   // the ceiling of any better list order: no bank conflict at all (wrong partners, timing only)
                         time_ms(1, [&] { k_reorder_tile<M, 1><<<ntiles, M>>>(n, g, d_tiles, d_cs, d_cl, d_nn2, d_w3, d_w4); });
                         VARIANT_TMA3("force_tma_fast_u8_IDEAL_ORDER_timing_only", 8, 4)
