@@ -88,3 +88,44 @@ def test_lj_pair_arithmetic_equals_the_reference_module(host, uniform):
         prog.lennard_jones(r.neighbor_capacity, n, nn.astype(np.int32), np.ascontiguousarray(nl, np.int32), r.ints("flags", tot),
                            r.real("position", tot), r.ints("type", tot), f_ref, sig6, eps)
         assert np.array_equal(force, f_ref)                                   # the reference's generated lennard_jones itself
+
+
+def test_fp32_prefilter_band_of_the_tile_build_never_misclassifies():
+    """The tile build (csrc/tile_lists.cu pb_k_tile_build32) tests list candidates in fp32 first and lets fp32 decide only outside a
+    band of +- 2 err around the squared cutoff, err = 2 sqrt(3) rc (2^-23 A + 2^-24 rc) + 8 * 2^-24 rc^2 + 3 (2^-23 A)^2 with A = the
+    particle's largest coordinate plus the cutoff.  Host restatement of that arithmetic (positions rounded to fp32, differences, one
+    product and two fused multiply-adds in fp32) on ten million random pairs placed close to the cutoff, at coordinate magnitudes
+    from 10 to 10^5: the fp32 value is within err of the reference's fp64 expression, hence whatever fp32 decides agrees with
+    rsq < cutsq in fp64.  (The GPU side -- identical lists with and without the pre-filter on adversarial pairs -- is
+    tests/test_gpu_tiles.py.)"""
+    rc = 2.8
+    cutsq = rc * rc
+    u = 2.0 ** -24
+    rng = np.random.default_rng(11)
+    for scale in (10.0, 170.0, 4000.0, 1.0e5):
+        n = 2_500_000
+        xi = rng.uniform(-scale, scale, (n, 3))
+        d = rng.standard_normal((n, 3))
+        d /= np.linalg.norm(d, axis=1)[:, None]
+        r = rc * (1.0 + rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-9.0, -1.0, n))        # |r - rc| / rc from 1e-9 to 0.1
+        xj = xi + d * r[:, None]
+        # the reference's fp64 expression (md_math.h pb_pair_rsq): (dx*dx + dy*dy) + dz*dz
+        e = xi - xj
+        rsq64 = (e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1]) + e[:, 2] * e[:, 2]
+        # the kernel's fp32 arithmetic: fmaf(dz, dz, fmaf(dy, dy, dx * dx)) on rounded positions
+        f = (xi.astype(np.float32) - xj.astype(np.float32)).astype(np.float32)
+        p = (f[:, 0] * f[:, 0]).astype(np.float32)
+        q = (f[:, 1].astype(np.float64) * f[:, 1].astype(np.float64) + p.astype(np.float64)).astype(np.float32)
+        rsq32 = (f[:, 2].astype(np.float64) * f[:, 2].astype(np.float64) + q.astype(np.float64)).astype(np.float32)
+        A = np.abs(xi).max(axis=1) + rc
+        err = 2.0 * np.sqrt(3.0) * rc * (2.0 * u * A + u * rc) + 8.0 * u * cutsq + 3.0 * (2.0 * u * A) ** 2
+        near = np.abs(r - rc) < 0.02 * rc                                       # the bound is stated for pairs around the cutoff
+        assert (np.abs(rsq32.astype(np.float64) - rsq64)[near] <= err[near]).all(), scale
+        cut_lo = np.nextafter((cutsq - 2.0 * err).astype(np.float32), np.float32(-np.inf))      # rounded outwards, as the kernel does
+        cut_hi = np.nextafter((cutsq + 2.0 * err).astype(np.float32), np.float32(np.inf))
+        decided_in, decided_out = rsq32 <= cut_lo, rsq32 >= cut_hi
+        assert (rsq64[decided_in] < cutsq).all() and (rsq64[decided_out] >= cutsq).all(), scale
+        assert decided_in.sum() > 1000 and decided_out.sum() > 1000             # (both outcomes occur at every magnitude)
+        if scale <= 170.0:                                                      # at the benchmark's box size fp32 leaves only a thin
+            far = np.abs(r - rc) > 1e-4 * rc                                    # shell to fp64: |r - rc| < 1e-4 rc, ~0.02 entries per atom
+            assert (decided_in | decided_out)[far].all()
