@@ -19,6 +19,7 @@ Variants (name -> substitutions applied to examples/md.py in a scratch copy):
   dem_vtk_t1 dem_t1 for 60 steps with the example's psim.vtk_output(..., frequency) kept, writing every 30 iterations
   dem_cn_t1 dem_t1 with build_cell_lists(..., store_neighbors_per_cell=True)
   dem_rn3_t1 dem_t1 with psim.reneighbor_every(3): exchange / borders / cell lists every third iteration, synchronize in between
+  dem_more_t1 dem_t1 with three further contact properties kept by the contact model (contact tables beyond examples/dem.py's three)
   dem_stock_t1 examples/dem.py as shipped (0.8 x 0.015 x 0.2 box, VTK every 100 iterations), cut to 103 iterations
   dem_bench examples/dem.py on the 0.8 x 0.8 x 0.2 box (998400 spheres), bounded by the harness
   md_custom_t1  md_t1 with other kernel bodies (softened LJ using sqrt / select / symbols, integrators with drag) -> generic kernels
@@ -215,6 +216,28 @@ def dem_variant(domain, steps, pcap=None, per_cell=False, vtk_every=None, verlet
     return patch
 
 
+def dem_more_variant(domain, steps):
+    """examples/dem.py with three FURTHER contact properties (a second vector, a second real with default -1, a second integer with
+    default 3) and three statements on them at the end of its contact model -- the same text tests/scripts/dem_script.py composes
+    with more_contact_props=True: the reference's own generated code for contact tables beyond dem.py's three."""
+    base = dem_variant(domain, steps)
+
+    def patch(text):
+        text = base(text)
+        text = _sub(text, r"^psim\.add_contact_property\('impact_velocity_magnitude', pairs\.real\(\), 0\.0\)",
+                    "psim.add_contact_property('impact_velocity_magnitude', pairs.real(), 0.0)\n"
+                    "psim.add_contact_property('tsd_seen', pairs.vector(), [0.0, 0.0, 0.0])\n"
+                    "psim.add_contact_property('contact_age', pairs.real(), -1.0)\n"
+                    "psim.add_contact_property('hits', pairs.int32(), 3)")
+        text = _sub(text, r"^    apply\(torque, cross\(contact_point\(i, j\) - position, partial_force\)\)",
+                    "    apply(torque, cross(contact_point(i, j) - position, partial_force))\n"
+                    "    tsd_seen[i, j] = tangential_spring_displacement[i, j]\n"
+                    "    contact_age[i, j] = contact_age[i, j] + 1.0\n"
+                    "    hits[i, j] = hits[i, j] + 2")
+        return text
+    return patch
+
+
 # The reference's own CUDA target (SECONDARY baseline of BASELINE.json's north_star): `md.py gpu` -> md.cu, compiled with nvcc for
 # sm_100a together with the reference's runtime/devices/cuda.cu where they lie.  Stock semantics: nvcc's default FMA contraction
 # (the reference's Makefile does not disable it) and its -DENABLE_CUDA_AWARE_MPI; the image has no MPI, with one rank every
@@ -287,6 +310,8 @@ VARIANTS = {
     "dem_stock_t1": ("examples/dem.py", dem_variant((0.8, 0.015, 0.2), 102, vtk_every=100), [], False),
     # dem_t1 generated by a CORRECTED copy of the reference generator: see corrected_generator()
     "dem_fix_t1": ("examples/dem.py", dem_variant((0.1, 0.015, 0.04), 700), ["generator:contact_history_fix"], False),
+    # dem_t1 with three further contact properties kept by the contact model (contact tables beyond dem.py's three)
+    "dem_more_t1": ("examples/dem.py", dem_more_variant((0.1, 0.015, 0.04), 400), [], False),
 }
 
 

@@ -163,6 +163,10 @@ def _main(argv):
                         d[k] = prog.array(k, np.int32, n * 20).reshape(n, 20)
                     elif k == "is_sticking":
                         d[k] = prog.contact_prop(k, n * 20, 1, np.int32).reshape(n, 20)
+                    elif k.startswith("cp:"):          # any contact property: cp:<name>:<width>:<int|real>
+                        _, cname, width, kind = k.split(":")
+                        a = prog.contact_prop(cname, n * 20, int(width), np.int32 if kind == "int" else np.float64)
+                        d[cname] = a.reshape(n, 20, int(width)) if int(width) > 1 else a.reshape(n, 20)
                     else:
                         d[k] = prog.array(k, np.int32, n)
             st["ts"] += 1

@@ -64,3 +64,14 @@ for ts in FIX_STEPS:
 pathf = os.path.join(HERE, "dem_fix_t1.npz")
 np.savez_compressed(pathf, **outf)
 print("dem_fix_t1:", os.path.getsize(pathf) // 1024, "KiB")
+
+
+# variant dem_more_t1: examples/dem.py with three FURTHER contact properties (second vector / real / integer) kept by its contact
+# model -- what the reference's generated code holds in them at the end of iteration 300
+MORE = ["uid", "position", "num_contacts", "contact_lists", "is_sticking", "cp:tangential_spring_displacement:3:real",
+        "cp:tsd_seen:3:real", "cp:contact_age:1:real", "cp:hits:1:int"]
+zm = ref_worker.dump_dem_end("dem_more_t1", "/tmp/dem_more_t1_golden_raw.npz", 300, MORE)
+pathm = os.path.join(HERE, "dem_more_t1.npz")
+np.savez_compressed(pathm, **{k: zm[k] for k in zm.files})
+live = np.arange(20)[None, :] < zm["num_contacts"][:, None]
+print("dem_more_t1:", os.path.getsize(pathm) // 1024, "KiB,", int(live.sum()), "live contacts, oldest", float(zm["contact_age"][live].max()))

@@ -76,3 +76,19 @@ def test_inverse_inertia_of_spheres_is_bit_exact(host):
         out = np.zeros(9)
         lib.host_dem_sphere_inv_inertia(ctypes.c_double(m[i]), ctypes.c_double(r[i]), dp(out))
         assert np.array_equal(out, ref[i])
+
+
+def test_reference_golden_of_further_contact_properties_is_what_the_statements_say():
+    """tests/golden/dem_more_t1.npz (the reference's generated C++ for examples/dem.py plus three further contact properties,
+    tests/golden/make_golden_dem.py): in every live contact the displacement copy equals the displacement bit for bit, the age
+    counts iterations from the default -1, hits = 3 + 2 (age + 1); the particles are those of the plain run (dem_t1): further
+    contact state changes no force.  This is the behaviour the extra lanes of the contact rows reproduce (tests/test_gpu_props.py)."""
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z, t1 = np.load(os.path.join(gold, "dem_more_t1.npz")), np.load(os.path.join(gold, "dem_t1.npz"))
+    live = np.arange(20)[None, :] < z["num_contacts"][:, None]
+    assert live.sum() > 100
+    assert np.array_equal(z["tsd_seen"][live], z["tangential_spring_displacement"][live])
+    age, hits = z["contact_age"][live], z["hits"][live]
+    assert age.min() >= 0.0 and age.max() >= 20.0 and np.array_equal(age, np.round(age))
+    assert np.array_equal(hits, (3 + 2 * (age + 1)).astype(np.int32))
+    assert np.array_equal(z["position"], t1["end_300_position"]) and np.array_equal(z["contact_lists"][live], t1["end_300_contact_lists"][live])

@@ -143,6 +143,38 @@ def test_contact_model_with_further_contact_properties_keeps_them_with_the_conta
     assert np.array_equal(ctx.dem_download_contact_extras(n), back)
 
 
+def test_further_contact_properties_match_the_reference_generated_code(capsys):
+    """The same script through the REFERENCE: oracle/build_ref.py variant dem_more_t1 is examples/dem.py with the three further
+    contact properties and the three statements, generated and compiled by the reference itself; tests/golden/dem_more_t1.npz holds
+    what its contact tables contain at the end of iteration 300.  Ours: same particles (positions to 1e-12), the same contacts
+    (partner uids per particle), and in every one of them the same age and hit count exactly and the displacement copy to 1e-12."""
+    import dem_script
+    from tests import dem_common as dc
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dem_more_t1.npz"))
+    ctx = dem_script.build("gpu", dc.DOMAIN, 300, more_contact_props=True).generate()
+    capsys.readouterr()
+    n = ctx.counts()[0]
+    assert n == int(z["nlocal"][0]) == 422
+    o, r = np.argsort(ctx.ints("uid")), np.argsort(z["uid"])
+    pref = z["position"][r]
+    assert np.abs(ctx.real("position")[o] - pref).max() <= 1e-12 * np.abs(pref[:n - 2]).max()
+    c, cx = ctx.dem_download_contacts(n), ctx.dem_download_contact_extras(n)
+    assert np.array_equal(c["num_contacts"][o], z["num_contacts"][r]) and z["num_contacts"].sum() > 100
+    scale = np.abs(z["tsd_seen"]).max()
+    checked = 0
+    for a, b in zip(o, r):
+        m = int(z["num_contacts"][b])
+        ours = {int(c["contact_lists"][a, k]): cx[a, k] for k in range(m)}
+        ref = {int(z["contact_lists"][b, k]): (z["tsd_seen"][b, k], z["contact_age"][b, k], z["hits"][b, k]) for k in range(m)}
+        assert set(ours) == set(ref)
+        for partner, (seen, age, hits) in ref.items():
+            lanes = ours[partner]
+            assert lanes[3] == age and lanes[4] == float(hits), (partner, lanes, age, hits)
+            assert np.abs(lanes[:3] - seen).max() <= 1e-12 * scale
+            checked += 1
+    assert checked == int(z["num_contacts"].sum())
+
+
 def test_dem_script_with_a_generated_per_particle_kernel_reproduces_the_built_in_run(capsys):
     """A DEM procedure list that is not exactly gravity / model / euler runs module by module with the user bodies generated: here
     gravity, euler and the set-up function update_mass_and_inertia are sent through the generic path (matrix / quaternion algebra
