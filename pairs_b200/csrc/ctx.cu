@@ -59,7 +59,7 @@ extern "C" int pb_create(pb_ctx **out, int device) {
     PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_io[0], cudaEventDisableTiming));
     PB_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->ev_io[1], cudaEventDisableTiming));
     PB_CREATE_CHECK(cudaMalloc(&ctx->d_scalars, sizeof(int) * PB_NSCALARS));
-    PB_CREATE_CHECK(cudaMemset(ctx->d_scalars, 0, sizeof(int) * PB_NSCALARS));
+    PB_CREATE_CHECK(cudaMemsetAsync(ctx->d_scalars, 0, sizeof(int) * PB_NSCALARS, ctx->stream));      // (on the stream the kernels use: the legacy stream does not order against it)
     PB_CREATE_CHECK(cudaMallocHost(&ctx->h_scalars, sizeof(int) * PB_NSCALARS));
 #undef PB_CREATE_CHECK
     *out = ctx;

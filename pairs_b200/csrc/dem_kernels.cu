@@ -93,7 +93,7 @@ extern "C" int pb_dem_enable_ex(pb_ctx *ctx, int contact_capacity, int extra_lan
     if(ctx->recv_buf != nullptr) { PB_CHECK(cudaFree(ctx->recv_buf)); ctx->recv_buf = nullptr; ctx->recv_cap = 0; }
     ctx->cells_set = false;       // DEM bins without z slabs: cell arrays are re-sized by the next pb_setup_cells
     PB_CHECK(cudaMalloc(&ctx->d_dem_flag, sizeof(int) * 4));
-    PB_CHECK(cudaMemset(ctx->d_dem_flag, 0, sizeof(int) * 4));
+    PB_CHECK(cudaMemsetAsync(ctx->d_dem_flag, 0, sizeof(int) * 4, ctx->stream));
     if(ctx->pcap > 0) { PB_TRY(pb_dem_grow(ctx, (size_t) ctx->pcap, (size_t) ctx->pcap, (size_t) ctx->nlocal + ctx->nghost)); }
     return 0;
 }
@@ -123,8 +123,9 @@ extern "C" int pb_dem_set_params(pb_ctx *ctx, double dt, double pi, double kappa
         PB_CHECK(cudaMalloc(&ctx->d_fric_static, sizeof(double) * 64));
         PB_CHECK(cudaMalloc(&ctx->d_fric_dynamic, sizeof(double) * 64));
     }
-    PB_CHECK(cudaMemcpy(ctx->d_fric_static, friction_static, sizeof(double) * ntypes * ntypes, cudaMemcpyHostToDevice));
-    PB_CHECK(cudaMemcpy(ctx->d_fric_dynamic, friction_dynamic, sizeof(double) * ntypes * ntypes, cudaMemcpyHostToDevice));
+    PB_CHECK(cudaMemcpyAsync(ctx->d_fric_static, friction_static, sizeof(double) * ntypes * ntypes, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(ctx->d_fric_dynamic, friction_dynamic, sizeof(double) * ntypes * ntypes, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaStreamSynchronize(ctx->stream));      // (stream-ordered with the kernels that read them; the caller's arrays are free again)
     return 0;
 }
 
@@ -314,11 +315,14 @@ extern "C" int pb_dem_upload_contacts(pb_ctx *ctx, int n, const int *num, const 
     PB_CHECK(b_ivm.alloc(sizeof(double) * (size_t) n * C));
     int *d_num = b_num.as<int>(), *d_uid = b_uid.as<int>(), *d_st = b_st.as<int>();
     double *d_tsd = b_tsd.as<double>(), *d_ivm = b_ivm.as<double>();
-    PB_CHECK(cudaMemcpy(d_num, num, sizeof(int) * n, cudaMemcpyHostToDevice));
-    PB_CHECK(cudaMemcpy(d_uid, uid, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice));
-    PB_CHECK(cudaMemcpy(d_st, sticking, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice));
-    PB_CHECK(cudaMemcpy(d_tsd, tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyHostToDevice));
-    PB_CHECK(cudaMemcpy(d_ivm, ivm, sizeof(double) * (size_t) n * C, cudaMemcpyHostToDevice));
+    // on the context's stream: a synchronous cudaMemcpy from pageable memory may return before its DMA has landed, and the legacy
+    // stream it runs on does not order against this (non-blocking) stream -- the kernel below was seen reading the last array
+    // before it had arrived (one contact of 115 with a zero impact velocity, once in many runs)
+    PB_CHECK(cudaMemcpyAsync(d_num, num, sizeof(int) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(d_uid, uid, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(d_st, sticking, sizeof(int) * (size_t) n * C, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(d_tsd, tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyHostToDevice, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(d_ivm, ivm, sizeof(double) * (size_t) n * C, cudaMemcpyHostToDevice, ctx->stream));
     PB_LAUNCH(pb_k_contacts_in, pb_blocks(n, 128), 128, n, ctx->pcap, C, d_num, d_uid, d_st, d_tsd, d_ivm, ctx->num_contacts,
               ctx->contact_uid, ctx->contact_used, ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm);
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -370,13 +374,13 @@ extern "C" int pb_dem_download_contacts(pb_ctx *ctx, int n, int *num, int *uid, 
     double *d_tsd = b_tsd.as<double>(), *d_ivm = b_ivm.as<double>();
     PB_LAUNCH(pb_k_contacts_out, pb_blocks(n, 128), 128, n, ctx->pcap, C, ctx->num_contacts, ctx->contact_uid, ctx->contact_used,
               ctx->contact_stick, ctx->contact_tsd, ctx->contact_ivm, d_num, d_uid, d_us, d_st, d_tsd, d_ivm);
+    PB_CHECK(cudaMemcpyAsync(num, d_num, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(uid, d_uid, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(used, d_us, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(sticking, d_st, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(tsd, d_tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CHECK(cudaMemcpyAsync(ivm, d_ivm, sizeof(double) * (size_t) n * C, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CHECK(cudaStreamSynchronize(ctx->stream));
-    PB_CHECK(cudaMemcpy(num, d_num, sizeof(int) * n, cudaMemcpyDeviceToHost));
-    PB_CHECK(cudaMemcpy(uid, d_uid, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
-    PB_CHECK(cudaMemcpy(used, d_us, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
-    PB_CHECK(cudaMemcpy(sticking, d_st, sizeof(int) * (size_t) n * C, cudaMemcpyDeviceToHost));
-    PB_CHECK(cudaMemcpy(tsd, d_tsd, sizeof(double) * (size_t) n * C * 3, cudaMemcpyDeviceToHost));
-    PB_CHECK(cudaMemcpy(ivm, d_ivm, sizeof(double) * (size_t) n * C, cudaMemcpyDeviceToHost));
     return 0;
 }
 
